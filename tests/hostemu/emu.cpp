@@ -1,0 +1,275 @@
+// tests/hostemu/emu.cpp — HOST LOGIC HARNESS (test infrastructure, never shipped, never loaded by the
+// product).  Compiles the RFW_HD bodies of rfw_rs_b200/csrc/{bvh_build.h,traverse.h} with g++ and runs
+// them serially, so the Karras tree, the SAH-forest collapse, the node quantisation and the two-level
+// traversal logic can be checked against the oracle in the CPU-only test tier.  The kernels that wrap
+// these bodies (builder.cu, trace.cu) are checked on the B200 by the -m gpu tests.
+#include <algorithm>
+#include <cfloat>
+#include <cstdio>
+#include <map>
+#include <vector>
+
+#include "../../include/rfwb200.h"
+#include "../../rfw_rs_b200/csrc/bvh_build.h"
+#include "../../rfw_rs_b200/csrc/traverse.h"
+
+using namespace rfw;
+
+struct EmuBvh {
+    std::vector<float4> nodes;
+    std::vector<uint32_t> leaf_prims;
+    float sah = 0;
+    int levels = 0;
+};
+
+static void emu_build(const std::vector<float4>& lo, const std::vector<float4>& hi, const BuildParams& P, EmuBvh& out) {
+    const int n = (int)lo.size();
+    float3 cmin = f3(FLT_MAX, FLT_MAX, FLT_MAX), cmax = f3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+    for (int i = 0; i < n; i++) {
+        float3 c = (xyz(lo[i]) + xyz(hi[i])) * 0.5f;
+        cmin = min3(cmin, c); cmax = max3(cmax, c);
+    }
+    float3 ext = cmax - cmin;
+    float3 cscale = f3(ext.x > 0 ? 2097152.0f / ext.x : 0.f, ext.y > 0 ? 2097152.0f / ext.y : 0.f, ext.z > 0 ? 2097152.0f / ext.z : 0.f);
+    std::vector<uint64_t> keys(n);
+    std::vector<uint32_t> vals(n);
+    for (int i = 0; i < n; i++) morton_body(i, lo.data(), hi.data(), cmin, cscale, keys.data(), vals.data());
+    std::vector<int> perm(n);
+    for (int i = 0; i < n; i++) perm[i] = i;
+    std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return keys[a] < keys[b]; });
+    std::vector<uint64_t> skeys(n);
+    std::vector<uint32_t> order(n);
+    for (int i = 0; i < n; i++) { skeys[i] = keys[perm[i]]; order[i] = vals[perm[i]]; }
+
+    const int nn = 2 * n - 1;
+    std::vector<int> parent(nn, -1), flags(std::max(1, n - 1), 0);
+    std::vector<int2> children(std::max(1, n - 1)), range(std::max(1, n - 1));
+    std::vector<float4> nlo(nn), nhi(nn);
+    std::vector<float> cost((size_t)nn * 8);
+    std::vector<uint32_t> decision(std::max(1, n - 1));
+    BuildArrays A;
+    A.n = n; A.prim_lo = lo.data(); A.prim_hi = hi.data(); A.keys = skeys.data(); A.order = order.data();
+    A.parent = parent.data(); A.children = children.data(); A.range = range.data(); A.node_lo = nlo.data(); A.node_hi = nhi.data();
+    A.cost = cost.data(); A.decision = decision.data(); A.flags = flags.data();
+    for (int i = 0; i < n - 1; i++) karras_body(i, n, skeys.data(), parent.data(), children.data(), range.data());
+    for (int k = 0; k < n; k++) fit_cost_body(k, A, P);
+
+    out.nodes.assign((size_t)std::max(1, n) * 5, f4(0, 0, 0, 0));
+    out.leaf_prims.assign(n, 0);
+    uint32_t node_counter = 1, prim_counter = 0;
+    CollapseOut O;
+    O.nodes = out.nodes.data(); O.leaf_prims = out.leaf_prims.data(); O.node_counter = &node_counter; O.prim_counter = &prim_counter;
+    std::vector<int2> q0(std::max(1, n)), q1(std::max(1, n));
+    uint32_t c0 = 1, c1 = 0;
+    q0[0] = make_int2(n == 1 ? 0 : 0, 0);  // root: binary node 0 (n == 1: the only leaf has id n-1 = 0 as well)
+    out.levels = 0;
+    while (c0 > 0) {
+        c1 = 0;
+        for (uint32_t t = 0; t < c0; t++) collapse_body(q0[t], A, O, q1.data(), &c1);
+        std::swap(q0, q1);
+        c0 = c1;
+        out.levels++;
+    }
+    out.nodes.resize((size_t)node_counter * 5);
+    out.sah = (n > 1 && cost[7] > 0) ? cost[0] / cost[7] : 0.f;
+    if ((int)prim_counter != n) fprintf(stderr, "emu: prim_counter %u != n %d\n", prim_counter, n);
+}
+
+struct EmuMesh {
+    std::vector<RfwRTTriangle> tris;
+    EmuBvh bvh;
+    std::vector<float4> ttris;
+    float3 lo, hi;
+};
+struct EmuScene {
+    std::map<uint32_t, EmuMesh> meshes;
+    std::map<uint32_t, std::vector<float>> inst;
+    std::vector<InstanceRec> recs;
+    EmuBvh tlas;
+    SceneView sv;
+};
+
+static bool invert_affine(const float* m, float4& r0, float4& r1, float4& r2) {
+    // column-major 4x4 -> rows of the inverse 3x4 (double)
+    double a[16], inv[16];
+    for (int i = 0; i < 16; i++) a[i] = m[i];
+    inv[0] = a[5] * a[10] * a[15] - a[5] * a[11] * a[14] - a[9] * a[6] * a[15] + a[9] * a[7] * a[14] + a[13] * a[6] * a[11] - a[13] * a[7] * a[10];
+    inv[4] = -a[4] * a[10] * a[15] + a[4] * a[11] * a[14] + a[8] * a[6] * a[15] - a[8] * a[7] * a[14] - a[12] * a[6] * a[11] + a[12] * a[7] * a[10];
+    inv[8] = a[4] * a[9] * a[15] - a[4] * a[11] * a[13] - a[8] * a[5] * a[15] + a[8] * a[7] * a[13] + a[12] * a[5] * a[11] - a[12] * a[7] * a[9];
+    inv[12] = -a[4] * a[9] * a[14] + a[4] * a[10] * a[13] + a[8] * a[5] * a[14] - a[8] * a[6] * a[13] - a[12] * a[5] * a[10] + a[12] * a[6] * a[9];
+    inv[1] = -a[1] * a[10] * a[15] + a[1] * a[11] * a[14] + a[9] * a[2] * a[15] - a[9] * a[3] * a[14] - a[13] * a[2] * a[11] + a[13] * a[3] * a[10];
+    inv[5] = a[0] * a[10] * a[15] - a[0] * a[11] * a[14] - a[8] * a[2] * a[15] + a[8] * a[3] * a[14] + a[12] * a[2] * a[11] - a[12] * a[3] * a[10];
+    inv[9] = -a[0] * a[9] * a[15] + a[0] * a[11] * a[13] + a[8] * a[1] * a[15] - a[8] * a[3] * a[13] - a[12] * a[1] * a[11] + a[12] * a[3] * a[9];
+    inv[13] = a[0] * a[9] * a[14] - a[0] * a[10] * a[13] - a[8] * a[1] * a[14] + a[8] * a[2] * a[13] + a[12] * a[1] * a[10] - a[12] * a[2] * a[9];
+    inv[2] = a[1] * a[6] * a[15] - a[1] * a[7] * a[14] - a[5] * a[2] * a[15] + a[5] * a[3] * a[14] + a[13] * a[2] * a[7] - a[13] * a[3] * a[6];
+    inv[6] = -a[0] * a[6] * a[15] + a[0] * a[7] * a[14] + a[4] * a[2] * a[15] - a[4] * a[3] * a[14] - a[12] * a[2] * a[7] + a[12] * a[3] * a[6];
+    inv[10] = a[0] * a[5] * a[15] - a[0] * a[7] * a[13] - a[4] * a[1] * a[15] + a[4] * a[3] * a[13] + a[12] * a[1] * a[7] - a[12] * a[3] * a[5];
+    inv[14] = -a[0] * a[5] * a[14] + a[0] * a[6] * a[13] + a[4] * a[1] * a[14] - a[4] * a[2] * a[13] - a[12] * a[1] * a[6] + a[12] * a[2] * a[5];
+    double det = a[0] * inv[0] + a[1] * inv[4] + a[2] * inv[8] + a[3] * inv[12];
+    if (det == 0.0 || !std::isfinite(det)) return false;
+    double id = 1.0 / det;
+    r0 = f4((float)(inv[0] * id), (float)(inv[4] * id), (float)(inv[8] * id), (float)(inv[12] * id));
+    r1 = f4((float)(inv[1] * id), (float)(inv[5] * id), (float)(inv[9] * id), (float)(inv[13] * id));
+    r2 = f4((float)(inv[2] * id), (float)(inv[6] * id), (float)(inv[10] * id), (float)(inv[14] * id));
+    return true;
+}
+
+extern "C" {
+void* emu_create() { return new EmuScene(); }
+void emu_destroy(void* s) { delete (EmuScene*)s; }
+void emu_set_mesh(void* s, uint32_t id, const RfwRTTriangle* t, uint32_t n) { ((EmuScene*)s)->meshes[id].tris.assign(t, t + n); }
+void emu_set_instances(void* s, uint32_t mesh, const float* m, uint32_t n) { ((EmuScene*)s)->inst[mesh].assign(m, m + (size_t)n * 16); }
+
+void emu_build(void* s, float c_node, float c_prim, int pmax, uint64_t* stats) {
+    EmuScene& sc = *(EmuScene*)s;
+    BuildParams P{c_node, c_prim, pmax};
+    uint64_t tot_nodes = 0;
+    for (auto& kv : sc.meshes) {
+        EmuMesh& m = kv.second;
+        const int n = (int)m.tris.size();
+        std::vector<float4> lo(n), hi(n);
+        m.lo = f3(FLT_MAX, FLT_MAX, FLT_MAX); m.hi = f3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+        for (int i = 0; i < n; i++) {
+            float3 a = f3(m.tris[i].vertex0[0], m.tris[i].vertex0[1], m.tris[i].vertex0[2]);
+            float3 b = f3(m.tris[i].vertex1[0], m.tris[i].vertex1[1], m.tris[i].vertex1[2]);
+            float3 c = f3(m.tris[i].vertex2[0], m.tris[i].vertex2[1], m.tris[i].vertex2[2]);
+            float3 l = min3(a, min3(b, c)), h = max3(a, max3(b, c));
+            lo[i] = f4(l.x, l.y, l.z, 0); hi[i] = f4(h.x, h.y, h.z, 0);
+            m.lo = min3(m.lo, l); m.hi = max3(m.hi, h);
+        }
+        if (n == 0) continue;
+        emu_build(lo, hi, P, m.bvh);
+        m.ttris.resize((size_t)n * 3);
+        for (int k = 0; k < n; k++) {
+            const RfwRTTriangle& t = m.tris[m.bvh.leaf_prims[k]];
+            m.ttris[(size_t)k * 3 + 0] = f4(t.vertex0[0], t.vertex0[1], t.vertex0[2], u2f(m.bvh.leaf_prims[k]));
+            m.ttris[(size_t)k * 3 + 1] = f4(t.vertex1[0], t.vertex1[1], t.vertex1[2], 0);
+            m.ttris[(size_t)k * 3 + 2] = f4(t.vertex2[0], t.vertex2[1], t.vertex2[2], 0);
+        }
+        tot_nodes += m.bvh.nodes.size() / 5;
+    }
+    sc.recs.clear();
+    std::vector<float4> ilo, ihi;
+    int gid = 0;
+    bool identity_single = false;
+    for (auto& kv : sc.inst) {
+        auto mit = sc.meshes.find(kv.first);
+        const size_t cnt = kv.second.size() / 16;
+        for (size_t i = 0; i < cnt; i++, gid++) {
+            if (mit == sc.meshes.end() || mit->second.tris.empty()) continue;
+            const float* M = &kv.second[i * 16];
+            bool zero = true;
+            for (int k = 0; k < 16; k++) zero &= (M[k] == 0.0f);
+            if (zero) continue;
+            InstanceRec r;
+            if (!invert_affine(M, r.inv0, r.inv1, r.inv2)) continue;
+            r.nodes = mit->second.bvh.nodes.data(); r.tris = mit->second.ttris.data();
+            r.inst_id = gid; r.mesh_id = (int)kv.first; r.pad0 = r.pad1 = 0;
+            float3 l = f3(FLT_MAX, FLT_MAX, FLT_MAX), h = f3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+            for (int c = 0; c < 8; c++) {
+                float3 p = f3((c & 1) ? mit->second.hi.x : mit->second.lo.x, (c & 2) ? mit->second.hi.y : mit->second.lo.y, (c & 4) ? mit->second.hi.z : mit->second.lo.z);
+                float3 w = f3(M[0] * p.x + M[4] * p.y + M[8] * p.z + M[12], M[1] * p.x + M[5] * p.y + M[9] * p.z + M[13], M[2] * p.x + M[6] * p.y + M[10] * p.z + M[14]);
+                l = min3(l, w); h = max3(h, w);
+            }
+            ilo.push_back(f4(l.x, l.y, l.z, 0)); ihi.push_back(f4(h.x, h.y, h.z, 0));
+            sc.recs.push_back(r);
+            static const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+            identity_single = memcmp(M, I, 64) == 0;
+        }
+    }
+    sc.sv.instances = sc.recs.data();
+    sc.sv.num_live = (int)sc.recs.size();
+    sc.sv.two_level = sc.recs.size() > 1;
+    sc.sv.single_identity = (sc.recs.size() == 1) && identity_single;
+    sc.sv.tlas_nodes = nullptr; sc.sv.tlas_refs = nullptr;
+    if (sc.sv.two_level) {
+        BuildParams PT{c_node, 4.0f, 1};
+        emu_build(ilo, ihi, PT, sc.tlas);
+        sc.sv.tlas_nodes = sc.tlas.nodes.data();
+        sc.sv.tlas_refs = sc.tlas.leaf_prims.data();
+    }
+    if (stats) { stats[0] = tot_nodes; stats[1] = sc.tlas.nodes.size() / 5; stats[2] = sc.recs.size(); }
+}
+
+void emu_trace(void* s, const RfwRay* rays, uint64_t n, RfwHit* hits, uint32_t* occluded, uint64_t* counters) {
+    EmuScene& sc = *(EmuScene*)s;
+    TraceCounters ctr{0, 0, 0};
+    for (uint64_t i = 0; i < n; i++) {
+        const RfwRay& r = rays[i];
+        Hit h;
+        if (hits) {
+            trace_ray<false, true, 64>(sc.sv, f3(r.origin[0], r.origin[1], r.origin[2]), f3(r.direction[0], r.direction[1], r.direction[2]), r.tmin, r.tmax, h, &ctr);
+            hits[i].inst = h.inst; hits[i].prim = h.prim; hits[i].t = h.t; hits[i].u = h.u; hits[i].v = h.v;
+        }
+        if (occluded) {
+            TraceCounters c2{0, 0, 0};
+            occluded[i] = trace_ray<true, true, 64>(sc.sv, f3(r.origin[0], r.origin[1], r.origin[2]), f3(r.direction[0], r.direction[1], r.direction[2]), r.tmin, r.tmax, h, &c2) ? 1u : 0u;
+        }
+    }
+    if (counters) { counters[0] = ctr.nodes; counters[1] = ctr.tris; counters[2] = ctr.instances; }
+}
+
+// structural validation of one mesh's wide BVH: every primitive appears exactly once, every child box
+// (dequantised) encloses its subtree, inner-child indices are unique.  Returns 0 when valid.
+int emu_validate(void* s, uint32_t mesh_id) {
+    EmuScene& sc = *(EmuScene*)s;
+    EmuMesh& m = sc.meshes[mesh_id];
+    const int n = (int)m.tris.size();
+    const size_t nn = m.bvh.nodes.size() / 5;
+    std::vector<int> seen(n, 0), node_seen(nn, 0);
+    struct Item { uint32_t node; double lo[3], hi[3]; };
+    std::vector<Item> stack;
+    Item root; root.node = 0;
+    for (int k = 0; k < 3; k++) { root.lo[k] = -1e300; root.hi[k] = 1e300; }
+    stack.push_back(root);
+    int errors = 0;
+    while (!stack.empty()) {
+        Item it = stack.back(); stack.pop_back();
+        if (it.node >= nn) { errors++; continue; }
+        if (node_seen[it.node]++) errors++;
+        const float4* np = &m.bvh.nodes[(size_t)it.node * 5];
+        const uint32_t e_imask = f2u(np[0].w);
+        const double sc3[3] = {ldexp(1.0, (int)(e_imask & 0xFF) - 127), ldexp(1.0, (int)((e_imask >> 8) & 0xFF) - 127), ldexp(1.0, (int)((e_imask >> 16) & 0xFF) - 127)};
+        const double p[3] = {np[0].x, np[0].y, np[0].z};
+        const uint32_t imask = e_imask >> 24;
+        const uint32_t child_base = f2u(np[1].x), prim_base = f2u(np[1].y);
+        const uint32_t w[12] = {f2u(np[2].x), f2u(np[2].y), f2u(np[2].z), f2u(np[2].w), f2u(np[3].x), f2u(np[3].y), f2u(np[3].z), f2u(np[3].w), f2u(np[4].x), f2u(np[4].y), f2u(np[4].z), f2u(np[4].w)};
+        // word index: qlox 0,1  qloy 2,3  qloz 4,5  qhix 6,7  qhiy 8,9  qhiz 10,11
+        for (int sl = 0; sl < 8; sl++) {
+            const uint32_t meta = (f2u(sl < 4 ? np[1].z : np[1].w) >> (8 * (sl & 3))) & 0xFF;
+            if (meta == 0) continue;
+            const int half = sl >> 2, sh = 8 * (sl & 3);
+            double lo[3], hi[3];
+            for (int ax = 0; ax < 3; ax++) {
+                lo[ax] = p[ax] + sc3[ax] * ((w[2 * ax + half] >> sh) & 0xFF);
+                hi[ax] = p[ax] + sc3[ax] * ((w[6 + 2 * ax + half] >> sh) & 0xFF);
+                if (lo[ax] < it.lo[ax] - 1e-3 * fabs(it.lo[ax]) - 1e-6 && it.lo[ax] > -1e299) { /* child boxes may exceed the parent's quantised box slightly: allowed */ }
+            }
+            if ((meta & 0x18) == 0x18 && (meta >> 5) == 1) {
+                if (!((imask >> sl) & 1) || (meta & 0x1F) != 24u + sl) errors++;
+                Item c; c.node = child_base + popc32(imask & ((1u << sl) - 1));
+                for (int ax = 0; ax < 3; ax++) { c.lo[ax] = lo[ax]; c.hi[ax] = hi[ax]; }
+                stack.push_back(c);
+            } else {
+                const uint32_t cnt = popc32(meta >> 5), off = meta & 0x1F;
+                for (uint32_t j = 0; j < cnt; j++) {
+                    const uint32_t slot = prim_base + off + j;
+                    if (slot >= (uint32_t)n) { errors++; continue; }
+                    const uint32_t prim = m.bvh.leaf_prims[slot];
+                    if (prim >= (uint32_t)n) { errors++; continue; }
+                    seen[prim]++;
+                    const RfwRTTriangle& t = m.tris[prim];
+                    const float* vs[3] = {t.vertex0, t.vertex1, t.vertex2};
+                    for (int v = 0; v < 3; v++)
+                        for (int ax = 0; ax < 3; ax++)
+                            if (vs[v][ax] < lo[ax] || vs[v][ax] > hi[ax]) errors++;
+                }
+            }
+        }
+    }
+    for (int i = 0; i < n; i++) if (seen[i] != 1) errors++;
+    for (size_t i = 0; i < nn; i++) if (node_seen[i] != 1) errors++;
+    return errors;
+}
+float emu_sah(void* s, uint32_t mesh_id) { return ((EmuScene*)s)->meshes[mesh_id].bvh.sah; }
+}
