@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 ray-tracing backend.
+
+Metric (BASELINE.json): Mrays/s closest-hit, incoherent rays.  Workload at every N: config C2 of BASELINE.json
+(`configs[1]`): synthetic 1M-triangle random soup, 2^24 incoherent random rays, closest hit.
+A "step" = one closest-hit pass over the 2^24 rays.  N > 1: the scene is replicated, every rank traces its own
+2^24 rays (weak scaling, no data-path collective); value = total rays / max-over-ranks device time.
+
+  value      rays already resident in HBM, device time of the persistent traversal kernel (CUDA events on the
+             backend's launching stream, taken inside librfwb200)
+  e2e        same metric through the C-ABI host entry point rfwb200_trace_closest with pinned HOST buffers:
+             H2D of the rays and D2H of the hit records are inside the timed region, every step
+  roofline   HBM roofline of the traversal kernel from ALGORITHMIC bytes (52 B/ray: 32 B ray in + 20 B hit out)
+  cpu_baseline  the CPU oracle (a port of the reference path; the reference itself is Rust and cannot be built
+             here) on the box's host cores over a bounded prefix of the same rays
+  extra      any-hit Mrays/s, BVH build ms, traversal statistics, wavefront path-tracing samples/s (C3)
+
+`--impl reference` times the CPU port alone on the same config/metric (all host threads).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_TRIS, SOUP_S, N_RAYS = 1_000_000, 0.005, 1 << 24
+BYTES_PER_RAY_CLOSEST = 52
+CPU_SAMPLE_RAYS = 1 << 20
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_rate(desc, rays, threads=0):
+    """The CPU oracle (BVH2 traversal: the faster of its two modes) on a bounded sample; returns Mrays/s."""
+    from oracle import oracle as orc
+
+    o = orc.OracleBackend(det_eps=0.0, threads=threads)
+    desc.apply(o)
+    best = None
+    for _ in range(2):
+        o.trace_closest(rays, mode=orc.MODE_BVH2)
+        best = o.trace_seconds if best is None else min(best, o.trace_seconds)
+    return len(rays) / best / 1e6, o.max_threads() if threads <= 0 else threads, o.build_seconds
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from rfw_rs_b200 import scenes
+
+    desc = scenes.soup_scene(N_TRIS, SOUP_S)
+    rays = scenes.random_rays(CPU_SAMPLE_RAYS)
+    from oracle import oracle as orc
+
+    o = orc.OracleBackend(det_eps=0.0)
+    desc.apply(o)
+    for _ in range(args.warmup):
+        o.trace_closest(rays[: 1 << 16], mode=orc.MODE_BVH2)
+    t = 0.0
+    for _ in range(args.steps):
+        o.trace_closest(rays, mode=orc.MODE_BVH2)
+        t += o.trace_seconds
+    value = args.steps * len(rays) / t / 1e6
+    sample = f"first {CPU_SAMPLE_RAYS} of the {N_RAYS} rays per step (BVH2 binned-SAH + Moller-Trumbore port, OpenMP)"
+    line = {
+        "impl": "reference", "metric": "Mrays/s closest-hit (incoherent)", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": "C2: 1M-triangle random soup, 2^24 incoherent rays, closest hit", "triangles": N_TRIS, "rays_per_step": len(rays)},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": o.max_threads(), "kind": "port", "sample": sample, "bvh_build_s": o.build_seconds},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def path_tracing_extra(backend_mod, scenes, torch, rank, world, spp, dist):
+    """C3: 10k-instance scene, 1920x1080, `spp` spp, depth 5 — tile-sharded over the ranks; the final accumulator
+    gather is one NCCL all_gather of tile-major buffers."""
+    w, h, depth, tile = 1920, 1080, 5, 64
+    desc = scenes.instanced_scene(grid=100, subdiv=3, n_lights=16)
+    be = backend_mod.B200Backend(w, h, tile_size=tile, rank=rank, world=world, sky=(0.3, 0.35, 0.5))
+    desc.apply(be)
+    view = scenes.camera_view((0.0, 14.0, -62.0), (0.0, -0.25, 1.0), w, h)
+    be.render_spp(view, 1, depth)  # warm-up frame
+    be.reset_accumulator()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    be.render_spp(view, spp, depth)
+    rs = be.render_stats()
+    ms = torch.tensor([rs["render_ms"]], device="cuda")
+    tot = torch.tensor([float(rs["samples"]), float(rs["extension_rays"]), float(rs["shadow_rays"])], device="cuda", dtype=torch.float64)
+    gather_ms = 0.0
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot)
+        tpr = be.tiles_per_rank
+        send = torch.zeros(tpr * tile * tile * 4, dtype=torch.float32, device="cuda")
+        recv = torch.empty(world * tpr * tile * tile * 4, dtype=torch.float32, device="cuda")
+        image = torch.empty(h * w * 4, dtype=torch.float32, device="cuda")
+        be.export_tiles_device(send.data_ptr(), tpr)
+        dist.all_gather_into_tensor(recv, send)  # warm-up of the communicator
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        be.export_tiles_device(send.data_ptr(), tpr)
+        dist.all_gather_into_tensor(recv, send)
+        be.assemble_tiles_device(recv.data_ptr(), tpr, world, image.data_ptr())
+        e1.record()
+        torch.cuda.synchronize()
+        gather_ms = e0.elapsed_time(e1)
+    bs = be.build_stats()
+    seg = float(tot[1].item())
+    samples = float(tot[0].item())
+    t_s = ms.item() / 1e3
+    return {
+        "workload": f"C3: 10k icosphere instances (12.8M instanced triangles) + ground + 16 area lights, 1920x1080, {spp} spp, depth 5, tile-sharded",
+        "samples_per_s": samples / t_s, "Msamples_per_s": samples / t_s / 1e6, "render_ms": ms.item(), "extension_rays": seg, "shadow_rays": float(tot[2].item()),
+        "Mrays_per_s_all_kinds": (seg + float(tot[2].item())) / t_s / 1e6, "mean_segments_per_sample": seg / max(1.0, samples),
+        "hbm_roofline_frac_algorithmic": (seg * 320.0 / t_s) / 1e9 / load_peaks()[0] / max(1, world),
+        "gather_ms": gather_ms, "tlas_build_ms": bs["tlas_build_ms"], "blas_build_ms": bs["blas_build_ms"], "instances": bs["num_instances"],
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--pt-spp", type=int, default=16)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+
+    from rfw_rs_b200 import backend, scenes, wire
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the backend has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- scene (replicated) and this rank's rays -------------------------------------------------------
+    desc = scenes.soup_scene(N_TRIS, SOUP_S)
+    be = backend.B200Backend(device=local_rank)
+    t0 = time.time()
+    desc.apply(be)
+    sync_wall_ms = (time.time() - t0) * 1e3
+    bs = be.build_stats()
+    rays = scenes.random_rays(N_RAYS, start=rank * N_RAYS)
+    pin_rays = backend.PinnedArray(N_RAYS, wire.RAY)
+    pin_hits = backend.PinnedArray(N_RAYS, wire.HIT)
+    pin_rays.array[:] = rays
+    d_rays = torch.empty(N_RAYS * 32, dtype=torch.uint8, device="cuda")
+    d_hits = torch.empty(N_RAYS * 20, dtype=torch.uint8, device="cuda")
+    d_occ = torch.empty(N_RAYS, dtype=torch.int32, device="cuda")
+    d_rays.copy_(torch.from_numpy(pin_rays.array.view(np.uint8).reshape(-1)))
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: rays resident in HBM ---------------------------------------------------------------------
+    for _ in range(args.warmup):
+        be.trace_closest_device(d_rays.data_ptr(), N_RAYS, d_hits.data_ptr())
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    l0 = be.launch_count()
+    kernel_ms = 0.0
+    w0 = time.time()
+    for _ in range(args.steps):
+        be.trace_closest_device(d_rays.data_ptr(), N_RAYS, d_hits.data_ptr())  # synchronous; CUDA-event time inside
+        kernel_ms += be.trace_stats()["kernel_ms"]
+    barrier()
+    wall_ms = (time.time() - w0) * 1e3
+    launches = be.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([kernel_ms], device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    kernel_ms_max = t.item()
+    value = world * args.steps * N_RAYS / (kernel_ms_max / 1e3) / 1e6
+
+    # ---- e2e: host buffers through the C-ABI entry point ----------------------------------------------------
+    for _ in range(max(1, args.warmup - 1)):
+        be.trace_closest(pin_rays.array, out=pin_hits.array)
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        be.trace_closest(pin_rays.array, out=pin_hits.array)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - e0
+    t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps * N_RAYS / t.item() / 1e6
+    launches += 0  # e2e launches are counted separately below
+    hit_rate = float((pin_hits.array["inst"] >= 0).mean())
+
+    # ---- extras -----------------------------------------------------------------------------------------------
+    extra = {}
+    if rank == 0 or dist is not None:
+        be.trace_any_device(d_rays.data_ptr(), N_RAYS, d_occ.data_ptr())
+        any_ms = 0.0
+        for _ in range(3):
+            be.trace_any_device(d_rays.data_ptr(), N_RAYS, d_occ.data_ptr())
+            any_ms += be.trace_stats()["kernel_ms"]
+        extra["any_hit_Mrays_per_s_per_gpu"] = 3 * N_RAYS / (any_ms / 1e3) / 1e6
+    if rank == 0:
+        st = be.trace_closest_counted(d_rays.data_ptr(), 1 << 22, d_hits.data_ptr())
+        extra["nodes_per_ray"] = st["nodes_visited"] / st["rays"]
+        extra["tris_per_ray"] = st["tris_tested"] / st["rays"]
+        extra["traversal_bytes_per_ray"] = extra["nodes_per_ray"] * 80 + extra["tris_per_ray"] * 48
+        extra["hit_rate"] = hit_rate
+        extra["bvh_build"] = {"blas_build_ms": bs["blas_build_ms"], "synchronize_wall_ms_incl_upload": sync_wall_ms, "wide_nodes": bs["blas_nodes"],
+                              "bvh_bytes": bs["bvh_bytes"], "sah_cost": bs["sah_cost"]}
+    if not args.no_extras:
+        try:
+            pt = path_tracing_extra(backend, scenes, torch, rank, world, args.pt_spp, dist)
+            if rank == 0:
+                extra["path_tracing"] = pt
+        except Exception as ex:  # the headline metric must still be reported
+            if rank == 0:
+                extra["path_tracing"] = {"error": repr(ex)}
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        per_launch_ms = kernel_ms / max(1, args.steps)
+        achieved = BYTES_PER_RAY_CLOSEST * N_RAYS / (per_launch_ms / 1e3) / 1e9
+        cpu_rate, cores, cpu_build_s = cpu_port_rate(desc, rays[:CPU_SAMPLE_RAYS])
+        line = {
+            "metric": "Mrays/s closest-hit (incoherent)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": kernel_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2: 1M-triangle random soup (s=0.005), 2^24 incoherent rays per GPU, closest hit", "triangles": N_TRIS, "rays_per_step_per_gpu": N_RAYS,
+                       "l2_policy": "inputs larger than L2: 512 MiB rays + 320 MiB hits streamed per step (evict-first); the 58 MB BVH is the step's reused working set",
+                       "scene": "replicated per GPU", "timing": "CUDA events on the backend stream inside librfwb200, max over ranks"},
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": N_RAYS * 32, "d2h_bytes_per_step": N_RAYS * 20,
+                    "note": "rfwb200_trace_closest with pinned host buffers; chunked H2D / kernel / D2H pipeline on 3 streams; wall clock, max over ranks"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "k_trace_persistent<RayBufferIO, closest, single-level>", "algorithmic_bytes_per_ray": BYTES_PER_RAY_CLOSEST, "peak_source": peak_src,
+                         "note": "pointer-chasing traversal over an L2-resident BVH: the HBM fraction is small by construction (SURVEY 8d); see extra.traversal_bytes_per_ray for the L2-side traffic"},
+            "cpu_baseline": {"value": cpu_rate, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                             "sample": f"first {CPU_SAMPLE_RAYS} rays of rank 0's step (best of 2); oracle BVH2 binned-SAH + Moller-Trumbore, OpenMP", "bvh_build_s": cpu_build_s},
+            "wall_ms_timed_region": wall_ms,
+            "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

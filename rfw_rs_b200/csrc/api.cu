@@ -1,0 +1,77 @@
+// api.cu — extern "C" trampolines of include/rfwb200.h onto rfw::Backend
+// (the shape of backends/metal/cpp/src/library.mm:7-76 in the reference).
+#include <new>
+
+#include "backend.h"
+
+using rfw::Backend;
+
+#define RFW_GUARD(h)                                          \
+    if (!(h)) {                                               \
+        rfw::set_last_error("null backend handle");           \
+        return RFWB200_ERR_INVALID;                           \
+    }                                                         \
+    Backend* b = static_cast<Backend*>(h)
+
+extern "C" {
+
+int rfwb200_create(const RfwB200Config* config, void** out_handle) {
+    if (!config || !out_handle) { rfw::set_last_error("rfwb200_create: null argument"); return RFWB200_ERR_INVALID; }
+    *out_handle = nullptr;
+    Backend* b = new (std::nothrow) Backend(*config);
+    if (!b) { rfw::set_last_error("out of host memory"); return RFWB200_ERR_OOM; }
+    const int rc = b->init();
+    if (rc != RFWB200_OK) { delete b; return rc; }
+    *out_handle = b;
+    return RFWB200_OK;
+}
+void rfwb200_destroy(void* handle) { delete static_cast<Backend*>(handle); }
+
+int rfwb200_set_3d_mesh(void* handle, uint32_t id, const RfwMeshData3D* data) { RFW_GUARD(handle); return b->set_3d_mesh(id, data); }
+int rfwb200_unload_3d_meshes(void* handle, const uint32_t* ids, uint32_t num) { RFW_GUARD(handle); return b->unload_3d_meshes(ids, num); }
+int rfwb200_set_3d_instances(void* handle, uint32_t mesh, const RfwInstancesData3D* data) { RFW_GUARD(handle); return b->set_3d_instances(mesh, data); }
+int rfwb200_set_materials(void* handle, const RfwDeviceMaterial* m, uint32_t num, const uint32_t*) { RFW_GUARD(handle); return b->set_materials(m, num); }
+int rfwb200_set_textures(void* handle, const RfwTextureData*, uint32_t, const uint32_t*) { RFW_GUARD(handle); return b ? RFWB200_OK : RFWB200_ERR_INVALID; }
+int rfwb200_synchronize(void* handle) { RFW_GUARD(handle); return b->synchronize(); }
+int rfwb200_render(void* handle, const RfwCameraView3D* view, uint32_t mode) { RFW_GUARD(handle); return b->render(view, mode); }
+int rfwb200_resize(void* handle, uint32_t w, uint32_t h, double) { RFW_GUARD(handle); return b->resize(w, h); }
+int rfwb200_set_point_lights(void* handle, const RfwPointLight* l, uint32_t n, const uint32_t*) { RFW_GUARD(handle); return b->set_point_lights(l, n); }
+int rfwb200_set_spot_lights(void* handle, const RfwSpotLight* l, uint32_t n, const uint32_t*) { RFW_GUARD(handle); return b->set_spot_lights(l, n); }
+int rfwb200_set_area_lights(void* handle, const RfwAreaLight* l, uint32_t n, const uint32_t*) { RFW_GUARD(handle); return b->set_area_lights(l, n); }
+int rfwb200_set_directional_lights(void* handle, const RfwDirectionalLight* l, uint32_t n, const uint32_t*) { RFW_GUARD(handle); return b->set_directional_lights(l, n); }
+int rfwb200_set_skybox(void* handle, const RfwTextureData*) { RFW_GUARD(handle); return b ? RFWB200_OK : RFWB200_ERR_INVALID; }
+int rfwb200_set_skins(void* handle, uint32_t) { RFW_GUARD(handle); return b ? RFWB200_OK : RFWB200_ERR_INVALID; }
+int rfwb200_set_2d_mesh(void* handle, uint32_t, const void*, uint32_t, int32_t) { RFW_GUARD(handle); return b ? RFWB200_OK : RFWB200_ERR_INVALID; }
+int rfwb200_set_2d_instances(void* handle, uint32_t, const float*, uint32_t) { RFW_GUARD(handle); return b ? RFWB200_OK : RFWB200_ERR_INVALID; }
+
+int rfwb200_trace_closest(void* handle, const RfwRay* rays, uint64_t num, RfwHit* out) { RFW_GUARD(handle); return b->trace_closest_host(rays, num, out); }
+int rfwb200_trace_any(void* handle, const RfwRay* rays, uint64_t num, uint32_t* out) { RFW_GUARD(handle); return b->trace_any_host(rays, num, out); }
+int rfwb200_trace_closest_device(void* handle, const RfwRay* d_rays, uint64_t num, RfwHit* d_hits, int sync) { RFW_GUARD(handle); return b->trace_closest_device(d_rays, num, d_hits, sync); }
+int rfwb200_trace_any_device(void* handle, const RfwRay* d_rays, uint64_t num, uint32_t* d_occ, int sync) { RFW_GUARD(handle); return b->trace_any_device(d_rays, num, d_occ, sync); }
+int rfwb200_trace_closest_counted(void* handle, const RfwRay* d_rays, uint64_t num, RfwHit* d_hits, RfwTraceStats* out) { RFW_GUARD(handle); return b->trace_closest_counted(d_rays, num, d_hits, out); }
+int rfwb200_cast_primary(void* handle, const RfwCameraView3D* view, RfwHit* out) { RFW_GUARD(handle); return b->cast_primary(view, out); }
+
+int rfwb200_render_spp(void* handle, const RfwCameraView3D* view, uint32_t spp, uint32_t depth) { RFW_GUARD(handle); return b->render_spp(view, spp, depth); }
+int rfwb200_reset_accumulator(void* handle) { RFW_GUARD(handle); return b->reset_accumulator(); }
+int rfwb200_read_accumulator(void* handle, float* out) { RFW_GUARD(handle); return b->read_accumulator(out); }
+int rfwb200_read_output(void* handle, float* out) { RFW_GUARD(handle); return b->read_output(out); }
+int rfwb200_export_tiles_device(void* handle, float* d_out, uint32_t cap, uint32_t* out_tiles) { RFW_GUARD(handle); return b->export_tiles_device(d_out, cap, out_tiles); }
+int rfwb200_assemble_tiles_device(void* handle, const float* d_g, uint32_t tpr, uint32_t world, float* d_img) { RFW_GUARD(handle); return b->assemble_tiles_device(d_g, tpr, world, d_img); }
+uint32_t rfwb200_sample_count(void* handle) { return handle ? static_cast<Backend*>(handle)->sample_count : 0; }
+uint32_t rfwb200_tiles_per_rank(void* handle) { return handle ? static_cast<Backend*>(handle)->tiles_per_rank() : 0; }
+
+int rfwb200_build_stats(void* handle, RfwBuildStats* out) { RFW_GUARD(handle); if (out) *out = b->build_stats; return RFWB200_OK; }
+int rfwb200_trace_stats(void* handle, RfwTraceStats* out) { RFW_GUARD(handle); if (out) *out = b->trace_stats; return RFWB200_OK; }
+int rfwb200_render_stats(void* handle, RfwRenderStats* out) { RFW_GUARD(handle); if (out) *out = b->render_stats; return RFWB200_OK; }
+int rfwb200_set_option(void* handle, const char* key, int64_t value) { RFW_GUARD(handle); return b->set_option(key, value); }
+
+void* rfwb200_host_alloc(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { rfw::set_last_error("cudaMallocHost failed"); return nullptr; }
+    return p;
+}
+void rfwb200_host_free(void* ptr) { if (ptr) cudaFreeHost(ptr); }
+const char* rfwb200_last_error(void) { return rfw::get_last_error(); }
+const char* rfwb200_version(void) { return "rfwb200 0.1 (sm_100a)"; }
+uint64_t rfwb200_launch_count(void* handle) { return handle ? static_cast<Backend*>(handle)->launches() : 0; }
+}

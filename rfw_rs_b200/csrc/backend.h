@@ -1,0 +1,141 @@
+// backend.h — the B200 backend object behind the C ABI of include/rfwb200.h.
+// Mirrors the state a `rfw_backend::Backend` implementation keeps (cf. RayTracer,
+// backends/gpu-rt/src/lib.rs:279-355): meshes, per-mesh instance lists, materials, lights,
+// acceleration structures, wavefront buffers — all device-resident, built and traced on the GPU.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/rfwb200.h"
+#include "builder.h"
+#include "trace.h"
+#include "wavefront.h"
+
+namespace rfw {
+
+struct MeshRec {
+    bool present = false;
+    bool dirty = false;
+    uint32_t n = 0;
+    uint32_t flags = 0;
+    RfwRTTriangle* d_tris = nullptr;  // full 176-byte records (shading reads them)
+    float4* d_ttris = nullptr;        // traversal triangles in leaf order
+    DeviceBvh bvh;
+};
+
+struct InstanceList {
+    bool present = false;
+    std::vector<float> matrices;  // 16 per instance, column-major
+};
+
+template <typename T>
+struct DeviceArray {
+    T* ptr = nullptr;
+    size_t capacity = 0;  // elements
+    cudaError_t reserve(size_t count) {
+        if (count <= capacity) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr; capacity = 0;
+        cudaError_t e = cudaMalloc(&ptr, count * sizeof(T));
+        if (e == cudaSuccess) capacity = count;
+        return e;
+    }
+    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; capacity = 0; }
+};
+
+class Backend {
+public:
+    explicit Backend(const RfwB200Config& cfg);
+    ~Backend();
+    int init();
+
+    int set_3d_mesh(uint32_t id, const RfwMeshData3D* data);
+    int unload_3d_meshes(const uint32_t* ids, uint32_t num);
+    int set_3d_instances(uint32_t mesh, const RfwInstancesData3D* data);
+    int set_materials(const RfwDeviceMaterial* m, uint32_t num);
+    int set_area_lights(const RfwAreaLight* l, uint32_t num);
+    int set_point_lights(const RfwPointLight* l, uint32_t num);
+    int set_spot_lights(const RfwSpotLight* l, uint32_t num);
+    int set_directional_lights(const RfwDirectionalLight* l, uint32_t num);
+    int synchronize();
+    int resize(uint32_t w, uint32_t h);
+
+    int trace_closest_host(const RfwRay* rays, uint64_t num, RfwHit* out);
+    int trace_any_host(const RfwRay* rays, uint64_t num, uint32_t* out);
+    int trace_closest_device(const RfwRay* d_rays, uint64_t num, RfwHit* d_hits, int sync);
+    int trace_any_device(const RfwRay* d_rays, uint64_t num, uint32_t* d_occ, int sync);
+    int trace_closest_counted(const RfwRay* d_rays, uint64_t num, RfwHit* d_hits, RfwTraceStats* out);
+    int cast_primary(const RfwCameraView3D* view, RfwHit* out_hits);
+
+    int render(const RfwCameraView3D* view, uint32_t mode);
+    int render_spp(const RfwCameraView3D* view, uint32_t spp, uint32_t depth);
+    int reset_accumulator();
+    int read_accumulator(float* out);
+    int read_output(float* out);
+    int export_tiles_device(float* d_out, uint32_t capacity_tiles, uint32_t* out_tiles);
+    int assemble_tiles_device(const float* d_gathered, uint32_t tiles_per_rank, uint32_t world, float* d_image);
+    uint32_t tiles_per_rank() const;
+
+    int set_option(const char* key, int64_t value);
+
+    RfwBuildStats build_stats{};
+    RfwTraceStats trace_stats{};
+    RfwRenderStats render_stats{};
+    uint32_t sample_count = 0;
+    uint64_t launches() const { return launch_count + bctx.launches; }
+
+private:
+    int fail(int code, const std::string& msg);
+    int cuda_fail(cudaError_t e, const char* what);
+    int ensure_synchronized(const char* who);
+    int update_wavefront_scene();
+
+    RfwB200Config cfg;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
+    BuilderContext bctx;
+    TraceConfig tcfg;
+    uint64_t launch_count = 0;
+
+    std::vector<MeshRec> meshes;
+    std::vector<InstanceList> inst_lists;
+    std::vector<RfwDeviceMaterial> materials;
+    std::vector<RfwAreaLight> area_lights;
+    std::vector<RfwPointLight> point_lights;
+    std::vector<RfwSpotLight> spot_lights;
+    std::vector<RfwDirectionalLight> dir_lights;
+    bool scene_dirty = true, shading_dirty = true, synchronized = false;
+
+    DeviceBvh tlas;
+    DeviceArray<InstanceRec> d_instances;
+    DeviceArray<InstanceShading> d_inst_shading;  // indexed by GLOBAL instance id
+    DeviceArray<RfwDeviceMaterial> d_materials;
+    DeviceArray<RfwAreaLight> d_area;
+    DeviceArray<RfwPointLight> d_point;
+    DeviceArray<RfwSpotLight> d_spot;
+    DeviceArray<RfwDirectionalLight> d_dir;
+    SceneView sv{};
+    uint32_t total_instance_slots = 0;
+
+    // ray-casting staging
+    DeviceArray<RfwRay> d_rays;
+    DeviceArray<RfwHit> d_hits;
+    DeviceArray<uint32_t> d_occ;
+    uint32_t* d_counter = nullptr;          // work counter of the persistent kernels
+    unsigned long long* d_counters3 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> chunk_events;
+    uint64_t chunk_rays = 1u << 21;
+
+    // wavefront renderer
+    Wavefront wf;
+    RfwCameraView3D last_view{};
+    bool have_view = false;
+};
+
+void set_last_error(const std::string& s);
+const char* get_last_error();
+
+}  // namespace rfw

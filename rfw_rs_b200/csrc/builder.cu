@@ -1,0 +1,299 @@
+// builder.cu — device BVH build: kernels wrapping the bodies of bvh_build.h + host orchestration.
+// Replaces the reference's CPU builds (rtbvh BinnedSahBuilder / MBVH::construct,
+// backends/gpu-rt/src/lib.rs:1345-1357, :1576-1581).  Everything after the H2D copy of the
+// triangles runs on the GPU; the host only reads back the per-level task counts of the collapse.
+#include <stdio.h>
+
+#include "builder.h"
+
+namespace rfw {
+
+#define RFW_CK(x)                              \
+    do {                                       \
+        cudaError_t e_ = (x);                  \
+        if (e_ != cudaSuccess) return e_;      \
+    } while (0)
+
+static constexpr int TB = 256;
+static inline int blocks_for(long long n, int tb = TB) { return (int)((n + tb - 1) / tb); }
+
+// order-preserving float <-> uint encoding for atomicMin/Max
+__device__ __forceinline__ uint32_t enc_f(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float dec_f(uint32_t u) {
+    const uint32_t v = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(v);
+#else
+    float f; memcpy(&f, &v, 4); return f;
+#endif
+}
+
+__global__ void __launch_bounds__(TB) k_triangle_boxes(const RfwRTTriangle* __restrict__ tris, int n, float4* __restrict__ lo, float4* __restrict__ hi) {
+    const int i = blockIdx.x * TB + threadIdx.x;
+    if (i >= n) return;
+    // the three vertices are the first 3 x 16 bytes of the 176-byte record
+    const float4* p = reinterpret_cast<const float4*>(tris + i);
+    const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    lo[i] = make_float4(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)), 0.0f);
+    hi[i] = make_float4(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)), 0.0f);
+}
+
+// bounds[0..5]: centroid min xyz / max xyz; bounds[6..11]: box min xyz / max xyz (encoded)
+__global__ void __launch_bounds__(TB) k_bounds(const float4* __restrict__ lo, const float4* __restrict__ hi, int n, uint32_t* __restrict__ bounds) {
+    const int i = blockIdx.x * TB + threadIdx.x;
+    float v[12];
+    if (i < n) {
+        const float4 l = lo[i], h = hi[i];
+        v[0] = v[3] = (l.x + h.x) * 0.5f; v[1] = v[4] = (l.y + h.y) * 0.5f; v[2] = v[5] = (l.z + h.z) * 0.5f;
+        v[6] = l.x; v[7] = l.y; v[8] = l.z; v[9] = h.x; v[10] = h.y; v[11] = h.z;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 12; k++) v[k] = ((k % 6) < 3) ? 3.0e38f : -3.0e38f;
+    }
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        const bool is_min = (k % 6) < 3;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float y = __shfl_xor_sync(0xFFFFFFFFu, v[k], o);
+            v[k] = is_min ? fminf(v[k], y) : fmaxf(v[k], y);
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+            if ((k % 6) < 3) atomicMin(&bounds[k], enc_f(v[k]));
+            else atomicMax(&bounds[k], enc_f(v[k]));
+        }
+    }
+}
+
+__global__ void k_init_bounds(uint32_t* bounds) {
+    const int k = threadIdx.x;
+    if (k < 12) bounds[k] = ((k % 6) < 3) ? 0xFFFFFFFFu : 0u;
+}
+
+__global__ void __launch_bounds__(TB) k_morton(const float4* __restrict__ lo, const float4* __restrict__ hi, int n, const uint32_t* __restrict__ bounds,
+                                               uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const int i = blockIdx.x * TB + threadIdx.x;
+    if (i >= n) return;
+    const float3 cmin = f3(dec_f(bounds[0]), dec_f(bounds[1]), dec_f(bounds[2]));
+    const float3 cmax = f3(dec_f(bounds[3]), dec_f(bounds[4]), dec_f(bounds[5]));
+    const float3 e = cmax - cmin;
+    const float3 cscale = f3(e.x > 0.0f ? 2097152.0f / e.x : 0.0f, e.y > 0.0f ? 2097152.0f / e.y : 0.0f, e.z > 0.0f ? 2097152.0f / e.z : 0.0f);
+    morton_body(i, lo, hi, cmin, cscale, keys, vals);
+}
+
+__global__ void __launch_bounds__(TB) k_karras(int n, const uint64_t* __restrict__ keys, int* __restrict__ parent, int2* __restrict__ children, int2* __restrict__ range) {
+    const int i = blockIdx.x * TB + threadIdx.x;
+    if (i >= n - 1) return;
+    karras_body(i, n, keys, parent, children, range);
+}
+
+__global__ void __launch_bounds__(TB) k_fit_cost(BuildArrays A, BuildParams P) {
+    const int k = blockIdx.x * TB + threadIdx.x;
+    if (k >= A.n) return;
+    fit_cost_body(k, A, P);
+}
+
+__global__ void __launch_bounds__(128) k_collapse(const int2* __restrict__ queue, uint32_t count, BuildArrays A, CollapseOut O, int2* __restrict__ next_queue,
+                                                  uint32_t* __restrict__ next_count) {
+    const uint32_t t = blockIdx.x * 128 + threadIdx.x;
+    if (t >= count) return;
+    collapse_body(queue[t], A, O, next_queue, next_count);
+}
+
+__global__ void k_init_collapse(int2* q0, uint32_t* counters) {
+    q0[0] = make_int2(0, 0);
+    counters[0] = 1;  // wide nodes allocated (root)
+    counters[1] = 0;  // leaf slots allocated
+    counters[2] = 0;  // next-level task count (ping)
+    counters[3] = 0;  // next-level task count (pong)
+}
+
+__global__ void __launch_bounds__(TB) k_gather_tris(const RfwRTTriangle* __restrict__ tris, const uint32_t* __restrict__ leaf_prims, int n, float4* __restrict__ out) {
+    const int k = blockIdx.x * TB + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t prim = leaf_prims[k];
+    const float4* p = reinterpret_cast<const float4*>(tris + prim);
+    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    a.w = __uint_as_float(prim);
+    b.w = 0.0f; c.w = 0.0f;
+    out[(size_t)k * 3 + 0] = a;
+    out[(size_t)k * 3 + 1] = b;
+    out[(size_t)k * 3 + 2] = c;
+}
+
+__global__ void __launch_bounds__(TB) k_checksum(const uint32_t* __restrict__ words, size_t count, unsigned long long* accum) {
+    unsigned long long s = 0;
+    for (size_t i = (size_t)blockIdx.x * TB + threadIdx.x; i < count; i += (size_t)gridDim.x * TB) {
+        unsigned long long x = (unsigned long long)words[i] + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
+        x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+        x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+        s += x ^ (x >> 31);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(accum, s);
+}
+
+void DeviceBvh::release() {
+    if (nodes) cudaFree(nodes);
+    if (leaf_prims) cudaFree(leaf_prims);
+    nodes = nullptr; leaf_prims = nullptr; num_nodes = 0; num_prims = 0;
+}
+
+BuildScratch::~BuildScratch() {
+    if (base) cudaFree(base);
+}
+void* BuildScratch::reserve(size_t bytes) {
+    if (bytes > capacity) {
+        if (base) cudaFree(base);
+        base = nullptr; capacity = 0;
+        const size_t want = bytes + bytes / 4;
+        if (cudaMalloc(&base, want) != cudaSuccess) { base = nullptr; return nullptr; }
+        capacity = want;
+    }
+    return base;
+}
+
+cudaError_t triangle_boxes(BuilderContext& ctx, const RfwRTTriangle* tris, int n, float4* prim_lo, float4* prim_hi) {
+    if (n == 0) return cudaSuccess;
+    k_triangle_boxes<<<blocks_for(n), TB, 0, ctx.stream>>>(tris, n, prim_lo, prim_hi);
+    ctx.launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t gather_traversal_triangles(BuilderContext& ctx, const RfwRTTriangle* tris, const uint32_t* leaf_prims, int n, float4* out) {
+    if (n == 0) return cudaSuccess;
+    k_gather_tris<<<blocks_for(n), TB, 0, ctx.stream>>>(tris, leaf_prims, n, out);
+    ctx.launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t buffer_checksum(BuilderContext& ctx, const uint32_t* words, size_t count, unsigned long long* d_accum) {
+    if (count == 0) return cudaSuccess;
+    int blocks = (int)((count + TB - 1) / TB);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_checksum<<<blocks, TB, 0, ctx.stream>>>(words, count, d_accum);
+    ctx.launches++;
+    return cudaGetLastError();
+}
+
+namespace {
+struct Carver {
+    char* p;
+    size_t off = 0;
+    template <typename T>
+    T* take(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        T* r = reinterpret_cast<T*>(p + off);
+        off += count * sizeof(T);
+        return r;
+    }
+};
+}  // namespace
+
+cudaError_t build_wide_bvh(BuilderContext& ctx, const float4* prim_lo, const float4* prim_hi, int n, const BuildParams& params, DeviceBvh& out) {
+    out.release();
+    if (n <= 0) return cudaSuccess;
+    cudaStream_t s = ctx.stream;
+    const int tiles = radix_sort_tiles(n);
+    const size_t nn = 2 * (size_t)n - 1, ni = n > 1 ? (size_t)n - 1 : 1;
+
+    // pass 1 computes the size, pass 2 carves
+    Carver cv{nullptr};
+    uint64_t *keys = nullptr, *keys_tmp = nullptr;
+    uint32_t *vals = nullptr, *vals_tmp = nullptr, *hist = nullptr, *decision = nullptr, *counters = nullptr, *bounds = nullptr, *tmp_leaf = nullptr;
+    int *parent = nullptr, *flags = nullptr;
+    int2 *children = nullptr, *range = nullptr, *q0 = nullptr, *q1 = nullptr;
+    float4 *node_lo = nullptr, *node_hi = nullptr, *tmp_nodes = nullptr;
+    float* cost = nullptr;
+    for (int pass = 0; pass < 2; pass++) {
+        cv.off = 0;
+        keys = cv.take<uint64_t>(n); keys_tmp = cv.take<uint64_t>(n);
+        vals = cv.take<uint32_t>(n); vals_tmp = cv.take<uint32_t>(n);
+        hist = cv.take<uint32_t>((size_t)256 * tiles);
+        parent = cv.take<int>(nn); flags = cv.take<int>(ni);
+        children = cv.take<int2>(ni); range = cv.take<int2>(ni);
+        node_lo = cv.take<float4>(nn); node_hi = cv.take<float4>(nn);
+        cost = cv.take<float>(nn * 8);
+        decision = cv.take<uint32_t>(ni);
+        q0 = cv.take<int2>(n); q1 = cv.take<int2>(n);
+        tmp_nodes = cv.take<float4>((size_t)n * 5);
+        tmp_leaf = cv.take<uint32_t>(n);
+        counters = cv.take<uint32_t>(8);
+        bounds = cv.take<uint32_t>(16);
+        if (pass == 0) {
+            void* base = ctx.scratch.reserve(cv.off + 512);
+            if (!base) return cudaErrorMemoryAllocation;
+            cv.p = (char*)base;
+        }
+    }
+
+    k_init_bounds<<<1, 32, 0, s>>>(bounds);
+    k_bounds<<<blocks_for(n), TB, 0, s>>>(prim_lo, prim_hi, n, bounds);
+    k_morton<<<blocks_for(n), TB, 0, s>>>(prim_lo, prim_hi, n, bounds, keys, vals);
+    ctx.launches += 3;
+    RFW_CK(cudaGetLastError());
+    const int flip = radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, hist, n, 0, 64, s, &ctx.launches);
+    const uint64_t* skeys = flip ? keys_tmp : keys;
+    const uint32_t* order = flip ? vals_tmp : vals;
+
+    BuildArrays A;
+    A.n = n; A.prim_lo = prim_lo; A.prim_hi = prim_hi; A.keys = skeys; A.order = order;
+    A.parent = parent; A.children = children; A.range = range; A.node_lo = node_lo; A.node_hi = node_hi;
+    A.cost = cost; A.decision = decision; A.flags = flags;
+    if (n > 1) {
+        RFW_CK(cudaMemsetAsync(flags, 0, ni * sizeof(int), s));
+        k_karras<<<blocks_for(n - 1), TB, 0, s>>>(n, skeys, parent, children, range);
+        ctx.launches++;
+    }
+    k_fit_cost<<<blocks_for(n), TB, 0, s>>>(A, params);
+    ctx.launches++;
+    RFW_CK(cudaGetLastError());
+
+    CollapseOut O;
+    O.nodes = tmp_nodes; O.leaf_prims = tmp_leaf; O.node_counter = counters + 0; O.prim_counter = counters + 1;
+    k_init_collapse<<<1, 1, 0, s>>>(q0, counters);
+    ctx.launches++;
+    uint32_t count = 1;
+    int2 *qin = q0, *qout = q1;
+    int ping = 0;
+    uint32_t h_counters[4];
+    while (count > 0) {
+        uint32_t* next_count = counters + 2 + ping;
+        k_collapse<<<blocks_for(count, 128), 128, 0, s>>>(qin, count, A, O, qout, next_count);
+        ctx.launches++;
+        RFW_CK(cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, s));
+        RFW_CK(cudaStreamSynchronize(s));
+        count = h_counters[2 + ping];
+        RFW_CK(cudaMemsetAsync(next_count, 0, sizeof(uint32_t), s));
+        int2* t = qin; qin = qout; qout = t;
+        ping ^= 1;
+    }
+    out.num_nodes = h_counters[0];
+    out.num_prims = h_counters[1];
+    if (out.num_prims != (uint32_t)n) {
+        fprintf(stderr, "rfwb200: collapse emitted %u leaf slots for %d primitives\n", out.num_prims, n);
+        return cudaErrorUnknown;
+    }
+    RFW_CK(cudaMalloc(&out.nodes, (size_t)out.num_nodes * 80));
+    RFW_CK(cudaMalloc(&out.leaf_prims, (size_t)n * sizeof(uint32_t)));
+    RFW_CK(cudaMemcpyAsync(out.nodes, tmp_nodes, (size_t)out.num_nodes * 80, cudaMemcpyDeviceToDevice, s));
+    RFW_CK(cudaMemcpyAsync(out.leaf_prims, tmp_leaf, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    uint32_t h_bounds[12];
+    float h_cost[8];
+    RFW_CK(cudaMemcpyAsync(h_bounds, bounds, sizeof(h_bounds), cudaMemcpyDeviceToHost, s));
+    // root cost: binary node 0 (for n == 1 the only leaf has id 0 as well)
+    RFW_CK(cudaMemcpyAsync(h_cost, cost, sizeof(h_cost), cudaMemcpyDeviceToHost, s));
+    RFW_CK(cudaStreamSynchronize(s));
+    for (int k = 0; k < 3; k++) { out.lo[k] = dec_f(h_bounds[6 + k]); out.hi[k] = dec_f(h_bounds[9 + k]); }
+    out.sah = h_cost[7] > 0.0f ? h_cost[0] / h_cost[7] : 0.0f;
+    return cudaSuccess;
+}
+
+}  // namespace rfw

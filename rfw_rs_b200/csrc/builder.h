@@ -1,0 +1,51 @@
+// builder.h — host-side interface of the device BVH builder (builder.cu, radix_sort.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rfwb200.h"
+#include "bvh_build.h"
+
+namespace rfw {
+
+int radix_sort_tiles(int n);
+int radix_sort_pairs(uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp, uint32_t* hist, int n, int begin_bit, int end_bit, cudaStream_t stream,
+                     uint64_t* launches);
+
+// A built wide BVH resident in HBM.
+struct DeviceBvh {
+    float4* nodes = nullptr;        // 5 float4 per node
+    uint32_t* leaf_prims = nullptr; // leaf slot -> primitive index
+    uint32_t num_nodes = 0;
+    uint32_t num_prims = 0;
+    float sah = 0.0f;
+    float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};  // bounds of all primitive boxes
+    void release();
+};
+
+// Scratch arena reused across builds (grown on demand, never shrunk).
+struct BuildScratch {
+    void* base = nullptr;
+    size_t capacity = 0;
+    ~BuildScratch();
+    void* reserve(size_t bytes);
+};
+
+struct BuilderContext {
+    cudaStream_t stream = nullptr;
+    BuildScratch scratch;
+    uint64_t launches = 0;
+};
+
+// prim_lo / prim_hi: device arrays of n boxes.  Builds the wide BVH into `out` (allocating exact-size buffers).
+// Returns a cudaError_t (cudaSuccess on success).
+cudaError_t build_wide_bvh(BuilderContext& ctx, const float4* prim_lo, const float4* prim_hi, int n, const BuildParams& params, DeviceBvh& out);
+
+// triangle boxes of a 176-byte RTTriangle array (device pointers)
+cudaError_t triangle_boxes(BuilderContext& ctx, const RfwRTTriangle* tris, int n, float4* prim_lo, float4* prim_hi);
+// traversal triangles: out[3k..3k+2] = vertices of tris[leaf_prims[k]], v0.w = prim index bits
+cudaError_t gather_traversal_triangles(BuilderContext& ctx, const RfwRTTriangle* tris, const uint32_t* leaf_prims, int n, float4* out);
+// order-independent checksum of a device buffer of 32-bit words (sum of word * (index+1) mixed)
+cudaError_t buffer_checksum(BuilderContext& ctx, const uint32_t* words, size_t count, unsigned long long* d_accum);
+
+}  // namespace rfw

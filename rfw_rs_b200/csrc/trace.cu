@@ -1,0 +1,130 @@
+// trace.cu — closest-hit / any-hit ray casting kernels for sm_100a.
+//
+// Replaces the reference's traversal stages: ray_extend.comp:245-268 (closest hit, one thread per ray,
+// 32-entry private stack per level) and ray_shadow.comp:245-269 (any hit).
+//
+// k_trace_persistent: persistent CTAs (grid = SMs x resident CTAs), each warp fetches rays from a global
+// counter with one atomicAdd per refill (ballot + popc + shfl), refills idle lanes when too few lanes are
+// still traversing, keeps the traversal stack in shared memory ([entry][thread], conflict-free) with a
+// local-memory overflow, walks 80-byte compressed 8-wide nodes in ray-octant order and tests triangles
+// with the watertight test of traverse.h.  k_trace_simple: one thread per ray, private stack — the
+// reference form used by the instrumented entry point and as a cross-check in the tests.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "trace.h"
+#include "trace_kernel.cuh"
+
+namespace rfw {
+
+// C-ABI ray buffers: RfwRay (32 B) in, RfwHit (20 B) / uint32 flag out; streamed (evict-first) accesses
+struct RayBufferIO {
+    const float4* rays;
+    uint32_t n;
+    RfwHit* hits;
+    uint32_t* occluded;
+    __device__ __forceinline__ uint32_t count() const { return n; }
+    __device__ __forceinline__ void load(uint32_t i, float4& r0, float4& r1) const {
+        r0 = __ldcs(rays + 2 * (size_t)i);
+        r1 = __ldcs(rays + 2 * (size_t)i + 1);
+    }
+    __device__ __forceinline__ void store_closest(uint32_t i, const Hit& h) const {
+        float* out = reinterpret_cast<float*>(hits + i);
+        __stcs(reinterpret_cast<int*>(out) + 0, h.inst);
+        __stcs(reinterpret_cast<int*>(out) + 1, h.prim);
+        __stcs(out + 2, h.t);
+        __stcs(out + 3, h.u);
+        __stcs(out + 4, h.v);
+    }
+    __device__ __forceinline__ void store_any(uint32_t i, bool occ) const { __stcs(occluded + i, occ ? 1u : 0u); }
+};
+
+template <bool ANY, bool COUNT>
+__global__ void __launch_bounds__(128) k_trace_simple(SceneView sv, const float4* __restrict__ rays, uint32_t n, RfwHit* __restrict__ hits, uint32_t* __restrict__ occluded,
+                                                      unsigned long long* __restrict__ counters) {
+    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    TraceCounters ctr{0, 0, 0};
+    if (i < n) {
+        const float4 r0 = __ldcs(rays + 2 * (size_t)i), r1 = __ldcs(rays + 2 * (size_t)i + 1);
+        Hit h;
+        const bool occ = trace_ray<ANY, COUNT, 48>(sv, xyz(r0), xyz(r1), r0.w, r1.w, h, &ctr);
+        if (ANY) occluded[i] = occ ? 1u : 0u;
+        else {
+            RfwHit out;
+            out.inst = h.inst; out.prim = h.prim; out.t = h.t; out.u = h.u; out.v = h.v;
+            hits[i] = out;
+        }
+    }
+    if (COUNT) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ctr.nodes += __shfl_xor_sync(FULL, ctr.nodes, o);
+            ctr.tris += __shfl_xor_sync(FULL, ctr.tris, o);
+            ctr.instances += __shfl_xor_sync(FULL, ctr.instances, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(counters + 0, ctr.nodes);
+            atomicAdd(counters + 1, ctr.tris);
+            atomicAdd(counters + 2, ctr.instances);
+        }
+    }
+}
+
+// pinhole primary rays: CameraView3D::generate_ray, crates/rfw-backend/src/structs.rs:549-556
+__global__ void __launch_bounds__(256) k_generate_pinhole(RfwCameraView3D cam, uint32_t w, uint32_t h, float4* __restrict__ rays) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= w * h) return;
+    const uint32_t x = i % w, y = i / w;
+    const float u = (float)x * cam.inv_width, v = (float)y * cam.inv_height;
+    const float3 pos = f3(cam.pos[0], cam.pos[1], cam.pos[2]);
+    const float3 p = f3(cam.p1[0], cam.p1[1], cam.p1[2]) + u * f3(cam.right[0], cam.right[1], cam.right[2]) + v * f3(cam.up[0], cam.up[1], cam.up[2]);
+    const float3 d = normalize3(p - pos);
+    rays[2 * (size_t)i] = f4(pos.x, pos.y, pos.z, 1e-4f);
+    rays[2 * (size_t)i + 1] = f4(d.x, d.y, d.z, 1e26f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <bool ANY, bool TWO_LEVEL>
+static cudaError_t launch_persistent(const TraceConfig& cfg, const SceneView& sv, const float4* rays, uint32_t n, RfwHit* hits, uint32_t* occ, uint32_t* counter) {
+    RayBufferIO io{rays, n, hits, occ};
+    return launch_persistent_io<RayBufferIO, ANY, TWO_LEVEL>(cfg.stream, cfg.sm_count, cfg.blocks_per_sm, cfg.refill_below, sv, io, n, counter);
+}
+
+cudaError_t trace_closest(const TraceConfig& cfg, const SceneView& sv, const RfwRay* d_rays, uint32_t n, RfwHit* d_hits, uint32_t* d_counter) {
+    if (n == 0) return cudaSuccess;
+    const float4* rays = reinterpret_cast<const float4*>(d_rays);
+    if (cfg.variant == TRACE_VARIANT_SIMPLE) {
+        k_trace_simple<false, false><<<(n + 127) / 128, 128, 0, cfg.stream>>>(sv, rays, n, d_hits, nullptr, nullptr);
+        return cudaGetLastError();
+    }
+    return sv.two_level ? launch_persistent<false, true>(cfg, sv, rays, n, d_hits, nullptr, d_counter)
+                        : launch_persistent<false, false>(cfg, sv, rays, n, d_hits, nullptr, d_counter);
+}
+
+cudaError_t trace_any(const TraceConfig& cfg, const SceneView& sv, const RfwRay* d_rays, uint32_t n, uint32_t* d_occluded, uint32_t* d_counter) {
+    if (n == 0) return cudaSuccess;
+    const float4* rays = reinterpret_cast<const float4*>(d_rays);
+    if (cfg.variant == TRACE_VARIANT_SIMPLE) {
+        k_trace_simple<true, false><<<(n + 127) / 128, 128, 0, cfg.stream>>>(sv, rays, n, nullptr, d_occluded, nullptr);
+        return cudaGetLastError();
+    }
+    return sv.two_level ? launch_persistent<true, true>(cfg, sv, rays, n, nullptr, d_occluded, d_counter)
+                        : launch_persistent<true, false>(cfg, sv, rays, n, nullptr, d_occluded, d_counter);
+}
+
+cudaError_t trace_closest_counted(const TraceConfig& cfg, const SceneView& sv, const RfwRay* d_rays, uint32_t n, RfwHit* d_hits, unsigned long long* d_counters3) {
+    if (n == 0) return cudaSuccess;
+    k_trace_simple<false, true><<<(n + 127) / 128, 128, 0, cfg.stream>>>(sv, reinterpret_cast<const float4*>(d_rays), n, d_hits, nullptr, d_counters3);
+    return cudaGetLastError();
+}
+
+cudaError_t generate_pinhole_rays(cudaStream_t stream, const RfwCameraView3D& cam, uint32_t w, uint32_t h, RfwRay* d_rays) {
+    const uint32_t n = w * h;
+    if (n == 0) return cudaSuccess;
+    k_generate_pinhole<<<(n + 255) / 256, 256, 0, stream>>>(cam, w, h, reinterpret_cast<float4*>(d_rays));
+    return cudaGetLastError();
+}
+
+}  // namespace rfw

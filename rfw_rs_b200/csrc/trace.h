@@ -1,0 +1,27 @@
+// trace.h — host-side interface of the ray-casting kernels (trace.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rfwb200.h"
+#include "traverse.h"
+
+namespace rfw {
+
+enum { TRACE_VARIANT_PERSISTENT = 0, TRACE_VARIANT_SIMPLE = 1 };
+
+struct TraceConfig {
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    int variant = TRACE_VARIANT_PERSISTENT;
+    int blocks_per_sm = 0;   // 0 = as many as fit
+    int refill_below = 20;   // refill idle lanes when fewer than this many lanes of a warp are traversing
+};
+
+// all pointers are device pointers; d_counter is one zero-initialisable uint32 work counter
+cudaError_t trace_closest(const TraceConfig& cfg, const SceneView& sv, const RfwRay* d_rays, uint32_t n, RfwHit* d_hits, uint32_t* d_counter);
+cudaError_t trace_any(const TraceConfig& cfg, const SceneView& sv, const RfwRay* d_rays, uint32_t n, uint32_t* d_occluded, uint32_t* d_counter);
+cudaError_t trace_closest_counted(const TraceConfig& cfg, const SceneView& sv, const RfwRay* d_rays, uint32_t n, RfwHit* d_hits, unsigned long long* d_counters3);
+cudaError_t generate_pinhole_rays(cudaStream_t stream, const RfwCameraView3D& cam, uint32_t w, uint32_t h, RfwRay* d_rays);
+
+}  // namespace rfw

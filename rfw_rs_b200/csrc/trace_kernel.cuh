@@ -1,0 +1,215 @@
+// trace_kernel.cuh — the persistent traversal kernel, templated on a ray I/O policy so the same code
+// serves the C-ABI ray buffers (trace.cu) and the wavefront extend / connect stages (wavefront.cu).
+//
+// IO policy:  uint32_t count() const;                         rays in this launch (may read device memory)
+//             void load(uint32_t i, float4& o_tmin, float4& d_tmax) const;
+//             void store_closest(uint32_t i, const Hit&) const;   void store_any(uint32_t i, bool occluded) const;
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "traverse.h"
+
+namespace rfw {
+
+static constexpr uint32_t FULL = 0xFFFFFFFFu;
+static constexpr int PT_THREADS = 128;
+static constexpr int PT_MIN_BLOCKS = 4;
+static constexpr int PT_SM_STACK = 12;
+
+// ------------------------------------------------------------------------------------------------
+// persistent kernel
+// ------------------------------------------------------------------------------------------------
+template <int SM_STACK, int L_STACK>
+struct LaneStack {
+    uint2* sm;       // &shared[threadIdx.x], stride blockDim.x
+    int stride;
+    uint2 local[L_STACK];
+    int sp;
+    __device__ __forceinline__ void push(uint2 v) {
+        if (sp < SM_STACK) sm[sp * stride] = v;
+        else if (sp - SM_STACK < L_STACK) local[sp - SM_STACK] = v;
+        sp++;
+    }
+    __device__ __forceinline__ uint2 pop() {
+        sp--;
+        if (sp < SM_STACK) return sm[sp * stride];
+        return local[(sp - SM_STACK) < L_STACK ? (sp - SM_STACK) : (L_STACK - 1)];
+    }
+};
+
+template <class IO, bool ANY, bool TWO_LEVEL, int THREADS, int MIN_BLOCKS, int SM_STACK>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneView sv, IO io, uint32_t* __restrict__ counter, int refill_below) {
+    extern __shared__ uint2 smem_stack[];
+    const uint32_t n = io.count();
+    const int lane = threadIdx.x & 31;
+    const uint32_t lanemask_lt = (1u << lane) - 1u;
+
+    LaneStack<SM_STACK, 24> st;
+    st.sm = smem_stack + threadIdx.x;
+    st.stride = THREADS;
+    st.sp = 0;
+
+    bool active = false;
+    bool more = true;
+    uint32_t ray_idx = 0;
+    // world-space ray (kept only for the two-level variant), current-space context
+    float3 wo = f3(0, 0, 0), wd = f3(0, 0, 0);
+    RayCtx rc;
+    rc.o = wo; rc.d = wd; rc.idir = wo; rc.octinv4 = 0; rc.kx = 0; rc.ky = 1; rc.kz = 2; rc.Sx = rc.Sy = rc.Sz = 0.0f;
+    float tmin = 0.0f;
+    Hit hit;
+    hit.inst = -1; hit.prim = -1; hit.t = 0.0f; hit.u = hit.v = 0.0f;
+    const float4* nodes = nullptr;
+    const float4* tris = nullptr;
+    bool in_blas = false;
+    int cur_inst = -1;
+    int blas_base_sp = 0;
+    uint2 ng = make_uint2(0u, 0u), tg = make_uint2(0u, 0u);
+
+    for (;;) {
+        // ---- refill idle lanes: one atomicAdd per warp ---------------------------------------------
+        {
+            const uint32_t idle = __ballot_sync(FULL, !active);
+            if (idle != 0u && more) {
+                const uint32_t cnt = __popc(idle);
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(counter, cnt);
+                base = __shfl_sync(FULL, base, 0);
+                if (!active) {
+                    const uint32_t my = base + __popc(idle & lanemask_lt);
+                    if (my < n) {
+                        float4 r0, r1;
+                        io.load(my, r0, r1);
+                        ray_idx = my;
+                        active = true;
+                        tmin = r0.w;
+                        hit.inst = -1; hit.prim = -1; hit.t = r1.w; hit.u = 0.0f; hit.v = 0.0f;
+                        st.sp = 0;
+                        ng = make_uint2(0u, 0x80000000u);
+                        tg = make_uint2(0u, 0u);
+                        if (TWO_LEVEL) {
+                            wo = xyz(r0); wd = xyz(r1);
+                            rc.o = wo; rc.d = wd;
+                            nodes = sv.tlas_nodes;
+                            in_blas = false;
+                            blas_base_sp = 0;
+                        } else {
+                            const InstanceRec& rec = sv.instances[0];
+                            if (sv.single_identity) { rc.o = xyz(r0); rc.d = xyz(r1); }
+                            else xform_ray(rec, xyz(r0), xyz(r1), rc.o, rc.d);
+                            nodes = rec.nodes; tris = rec.tris; cur_inst = rec.inst_id;
+                            in_blas = true;
+                            ray_setup_tri(rc);
+                        }
+                        ray_setup_box(rc);
+                    }
+                }
+                if (base + cnt >= n) more = false;
+            }
+            if (__ballot_sync(FULL, active) == 0u) break;
+        }
+        // ---- traverse until too few lanes are busy -------------------------------------------------
+        for (;;) {
+            if (active) {
+                if (RFW_NODE_HITS(ng)) {
+                    const uint32_t hits_imask = ng.y;
+                    const int bit = 31 - __clz((int)hits_imask);
+                    const uint32_t base = ng.x;
+                    ng.y &= ~(1u << bit);
+                    if (RFW_NODE_HITS(ng)) st.push(ng);
+                    const uint32_t slot = (uint32_t)(bit - 24) ^ (rc.octinv4 & 7u);
+                    const uint32_t rel = __popc(hits_imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
+                    const float4* np = nodes + (size_t)(base + rel) * 5;
+                    const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+                    const uint32_t hm = intersect_wide_node(n0, n1, n2, n3, n4, rc, tmin, hit.t);
+                    ng.x = __float_as_uint(n1.x);
+                    tg.x = __float_as_uint(n1.y);
+                    ng.y = (hm & 0xFF000000u) | (__float_as_uint(n0.w) >> 24);
+                    tg.y = hm & 0x00FFFFFFu;
+                } else {
+                    tg = ng;
+                    ng = make_uint2(0u, 0u);
+                }
+                bool done = false;
+                while (tg.y != 0u) {
+                    const int tb = 31 - __clz((int)tg.y);
+                    tg.y &= ~(1u << tb);
+                    const uint32_t idx = tg.x + (uint32_t)tb;
+                    if (!TWO_LEVEL || in_blas) {
+                        const float4* tp = tris + (size_t)idx * 3;
+                        const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                        float t, u, v;
+                        if (intersect_tri_wt(xyz(a), xyz(b), xyz(c), rc, t, u, v) && t > tmin) {
+                            const int prim = (int)__float_as_uint(a.w);
+                            if (ANY) {
+                                if (t < hit.t) { done = true; hit.prim = prim; break; }
+                            } else if (closer_hit(t, cur_inst, prim, hit)) {
+                                hit.t = t; hit.u = u; hit.v = v; hit.prim = prim; hit.inst = cur_inst;
+                            }
+                        }
+                    } else {
+                        const InstanceRec* rec = sv.instances + __ldg(sv.tlas_refs + idx);
+                        if (tg.y != 0u) st.push(tg);
+                        if (RFW_NODE_HITS(ng)) st.push(ng);
+                        blas_base_sp = st.sp;
+                        in_blas = true;
+                        cur_inst = rec->inst_id;
+                        xform_ray(*rec, wo, wd, rc.o, rc.d);
+                        ray_setup_box(rc);
+                        ray_setup_tri(rc);
+                        nodes = rec->nodes; tris = rec->tris;
+                        ng = make_uint2(0u, 0x80000000u);
+                        tg = make_uint2(0u, 0u);
+                        break;
+                    }
+                }
+                if (!done && !RFW_NODE_HITS(ng) && tg.y == 0u) {
+                    if (TWO_LEVEL && in_blas && st.sp == blas_base_sp) {
+                        in_blas = false;
+                        rc.o = wo; rc.d = wd;
+                        ray_setup_box(rc);
+                        nodes = sv.tlas_nodes;
+                    }
+                    if (st.sp == 0) done = true;
+                    else ng = st.pop();
+                }
+                if (done) {
+                    if (ANY) io.store_any(ray_idx, hit.prim >= 0);
+                    else io.store_closest(ray_idx, hit);
+                    active = false;
+                }
+            }
+            const uint32_t act = __ballot_sync(FULL, active);
+            if (act == 0u) break;
+            if (more && (int)__popc(act) < refill_below) break;
+        }
+    }
+}
+
+
+// launch with a persistent grid: min(SMs * resident CTAs, CTAs needed for `n_hint` rays)
+template <class IO, bool ANY, bool TWO_LEVEL>
+static cudaError_t launch_persistent_io(cudaStream_t stream, int sm_count, int blocks_per_sm_limit, int refill_below, const SceneView& sv, const IO& io, uint32_t n_hint,
+                                        uint32_t* counter) {
+    auto kern = k_trace_persistent<IO, ANY, TWO_LEVEL, PT_THREADS, PT_MIN_BLOCKS, PT_SM_STACK>;
+    const size_t smem = (size_t)PT_SM_STACK * PT_THREADS * sizeof(uint2);
+    static int bps = 0;  // one static per template instantiation
+    if (bps == 0) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, PT_THREADS, smem);
+        if (e != cudaSuccess) return e;
+        if (bps < 1) bps = 1;
+    }
+    int per_sm = bps;
+    if (blocks_per_sm_limit > 0 && blocks_per_sm_limit < per_sm) per_sm = blocks_per_sm_limit;
+    long long grid = (long long)sm_count * per_sm;
+    const long long needed = ((long long)n_hint + PT_THREADS - 1) / PT_THREADS;
+    if (grid > needed) grid = needed;
+    if (grid < 1) grid = 1;
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+    kern<<<(int)grid, PT_THREADS, smem, stream>>>(sv, io, counter, refill_below);
+    return cudaGetLastError();
+}
+
+}  // namespace rfw

@@ -1,0 +1,456 @@
+// wavefront.cu — wavefront path tracer for sm_100a: generate, extend, shade, connect, accumulate.
+//
+// Reference stages and what replaces them:
+//   ray_gen.comp:39-146        k_wf_generate   thin-lens eye rays (hash RNG), SoA queue write, tile-sharded
+//   ray_extend.comp:245-268    k_trace_persistent<ExtendIO>   persistent closest-hit traversal on the queue
+//   shade.comp:70-266          k_wf_shade      Disney BSDF, MIS on emissive hits, NEE shadow-ray emission,
+//                                              queue compaction with ONE atomic per warp (ballot + popc)
+//   ray_shadow.comp:245-269    k_trace_persistent<ConnectIO>  persistent any-hit + atomic accumulate
+//   blit.comp:15-22            k_wf_finalize   sqrt(acc / spp)
+//   host loop src/lib.rs:1706-1729 -> Wavefront::render: no per-bounce host read-back; counts stay in HBM.
+// Path state is 64 B/path (4 x float4 SoA), shadow jobs 48 B — the reference's record sizes
+// (structs.glsl:4-9, 172-176) so the algorithmic byte counts of SURVEY §8d apply.
+#include <algorithm>
+
+#include "shading.cuh"
+#include "trace_kernel.cuh"
+#include "wavefront.h"
+
+namespace rfw {
+
+#define WF_CK(x)                          \
+    do {                                  \
+        cudaError_t e_ = (x);             \
+        if (e_ != cudaSuccess) return e_; \
+    } while (0)
+
+struct FrameParams {
+    RfwCameraView3D cam;
+    uint32_t width, height, tile, tiles_x, max_paths;
+    uint32_t sample, path_length;
+    float clamp_value;
+    float sky[3];
+};
+
+__device__ __forceinline__ bool slot_to_pixel(const FrameParams& fp, const uint32_t* __restrict__ owned_tiles, uint32_t slot, uint32_t& pixel) {
+    const uint32_t tt = fp.tile * fp.tile;
+    const uint32_t tl = slot / tt, within = slot % tt;
+    const uint32_t tile = owned_tiles[tl];
+    const uint32_t x = (tile % fp.tiles_x) * fp.tile + within % fp.tile;
+    const uint32_t y = (tile / fp.tiles_x) * fp.tile + within / fp.tile;
+    pixel = x + y * fp.width;
+    return x < fp.width && y < fp.height;
+}
+
+// ---- generate: ray_gen.comp:103-146 ------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_wf_generate(FrameParams fp, const uint32_t* __restrict__ owned_tiles, float4* __restrict__ O, float4* __restrict__ D,
+                                                     uint32_t* __restrict__ counts) {
+    const uint32_t slot = blockIdx.x * 256 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    uint32_t pixel = 0;
+    const bool valid = slot < fp.max_paths && slot_to_pixel(fp, owned_tiles, slot, pixel);
+    float3 o = f3(0, 0, 0), d = f3(0, 0, 1);
+    if (valid) {
+        uint32_t seed = wang_hash(pixel * 16789u + fp.sample * 1791u);
+        const int sx = (int)(pixel % fp.width), sy = (int)(pixel / fp.width);
+        float r0 = randf(seed), r1 = randf(seed), r2 = randf(seed), r3 = randf(seed);
+        const float blade = (float)(int)(r0 * 9.0f);
+        r2 = (r2 - blade * (1.0f / 9.0f)) * 9.0f;
+        const float piOver4point5 = 3.14159265359f / 4.5f;
+        const float x1 = cosf(blade * piOver4point5), y1 = sinf(blade * piOver4point5);
+        const float x2 = cosf((blade + 1.0f) * piOver4point5), y2 = sinf((blade + 1.0f) * piOver4point5);
+        if ((r2 + r3) > 1.0f) { r2 = 1.0f - r2; r3 = 1.0f - r3; }
+        const float xr = x1 * r2 + x2 * r3, yr = y1 * r2 + y2 * r3;
+        const float3 right = ld3(fp.cam.right), up = ld3(fp.cam.up);
+        o = ld3(fp.cam.pos) + (right * xr + up * yr) * fp.cam.lens_size;
+        const float u = ((float)sx + r0) * (1.0f / (float)fp.width);
+        const float v = ((float)sy + r1) * (1.0f / (float)fp.height);
+        const float3 p = ld3(fp.cam.p1) + right * u + up * v;
+        d = normalize3(p - o);
+    }
+    const uint32_t m = __ballot_sync(FULL, valid);
+    if (m == 0u) return;
+    uint32_t base = 0;
+    const int leader = __ffs(m) - 1;
+    if (lane == leader) base = atomicAdd(&counts[0], (uint32_t)__popc(m));
+    base = __shfl_sync(FULL, base, leader);
+    if (valid) {
+        const uint32_t k = base + __popc(m & ((1u << lane) - 1u));
+        O[k] = f4(o.x, o.y, o.z, __uint_as_float(pixel));
+        D[k] = f4(d.x, d.y, d.z, 0.0f);
+    }
+}
+
+// ---- extend / connect I/O policies for the persistent traversal kernel --------------------------------
+struct ExtendIO {
+    const float4* O;
+    const float4* D;
+    const uint32_t* n;
+    float4* S;
+    __device__ __forceinline__ uint32_t count() const { return *n; }
+    __device__ __forceinline__ void load(uint32_t i, float4& r0, float4& r1) const {
+        r0 = O[i]; r1 = D[i];
+        r0.w = 1e-4f;  // ray_extend.comp:257-258
+        r1.w = 1e26f;
+    }
+    __device__ __forceinline__ void store_closest(uint32_t i, const Hit& h) const {
+        const uint32_t bary = (uint32_t)(65535.0f * h.u) + ((uint32_t)(65535.0f * h.v) << 16);  // ray_extend.comp:267
+        S[i] = f4(__int_as_float(h.inst), __int_as_float(h.prim), h.t, __uint_as_float(bary));
+    }
+    __device__ __forceinline__ void store_any(uint32_t, bool) const {}
+};
+
+struct ConnectIO {
+    const float4* O;
+    const float4* D;
+    const float4* E;
+    const uint32_t* n;
+    float* accum;  // float4 per pixel
+    __device__ __forceinline__ uint32_t count() const { return *n; }
+    __device__ __forceinline__ void load(uint32_t i, float4& r0, float4& r1) const {
+        r0 = O[i]; r1 = D[i];
+        r0.w = 0.001f;           // ray_shadow.comp:254
+        r1.w = r1.w - 0.0001f;   // ray_shadow.comp:257 (D.w = dist - 1e-4 from shade.comp:253)
+    }
+    __device__ __forceinline__ void store_closest(uint32_t, const Hit&) const {}
+    __device__ __forceinline__ void store_any(uint32_t i, bool occluded) const {
+        if (occluded) return;
+        const float4 e = E[i];
+        float* a = accum + 4 * (size_t)__float_as_uint(e.w);
+        atomicAdd(a + 0, e.x);
+        atomicAdd(a + 1, e.y);
+        atomicAdd(a + 2, e.z);
+    }
+};
+
+// ---- shade: shade.comp:70-266 ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_wf_shade(FrameParams fp, ShadeScene ss, const float4* __restrict__ S, const float4* __restrict__ O, const float4* __restrict__ D,
+                                                  const float4* __restrict__ T, float4* __restrict__ On, float4* __restrict__ Dn, float4* __restrict__ Tn,
+                                                  float4* __restrict__ shO, float4* __restrict__ shD, float4* __restrict__ shE, float* __restrict__ accum,
+                                                  const uint32_t* __restrict__ count_cur, uint32_t* __restrict__ count_next, uint32_t* __restrict__ count_shadow) {
+    const uint32_t count = *count_cur;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+    const uint32_t warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lightCount = ss.n_area + ss.n_point + ss.n_spot + ss.n_dir;
+    for (uint32_t base = warp_id * 32u; base < count; base += warps_total * 32u) {
+        const uint32_t k = base + lane;
+        const bool valid = k < count;
+        bool emit_ext = false, emit_sh = false;
+        float3 nO = f3(0, 0, 0), nD = f3(0, 0, 1), nT = f3(0, 0, 0);
+        float nPdf = 0.0f;
+        float3 sO = f3(0, 0, 0), sD = f3(0, 0, 1), sE = f3(0, 0, 0);
+        float sDist = 0.0f;
+        uint32_t pixel = 0;
+        if (valid) {
+            const float4 s4 = S[k], o4 = O[k], d4 = D[k];
+            const float4 t4 = fp.path_length == 0 ? f4(1.0f, 1.0f, 1.0f, 1.0f) : T[k];
+            pixel = __float_as_uint(o4.w);
+            const int inst = __float_as_int(s4.x), prim = __float_as_int(s4.y);
+            const float t = s4.z;
+            const float3 Dv = xyz(d4), Ov = xyz(o4);
+            float3 throughput = xyz(t4);
+            const float bsdfPdf = t4.w;
+            float3 contrib = f3(0, 0, 0);
+            bool add = false;
+            if (inst < 0) {  // :90-96 (constant sky; the skybox texture is SURVEY §8 f1)
+                contrib = throughput * f3(fp.sky[0], fp.sky[1], fp.sky[2]) * (1.0f / bsdfPdf);
+                clamp_intensity(contrib, fp.clamp_value);
+                add = true;
+            } else {
+                const InstanceShading* is = ss.inst + inst;
+                const float4* tp = reinterpret_cast<const float4*>(is->tris + prim);
+                const float4 q3 = __ldg(tp + 3), q4 = __ldg(tp + 4), q5 = __ldg(tp + 5), q6 = __ldg(tp + 6);  // normal|v0, n0|v1, n1|v2, n2|id
+                const float4 q7 = __ldg(tp + 7), q8 = __ldg(tp + 8), q9 = __ldg(tp + 9), q10 = __ldg(tp + 10);  // T0, T1, T2, light_id|mat_id|lod|area
+                const int mat_id = __float_as_int(q10.y);
+                const float tri_area = q10.w;
+                const ShadingData sd = extract_material(ss.materials + mat_id);
+                uint32_t seed = wang_hash(pixel * 16789u + fp.sample * 1791u + fp.path_length * 720898027u);  // :102-103
+                const uint32_t bary = __float_as_uint(s4.w);
+                const float u = (float)(bary & 65535u) * (1.0f / 65535.0f), v = (float)(bary >> 16) * (1.0f / 65535.0f);
+                const float w = 1.0f - u - v;
+                float3 gN = xyz(q3);
+                float3 N = xyz(q4) * w + xyz(q5) * u + xyz(q6) * v;
+                float3 T3 = xyz(q7) * w + xyz(q8) * u + xyz(q9) * v;
+                const float Tw = w * q7.w + u * q8.w + v * q9.w;
+                const float4 m0 = is->nrm0, m1 = is->nrm1, m2 = is->nrm2;
+                gN = normalize3(f3(m0.x * gN.x + m0.y * gN.y + m0.z * gN.z, m1.x * gN.x + m1.y * gN.y + m1.z * gN.z, m2.x * gN.x + m2.y * gN.y + m2.z * gN.z));
+                N = normalize3(f3(m0.x * N.x + m0.y * N.y + m0.z * N.z, m1.x * N.x + m1.y * N.y + m1.z * N.z, m2.x * N.x + m2.y * N.y + m2.z * N.z));
+                T3 = normalize3(f3(m0.x * T3.x + m0.y * T3.y + m0.z * T3.z, m1.x * T3.x + m1.y * T3.y + m1.z * T3.z, m2.x * T3.x + m2.y * T3.y + m2.z * T3.z));
+                const float3 B = cross3(N, T3) * Tw;
+                const float3 P = Ov + Dv * t;
+                if (sd.color.x > 1.0f || sd.color.y > 1.0f || sd.color.z > 1.0f) {  // hit a light, :128-160
+                    const float DdotNL = -dot3(Dv, N);
+                    if (DdotNL > 0.0f) {
+                        if (fp.path_length == 0) {
+                            contrib = throughput * sd.color * (1.0f / bsdfPdf);
+                        } else {
+                            const float lightPdf = (t * t) / (-dot3(Dv, N) * tri_area);  // :327-330
+                            const float pickProb = 1.0f / (float)lightCount;               // :368
+                            if ((bsdfPdf + lightPdf * pickProb) > 0.0f) contrib = throughput * sd.color * (1.0f / (bsdfPdf + lightPdf * pickProb));
+                        }
+                        clamp_intensity(contrib, fp.clamp_value);
+                    }
+                    add = true;
+                } else {
+                    const bool backFacing = dot3(Dv, gN) >= 0.0f;  // :177-181
+                    if (backFacing) { N = N * -1.0f; gN = gN * -1.0f; }
+                    throughput = throughput * (1.0f / bsdfPdf);  // :183
+                    const float r1 = randf(seed), r2 = randf(seed);
+                    const float3 wo = Dv * -1.0f;
+                    float3 R = f3(0, 0, 1);
+                    float newPdf = 0.0f;
+                    bsdf_sample(sd, T3, B, gN, wo, R, newPdf, r1, r2);                       // sampling frame: geometric normal (disney.glsl:275-285)
+                    const float3 bsdf = bsdf_eval(sd, N, wo, R, t, backFacing);             // evaluation: shading normal
+                    throughput = throughput * bsdf * fabsf(dot3(N, R));
+                    throughput = f3(throughput.x > 0.0f ? throughput.x : 0.0f, throughput.y > 0.0f ? throughput.y : 0.0f, throughput.z > 0.0f ? throughput.z : 0.0f);
+                    if (!(newPdf <= 1e-4f || isnan(newPdf))) {  // :208
+                        if (lightCount > 0) {                   // :213-258
+                            const float r3 = randf(seed);
+                            (void)randf(seed);  // r4 is drawn but unused by the uniform light pick
+                            float3 lightColor;
+                            float pickProb, lightPdf;
+                            float3 L = random_point_on_light(ss, r3, P, N, pickProb, lightPdf, lightColor) - P;
+                            const float dist = length3(L);
+                            L = L * (1.0f / dist);
+                            const float NdotL = dot3(L, N);
+                            if (NdotL > 0.0f && lightPdf > 0.0f) {
+                                const float3 sampled = bsdf_eval(sd, gN, wo, L, 0.0f, false);  // :235-239
+                                const float shadowPdf = bsdf_pdf(sd, gN, wo, L);
+                                if (shadowPdf > 0.0f) {
+                                    float3 c = throughput * sampled * lightColor * (NdotL / (lightPdf * pickProb));
+                                    if (!(isnan(c.x) || isnan(c.y) || isnan(c.z))) {
+                                        clamp_intensity(c, fp.clamp_value);
+                                        emit_sh = true;
+                                        sO = safe_origin(P, L, gN);
+                                        sD = L;
+                                        sDist = dist - 1e-4f;  // :253
+                                        sE = c;
+                                    }
+                                }
+                            }
+                        }
+                        emit_ext = true;  // :261-265
+                        nO = safe_origin(P, R, gN);
+                        nD = R;
+                        nT = throughput;
+                        nPdf = newPdf;
+                    }
+                }
+            }
+            if (add && (contrib.x != 0.0f || contrib.y != 0.0f || contrib.z != 0.0f)) {
+                float* a = accum + 4 * (size_t)pixel;
+                atomicAdd(a + 0, contrib.x);
+                atomicAdd(a + 1, contrib.y);
+                atomicAdd(a + 2, contrib.z);
+            }
+        }
+        // queue compaction: one atomic per warp per queue
+        const uint32_t ms = __ballot_sync(FULL, emit_sh);
+        if (ms) {
+            const int leader = __ffs(ms) - 1;
+            uint32_t b = 0;
+            if (lane == leader) b = atomicAdd(count_shadow, (uint32_t)__popc(ms));
+            b = __shfl_sync(FULL, b, leader);
+            if (emit_sh) {
+                const uint32_t j = b + __popc(ms & ((1u << lane) - 1u));
+                shO[j] = f4(sO.x, sO.y, sO.z, 0.0f);
+                shD[j] = f4(sD.x, sD.y, sD.z, sDist);
+                shE[j] = f4(sE.x, sE.y, sE.z, __uint_as_float(pixel));
+            }
+        }
+        const uint32_t me = __ballot_sync(FULL, emit_ext);
+        if (me) {
+            const int leader = __ffs(me) - 1;
+            uint32_t b = 0;
+            if (lane == leader) b = atomicAdd(count_next, (uint32_t)__popc(me));
+            b = __shfl_sync(FULL, b, leader);
+            if (emit_ext) {
+                const uint32_t j = b + __popc(me & ((1u << lane) - 1u));
+                On[j] = f4(nO.x, nO.y, nO.z, __uint_as_float(pixel));
+                Dn[j] = f4(nD.x, nD.y, nD.z, 0.0f);
+                Tn[j] = f4(nT.x, nT.y, nT.z, nPdf);
+            }
+        }
+    }
+}
+
+// bookkeeping between bounces: stats += counts, retire the consumed queues
+__global__ void k_wf_advance(uint32_t* counts, unsigned long long* stats, int cur) {
+    stats[0] += counts[cur];
+    stats[1] += counts[2];
+    stats[2] += counts[cur];
+    counts[cur] = 0;
+    counts[2] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_wf_finalize(FrameParams fp, const uint32_t* __restrict__ owned_tiles, const float4* __restrict__ accum, float4* __restrict__ out,
+                                                     float inv_spp) {
+    const uint32_t slot = blockIdx.x * 256 + threadIdx.x;
+    uint32_t pixel;
+    if (slot >= fp.max_paths || !slot_to_pixel(fp, owned_tiles, slot, pixel)) return;
+    const float4 a = accum[pixel];
+    out[pixel] = f4(sqrtf(a.x * inv_spp), sqrtf(a.y * inv_spp), sqrtf(a.z * inv_spp), sqrtf(a.w * inv_spp));  // blit.comp:22
+}
+
+__global__ void __launch_bounds__(256) k_wf_export(FrameParams fp, const uint32_t* __restrict__ owned_tiles, const float4* __restrict__ accum, float4* __restrict__ out) {
+    const uint32_t slot = blockIdx.x * 256 + threadIdx.x;
+    if (slot >= fp.max_paths) return;
+    uint32_t pixel;
+    out[slot] = slot_to_pixel(fp, owned_tiles, slot, pixel) ? accum[pixel] : f4(0, 0, 0, 0);
+}
+
+__global__ void __launch_bounds__(256) k_wf_assemble(FrameParams fp, const uint32_t* __restrict__ morton_tiles, uint32_t n_tiles, const float4* __restrict__ gathered,
+                                                      uint32_t tiles_per_rank, uint32_t world, float inv_spp, float4* __restrict__ image) {
+    const uint32_t tt = fp.tile * fp.tile;
+    const size_t g = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (g >= (size_t)world * tiles_per_rank * tt) return;
+    const uint32_t r = (uint32_t)(g / ((size_t)tiles_per_rank * tt));
+    const uint32_t tl = (uint32_t)((g / tt) % tiles_per_rank);
+    const uint32_t within = (uint32_t)(g % tt);
+    const uint32_t mr = tl * world + r;
+    if (mr >= n_tiles) return;
+    const uint32_t tile = morton_tiles[mr];
+    const uint32_t x = (tile % fp.tiles_x) * fp.tile + within % fp.tile;
+    const uint32_t y = (tile / fp.tiles_x) * fp.tile + within / fp.tile;
+    if (x >= fp.width || y >= fp.height) return;
+    const float4 a = gathered[g];
+    image[x + (size_t)y * fp.width] = f4(sqrtf(a.x * inv_spp), sqrtf(a.y * inv_spp), sqrtf(a.z * inv_spp), sqrtf(a.w * inv_spp));
+}
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+static uint32_t morton2(uint32_t x, uint32_t y) {
+    auto part = [](uint32_t v) {
+        v &= 0xFFFF;
+        v = (v | (v << 8)) & 0x00FF00FF;
+        v = (v | (v << 4)) & 0x0F0F0F0F;
+        v = (v | (v << 2)) & 0x33333333;
+        v = (v | (v << 1)) & 0x55555555;
+        return v;
+    };
+    return part(x) | (part(y) << 1);
+}
+
+void Wavefront::release() {
+    auto fr = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
+    fr(d_owned_tiles); fr(d_morton_tiles);
+    for (int i = 0; i < 2; i++) { fr(d_O[i]); fr(d_D[i]); fr(d_T[i]); }
+    fr(d_S); fr(d_shO); fr(d_shD); fr(d_shE); fr(d_accum); fr(d_output); fr(d_counts); fr(d_stats);
+    max_paths = 0;
+}
+
+cudaError_t Wavefront::configure(uint32_t w, uint32_t h, uint32_t tile_size, uint32_t rank_, uint32_t world_) {
+    release();
+    width = w; height = h; tile = tile_size ? tile_size : 64; rank = rank_; world = world_ ? world_ : 1;
+    tiles_x = (w + tile - 1) / tile; tiles_y = (h + tile - 1) / tile;
+    const uint32_t n_tiles = tiles_x * tiles_y;
+    morton_tiles.resize(n_tiles);
+    for (uint32_t i = 0; i < n_tiles; i++) morton_tiles[i] = i;
+    const uint32_t tx = tiles_x;
+    std::stable_sort(morton_tiles.begin(), morton_tiles.end(), [tx](uint32_t a, uint32_t b) { return morton2(a % tx, a / tx) < morton2(b % tx, b / tx); });
+    std::vector<uint32_t> owned;
+    for (uint32_t r = rank; r < n_tiles; r += world) owned.push_back(morton_tiles[r]);  // tile k (Morton order) -> rank k mod n
+    n_owned_tiles = (uint32_t)owned.size();
+    tiles_per_rank = (n_tiles + world - 1) / world;
+    max_paths = n_owned_tiles * tile * tile;
+    if (w == 0 || h == 0) return cudaSuccess;
+    WF_CK(cudaMalloc(&d_owned_tiles, sizeof(uint32_t) * std::max<size_t>(1, owned.size())));
+    WF_CK(cudaMalloc(&d_morton_tiles, sizeof(uint32_t) * n_tiles));
+    WF_CK(cudaMemcpy(d_owned_tiles, owned.data(), sizeof(uint32_t) * owned.size(), cudaMemcpyHostToDevice));
+    WF_CK(cudaMemcpy(d_morton_tiles, morton_tiles.data(), sizeof(uint32_t) * n_tiles, cudaMemcpyHostToDevice));
+    const size_t mp = std::max<uint32_t>(1, max_paths);
+    for (int i = 0; i < 2; i++) {
+        WF_CK(cudaMalloc(&d_O[i], mp * sizeof(float4)));
+        WF_CK(cudaMalloc(&d_D[i], mp * sizeof(float4)));
+        WF_CK(cudaMalloc(&d_T[i], mp * sizeof(float4)));
+    }
+    WF_CK(cudaMalloc(&d_S, mp * sizeof(float4)));
+    WF_CK(cudaMalloc(&d_shO, mp * sizeof(float4)));
+    WF_CK(cudaMalloc(&d_shD, mp * sizeof(float4)));
+    WF_CK(cudaMalloc(&d_shE, mp * sizeof(float4)));
+    WF_CK(cudaMalloc(&d_accum, (size_t)w * h * sizeof(float4)));
+    WF_CK(cudaMalloc(&d_output, (size_t)w * h * sizeof(float4)));
+    WF_CK(cudaMalloc(&d_counts, 8 * sizeof(uint32_t)));
+    WF_CK(cudaMalloc(&d_stats, 4 * sizeof(unsigned long long)));
+    WF_CK(cudaMemset(d_accum, 0, (size_t)w * h * sizeof(float4)));
+    WF_CK(cudaMemset(d_output, 0, (size_t)w * h * sizeof(float4)));
+    WF_CK(cudaMemset(d_counts, 0, 8 * sizeof(uint32_t)));
+    WF_CK(cudaMemset(d_stats, 0, 4 * sizeof(unsigned long long)));
+    return cudaSuccess;
+}
+
+static FrameParams make_params(const Wavefront& wf, const RfwCameraView3D& cam, uint32_t sample, uint32_t path_length) {
+    FrameParams fp;
+    fp.cam = cam;
+    fp.width = wf.width; fp.height = wf.height; fp.tile = wf.tile; fp.tiles_x = wf.tiles_x; fp.max_paths = wf.max_paths;
+    fp.sample = sample; fp.path_length = path_length;
+    fp.clamp_value = wf.clamp_value;
+    fp.sky[0] = wf.sky[0]; fp.sky[1] = wf.sky[1]; fp.sky[2] = wf.sky[2];
+    return fp;
+}
+
+cudaError_t Wavefront::clear(cudaStream_t stream) {
+    if (!d_accum) return cudaSuccess;
+    WF_CK(cudaMemsetAsync(d_accum, 0, (size_t)width * height * sizeof(float4), stream));
+    WF_CK(cudaMemsetAsync(d_stats, 0, 4 * sizeof(unsigned long long), stream));
+    return cudaSuccess;
+}
+
+cudaError_t Wavefront::render(cudaStream_t stream, const SceneView& sv, const ShadeScene& ss, const RfwCameraView3D& cam, uint32_t first_sample, uint32_t spp, uint32_t depth) {
+    if (max_paths == 0) return cudaSuccess;
+    const int shade_blocks = sm_count * 8;
+    for (uint32_t s = 0; s < spp; s++) {
+        FrameParams fp = make_params(*this, cam, first_sample + s, 0);
+        WF_CK(cudaMemsetAsync(d_counts, 0, 8 * sizeof(uint32_t), stream));
+        k_wf_generate<<<(max_paths + 255) / 256, 256, 0, stream>>>(fp, d_owned_tiles, d_O[0], d_D[0], d_counts);
+        launches++;
+        for (uint32_t b = 0; b < depth; b++) {
+            const int cur = b & 1, nxt = cur ^ 1;
+            fp.path_length = b;
+            ExtendIO eio{d_O[cur], d_D[cur], d_counts + cur, d_S};
+            if (sv.two_level) WF_CK((launch_persistent_io<ExtendIO, false, true>(stream, sm_count, 0, refill_below, sv, eio, max_paths, d_counts + 3)));
+            else WF_CK((launch_persistent_io<ExtendIO, false, false>(stream, sm_count, 0, refill_below, sv, eio, max_paths, d_counts + 3)));
+            k_wf_shade<<<shade_blocks, 128, 0, stream>>>(fp, ss, d_S, d_O[cur], d_D[cur], d_T[cur], d_O[nxt], d_D[nxt], d_T[nxt], d_shO, d_shD, d_shE,
+                                                         reinterpret_cast<float*>(d_accum), d_counts + cur, d_counts + nxt, d_counts + 2);
+            ConnectIO cio{d_shO, d_shD, d_shE, d_counts + 2, reinterpret_cast<float*>(d_accum)};
+            if (sv.two_level) WF_CK((launch_persistent_io<ConnectIO, true, true>(stream, sm_count, 0, refill_below, sv, cio, max_paths, d_counts + 4)));
+            else WF_CK((launch_persistent_io<ConnectIO, true, false>(stream, sm_count, 0, refill_below, sv, cio, max_paths, d_counts + 4)));
+            k_wf_advance<<<1, 1, 0, stream>>>(d_counts, d_stats, cur);
+            launches += 4;
+        }
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t Wavefront::finalize(cudaStream_t stream, uint32_t sample_count) {
+    if (max_paths == 0) return cudaSuccess;
+    RfwCameraView3D cam{};
+    FrameParams fp = make_params(*this, cam, 0, 0);
+    k_wf_finalize<<<(max_paths + 255) / 256, 256, 0, stream>>>(fp, d_owned_tiles, d_accum, d_output, 1.0f / (float)std::max(1u, sample_count));
+    launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t Wavefront::export_tiles(cudaStream_t stream, float* d_out) {
+    if (max_paths == 0) return cudaSuccess;
+    RfwCameraView3D cam{};
+    FrameParams fp = make_params(*this, cam, 0, 0);
+    k_wf_export<<<(max_paths + 255) / 256, 256, 0, stream>>>(fp, d_owned_tiles, d_accum, reinterpret_cast<float4*>(d_out));
+    launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t Wavefront::assemble(cudaStream_t stream, const float* d_gathered, uint32_t tiles_per_rank_, uint32_t world_, uint32_t sample_count, float* d_image) {
+    RfwCameraView3D cam{};
+    FrameParams fp = make_params(*this, cam, 0, 0);
+    const size_t total = (size_t)world_ * tiles_per_rank_ * tile * tile;
+    if (total == 0) return cudaSuccess;
+    k_wf_assemble<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(fp, d_morton_tiles, tiles_x * tiles_y, reinterpret_cast<const float4*>(d_gathered), tiles_per_rank_, world_,
+                                                                       1.0f / (float)std::max(1u, sample_count), reinterpret_cast<float4*>(d_image));
+    launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace rfw

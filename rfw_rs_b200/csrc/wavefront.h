@@ -1,0 +1,73 @@
+// wavefront.h — host-side interface of the wavefront path tracer (wavefront.cu).
+// Stages (reference: backends/gpu-rt/src/lib.rs:1685-1780 host loop; shaders ray_gen.comp, ray_extend.comp,
+// shade.comp, ray_shadow.comp, blit.comp): generate -> { extend -> shade -> connect } x depth -> finalize.
+// Unlike the reference there is no host read-back between bounces: queue counts live in device memory
+// and every kernel is launched with a persistent grid that reads them.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "../../include/rfwb200.h"
+#include "traverse.h"
+
+namespace rfw {
+
+// per GLOBAL instance id: what shading needs (normal matrix rows, triangle records of the mesh)
+struct InstanceShading {
+    float4 nrm0, nrm1, nrm2;      // rows of (M^-1)^T (shade.comp:113-115)
+    const RfwRTTriangle* tris;    // 176-byte records of the instance's mesh
+    int mesh_id;
+    int pad;
+};
+
+struct ShadeScene {
+    const InstanceShading* inst;
+    const RfwDeviceMaterial* materials;
+    const RfwAreaLight* area;
+    const RfwPointLight* point;
+    const RfwSpotLight* spot;
+    const RfwDirectionalLight* dir;
+    int n_area, n_point, n_spot, n_dir;
+    uint32_t n_materials;
+};
+
+struct Wavefront {
+    uint32_t width = 0, height = 0;
+    uint32_t tile = 64, rank = 0, world = 1;
+    uint32_t tiles_x = 0, tiles_y = 0;
+    uint32_t n_owned_tiles = 0, tiles_per_rank = 0;
+    uint32_t max_paths = 0;              // owned tiles * tile * tile
+    float clamp_value = 10.0f;
+    float sky[3] = {0, 0, 0};
+    // device buffers
+    uint32_t* d_owned_tiles = nullptr;   // tile ids owned by this rank, Morton order
+    uint32_t* d_morton_tiles = nullptr;  // all tile ids in Morton order (for assemble)
+    float4* d_O[2] = {nullptr, nullptr};
+    float4* d_D[2] = {nullptr, nullptr};
+    float4* d_T[2] = {nullptr, nullptr};
+    float4* d_S = nullptr;               // hit state: inst, prim, t, packed bary
+    float4* d_shO = nullptr;             // shadow queue
+    float4* d_shD = nullptr;
+    float4* d_shE = nullptr;
+    float4* d_accum = nullptr;           // width*height
+    float4* d_output = nullptr;          // width*height
+    uint32_t* d_counts = nullptr;        // [0],[1] path counts (ping/pong), [2] shadow count, [3..5] work counters
+    unsigned long long* d_stats = nullptr;  // [0] extension rays, [1] shadow rays, [2] segments(shaded)
+    std::vector<uint32_t> morton_tiles;
+    int sm_count = 148;
+    int refill_below = 20;
+    uint64_t launches = 0;
+
+    cudaError_t configure(uint32_t w, uint32_t h, uint32_t tile_size, uint32_t rank_, uint32_t world_);
+    void release();
+    // `spp` frames starting at sample index `first_sample`, `depth` segments each; asynchronous on `stream`
+    cudaError_t render(cudaStream_t stream, const SceneView& sv, const ShadeScene& ss, const RfwCameraView3D& cam, uint32_t first_sample, uint32_t spp, uint32_t depth);
+    cudaError_t clear(cudaStream_t stream);
+    cudaError_t finalize(cudaStream_t stream, uint32_t sample_count);  // d_output = sqrt(accum / sample_count), own tiles
+    cudaError_t export_tiles(cudaStream_t stream, float* d_out);      // own tiles, tile-major
+    cudaError_t assemble(cudaStream_t stream, const float* d_gathered, uint32_t tiles_per_rank_, uint32_t world_, uint32_t sample_count, float* d_image);
+};
+
+}  // namespace rfw

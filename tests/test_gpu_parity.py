@@ -1,0 +1,304 @@
+"""-m gpu: parity of the CUDA path (through the C ABI) with the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): instance / primitive IDs bit-exact except classified near-ties
+(tests/parity.py), t within 1e-4 relative (+ a float32 ulp floor), barycentrics within 2e-3, any-hit flags
+equal to the oracle's, accumulated radiance RMSE <= 1e-3 at fixed seed.  Full-size configs are checked through
+size-independent properties (any-hit == closest-hit-exists, direction scaling, determinism, tile-shard
+invariance) plus an oracle comparison on a prefix of the rays.
+"""
+import numpy as np
+import pytest
+
+from rfw_rs_b200 import scenes, wire
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+@pytest.fixture(scope="module")
+def B(torch_cuda):
+    from rfw_rs_b200 import backend
+
+    return backend
+
+
+def make_pair(B, oracle_mod, desc, w=0, h=0, **kw):
+    gpu = B.B200Backend(w, h, **kw)
+    desc.apply(gpu)
+    cpu = oracle_mod.OracleBackend(det_eps=0.0)
+    desc.apply(cpu)
+    return gpu, cpu
+
+
+def dev_buf(torch, arr):
+    return torch.from_numpy(np.frombuffer(arr.tobytes(), dtype=np.uint8).copy()).cuda()
+
+
+@pytest.mark.parametrize("n_tris", [1, 2, 3, 4, 9, 100, 3000])
+def test_small_soups(B, oracle_mod, n_tris):
+    desc = scenes.soup_scene(n_tris, 0.3 if n_tris < 200 else 0.05)
+    gpu, cpu = make_pair(B, oracle_mod, desc)
+    rays = scenes.random_rays(20000)
+    ref = cpu.trace_closest(rays, mode=oracle_mod.MODE_BVH2)
+    for variant in (0, 1):
+        gpu.set_option("trace_variant", variant)
+        hits = gpu.trace_closest(rays)
+        parity.compare_hits(rays, hits, ref, parity.lookup_from_desc(desc), f"soup{n_tris}/v{variant}")
+        occ = gpu.trace_any(rays)
+        assert (occ != cpu.trace_any(rays, mode=oracle_mod.MODE_BVH2)).sum() <= 2
+    st = gpu.build_stats()
+    assert st["num_triangles"] == n_tris and st["num_instances"] == 1 and st["blas_nodes"] >= 1
+
+
+def test_empty_and_ragged_inputs(B, oracle_mod):
+    desc = scenes.soup_scene(500, 0.1)
+    gpu, cpu = make_pair(B, oracle_mod, desc)
+    assert len(gpu.trace_closest(np.zeros(0, wire.RAY))) == 0
+    for n in (1, 31, 33, 127, 129, 1000):  # ragged warp / CTA tails
+        rays = scenes.random_rays(n, start=n * 7)
+        parity.compare_hits(rays, gpu.trace_closest(rays), cpu.trace_closest(rays), parity.lookup_from_desc(desc), f"ragged{n}")
+    # empty scene: every ray misses and carries tmax
+    empty = B.B200Backend()
+    empty.set_materials(scenes.material())
+    empty.synchronize()
+    rays = scenes.random_rays(100)
+    h = empty.trace_closest(rays)
+    assert (h["inst"] == -1).all() and (h["prim"] == -1).all() and np.array_equal(h["t"], rays["tmax"])
+    assert (empty.trace_any(rays) == 0).all()
+    # a mesh that was sent without an instance list is not traced (crates/rfw-scene/src/lib.rs:285-292)
+    noinst = B.B200Backend()
+    noinst.set_3d_mesh(0, scenes.soup(100, 0.2))
+    noinst.synchronize()
+    assert (noinst.trace_closest(rays)["inst"] == -1).all()
+    # tracing before synchronize() is an error, not a stale answer
+    gpu.set_3d_mesh(1, scenes.soup(10, 0.1))
+    with pytest.raises(B.RfwError):
+        gpu.trace_closest(rays)
+
+
+def test_soup_200k(B, oracle_mod):
+    desc = scenes.soup_scene(200000, 0.01)
+    gpu, cpu = make_pair(B, oracle_mod, desc)
+    rays = scenes.random_rays(500000)
+    ref = cpu.trace_closest(rays, mode=oracle_mod.MODE_BVH2)
+    assert 0.5 < (ref["inst"] >= 0).mean() < 0.99
+    hits = gpu.trace_closest(rays)
+    nbad = parity.compare_hits(rays, hits, ref, parity.lookup_from_desc(desc), "soup200k")
+    occ = gpu.trace_any(rays)
+    ref_occ = cpu.trace_any(rays, mode=oracle_mod.MODE_BVH2)
+    assert (occ != ref_occ).sum() <= max(2, nbad + 2)
+    # short rays exercise the tmax bound of the any-hit form (shadow rays)
+    short = rays.copy()
+    short["tmax"] = 0.05
+    short["tmin"] = 1e-3
+    assert ((gpu.trace_any(short) != 0) != (cpu.trace_any(short, mode=oracle_mod.MODE_BVH2) != 0)).sum() <= 2
+    hs = gpu.trace_closest(short)
+    parity.compare_hits(short, hs, cpu.trace_closest(short, mode=oracle_mod.MODE_BVH2), parity.lookup_from_desc(desc), "short")
+
+
+def test_instanced_two_level(B, oracle_mod):
+    desc = scenes.instanced_scene(grid=12, subdiv=2, n_lights=4)
+    gpu, cpu = make_pair(B, oracle_mod, desc)
+    rays = scenes.random_rays(300000, lo=-7.0, hi=7.0)
+    rays["origin"][:, 1] = np.abs(rays["origin"][:, 1]) * 0.3 + 0.05
+    ref = cpu.trace_closest(rays)
+    assert (ref["inst"] >= 0).mean() > 0.3
+    for variant in (0, 1):
+        gpu.set_option("trace_variant", variant)
+        hits = gpu.trace_closest(rays)
+        parity.compare_hits(rays, hits, ref, parity.lookup_from_desc(desc), f"instanced/v{variant}")
+        assert (gpu.trace_any(rays) != cpu.trace_any(rays)).sum() <= 3
+    st = gpu.build_stats()
+    assert st["num_instances"] == 144 + 1 + 4 and st["tlas_nodes"] >= 1
+    # removed instance: all-zero matrix keeps its slot and is never hit (instances_3d.rs:79-86)
+    m0 = desc.instances[0].copy()
+    m0[1] = 0.0
+    gpu.set_3d_instances(0, m0); gpu.synchronize()
+    cpu.set_3d_instances(0, m0); cpu.synchronize()
+    desc2 = scenes.SceneDesc(); desc2.meshes = desc.meshes; desc2.instances = dict(desc.instances); desc2.instances[0] = m0
+    hits = gpu.trace_closest(rays)
+    parity.compare_hits(rays, hits, cpu.trace_closest(rays), parity.lookup_from_desc(desc2), "removed")
+    assert not np.any(hits["inst"] == 1)
+    # unload a mesh: its instances disappear, the slot can be reused by another mesh (collections.rs:87-107)
+    gpu.unload_3d_meshes([3]); cpu.unload_3d_meshes([3])
+    gpu.set_3d_mesh(3, desc.meshes[8]); cpu.set_3d_mesh(3, desc.meshes[8])  # the ground quad in slot 3
+    lift = scenes.to_column_major([scenes.trs((0, 2.0, 0))])
+    gpu.set_3d_instances(3, lift); cpu.set_3d_instances(3, lift)
+    gpu.synchronize(); cpu.synchronize()
+    desc3 = scenes.SceneDesc(); desc3.meshes = dict(desc.meshes); desc3.meshes[3] = desc.meshes[8]
+    desc3.instances = dict(desc2.instances); desc3.instances[3] = lift
+    parity.compare_hits(rays, gpu.trace_closest(rays), cpu.trace_closest(rays), parity.lookup_from_desc(desc3), "reused-slot")
+
+
+def test_single_transformed_instance(B, oracle_mod):
+    desc = scenes.soup_scene(5000, 0.05)
+    desc.instances[0] = scenes.to_column_major([scenes.trs((0.3, -0.2, 0.1), (1, 2, 3), 0.7, (1.5, 0.7, 1.1))])
+    gpu, cpu = make_pair(B, oracle_mod, desc)
+    rays = scenes.random_rays(100000, lo=-0.5, hi=1.8)
+    parity.compare_hits(rays, gpu.trace_closest(rays), cpu.trace_closest(rays), parity.lookup_from_desc(desc), "single-xform")
+
+
+def test_primary_cast_matches_oracle(B, oracle_mod):
+    desc = scenes.instanced_scene(grid=8, subdiv=2, n_lights=4)
+    w, h = 320, 180
+    gpu, cpu = make_pair(B, oracle_mod, desc, w, h)
+    view = scenes.camera_view((0, 4.0, -9.0), (0, -0.4, 1.0), w, h)
+    rays = cpu.primary_rays(view, w, h)
+    ref = cpu.trace_closest(rays)
+    hits = gpu.cast_primary(view)
+    assert (ref["inst"] >= 0).mean() > 0.5
+    parity.compare_hits(rays, hits, ref, parity.lookup_from_desc(desc), "primary")
+
+
+def test_direction_scaling_and_determinism_property(B):
+    """Size-independent properties at a size the oracle is not needed for: scaling a direction by s scales t by
+    1/s and keeps the primitive; any-hit == closest-hit exists; two runs are bit-identical."""
+    desc = scenes.soup_scene(300000, 0.008)
+    gpu = B.B200Backend(); desc.apply(gpu)
+    rays = scenes.random_rays(1 << 20)
+    h1 = gpu.trace_closest(rays)
+    h2 = gpu.trace_closest(rays)
+    assert np.array_equal(h1.view(np.uint8), h2.view(np.uint8))
+    occ = gpu.trace_any(rays)
+    assert np.array_equal(occ != 0, h1["inst"] >= 0)
+    scaled = rays.copy()
+    scaled["direction"] *= np.float32(4.0)  # exact in float32
+    hs = gpu.trace_closest(scaled)
+    same = (hs["prim"] == h1["prim"])
+    assert same.mean() > 0.99999
+    hit = same & (h1["prim"] >= 0)
+    assert np.allclose(hs["t"][hit] * 4.0, h1["t"][hit], rtol=1e-5)
+    # rebuilding the same scene gives the same acceleration structure (replicated-scene multi-GPU relies on it)
+    cs = gpu.build_stats()["checksum"]
+    gpu2 = B.B200Backend(); desc.apply(gpu2)
+    assert gpu2.build_stats()["checksum"] == cs
+
+
+def test_device_pointer_entry_points_and_counters(B, torch_cuda, oracle_mod):
+    torch = torch_cuda
+    desc = scenes.soup_scene(50000, 0.02)
+    gpu, cpu = make_pair(B, oracle_mod, desc)
+    rays = scenes.random_rays(200000)
+    d_rays = dev_buf(torch, rays)
+    d_hits = torch.empty(len(rays) * 20, dtype=torch.uint8, device="cuda")
+    d_occ = torch.empty(len(rays), dtype=torch.int32, device="cuda")
+    gpu.trace_closest_device(d_rays.data_ptr(), len(rays), d_hits.data_ptr())
+    hits = np.frombuffer(d_hits.cpu().numpy().tobytes(), dtype=wire.HIT)
+    ref = cpu.trace_closest(rays, mode=oracle_mod.MODE_BVH2)
+    parity.compare_hits(rays, hits, ref, parity.lookup_from_desc(desc), "device-ptr")
+    gpu.trace_any_device(d_rays.data_ptr(), len(rays), d_occ.data_ptr())
+    assert np.array_equal(d_occ.cpu().numpy() != 0, hits["inst"] >= 0)
+    st = gpu.trace_closest_counted(d_rays.data_ptr(), len(rays), d_hits.data_ptr())
+    hits2 = np.frombuffer(d_hits.cpu().numpy().tobytes(), dtype=wire.HIT)
+    assert np.array_equal(hits2["prim"], hits["prim"])
+    assert st["rays"] == len(rays) and 1 <= st["nodes_visited"] / len(rays) < 100 and st["tris_tested"] > 0
+    assert gpu.launch_count() > 0
+    # pinned host buffers through the host entry point
+    pr = B.PinnedArray(len(rays), wire.RAY); ph = B.PinnedArray(len(rays), wire.HIT)
+    pr.array[:] = rays
+    gpu.set_option("chunk_rays", 32768)
+    gpu.trace_closest(pr.array, out=ph.array)
+    assert np.array_equal(ph.array["prim"], hits["prim"]) and np.array_equal(ph.array["t"], hits["t"])
+
+
+def render_pair(B, oracle_mod, desc, view, w, h, spp, depth, sky=(0.0, 0.0, 0.0), **kw):
+    gpu = B.B200Backend(w, h, sky=sky, **kw); desc.apply(gpu)
+    cpu = oracle_mod.OracleBackend(det_eps=0.0); desc.apply(cpu)
+    gpu.render_spp(view, spp, depth)
+    acc = gpu.read_accumulator()
+    ref, st = cpu.render(view, w, h, spp, depth, clamp=10.0, sky=sky)
+    return gpu, acc, ref, st
+
+
+def rmse(a, b):
+    return float(np.sqrt(np.mean((a[..., :3].astype(np.float64) - b[..., :3].astype(np.float64)) ** 2)))
+
+
+def test_wavefront_matches_oracle_rmse(B, oracle_mod):
+    """C3 flavour at a size the oracle renders in seconds: instanced spheres (Lambert + GGX metal), area lights,
+    NEE + MIS, depth 5.  Same RNG streams on both sides -> RMSE <= 1e-3 on radiance/spp and on the sqrt image."""
+    desc = scenes.instanced_scene(grid=10, subdiv=2, n_lights=16)
+    w, h, spp, depth = 256, 144, 8, 5
+    view = scenes.camera_view((0, 3.5, -9.0), (0, -0.35, 1.0), w, h)
+    gpu, acc, ref, st = render_pair(B, oracle_mod, desc, view, w, h, spp, depth, sky=(0.3, 0.35, 0.5))
+    a, r = acc / spp, ref / spp
+    assert np.isfinite(a).all() and a.min() >= 0
+    assert r[..., :3].mean() > 0.01
+    e = rmse(a, r)
+    assert e <= 1e-3, f"radiance RMSE {e}"
+    out = gpu.read_output()
+    e2 = rmse(out, np.sqrt(r))
+    assert e2 <= 1e-3, f"image RMSE {e2}"
+    rs = gpu.render_stats()
+    assert rs["samples"] == w * h * spp
+    assert abs(rs["extension_rays"] - st["extension_rays"]) <= 1e-3 * st["extension_rays"]
+    assert abs(rs["shadow_rays"] - st["shadow_rays"]) <= 1e-3 * max(1, st["shadow_rays"])
+    # accumulation continues across calls exactly like sample_count in the reference (src/lib.rs:1731)
+    gpu.render_spp(view, 4, depth)
+    cpu2 = oracle_mod.OracleBackend(); desc.apply(cpu2)
+    ref2, _ = cpu2.render(view, w, h, 4, depth, clamp=10.0, sky=(0.3, 0.35, 0.5), first_sample=spp, acc=ref.copy())
+    assert gpu.sample_count == spp + 4
+    assert rmse(gpu.read_accumulator() / (spp + 4), ref2 / (spp + 4)) <= 1e-3
+
+
+def test_wavefront_soup_with_many_lights(B, oracle_mod):
+    """C4 flavour: soup + 64 emissive triangles, NEE any-hit rays."""
+    desc = scenes.soup_with_lights(20000, 0.03, n_lights=64, light_area=0.05)
+    w, h, spp, depth = 128, 96, 4, 3
+    view = scenes.camera_view((0.5, 0.5, -1.6), (0, 0, 1.0), w, h)
+    gpu, acc, ref, st = render_pair(B, oracle_mod, desc, view, w, h, spp, depth)
+    assert st["shadow_rays"] > 1000 and ref[..., :3].sum() > 0
+    assert rmse(acc / spp, ref / spp) <= 1e-3
+
+
+def test_backend_render_resets_on_camera_change(B):
+    desc = scenes.instanced_scene(grid=4, subdiv=1, n_lights=2)
+    w, h = 64, 48
+    gpu = B.B200Backend(w, h, max_depth=3); desc.apply(gpu)
+    v1 = scenes.camera_view((0, 3.0, -6.0), (0, -0.4, 1.0), w, h)
+    v2 = scenes.camera_view((1, 3.0, -6.0), (0, -0.4, 1.0), w, h)
+    gpu.render(None, v1); gpu.render(None, v1)
+    assert gpu.sample_count == 2
+    gpu.render(None, v2)
+    assert gpu.sample_count == 1  # no reset signal in the trait: restart on changed camera bytes
+    gpu.set_materials(desc.materials); gpu.synchronize()
+    gpu.render(None, v2)
+    assert gpu.sample_count == 1  # scene change restarts too
+    gpu.resize((32, 32))
+    gpu.render(None, scenes.camera_view((0, 3.0, -6.0), (0, -0.4, 1.0), 32, 32))
+    assert gpu.read_output().shape == (32, 32, 4)
+
+
+def test_tile_sharding_is_invariant(B, torch_cuda):
+    """Tile-sharded rendering (tile k in Morton order -> rank k mod n) reproduces the single-rank image exactly:
+    RNG streams are keyed by the global pixel id."""
+    torch = torch_cuda
+    desc = scenes.instanced_scene(grid=6, subdiv=1, n_lights=4)
+    w, h, spp, depth, tile = 200, 120, 2, 4, 32  # not multiples of the tile: ragged edge tiles
+    view = scenes.camera_view((0, 3.0, -7.0), (0, -0.4, 1.0), w, h)
+    single = B.B200Backend(w, h, tile_size=tile); desc.apply(single)
+    single.render_spp(view, spp, depth)
+    ref = single.read_output()
+    world = 3
+    ranks = [B.B200Backend(w, h, tile_size=tile, rank=r, world=world) for r in range(world)]
+    tpr = ranks[0].tiles_per_rank
+    gathered = torch.zeros(world * tpr * tile * tile * 4, dtype=torch.float32, device="cuda")
+    for r, be in enumerate(ranks):
+        desc.apply(be)
+        be.render_spp(view, spp, depth)
+        n = be.export_tiles_device(gathered.data_ptr() + r * tpr * tile * tile * 16, tpr)
+        assert n <= tpr
+    image = torch.zeros(h * w * 4, dtype=torch.float32, device="cuda")
+    ranks[0].assemble_tiles_device(gathered.data_ptr(), tpr, world, image.data_ptr())
+    img = image.cpu().numpy().reshape(h, w, 4)
+    assert np.array_equal(img[..., :3], ref[..., :3])
+    assert sum(be.render_stats()["samples"] for be in ranks) == w * h * spp
