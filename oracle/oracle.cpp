@@ -855,7 +855,9 @@ static void eye_ray(const RfwCameraView3D& c, int w, int h, int sx, int sy, uint
 struct RenderStats { uint64_t samples, extension_rays, shadow_rays, segments; };
 
 // one full path: generate -> (extend -> shade -> connect)^depth.  Returns the radiance to accumulate.
-static V3 trace_path(const Scene& sc, const RfwCameraView3D& cam, int w, int h, int path_id, uint32_t sample, int depth, float clampv, V3 sky, float det_eps, RenderStats& st) {
+static V3 trace_path(const Scene& sc, const RfwCameraView3D& cam, int w, int h, int path_id, uint32_t sample, int depth, float clampv, V3 sky, float det_eps, RenderStats& st,
+                     float* probe = nullptr) {
+    // probe (debug): 20 floats per segment: O(3) D(3) inst prim t u v | next O(3) next D(3) throughput(3)... see orc_path_probe
     V3 acc(0.0f);
     const int lightCount = (int)(sc.area_lights.size() + sc.point_lights.size() + sc.spot_lights.size() + sc.dir_lights.size());
     uint32_t seed = wang_hash((uint32_t)path_id * 16789u + sample * 1791u + 0u * 720898027u);  // ray_gen.comp:54
@@ -866,6 +868,12 @@ static V3 trace_path(const Scene& sc, const RfwCameraView3D& cam, int w, int h, 
     for (int path_length = 0; path_length < depth; path_length++) {
         HitRec hit;
         sc.trace<false>(O, D, 1e-4f, 1e26f, det_eps, MODE_MBVH, hit);  // ray_extend.comp:257-258
+        if (probe) {
+            float* q = probe + 24 * path_length;
+            q[0] = O.x; q[1] = O.y; q[2] = O.z; q[3] = D.x; q[4] = D.y; q[5] = D.z;
+            q[6] = (float)hit.inst; q[7] = (float)hit.prim; q[8] = hit.t; q[9] = hit.u; q[10] = hit.v;
+            q[11] = throughput.x; q[12] = throughput.y; q[13] = throughput.z; q[14] = bsdfPdf; q[15] = 1.0f;
+        }
         st.extension_rays++;
         st.segments++;
         if (hit.inst < 0) {  // shade.comp:90-96
@@ -947,6 +955,10 @@ static V3 trace_path(const Scene& sc, const RfwCameraView3D& cam, int w, int h, 
         O = safe_origin(P, R, gN);  // :263
         D = R;
         bsdfPdf = newPdf;
+        if (probe) {
+            float* q = probe + 24 * path_length;
+            q[16] = O.x; q[17] = O.y; q[18] = O.z; q[19] = D.x; q[20] = D.y; q[21] = D.z; q[22] = acc.x; q[23] = newPdf;
+        }
     }
     st.samples++;
     return acc;
@@ -1058,6 +1070,14 @@ double orc_render(void* s, const RfwCameraView3D* cam, uint32_t w, uint32_t h, u
     double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (stats_out) { stats_out[0] = s_samples; stats_out[1] = s_ext; stats_out[2] = s_sh; stats_out[3] = s_seg; }
     return dt;
+}
+
+// debug: per-segment state of one path (24 floats per segment, zero-filled beyond termination)
+void orc_path_probe(void* s, const RfwCameraView3D* cam, uint32_t w, uint32_t h, uint32_t path_id, uint32_t sample, uint32_t depth, float clampv, const float* sky, float det_eps,
+                    float* out) {
+    RenderStats st = {0, 0, 0, 0};
+    for (uint32_t i = 0; i < depth * 24; i++) out[i] = 0.0f;
+    trace_path(*(Scene*)s, *cam, (int)w, (int)h, (int)path_id, sample, (int)depth, clampv, V3(sky[0], sky[1], sky[2]), det_eps, st, out);
 }
 
 // single MT test for known-answer checks: returns 1 on hit and fills t,u,v

@@ -79,6 +79,7 @@ def load_library():
         "rfwb200_trace_stats": ([vp, vp], i32),
         "rfwb200_render_stats": ([vp, vp], i32),
         "rfwb200_set_option": ([vp, C.c_char_p, C.c_int64], i32),
+        "rfwb200_debug_read_queue": ([vp, u32, vp, vp, vp, vp, u32, vp], i32),
         "rfwb200_host_alloc": ([u64], vp),
         "rfwb200_host_free": ([vp], None),
         "rfwb200_last_error": ([], C.c_char_p),
@@ -310,6 +311,14 @@ class B200Backend:
 
     def set_option(self, key, value):
         self._ck(self.L.rfwb200_set_option(self.h, key.encode(), int(value)), "set_option")
+
+    def debug_read_queue(self, which, capacity):
+        """Debug: (O, D, T, S, count) of wavefront queue `which` after the last render call."""
+        O = np.zeros((capacity, 4), np.float32); D = np.zeros((capacity, 4), np.float32)
+        T = np.zeros((capacity, 4), np.float32); S = np.zeros((capacity, 4), np.float32)
+        n = C.c_uint32(0)
+        self._ck(self.L.rfwb200_debug_read_queue(self.h, which, _ptr(O), _ptr(D), _ptr(T), _ptr(S), capacity, C.addressof(n)), "debug_read_queue")
+        return O, D, T, S, n.value
 
     def launch_count(self):
         return self.L.rfwb200_launch_count(self.h)

@@ -65,6 +65,8 @@ int rfwb200_trace_stats(void* handle, RfwTraceStats* out) { RFW_GUARD(handle); i
 int rfwb200_render_stats(void* handle, RfwRenderStats* out) { RFW_GUARD(handle); if (out) *out = b->render_stats; return RFWB200_OK; }
 int rfwb200_set_option(void* handle, const char* key, int64_t value) { RFW_GUARD(handle); return b->set_option(key, value); }
 
+int rfwb200_debug_read_queue(void* handle, uint32_t which, float* o, float* d, float* t, float* s, uint32_t cap, uint32_t* cnt) { RFW_GUARD(handle); return b->debug_read_queue(which, o, d, t, s, cap, cnt); }
+
 void* rfwb200_host_alloc(uint64_t bytes) {
     void* p = nullptr;
     if (cudaMallocHost(&p, bytes) != cudaSuccess) { rfw::set_last_error("cudaMallocHost failed"); return nullptr; }

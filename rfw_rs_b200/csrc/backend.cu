@@ -294,11 +294,11 @@ int Backend::synchronize() {
             build_stats.bvh_bytes += (uint64_t)m.bvh.num_nodes * 80 + (uint64_t)m.n * 48;
             if (m.bvh.sah > build_stats.sah_cost) build_stats.sah_cost = m.bvh.sah;
             if (m.n) {
-                BK_CUDA(buffer_checksum(bctx, reinterpret_cast<const uint32_t*>(m.bvh.nodes), (size_t)m.bvh.num_nodes * 20, d_counters3), "checksum");
-                BK_CUDA(buffer_checksum(bctx, reinterpret_cast<const uint32_t*>(m.d_ttris), (size_t)m.n * 12, d_counters3), "checksum");
+                BK_CUDA(buffer_checksum(bctx, reinterpret_cast<const uint32_t*>(m.bvh.nodes), 20, m.bvh.num_nodes, 0x30u, d_counters3), "checksum");
+                BK_CUDA(buffer_checksum(bctx, reinterpret_cast<const uint32_t*>(m.d_ttris), 12, m.n, 0u, d_counters3), "checksum");
             }
         }
-        if (tlas.num_nodes) BK_CUDA(buffer_checksum(bctx, reinterpret_cast<const uint32_t*>(tlas.nodes), (size_t)tlas.num_nodes * 20, d_counters3), "checksum");
+        if (tlas.num_nodes) BK_CUDA(buffer_checksum(bctx, reinterpret_cast<const uint32_t*>(tlas.nodes), 20, tlas.num_nodes, 0x30u, d_counters3), "checksum");
         unsigned long long cs = 0;
         BK_CUDA(cudaMemcpyAsync(&cs, d_counters3, 8, cudaMemcpyDeviceToHost, stream), "checksum");
         BK_CUDA(cudaStreamSynchronize(stream), "checksum");
@@ -592,6 +592,24 @@ int Backend::assemble_tiles_device(const float* d_gathered, uint32_t tpr, uint32
     return RFWB200_OK;
 }
 
+int Backend::debug_read_queue(uint32_t which, float* o, float* d, float* t, float* s, uint32_t cap, uint32_t* cnt) {
+    BK_CUDA(cudaSetDevice(cfg.device), "cudaSetDevice");
+    if (which > 3 || !wf.d_counts) return fail(RFWB200_ERR_INVALID, "debug_read_queue: bad queue");
+    BK_CUDA(cudaStreamSynchronize(stream), "sync");
+    uint32_t counts[8];
+    BK_CUDA(cudaMemcpy(counts, wf.d_counts, sizeof(counts), cudaMemcpyDeviceToHost), "counts");
+    // which = 0/1: the live count of that queue; which + 2: the same buffers with the count the last extend/shade consumed
+    const uint32_t live = which < 2 ? counts[which] : counts[5];
+    which &= 1u;
+    const uint32_t n = std::min(std::min(live, cap), wf.max_paths);
+    if (o) BK_CUDA(cudaMemcpy(o, wf.d_O[which], (size_t)n * 16, cudaMemcpyDeviceToHost), "queue");
+    if (d) BK_CUDA(cudaMemcpy(d, wf.d_D[which], (size_t)n * 16, cudaMemcpyDeviceToHost), "queue");
+    if (t) BK_CUDA(cudaMemcpy(t, wf.d_T[which], (size_t)n * 16, cudaMemcpyDeviceToHost), "queue");
+    if (s) BK_CUDA(cudaMemcpy(s, wf.d_S, (size_t)std::min(cap, wf.max_paths) * 16, cudaMemcpyDeviceToHost), "queue");
+    if (cnt) *cnt = live;
+    return RFWB200_OK;
+}
+
 int Backend::set_option(const char* key, int64_t value) {
     if (!key) return fail(RFWB200_ERR_INVALID, "set_option: null key");
     const std::string k(key);
@@ -600,6 +618,7 @@ int Backend::set_option(const char* key, int64_t value) {
     else if (k == "refill_below") tcfg.refill_below = (int)value;
     else if (k == "chunk_rays") chunk_rays = (uint64_t)std::max<int64_t>(1024, value);
     else if (k == "max_depth") cfg.max_depth = (uint32_t)value;
+    else if (k == "sample_count") sample_count = (uint32_t)value;  // debug: render a chosen sample index next
     else return fail(RFWB200_ERR_INVALID, "set_option: unknown key " + k);
     return RFWB200_OK;
 }

@@ -127,13 +127,21 @@ __global__ void __launch_bounds__(TB) k_gather_tris(const RfwRTTriangle* __restr
     out[(size_t)k * 3 + 2] = c;
 }
 
-__global__ void __launch_bounds__(TB) k_checksum(const uint32_t* __restrict__ words, size_t count, unsigned long long* accum) {
+// layout-independent checksum: every record (node / triangle) is hashed on its own (words flagged in skip_mask —
+// the allocation-order dependent child/leaf base indices — are left out) and the record hashes are summed, so two
+// builds of the same scene agree even though their atomics handed out node slots in a different order.
+__global__ void __launch_bounds__(TB) k_checksum(const uint32_t* __restrict__ words, int record_words, size_t n_records, uint32_t skip_mask, unsigned long long* accum) {
     unsigned long long s = 0;
-    for (size_t i = (size_t)blockIdx.x * TB + threadIdx.x; i < count; i += (size_t)gridDim.x * TB) {
-        unsigned long long x = (unsigned long long)words[i] + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
-        x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-        x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-        s += x ^ (x >> 31);
+    for (size_t r = (size_t)blockIdx.x * TB + threadIdx.x; r < n_records; r += (size_t)gridDim.x * TB) {
+        unsigned long long h = 0x243F6A8885A308D3ull;
+        for (int w = 0; w < record_words; w++) {
+            if ((skip_mask >> w) & 1u) continue;
+            unsigned long long x = h ^ ((unsigned long long)words[r * record_words + w] + 0x9E3779B97F4A7C15ull * (unsigned long long)(w + 1));
+            x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+            x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+            h = x ^ (x >> 31);
+        }
+        s += h;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
@@ -174,11 +182,11 @@ cudaError_t gather_traversal_triangles(BuilderContext& ctx, const RfwRTTriangle*
     return cudaGetLastError();
 }
 
-cudaError_t buffer_checksum(BuilderContext& ctx, const uint32_t* words, size_t count, unsigned long long* d_accum) {
-    if (count == 0) return cudaSuccess;
-    int blocks = (int)((count + TB - 1) / TB);
+cudaError_t buffer_checksum(BuilderContext& ctx, const uint32_t* words, int record_words, size_t n_records, uint32_t skip_mask, unsigned long long* d_accum) {
+    if (n_records == 0) return cudaSuccess;
+    int blocks = (int)((n_records + TB - 1) / TB);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    k_checksum<<<blocks, TB, 0, ctx.stream>>>(words, count, d_accum);
+    k_checksum<<<blocks, TB, 0, ctx.stream>>>(words, record_words, n_records, skip_mask, d_accum);
     ctx.launches++;
     return cudaGetLastError();
 }

@@ -45,7 +45,7 @@ cudaError_t build_wide_bvh(BuilderContext& ctx, const float4* prim_lo, const flo
 cudaError_t triangle_boxes(BuilderContext& ctx, const RfwRTTriangle* tris, int n, float4* prim_lo, float4* prim_hi);
 // traversal triangles: out[3k..3k+2] = vertices of tris[leaf_prims[k]], v0.w = prim index bits
 cudaError_t gather_traversal_triangles(BuilderContext& ctx, const RfwRTTriangle* tris, const uint32_t* leaf_prims, int n, float4* out);
-// order-independent checksum of a device buffer of 32-bit words (sum of word * (index+1) mixed)
-cudaError_t buffer_checksum(BuilderContext& ctx, const uint32_t* words, size_t count, unsigned long long* d_accum);
+// layout-independent checksum: sum over records of a hash of each record's words (skip_mask: words left out)
+cudaError_t buffer_checksum(BuilderContext& ctx, const uint32_t* words, int record_words, size_t n_records, uint32_t skip_mask, unsigned long long* d_accum);
 
 }  // namespace rfw

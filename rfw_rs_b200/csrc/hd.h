@@ -63,7 +63,11 @@ RFW_HD int bfind32(uint32_t x) { return 31 - clz32(x); }
 // __byte_perm semantics (PTX prmt default mode, incl. the sign-replicating selectors 8..15)
 RFW_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
 #if defined(__CUDA_ARCH__)
-    return __byte_perm(a, b, sel);
+    // inline PTX: the __byte_perm intrinsic documents only 3 selector bits per nibble; the sign-replicating
+    // selectors (8..15) used by the node test need the generic prmt form
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
 #else
     uint64_t src = ((uint64_t)b << 32) | a;
     uint32_t r = 0;

@@ -88,7 +88,12 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
                         st.sp = 0;
                         ng = make_uint2(0u, 0x80000000u);
                         tg = make_uint2(0u, 0u);
-                        if (TWO_LEVEL) {
+                        if (sv.num_live == 0) {  // empty scene: nothing to traverse, the ray retires as a miss
+                            ng = make_uint2(0u, 0u);
+                            rc.o = xyz(r0); rc.d = xyz(r1);
+                            in_blas = false;
+                            blas_base_sp = 0;
+                        } else if (TWO_LEVEL) {
                             wo = xyz(r0); wd = xyz(r1);
                             rc.o = wo; rc.d = wd;
                             nodes = sv.tlas_nodes;

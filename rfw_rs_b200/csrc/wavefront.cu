@@ -280,6 +280,7 @@ __global__ void k_wf_advance(uint32_t* counts, unsigned long long* stats, int cu
     stats[0] += counts[cur];
     stats[1] += counts[2];
     stats[2] += counts[cur];
+    counts[5] = counts[cur];  // debug: size of the queue the last extend/shade consumed
     counts[cur] = 0;
     counts[2] = 0;
 }

@@ -39,7 +39,7 @@ def _norm(v):
     return v / np.maximum(np.linalg.norm(v, axis=-1, keepdims=True), 1e-30)
 
 
-def make_triangles(v0, v1, v2, mat_id=0, n0=None, n1=None, n2=None):
+def make_triangles(v0, v1, v2, mat_id=0, n0=None, n1=None, n2=None, t0=None, t1=None, t2=None):
     """Fill RTTriangle records the way Mesh3D::new does (objects_3d/mod.rs:331-383): unit geometric
     normal, vertex normals (flat unless given), id = index, Heron area, light_id = -1."""
     v0 = np.asarray(v0, np.float32); v1 = np.asarray(v1, np.float32); v2 = np.asarray(v2, np.float32)
@@ -51,6 +51,8 @@ def make_triangles(v0, v1, v2, mat_id=0, n0=None, n1=None, n2=None):
         v0, v1, v2, cr, ln = v0[keep], v1[keep], v2[keep], cr[keep], ln[keep]
         if n0 is not None:
             n0, n1, n2 = n0[keep], n1[keep], n2[keep]
+        if t0 is not None:
+            t0, t1, t2 = t0[keep], t1[keep], t2[keep]
         if np.ndim(mat_id) > 0:
             mat_id = np.asarray(mat_id)[keep]
         n = v0.shape[0]
@@ -65,8 +67,8 @@ def make_triangles(v0, v1, v2, mat_id=0, n0=None, n1=None, n2=None):
     # tangent: unit vector perpendicular to the normal, w = 1 (objects_3d/mod.rs:256-266)
     ref = np.where(np.abs(normal[:, :1]) > 0.9, np.array([[0, 1, 0]], np.float32), np.array([[1, 0, 0]], np.float32))
     tan = _norm(np.cross(normal, ref)).astype(np.float32)
-    for k in ("tangent0", "tangent1", "tangent2"):
-        t[k][:, :3] = tan
+    for k, tv in (("tangent0", t0), ("tangent1", t1), ("tangent2", t2)):
+        t[k][:, :3] = tan if tv is None else tv  # per-vertex tangents keep shading continuous across shared edges
         t[k][:, 3] = 1.0
     t["light_id"] = -1
     t["mat_id"] = mat_id
@@ -138,7 +140,10 @@ def icosphere(subdiv=3, radius=0.4, mat_id=0):
     f = np.array(faces, np.int64)
     nrm = v.astype(np.float32)
     p = (v * radius).astype(np.float32)
-    return make_triangles(p[f[:, 0]], p[f[:, 1]], p[f[:, 2]], mat_id, nrm[f[:, 0]], nrm[f[:, 1]], nrm[f[:, 2]])
+    # per-vertex tangent = normalize(up x n) (Mesh3D::new derives per-vertex tangents too, objects_3d/mod.rs:256-266)
+    up = np.where(np.abs(v[:, 1:2]) > 0.99, np.array([[1.0, 0.0, 0.0]]), np.array([[0.0, 1.0, 0.0]]))
+    tanv = _norm(np.cross(up, v)).astype(np.float32)
+    return make_triangles(p[f[:, 0]], p[f[:, 1]], p[f[:, 2]], mat_id, nrm[f[:, 0]], nrm[f[:, 1]], nrm[f[:, 2]], tanv[f[:, 0]], tanv[f[:, 1]], tanv[f[:, 2]])
 
 
 def quad(pos, normal, width, height, mat_id=0):

@@ -55,10 +55,20 @@ def compare_hits(rays, gpu, ref, scene_lookup, label=""):
     same = (gpu["inst"] == ref["inst"]) & (gpu["prim"] == ref["prim"])
     hit = same & (ref["inst"] >= 0)
     if hit.any():
-        tol = t_tolerance(rays[hit], ref["t"][hit])
-        err = np.abs(gpu["t"][hit].astype(np.float64) - ref["t"][hit].astype(np.float64))
-        worst = int(np.argmax(err - tol))
-        assert (err <= tol).all(), f"{label}: t err {err[worst]} > tol {tol[worst]} (t={ref['t'][hit][worst]})"
+        idx = np.nonzero(hit)[0]
+        tol = t_tolerance(rays[idx], ref["t"][idx])
+        err = np.abs(gpu["t"][idx].astype(np.float64) - ref["t"][idx].astype(np.float64))
+        # grazing hits: a float32 perturbation of the ray moves t by 1/|cos(theta)| as much as it moves the hit point
+        # off the surface, so for the (few) hits over the plain tolerance the error is measured along the normal
+        for j in np.nonzero(err > tol)[0]:
+            i = idx[j]
+            tris, inv = scene_lookup(int(ref["inst"][i]))
+            v0, v1, v2 = _tri_f64(tris, int(ref["prim"][i]))
+            nrm = np.cross(v1 - v0, v2 - v0)
+            nrm /= np.linalg.norm(nrm)
+            dd = inv[:3, :3] @ rays["direction"][i].astype(np.float64)
+            cos = abs(np.dot(nrm, dd)) / max(np.linalg.norm(dd), 1e-30)
+            assert err[j] * max(cos, 1e-3) <= tol[j], f"{label}: t err {err[j]} (cos {cos}) > tol {tol[j]} (t={ref['t'][i]})"
         assert np.abs(gpu["u"][hit] - ref["u"][hit]).max() <= ABS_UV, f"{label}: u err"
         assert np.abs(gpu["v"][hit] - ref["v"][hit]).max() <= ABS_UV, f"{label}: v err"
     miss = same & (ref["inst"] < 0)
@@ -86,7 +96,11 @@ def compare_hits(rays, gpu, ref, scene_lookup, label=""):
         for c in cand:
             if c is None:
                 continue
-            _, u, v = c
+            tc, u, v = c
+            # a hit within tolerance of the ray interval's own bounds: accepted by one formulation, rejected by the other
+            for bound in (float(rays["tmin"][i]), float(rays["tmax"][i])):
+                if abs(tc - bound) <= REL_T * max(abs(bound), 1e-6):
+                    ok = True
             if min(u, v, 1.0 - u - v) <= EDGE_EPS:
                 ok = True  # edge graze: MT and the watertight test may disagree about inside/outside
         if not ok:
