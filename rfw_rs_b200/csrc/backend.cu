@@ -511,6 +511,7 @@ int Backend::render_spp(const RfwCameraView3D* view, uint32_t spp, uint32_t dept
     ss.n_materials = (uint32_t)materials.size();
     if (materials.empty()) return fail(RFWB200_ERR_INVALID, "render: no materials set");
     wf.refill_below = tcfg.refill_below;
+    wf.tri_batch = tcfg.tri_batch;
     const uint64_t before = wf.launches;
     BK_CUDA(cudaEventRecord(ev0, stream), "event");
     BK_CUDA(wf.render(stream, sv, ss, *view, sample_count, spp, depth), "render");
@@ -616,6 +617,8 @@ int Backend::set_option(const char* key, int64_t value) {
     if (k == "trace_variant") tcfg.variant = (int)value;
     else if (k == "blocks_per_sm") tcfg.blocks_per_sm = (int)value;
     else if (k == "refill_below") tcfg.refill_below = (int)value;
+    else if (k == "tri_batch") tcfg.tri_batch = (int)value;
+    else if (k == "min_blocks") tcfg.min_blocks = (int)value;
     else if (k == "chunk_rays") chunk_rays = (uint64_t)std::max<int64_t>(1024, value);
     else if (k == "max_depth") cfg.max_depth = (uint32_t)value;
     else if (k == "sample_count") sample_count = (uint32_t)value;  // debug: render a chosen sample index next

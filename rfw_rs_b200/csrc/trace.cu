@@ -86,10 +86,23 @@ __global__ void __launch_bounds__(256) k_generate_pinhole(RfwCameraView3D cam, u
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+// MIN_BLOCKS (the register budget / occupancy trade-off) is selectable at run time for tuning sweeps
+template <bool ANY, bool TWO_LEVEL>
+static cudaError_t launch_persistent_dispatch(const TraceConfig& cfg, const SceneView& sv, const RayBufferIO& io, uint32_t n, uint32_t* counter) {
+    const TraceTuning tune{cfg.refill_below, cfg.tri_batch};
+    switch (cfg.min_blocks > 0 ? cfg.min_blocks : (TWO_LEVEL ? 6 : 8)) {
+        case 3: return launch_persistent_mb<RayBufferIO, ANY, TWO_LEVEL, 3>(cfg.stream, cfg.sm_count, cfg.blocks_per_sm, tune, sv, io, n, counter);
+        case 5: return launch_persistent_mb<RayBufferIO, ANY, TWO_LEVEL, 5>(cfg.stream, cfg.sm_count, cfg.blocks_per_sm, tune, sv, io, n, counter);
+        case 6: return launch_persistent_mb<RayBufferIO, ANY, TWO_LEVEL, 6>(cfg.stream, cfg.sm_count, cfg.blocks_per_sm, tune, sv, io, n, counter);
+        case 4: return launch_persistent_mb<RayBufferIO, ANY, TWO_LEVEL, 4>(cfg.stream, cfg.sm_count, cfg.blocks_per_sm, tune, sv, io, n, counter);
+        default: return launch_persistent_mb<RayBufferIO, ANY, TWO_LEVEL, 8>(cfg.stream, cfg.sm_count, cfg.blocks_per_sm, tune, sv, io, n, counter);
+    }
+}
+
 template <bool ANY, bool TWO_LEVEL>
 static cudaError_t launch_persistent(const TraceConfig& cfg, const SceneView& sv, const float4* rays, uint32_t n, RfwHit* hits, uint32_t* occ, uint32_t* counter) {
     RayBufferIO io{rays, n, hits, occ};
-    return launch_persistent_io<RayBufferIO, ANY, TWO_LEVEL>(cfg.stream, cfg.sm_count, cfg.blocks_per_sm, cfg.refill_below, sv, io, n, counter);
+    return launch_persistent_dispatch<ANY, TWO_LEVEL>(cfg, sv, io, n, counter);
 }
 
 cudaError_t trace_closest(const TraceConfig& cfg, const SceneView& sv, const RfwRay* d_rays, uint32_t n, RfwHit* d_hits, uint32_t* d_counter) {

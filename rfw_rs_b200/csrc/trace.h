@@ -15,7 +15,9 @@ struct TraceConfig {
     int sm_count = 148;
     int variant = TRACE_VARIANT_PERSISTENT;
     int blocks_per_sm = 0;   // 0 = as many as fit
-    int refill_below = 20;   // refill idle lanes when fewer than this many lanes of a warp are traversing
+    int refill_below = 28;   // refill idle lanes when fewer than this many lanes of a warp are traversing
+    int tri_batch = 1;       // run the triangle phase when this many lanes have pending leaf triangles
+    int min_blocks = 0;      // __launch_bounds__ min CTAs/SM variant of the persistent kernel (3,4,5,6,8); 0 = tuned default
 };
 
 // all pointers are device pointers; d_counter is one zero-initialisable uint32 work counter

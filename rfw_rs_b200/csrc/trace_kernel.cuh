@@ -4,6 +4,17 @@
 // IO policy:  uint32_t count() const;                         rays in this launch (may read device memory)
 //             void load(uint32_t i, float4& o_tmin, float4& d_tmax) const;
 //             void store_closest(uint32_t i, const Hit&) const;   void store_any(uint32_t i, bool occluded) const;
+//
+// Warp-level schedule (every lane owns one ray; all lanes re-converge once per iteration at the ballots):
+//   refill   lanes without a ray take the next indices of a global counter: ONE atomicAdd per warp
+//            (ballot -> popc -> lane 0 adds -> shfl), done when fewer than `refill_below` lanes are busy
+//   node     lanes with no pending triangles pop the nearest child of their node group (ray-octant order)
+//            and test its 8 quantised child boxes (5 x LDG.128 per visit)
+//   triangle triangle tests are BATCHED: a lane that found leaf triangles parks until at least `tri_batch`
+//            lanes of the warp have some (or nobody can make node progress), then all of them run the
+//            watertight test together — the leaf phase otherwise runs with a handful of live lanes
+//   stack    first SM_STACK entries in shared memory laid out [entry][thread] (bank-conflict free),
+//            overflow in local memory
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -14,32 +25,32 @@ namespace rfw {
 
 static constexpr uint32_t FULL = 0xFFFFFFFFu;
 static constexpr int PT_THREADS = 128;
-static constexpr int PT_MIN_BLOCKS = 4;
 static constexpr int PT_SM_STACK = 12;
 
-// ------------------------------------------------------------------------------------------------
-// persistent kernel
-// ------------------------------------------------------------------------------------------------
 template <int SM_STACK, int L_STACK>
 struct LaneStack {
     uint2* sm;       // &shared[threadIdx.x], stride blockDim.x
-    int stride;
     uint2 local[L_STACK];
     int sp;
-    __device__ __forceinline__ void push(uint2 v) {
+    __device__ __forceinline__ void push(uint2 v, int stride) {
         if (sp < SM_STACK) sm[sp * stride] = v;
         else if (sp - SM_STACK < L_STACK) local[sp - SM_STACK] = v;
         sp++;
     }
-    __device__ __forceinline__ uint2 pop() {
+    __device__ __forceinline__ uint2 pop(int stride) {
         sp--;
         if (sp < SM_STACK) return sm[sp * stride];
         return local[(sp - SM_STACK) < L_STACK ? (sp - SM_STACK) : (L_STACK - 1)];
     }
 };
 
+struct TraceTuning {
+    int refill_below;  // refill when fewer than this many lanes still traverse
+    int tri_batch;     // run the triangle phase when at least this many lanes have pending triangles
+};
+
 template <class IO, bool ANY, bool TWO_LEVEL, int THREADS, int MIN_BLOCKS, int SM_STACK>
-__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneView sv, IO io, uint32_t* __restrict__ counter, int refill_below) {
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneView sv, IO io, uint32_t* __restrict__ counter, TraceTuning tune) {
     extern __shared__ uint2 smem_stack[];
     const uint32_t n = io.count();
     const int lane = threadIdx.x & 31;
@@ -47,14 +58,12 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
 
     LaneStack<SM_STACK, 24> st;
     st.sm = smem_stack + threadIdx.x;
-    st.stride = THREADS;
     st.sp = 0;
 
     bool active = false;
     bool more = true;
     uint32_t ray_idx = 0;
-    // world-space ray (kept only for the two-level variant), current-space context
-    float3 wo = f3(0, 0, 0), wd = f3(0, 0, 0);
+    float3 wo = f3(0, 0, 0), wd = f3(0, 0, 0);  // world-space ray (two-level variant only)
     RayCtx rc;
     rc.o = wo; rc.d = wd; rc.idir = wo; rc.octinv4 = 0; rc.kx = 0; rc.ky = 1; rc.kz = 2; rc.Sx = rc.Sy = rc.Sz = 0.0f;
     float tmin = 0.0f;
@@ -68,7 +77,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
     uint2 ng = make_uint2(0u, 0u), tg = make_uint2(0u, 0u);
 
     for (;;) {
-        // ---- refill idle lanes: one atomicAdd per warp ---------------------------------------------
+        // ---- refill idle lanes: one atomicAdd per warp -------------------------------------------------
         {
             const uint32_t idle = __ballot_sync(FULL, !active);
             if (idle != 0u && more) {
@@ -114,15 +123,31 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
             }
             if (__ballot_sync(FULL, active) == 0u) break;
         }
-        // ---- traverse until too few lanes are busy -------------------------------------------------
+        // ---- traverse until too few lanes are busy -----------------------------------------------------
         for (;;) {
-            if (active) {
+            bool done = false;
+            if (active && tg.y == 0u) {
+                // (a) nothing at hand: pop (leaving the BLAS when its part of the stack is exhausted)
+                if (!RFW_NODE_HITS(ng)) {
+                    if (TWO_LEVEL && in_blas && st.sp == blas_base_sp) {
+                        in_blas = false;
+                        rc.o = wo; rc.d = wd;
+                        ray_setup_box(rc);
+                        nodes = sv.tlas_nodes;
+                    }
+                    if (st.sp == 0) done = true;
+                    else {
+                        ng = st.pop(THREADS);
+                        if (!RFW_NODE_HITS(ng)) { tg = ng; ng = make_uint2(0u, 0u); }  // a parked TLAS leaf group
+                    }
+                }
+                // (b) node step
                 if (RFW_NODE_HITS(ng)) {
                     const uint32_t hits_imask = ng.y;
                     const int bit = 31 - __clz((int)hits_imask);
                     const uint32_t base = ng.x;
                     ng.y &= ~(1u << bit);
-                    if (RFW_NODE_HITS(ng)) st.push(ng);
+                    if (RFW_NODE_HITS(ng)) st.push(ng, THREADS);
                     const uint32_t slot = (uint32_t)(bit - 24) ^ (rc.octinv4 & 7u);
                     const uint32_t rel = __popc(hits_imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
                     const float4* np = nodes + (size_t)(base + rel) * 5;
@@ -132,72 +157,65 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
                     tg.x = __float_as_uint(n1.y);
                     ng.y = (hm & 0xFF000000u) | (__float_as_uint(n0.w) >> 24);
                     tg.y = hm & 0x00FFFFFFu;
-                } else {
-                    tg = ng;
-                    ng = make_uint2(0u, 0u);
                 }
-                bool done = false;
-                while (tg.y != 0u) {
-                    const int tb = 31 - __clz((int)tg.y);
-                    tg.y &= ~(1u << tb);
-                    const uint32_t idx = tg.x + (uint32_t)tb;
-                    if (!TWO_LEVEL || in_blas) {
-                        const float4* tp = tris + (size_t)idx * 3;
+            }
+            // (c) TLAS leaves are entered right away: cheap, and they only produce more node work
+            if (TWO_LEVEL && active && !in_blas && tg.y != 0u) {
+                const int tb = 31 - __clz((int)tg.y);
+                tg.y &= ~(1u << tb);
+                const InstanceRec* rec = sv.instances + __ldg(sv.tlas_refs + tg.x + (uint32_t)tb);
+                if (tg.y != 0u) st.push(tg, THREADS);
+                if (RFW_NODE_HITS(ng)) st.push(ng, THREADS);
+                blas_base_sp = st.sp;
+                in_blas = true;
+                cur_inst = rec->inst_id;
+                xform_ray(*rec, wo, wd, rc.o, rc.d);
+                ray_setup_box(rc);
+                ray_setup_tri(rc);
+                nodes = rec->nodes; tris = rec->tris;
+                ng = make_uint2(0u, 0x80000000u);
+                tg = make_uint2(0u, 0u);
+            }
+            // (d) batched triangle phase
+            const bool pending = active && !done && tg.y != 0u;
+            const uint32_t pend = __ballot_sync(FULL, pending);
+            if (pend != 0u) {
+                const uint32_t can_node = __ballot_sync(FULL, active && !done && !pending);
+                if ((int)__popc(pend) >= tune.tri_batch || can_node == 0u) {
+                    if (pending) {
+                        const int tb = 31 - __clz((int)tg.y);
+                        tg.y &= ~(1u << tb);
+                        const float4* tp = tris + (size_t)(tg.x + (uint32_t)tb) * 3;
                         const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
                         float t, u, v;
                         if (intersect_tri_wt(xyz(a), xyz(b), xyz(c), rc, t, u, v) && t > tmin) {
                             const int prim = (int)__float_as_uint(a.w);
                             if (ANY) {
-                                if (t < hit.t) { done = true; hit.prim = prim; break; }
+                                if (t < hit.t) { done = true; hit.prim = prim; }
                             } else if (closer_hit(t, cur_inst, prim, hit)) {
                                 hit.t = t; hit.u = u; hit.v = v; hit.prim = prim; hit.inst = cur_inst;
                             }
                         }
-                    } else {
-                        const InstanceRec* rec = sv.instances + __ldg(sv.tlas_refs + idx);
-                        if (tg.y != 0u) st.push(tg);
-                        if (RFW_NODE_HITS(ng)) st.push(ng);
-                        blas_base_sp = st.sp;
-                        in_blas = true;
-                        cur_inst = rec->inst_id;
-                        xform_ray(*rec, wo, wd, rc.o, rc.d);
-                        ray_setup_box(rc);
-                        ray_setup_tri(rc);
-                        nodes = rec->nodes; tris = rec->tris;
-                        ng = make_uint2(0u, 0x80000000u);
-                        tg = make_uint2(0u, 0u);
-                        break;
                     }
                 }
-                if (!done && !RFW_NODE_HITS(ng) && tg.y == 0u) {
-                    if (TWO_LEVEL && in_blas && st.sp == blas_base_sp) {
-                        in_blas = false;
-                        rc.o = wo; rc.d = wd;
-                        ray_setup_box(rc);
-                        nodes = sv.tlas_nodes;
-                    }
-                    if (st.sp == 0) done = true;
-                    else ng = st.pop();
-                }
-                if (done) {
-                    if (ANY) io.store_any(ray_idx, hit.prim >= 0);
-                    else io.store_closest(ray_idx, hit);
-                    active = false;
-                }
+            }
+            if (done) {
+                if (ANY) io.store_any(ray_idx, hit.prim >= 0);
+                else io.store_closest(ray_idx, hit);
+                active = false;
             }
             const uint32_t act = __ballot_sync(FULL, active);
             if (act == 0u) break;
-            if (more && (int)__popc(act) < refill_below) break;
+            if (more && (int)__popc(act) < tune.refill_below) break;
         }
     }
 }
 
-
 // launch with a persistent grid: min(SMs * resident CTAs, CTAs needed for `n_hint` rays)
-template <class IO, bool ANY, bool TWO_LEVEL>
-static cudaError_t launch_persistent_io(cudaStream_t stream, int sm_count, int blocks_per_sm_limit, int refill_below, const SceneView& sv, const IO& io, uint32_t n_hint,
+template <class IO, bool ANY, bool TWO_LEVEL, int MIN_BLOCKS>
+static cudaError_t launch_persistent_mb(cudaStream_t stream, int sm_count, int blocks_per_sm_limit, TraceTuning tune, const SceneView& sv, const IO& io, uint32_t n_hint,
                                         uint32_t* counter) {
-    auto kern = k_trace_persistent<IO, ANY, TWO_LEVEL, PT_THREADS, PT_MIN_BLOCKS, PT_SM_STACK>;
+    auto kern = k_trace_persistent<IO, ANY, TWO_LEVEL, PT_THREADS, MIN_BLOCKS, PT_SM_STACK>;
     const size_t smem = (size_t)PT_SM_STACK * PT_THREADS * sizeof(uint2);
     static int bps = 0;  // one static per template instantiation
     if (bps == 0) {
@@ -213,8 +231,20 @@ static cudaError_t launch_persistent_io(cudaStream_t stream, int sm_count, int b
     if (grid < 1) grid = 1;
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
-    kern<<<(int)grid, PT_THREADS, smem, stream>>>(sv, io, counter, refill_below);
+    kern<<<(int)grid, PT_THREADS, smem, stream>>>(sv, io, counter, tune);
     return cudaGetLastError();
+}
+
+#ifndef RFW_PT_MIN_BLOCKS
+#define RFW_PT_MIN_BLOCKS 8
+#endif
+
+template <class IO, bool ANY, bool TWO_LEVEL>
+static cudaError_t launch_persistent_io(cudaStream_t stream, int sm_count, int blocks_per_sm_limit, TraceTuning tune, const SceneView& sv, const IO& io, uint32_t n_hint,
+                                        uint32_t* counter) {
+    // single-level: 64 registers / 32 warps per SM (measured best on C2); the two-level variant carries the world-space
+    // ray and the instance context as well and spills at 64, so it gets 80 registers / 24 warps per SM
+    return launch_persistent_mb<IO, ANY, TWO_LEVEL, (TWO_LEVEL ? 6 : RFW_PT_MIN_BLOCKS)>(stream, sm_count, blocks_per_sm_limit, tune, sv, io, n_hint, counter);
 }
 
 }  // namespace rfw

@@ -58,8 +58,16 @@ struct RayCtx {
     float Sx, Sy, Sz;
 };
 
+RFW_HD float safe_rcp_dir(float d) {
+    // |d| below 2^-80 (incl. exact zeros of axis-parallel rays) is replaced by +-2^-80: with an infinite reciprocal
+    // the quantised slab expression q*(s*idir) + (p-o)*idir turns into inf - inf = NaN for EVERY child, the slab
+    // stops culling and such a ray walks the whole tree.  A huge finite reciprocal keeps the inside/outside sign.
+    const float eps = 8.2718061e-25f;  // 2^-80
+    return 1.0f / (fabsf(d) > eps ? d : copysignf(eps, d));
+}
+
 RFW_HD void ray_setup_box(RayCtx& r) {
-    r.idir = f3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+    r.idir = f3(safe_rcp_dir(r.d.x), safe_rcp_dir(r.d.y), safe_rcp_dir(r.d.z));
     const uint32_t octinv = (r.d.x < 0.0f ? 0u : 4u) | (r.d.y < 0.0f ? 0u : 2u) | (r.d.z < 0.0f ? 0u : 1u);
     r.octinv4 = octinv * 0x01010101u;
 }

@@ -411,13 +411,13 @@ cudaError_t Wavefront::render(cudaStream_t stream, const SceneView& sv, const Sh
             const int cur = b & 1, nxt = cur ^ 1;
             fp.path_length = b;
             ExtendIO eio{d_O[cur], d_D[cur], d_counts + cur, d_S};
-            if (sv.two_level) WF_CK((launch_persistent_io<ExtendIO, false, true>(stream, sm_count, 0, refill_below, sv, eio, max_paths, d_counts + 3)));
-            else WF_CK((launch_persistent_io<ExtendIO, false, false>(stream, sm_count, 0, refill_below, sv, eio, max_paths, d_counts + 3)));
+            if (sv.two_level) WF_CK((launch_persistent_io<ExtendIO, false, true>(stream, sm_count, 0, TraceTuning{refill_below, tri_batch}, sv, eio, max_paths, d_counts + 3)));
+            else WF_CK((launch_persistent_io<ExtendIO, false, false>(stream, sm_count, 0, TraceTuning{refill_below, tri_batch}, sv, eio, max_paths, d_counts + 3)));
             k_wf_shade<<<shade_blocks, 128, 0, stream>>>(fp, ss, d_S, d_O[cur], d_D[cur], d_T[cur], d_O[nxt], d_D[nxt], d_T[nxt], d_shO, d_shD, d_shE,
                                                          reinterpret_cast<float*>(d_accum), d_counts + cur, d_counts + nxt, d_counts + 2);
             ConnectIO cio{d_shO, d_shD, d_shE, d_counts + 2, reinterpret_cast<float*>(d_accum)};
-            if (sv.two_level) WF_CK((launch_persistent_io<ConnectIO, true, true>(stream, sm_count, 0, refill_below, sv, cio, max_paths, d_counts + 4)));
-            else WF_CK((launch_persistent_io<ConnectIO, true, false>(stream, sm_count, 0, refill_below, sv, cio, max_paths, d_counts + 4)));
+            if (sv.two_level) WF_CK((launch_persistent_io<ConnectIO, true, true>(stream, sm_count, 0, TraceTuning{refill_below, tri_batch}, sv, cio, max_paths, d_counts + 4)));
+            else WF_CK((launch_persistent_io<ConnectIO, true, false>(stream, sm_count, 0, TraceTuning{refill_below, tri_batch}, sv, cio, max_paths, d_counts + 4)));
             k_wf_advance<<<1, 1, 0, stream>>>(d_counts, d_stats, cur);
             launches += 4;
         }

@@ -202,6 +202,15 @@ def test_device_pointer_entry_points_and_counters(B, torch_cuda, oracle_mod):
     assert np.array_equal(hits2["prim"], hits["prim"])
     assert st["rays"] == len(rays) and 1 <= st["nodes_visited"] / len(rays) < 100 and st["tris_tested"] > 0
     assert gpu.launch_count() > 0
+    # axis-parallel rays (exact zero direction components) must still be culled by the slabs of the zero axes:
+    # parity with the oracle AND a bounded node count (a NaN-poisoned slab test would walk the whole tree)
+    ax = scenes.random_rays(3072, start=5)
+    ax["direction"] = np.tile(np.array([[0, 0, 1], [0, -1, 0], [1, 0, 0]], np.float32), (1024, 1))
+    d_ax = dev_buf(torch, ax)
+    st_ax = gpu.trace_closest_counted(d_ax.data_ptr(), len(ax), d_hits.data_ptr())
+    hits_ax = np.frombuffer(d_hits.cpu().numpy().tobytes(), dtype=wire.HIT)[: len(ax)]
+    parity.compare_hits(ax, hits_ax, cpu.trace_closest(ax, mode=oracle_mod.MODE_BVH2), parity.lookup_from_desc(desc), "axis-parallel")
+    assert st_ax["nodes_visited"] / len(ax) < 4 * st["nodes_visited"] / len(rays)
     # pinned host buffers through the host entry point
     pr = B.PinnedArray(len(rays), wire.RAY); ph = B.PinnedArray(len(rays), wire.HIT)
     pr.array[:] = rays
