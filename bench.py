@@ -36,6 +36,15 @@ BYTES_PER_RAY_CLOSEST = 52
 CPU_SAMPLE_RAYS = 1 << 20
 
 
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed ncu capture."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        return float(json.load(open(p))["traffic_bytes_per_launch"]) / 1e9
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -314,7 +323,8 @@ def main():
                     "note": "rfwb200_trace_closest with pinned host buffers; chunked H2D / kernel / D2H pipeline on 3 streams; wall clock, max over ranks"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic(), "traffic_unit": "GB per launch (ncu dram__bytes_read+write, profiles/r1_traffic.json)",
+                         "algorithmic_GB_per_launch": BYTES_PER_RAY_CLOSEST * N_RAYS / 1e9,
                          "kernel": "k_trace_persistent<RayBufferIO, closest, single-level>", "algorithmic_bytes_per_ray": BYTES_PER_RAY_CLOSEST, "peak_source": peak_src,
                          "note": "pointer-chasing traversal over an L2-resident BVH: the HBM fraction is small by construction (SURVEY 8d); see extra.traversal_bytes_per_ray for the L2-side traffic"},
             "cpu_baseline": {"value": cpu_rate, "unit": "Mrays/s", "cores": cores, "kind": "port",

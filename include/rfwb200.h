@@ -374,6 +374,9 @@ RFWB200_API int rfwb200_export_tiles_device(void* handle, float* d_out, uint32_t
 /* rank-0 side: scatter a gathered tile-major buffer (world * tiles_per_rank tiles) back to a row-major
  * width*height*4 DEVICE image and apply sqrt(acc/spp) */
 RFWB200_API int rfwb200_assemble_tiles_device(void* handle, const float* d_gathered, uint32_t tiles_per_rank, uint32_t world, float* d_image);
+/* host-only, needs no device: all tile ids of the width x height framebuffer in Morton order.  Entry k belongs to rank
+ * k % world and is that rank's tile number k / world (the layout export/assemble use).  Returns the tile count. */
+RFWB200_API uint32_t rfwb200_tile_layout(uint32_t width, uint32_t height, uint32_t tile, uint32_t* out_morton_tiles, uint32_t capacity);
 RFWB200_API uint32_t rfwb200_sample_count(void* handle);
 RFWB200_API uint32_t rfwb200_tiles_per_rank(void* handle);
 

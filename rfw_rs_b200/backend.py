@@ -80,6 +80,7 @@ def load_library():
         "rfwb200_render_stats": ([vp, vp], i32),
         "rfwb200_set_option": ([vp, C.c_char_p, C.c_int64], i32),
         "rfwb200_debug_read_queue": ([vp, u32, vp, vp, vp, vp, u32, vp], i32),
+        "rfwb200_tile_layout": ([u32, u32, u32, vp, u32], u32),
         "rfwb200_host_alloc": ([u64], vp),
         "rfwb200_host_free": ([vp], None),
         "rfwb200_last_error": ([], C.c_char_p),

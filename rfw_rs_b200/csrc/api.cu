@@ -67,6 +67,16 @@ int rfwb200_set_option(void* handle, const char* key, int64_t value) { RFW_GUARD
 
 int rfwb200_debug_read_queue(void* handle, uint32_t which, float* o, float* d, float* t, float* s, uint32_t cap, uint32_t* cnt) { RFW_GUARD(handle); return b->debug_read_queue(which, o, d, t, s, cap, cnt); }
 
+// host-only (no device needed): the tile -> rank layout the multi-GPU sharding uses
+uint32_t rfwb200_tile_layout(uint32_t width, uint32_t height, uint32_t tile, uint32_t* out_morton_tiles, uint32_t capacity) {
+    if (tile == 0) tile = 64;
+    const uint32_t tx = (width + tile - 1) / tile, ty = (height + tile - 1) / tile;
+    const std::vector<uint32_t> order = rfw::morton_tile_order(tx, ty);
+    if (out_morton_tiles)
+        for (uint32_t i = 0; i < order.size() && i < capacity; i++) out_morton_tiles[i] = order[i];
+    return (uint32_t)order.size();
+}
+
 void* rfwb200_host_alloc(uint64_t bytes) {
     void* p = nullptr;
     if (cudaMallocHost(&p, bytes) != cudaSuccess) { rfw::set_last_error("cudaMallocHost failed"); return nullptr; }

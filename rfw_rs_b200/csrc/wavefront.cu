@@ -334,6 +334,15 @@ static uint32_t morton2(uint32_t x, uint32_t y) {
     return part(x) | (part(y) << 1);
 }
 
+// all tile ids of a tiles_x x tiles_y grid in Morton order (host logic of the multi-GPU sharding: tile k of this
+// list belongs to rank k mod world and is that rank's tile number k / world)
+std::vector<uint32_t> morton_tile_order(uint32_t tiles_x, uint32_t tiles_y) {
+    std::vector<uint32_t> order(tiles_x * tiles_y);
+    for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [tiles_x](uint32_t a, uint32_t b) { return morton2(a % tiles_x, a / tiles_x) < morton2(b % tiles_x, b / tiles_x); });
+    return order;
+}
+
 void Wavefront::release() {
     auto fr = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
     fr(d_owned_tiles); fr(d_morton_tiles);
@@ -347,10 +356,7 @@ cudaError_t Wavefront::configure(uint32_t w, uint32_t h, uint32_t tile_size, uin
     width = w; height = h; tile = tile_size ? tile_size : 64; rank = rank_; world = world_ ? world_ : 1;
     tiles_x = (w + tile - 1) / tile; tiles_y = (h + tile - 1) / tile;
     const uint32_t n_tiles = tiles_x * tiles_y;
-    morton_tiles.resize(n_tiles);
-    for (uint32_t i = 0; i < n_tiles; i++) morton_tiles[i] = i;
-    const uint32_t tx = tiles_x;
-    std::stable_sort(morton_tiles.begin(), morton_tiles.end(), [tx](uint32_t a, uint32_t b) { return morton2(a % tx, a / tx) < morton2(b % tx, b / tx); });
+    morton_tiles = morton_tile_order(tiles_x, tiles_y);
     std::vector<uint32_t> owned;
     for (uint32_t r = rank; r < n_tiles; r += world) owned.push_back(morton_tiles[r]);  // tile k (Morton order) -> rank k mod n
     n_owned_tiles = (uint32_t)owned.size();

@@ -33,6 +33,8 @@ struct ShadeScene {
     uint32_t n_materials;
 };
 
+std::vector<uint32_t> morton_tile_order(uint32_t tiles_x, uint32_t tiles_y);
+
 struct Wavefront {
     uint32_t width = 0, height = 0;
     uint32_t tile = 64, rank = 0, world = 1;
