@@ -101,10 +101,20 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which must not throttle the CPU arm)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_port_rate(desc, rays, threads=0):
     """The CPU oracle (BVH2 traversal: the faster of its two modes) on a bounded sample; returns Mrays/s."""
     from oracle import oracle as orc
 
+    if threads <= 0:
+        threads = host_threads()
     o = orc.OracleBackend(det_eps=0.0, threads=threads)
     desc.apply(o)
     best = None
@@ -124,7 +134,7 @@ def run_reference(args):
     rays = scenes.random_rays(CPU_SAMPLE_RAYS)
     from oracle import oracle as orc
 
-    o = orc.OracleBackend(det_eps=0.0)
+    o = orc.OracleBackend(det_eps=0.0, threads=host_threads())
     desc.apply(o)
     for _ in range(args.warmup):
         o.trace_closest(rays[: 1 << 16], mode=orc.MODE_BVH2)
@@ -138,7 +148,7 @@ def run_reference(args):
         "impl": "reference", "metric": "Mrays/s closest-hit (incoherent)", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": {"workload": "C2: 1M-triangle random soup, 2^24 incoherent rays, closest hit", "triangles": N_TRIS, "rays_per_step": len(rays)},
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": o.max_threads(), "kind": "port", "sample": sample, "bvh_build_s": o.build_seconds},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": host_threads(), "kind": "port", "sample": sample, "bvh_build_s": o.build_seconds},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -148,14 +158,23 @@ def path_tracing_extra(backend_mod, scenes, torch, rank, world, spp, dist):
     """C3: 10k-instance scene, 1920x1080, `spp` spp, depth 5 — tile-sharded over the ranks; the final accumulator
     gather is one NCCL all_gather of tile-major buffers."""
     w, h, depth, tile = 1920, 1080, 5, 64
-    desc = scenes.instanced_scene(grid=100, subdiv=3, n_lights=16)
-    be = backend_mod.B200Backend(w, h, tile_size=tile, rank=rank, world=world, sky=(0.3, 0.35, 0.5))
-    desc.apply(be)
-    view = scenes.camera_view((0.0, 14.0, -62.0), (0.0, -0.25, 1.0), w, h)
-    be.render_spp(view, 1, depth)  # warm-up frame
-    be.reset_accumulator()
+    err = None
+    be = None
+    rs = {"render_ms": 0.0, "samples": 0, "extension_rays": 0, "shadow_rays": 0}
+    try:  # the rank-local part first; a failure here must not leave the other ranks waiting in a collective
+        desc = scenes.instanced_scene(grid=100, subdiv=3, n_lights=16)
+        be = backend_mod.B200Backend(w, h, device=torch.cuda.current_device(), tile_size=tile, rank=rank, world=world, sky=(0.3, 0.35, 0.5))
+        desc.apply(be)
+        view = scenes.camera_view((0.0, 14.0, -62.0), (0.0, -0.25, 1.0), w, h)
+        be.render_spp(view, 1, depth)  # warm-up frame
+        be.reset_accumulator()
+    except Exception as ex:
+        err = repr(ex)
+    ok = torch.tensor([0 if err else 1], device="cuda", dtype=torch.int32)
     if dist is not None:
-        dist.barrier()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if ok.item() == 0:
+        return {"error": err or "another rank failed"}
     torch.cuda.synchronize()
     be.render_spp(view, spp, depth)
     rs = be.render_stats()
@@ -163,20 +182,15 @@ def path_tracing_extra(backend_mod, scenes, torch, rank, world, spp, dist):
     tot = torch.tensor([float(rs["samples"]), float(rs["extension_rays"]), float(rs["shadow_rays"])], device="cuda", dtype=torch.float64)
     gather_ms = 0.0
     if dist is not None:
+        from rfw_rs_b200 import sharding
+
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot)
-        tpr = be.tiles_per_rank
-        send = torch.zeros(tpr * tile * tile * 4, dtype=torch.float32, device="cuda")
-        recv = torch.empty(world * tpr * tile * tile * 4, dtype=torch.float32, device="cuda")
-        image = torch.empty(h * w * 4, dtype=torch.float32, device="cuda")
-        be.export_tiles_device(send.data_ptr(), tpr)
-        dist.all_gather_into_tensor(recv, send)  # warm-up of the communicator
+        sharding.gather_image(be, dist, torch, w, h, tile, world)  # warm-up of the communicator and the buffers
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
-        be.export_tiles_device(send.data_ptr(), tpr)
-        dist.all_gather_into_tensor(recv, send)
-        be.assemble_tiles_device(recv.data_ptr(), tpr, world, image.data_ptr())
+        sharding.gather_image(be, dist, torch, w, h, tile, world)  # export tiles -> ONE all_gather -> assemble + sqrt(acc/spp)
         e1.record()
         torch.cuda.synchronize()
         gather_ms = e0.elapsed_time(e1)
@@ -219,7 +233,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=240))
 
     # ---- scene (replicated) and this rank's rays -------------------------------------------------------
     desc = scenes.soup_scene(N_TRIS, SOUP_S)

@@ -30,6 +30,20 @@ int Backend::cuda_fail(cudaError_t e, const char* what) {
         if (e_ != cudaSuccess) return cuda_fail(e_, what); \
     } while (0)
 
+// Calls may arrive on any thread (rfw/src/ecs/mod.rs:35-37) and the caller may be using another device (torch in a
+// multi-GPU process): select the backend's device for the duration of the call and put the caller's device back.
+struct DeviceScope {
+    int prev = -1;
+    cudaError_t status;
+    explicit DeviceScope(int dev) {
+        cudaGetDevice(&prev);
+        status = cudaSetDevice(dev);
+    }
+    ~DeviceScope() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 Backend::Backend(const RfwB200Config& c) : cfg(c) {
     if (cfg.max_depth == 0) cfg.max_depth = 3;  // reference host loop: 3 segments (backends/gpu-rt/src/lib.rs:1708)
     if (cfg.clamp_value <= 0.0f) cfg.clamp_value = 10.0f;
@@ -42,7 +56,8 @@ int Backend::init() {
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) return fail(RFWB200_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
     if (cfg.device < 0 || cfg.device >= count) return fail(RFWB200_ERR_INVALID, "device ordinal out of range");
-    BK_CUDA(cudaSetDevice(cfg.device), "cudaSetDevice");
+    DeviceScope device_scope(cfg.device);
+    BK_CUDA(device_scope.status, "cudaSetDevice");
     cudaDeviceProp prop;
     BK_CUDA(cudaGetDeviceProperties(&prop, cfg.device), "cudaGetDeviceProperties");
     if (prop.major < 10) return fail(RFWB200_ERR_NO_DEVICE, "librfwb200 is built for sm_100a only; found compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor));
@@ -65,7 +80,7 @@ int Backend::init() {
 }
 
 Backend::~Backend() {
-    cudaSetDevice(cfg.device);
+    DeviceScope device_scope(cfg.device);
     if (stream) cudaStreamSynchronize(stream);
     for (auto& m : meshes) {
         if (m.d_tris) cudaFree(m.d_tris);
@@ -91,7 +106,8 @@ Backend::~Backend() {
 int Backend::set_3d_mesh(uint32_t id, const RfwMeshData3D* data) {
     if (!data) return fail(RFWB200_ERR_INVALID, "set_3d_mesh: null data");
     if (data->num_triangles && !data->triangles) return fail(RFWB200_ERR_INVALID, "set_3d_mesh: null triangles");
-    BK_CUDA(cudaSetDevice(cfg.device), "cudaSetDevice");
+    DeviceScope device_scope(cfg.device);
+    BK_CUDA(device_scope.status, "cudaSetDevice");
     if (id >= meshes.size()) meshes.resize(id + 1);
     MeshRec& m = meshes[id];
     BK_CUDA(cudaStreamSynchronize(stream), "sync");
@@ -111,7 +127,8 @@ int Backend::set_3d_mesh(uint32_t id, const RfwMeshData3D* data) {
 }
 
 int Backend::unload_3d_meshes(const uint32_t* ids, uint32_t num) {
-    BK_CUDA(cudaSetDevice(cfg.device), "cudaSetDevice");
+    DeviceScope device_scope(cfg.device);
+    BK_CUDA(device_scope.status, "cudaSetDevice");
     BK_CUDA(cudaStreamSynchronize(stream), "sync");
     for (uint32_t i = 0; i < num; i++) {
         const uint32_t id = ids[i];
@@ -182,7 +199,8 @@ static bool invert_affine(const float* m, float4& r0, float4& r1, float4& r2, fl
 }
 
 int Backend::synchronize() {
-    BK_CUDA(cudaSetDevice(cfg.device), "cudaSetDevice");
+    DeviceScope device_scope(cfg.device);
+    BK_CUDA(device_scope.status, "cudaSetDevice");
     float blas_ms = 0.0f, tlas_ms = 0.0f;
     if (scene_dirty) {
         // ---- BLAS for dirty meshes ------------------------------------------------------------------
@@ -336,7 +354,8 @@ int Backend::ensure_synchronized(const char* who) {
 }
 
 int Backend::resize(uint32_t w, uint32_t h) {
-    BK_CUDA(cudaSetDevice(cfg.device), "cudaSetDevice");
+    DeviceScope device_scope(cfg.device);
+    BK_CUDA(device_scope.status, "cudaSetDevice");
     BK_CUDA(cudaStreamSynchronize(stream), "sync");
     cfg.width = w; cfg.height = h;
     BK_CUDA(wf.configure(w, h, cfg.tile_size, cfg.rank, cfg.world), "framebuffer");
@@ -347,7 +366,8 @@ int Backend::resize(uint32_t w, uint32_t h) {
 
 // ---- ray casting ---------------------------------------------------------------------------------------
 int Backend::trace_closest_device(const RfwRay* d_r, uint64_t num, RfwHit* d_h, int sync) {
-    BK_CUDA(cudaSetDevice(cfg.device), "cudaSetDevice");
+    DeviceScope device_scope(cfg.device);
+    BK_CUDA(device_scope.status, "cudaSetDevice");
     if (int rc = ensure_synchronized("trace_closest")) return rc;
     BK_CUDA(cudaEventRecord(ev0, stream), "event");
     for (uint64_t off = 0; off < num; off += (1ull << 30)) {
@@ -366,7 +386,8 @@ int Backend::trace_closest_device(const RfwRay* d_r, uint64_t num, RfwHit* d_h, 
 }
 
 int Backend::trace_any_device(const RfwRay* d_r, uint64_t num, uint32_t* d_o, int sync) {
-    BK_CUDA(cudaSetDevice(cfg.device), "cudaSetDevice");
+    DeviceScope device_scope(cfg.device);
+    BK_CUDA(device_scope.status, "cudaSetDevice");
     if (int rc = ensure_synchronized("trace_any")) return rc;
     BK_CUDA(cudaEventRecord(ev0, stream), "event");
     for (uint64_t off = 0; off < num; off += (1ull << 30)) {
@@ -385,7 +406,8 @@ int Backend::trace_any_device(const RfwRay* d_r, uint64_t num, uint32_t* d_o, in
 }
 
 int Backend::trace_closest_counted(const RfwRay* d_r, uint64_t num, RfwHit* d_h, RfwTraceStats* out) {
-    BK_CUDA(cudaSetDevice(cfg.device), "cudaSetDevice");
+    DeviceScope device_scope(cfg.device);
+    BK_CUDA(device_scope.status, "cudaSetDevice");
     if (int rc = ensure_synchronized("trace_closest_counted")) return rc;
     if (num > (1ull << 30)) return fail(RFWB200_ERR_INVALID, "trace_closest_counted: at most 2^30 rays");
     BK_CUDA(cudaMemsetAsync(d_counters3, 0, 24, stream), "counters");
@@ -435,7 +457,8 @@ static cudaError_t pipelined(cudaStream_t compute, cudaStream_t in, cudaStream_t
 }
 
 int Backend::trace_closest_host(const RfwRay* rays, uint64_t num, RfwHit* out) {
-    BK_CUDA(cudaSetDevice(cfg.device), "cudaSetDevice");
+    DeviceScope device_scope(cfg.device);
+    BK_CUDA(device_scope.status, "cudaSetDevice");
     if (int rc = ensure_synchronized("trace_closest")) return rc;
     if (num == 0) return RFWB200_OK;
     if (!rays || !out) return fail(RFWB200_ERR_INVALID, "trace_closest: null buffer");
@@ -456,7 +479,8 @@ int Backend::trace_closest_host(const RfwRay* rays, uint64_t num, RfwHit* out) {
 }
 
 int Backend::trace_any_host(const RfwRay* rays, uint64_t num, uint32_t* out) {
-    BK_CUDA(cudaSetDevice(cfg.device), "cudaSetDevice");
+    DeviceScope device_scope(cfg.device);
+    BK_CUDA(device_scope.status, "cudaSetDevice");
     if (int rc = ensure_synchronized("trace_any")) return rc;
     if (num == 0) return RFWB200_OK;
     if (!rays || !out) return fail(RFWB200_ERR_INVALID, "trace_any: null buffer");
@@ -477,7 +501,8 @@ int Backend::trace_any_host(const RfwRay* rays, uint64_t num, uint32_t* out) {
 }
 
 int Backend::cast_primary(const RfwCameraView3D* view, RfwHit* out_hits) {
-    BK_CUDA(cudaSetDevice(cfg.device), "cudaSetDevice");
+    DeviceScope device_scope(cfg.device);
+    BK_CUDA(device_scope.status, "cudaSetDevice");
     if (int rc = ensure_synchronized("cast_primary")) return rc;
     if (!view || !out_hits) return fail(RFWB200_ERR_INVALID, "cast_primary: null argument");
     const uint64_t n = (uint64_t)cfg.width * cfg.height;
@@ -499,7 +524,8 @@ int Backend::cast_primary(const RfwCameraView3D* view, RfwHit* out_hits) {
 
 // ---- rendering ---------------------------------------------------------------------------------------------
 int Backend::render_spp(const RfwCameraView3D* view, uint32_t spp, uint32_t depth) {
-    BK_CUDA(cudaSetDevice(cfg.device), "cudaSetDevice");
+    DeviceScope device_scope(cfg.device);
+    BK_CUDA(device_scope.status, "cudaSetDevice");
     if (int rc = ensure_synchronized("render")) return rc;
     if (!view) return fail(RFWB200_ERR_INVALID, "render: null view");
     if (wf.width == 0 || wf.height == 0) return fail(RFWB200_ERR_INVALID, "render: zero-sized framebuffer");
@@ -549,14 +575,16 @@ int Backend::render(const RfwCameraView3D* view, uint32_t mode) {
 }
 
 int Backend::reset_accumulator() {
-    BK_CUDA(cudaSetDevice(cfg.device), "cudaSetDevice");
+    DeviceScope device_scope(cfg.device);
+    BK_CUDA(device_scope.status, "cudaSetDevice");
     BK_CUDA(wf.clear(stream), "clear");
     sample_count = 0;
     return RFWB200_OK;
 }
 
 int Backend::read_accumulator(float* out) {
-    BK_CUDA(cudaSetDevice(cfg.device), "cudaSetDevice");
+    DeviceScope device_scope(cfg.device);
+    BK_CUDA(device_scope.status, "cudaSetDevice");
     if (!out || !wf.d_accum) return fail(RFWB200_ERR_INVALID, "read_accumulator: no framebuffer");
     BK_CUDA(cudaMemcpyAsync(out, wf.d_accum, (size_t)wf.width * wf.height * sizeof(float4), cudaMemcpyDeviceToHost, stream), "download");
     BK_CUDA(cudaStreamSynchronize(stream), "download");
@@ -564,7 +592,8 @@ int Backend::read_accumulator(float* out) {
 }
 
 int Backend::read_output(float* out) {
-    BK_CUDA(cudaSetDevice(cfg.device), "cudaSetDevice");
+    DeviceScope device_scope(cfg.device);
+    BK_CUDA(device_scope.status, "cudaSetDevice");
     if (!out || !wf.d_output) return fail(RFWB200_ERR_INVALID, "read_output: no framebuffer");
     BK_CUDA(cudaMemcpyAsync(out, wf.d_output, (size_t)wf.width * wf.height * sizeof(float4), cudaMemcpyDeviceToHost, stream), "download");
     BK_CUDA(cudaStreamSynchronize(stream), "download");
@@ -574,7 +603,8 @@ int Backend::read_output(float* out) {
 uint32_t Backend::tiles_per_rank() const { return wf.tiles_per_rank; }
 
 int Backend::export_tiles_device(float* d_out, uint32_t capacity_tiles, uint32_t* out_tiles) {
-    BK_CUDA(cudaSetDevice(cfg.device), "cudaSetDevice");
+    DeviceScope device_scope(cfg.device);
+    BK_CUDA(device_scope.status, "cudaSetDevice");
     if (!d_out) return fail(RFWB200_ERR_INVALID, "export_tiles: null buffer");
     if (capacity_tiles < wf.n_owned_tiles) return fail(RFWB200_ERR_INVALID, "export_tiles: buffer too small");
     BK_CUDA(wf.export_tiles(stream, d_out), "export_tiles");
@@ -585,7 +615,8 @@ int Backend::export_tiles_device(float* d_out, uint32_t capacity_tiles, uint32_t
 }
 
 int Backend::assemble_tiles_device(const float* d_gathered, uint32_t tpr, uint32_t world, float* d_image) {
-    BK_CUDA(cudaSetDevice(cfg.device), "cudaSetDevice");
+    DeviceScope device_scope(cfg.device);
+    BK_CUDA(device_scope.status, "cudaSetDevice");
     if (!d_gathered || !d_image) return fail(RFWB200_ERR_INVALID, "assemble_tiles: null buffer");
     BK_CUDA(wf.assemble(stream, d_gathered, tpr, world, sample_count, d_image), "assemble_tiles");
     BK_CUDA(cudaStreamSynchronize(stream), "assemble_tiles");
@@ -594,7 +625,8 @@ int Backend::assemble_tiles_device(const float* d_gathered, uint32_t tpr, uint32
 }
 
 int Backend::debug_read_queue(uint32_t which, float* o, float* d, float* t, float* s, uint32_t cap, uint32_t* cnt) {
-    BK_CUDA(cudaSetDevice(cfg.device), "cudaSetDevice");
+    DeviceScope device_scope(cfg.device);
+    BK_CUDA(device_scope.status, "cudaSetDevice");
     if (which > 3 || !wf.d_counts) return fail(RFWB200_ERR_INVALID, "debug_read_queue: bad queue");
     BK_CUDA(cudaStreamSynchronize(stream), "sync");
     uint32_t counts[8];
