@@ -1,0 +1,87 @@
+"""Config C1 (BASELINE.json configs[0]): primary-ray closest-hit casting of the reference's glTF assets at 1280x720.
+Geometry comes from the committed fixtures tests/golden/{cesium_man,pica}.npz (made from /root/reference/assets by
+tests/golden/make_c1_fixtures.py; the GPU box has no /root/reference).  CPU tier: the oracle reproduces its golden hits
+bit-exactly and the two submission variants (C1a flattened / C1b BLAS per mesh + TLAS) agree.  GPU tier: the CUDA path
+matches the oracle on all 921 600 pixels for both variants."""
+import os
+
+import numpy as np
+import pytest
+
+from rfw_rs_b200 import gltf
+from tests import parity
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    asset = gltf.load_npz(os.path.join(GOLD, name + ".npz"))
+    gold = np.load(os.path.join(GOLD, f"c1_{name}_golden.npz"))
+    return asset, gold
+
+
+@pytest.mark.parametrize("name,ntris,nmesh", [("cesium_man", 4672, 1), ("pica", 76274, 170)])
+def test_c1_oracle_reproduces_golden_and_variants_agree(oracle_mod, name, ntris, nmesh):
+    asset, gold = load(name)
+    assert len(asset.meshes) == nmesh and len(asset.mesh_nodes) == nmesh
+    flat = gltf.flatten(asset)
+    assert len(flat.meshes[0]) == ntris
+    w, h, sub = int(gold["width"]), int(gold["height"]), int(gold["sub"])
+    view = gltf.c1_camera(flat, w, h)
+    o = oracle_mod.OracleBackend(det_eps=0.0)
+    flat.apply(o)
+    rays = o.primary_rays(view, w, h).reshape(h, w)[::sub, ::sub].reshape(-1)
+    hits = o.trace_closest(rays, mode=oracle_mod.MODE_BVH2)
+    assert np.array_equal(hits["prim"], gold["prim"]) and np.array_equal(hits["inst"], gold["inst"].astype(np.int32))
+    assert np.array_equal(hits["t"], gold["t"])
+    assert int((hits["inst"] >= 0).sum()) == int(gold["hit_count_eps_0"]) > 3000
+    # the reference's determinant epsilons (intersection.glsl:12 / structs.rs:1046) never ADD hits
+    assert int(gold["hit_count_eps_0.0001"]) <= int(gold["hit_count_eps_1e-06"]) <= int(gold["hit_count_eps_0"])
+    # C1b: per-mesh BLAS + TLAS gives the same world-space hits (t within tolerance; ids map mesh-local -> flattened)
+    pm = gltf.per_mesh(asset)
+    o2 = oracle_mod.OracleBackend(det_eps=0.0)
+    pm.apply(o2)
+    h2 = o2.trace_closest(rays)
+    assert np.array_equal(h2["inst"] >= 0, hits["inst"] >= 0) or ((h2["inst"] >= 0) != (hits["inst"] >= 0)).sum() <= 3
+    both = (h2["inst"] >= 0) & (hits["inst"] >= 0)
+    assert np.allclose(h2["t"][both], hits["t"][both], rtol=2e-4, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cesium_man", "pica"])
+def test_c1_gpu_primary_cast_both_variants(oracle_mod, name):
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from rfw_rs_b200 import backend
+
+    asset, gold = load(name)
+    w, h, sub = int(gold["width"]), int(gold["height"]), int(gold["sub"])
+    flat, pm = gltf.flatten(asset), gltf.per_mesh(asset)
+    view = gltf.c1_camera(flat, w, h)
+    results = {}
+    for label, desc in (("C1a", flat), ("C1b", pm)):
+        gpu = backend.B200Backend(w, h)
+        desc.apply(gpu)
+        cpu = oracle_mod.OracleBackend(det_eps=0.0)
+        desc.apply(cpu)
+        rays = cpu.primary_rays(view, w, h)
+        ref = cpu.trace_closest(rays, mode=oracle_mod.MODE_BVH2)
+        hits = gpu.cast_primary(view)
+        parity.compare_hits(rays, hits, ref, parity.lookup_from_desc(desc), f"{name}/{label}")
+        results[label] = hits
+        st = gpu.build_stats()
+        assert st["num_triangles"] == len(flat.meshes[0])
+        if label == "C1b":
+            assert st["num_instances"] == len(asset.mesh_nodes) and (st["tlas_nodes"] >= 1 or len(asset.mesh_nodes) == 1)
+    # golden (subsampled) pin on the flattened variant
+    g = results["C1a"].reshape(h, w)[::sub, ::sub].reshape(-1)
+    same = g["prim"] == gold["prim"]
+    assert same.mean() > 0.9999
+    assert np.allclose(g["t"][same & (gold["prim"] >= 0)], gold["t"][same & (gold["prim"] >= 0)], rtol=2e-4, atol=1e-5)
+    # both variants see the same surface
+    a, b = results["C1a"], results["C1b"]
+    assert ((a["inst"] >= 0) != (b["inst"] >= 0)).sum() <= 10
+    both = (a["inst"] >= 0) & (b["inst"] >= 0)
+    assert np.allclose(a["t"][both], b["t"][both], rtol=2e-4, atol=1e-5)
