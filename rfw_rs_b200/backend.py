@@ -15,7 +15,7 @@ import numpy as np
 from . import wire
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librfwb200.so")
+LIB_PATH = os.environ.get("RFWB200_LIB") or os.path.join(_HERE, "librfwb200.so")  # RFWB200_LIB: A/B builds in tuning scripts
 
 
 class RfwError(RuntimeError):

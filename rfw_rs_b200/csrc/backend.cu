@@ -67,6 +67,13 @@ int Backend::init() {
     BK_CUDA(cudaStreamCreateWithFlags(&copy_out, cudaStreamNonBlocking), "stream");
     BK_CUDA(cudaEventCreate(&ev0), "event");
     BK_CUDA(cudaEventCreate(&ev1), "event");
+    {   // keep freed blocks of the stream-ordered allocator cached: BLAS builds of many small meshes reuse them
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, cfg.device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     BK_CUDA(cudaMalloc(&d_counter, 64), "counter");
     BK_CUDA(cudaMalloc(&d_counters3, 64), "counters");
     bctx.stream = stream;
@@ -212,13 +219,13 @@ int Backend::synchronize() {
             m.bvh.release();
             if (m.n) {
                 float4 *lo = nullptr, *hi = nullptr;
-                BK_CUDA(cudaMalloc(&lo, (size_t)m.n * sizeof(float4)), "box alloc");
-                BK_CUDA(cudaMalloc(&hi, (size_t)m.n * sizeof(float4)), "box alloc");
+                BK_CUDA(cudaMallocAsync(&lo, (size_t)m.n * sizeof(float4), stream), "box alloc");
+                BK_CUDA(cudaMallocAsync(&hi, (size_t)m.n * sizeof(float4), stream), "box alloc");
                 cudaError_t e = triangle_boxes(bctx, m.d_tris, (int)m.n, lo, hi);
                 if (e == cudaSuccess) e = build_wide_bvh(bctx, lo, hi, (int)m.n, blas_params, m.bvh);
-                cudaFree(lo); cudaFree(hi);
+                cudaFreeAsync(lo, stream); cudaFreeAsync(hi, stream);
                 if (e != cudaSuccess) return cuda_fail(e, "BLAS build");
-                BK_CUDA(cudaMalloc(&m.d_ttris, (size_t)m.n * 3 * sizeof(float4)), "triangle alloc");
+                BK_CUDA(cudaMallocAsync(&m.d_ttris, (size_t)m.n * 3 * sizeof(float4), stream), "triangle alloc");
                 BK_CUDA(gather_traversal_triangles(bctx, m.d_tris, m.bvh.leaf_prims, (int)m.n, m.d_ttris), "gather triangles");
             }
             m.dirty = false;
@@ -281,13 +288,13 @@ int Backend::synchronize() {
         BK_CUDA(cudaMemcpyAsync(d_inst_shading.ptr, shading.data(), shading.size() * sizeof(InstanceShading), cudaMemcpyHostToDevice, stream), "instance shading");
         if (live > 1) {
             float4 *lo = nullptr, *hi = nullptr;
-            BK_CUDA(cudaMalloc(&lo, live * sizeof(float4)), "tlas boxes");
-            BK_CUDA(cudaMalloc(&hi, live * sizeof(float4)), "tlas boxes");
+            BK_CUDA(cudaMallocAsync(&lo, live * sizeof(float4), stream), "tlas boxes");
+            BK_CUDA(cudaMallocAsync(&hi, live * sizeof(float4), stream), "tlas boxes");
             BK_CUDA(cudaMemcpyAsync(lo, ilo.data(), live * sizeof(float4), cudaMemcpyHostToDevice, stream), "tlas boxes");
             BK_CUDA(cudaMemcpyAsync(hi, ihi.data(), live * sizeof(float4), cudaMemcpyHostToDevice, stream), "tlas boxes");
             const BuildParams tlas_params{1.0f, 4.0f, 1};
             cudaError_t e = build_wide_bvh(bctx, lo, hi, (int)live, tlas_params, tlas);
-            cudaFree(lo); cudaFree(hi);
+            cudaFreeAsync(lo, stream); cudaFreeAsync(hi, stream);
             if (e != cudaSuccess) return cuda_fail(e, "TLAS build");
         }
         BK_CUDA(cudaStreamSynchronize(stream), "instance upload");

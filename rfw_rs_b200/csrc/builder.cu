@@ -289,8 +289,8 @@ cudaError_t build_wide_bvh(BuilderContext& ctx, const float4* prim_lo, const flo
         fprintf(stderr, "rfwb200: collapse emitted %u leaf slots for %d primitives\n", out.num_prims, n);
         return cudaErrorUnknown;
     }
-    RFW_CK(cudaMalloc(&out.nodes, (size_t)out.num_nodes * 80));
-    RFW_CK(cudaMalloc(&out.leaf_prims, (size_t)n * sizeof(uint32_t)));
+    RFW_CK(cudaMallocAsync(&out.nodes, (size_t)out.num_nodes * 80, s));  // stream-ordered pool: no device-wide sync per mesh
+    RFW_CK(cudaMallocAsync(&out.leaf_prims, (size_t)n * sizeof(uint32_t), s));
     RFW_CK(cudaMemcpyAsync(out.nodes, tmp_nodes, (size_t)out.num_nodes * 80, cudaMemcpyDeviceToDevice, s));
     RFW_CK(cudaMemcpyAsync(out.leaf_prims, tmp_leaf, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
     uint32_t h_bounds[12];

@@ -84,6 +84,17 @@ RFW_HD void ray_setup_tri(RayCtx& r) {
     r.Sz = 1.0f / dz;
 }
 
+// byte j of a word as a float.  Default: the integer->float conversion instruction with a byte selector (I2F.U8).
+// RFW_BYTE2F_MAGIC: one PRMT builds the bit pattern of 2^23 + byte (0x4B0000bb), one FADD removes the 2^23 — keeps the
+// conversion off the (narrower) conversion pipe.
+RFW_HD float byte_to_float(uint32_t w, int j) {
+#if defined(RFW_BYTE2F_MAGIC)
+    return u2f(byte_perm(w, 0x4B000000u, 0x7650u | (uint32_t)j)) - 8388608.0f;
+#else
+    return (float)((w >> (8 * j)) & 0xFFu);
+#endif
+}
+
 // 8 quantised child boxes against the ray; returns the hit mask (bits 24..31 inner children by
 // octant priority, bits 0..23 leaf primitives).  Accepts tmin_box <= tmax_box (ties kept, so exact-t
 // ties between primitives are resolved canonically by the caller).
@@ -113,9 +124,9 @@ RFW_HD uint32_t intersect_wide_node(const float4 n0, const float4 n1, const floa
 #endif
         for (int j = 0; j < 4; j++) {
             const int sh = 8 * j;
-            const float tlx = fmaf((float)((xmin >> sh) & 0xFFu), aix, aox), thx = fmaf((float)((xmax >> sh) & 0xFFu), aix, aox);
-            const float tly = fmaf((float)((ymin >> sh) & 0xFFu), aiy, aoy), thy = fmaf((float)((ymax >> sh) & 0xFFu), aiy, aoy);
-            const float tlz = fmaf((float)((zmin >> sh) & 0xFFu), aiz, aoz), thz = fmaf((float)((zmax >> sh) & 0xFFu), aiz, aoz);
+            const float tlx = fmaf(byte_to_float(xmin, j), aix, aox), thx = fmaf(byte_to_float(xmax, j), aix, aox);
+            const float tly = fmaf(byte_to_float(ymin, j), aiy, aoy), thy = fmaf(byte_to_float(ymax, j), aiy, aoy);
+            const float tlz = fmaf(byte_to_float(zmin, j), aiz, aoz), thz = fmaf(byte_to_float(zmax, j), aiz, aoz);
             // fminf/fmaxf drop NaN operands (0 * inf): such a slab simply does not constrain
             const float cmin = fmaxf(fmaxf(tlx, tly), fmaxf(tlz, tmin));
             const float cmax = fminf(fminf(thx, thy), fminf(thz, tmax)) * 1.0000004f;  // 2-ulp pad: conservative slabs

@@ -69,8 +69,18 @@ def compare_hits(rays, gpu, ref, scene_lookup, label=""):
             dd = inv[:3, :3] @ rays["direction"][i].astype(np.float64)
             cos = abs(np.dot(nrm, dd)) / max(np.linalg.norm(dd), 1e-30)
             assert err[j] * max(cos, 1e-3) <= tol[j], f"{label}: t err {err[j]} (cos {cos}) > tol {tol[j]} (t={ref['t'][i]})"
-        assert np.abs(gpu["u"][hit] - ref["u"][hit]).max() <= ABS_UV, f"{label}: u err"
-        assert np.abs(gpu["v"][hit] - ref["v"][hit]).max() <= ABS_UV, f"{label}: v err"
+        # barycentrics: abs ABS_UV; on small / distant triangles float32 cannot resolve them that finely, so for the few
+        # hits over the bound the two barycentric pairs must name the same POINT within 256 ulp of the coordinate scale
+        duv = np.maximum(np.abs(gpu["u"][idx] - ref["u"][idx]), np.abs(gpu["v"][idx] - ref["v"][idx]))
+        for j in np.nonzero(duv > ABS_UV)[0]:
+            i = idx[j]
+            tris, inv = scene_lookup(int(ref["inst"][i]))
+            v0, v1, v2 = _tri_f64(tris, int(ref["prim"][i]))
+            pg = (1 - gpu["u"][i] - gpu["v"][i]) * v0 + gpu["u"][i] * v1 + gpu["v"][i] * v2
+            pr = (1 - ref["u"][i] - ref["v"][i]) * v0 + ref["u"][i] * v1 + ref["v"][i] * v2
+            oo = inv[:3, :3] @ rays["origin"][i].astype(np.float64) + inv[:3, 3]
+            scale = max(np.abs(oo).max(), np.abs(pr).max(), 1e-6)
+            assert np.abs(pg - pr).max() <= 256 * 2.0 ** -24 * scale, f"{label}: barycentric err {duv[j]} = point err {np.abs(pg - pr).max()} at scale {scale}"
     miss = same & (ref["inst"] < 0)
     if miss.any():
         assert np.array_equal(gpu["t"][miss], ref["t"][miss]), f"{label}: miss records must carry tmax"
