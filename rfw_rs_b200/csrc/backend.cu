@@ -77,6 +77,7 @@ int Backend::init() {
     BK_CUDA(cudaMalloc(&d_counter, 64), "counter");
     BK_CUDA(cudaMalloc(&d_counters3, 64), "counters");
     bctx.stream = stream;
+    bctx.sm_count = sm_count;
     tcfg.stream = stream;
     tcfg.sm_count = sm_count;
     wf.sm_count = sm_count;
@@ -212,7 +213,7 @@ int Backend::synchronize() {
     if (scene_dirty) {
         // ---- BLAS for dirty meshes ------------------------------------------------------------------
         BK_CUDA(cudaEventRecord(ev0, stream), "event");
-        const BuildParams blas_params{1.0f, 0.3f, 3};
+        const BuildParams blas_params{1.0f, 0.3f, 3, sah_treelet};
         for (MeshRec& m : meshes) {
             if (!m.present || !m.dirty) continue;
             if (m.d_ttris) { cudaFree(m.d_ttris); m.d_ttris = nullptr; }
@@ -292,7 +293,7 @@ int Backend::synchronize() {
             BK_CUDA(cudaMallocAsync(&hi, live * sizeof(float4), stream), "tlas boxes");
             BK_CUDA(cudaMemcpyAsync(lo, ilo.data(), live * sizeof(float4), cudaMemcpyHostToDevice, stream), "tlas boxes");
             BK_CUDA(cudaMemcpyAsync(hi, ihi.data(), live * sizeof(float4), cudaMemcpyHostToDevice, stream), "tlas boxes");
-            const BuildParams tlas_params{1.0f, 4.0f, 1};
+            const BuildParams tlas_params{1.0f, 4.0f, 1, sah_treelet};
             cudaError_t e = build_wide_bvh(bctx, lo, hi, (int)live, tlas_params, tlas);
             cudaFreeAsync(lo, stream); cudaFreeAsync(hi, stream);
             if (e != cudaSuccess) return cuda_fail(e, "TLAS build");
@@ -660,6 +661,7 @@ int Backend::set_option(const char* key, int64_t value) {
     else if (k == "min_blocks") tcfg.min_blocks = (int)value;
     else if (k == "chunk_rays") chunk_rays = (uint64_t)std::max<int64_t>(1024, value);
     else if (k == "max_depth") cfg.max_depth = (uint32_t)value;
+    else if (k == "sah_treelet") { sah_treelet = (int)value; for (auto& m : meshes) if (m.present) m.dirty = true; scene_dirty = true; synchronized = false; }
     else if (k == "sample_count") sample_count = (uint32_t)value;  // debug: render a chosen sample index next
     else return fail(RFWB200_ERR_INVALID, "set_option: unknown key " + k);
     return RFWB200_OK;

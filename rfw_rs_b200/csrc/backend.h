@@ -129,6 +129,7 @@ private:
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> chunk_events;
     uint64_t chunk_rays = 1u << 21;
+    int sah_treelet = 8;  // binned-SAH refinement above LBVH treelets of this many primitives (0 = plain LBVH)
 
     // wavefront renderer
     Wavefront wf;

@@ -1,10 +1,19 @@
 // builder.cu — device BVH build: kernels wrapping the bodies of bvh_build.h + host orchestration.
 // Replaces the reference's CPU builds (rtbvh BinnedSahBuilder / MBVH::construct,
-// backends/gpu-rt/src/lib.rs:1345-1357, :1576-1581).  Everything after the H2D copy of the
-// triangles runs on the GPU; the host only reads back the per-level task counts of the collapse.
+// backends/gpu-rt/src/lib.rs:1345-1357, :1576-1581).  Everything after the H2D copy of the triangles runs on
+// the GPU with ONE host synchronisation per build (the final node count): the level loops of the SAH top build
+// and of the wide collapse are cooperative kernels that grid-sync between levels.
+//
+//   boxes -> centroid bounds -> 63-bit Morton -> radix sort -> Karras radix tree -> bottom-up fit + SAH forest cost DP
+//   -> [binned-SAH refinement: LBVH subtrees of <= `treelet` primitives are kept, the tree ABOVE them is rebuilt
+//       top-down with 16-bin SAH over the treelet boxes (one warp per segment, level by level), then re-costed]
+//   -> top-down collapse into 80-byte 8-wide nodes -> leaf-ordered traversal triangles
+#include <cooperative_groups.h>
 #include <stdio.h>
 
 #include "builder.h"
+
+namespace cg = cooperative_groups;
 
 namespace rfw {
 
@@ -15,6 +24,7 @@ namespace rfw {
     } while (0)
 
 static constexpr int TB = 256;
+static constexpr uint32_t FULLMASK = 0xFFFFFFFFu;
 static inline int blocks_for(long long n, int tb = TB) { return (int)((n + tb - 1) / tb); }
 
 // order-preserving float <-> uint encoding for atomicMin/Max
@@ -58,7 +68,7 @@ __global__ void __launch_bounds__(TB) k_bounds(const float4* __restrict__ lo, co
         const bool is_min = (k % 6) < 3;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            const float y = __shfl_xor_sync(0xFFFFFFFFu, v[k], o);
+            const float y = __shfl_xor_sync(FULLMASK, v[k], o);
             v[k] = is_min ? fminf(v[k], y) : fmaxf(v[k], y);
         }
     }
@@ -99,19 +109,266 @@ __global__ void __launch_bounds__(TB) k_fit_cost(BuildArrays A, BuildParams P) {
     fit_cost_body(k, A, P);
 }
 
-__global__ void __launch_bounds__(128) k_collapse(const int2* __restrict__ queue, uint32_t count, BuildArrays A, CollapseOut O, int2* __restrict__ next_queue,
-                                                  uint32_t* __restrict__ next_count) {
-    const uint32_t t = blockIdx.x * 128 + threadIdx.x;
-    if (t >= count) return;
-    collapse_body(queue[t], A, O, next_queue, next_count);
+// ------------------------------------------------------------------------------------------------
+// binned-SAH refinement of the tree above the treelets
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int node_prim_count(int node, const BuildArrays& A) {
+    if (is_leaf_node(node, A.n)) return 1;
+    const int2 rg = A.range[inner_index(node, A.n)];
+    return rg.y - rg.x + 1;
 }
 
-__global__ void k_init_collapse(int2* q0, uint32_t* counters) {
-    q0[0] = make_int2(0, 0);
-    counters[0] = 1;  // wide nodes allocated (root)
-    counters[1] = 0;  // leaf slots allocated
-    counters[2] = 0;  // next-level task count (ping)
-    counters[3] = 0;  // next-level task count (pong)
+// one thread per Karras node: a node is a treelet root iff it holds <= K primitives and its parent holds more.
+// Treelet roots are recorded at their first sorted position, so a scan over positions orders them deterministically.
+__global__ void __launch_bounds__(TB) k_mark_treelets(BuildArrays A, int K, uint32_t* __restrict__ flag, int* __restrict__ node_at) {
+    const int node = blockIdx.x * TB + threadIdx.x;
+    const int n = A.n;
+    if (node >= 2 * n - 1) return;
+    const int cnt = node_prim_count(node, A);
+    if (cnt > K) return;
+    const int par = A.parent[node];
+    if (par >= 0 && node_prim_count(par, A) <= K) return;
+    const int first = is_leaf_node(node, n) ? node - (n - 1) : A.range[node].x;
+    flag[first] = 1u;
+    node_at[first] = node;
+}
+
+__global__ void __launch_bounds__(TB) k_gather_treelets(int n, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ rank, const int* __restrict__ node_at,
+                                                        int* __restrict__ items, uint32_t* __restrict__ counters) {
+    const int p = blockIdx.x * TB + threadIdx.x;
+    if (p >= n) return;
+    if (flag[p]) items[rank[p]] = node_at[p];
+    if (p == n - 1) counters[4] = rank[p] + flag[p];  // number of treelets
+}
+
+struct SahBins {
+    int cnt[3][16];
+    uint32_t lo[3][16][3];
+    uint32_t hi[3][16][3];
+};
+
+__device__ __forceinline__ float bins_area(const uint32_t lo[3], const uint32_t hi[3]) {
+    const float ex = dec_f(hi[0]) - dec_f(lo[0]), ey = dec_f(hi[1]) - dec_f(lo[1]), ez = dec_f(hi[2]) - dec_f(lo[2]);
+    return 2.0f * (ex * ey + ey * ez + ez * ex);
+}
+
+// One warp splits one segment [begin, end) of the treelet array with 16-bin SAH on the best of 3 axes, partitions
+// it (stable) and emits the top node; children / next segments are written to the arrays.
+__device__ void sah_split_segment(int4 seg, int* __restrict__ items, int* __restrict__ items_tmp, const BuildArrays& A, SahBins& bins, int4* __restrict__ next_segs,
+                                  uint32_t* __restrict__ next_count, uint32_t* __restrict__ top_counter) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    const int begin = seg.x, end = seg.y, top = seg.z;
+    const int n = A.n;
+    // a. centroid bounds, primitive count
+    float cmin[3] = {3e38f, 3e38f, 3e38f}, cmax[3] = {-3e38f, -3e38f, -3e38f};
+    int prims = 0;
+    for (int i = begin + lane; i < end; i += 32) {
+        const int node = items[i];
+        const float4 l = A.node_lo[node], h = A.node_hi[node];
+        const float c[3] = {(l.x + h.x) * 0.5f, (l.y + h.y) * 0.5f, (l.z + h.z) * 0.5f};
+#pragma unroll
+        for (int a = 0; a < 3; a++) { cmin[a] = fminf(cmin[a], c[a]); cmax[a] = fmaxf(cmax[a], c[a]); }
+        prims += node_prim_count(node, A);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            cmin[a] = fminf(cmin[a], __shfl_xor_sync(FULLMASK, cmin[a], o));
+            cmax[a] = fmaxf(cmax[a], __shfl_xor_sync(FULLMASK, cmax[a], o));
+        }
+        prims += __shfl_xor_sync(FULLMASK, prims, o);
+    }
+    float scale[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) scale[a] = cmax[a] > cmin[a] ? 16.0f / (cmax[a] - cmin[a]) : 0.0f;
+    // b. bins
+    for (int k = lane; k < 48; k += 32) {
+        const int a = k / 16, b = k % 16;
+        bins.cnt[a][b] = 0;
+#pragma unroll
+        for (int d = 0; d < 3; d++) { bins.lo[a][b][d] = 0xFFFFFFFFu; bins.hi[a][b][d] = 0u; }
+    }
+    __syncwarp();
+    for (int i = begin + lane; i < end; i += 32) {
+        const int node = items[i];
+        const float4 l = A.node_lo[node], h = A.node_hi[node];
+        const float c[3] = {(l.x + h.x) * 0.5f, (l.y + h.y) * 0.5f, (l.z + h.z) * 0.5f};
+        const uint32_t el[3] = {enc_f(l.x), enc_f(l.y), enc_f(l.z)}, eh[3] = {enc_f(h.x), enc_f(h.y), enc_f(h.z)};
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const int b = min(15, (int)((c[a] - cmin[a]) * scale[a]));
+            atomicAdd(&bins.cnt[a][b], 1);
+#pragma unroll
+            for (int d = 0; d < 3; d++) { atomicMin(&bins.lo[a][b][d], el[d]); atomicMax(&bins.hi[a][b][d], eh[d]); }
+        }
+    }
+    __syncwarp();
+    // c. 45 candidates (3 axes x 15 split planes), strided over the lanes
+    float best_cost = 3.0e38f;
+    int best_cand = -1, best_nl = 0;
+    for (int cand = lane; cand < 45; cand += 32) {
+        const int a = cand / 15, split = cand % 15;
+        if (scale[a] == 0.0f) continue;
+        uint32_t llo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, lhi[3] = {0, 0, 0}, rlo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, rhi[3] = {0, 0, 0};
+        int nl = 0, nr = 0;
+        for (int b = 0; b < 16; b++) {
+            const int c = bins.cnt[a][b];
+            if (c == 0) continue;
+            if (b <= split) {
+                nl += c;
+#pragma unroll
+                for (int d = 0; d < 3; d++) { llo[d] = min(llo[d], bins.lo[a][b][d]); lhi[d] = max(lhi[d], bins.hi[a][b][d]); }
+            } else {
+                nr += c;
+#pragma unroll
+                for (int d = 0; d < 3; d++) { rlo[d] = min(rlo[d], bins.lo[a][b][d]); rhi[d] = max(rhi[d], bins.hi[a][b][d]); }
+            }
+        }
+        if (nl == 0 || nr == 0) continue;
+        const float cost = bins_area(llo, lhi) * (float)nl + bins_area(rlo, rhi) * (float)nr;
+        if (cost < best_cost) { best_cost = cost; best_cand = cand; best_nl = nl; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float oc = __shfl_xor_sync(FULLMASK, best_cost, o);
+        const int ocand = __shfl_xor_sync(FULLMASK, best_cand, o);
+        const int onl = __shfl_xor_sync(FULLMASK, best_nl, o);
+        // deterministic: lower cost wins, ties by lower candidate index
+        if (ocand >= 0 && (best_cand < 0 || oc < best_cost || (oc == best_cost && ocand < best_cand))) { best_cost = oc; best_cand = ocand; best_nl = onl; }
+    }
+    // d. partition
+    int nl;
+    if (best_cand < 0) {
+        nl = (end - begin) / 2;  // all centroids coincide: median split in Morton order
+    } else {
+        nl = best_nl;
+        const int a = best_cand / 15, split = best_cand % 15;
+        const float cm = a == 0 ? cmin[0] : (a == 1 ? cmin[1] : cmin[2]);
+        const float sc = a == 0 ? scale[0] : (a == 1 ? scale[1] : scale[2]);
+        int loff = 0, roff = 0;
+        for (int base = begin; base < end; base += 32) {
+            const int i = base + lane;
+            const bool valid = i < end;
+            int node = 0;
+            bool left = false;
+            if (valid) {
+                node = items[i];
+                const float4 l = A.node_lo[node], h = A.node_hi[node];
+                const float c = a == 0 ? (l.x + h.x) * 0.5f : (a == 1 ? (l.y + h.y) * 0.5f : (l.z + h.z) * 0.5f);
+                left = min(15, (int)((c - cm) * sc)) <= split;
+            }
+            const uint32_t ml = __ballot_sync(FULLMASK, valid && left), mr = __ballot_sync(FULLMASK, valid && !left);
+            if (valid) items_tmp[left ? begin + loff + __popc(ml & lt) : begin + nl + roff + __popc(mr & lt)] = node;
+            loff += __popc(ml); roff += __popc(mr);
+        }
+        __syncwarp();
+        for (int i = begin + lane; i < end; i += 32) items[i] = items_tmp[i];
+        __syncwarp();
+    }
+    // e. children
+    if (lane == 0) {
+        const int nr = (end - begin) - nl;
+        int child[2];
+        const int cb[2] = {begin, begin + nl}, cn[2] = {nl, nr};
+        for (int s = 0; s < 2; s++) {
+            if (cn[s] == 1) {
+                child[s] = items[cb[s]];
+            } else {
+                child[s] = 2 * n - 1 + (int)atomicAdd(top_counter, 1u);
+                next_segs[atomicAdd(next_count, 1u)] = make_int4(cb[s], cb[s] + cn[s], child[s], 0);
+            }
+            A.parent[child[s]] = top;
+        }
+        const int ti = inner_index(top, n);
+        A.children[ti] = make_int2(child[0], child[1]);
+        A.range[ti] = make_int2(0, prims - 1);  // only the COUNT of a top node is meaningful: its primitives are not contiguous
+        A.flags[ti] = 0;
+    }
+    __syncwarp();
+}
+
+// cooperative: all levels of the top-down build in one launch, grid.sync between levels
+__global__ void __launch_bounds__(128) k_sah_top(BuildArrays A, int* __restrict__ items, int* __restrict__ items_tmp, int4* __restrict__ seg0, int4* __restrict__ seg1,
+                                                 uint32_t* __restrict__ counters) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ SahBins bins[4];
+    const int warp_in_block = threadIdx.x >> 5;
+    const uint32_t warp = blockIdx.x * 4 + warp_in_block, n_warps = gridDim.x * 4;
+    const uint32_t m = counters[4];
+    if (m < 2) return;  // uniform across the grid: nobody reaches a grid.sync
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        seg0[0] = make_int4(0, (int)m, 2 * A.n - 1, 0);
+        A.parent[2 * A.n - 1] = -1;
+        counters[5] = 1;  // top nodes allocated (the root)
+        counters[6] = 0; counters[7] = 0;
+    }
+    __threadfence();
+    grid.sync();
+    uint32_t count = 1;
+    int ping = 0;
+    int4 *sin = seg0, *sout = seg1;
+    while (count > 0) {
+        uint32_t* next = counters + 6 + ping;
+        for (uint32_t s = warp; s < count; s += n_warps) sah_split_segment(sin[s], items, items_tmp, A, bins[warp_in_block], sout, next, counters + 5);
+        __threadfence();
+        grid.sync();
+        count = *((volatile uint32_t*)next);
+        if (blockIdx.x == 0 && threadIdx.x == 0) counters[6 + (ping ^ 1)] = 0;
+        __threadfence();
+        grid.sync();
+        int4* t = sin; sin = sout; sout = t;
+        ping ^= 1;
+    }
+}
+
+// re-cost the top tree bottom-up: one thread per treelet root climbs (second arrival computes the node)
+__global__ void __launch_bounds__(TB) k_fit_top(BuildArrays A, BuildParams P, const int* __restrict__ items, const uint32_t* __restrict__ counters) {
+    const uint32_t m = counters[4];
+    const uint32_t k = blockIdx.x * TB + threadIdx.x;
+    if (m < 2 || k >= m) return;
+    int cur = A.parent[items[k]];
+    while (cur >= 0) {
+        __threadfence();
+        const int old = atomicAdd(&A.flags[inner_index(cur, A.n)], 1);
+        if (old == 0) return;
+        __threadfence();
+        fit_cost_node(cur, A, P);
+        cur = A.parent[cur];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// collapse: cooperative level loop
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_collapse_all(BuildArrays A, CollapseOut O, int2* __restrict__ q0, int2* __restrict__ q1, uint32_t* __restrict__ counters) {
+    cg::grid_group grid = cg::this_grid();
+    const uint32_t tid = blockIdx.x * 128 + threadIdx.x, n_threads = gridDim.x * 128;
+    if (tid == 0) {
+        const bool refined = counters[4] >= 2;  // the SAH top tree exists: its root is node 2n-1
+        q0[0] = make_int2(refined ? 2 * A.n - 1 : 0, 0);
+        counters[0] = 1;  // wide nodes allocated (root)
+        counters[1] = 0;  // leaf slots allocated
+        counters[2] = 0; counters[3] = 0;
+    }
+    __threadfence();
+    grid.sync();
+    uint32_t count = 1;
+    int ping = 0;
+    int2 *qin = q0, *qout = q1;
+    while (count > 0) {
+        uint32_t* next = counters + 2 + ping;
+        for (uint32_t t = tid; t < count; t += n_threads) collapse_body(qin[t], A, O, qout, next);
+        __threadfence();
+        grid.sync();
+        count = *((volatile uint32_t*)next);
+        if (tid == 0) counters[2 + (ping ^ 1)] = 0;
+        __threadfence();
+        grid.sync();
+        int2* t = qin; qin = qout; qout = t;
+        ping ^= 1;
+    }
 }
 
 __global__ void __launch_bounds__(TB) k_gather_tris(const RfwRTTriangle* __restrict__ tris, const uint32_t* __restrict__ leaf_prims, int n, float4* __restrict__ out) {
@@ -144,7 +401,7 @@ __global__ void __launch_bounds__(TB) k_checksum(const uint32_t* __restrict__ wo
         s += h;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULLMASK, s, o);
     if ((threadIdx.x & 31) == 0) atomicAdd(accum, s);
 }
 
@@ -203,21 +460,45 @@ struct Carver {
         return r;
     }
 };
+
+// persistent grid for a cooperative kernel: as many CTAs as can be co-resident, but no more than the work needs
+template <typename K>
+cudaError_t coop_grid(K kernel, int block, int sm_count, long long work_items, int items_per_block, int& grid) {
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    long long g = (long long)per_sm * sm_count;
+    const long long need = (work_items + items_per_block - 1) / items_per_block;
+    if (g > need) g = need;
+    grid = (int)(g < 1 ? 1 : g);
+    return cudaSuccess;
+}
 }  // namespace
 
 cudaError_t build_wide_bvh(BuilderContext& ctx, const float4* prim_lo, const float4* prim_hi, int n, const BuildParams& params, DeviceBvh& out) {
     out.release();
     if (n <= 0) return cudaSuccess;
     cudaStream_t s = ctx.stream;
+    if (ctx.sm_count <= 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&ctx.sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
     const int tiles = radix_sort_tiles(n);
-    const size_t nn = 2 * (size_t)n - 1, ni = n > 1 ? (size_t)n - 1 : 1;
+    const bool refine = params.treelet > 0 && n > params.treelet;
+    const size_t m_max = refine ? (size_t)n : 0;                       // treelets (<= n)
+    const size_t nn = 2 * (size_t)n - 1 + m_max;                       // node ids: Karras + SAH top nodes
+    const size_t ni = (n > 1 ? (size_t)n - 1 : 1) + m_max;             // inner-node arrays
 
     // pass 1 computes the size, pass 2 carves
     Carver cv{nullptr};
     uint64_t *keys = nullptr, *keys_tmp = nullptr;
     uint32_t *vals = nullptr, *vals_tmp = nullptr, *hist = nullptr, *decision = nullptr, *counters = nullptr, *bounds = nullptr, *tmp_leaf = nullptr;
-    int *parent = nullptr, *flags = nullptr;
+    uint32_t *tre_flag = nullptr, *tre_rank = nullptr;
+    int *parent = nullptr, *flags = nullptr, *tre_node = nullptr, *items = nullptr, *items_tmp = nullptr;
     int2 *children = nullptr, *range = nullptr, *q0 = nullptr, *q1 = nullptr;
+    int4 *seg0 = nullptr, *seg1 = nullptr;
     float4 *node_lo = nullptr, *node_hi = nullptr, *tmp_nodes = nullptr;
     float* cost = nullptr;
     for (int pass = 0; pass < 2; pass++) {
@@ -233,8 +514,13 @@ cudaError_t build_wide_bvh(BuilderContext& ctx, const float4* prim_lo, const flo
         q0 = cv.take<int2>(n); q1 = cv.take<int2>(n);
         tmp_nodes = cv.take<float4>((size_t)n * 5);
         tmp_leaf = cv.take<uint32_t>(n);
-        counters = cv.take<uint32_t>(8);
+        counters = cv.take<uint32_t>(16);
         bounds = cv.take<uint32_t>(16);
+        if (refine) {
+            tre_flag = cv.take<uint32_t>(n); tre_rank = cv.take<uint32_t>(n); tre_node = cv.take<int>(n);
+            items = cv.take<int>(n); items_tmp = cv.take<int>(n);
+            seg0 = cv.take<int4>(n); seg1 = cv.take<int4>(n);
+        }
         if (pass == 0) {
             void* base = ctx.scratch.reserve(cv.off + 512);
             if (!base) return cudaErrorMemoryAllocation;
@@ -242,6 +528,7 @@ cudaError_t build_wide_bvh(BuilderContext& ctx, const float4* prim_lo, const flo
         }
     }
 
+    RFW_CK(cudaMemsetAsync(counters, 0, 16 * sizeof(uint32_t), s));
     k_init_bounds<<<1, 32, 0, s>>>(bounds);
     k_bounds<<<blocks_for(n), TB, 0, s>>>(prim_lo, prim_hi, n, bounds);
     k_morton<<<blocks_for(n), TB, 0, s>>>(prim_lo, prim_hi, n, bounds, keys, vals);
@@ -264,27 +551,38 @@ cudaError_t build_wide_bvh(BuilderContext& ctx, const float4* prim_lo, const flo
     ctx.launches++;
     RFW_CK(cudaGetLastError());
 
+    if (refine) {
+        RFW_CK(cudaMemsetAsync(tre_flag, 0, (size_t)n * sizeof(uint32_t), s));
+        k_mark_treelets<<<blocks_for(2 * (long long)n - 1), TB, 0, s>>>(A, params.treelet, tre_flag, tre_node);
+        RFW_CK(cudaMemcpyAsync(tre_rank, tre_flag, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+        exclusive_scan_u32(tre_rank, n, s);
+        k_gather_treelets<<<blocks_for(n), TB, 0, s>>>(n, tre_flag, tre_rank, tre_node, items, counters);
+        int grid = 1;
+        RFW_CK(coop_grid(k_sah_top, 128, ctx.sm_count, n / 2 + 1, 4, grid));  // 4 warps = 4 segments per CTA per round
+        void* args[] = {&A, &items, &items_tmp, &seg0, &seg1, &counters};
+        RFW_CK(cudaLaunchCooperativeKernel((void*)k_sah_top, dim3(grid), dim3(128), args, 0, s));
+        k_fit_top<<<blocks_for(n), TB, 0, s>>>(A, params, items, counters);
+        ctx.launches += 5;
+        RFW_CK(cudaGetLastError());
+    }
+
     CollapseOut O;
     O.nodes = tmp_nodes; O.leaf_prims = tmp_leaf; O.node_counter = counters + 0; O.prim_counter = counters + 1;
-    k_init_collapse<<<1, 1, 0, s>>>(q0, counters);
-    ctx.launches++;
-    uint32_t count = 1;
-    int2 *qin = q0, *qout = q1;
-    int ping = 0;
-    uint32_t h_counters[4];
-    while (count > 0) {
-        uint32_t* next_count = counters + 2 + ping;
-        k_collapse<<<blocks_for(count, 128), 128, 0, s>>>(qin, count, A, O, qout, next_count);
+    {
+        int grid = 1;
+        RFW_CK(coop_grid(k_collapse_all, 128, ctx.sm_count, n / 2 + 1, 128, grid));
+        void* args[] = {&A, &O, &q0, &q1, &counters};
+        RFW_CK(cudaLaunchCooperativeKernel((void*)k_collapse_all, dim3(grid), dim3(128), args, 0, s));
         ctx.launches++;
-        RFW_CK(cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, s));
-        RFW_CK(cudaStreamSynchronize(s));
-        count = h_counters[2 + ping];
-        RFW_CK(cudaMemsetAsync(next_count, 0, sizeof(uint32_t), s));
-        int2* t = qin; qin = qout; qout = t;
-        ping ^= 1;
     }
+    uint32_t h_counters[8];
+    uint32_t h_bounds[12];
+    RFW_CK(cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, s));
+    RFW_CK(cudaMemcpyAsync(h_bounds, bounds, sizeof(h_bounds), cudaMemcpyDeviceToHost, s));
+    RFW_CK(cudaStreamSynchronize(s));  // the host sync of the build: the node count sizes the final buffers
     out.num_nodes = h_counters[0];
     out.num_prims = h_counters[1];
+    out.num_treelets = h_counters[4];
     if (out.num_prims != (uint32_t)n) {
         fprintf(stderr, "rfwb200: collapse emitted %u leaf slots for %d primitives\n", out.num_prims, n);
         return cudaErrorUnknown;
@@ -293,11 +591,10 @@ cudaError_t build_wide_bvh(BuilderContext& ctx, const float4* prim_lo, const flo
     RFW_CK(cudaMallocAsync(&out.leaf_prims, (size_t)n * sizeof(uint32_t), s));
     RFW_CK(cudaMemcpyAsync(out.nodes, tmp_nodes, (size_t)out.num_nodes * 80, cudaMemcpyDeviceToDevice, s));
     RFW_CK(cudaMemcpyAsync(out.leaf_prims, tmp_leaf, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
-    uint32_t h_bounds[12];
+    // SAH cost of the tree the collapse started from (root = SAH top root when refined, else Karras node 0 / the only leaf)
+    const size_t root = (refine && out.num_treelets >= 2) ? 2 * (size_t)n - 1 : 0;
     float h_cost[8];
-    RFW_CK(cudaMemcpyAsync(h_bounds, bounds, sizeof(h_bounds), cudaMemcpyDeviceToHost, s));
-    // root cost: binary node 0 (for n == 1 the only leaf has id 0 as well)
-    RFW_CK(cudaMemcpyAsync(h_cost, cost, sizeof(h_cost), cudaMemcpyDeviceToHost, s));
+    RFW_CK(cudaMemcpyAsync(h_cost, cost + root * 8, sizeof(h_cost), cudaMemcpyDeviceToHost, s));
     RFW_CK(cudaStreamSynchronize(s));
     for (int k = 0; k < 3; k++) { out.lo[k] = dec_f(h_bounds[6 + k]); out.hi[k] = dec_f(h_bounds[9 + k]); }
     out.sah = h_cost[7] > 0.0f ? h_cost[0] / h_cost[7] : 0.0f;

@@ -9,6 +9,7 @@
 namespace rfw {
 
 int radix_sort_tiles(int n);
+void exclusive_scan_u32(uint32_t* data, int count, cudaStream_t stream);
 int radix_sort_pairs(uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp, uint32_t* hist, int n, int begin_bit, int end_bit, cudaStream_t stream,
                      uint64_t* launches);
 
@@ -18,6 +19,7 @@ struct DeviceBvh {
     uint32_t* leaf_prims = nullptr; // leaf slot -> primitive index
     uint32_t num_nodes = 0;
     uint32_t num_prims = 0;
+    uint32_t num_treelets = 0;      // items of the SAH top build (0 = plain LBVH)
     float sah = 0.0f;
     float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};  // bounds of all primitive boxes
     void release();
@@ -35,6 +37,7 @@ struct BuilderContext {
     cudaStream_t stream = nullptr;
     BuildScratch scratch;
     uint64_t launches = 0;
+    int sm_count = 0;
 };
 
 // prim_lo / prim_hi: device arrays of n boxes.  Builds the wide BVH into `out` (allocating exact-size buffers).

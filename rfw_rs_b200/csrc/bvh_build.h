@@ -20,6 +20,8 @@ struct BuildParams {
     float c_node;  // cost of visiting one wide node
     float c_prim;  // cost of testing one primitive
     int pmax;      // max primitives per leaf child (<= 3: unary count in 3 meta bits)
+    int treelet;   // binned-SAH refinement: LBVH subtrees of <= treelet primitives are kept, the tree above them is
+                   // rebuilt top-down with binned SAH (builder.cu); 0 = plain LBVH
 };
 
 struct BuildArrays {
@@ -102,6 +104,12 @@ RFW_HD void karras_body(int i, int n, const uint64_t* keys, int* parent, int2* c
     if (i == 0) parent[0] = -1;
 }
 
+// Node ids: Karras internal i in [0, n-2]; leaf of sorted position k = n-1+k; nodes of the SAH-built top tree
+// (builder.cu, optional) = 2n-1+j.  The per-inner-node arrays (children, range, decision, flags) are indexed by
+// inner_index(): Karras internals first, top nodes behind them.
+RFW_HD bool is_leaf_node(int node, int n) { return node >= n - 1 && node < 2 * n - 1; }
+RFW_HD int inner_index(int node, int n) { return node < n - 1 ? node : node - n; }
+
 // ---- 5. fit + SAH forest costs ---------------------------------------------------------------------
 RFW_HD float box_area(float3 lo, float3 hi) {
     const float3 e = hi - lo;
@@ -115,7 +123,7 @@ RFW_HD uint32_t dec_k8(uint32_t w) { return (w >> 1) & 7u; }
 RFW_HD uint32_t dec_ki(uint32_t w, int i) { return (w >> (4 + 3 * (i - 2))) & 7u; }
 
 RFW_HD void fit_cost_node(int node, const BuildArrays& A, const BuildParams& P) {
-    const int2 ch = A.children[node];
+    const int2 ch = A.children[inner_index(node, A.n)];
     const float3 lo = min3(xyz(A.node_lo[ch.x]), xyz(A.node_lo[ch.y]));
     const float3 hi = max3(xyz(A.node_hi[ch.x]), xyz(A.node_hi[ch.y]));
     A.node_lo[node] = f4(lo.x, lo.y, lo.z, 0.0f);
@@ -134,7 +142,7 @@ RFW_HD void fit_cost_node(int node, const BuildArrays& A, const BuildParams& P) 
         }
         dist[j] = best; kd[j] = bk;
     }
-    const int2 rg = A.range[node];
+    const int2 rg = A.range[inner_index(node, A.n)];
     const int count = rg.y - rg.x + 1;
     const float c_leaf = (count <= P.pmax) ? area * (float)count * P.c_prim : 3.0e38f;
     const float c_internal = dist[8] + area * P.c_node;
@@ -148,7 +156,7 @@ RFW_HD void fit_cost_node(int node, const BuildArrays& A, const BuildParams& P) 
     }
     for (int i = 1; i <= 7; i++) A.cost[(size_t)node * 8 + (i - 1)] = c[i];
     A.cost[(size_t)node * 8 + 7] = area;
-    A.decision[node] = w;
+    A.decision[inner_index(node, A.n)] = w;
 }
 
 // one thread per sorted leaf k: write the leaf, then climb; the second thread to arrive at a node computes it
@@ -166,7 +174,7 @@ RFW_HD void fit_cost_body(int k, const BuildArrays& A, const BuildParams& P) {
     int cur = A.parent[leaf];
     while (cur >= 0) {
         thread_fence();
-        const int old = atomic_add(&A.flags[cur], 1);
+        const int old = atomic_add(&A.flags[inner_index(cur, n)], 1);
         if (old == 0) return;  // first arrival: the sibling subtree is not finished yet
         thread_fence();
         fit_cost_node(cur, A, P);
@@ -185,16 +193,16 @@ struct WideChild {
 RFW_HD int gather_wide_children(int bnode, const BuildArrays& A, WideChild* out) {
     const int n = A.n;
     int nch = 0;
-    if (bnode >= n - 1) {  // single-primitive tree
+    if (is_leaf_node(bnode, n)) {  // single-primitive tree
         out[0].bnode = bnode; out[0].first = bnode - (n - 1); out[0].count = 1;
         return 1;
     }
     int sn[16], sb[16];
     int sp = 0;
     {
-        const uint32_t w = A.decision[bnode];
+        const uint32_t w = A.decision[inner_index(bnode, n)];
         const int k = (int)dec_k8(w);
-        const int2 ch = A.children[bnode];
+        const int2 ch = A.children[inner_index(bnode, n)];
         sn[sp] = ch.y; sb[sp] = 8 - k; sp++;
         sn[sp] = ch.x; sb[sp] = k; sp++;
     }
@@ -202,15 +210,15 @@ RFW_HD int gather_wide_children(int bnode, const BuildArrays& A, WideChild* out)
         sp--;
         const int m = sn[sp];
         int j = sb[sp];
-        if (m >= n - 1) {
+        if (is_leaf_node(m, n)) {
             out[nch].bnode = m; out[nch].first = m - (n - 1); out[nch].count = 1; nch++;
             continue;
         }
-        const uint32_t w = A.decision[m];
+        const uint32_t w = A.decision[inner_index(m, n)];
         while (j > 1 && dec_ki(w, j) == 0u) j--;  // "use C(m, j-1)"
         if (j == 1) {
             if (dec_leaf(w)) {
-                const int2 rg = A.range[m];
+                const int2 rg = A.range[inner_index(m, n)];
                 out[nch].bnode = m; out[nch].first = rg.x; out[nch].count = rg.y - rg.x + 1; nch++;
             } else {
                 out[nch].bnode = m; out[nch].first = 0; out[nch].count = 0; nch++;
@@ -218,7 +226,7 @@ RFW_HD int gather_wide_children(int bnode, const BuildArrays& A, WideChild* out)
             continue;
         }
         const int k = (int)dec_ki(w, j);
-        const int2 ch = A.children[m];
+        const int2 ch = A.children[inner_index(m, n)];
         sn[sp] = ch.y; sb[sp] = j - k; sp++;
         sn[sp] = ch.x; sb[sp] = k; sp++;
     }

@@ -130,6 +130,11 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const uint64_t* _
 
 int radix_sort_tiles(int n) { return (n + SORT_TILE - 1) / SORT_TILE; }
 
+// in-place exclusive scan of `count` uint32 (single CTA; used for the builder's small compactions)
+void exclusive_scan_u32(uint32_t* data, int count, cudaStream_t stream) {
+    if (count > 0) k_sort_scan<<<1, 1024, 0, stream>>>(data, count);
+}
+
 // Sorts bits [begin_bit, end_bit) of the keys; ping-pongs between (keys, vals) and (keys_tmp, vals_tmp).
 // Returns 0 if the result is in (keys, vals), 1 if it is in the tmp buffers.  `hist` holds 256 * tiles words.
 int radix_sort_pairs(uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp, uint32_t* hist, int n, int begin_bit, int end_bit, cudaStream_t stream,

@@ -48,7 +48,10 @@ def t_tolerance(rays, t):
     return REL_T * np.abs(t) + ULPS_T * 2.0 ** -24 * scale / dlen
 
 
-def compare_hits(rays, gpu, ref, scene_lookup, label=""):
+def compare_hits(rays, gpu, ref, scene_lookup, label="", max_fraction=MAX_MISMATCH_FRACTION):
+    """max_fraction bounds the number of CLASSIFIED near-ties (unclassified ones are never allowed).  Authored assets
+    with coplanar duplicated faces (pica) need a looser count bound than the synthetic scenes: every pixel looking at
+    such a face pair is an exact-depth tie between two different triangles."""
     """scene_lookup(inst) -> (tris, 4x4 inverse matrix as float64 row-indexed) for the global instance id."""
     n = len(rays)
     assert len(gpu) == n and len(ref) == n
@@ -85,7 +88,7 @@ def compare_hits(rays, gpu, ref, scene_lookup, label=""):
     if miss.any():
         assert np.array_equal(gpu["t"][miss], ref["t"][miss]), f"{label}: miss records must carry tmax"
     bad = np.nonzero(~same)[0]
-    assert len(bad) <= max(2, int(MAX_MISMATCH_FRACTION * n)), f"{label}: {len(bad)} ID mismatches of {n}"
+    assert len(bad) <= max(2, int(max_fraction * n)), f"{label}: {len(bad)} ID mismatches of {n}"
     unexplained = []
     for i in bad:
         o = rays["origin"][i].astype(np.float64)

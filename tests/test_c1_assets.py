@@ -69,7 +69,9 @@ def test_c1_gpu_primary_cast_both_variants(oracle_mod, name):
         rays = cpu.primary_rays(view, w, h)
         ref = cpu.trace_closest(rays, mode=oracle_mod.MODE_BVH2)
         hits = gpu.cast_primary(view)
-        parity.compare_hits(rays, hits, ref, parity.lookup_from_desc(desc), f"{name}/{label}")
+        # pica has coplanar duplicated faces (exact depth ties between different triangles): looser COUNT bound, every
+        # disagreement must still classify as a near-tie
+        parity.compare_hits(rays, hits, ref, parity.lookup_from_desc(desc), f"{name}/{label}", max_fraction=5e-3 if name == "pica" else 2e-5)
         results[label] = hits
         st = gpu.build_stats()
         assert st["num_triangles"] == len(flat.meshes[0])
@@ -78,7 +80,7 @@ def test_c1_gpu_primary_cast_both_variants(oracle_mod, name):
     # golden (subsampled) pin on the flattened variant
     g = results["C1a"].reshape(h, w)[::sub, ::sub].reshape(-1)
     same = g["prim"] == gold["prim"]
-    assert same.mean() > 0.9999
+    assert same.mean() > (0.995 if name == "pica" else 0.9999)
     assert np.allclose(g["t"][same & (gold["prim"] >= 0)], gold["t"][same & (gold["prim"] >= 0)], rtol=2e-4, atol=1e-5)
     # both variants see the same surface
     a, b = results["C1a"], results["C1b"]
