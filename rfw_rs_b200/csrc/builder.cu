@@ -152,6 +152,36 @@ __device__ __forceinline__ float bins_area(const uint32_t lo[3], const uint32_t 
     return 2.0f * (ex * ey + ey * ez + ez * ex);
 }
 
+// segments with more items than this are split like the radix tree does (highest differing Morton bit): the top few
+// levels of a big scene are spatial-median splits either way, and one warp per segment would serialise on them
+static constexpr int SAH_BIG_SEGMENT = 4096;
+
+// lane 0: the top node of segment [begin, end) gets its two children (a treelet root when a side has one item, else a
+// new top node + a segment for the next level)
+__device__ void sah_emit_children(int begin, int end, int nl, int prims, int top, const int* __restrict__ items, const BuildArrays& A, int4* __restrict__ next_segs,
+                                  uint32_t* __restrict__ next_count, uint32_t* __restrict__ top_counter) {
+    const int n = A.n;
+    const int nr = (end - begin) - nl;
+    int child[2];
+    const int cb[2] = {begin, begin + nl}, cn[2] = {nl, nr};
+    for (int s = 0; s < 2; s++) {
+        if (cn[s] == 1) {
+            child[s] = items[cb[s]];
+        } else {
+            child[s] = 2 * n - 1 + (int)atomicAdd(top_counter, 1u);
+            next_segs[atomicAdd(next_count, 1u)] = make_int4(cb[s], cb[s] + cn[s], child[s], 0);
+        }
+        A.parent[child[s]] = top;
+    }
+    const int ti = inner_index(top, n);
+    A.children[ti] = make_int2(child[0], child[1]);
+    A.range[ti] = make_int2(0, prims - 1);  // only the COUNT of a top node is meaningful: its primitives are not contiguous
+    A.flags[ti] = 0;
+}
+
+__device__ __forceinline__ int item_first_pos(int node, const BuildArrays& A) { return is_leaf_node(node, A.n) ? node - (A.n - 1) : A.range[node].x; }
+__device__ __forceinline__ int item_last_pos(int node, const BuildArrays& A) { return is_leaf_node(node, A.n) ? node - (A.n - 1) : A.range[node].y; }
+
 // One warp splits one segment [begin, end) of the treelet array with 16-bin SAH on the best of 3 axes, partitions
 // it (stable) and emits the top node; children / next segments are written to the arrays.
 __device__ void sah_split_segment(int4 seg, int* __restrict__ items, int* __restrict__ items_tmp, const BuildArrays& A, SahBins& bins, int4* __restrict__ next_segs,
@@ -160,6 +190,27 @@ __device__ void sah_split_segment(int4 seg, int* __restrict__ items, int* __rest
     const uint32_t lt = (1u << lane) - 1u;
     const int begin = seg.x, end = seg.y, top = seg.z;
     const int n = A.n;
+    if (end - begin > SAH_BIG_SEGMENT) {
+        // a big segment is still a contiguous run of the Morton order (all its ancestors were split this way too)
+        if (lane == 0) {
+            const int pb = item_first_pos(items[begin], A), pl = item_first_pos(items[end - 1], A);
+            const int prims_big = item_last_pos(items[end - 1], A) - pb + 1;
+            const uint64_t kb = A.keys[pb], ke = A.keys[pl];
+            int nl_big = (end - begin) / 2;
+            if (kb != ke) {
+                const int prefix = clz64(kb ^ ke);
+                int lo = begin, hi = end - 1;  // key(lo) shares more than `prefix` bits with kb, key(hi) does not
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (clz64(kb ^ A.keys[item_first_pos(items[mid], A)]) > prefix) lo = mid; else hi = mid;
+                }
+                nl_big = lo - begin + 1;
+            }
+            sah_emit_children(begin, end, nl_big, prims_big, top, items, A, next_segs, next_count, top_counter);
+        }
+        __syncwarp();
+        return;
+    }
     // a. centroid bounds, primitive count
     float cmin[3] = {3e38f, 3e38f, 3e38f}, cmax[3] = {-3e38f, -3e38f, -3e38f};
     int prims = 0;
@@ -268,24 +319,7 @@ __device__ void sah_split_segment(int4 seg, int* __restrict__ items, int* __rest
         __syncwarp();
     }
     // e. children
-    if (lane == 0) {
-        const int nr = (end - begin) - nl;
-        int child[2];
-        const int cb[2] = {begin, begin + nl}, cn[2] = {nl, nr};
-        for (int s = 0; s < 2; s++) {
-            if (cn[s] == 1) {
-                child[s] = items[cb[s]];
-            } else {
-                child[s] = 2 * n - 1 + (int)atomicAdd(top_counter, 1u);
-                next_segs[atomicAdd(next_count, 1u)] = make_int4(cb[s], cb[s] + cn[s], child[s], 0);
-            }
-            A.parent[child[s]] = top;
-        }
-        const int ti = inner_index(top, n);
-        A.children[ti] = make_int2(child[0], child[1]);
-        A.range[ti] = make_int2(0, prims - 1);  // only the COUNT of a top node is meaningful: its primitives are not contiguous
-        A.flags[ti] = 0;
-    }
+    if (lane == 0) sah_emit_children(begin, end, nl, prims, top, items, A, next_segs, next_count, top_counter);
     __syncwarp();
 }
 

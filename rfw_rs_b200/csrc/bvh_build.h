@@ -144,7 +144,8 @@ RFW_HD void fit_cost_node(int node, const BuildArrays& A, const BuildParams& P) 
     }
     const int2 rg = A.range[inner_index(node, A.n)];
     const int count = rg.y - rg.x + 1;
-    const float c_leaf = (count <= P.pmax) ? area * (float)count * P.c_prim : 3.0e38f;
+    // a node of the SAH-built top tree can never be a leaf: its primitives are not contiguous in the sorted order
+    const float c_leaf = (count <= P.pmax && node < 2 * A.n - 1) ? area * (float)count * P.c_prim : 3.0e38f;
     const float c_internal = dist[8] + area * P.c_node;
     uint32_t w = (c_leaf <= c_internal) ? 1u : 0u;
     w |= kd[8] << 1;
