@@ -312,6 +312,12 @@ def main():
         extra["nodes_per_ray"] = st["nodes_visited"] / st["rays"]
         extra["tris_per_ray"] = st["tris_tested"] / st["rays"]
         extra["traversal_bytes_per_ray"] = extra["nodes_per_ray"] * 80 + extra["tris_per_ray"] * 48
+        # L2-side roofline: measured traversal bytes against a self-measured L2-resident read bandwidth
+        l2_peak = be.measure_l2_read_gbs(32 << 20, 50)
+        trav_gbs = extra["traversal_bytes_per_ray"] * N_RAYS / (kernel_ms / max(1, args.steps) / 1e3) / 1e9
+        extra["l2_roofline"] = {"peak_GBps": l2_peak, "peak_source": "k_l2_read microbenchmark: 32 MiB buffer, L1-bypassing loads, same run",
+                                "achieved_GBps": trav_gbs, "frac": trav_gbs / l2_peak if l2_peak else None,
+                                "note": "traversal bytes = nodes/ray x 80 B + tris/ray x 48 B requested by the SMs; 45% of them hit in L1 (ncu), the rest go to L2"}
         extra["hit_rate"] = hit_rate
         extra["bvh_build"] = {"blas_build_ms": bs["blas_build_ms"], "synchronize_wall_ms_incl_upload": sync_wall_ms, "wide_nodes": bs["blas_nodes"],
                               "bvh_bytes": bs["bvh_bytes"], "sah_cost": bs["sah_cost"]}

@@ -388,6 +388,9 @@ RFWB200_API int rfwb200_set_option(void* handle, const char* key, int64_t value)
 /* debug: copy wavefront queue `which` (0/1) to host: O, D, T (4 floats per path each; any may be NULL), the hit
  * state S of the last extend, and the queue's current count */
 RFWB200_API int rfwb200_debug_read_queue(void* handle, uint32_t which, float* out_O, float* out_D, float* out_T, float* out_S, uint32_t capacity, uint32_t* out_count);
+/* microbenchmark: read bandwidth (GB/s) of an L2-resident buffer of `bytes` (<= ~100 MB) streamed `iters` times with
+ * L1-bypassing loads — the denominator of the L2-side roofline of the traversal kernels */
+RFWB200_API int rfwb200_measure_l2_read_gbs(void* handle, uint64_t bytes, uint32_t iters, float* out_gbs);
 /* pinned host memory for the host-buffer entry points */
 RFWB200_API void* rfwb200_host_alloc(uint64_t bytes);
 RFWB200_API void rfwb200_host_free(void* ptr);

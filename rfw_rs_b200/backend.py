@@ -81,6 +81,7 @@ def load_library():
         "rfwb200_set_option": ([vp, C.c_char_p, C.c_int64], i32),
         "rfwb200_debug_read_queue": ([vp, u32, vp, vp, vp, vp, u32, vp], i32),
         "rfwb200_tile_layout": ([u32, u32, u32, vp, u32], u32),
+        "rfwb200_measure_l2_read_gbs": ([vp, u64, u32, vp], i32),
         "rfwb200_host_alloc": ([u64], vp),
         "rfwb200_host_free": ([vp], None),
         "rfwb200_last_error": ([], C.c_char_p),
@@ -320,6 +321,11 @@ class B200Backend:
         n = C.c_uint32(0)
         self._ck(self.L.rfwb200_debug_read_queue(self.h, which, _ptr(O), _ptr(D), _ptr(T), _ptr(S), capacity, C.addressof(n)), "debug_read_queue")
         return O, D, T, S, n.value
+
+    def measure_l2_read_gbs(self, nbytes=32 << 20, iters=50):
+        out = C.c_float(0)
+        self._ck(self.L.rfwb200_measure_l2_read_gbs(self.h, nbytes, iters, C.addressof(out)), "measure_l2_read_gbs")
+        return out.value
 
     def launch_count(self):
         return self.L.rfwb200_launch_count(self.h)

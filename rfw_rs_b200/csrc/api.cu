@@ -77,6 +77,8 @@ uint32_t rfwb200_tile_layout(uint32_t width, uint32_t height, uint32_t tile, uin
     return (uint32_t)order.size();
 }
 
+int rfwb200_measure_l2_read_gbs(void* handle, uint64_t bytes, uint32_t iters, float* out_gbs) { RFW_GUARD(handle); return b->measure_l2(bytes, iters, out_gbs); }
+
 void* rfwb200_host_alloc(uint64_t bytes) {
     void* p = nullptr;
     if (cudaMallocHost(&p, bytes) != cudaSuccess) { rfw::set_last_error("cudaMallocHost failed"); return nullptr; }

@@ -651,6 +651,14 @@ int Backend::debug_read_queue(uint32_t which, float* o, float* d, float* t, floa
     return RFWB200_OK;
 }
 
+int Backend::measure_l2(uint64_t bytes, uint32_t iters, float* out_gbs) {
+    DeviceScope device_scope(cfg.device);
+    BK_CUDA(device_scope.status, "cudaSetDevice");
+    BK_CUDA(measure_l2_read(stream, sm_count, (size_t)bytes, (int)iters, out_gbs), "measure_l2_read");
+    launch_count += 2;
+    return RFWB200_OK;
+}
+
 int Backend::set_option(const char* key, int64_t value) {
     if (!key) return fail(RFWB200_ERR_INVALID, "set_option: null key");
     const std::string k(key);

@@ -79,6 +79,7 @@ public:
     uint32_t tiles_per_rank() const;
 
     int set_option(const char* key, int64_t value);
+    int measure_l2(uint64_t bytes, uint32_t iters, float* out_gbs);
     int debug_read_queue(uint32_t which, float* o, float* d, float* t, float* s, uint32_t cap, uint32_t* cnt);
 
     RfwBuildStats build_stats{};

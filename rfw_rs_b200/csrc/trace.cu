@@ -133,6 +133,42 @@ cudaError_t trace_closest_counted(const TraceConfig& cfg, const SceneView& sv, c
     return cudaGetLastError();
 }
 
+// L2-resident read bandwidth microbenchmark (the denominator of the L2-side roofline): every CTA streams
+// the whole buffer `iters` times with ld.global.cg (L2 only, no L1 allocation); the buffer must fit the 126 MB L2.
+__global__ void __launch_bounds__(256) k_l2_read(const float4* __restrict__ buf, size_t n_vec, int iters, float* __restrict__ sink) {
+    float acc = 0.0f;
+    const size_t stride = (size_t)gridDim.x * 256;
+    for (int it = 0; it < iters; it++)
+        for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n_vec; i += stride) {
+            const float4 v = __ldcg(buf + i);
+            acc += v.x + v.y + v.z + v.w;
+        }
+    if (acc == 12345.678f) *sink = acc;  // keeps the loads alive
+}
+
+cudaError_t measure_l2_read(cudaStream_t stream, int sm_count, size_t bytes, int iters, float* out_gbs) {
+    float4* buf = nullptr;
+    float* sink = nullptr;
+    cudaError_t e = cudaMalloc(&buf, bytes);
+    if (e != cudaSuccess) return e;
+    cudaMalloc(&sink, 4);
+    cudaMemsetAsync(buf, 0, bytes, stream);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    const size_t n_vec = bytes / 16;
+    k_l2_read<<<sm_count * 8, 256, 0, stream>>>(buf, n_vec, 2, sink);  // warm the L2
+    cudaEventRecord(a, stream);
+    k_l2_read<<<sm_count * 8, 256, 0, stream>>>(buf, n_vec, iters, sink);
+    cudaEventRecord(b, stream);
+    e = cudaEventSynchronize(b);
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, a, b);
+    if (out_gbs) *out_gbs = ms > 0.0f ? (float)((double)n_vec * 16.0 * iters / (ms * 1e-3) / 1e9) : 0.0f;
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(buf); cudaFree(sink);
+    return e;
+}
+
 cudaError_t generate_pinhole_rays(cudaStream_t stream, const RfwCameraView3D& cam, uint32_t w, uint32_t h, RfwRay* d_rays) {
     const uint32_t n = w * h;
     if (n == 0) return cudaSuccess;
