@@ -213,7 +213,7 @@ int Backend::synchronize() {
     if (scene_dirty) {
         // ---- BLAS for dirty meshes ------------------------------------------------------------------
         BK_CUDA(cudaEventRecord(ev0, stream), "event");
-        const BuildParams blas_params{1.0f, 0.3f, 3, sah_treelet};
+        const BuildParams blas_params{1.0f, sah_c_prim, sah_pmax, sah_treelet};
         for (MeshRec& m : meshes) {
             if (!m.present || !m.dirty) continue;
             if (m.d_ttris) { cudaFree(m.d_ttris); m.d_ttris = nullptr; }
@@ -642,11 +642,11 @@ int Backend::debug_read_queue(uint32_t which, float* o, float* d, float* t, floa
     // which = 0/1: the live count of that queue; which + 2: the same buffers with the count the last extend/shade consumed
     const uint32_t live = which < 2 ? counts[which] : counts[5];
     which &= 1u;
-    const uint32_t n = std::min(std::min(live, cap), wf.max_paths);
+    const uint32_t n = (uint32_t)std::min<size_t>(std::min(live, cap), wf.capacity());
     if (o) BK_CUDA(cudaMemcpy(o, wf.d_O[which], (size_t)n * 16, cudaMemcpyDeviceToHost), "queue");
     if (d) BK_CUDA(cudaMemcpy(d, wf.d_D[which], (size_t)n * 16, cudaMemcpyDeviceToHost), "queue");
     if (t) BK_CUDA(cudaMemcpy(t, wf.d_T[which], (size_t)n * 16, cudaMemcpyDeviceToHost), "queue");
-    if (s) BK_CUDA(cudaMemcpy(s, wf.d_S, (size_t)std::min(cap, wf.max_paths) * 16, cudaMemcpyDeviceToHost), "queue");
+    if (s) BK_CUDA(cudaMemcpy(s, wf.d_S, std::min<size_t>(cap, wf.capacity()) * 16, cudaMemcpyDeviceToHost), "queue");
     if (cnt) *cnt = live;
     return RFWB200_OK;
 }
@@ -670,6 +670,13 @@ int Backend::set_option(const char* key, int64_t value) {
     else if (k == "chunk_rays") chunk_rays = (uint64_t)std::max<int64_t>(1024, value);
     else if (k == "max_depth") cfg.max_depth = (uint32_t)value;
     else if (k == "sah_treelet") { sah_treelet = (int)value; for (auto& m : meshes) if (m.present) m.dirty = true; scene_dirty = true; synchronized = false; }
+    else if (k == "sah_c_prim_milli" || k == "sah_pmax") {  // SAH leaf cost (x1000) / max triangles per leaf slot (1..3)
+        if (k == "sah_pmax") sah_pmax = (int)std::min<int64_t>(3, std::max<int64_t>(1, value));
+        else sah_c_prim = (float)value * 1e-3f;
+        for (auto& m : meshes) if (m.present) m.dirty = true;
+        scene_dirty = true; synchronized = false;
+    }
+    else if (k == "wave_paths") wf.wave_paths = (uint64_t)std::max<int64_t>(1, value);  // path slots per wavefront wave
     else if (k == "sample_count") sample_count = (uint32_t)value;  // debug: render a chosen sample index next
     else return fail(RFWB200_ERR_INVALID, "set_option: unknown key " + k);
     return RFWB200_OK;

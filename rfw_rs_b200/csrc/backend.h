@@ -130,6 +130,8 @@ private:
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> chunk_events;
     uint64_t chunk_rays = 1u << 21;
+    float sah_c_prim = 0.8f;  // SAH cost of one triangle test relative to one wide-node visit (BLAS); swept on C2/C4 (scripts/tune_leafcost.py)
+    int sah_pmax = 3;         // max triangles per leaf slot
     int sah_treelet = 8;  // binned-SAH refinement above LBVH treelets of this many primitives (0 = plain LBVH)
 
     // wavefront renderer

@@ -27,22 +27,29 @@ static constexpr uint32_t FULL = 0xFFFFFFFFu;
 static constexpr int PT_THREADS = 128;
 static constexpr int PT_SM_STACK = 12;
 
-template <int SM_STACK, int L_STACK>
-struct LaneStack {
-    uint2* sm;       // &shared[threadIdx.x], stride blockDim.x
-    uint2 local[L_STACK];
-    int sp;
-    __device__ __forceinline__ void push(uint2 v, int stride) {
-        if (sp < SM_STACK) sm[sp * stride] = v;
-        else if (sp - SM_STACK < L_STACK) local[sp - SM_STACK] = v;
-        sp++;
-    }
-    __device__ __forceinline__ uint2 pop(int stride) {
-        sp--;
-        if (sp < SM_STACK) return sm[sp * stride];
-        return local[(sp - SM_STACK) < L_STACK ? (sp - SM_STACK) : (L_STACK - 1)];
-    }
-};
+// Per-lane traversal stack: the first SM_STACK entries live in shared memory, laid out [entry][thread] so a warp's
+// accesses to one entry are 32 consecutive 8-byte words (conflict-free); deeper entries overflow to local memory.
+// Shared memory is addressed through its 32-bit window address with st/ld.shared (a generic pointer kept in a struct
+// made the compiler emit generic ST.E/LD.E and keep the stack pointer in local memory).
+__device__ __forceinline__ void sts_u2(uint32_t addr, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory"); }
+__device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+static constexpr int PT_L_STACK = 24;
+#define RFW_STACK_PUSH(v)                                                                   \
+    do {                                                                                    \
+        if (sp < SM_STACK) sts_u2(st_base + (uint32_t)sp * (uint32_t)(THREADS * 8), (v));  \
+        else if (sp - SM_STACK < PT_L_STACK) lstack[sp - SM_STACK] = (v);                   \
+        sp++;                                                                               \
+    } while (0)
+#define RFW_STACK_POP(dst)                                                                          \
+    do {                                                                                            \
+        sp--;                                                                                       \
+        if (sp < SM_STACK) (dst) = lds_u2(st_base + (uint32_t)sp * (uint32_t)(THREADS * 8));       \
+        else (dst) = lstack[(sp - SM_STACK) < PT_L_STACK ? (sp - SM_STACK) : (PT_L_STACK - 1)];     \
+    } while (0)
 
 struct TraceTuning {
     int refill_below;  // refill when fewer than this many lanes still traverse
@@ -56,9 +63,9 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
     const int lane = threadIdx.x & 31;
     const uint32_t lanemask_lt = (1u << lane) - 1u;
 
-    LaneStack<SM_STACK, 24> st;
-    st.sm = smem_stack + threadIdx.x;
-    st.sp = 0;
+    const uint32_t st_base = (uint32_t)__cvta_generic_to_shared(smem_stack) + threadIdx.x * 8u;
+    uint2 lstack[PT_L_STACK];
+    int sp = 0;
 
     bool active = false;
     bool more = true;
@@ -94,7 +101,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
                         active = true;
                         tmin = r0.w;
                         hit.inst = -1; hit.prim = -1; hit.t = r1.w; hit.u = 0.0f; hit.v = 0.0f;
-                        st.sp = 0;
+                        sp = 0;
                         ng = make_uint2(0u, 0x80000000u);
                         tg = make_uint2(0u, 0u);
                         if (sv.num_live == 0) {  // empty scene: nothing to traverse, the ray retires as a miss
@@ -129,15 +136,15 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
             if (active && tg.y == 0u) {
                 // (a) nothing at hand: pop (leaving the BLAS when its part of the stack is exhausted)
                 if (!RFW_NODE_HITS(ng)) {
-                    if (TWO_LEVEL && in_blas && st.sp == blas_base_sp) {
+                    if (TWO_LEVEL && in_blas && sp == blas_base_sp) {
                         in_blas = false;
                         rc.o = wo; rc.d = wd;
                         ray_setup_box(rc);
                         nodes = sv.tlas_nodes;
                     }
-                    if (st.sp == 0) done = true;
+                    if (sp == 0) done = true;
                     else {
-                        ng = st.pop(THREADS);
+                        RFW_STACK_POP(ng);
                         if (!RFW_NODE_HITS(ng)) { tg = ng; ng = make_uint2(0u, 0u); }  // a parked TLAS leaf group
                     }
                 }
@@ -147,7 +154,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
                     const int bit = 31 - __clz((int)hits_imask);
                     const uint32_t base = ng.x;
                     ng.y &= ~(1u << bit);
-                    if (RFW_NODE_HITS(ng)) st.push(ng, THREADS);
+                    if (RFW_NODE_HITS(ng)) RFW_STACK_PUSH(ng);
                     const uint32_t slot = (uint32_t)(bit - 24) ^ (rc.octinv4 & 7u);
                     const uint32_t rel = __popc(hits_imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
                     const float4* np = nodes + (size_t)(base + rel) * 5;
@@ -164,9 +171,9 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
                 const int tb = 31 - __clz((int)tg.y);
                 tg.y &= ~(1u << tb);
                 const InstanceRec* rec = sv.instances + __ldg(sv.tlas_refs + tg.x + (uint32_t)tb);
-                if (tg.y != 0u) st.push(tg, THREADS);
-                if (RFW_NODE_HITS(ng)) st.push(ng, THREADS);
-                blas_base_sp = st.sp;
+                if (tg.y != 0u) RFW_STACK_PUSH(tg);
+                if (RFW_NODE_HITS(ng)) RFW_STACK_PUSH(ng);
+                blas_base_sp = sp;
                 in_blas = true;
                 cur_inst = rec->inst_id;
                 xform_ray(*rec, wo, wd, rc.o, rc.d);

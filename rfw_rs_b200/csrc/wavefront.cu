@@ -27,7 +27,8 @@ namespace rfw {
 struct FrameParams {
     RfwCameraView3D cam;
     uint32_t width, height, tile, tiles_x, max_paths;
-    uint32_t sample, path_length;
+    uint32_t sample, path_length;  // sample = index of the wave's first sample; a path's own sample = sample + its wave slot b
+    uint32_t wave_spp, npix;       // samples per wave; pixels per frame (stride of the per-sample partial accumulators)
     float clamp_value;
     float sky[3];
 };
@@ -45,13 +46,14 @@ __device__ __forceinline__ bool slot_to_pixel(const FrameParams& fp, const uint3
 // ---- generate: ray_gen.comp:103-146 ------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_wf_generate(FrameParams fp, const uint32_t* __restrict__ owned_tiles, float4* __restrict__ O, float4* __restrict__ D,
                                                      uint32_t* __restrict__ counts) {
-    const uint32_t slot = blockIdx.x * 256 + threadIdx.x;
+    const uint32_t gslot = blockIdx.x * 256 + threadIdx.x;
+    const uint32_t b = gslot / fp.max_paths, slot = gslot - b * fp.max_paths;  // wave slot b = sample offset
     const int lane = threadIdx.x & 31;
     uint32_t pixel = 0;
-    const bool valid = slot < fp.max_paths && slot_to_pixel(fp, owned_tiles, slot, pixel);
+    const bool valid = b < fp.wave_spp && slot_to_pixel(fp, owned_tiles, slot, pixel);
     float3 o = f3(0, 0, 0), d = f3(0, 0, 1);
     if (valid) {
-        uint32_t seed = wang_hash(pixel * 16789u + fp.sample * 1791u);
+        uint32_t seed = wang_hash(pixel * 16789u + (fp.sample + b) * 1791u);
         const int sx = (int)(pixel % fp.width), sy = (int)(pixel / fp.width);
         float r0 = randf(seed), r1 = randf(seed), r2 = randf(seed), r3 = randf(seed);
         const float blade = (float)(int)(r0 * 9.0f);
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(256) k_wf_generate(FrameParams fp, const uint3
     if (valid) {
         const uint32_t k = base + __popc(m & ((1u << lane) - 1u));
         O[k] = f4(o.x, o.y, o.z, __uint_as_float(pixel));
-        D[k] = f4(d.x, d.y, d.z, 0.0f);
+        D[k] = f4(d.x, d.y, d.z, __uint_as_float(b));
     }
 }
 
@@ -141,11 +143,12 @@ __global__ void __launch_bounds__(128) k_wf_shade(FrameParams fp, ShadeScene ss,
         float nPdf = 0.0f;
         float3 sO = f3(0, 0, 0), sD = f3(0, 0, 1), sE = f3(0, 0, 0);
         float sDist = 0.0f;
-        uint32_t pixel = 0;
+        uint32_t pixel = 0, wave_b = 0;
         if (valid) {
             const float4 s4 = S[k], o4 = O[k], d4 = D[k];
             const float4 t4 = fp.path_length == 0 ? f4(1.0f, 1.0f, 1.0f, 1.0f) : T[k];
             pixel = __float_as_uint(o4.w);
+            wave_b = __float_as_uint(d4.w);
             const int inst = __float_as_int(s4.x), prim = __float_as_int(s4.y);
             const float t = s4.z;
             const float3 Dv = xyz(d4), Ov = xyz(o4);
@@ -165,7 +168,7 @@ __global__ void __launch_bounds__(128) k_wf_shade(FrameParams fp, ShadeScene ss,
                 const int mat_id = __float_as_int(q10.y);
                 const float tri_area = q10.w;
                 const ShadingData sd = extract_material(ss.materials + mat_id);
-                uint32_t seed = wang_hash(pixel * 16789u + fp.sample * 1791u + fp.path_length * 720898027u);  // :102-103
+                uint32_t seed = wang_hash(pixel * 16789u + (fp.sample + wave_b) * 1791u + fp.path_length * 720898027u);  // :102-103
                 const uint32_t bary = __float_as_uint(s4.w);
                 const float u = (float)(bary & 65535u) * (1.0f / 65535.0f), v = (float)(bary >> 16) * (1.0f / 65535.0f);
                 const float w = 1.0f - u - v;
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(128) k_wf_shade(FrameParams fp, ShadeScene ss,
                 }
             }
             if (add && (contrib.x != 0.0f || contrib.y != 0.0f || contrib.z != 0.0f)) {
-                float* a = accum + 4 * (size_t)pixel;
+                float* a = accum + 4 * ((size_t)wave_b * fp.npix + pixel);
                 atomicAdd(a + 0, contrib.x);
                 atomicAdd(a + 1, contrib.y);
                 atomicAdd(a + 2, contrib.z);
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(128) k_wf_shade(FrameParams fp, ShadeScene ss,
                 const uint32_t j = b + __popc(ms & ((1u << lane) - 1u));
                 shO[j] = f4(sO.x, sO.y, sO.z, 0.0f);
                 shD[j] = f4(sD.x, sD.y, sD.z, sDist);
-                shE[j] = f4(sE.x, sE.y, sE.z, __uint_as_float(pixel));
+                shE[j] = f4(sE.x, sE.y, sE.z, __uint_as_float(wave_b * fp.npix + pixel));  // index into the partial accumulators
             }
         }
         const uint32_t me = __ballot_sync(FULL, emit_ext);
@@ -268,7 +271,7 @@ __global__ void __launch_bounds__(128) k_wf_shade(FrameParams fp, ShadeScene ss,
             if (emit_ext) {
                 const uint32_t j = b + __popc(me & ((1u << lane) - 1u));
                 On[j] = f4(nO.x, nO.y, nO.z, __uint_as_float(pixel));
-                Dn[j] = f4(nD.x, nD.y, nD.z, 0.0f);
+                Dn[j] = f4(nD.x, nD.y, nD.z, __uint_as_float(wave_b));
                 Tn[j] = f4(nT.x, nT.y, nT.z, nPdf);
             }
         }
@@ -283,6 +286,22 @@ __global__ void k_wf_advance(uint32_t* counts, unsigned long long* stats, int cu
     counts[5] = counts[cur];  // debug: size of the queue the last extend/shade consumed
     counts[cur] = 0;
     counts[2] = 0;
+}
+
+// fold the wave's per-sample partial accumulators into the frame accumulator in SAMPLE ORDER (the image is then
+// independent of how many samples a wave carried and of the atomics' arrival order) and re-zero them for the next wave
+__global__ void __launch_bounds__(256) k_wf_reduce(FrameParams fp, const uint32_t* __restrict__ owned_tiles, float4* __restrict__ partial, float4* __restrict__ accum) {
+    const uint32_t slot = blockIdx.x * 256 + threadIdx.x;
+    uint32_t pixel;
+    if (slot >= fp.max_paths || !slot_to_pixel(fp, owned_tiles, slot, pixel)) return;
+    float4 a = accum[pixel];
+    for (uint32_t b = 0; b < fp.wave_spp; b++) {
+        float4* p = partial + (size_t)b * fp.npix + pixel;
+        const float4 v = *p;
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        *p = f4(0, 0, 0, 0);
+    }
+    accum[pixel] = a;
 }
 
 __global__ void __launch_bounds__(256) k_wf_finalize(FrameParams fp, const uint32_t* __restrict__ owned_tiles, const float4* __restrict__ accum, float4* __restrict__ out,
@@ -347,8 +366,9 @@ void Wavefront::release() {
     auto fr = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
     fr(d_owned_tiles); fr(d_morton_tiles);
     for (int i = 0; i < 2; i++) { fr(d_O[i]); fr(d_D[i]); fr(d_T[i]); }
-    fr(d_S); fr(d_shO); fr(d_shD); fr(d_shE); fr(d_accum); fr(d_output); fr(d_counts); fr(d_stats);
+    fr(d_S); fr(d_shO); fr(d_shD); fr(d_shE); fr(d_partial); fr(d_accum); fr(d_output); fr(d_counts); fr(d_stats);
     max_paths = 0;
+    wave_capacity = 0;
 }
 
 cudaError_t Wavefront::configure(uint32_t w, uint32_t h, uint32_t tile_size, uint32_t rank_, uint32_t world_) {
@@ -367,7 +387,25 @@ cudaError_t Wavefront::configure(uint32_t w, uint32_t h, uint32_t tile_size, uin
     WF_CK(cudaMalloc(&d_morton_tiles, sizeof(uint32_t) * n_tiles));
     WF_CK(cudaMemcpy(d_owned_tiles, owned.data(), sizeof(uint32_t) * owned.size(), cudaMemcpyHostToDevice));
     WF_CK(cudaMemcpy(d_morton_tiles, morton_tiles.data(), sizeof(uint32_t) * n_tiles, cudaMemcpyHostToDevice));
-    const size_t mp = std::max<uint32_t>(1, max_paths);
+    WF_CK(cudaMalloc(&d_accum, (size_t)w * h * sizeof(float4)));
+    WF_CK(cudaMalloc(&d_output, (size_t)w * h * sizeof(float4)));
+    WF_CK(cudaMalloc(&d_counts, 8 * sizeof(uint32_t)));
+    WF_CK(cudaMalloc(&d_stats, 4 * sizeof(unsigned long long)));
+    WF_CK(cudaMemset(d_accum, 0, (size_t)w * h * sizeof(float4)));
+    WF_CK(cudaMemset(d_output, 0, (size_t)w * h * sizeof(float4)));
+    WF_CK(cudaMemset(d_counts, 0, 8 * sizeof(uint32_t)));
+    WF_CK(cudaMemset(d_stats, 0, 4 * sizeof(unsigned long long)));
+    return ensure_wave(1);
+}
+
+// queues and partial accumulators for waves of `b` samples (grow-only)
+cudaError_t Wavefront::ensure_wave(uint32_t b) {
+    if (b <= wave_capacity) return cudaSuccess;
+    auto fr = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
+    for (int i = 0; i < 2; i++) { fr(d_O[i]); fr(d_D[i]); fr(d_T[i]); }
+    fr(d_S); fr(d_shO); fr(d_shD); fr(d_shE); fr(d_partial);
+    wave_capacity = 0;
+    const size_t mp = (size_t)std::max<uint32_t>(1, max_paths) * b;
     for (int i = 0; i < 2; i++) {
         WF_CK(cudaMalloc(&d_O[i], mp * sizeof(float4)));
         WF_CK(cudaMalloc(&d_D[i], mp * sizeof(float4)));
@@ -377,15 +415,20 @@ cudaError_t Wavefront::configure(uint32_t w, uint32_t h, uint32_t tile_size, uin
     WF_CK(cudaMalloc(&d_shO, mp * sizeof(float4)));
     WF_CK(cudaMalloc(&d_shD, mp * sizeof(float4)));
     WF_CK(cudaMalloc(&d_shE, mp * sizeof(float4)));
-    WF_CK(cudaMalloc(&d_accum, (size_t)w * h * sizeof(float4)));
-    WF_CK(cudaMalloc(&d_output, (size_t)w * h * sizeof(float4)));
-    WF_CK(cudaMalloc(&d_counts, 8 * sizeof(uint32_t)));
-    WF_CK(cudaMalloc(&d_stats, 4 * sizeof(unsigned long long)));
-    WF_CK(cudaMemset(d_accum, 0, (size_t)w * h * sizeof(float4)));
-    WF_CK(cudaMemset(d_output, 0, (size_t)w * h * sizeof(float4)));
-    WF_CK(cudaMemset(d_counts, 0, 8 * sizeof(uint32_t)));
-    WF_CK(cudaMemset(d_stats, 0, 4 * sizeof(unsigned long long)));
+    const size_t pb = (size_t)width * height * b * sizeof(float4);
+    WF_CK(cudaMalloc(&d_partial, pb));
+    WF_CK(cudaMemset(d_partial, 0, pb));
+    wave_capacity = b;
     return cudaSuccess;
+}
+
+uint32_t Wavefront::wave_spp_for(uint32_t spp) const {
+    // as many samples per wave as fit `wave_paths` path slots: deeper bounces then launch on queues large enough to
+    // fill the persistent grids (180 GB of HBM makes the 176 B/path of queue + partial accumulator state cheap)
+    const uint64_t mp = std::max<uint32_t>(1, max_paths), npix = std::max<uint64_t>(1, (uint64_t)width * height);
+    uint64_t b = std::max<uint64_t>(1, wave_paths / mp);
+    b = std::min<uint64_t>(b, 0xFFFFFFFFull / npix);  // partial-accumulator indices are 32-bit
+    return (uint32_t)std::min<uint64_t>(b, std::max(1u, spp));
 }
 
 static FrameParams make_params(const Wavefront& wf, const RfwCameraView3D& cam, uint32_t sample, uint32_t path_length) {
@@ -393,6 +436,7 @@ static FrameParams make_params(const Wavefront& wf, const RfwCameraView3D& cam, 
     fp.cam = cam;
     fp.width = wf.width; fp.height = wf.height; fp.tile = wf.tile; fp.tiles_x = wf.tiles_x; fp.max_paths = wf.max_paths;
     fp.sample = sample; fp.path_length = path_length;
+    fp.wave_spp = 1; fp.npix = wf.width * wf.height;
     fp.clamp_value = wf.clamp_value;
     fp.sky[0] = wf.sky[0]; fp.sky[1] = wf.sky[1]; fp.sky[2] = wf.sky[2];
     return fp;
@@ -408,25 +452,32 @@ cudaError_t Wavefront::clear(cudaStream_t stream) {
 cudaError_t Wavefront::render(cudaStream_t stream, const SceneView& sv, const ShadeScene& ss, const RfwCameraView3D& cam, uint32_t first_sample, uint32_t spp, uint32_t depth) {
     if (max_paths == 0) return cudaSuccess;
     const int shade_blocks = sm_count * 8;
-    for (uint32_t s = 0; s < spp; s++) {
+    const uint32_t wave = wave_spp_for(spp);
+    WF_CK(ensure_wave(wave));
+    const TraceTuning tune{refill_below, tri_batch};
+    for (uint32_t s = 0; s < spp; s += wave) {
         FrameParams fp = make_params(*this, cam, first_sample + s, 0);
+        fp.wave_spp = std::min(wave, spp - s);
+        const uint32_t cap = max_paths * fp.wave_spp;
         WF_CK(cudaMemsetAsync(d_counts, 0, 8 * sizeof(uint32_t), stream));
-        k_wf_generate<<<(max_paths + 255) / 256, 256, 0, stream>>>(fp, d_owned_tiles, d_O[0], d_D[0], d_counts);
+        k_wf_generate<<<(cap + 255) / 256, 256, 0, stream>>>(fp, d_owned_tiles, d_O[0], d_D[0], d_counts);
         launches++;
         for (uint32_t b = 0; b < depth; b++) {
             const int cur = b & 1, nxt = cur ^ 1;
             fp.path_length = b;
             ExtendIO eio{d_O[cur], d_D[cur], d_counts + cur, d_S};
-            if (sv.two_level) WF_CK((launch_persistent_io<ExtendIO, false, true>(stream, sm_count, 0, TraceTuning{refill_below, tri_batch}, sv, eio, max_paths, d_counts + 3)));
-            else WF_CK((launch_persistent_io<ExtendIO, false, false>(stream, sm_count, 0, TraceTuning{refill_below, tri_batch}, sv, eio, max_paths, d_counts + 3)));
+            if (sv.two_level) WF_CK((launch_persistent_io<ExtendIO, false, true>(stream, sm_count, 0, tune, sv, eio, cap, d_counts + 3)));
+            else WF_CK((launch_persistent_io<ExtendIO, false, false>(stream, sm_count, 0, tune, sv, eio, cap, d_counts + 3)));
             k_wf_shade<<<shade_blocks, 128, 0, stream>>>(fp, ss, d_S, d_O[cur], d_D[cur], d_T[cur], d_O[nxt], d_D[nxt], d_T[nxt], d_shO, d_shD, d_shE,
-                                                         reinterpret_cast<float*>(d_accum), d_counts + cur, d_counts + nxt, d_counts + 2);
-            ConnectIO cio{d_shO, d_shD, d_shE, d_counts + 2, reinterpret_cast<float*>(d_accum)};
-            if (sv.two_level) WF_CK((launch_persistent_io<ConnectIO, true, true>(stream, sm_count, 0, TraceTuning{refill_below, tri_batch}, sv, cio, max_paths, d_counts + 4)));
-            else WF_CK((launch_persistent_io<ConnectIO, true, false>(stream, sm_count, 0, TraceTuning{refill_below, tri_batch}, sv, cio, max_paths, d_counts + 4)));
+                                                         reinterpret_cast<float*>(d_partial), d_counts + cur, d_counts + nxt, d_counts + 2);
+            ConnectIO cio{d_shO, d_shD, d_shE, d_counts + 2, reinterpret_cast<float*>(d_partial)};
+            if (sv.two_level) WF_CK((launch_persistent_io<ConnectIO, true, true>(stream, sm_count, 0, tune, sv, cio, cap, d_counts + 4)));
+            else WF_CK((launch_persistent_io<ConnectIO, true, false>(stream, sm_count, 0, tune, sv, cio, cap, d_counts + 4)));
             k_wf_advance<<<1, 1, 0, stream>>>(d_counts, d_stats, cur);
             launches += 4;
         }
+        k_wf_reduce<<<(max_paths + 255) / 256, 256, 0, stream>>>(fp, d_owned_tiles, d_partial, d_accum);
+        launches++;
     }
     return cudaGetLastError();
 }

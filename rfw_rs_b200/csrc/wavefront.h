@@ -41,6 +41,8 @@ struct Wavefront {
     uint32_t tiles_x = 0, tiles_y = 0;
     uint32_t n_owned_tiles = 0, tiles_per_rank = 0;
     uint32_t max_paths = 0;              // owned tiles * tile * tile
+    uint32_t wave_capacity = 0;          // samples per wave the queues are allocated for (queue slots = max_paths * wave_capacity)
+    uint64_t wave_paths = 1ull << 25;    // target number of path slots per wave (option "wave_paths")
     float clamp_value = 10.0f;
     float sky[3] = {0, 0, 0};
     // device buffers
@@ -53,6 +55,7 @@ struct Wavefront {
     float4* d_shO = nullptr;             // shadow queue
     float4* d_shD = nullptr;
     float4* d_shE = nullptr;
+    float4* d_partial = nullptr;         // per-sample partial accumulators of the current wave: wave_capacity * width*height
     float4* d_accum = nullptr;           // width*height
     float4* d_output = nullptr;          // width*height
     uint32_t* d_counts = nullptr;        // [0],[1] path counts (ping/pong), [2] shadow count, [3..5] work counters
@@ -65,6 +68,9 @@ struct Wavefront {
 
     cudaError_t configure(uint32_t w, uint32_t h, uint32_t tile_size, uint32_t rank_, uint32_t world_);
     void release();
+    cudaError_t ensure_wave(uint32_t samples_per_wave);
+    uint32_t wave_spp_for(uint32_t spp) const;
+    size_t capacity() const { return (size_t)max_paths * wave_capacity; }
     // `spp` frames starting at sample index `first_sample`, `depth` segments each; asynchronous on `stream`
     cudaError_t render(cudaStream_t stream, const SceneView& sv, const ShadeScene& ss, const RfwCameraView3D& cam, uint32_t first_sample, uint32_t spp, uint32_t depth);
     cudaError_t clear(cudaStream_t stream);

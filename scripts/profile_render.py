@@ -7,8 +7,9 @@ spp, depth, grid = int(os.environ.get("SPP", 4)), int(os.environ.get("DEPTH", 5)
 desc = scenes.instanced_scene(grid=grid, subdiv=3, n_lights=16)
 be = backend.B200Backend(w, h, sky=(0.3, 0.35, 0.5)); desc.apply(be)
 view = scenes.camera_view((0.0, 14.0, -62.0), (0.0, -0.25, 1.0), w, h)
+if "WAVE_PATHS" in os.environ: be.set_option("wave_paths", int(os.environ["WAVE_PATHS"]))
 be.render_spp(view, 1, depth); be.reset_accumulator()
 for _ in range(int(os.environ.get("REPS", 2))):
     be.reset_accumulator(); be.render_spp(view, spp, depth)
     rs = be.render_stats(); print(rs, "Msamples/s", rs["samples"] / rs["render_ms"] / 1e3, "Mrays/s", (rs["extension_rays"] + rs["shadow_rays"]) / rs["render_ms"] / 1e3)
-print("l2 read GB/s", be.measure_l2_read_gbs(32 << 20, 50), "64MB:", be.measure_l2_read_gbs(64 << 20, 30), "512MB (HBM):", be.measure_l2_read_gbs(512 << 20, 5))
+if os.environ.get("L2", "0") == "1": print("l2 read GB/s", be.measure_l2_read_gbs(32 << 20, 50), "64MB:", be.measure_l2_read_gbs(64 << 20, 30), "512MB (HBM):", be.measure_l2_read_gbs(512 << 20, 5))
