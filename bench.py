@@ -166,7 +166,7 @@ def path_tracing_extra(backend_mod, scenes, torch, rank, world, spp, dist):
         be = backend_mod.B200Backend(w, h, device=torch.cuda.current_device(), tile_size=tile, rank=rank, world=world, sky=(0.3, 0.35, 0.5))
         desc.apply(be)
         view = scenes.camera_view((0.0, 14.0, -62.0), (0.0, -0.25, 1.0), w, h)
-        be.render_spp(view, 1, depth)  # warm-up frame
+        be.render_spp(view, spp, depth)  # warm-up pass of the same shape (allocates the wave queues, warms the L2)
         be.reset_accumulator()
     except Exception as ex:
         err = repr(ex)

@@ -31,7 +31,11 @@
 //     triangle it visits first, intersection.glsl:30).
 //   * the blue-noise sampler (first 256 samples, ray_gen.comp:72-91) is replaced by the hash RNG the
 //     reference uses afterwards, so CPU and GPU consume identical streams.
-//   * textures / skybox texture are not sampled: constant sky radiance.
+//   * textures are sampled in software with the explicit-LOD rules of the reference's samplers (material
+//     textures: Repeat, bilinear at level 0, nearest above; skybox: ClampToEdge, bilinear at level path_length —
+//     backends/gpu-rt/src/lib.rs:1026-1034, :471-480) at their submitted size (the reference resizes every
+//     texture to 1024x1024 with a third-party resampler, src/lib.rs:1235-1244); without a skybox the miss
+//     radiance is a constant colour.
 //   * slab tests drop NaN lanes (0 * inf) instead of propagating them.
 //   * det epsilon is a parameter (reference: 1e-4 GLSL / 1e-6 Rust twin); soups use 0.
 
@@ -329,7 +333,67 @@ enum { MODE_MBVH = 0, MODE_BVH2 = 1, MODE_BRUTE = 2 };
 
 struct Counters { uint64_t nodes = 0, tris = 0; };
 
+// Texture as submitted through set_textures / set_skybox (TextureData, crates/rfw-backend/src/structs.rs:197-249):
+// RGBA8 after the BGRA swizzle, mip levels contiguous (offset_for_level).
+struct Texture {
+    uint32_t width = 0, height = 0, mips = 0;
+    std::vector<uint8_t> rgba;
+    void set(uint32_t w, uint32_t h, uint32_t mip_levels, uint32_t format, const uint8_t* bytes, uint64_t nbytes) {
+        width = w; height = h; mips = 0; rgba.clear();
+        size_t texels = 0;
+        for (uint32_t l = 0; l < std::max(1u, mip_levels); l++) {
+            const size_t lw = w >> l, lh = h >> l;
+            if (lw == 0 || lh == 0 || (texels + lw * lh) * 4 > nbytes) break;
+            texels += lw * lh; mips++;
+        }
+        rgba.assign(bytes, bytes + texels * 4);
+        if (format == 0) for (size_t i = 0; i < texels; i++) std::swap(rgba[4 * i], rgba[4 * i + 2]);  // BGRA8 -> RGBA8
+    }
+    void texel(size_t idx, float out[4]) const { for (int c = 0; c < 4; c++) out[c] = (float)rgba[4 * idx + c] * (1.0f / 255.0f); }
+    static int wrap(int i, int n, bool repeat) {
+        if (repeat) { i %= n; return i < 0 ? i + n : i; }
+        return i < 0 ? 0 : (i >= n ? n - 1 : i);
+    }
+    // textureLod with an integer level: bilinear when `linear`, else nearest
+    void sample_level(float u, float v, int level, bool repeat, bool linear, float out[4]) const {
+        level = level < 0 ? 0 : (level >= (int)mips ? (int)mips - 1 : level);
+        size_t off = 0;
+        for (int i = 0; i < level; i++) off += (size_t)(width >> i) * (height >> i);
+        const int w = (int)(width >> level), h = (int)(height >> level);
+        if (repeat) { u -= std::floor(u); v -= std::floor(v); }
+        if (!linear) {
+            const int x = wrap((int)std::floor(u * (float)w), w, repeat), y = wrap((int)std::floor(v * (float)h), h, repeat);
+            texel(off + (size_t)y * w + x, out);
+            return;
+        }
+        const float x = u * (float)w - 0.5f, y = v * (float)h - 0.5f;
+        const float x0f = std::floor(x), y0f = std::floor(y);
+        const float fx = x - x0f, fy = y - y0f;
+        const int x0 = wrap((int)x0f, w, repeat), x1 = wrap((int)x0f + 1, w, repeat);
+        const int y0 = wrap((int)y0f, h, repeat), y1 = wrap((int)y0f + 1, h, repeat);
+        float c00[4], c10[4], c01[4], c11[4];
+        texel(off + (size_t)y0 * w + x0, c00); texel(off + (size_t)y0 * w + x1, c10);
+        texel(off + (size_t)y1 * w + x0, c01); texel(off + (size_t)y1 * w + x1, c11);
+        const float w00 = (1.0f - fx) * (1.0f - fy), w10 = fx * (1.0f - fy), w01 = (1.0f - fx) * fy, w11 = fx * fy;
+        for (int c = 0; c < 4; c++) out[c] = c00[c] * w00 + c10[c] * w10 + c01[c] * w01 + c11[c] * w11;
+    }
+    // fetchTexel (shade.comp:268-271) through the material sampler: LOD <= 0 magnifies (Linear), LOD > 0 minifies (Nearest)
+    void fetch(float u, float v, int level, float out[4]) const { sample_level(u, v, level, true, level <= 0, out); }
+    // fetchTexelTrilinear (shade.comp:273-281), MIPLEVELCOUNT = 5 (:39)
+    void fetch_trilinear(float lambda, float u, float v, float out[4]) const {
+        const int level0 = std::min(4, (int)lambda);
+        const int level1 = std::min(4, level0 + 1);
+        const float f = lambda - std::floor(lambda);
+        float p0[4], p1[4];
+        fetch(u, v, level0, p0); fetch(u, v, level1, p1);
+        for (int c = 0; c < 4; c++) out[c] = (1.0f - f) * p0[c] + f * p1[c];
+    }
+};
+
 struct Scene {
+    std::vector<Texture> textures;
+    Texture skybox;
+    bool has_sky = false;
     std::map<uint32_t, Mesh> meshes;
     std::map<uint32_t, std::vector<M4>> instance_lists;
     std::vector<Instance> instances;  // live ones, TLAS order
@@ -877,7 +941,15 @@ static V3 trace_path(const Scene& sc, const RfwCameraView3D& cam, int w, int h, 
         st.extension_rays++;
         st.segments++;
         if (hit.inst < 0) {  // shade.comp:90-96
-            V3 c = throughput * sky * (1.0f / bsdfPdf);
+            V3 skyc = sky;
+            if (sc.has_sky) {
+                const float su = 0.5f * (1.0f + std::atan2(D.x, -D.z) * (1.0f / 3.14159265359f));
+                const float sv = 1.0f - std::acos(std::fmin(std::fmax(D.y, -1.0f), 1.0f)) * (1.0f / 3.14159265359f);  // |D.y| can exceed 1 by an ulp: acos -> NaN
+                float px[4];
+                sc.skybox.sample_level(su, sv, path_length, false, true, px);  // textureLod(skybox, uv, path_length)
+                skyc = V3(px[0], px[1], px[2]);
+            }
+            V3 c = throughput * skyc * (1.0f / bsdfPdf);
             clamp_intensity(c, clampv);
             acc = acc + c;
             break;
@@ -886,6 +958,8 @@ static V3 trace_path(const Scene& sc, const RfwCameraView3D& cam, int w, int h, 
         const Mesh& mesh = sc.meshes.find(in->mesh)->second;
         const RfwRTTriangle& tri = mesh.tris[hit.prim];
         ShadingData sd = extract(sc.materials[tri.mat_id]);
+        const RfwDeviceMaterial& mat = sc.materials[tri.mat_id];
+        const uint32_t mflags = mat.flags;
         seed = wang_hash((uint32_t)path_id * 16789u + sample * 1791u + (uint32_t)path_length * 720898027u);  // shade.comp:102-103
         // hit barycentrics go through the 16-bit pack of ray_gen.comp:66-69 / shade.comp:41-46
         const uint32_t bu = (uint32_t)(65535.0f * hit.u), bv = (uint32_t)(65535.0f * hit.v);
@@ -900,7 +974,7 @@ static V3 trace_path(const Scene& sc, const RfwCameraView3D& cam, int w, int h, 
         T3 = normalize(xform_vec(in->normal, T3));
         const V3 B = cross(N, T3) * Tw;
         const V3 P = O + D * hit.t;
-        if (sd.color.x > 1.0f || sd.color.y > 1.0f || sd.color.z > 1.0f) {  // :128-160
+        if ((sd.color.x > 1.0f || sd.color.y > 1.0f || sd.color.z > 1.0f) && !(mflags & 16u)) {  // :128-160 (deferred when an emissive map is present)
             V3 c(0.0f);
             const float DdotNL = -dot(D, N);
             if (DdotNL > 0) {
@@ -916,6 +990,22 @@ static V3 trace_path(const Scene& sc, const RfwCameraView3D& cam, int w, int h, 
             }
             acc = acc + c;
             break;
+        }
+        if (mflags & 0x3Fu) {  // :162-175
+            const float lambda = std::sqrt(tri.lod) + std::log2(cam.spread_angle * (1.0f / std::fabs(dot(D, N))));
+            const float tu = wgt * tri.u0 + u * tri.u1 + v * tri.u2;
+            const float tv = wgt * tri.v0 + u * tri.v1 + v * tri.v2;
+            if ((mflags & 1u) && mat.diffuse_map >= 0 && (size_t)mat.diffuse_map < sc.textures.size()) {
+                float px[4];
+                sc.textures[mat.diffuse_map].fetch_trilinear(lambda, tu, tv, px);
+                sd.color = sd.color * V3(px[0], px[1], px[2]);
+            }
+            if ((mflags & 2u) && mat.normal_map >= 0 && (size_t)mat.normal_map < sc.textures.size()) {
+                float px[4];
+                sc.textures[mat.normal_map].fetch(tu, tv, (int)lambda, px);
+                const V3 m((px[0] - 0.5f) * 2.0f, (px[1] - 0.5f) * 2.0f, (px[2] - 0.5f) * 2.0f);
+                N = normalize(T3 * m.x + B * m.y + N * m.z);  // mat3(T, B, N) * m
+            }
         }
         const bool backFacing = dot(D, gN) >= 0.0f;  // :177-181
         if (backFacing) { N = N * -1.0f; gN = gN * -1.0f; }
@@ -991,6 +1081,25 @@ void orc_set_instances(void* s, uint32_t mesh, const float* matrices, uint32_t n
     if (n) std::memcpy(v.data(), matrices, (size_t)n * 64);
 }
 void orc_set_materials(void* s, const RfwDeviceMaterial* m, uint32_t n) { ((Scene*)s)->materials.assign(m, m + n); }
+void orc_set_num_textures(void* s, uint32_t n) { ((Scene*)s)->textures.resize(n); }
+void orc_set_texture(void* s, uint32_t i, uint32_t w, uint32_t h, uint32_t mips, uint32_t format, const uint8_t* bytes, uint64_t nbytes) {
+    Scene& sc = *(Scene*)s;
+    if (i >= sc.textures.size()) sc.textures.resize(i + 1);
+    sc.textures[i].set(w, h, mips, format, bytes, nbytes);
+}
+void orc_set_skybox(void* s, uint32_t w, uint32_t h, uint32_t mips, uint32_t format, const uint8_t* bytes, uint64_t nbytes) {
+    Scene& sc = *(Scene*)s;
+    sc.has_sky = bytes != nullptr && w > 0 && h > 0;
+    if (sc.has_sky) sc.skybox.set(w, h, mips, format, bytes, nbytes);
+}
+// debug / known-answer access to the samplers: mode 0 = fetchTexel(level), 1 = fetchTexelTrilinear(lambda), 2 = skybox level
+void orc_sample_texture(void* s, int tex, int mode, float u, float v, float lod, float* out) {
+    const Scene& sc = *(Scene*)s;
+    const Texture& t = tex < 0 ? sc.skybox : sc.textures[tex];
+    if (mode == 0) t.fetch(u, v, (int)lod, out);
+    else if (mode == 1) t.fetch_trilinear(lod, u, v, out);
+    else t.sample_level(u, v, (int)lod, false, true, out);
+}
 void orc_set_area_lights(void* s, const RfwAreaLight* l, uint32_t n) { ((Scene*)s)->area_lights.assign(l, l + n); }
 void orc_set_point_lights(void* s, const RfwPointLight* l, uint32_t n) { ((Scene*)s)->point_lights.assign(l, l + n); }
 void orc_set_spot_lights(void* s, const RfwSpotLight* l, uint32_t n) { ((Scene*)s)->spot_lights.assign(l, l + n); }

@@ -42,6 +42,10 @@ def lib():
         L.orc_set_instances.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         for nm in ("materials", "area_lights", "point_lights", "spot_lights", "directional_lights"):
             getattr(L, "orc_set_" + nm).argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.orc_set_num_textures.argtypes = [C.c_void_p, C.c_uint32]
+        L.orc_set_texture.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64]
+        L.orc_set_skybox.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64]
+        L.orc_sample_texture.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p]
         L.orc_build.argtypes = [C.c_void_p]
         L.orc_build.restype = C.c_double
         L.orc_trace_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p]
@@ -117,6 +121,26 @@ class OracleBackend:
 
     def set_materials(self, m):
         self._set("materials", m, 96)
+
+    def set_textures(self, textures=None, changed=None):
+        textures = list(textures or [])
+        self.L.orc_set_num_textures(self.h, len(textures))
+        for i, t in enumerate(textures):
+            b = np.ascontiguousarray(t.bytes, dtype=np.uint8)
+            self.L.orc_set_texture(self.h, i, t.width, t.height, t.mip_levels, t.format, _ptr(b), b.size)
+
+    def set_skybox(self, skybox=None):
+        if skybox is None:
+            self.L.orc_set_skybox(self.h, 0, 0, 0, 0, None, 0)
+        else:
+            b = np.ascontiguousarray(skybox.bytes, dtype=np.uint8)
+            self.L.orc_set_skybox(self.h, skybox.width, skybox.height, skybox.mip_levels, skybox.format, _ptr(b), b.size)
+
+    def sample_texture(self, tex, mode, u, v, lod):
+        """Known-answer access to the samplers: tex index (-1 = skybox); mode 0 fetchTexel(level), 1 trilinear(lambda), 2 skybox level."""
+        out = np.zeros(4, dtype=np.float32)
+        self.L.orc_sample_texture(self.h, tex, mode, u, v, lod, _ptr(out))
+        return out
 
     def set_area_lights(self, l):
         self._set("area_lights", l, 96)

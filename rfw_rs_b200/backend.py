@@ -194,8 +194,24 @@ class B200Backend:
     def set_materials(self, materials, changed=None):
         self._set_array("rfwb200_set_materials", materials, 96, "set_materials")
 
+    @staticmethod
+    def _texture_data(t):
+        d = wire.CTextureData()
+        b = np.ascontiguousarray(t.bytes, dtype=np.uint8)
+        d.width, d.height, d.mip_levels, d.format = t.width, t.height, t.mip_levels, t.format
+        d.bytes, d.num_bytes = _ptr(b), b.size
+        return d, b
+
     def set_textures(self, textures=None, changed=None):
-        self._ck(self.L.rfwb200_set_textures(self.h, None, 0, None), "set_textures")
+        """textures: objects with width/height/mip_levels/format/bytes (scenes.Texture)."""
+        textures = list(textures or [])
+        if not textures:
+            self._ck(self.L.rfwb200_set_textures(self.h, None, 0, None), "set_textures")
+            return
+        packed = [self._texture_data(t) for t in textures]  # keeps the byte arrays alive for the call
+        arr = (wire.CTextureData * len(packed))(*[p[0] for p in packed])
+        ch = None if changed is None else np.ascontiguousarray(changed, dtype=np.uint32)
+        self._ck(self.L.rfwb200_set_textures(self.h, C.addressof(arr), len(packed), None if ch is None else _ptr(ch)), "set_textures")
 
     def set_point_lights(self, lights, changed=None):
         self._set_array("rfwb200_set_point_lights", lights, 32, "set_point_lights")
@@ -210,7 +226,11 @@ class B200Backend:
         self._set_array("rfwb200_set_directional_lights", lights, 32, "set_directional_lights")
 
     def set_skybox(self, skybox=None):
-        self._ck(self.L.rfwb200_set_skybox(self.h, None), "set_skybox")
+        if skybox is None:
+            self._ck(self.L.rfwb200_set_skybox(self.h, None), "set_skybox")
+            return
+        d, _keep = self._texture_data(skybox)
+        self._ck(self.L.rfwb200_set_skybox(self.h, C.addressof(d)), "set_skybox")
 
     def set_skins(self, skins=(), changed=None):
         self._ck(self.L.rfwb200_set_skins(self.h, len(skins)), "set_skins")

@@ -31,7 +31,7 @@ int rfwb200_set_3d_mesh(void* handle, uint32_t id, const RfwMeshData3D* data) { 
 int rfwb200_unload_3d_meshes(void* handle, const uint32_t* ids, uint32_t num) { RFW_GUARD(handle); return b->unload_3d_meshes(ids, num); }
 int rfwb200_set_3d_instances(void* handle, uint32_t mesh, const RfwInstancesData3D* data) { RFW_GUARD(handle); return b->set_3d_instances(mesh, data); }
 int rfwb200_set_materials(void* handle, const RfwDeviceMaterial* m, uint32_t num, const uint32_t*) { RFW_GUARD(handle); return b->set_materials(m, num); }
-int rfwb200_set_textures(void* handle, const RfwTextureData*, uint32_t, const uint32_t*) { RFW_GUARD(handle); return b ? RFWB200_OK : RFWB200_ERR_INVALID; }
+int rfwb200_set_textures(void* handle, const RfwTextureData* t, uint32_t n, const uint32_t* changed) { RFW_GUARD(handle); return b->set_textures(t, n, changed); }
 int rfwb200_synchronize(void* handle) { RFW_GUARD(handle); return b->synchronize(); }
 int rfwb200_render(void* handle, const RfwCameraView3D* view, uint32_t mode) { RFW_GUARD(handle); return b->render(view, mode); }
 int rfwb200_resize(void* handle, uint32_t w, uint32_t h, double) { RFW_GUARD(handle); return b->resize(w, h); }
@@ -39,7 +39,7 @@ int rfwb200_set_point_lights(void* handle, const RfwPointLight* l, uint32_t n, c
 int rfwb200_set_spot_lights(void* handle, const RfwSpotLight* l, uint32_t n, const uint32_t*) { RFW_GUARD(handle); return b->set_spot_lights(l, n); }
 int rfwb200_set_area_lights(void* handle, const RfwAreaLight* l, uint32_t n, const uint32_t*) { RFW_GUARD(handle); return b->set_area_lights(l, n); }
 int rfwb200_set_directional_lights(void* handle, const RfwDirectionalLight* l, uint32_t n, const uint32_t*) { RFW_GUARD(handle); return b->set_directional_lights(l, n); }
-int rfwb200_set_skybox(void* handle, const RfwTextureData*) { RFW_GUARD(handle); return b ? RFWB200_OK : RFWB200_ERR_INVALID; }
+int rfwb200_set_skybox(void* handle, const RfwTextureData* t) { RFW_GUARD(handle); return b->set_skybox(t); }
 int rfwb200_set_skins(void* handle, uint32_t) { RFW_GUARD(handle); return b ? RFWB200_OK : RFWB200_ERR_INVALID; }
 int rfwb200_set_2d_mesh(void* handle, uint32_t, const void*, uint32_t, int32_t) { RFW_GUARD(handle); return b ? RFWB200_OK : RFWB200_ERR_INVALID; }
 int rfwb200_set_2d_instances(void* handle, uint32_t, const float*, uint32_t) { RFW_GUARD(handle); return b ? RFWB200_OK : RFWB200_ERR_INVALID; }

@@ -99,6 +99,8 @@ Backend::~Backend() {
     d_instances.release(); d_inst_shading.release(); d_materials.release();
     d_area.release(); d_point.release(); d_spot.release(); d_dir.release();
     d_rays.release(); d_hits.release(); d_occ.release();
+    for (auto& t : textures) t.texels.release();
+    skybox.texels.release(); d_tex_desc.release();
     wf.release();
     if (d_counter) cudaFree(d_counter);
     if (d_counters3) cudaFree(d_counters3);
@@ -171,6 +173,69 @@ int Backend::set_materials(const RfwDeviceMaterial* m, uint32_t num) {
     synchronized = false;
     return RFWB200_OK;
 }
+// BGRA8 -> RGBA8 in place (DataFormat::BGRA8, crates/rfw-backend/src/structs.rs:190-195)
+__global__ void __launch_bounds__(256) k_tex_swizzle_bgra(uchar4* __restrict__ texels, size_t n) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const uchar4 c = texels[i];
+    texels[i] = make_uchar4(c.z, c.y, c.x, c.w);
+}
+
+int Backend::upload_texture(TextureRec& rec, const RfwTextureData& t, const char* what) {
+    if (t.width == 0 || t.height == 0 || !t.bytes) return fail(RFWB200_ERR_INVALID, std::string(what) + ": empty texture");
+    // levels actually usable: both dimensions >= 1 and the bytes present (TextureData::offset_for_level layout)
+    uint32_t levels = 0;
+    size_t texels = 0;
+    for (uint32_t l = 0; l < std::max(1u, t.mip_levels); l++) {
+        const size_t w = t.width >> l, h = t.height >> l;
+        if (w == 0 || h == 0 || (texels + w * h) * 4 > t.num_bytes) break;
+        texels += w * h;
+        levels++;
+    }
+    if (levels == 0) return fail(RFWB200_ERR_INVALID, std::string(what) + ": num_bytes smaller than mip level 0");
+    BK_CUDA(rec.texels.reserve(texels), what);
+    BK_CUDA(cudaMemcpyAsync(rec.texels.ptr, t.bytes, texels * 4, cudaMemcpyHostToDevice, stream), what);
+    if (t.format == 0) {
+        k_tex_swizzle_bgra<<<(unsigned)((texels + 255) / 256), 256, 0, stream>>>(rec.texels.ptr, texels);
+        launch_count++;
+    }
+    BK_CUDA(cudaStreamSynchronize(stream), what);  // the caller's slice is borrowed for the call only
+    rec.desc.texels = rec.texels.ptr;
+    rec.desc.width = t.width; rec.desc.height = t.height; rec.desc.mip_levels = levels; rec.desc.pad = 0;
+    return RFWB200_OK;
+}
+
+int Backend::set_textures(const RfwTextureData* t, uint32_t num, const uint32_t* changed) {
+    DeviceScope device_scope(cfg.device);
+    BK_CUDA(device_scope.status, "cudaSetDevice");
+    if (num && !t) return fail(RFWB200_ERR_INVALID, "set_textures: null slice");
+    BK_CUDA(cudaStreamSynchronize(stream), "sync");
+    for (size_t i = num; i < textures.size(); i++) textures[i].texels.release();
+    textures.resize(num);
+    for (uint32_t i = 0; i < num; i++) {
+        if (changed && !changed[i] && textures[i].desc.texels) continue;
+        if (int rc = upload_texture(textures[i], t[i], "set_textures")) return rc;
+    }
+    shading_dirty = true;
+    synchronized = false;
+    return RFWB200_OK;
+}
+
+int Backend::set_skybox(const RfwTextureData* t) {
+    DeviceScope device_scope(cfg.device);
+    BK_CUDA(device_scope.status, "cudaSetDevice");
+    BK_CUDA(cudaStreamSynchronize(stream), "sync");
+    if (!t || !t->bytes || t->width == 0 || t->height == 0) {  // no skybox: back to the constant sky colour
+        have_skybox = false;
+    } else {
+        if (int rc = upload_texture(skybox, *t, "set_skybox")) return rc;
+        have_skybox = true;
+    }
+    shading_dirty = true;
+    synchronized = false;
+    return RFWB200_OK;
+}
+
 int Backend::set_area_lights(const RfwAreaLight* l, uint32_t num) { area_lights.assign(l, l + num); shading_dirty = true; synchronized = false; return RFWB200_OK; }
 int Backend::set_point_lights(const RfwPointLight* l, uint32_t num) { point_lights.assign(l, l + num); shading_dirty = true; synchronized = false; return RFWB200_OK; }
 int Backend::set_spot_lights(const RfwSpotLight* l, uint32_t num) { spot_lights.assign(l, l + num); shading_dirty = true; synchronized = false; return RFWB200_OK; }
@@ -348,6 +413,13 @@ int Backend::synchronize() {
         if (!point_lights.empty()) BK_CUDA(cudaMemcpyAsync(d_point.ptr, point_lights.data(), point_lights.size() * sizeof(RfwPointLight), cudaMemcpyHostToDevice, stream), "lights");
         if (!spot_lights.empty()) BK_CUDA(cudaMemcpyAsync(d_spot.ptr, spot_lights.data(), spot_lights.size() * sizeof(RfwSpotLight), cudaMemcpyHostToDevice, stream), "lights");
         if (!dir_lights.empty()) BK_CUDA(cudaMemcpyAsync(d_dir.ptr, dir_lights.data(), dir_lights.size() * sizeof(RfwDirectionalLight), cudaMemcpyHostToDevice, stream), "lights");
+        BK_CUDA(d_tex_desc.reserve(std::max<size_t>(1, textures.size())), "textures");
+        if (!textures.empty()) {
+            std::vector<TexDesc> descs(textures.size());
+            for (size_t i = 0; i < textures.size(); i++) descs[i] = textures[i].desc;
+            BK_CUDA(cudaMemcpyAsync(d_tex_desc.ptr, descs.data(), descs.size() * sizeof(TexDesc), cudaMemcpyHostToDevice, stream), "textures");
+            BK_CUDA(cudaStreamSynchronize(stream), "textures");  // `descs` is a local
+        }
         BK_CUDA(cudaStreamSynchronize(stream), "shading upload");
         shading_dirty = false;
     }
@@ -439,15 +511,32 @@ int Backend::trace_closest_counted(const RfwRay* d_r, uint64_t num, RfwHit* d_h,
 template <typename OutT, typename LaunchFn>
 static cudaError_t pipelined(cudaStream_t compute, cudaStream_t in, cudaStream_t out, std::vector<cudaEvent_t>& events, uint64_t chunk, const RfwRay* h_rays, uint64_t num,
                              RfwRay* d_rays, OutT* d_out, OutT* h_out, LaunchFn launch) {
-    const uint64_t n_chunks = (num + chunk - 1) / chunk;
+    // Chunk schedule: the kernel is the slowest stage, so what is exposed is the first chunk's upload and the last chunk's
+    // download.  Chunks therefore ramp up from chunk/8 (doubling) to `chunk`, and ramp down again over the last rays.
+    std::vector<uint64_t> sizes;
+    {
+        const uint64_t small = std::max<uint64_t>(chunk / 8, 1024);
+        uint64_t left = num, next = small;
+        std::vector<uint64_t> tail;
+        for (uint64_t t = small; t < chunk && left > 2 * t; t *= 2) { tail.push_back(t); left -= t; }  // reserved for the ramp down
+        while (left > 0) {
+            const uint64_t n = std::min(next, left);
+            sizes.push_back(n);
+            left -= n;
+            next = std::min(chunk, next * 2);
+        }
+        for (size_t i = tail.size(); i-- > 0;) sizes.push_back(tail[i]);
+    }
+    const uint64_t n_chunks = sizes.size();
     while (events.size() < 2 * n_chunks) {
         cudaEvent_t e;
         cudaError_t err = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
         if (err != cudaSuccess) return err;
         events.push_back(e);
     }
+    uint64_t off = 0;
     for (uint64_t c = 0; c < n_chunks; c++) {
-        const uint64_t off = c * chunk, n = std::min(chunk, num - off);
+        const uint64_t n = sizes[c];
         cudaError_t err = cudaMemcpyAsync(d_rays + off, h_rays + off, n * sizeof(RfwRay), cudaMemcpyHostToDevice, in);
         if (err != cudaSuccess) return err;
         cudaEventRecord(events[2 * c], in);
@@ -458,6 +547,7 @@ static cudaError_t pipelined(cudaStream_t compute, cudaStream_t in, cudaStream_t
         cudaStreamWaitEvent(out, events[2 * c + 1], 0);
         err = cudaMemcpyAsync(h_out + off, d_out + off, n * sizeof(OutT), cudaMemcpyDeviceToHost, out);
         if (err != cudaSuccess) return err;
+        off += n;
     }
     cudaError_t err = cudaStreamSynchronize(out);
     if (err != cudaSuccess) return err;
@@ -543,10 +633,14 @@ int Backend::render_spp(const RfwCameraView3D* view, uint32_t spp, uint32_t dept
     ss.area = d_area.ptr; ss.point = d_point.ptr; ss.spot = d_spot.ptr; ss.dir = d_dir.ptr;
     ss.n_area = (int)area_lights.size(); ss.n_point = (int)point_lights.size(); ss.n_spot = (int)spot_lights.size(); ss.n_dir = (int)dir_lights.size();
     ss.n_materials = (uint32_t)materials.size();
+    ss.textures = d_tex_desc.ptr; ss.n_textures = (uint32_t)textures.size();
+    ss.has_sky = have_skybox ? 1u : 0u;
+    ss.sky = skybox.desc;
     if (materials.empty()) return fail(RFWB200_ERR_INVALID, "render: no materials set");
     wf.refill_below = tcfg.refill_below;
     wf.tri_batch = tcfg.tri_batch;
     const uint64_t before = wf.launches;
+    BK_CUDA(wf.ensure_wave(wf.wave_spp_for(spp)), "wavefront queues");  // one-time (grow-only) allocation, outside the timed bracket
     BK_CUDA(cudaEventRecord(ev0, stream), "event");
     BK_CUDA(wf.render(stream, sv, ss, *view, sample_count, spp, depth), "render");
     sample_count += spp;

@@ -55,6 +55,8 @@ public:
     int unload_3d_meshes(const uint32_t* ids, uint32_t num);
     int set_3d_instances(uint32_t mesh, const RfwInstancesData3D* data);
     int set_materials(const RfwDeviceMaterial* m, uint32_t num);
+    int set_textures(const RfwTextureData* t, uint32_t num, const uint32_t* changed);
+    int set_skybox(const RfwTextureData* t);
     int set_area_lights(const RfwAreaLight* l, uint32_t num);
     int set_point_lights(const RfwPointLight* l, uint32_t num);
     int set_spot_lights(const RfwSpotLight* l, uint32_t num);
@@ -109,6 +111,16 @@ private:
     std::vector<RfwSpotLight> spot_lights;
     std::vector<RfwDirectionalLight> dir_lights;
     bool scene_dirty = true, shading_dirty = true, synchronized = false;
+    // material textures + skybox: RGBA8 texels in HBM, all mip levels of a texture contiguous
+    struct TextureRec {
+        DeviceArray<uchar4> texels;
+        TexDesc desc{};
+    };
+    std::vector<TextureRec> textures;
+    TextureRec skybox;
+    bool have_skybox = false;
+    DeviceArray<TexDesc> d_tex_desc;
+    int upload_texture(TextureRec& rec, const RfwTextureData& t, const char* what);
 
     DeviceBvh tlas;
     DeviceArray<InstanceRec> d_instances;
@@ -129,7 +141,7 @@ private:
     unsigned long long* d_counters3 = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> chunk_events;
-    uint64_t chunk_rays = 1u << 21;
+    uint64_t chunk_rays = 1u << 21;  // largest chunk of the host-buffer pipeline (the schedule ramps up to it and down again)
     float sah_c_prim = 0.8f;  // SAH cost of one triangle test relative to one wide-node visit (BLAS); swept on C2/C4 (scripts/tune_leafcost.py)
     int sah_pmax = 3;         // max triangles per leaf slot
     int sah_treelet = 8;  // binned-SAH refinement above LBVH treelets of this many primitives (0 = plain LBVH)

@@ -156,8 +156,9 @@ __global__ void __launch_bounds__(128) k_wf_shade(FrameParams fp, ShadeScene ss,
             const float bsdfPdf = t4.w;
             float3 contrib = f3(0, 0, 0);
             bool add = false;
-            if (inst < 0) {  // :90-96 (constant sky; the skybox texture is SURVEY §8 f1)
-                contrib = throughput * f3(fp.sky[0], fp.sky[1], fp.sky[2]) * (1.0f / bsdfPdf);
+            if (inst < 0) {  // :90-96: equirect skybox at mip level path_length (constant colour until set_skybox is called)
+                const float3 skyc = ss.has_sky ? sky_sample(ss.sky, Dv, (int)fp.path_length) : f3(fp.sky[0], fp.sky[1], fp.sky[2]);
+                contrib = throughput * skyc * (1.0f / bsdfPdf);
                 clamp_intensity(contrib, fp.clamp_value);
                 add = true;
             } else {
@@ -167,7 +168,9 @@ __global__ void __launch_bounds__(128) k_wf_shade(FrameParams fp, ShadeScene ss,
                 const float4 q7 = __ldg(tp + 7), q8 = __ldg(tp + 8), q9 = __ldg(tp + 9), q10 = __ldg(tp + 10);  // T0, T1, T2, light_id|mat_id|lod|area
                 const int mat_id = __float_as_int(q10.y);
                 const float tri_area = q10.w;
-                const ShadingData sd = extract_material(ss.materials + mat_id);
+                ShadingData sd = extract_material(ss.materials + mat_id);
+                const uint32_t mflags = __ldg(&ss.materials[mat_id].flags);
+                const bool has_maps = (mflags & 0x3Fu) != 0u;  // :120, :162
                 uint32_t seed = wang_hash(pixel * 16789u + (fp.sample + wave_b) * 1791u + fp.path_length * 720898027u);  // :102-103
                 const uint32_t bary = __float_as_uint(s4.w);
                 const float u = (float)(bary & 65535u) * (1.0f / 65535.0f), v = (float)(bary >> 16) * (1.0f / 65535.0f);
@@ -182,7 +185,7 @@ __global__ void __launch_bounds__(128) k_wf_shade(FrameParams fp, ShadeScene ss,
                 T3 = normalize3(f3(m0.x * T3.x + m0.y * T3.y + m0.z * T3.z, m1.x * T3.x + m1.y * T3.y + m1.z * T3.z, m2.x * T3.x + m2.y * T3.y + m2.z * T3.z));
                 const float3 B = cross3(N, T3) * Tw;
                 const float3 P = Ov + Dv * t;
-                if (sd.color.x > 1.0f || sd.color.y > 1.0f || sd.color.z > 1.0f) {  // hit a light, :128-160
+                if ((sd.color.x > 1.0f || sd.color.y > 1.0f || sd.color.z > 1.0f) && !(mflags & 16u)) {  // hit a light, :128-160
                     const float DdotNL = -dot3(Dv, N);
                     if (DdotNL > 0.0f) {
                         if (fp.path_length == 0) {
@@ -196,6 +199,22 @@ __global__ void __launch_bounds__(128) k_wf_shade(FrameParams fp, ShadeScene ss,
                     }
                     add = true;
                 } else {
+                    if (has_maps) {  // :162-175
+                        const float lambda = sqrtf(q10.z) + log2f(fp.cam.spread_angle * (1.0f / fabsf(dot3(Dv, N))));
+                        const float4 q0 = __ldg(tp + 0), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);  // vertex|tu
+                        const float tu = w * q0.w + u * q1.w + v * q2.w;
+                        const float tv = w * q3.w + u * q4.w + v * q5.w;
+                        const int dmap = __ldg(&ss.materials[mat_id].diffuse_map), nmap = __ldg(&ss.materials[mat_id].normal_map);
+                        if ((mflags & 1u) && dmap >= 0 && (uint32_t)dmap < ss.n_textures) {
+                            const float4 c = tex_fetch_trilinear(ss.textures[dmap], lambda, tu, tv);
+                            sd.color = sd.color * f3(c.x, c.y, c.z);
+                        }
+                        if ((mflags & 2u) && nmap >= 0 && (uint32_t)nmap < ss.n_textures) {
+                            const float4 c = tex_fetch(ss.textures[nmap], tu, tv, (int)lambda);
+                            const float3 m = f3((c.x - 0.5f) * 2.0f, (c.y - 0.5f) * 2.0f, (c.z - 0.5f) * 2.0f);
+                            N = normalize3(T3 * m.x + B * m.y + N * m.z);  // mat3(T, B, N) * m
+                        }
+                    }
                     const bool backFacing = dot3(Dv, gN) >= 0.0f;  // :177-181
                     if (backFacing) { N = N * -1.0f; gN = gN * -1.0f; }
                     throughput = throughput * (1.0f / bsdfPdf);  // :183

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/rfwb200.h"
+#include "texture.cuh"
 #include "traverse.h"
 
 namespace rfw {
@@ -31,6 +32,10 @@ struct ShadeScene {
     const RfwDirectionalLight* dir;
     int n_area, n_point, n_spot, n_dir;
     uint32_t n_materials;
+    const TexDesc* textures;  // material textures (set_textures), indexed by DeviceMaterial::*_map
+    uint32_t n_textures;
+    uint32_t has_sky;         // sky valid: miss radiance comes from the equirect skybox instead of the constant colour
+    TexDesc sky;
 };
 
 std::vector<uint32_t> morton_tile_order(uint32_t tiles_x, uint32_t tiles_y);

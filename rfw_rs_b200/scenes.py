@@ -217,7 +217,7 @@ def camera_view(pos, direction, width, height, fov_deg=40.0, aperture=1e-4, foca
 
 
 def material(color=(0.8, 0.8, 0.8), metallic=0.0, roughness=1.0, specular_f=0.5, subsurface=0.0, specular=(1, 1, 1), transmission=0.0, eta=1.0,
-             clearcoat=0.0, clearcoat_gloss=0.0):
+             clearcoat=0.0, clearcoat_gloss=0.0, diffuse_map=-1, normal_map=-1):
     """into_device_material (material/list.rs:755-814): u8-packed Disney parameters, no textures."""
     def ch(f):
         return int(min(f * 255.0, 255.0)) & 255
@@ -231,7 +231,70 @@ def material(color=(0.8, 0.8, 0.8), metallic=0.0, roughness=1.0, specular_f=0.5,
     m["parameters"][0] = [pk(metallic, subsurface, specular_f, roughness), pk(0, 0, 0, 0), pk(clearcoat, clearcoat_gloss, transmission, eta), 0]
     for k in ("diffuse_map", "normal_map", "metallic_roughness_map", "emissive_map", "sheen_map"):
         m[k] = -1
+    # MaterialProps flag bits (crates/rfw-scene/src/material/mod.rs:27-34): bit 0 diffuse map, bit 1 normal map
+    if diffuse_map >= 0:
+        m["diffuse_map"] = diffuse_map; m["flags"] |= 1
+    if normal_map >= 0:
+        m["normal_map"] = normal_map; m["flags"] |= 2
     return m
+
+
+class Texture:
+    """TextureData as it crosses the boundary (crates/rfw-backend/src/structs.rs:197-249): all mip levels in one
+    byte slice, level l at texel offset sum_{i<l} (w>>i)*(h>>i); format 0 = BGRA8, 1 = RGBA8."""
+
+    def __init__(self, level0, mip_levels=5, fmt=0):
+        img = np.ascontiguousarray(level0, dtype=np.uint8)
+        assert img.ndim == 3 and img.shape[2] == 4
+        self.height, self.width = img.shape[:2]
+        self.format = fmt
+        levels = [img]
+        while len(levels) < mip_levels and levels[-1].shape[0] > 1 and levels[-1].shape[1] > 1:
+            a = levels[-1].astype(np.uint16)
+            h2, w2 = a.shape[0] // 2, a.shape[1] // 2
+            a = a[: 2 * h2, : 2 * w2]
+            levels.append(((a[0::2, 0::2] + a[1::2, 0::2] + a[0::2, 1::2] + a[1::2, 1::2] + 2) // 4).astype(np.uint8))  # 2x2 box filter
+        self.mip_levels = len(levels)
+        self.levels = levels
+        self.bytes = np.concatenate([l.reshape(-1) for l in levels])
+
+
+def pattern_texture(size=64, seed=SEED_SCENE, kind="checker", fmt=0, mip_levels=5):
+    """Deterministic test textures: `checker` (coloured 8x8 checkerboard with a per-texel hash jitter), `normal`
+    (a smooth bump field encoded as a tangent-space normal map), `sky` (equirect gradient with a bright sun disc)."""
+    y, x = np.mgrid[0:size, 0: size * (2 if kind == "sky" else 1)].astype(np.float64)
+    w = x.shape[1]
+    jit = u01(seed, (y * w + x).astype(np.uint64)).astype(np.float64)
+    if kind == "checker":
+        c = ((x // (size // 8)).astype(int) + (y // (size // 8)).astype(int)) % 2
+        r = np.where(c, 0.9, 0.25) * (0.8 + 0.2 * jit); g = np.where(c, 0.6, 0.3) * (0.8 + 0.2 * jit); b = np.where(c, 0.3, 0.8)
+    elif kind == "normal":
+        fx = 0.35 * np.sin(2 * np.pi * 3 * x / size); fy = 0.35 * np.cos(2 * np.pi * 2 * y / size)
+        nz = 1.0 / np.sqrt(1 + fx * fx + fy * fy)
+        r, g, b = 0.5 + 0.5 * fx * nz, 0.5 + 0.5 * fy * nz, 0.5 + 0.5 * nz
+    else:
+        v = y / size
+        r = 0.25 + 0.5 * v; g = 0.35 + 0.4 * v; b = 0.9 - 0.3 * v
+        sun = ((x / w - 0.3) ** 2 * 4 + (v - 0.7) ** 2) < 0.002
+        r, g, b = np.where(sun, 1.0, r), np.where(sun, 1.0, g), np.where(sun, 0.9, b)
+    rgba = np.stack([r, g, b, np.ones_like(r)], axis=2)
+    img = np.clip(np.round(rgba * 255.0), 0, 255).astype(np.uint8)
+    if fmt == 0:
+        img = img[:, :, [2, 1, 0, 3]]  # stored as BGRA8
+    return Texture(img, mip_levels, fmt)
+
+
+def set_uvs(tris, scale=1.0, lod=0.0):
+    """Planar UVs from the two dominant axes of each triangle's normal (what a loader's UV set provides)."""
+    n = np.abs(tris["normal"])
+    ax = np.argmax(n, axis=1)
+    ua = np.where(ax == 0, 1, 0); va = np.where(ax == 2, 1, 2)
+    idx = np.arange(len(tris))
+    for k, vert in (("0", "vertex0"), ("1", "vertex1"), ("2", "vertex2")):
+        tris["u" + k] = tris[vert][idx, ua] * scale
+        tris["v" + k] = tris[vert][idx, va] * scale
+    tris["lod"] = lod
+    return tris
 
 
 def area_lights_from(tris, matrix, radiance, mesh_id, inst_idx, first_light_id=0):
@@ -280,6 +343,8 @@ class SceneDesc:
         self.point_lights = np.zeros(0, dtype=wire.POINT_LIGHT)
         self.spot_lights = np.zeros(0, dtype=wire.SPOT_LIGHT)
         self.directional_lights = np.zeros(0, dtype=wire.DIRECTIONAL_LIGHT)
+        self.textures = []   # list of Texture
+        self.skybox = None   # Texture or None
 
     def apply(self, backend):
         for mid, tris in self.meshes.items():
@@ -287,6 +352,9 @@ class SceneDesc:
         for mid, mats in self.instances.items():
             backend.set_3d_instances(mid, mats)
         backend.set_materials(self.materials)
+        if self.textures or self.skybox is not None:
+            backend.set_textures(self.textures)
+            backend.set_skybox(self.skybox)
         backend.set_area_lights(self.area_lights)
         backend.set_point_lights(self.point_lights)
         backend.set_spot_lights(self.spot_lights)
@@ -392,4 +460,49 @@ def soup_with_lights(n, s, n_lights=256, seed=SEED_SCENE, light_area=1e-2, radiu
     sc.meshes[1] = lt
     sc.instances[1] = to_column_major([identity()])
     sc.area_lights = L
+    return sc
+
+
+def textured_scene(grid=4, subdiv=2, seed=SEED_SCENE, tex_size=64, skybox=True):
+    """(f)1 flavour: a ground quad with a diffuse map + normal map, spheres with a diffuse map (one BGRA8, one RGBA8
+    texture), plain GGX spheres, two emissive quads and an equirect skybox."""
+    sc = SceneDesc()
+    sc.textures = [pattern_texture(tex_size, seed, "checker", fmt=0), pattern_texture(tex_size, seed + 1, "normal", fmt=0),
+                   pattern_texture(tex_size // 2, seed + 2, "checker", fmt=1)]
+    if skybox:
+        sc.skybox = pattern_texture(tex_size, seed + 3, "sky", fmt=0)
+    sc.materials = np.concatenate([
+        material(color=(0.9, 0.9, 0.9), roughness=1.0, diffuse_map=0, normal_map=1),   # 0 ground: diffuse + normal map
+        material(color=(1.0, 0.95, 0.9), roughness=0.8, diffuse_map=2),                 # 1 textured spheres
+        material(color=(0.8, 0.7, 0.5), metallic=1.0, roughness=0.3),                   # 2 metal spheres
+        material(color=(12.0, 12.0, 12.0)),                                             # 3 emissive
+    ])
+    g = quad((0, 0, 0), (0, 1, 0), grid * 2.0, grid * 2.0, mat_id=0)
+    if g["normal"][0, 1] < 0:
+        g = make_triangles(g["vertex0"], g["vertex2"], g["vertex1"], 0)
+    sc.meshes[0] = set_uvs(g, scale=0.37, lod=1.0)
+    sc.instances[0] = to_column_major([identity()])
+    sc.meshes[1] = set_uvs(icosphere(subdiv, 0.4, mat_id=1), scale=1.3, lod=4.0)
+    sc.meshes[2] = icosphere(subdiv, 0.4, mat_id=2)
+    per = {1: [], 2: []}
+    r = u01(seed + 5, np.arange(grid * grid * 4)).astype(np.float64).reshape(-1, 4)
+    for i in range(grid * grid):
+        gx, gz = i % grid, i // grid
+        axis = _norm(np.array([r[i, 0] - 0.5, r[i, 1] - 0.5, r[i, 2] - 0.5]) + 1e-6)
+        per[1 + i % 2].append(trs((gx - grid / 2 + 0.5, 0.4, gz - grid / 2 + 0.5), axis, r[i, 3] * 2 * np.pi, 0.7 + 0.3 * r[i, 3]))
+    for m in (1, 2):
+        sc.instances[m] = to_column_major(per[m])
+    lq = quad((0, 0, 0), (0, 1, 0), 1.5, 1.5, mat_id=3)
+    if lq["normal"][0, 1] > 0:
+        lq = make_triangles(lq["vertex0"], lq["vertex2"], lq["vertex1"], 3)
+    lmats = [trs((-1.0, 3.0, 0.0)), trs((1.5, 3.5, 1.0))]
+    inst_base = 1 + grid * grid
+    lights = []
+    lt = lq.copy()
+    for i, M in enumerate(lmats):
+        L, ids = area_lights_from(lq, M, (12.0, 12.0, 12.0), 3, inst_base + i, first_light_id=2 * i)
+        lights.append(L); lt["light_id"] = ids
+    sc.meshes[3] = lt
+    sc.instances[3] = to_column_major(lmats)
+    sc.area_lights = np.concatenate(lights)
     return sc
