@@ -38,7 +38,7 @@ CPU_SAMPLE_RAYS = 1 << 20
 
 def load_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed ncu capture."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r1b_traffic.json")  # refreshed with every ncu --set full capture of the kernel
     try:
         return float(json.load(open(p))["traffic_bytes_per_launch"]) / 1e9
     except Exception:
@@ -342,10 +342,10 @@ def main():
                        "l2_policy": "inputs larger than L2: 512 MiB rays + 320 MiB hits streamed per step (evict-first); the 58 MB BVH is the step's reused working set",
                        "scene": "replicated per GPU", "timing": "CUDA events on the backend stream inside librfwb200, max over ranks"},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": N_RAYS * 32, "d2h_bytes_per_step": N_RAYS * 20,
-                    "note": "rfwb200_trace_closest with pinned host buffers; chunked H2D / kernel / D2H pipeline on 3 streams; wall clock, max over ranks"},
+                    "note": "rfwb200_trace_closest with pinned host buffers: ONE persistent launch consumes rays as the upload lands them (device watermark) while completed 2^18-ray granules are downloaded (per-warp progress slots mirrored to the host); wall clock, max over ranks"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic(), "traffic_unit": "GB per launch (ncu dram__bytes_read+write, profiles/r1_traffic.json)",
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic(), "traffic_unit": "GB per launch (ncu dram__bytes_read+write, profiles/r1b_traffic.json)",
                          "algorithmic_GB_per_launch": BYTES_PER_RAY_CLOSEST * N_RAYS / 1e9,
                          "kernel": "k_trace_persistent<RayBufferIO, closest, single-level>", "algorithmic_bytes_per_ray": BYTES_PER_RAY_CLOSEST, "peak_source": peak_src,
                          "note": "pointer-chasing traversal over an L2-resident BVH: the HBM fraction is small by construction (SURVEY 8d); see extra.traversal_bytes_per_ray for the L2-side traffic"},

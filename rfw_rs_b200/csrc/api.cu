@@ -60,7 +60,7 @@ int rfwb200_assemble_tiles_device(void* handle, const float* d_g, uint32_t tpr, 
 uint32_t rfwb200_sample_count(void* handle) { return handle ? static_cast<Backend*>(handle)->sample_count : 0; }
 uint32_t rfwb200_tiles_per_rank(void* handle) { return handle ? static_cast<Backend*>(handle)->tiles_per_rank() : 0; }
 
-int rfwb200_build_stats(void* handle, RfwBuildStats* out) { RFW_GUARD(handle); if (out) *out = b->build_stats; return RFWB200_OK; }
+int rfwb200_build_stats(void* handle, RfwBuildStats* out) { RFW_GUARD(handle); return b->read_build_stats(out); }
 int rfwb200_trace_stats(void* handle, RfwTraceStats* out) { RFW_GUARD(handle); if (out) *out = b->trace_stats; return RFWB200_OK; }
 int rfwb200_render_stats(void* handle, RfwRenderStats* out) { RFW_GUARD(handle); if (out) *out = b->render_stats; return RFWB200_OK; }
 int rfwb200_set_option(void* handle, const char* key, int64_t value) { RFW_GUARD(handle); return b->set_option(key, value); }

@@ -8,8 +8,11 @@
 
 #include <math.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 
 namespace rfw {
 
@@ -74,6 +77,10 @@ int Backend::init() {
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
     }
+    {   // persisting-L2 carve-out for the acceleration structure (update_l2_policy)
+        l2_persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
+        l2_window_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
+    }
     BK_CUDA(cudaMalloc(&d_counter, 64), "counter");
     BK_CUDA(cudaMalloc(&d_counters3, 64), "counters");
     bctx.stream = stream;
@@ -101,7 +108,11 @@ Backend::~Backend() {
     d_rays.release(); d_hits.release(); d_occ.release();
     for (auto& t : textures) t.texels.release();
     skybox.texels.release(); d_tex_desc.release();
+    d_mesh_table.release(); d_matrices.release();
     wf.release();
+    if (d_stream_state) cudaFree(d_stream_state);
+    if (h_stream_flags) cudaFreeHost(h_stream_flags);
+    if (h_stream_marks) cudaFreeHost(h_stream_marks);
     if (d_counter) cudaFree(d_counter);
     if (d_counters3) cudaFree(d_counters3);
     for (auto ev : chunk_events) cudaEventDestroy(ev);
@@ -109,6 +120,7 @@ Backend::~Backend() {
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
     if (copy_in) cudaStreamDestroy(copy_in);
+    if (copy_poll) cudaStreamDestroy(copy_poll);
     if (copy_out) cudaStreamDestroy(copy_out);
 }
 
@@ -242,7 +254,7 @@ int Backend::set_spot_lights(const RfwSpotLight* l, uint32_t num) { spot_lights.
 int Backend::set_directional_lights(const RfwDirectionalLight* l, uint32_t num) { dir_lights.assign(l, l + num); shading_dirty = true; synchronized = false; return RFWB200_OK; }
 
 // ---- synchronize -----------------------------------------------------------------------------------
-static bool invert_affine(const float* m, float4& r0, float4& r1, float4& r2, float4& n0, float4& n1, float4& n2) {
+__host__ __device__ static bool invert_affine(const float* m, float4& r0, float4& r1, float4& r2, float4& n0, float4& n1, float4& n2) {
     // column-major 4x4 -> rows of the inverse (3x4) and rows of the normal matrix (inverse transposed, 3x3)
     double a[16], inv[16];
     for (int i = 0; i < 16; i++) a[i] = m[i];
@@ -259,7 +271,7 @@ static bool invert_affine(const float* m, float4& r0, float4& r1, float4& r2, fl
     inv[10] = a[0] * a[5] * a[15] - a[0] * a[7] * a[13] - a[4] * a[1] * a[15] + a[4] * a[3] * a[13] + a[12] * a[1] * a[7] - a[12] * a[3] * a[5];
     inv[14] = -a[0] * a[5] * a[14] + a[0] * a[6] * a[13] + a[4] * a[1] * a[14] - a[4] * a[2] * a[13] - a[12] * a[1] * a[6] + a[12] * a[2] * a[5];
     const double det = a[0] * inv[0] + a[1] * inv[4] + a[2] * inv[8] + a[3] * inv[12];
-    if (det == 0.0 || !std::isfinite(det)) return false;
+    if (det == 0.0 || !isfinite(det)) return false;
     const double id = 1.0 / det;
     r0 = make_float4((float)(inv[0] * id), (float)(inv[4] * id), (float)(inv[8] * id), (float)(inv[12] * id));
     r1 = make_float4((float)(inv[1] * id), (float)(inv[5] * id), (float)(inv[9] * id), (float)(inv[13] * id));
@@ -269,6 +281,93 @@ static bool invert_affine(const float* m, float4& r0, float4& r1, float4& r2, fl
     n1 = make_float4(r0.y, r1.y, r2.y, 0.0f);
     n2 = make_float4(r0.z, r1.z, r2.z, 0.0f);
     return true;
+}
+
+
+// ---- instance records on the device (reference: the host-side flatten of backends/gpu-rt/src/lib.rs:1571-1632) ------
+// One thread per instance SLOT (global instance id = exclusive prefix over mesh ids of the list lengths + index in the
+// list): inverse + normal matrix in double, world box of the 8 transformed BLAS corners (culling.comp:58-92), shading
+// record; removed slots (all-zero matrix, instances_3d.rs:79-86), singular matrices and slots of absent meshes are
+// flagged dead and compacted away in slot order, so the TLAS sees the live instances in a deterministic order.
+struct MeshEntry {
+    const float4* nodes;
+    const float4* ttris;
+    const RfwRTTriangle* tris;
+    float lo[3], hi[3];
+    uint32_t first_slot;  // global id of this mesh's first instance slot
+    uint32_t present;     // mesh has triangles and a BLAS
+};
+
+__global__ void __launch_bounds__(128) k_instance_prepare(const MeshEntry* __restrict__ meshes, uint32_t n_meshes, const float* __restrict__ matrices, uint32_t n_slots,
+                                                          InstanceRec* __restrict__ recs, InstanceShading* __restrict__ shading, float4* __restrict__ box_lo,
+                                                          float4* __restrict__ box_hi, uint32_t* __restrict__ live_flag, uint32_t* __restrict__ identity_flag) {
+    const uint32_t gid = blockIdx.x * 128 + threadIdx.x;
+    if (gid >= n_slots) return;
+    uint32_t lo_i = 0, hi_i = n_meshes;  // last mesh entry with first_slot <= gid (entries with empty lists share a first_slot)
+    while (hi_i - lo_i > 1) {
+        const uint32_t mid = (lo_i + hi_i) >> 1;
+        if (meshes[mid].first_slot <= gid) lo_i = mid; else hi_i = mid;
+    }
+    const MeshEntry me = meshes[lo_i];
+    float M[16];
+    bool zero = true;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float4 c = reinterpret_cast<const float4*>(matrices)[(size_t)gid * 4 + k];
+        M[4 * k + 0] = c.x; M[4 * k + 1] = c.y; M[4 * k + 2] = c.z; M[4 * k + 3] = c.w;
+        zero = zero && c.x == 0.0f && c.y == 0.0f && c.z == 0.0f && c.w == 0.0f;
+    }
+    InstanceRec r;
+    InstanceShading sh;
+    memset(&sh, 0, sizeof(sh));
+    bool live = me.present && !zero && invert_affine(M, r.inv0, r.inv1, r.inv2, sh.nrm0, sh.nrm1, sh.nrm2);
+    if (live) {
+        r.nodes = me.nodes; r.tris = me.ttris; r.inst_id = (int)gid; r.mesh_id = (int)lo_i; r.pad0 = r.pad1 = 0;
+        sh.tris = me.tris; sh.mesh_id = (int)lo_i; sh.pad = 0;
+        float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const float px = (c & 1) ? me.hi[0] : me.lo[0], py = (c & 2) ? me.hi[1] : me.lo[1], pz = (c & 4) ? me.hi[2] : me.lo[2];
+            // no FMA contraction: the same roundings as a plain host evaluation, on every rank
+            const float w0 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[0], px), __fmul_rn(M[4], py)), __fmul_rn(M[8], pz)), M[12]);
+            const float w1 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[1], px), __fmul_rn(M[5], py)), __fmul_rn(M[9], pz)), M[13]);
+            const float w2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[2], px), __fmul_rn(M[6], py)), __fmul_rn(M[10], pz)), M[14]);
+            lo[0] = fminf(lo[0], w0); hi[0] = fmaxf(hi[0], w0);
+            lo[1] = fminf(lo[1], w1); hi[1] = fmaxf(hi[1], w1);
+            lo[2] = fminf(lo[2], w2); hi[2] = fmaxf(hi[2], w2);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {  // pad: the object-space BLAS boxes are exact, the world box is rounded
+            const float pad = 4.0f * 1.1920929e-7f * fmaxf(fabsf(lo[k]), fabsf(hi[k]));
+            lo[k] -= pad; hi[k] += pad;
+        }
+        recs[gid] = r;
+        box_lo[gid] = make_float4(lo[0], lo[1], lo[2], 0.0f);
+        box_hi[gid] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+        bool ident = true;
+#pragma unroll
+        for (int k = 0; k < 16; k++) ident = ident && M[k] == ((k % 5 == 0) ? 1.0f : 0.0f);
+        identity_flag[gid] = ident ? 1u : 0u;
+    }
+    shading[gid] = sh;
+    live_flag[gid] = live ? 1u : 0u;
+}
+
+// rank = exclusive scan of live_flag; out[3] = {live count, identity flag of the last live slot, ...}
+__global__ void __launch_bounds__(128) k_instance_compact(uint32_t n_slots, const uint32_t* __restrict__ live_flag, const uint32_t* __restrict__ rank,
+                                                          const uint32_t* __restrict__ identity_flag, const InstanceRec* __restrict__ recs_in,
+                                                          const float4* __restrict__ lo_in, const float4* __restrict__ hi_in, InstanceRec* __restrict__ recs_out,
+                                                          float4* __restrict__ lo_out, float4* __restrict__ hi_out, uint32_t* __restrict__ out) {
+    const uint32_t gid = blockIdx.x * 128 + threadIdx.x;
+    if (gid >= n_slots) return;
+    if (live_flag[gid]) {
+        const uint32_t k = rank[gid];
+        recs_out[k] = recs_in[gid];
+        lo_out[k] = lo_in[gid];
+        hi_out[k] = hi_in[gid];
+        if (k == 0) out[1] = identity_flag[gid];  // meaningful when exactly one instance is live
+    }
+    if (gid == n_slots - 1) out[0] = rank[gid] + live_flag[gid];
 }
 
 int Backend::synchronize() {
@@ -302,65 +401,67 @@ int Backend::synchronize() {
 
         // ---- instances + TLAS (rebuilt on every synchronize, as the reference does: lib.rs:1576-1581) ----
         BK_CUDA(cudaEventRecord(ev0, stream), "event");
-        std::vector<InstanceRec> recs;
-        std::vector<float4> ilo, ihi;
+        // slot table: global instance id = exclusive prefix over mesh ids of the list lengths + index in the list
+        std::vector<MeshEntry> table(std::max<size_t>(1, inst_lists.size()));
         uint32_t gid = 0;
-        for (size_t mesh_id = 0; mesh_id < inst_lists.size(); mesh_id++) gid += inst_lists[mesh_id].present ? (uint32_t)(inst_lists[mesh_id].matrices.size() / 16) : 0;
-        total_instance_slots = gid;
-        std::vector<InstanceShading> shading(std::max<uint32_t>(1, total_instance_slots));
-        memset(shading.data(), 0, shading.size() * sizeof(InstanceShading));
-        gid = 0;
-        bool single_identity = false;
         for (size_t mesh_id = 0; mesh_id < inst_lists.size(); mesh_id++) {
-            const InstanceList& l = inst_lists[mesh_id];
-            if (!l.present) continue;
-            const size_t cnt = l.matrices.size() / 16;
+            MeshEntry& e = table[mesh_id];
+            memset(&e, 0, sizeof(e));
+            e.first_slot = gid;
             const MeshRec* m = (mesh_id < meshes.size() && meshes[mesh_id].present && meshes[mesh_id].n) ? &meshes[mesh_id] : nullptr;
-            for (size_t i = 0; i < cnt; i++, gid++) {
-                if (!m) continue;
-                const float* M = &l.matrices[i * 16];
-                bool zero = true;
-                for (int k = 0; k < 16; k++) zero &= (M[k] == 0.0f);
-                if (zero) continue;  // removed slot (instances_3d.rs:79-86)
-                InstanceRec r;
-                InstanceShading sh;
-                if (!invert_affine(M, r.inv0, r.inv1, r.inv2, sh.nrm0, sh.nrm1, sh.nrm2)) continue;  // singular: skip instead of inverting
-                r.nodes = m->bvh.nodes; r.tris = m->d_ttris; r.inst_id = (int)gid; r.mesh_id = (int)mesh_id; r.pad0 = r.pad1 = 0;
-                sh.tris = m->d_tris; sh.mesh_id = (int)mesh_id; sh.pad = 0;
-                shading[gid] = sh;
-                float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
-                for (int c = 0; c < 8; c++) {  // 8 transformed corners (culling.comp:58-92)
-                    const float px = (c & 1) ? m->bvh.hi[0] : m->bvh.lo[0], py = (c & 2) ? m->bvh.hi[1] : m->bvh.lo[1], pz = (c & 4) ? m->bvh.hi[2] : m->bvh.lo[2];
-                    const float w[3] = {M[0] * px + M[4] * py + M[8] * pz + M[12], M[1] * px + M[5] * py + M[9] * pz + M[13], M[2] * px + M[6] * py + M[10] * pz + M[14]};
-                    for (int k = 0; k < 3; k++) { lo[k] = fminf(lo[k], w[k]); hi[k] = fmaxf(hi[k], w[k]); }
-                }
-                // pad by 2 ulp-ish of the magnitude: the object-space BLAS boxes are exact, the world box is rounded
-                for (int k = 0; k < 3; k++) {
-                    const float pad = 4.0f * 1.1920929e-7f * fmaxf(fabsf(lo[k]), fabsf(hi[k]));
-                    lo[k] -= pad; hi[k] += pad;
-                }
-                ilo.push_back(make_float4(lo[0], lo[1], lo[2], 0.0f));
-                ihi.push_back(make_float4(hi[0], hi[1], hi[2], 0.0f));
-                recs.push_back(r);
-                static const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-                single_identity = memcmp(M, I, sizeof(I)) == 0;
+            if (m) {
+                e.nodes = m->bvh.nodes; e.ttris = m->d_ttris; e.tris = m->d_tris; e.present = 1;
+                for (int k = 0; k < 3; k++) { e.lo[k] = m->bvh.lo[k]; e.hi[k] = m->bvh.hi[k]; }
             }
+            gid += inst_lists[mesh_id].present ? (uint32_t)(inst_lists[mesh_id].matrices.size() / 16) : 0;
         }
+        total_instance_slots = gid;
+        const uint32_t slots = total_instance_slots;
         tlas.release();
-        const uint32_t live = (uint32_t)recs.size();
-        BK_CUDA(d_instances.reserve(std::max<uint32_t>(1, live)), "instances");
-        BK_CUDA(d_inst_shading.reserve(shading.size()), "instance shading");
-        if (live) BK_CUDA(cudaMemcpyAsync(d_instances.ptr, recs.data(), live * sizeof(InstanceRec), cudaMemcpyHostToDevice, stream), "instances");
-        BK_CUDA(cudaMemcpyAsync(d_inst_shading.ptr, shading.data(), shading.size() * sizeof(InstanceShading), cudaMemcpyHostToDevice, stream), "instance shading");
-        if (live > 1) {
-            float4 *lo = nullptr, *hi = nullptr;
-            BK_CUDA(cudaMallocAsync(&lo, live * sizeof(float4), stream), "tlas boxes");
-            BK_CUDA(cudaMallocAsync(&hi, live * sizeof(float4), stream), "tlas boxes");
-            BK_CUDA(cudaMemcpyAsync(lo, ilo.data(), live * sizeof(float4), cudaMemcpyHostToDevice, stream), "tlas boxes");
-            BK_CUDA(cudaMemcpyAsync(hi, ihi.data(), live * sizeof(float4), cudaMemcpyHostToDevice, stream), "tlas boxes");
-            const BuildParams tlas_params{1.0f, 4.0f, 1, sah_treelet};
-            cudaError_t e = build_wide_bvh(bctx, lo, hi, (int)live, tlas_params, tlas);
-            cudaFreeAsync(lo, stream); cudaFreeAsync(hi, stream);
+        BK_CUDA(d_instances.reserve(std::max<uint32_t>(1, slots)), "instances");
+        BK_CUDA(d_inst_shading.reserve(std::max<uint32_t>(1, slots)), "instance shading");
+        BK_CUDA(d_mesh_table.reserve(table.size()), "mesh table");
+        BK_CUDA(d_matrices.reserve(std::max<size_t>(16, (size_t)slots * 16)), "instance matrices");
+        uint32_t live = 0;
+        bool single_identity = false;
+        if (slots) {
+            // per-slot scratch: InstanceRec + 2 boxes + 3 words, compacted boxes
+            InstanceRec* tmp_recs = nullptr;
+            float4 *tmp_lo = nullptr, *tmp_hi = nullptr, *lo = nullptr, *hi = nullptr;
+            uint32_t *flags = nullptr, *rank = nullptr, *ident = nullptr, *out = nullptr;
+            BK_CUDA(cudaMallocAsync(&tmp_recs, (size_t)slots * sizeof(InstanceRec), stream), "instance scratch");
+            BK_CUDA(cudaMallocAsync(&tmp_lo, (size_t)slots * sizeof(float4), stream), "instance scratch");
+            BK_CUDA(cudaMallocAsync(&tmp_hi, (size_t)slots * sizeof(float4), stream), "instance scratch");
+            BK_CUDA(cudaMallocAsync(&lo, (size_t)slots * sizeof(float4), stream), "instance scratch");
+            BK_CUDA(cudaMallocAsync(&hi, (size_t)slots * sizeof(float4), stream), "instance scratch");
+            BK_CUDA(cudaMallocAsync(&flags, ((size_t)slots * 3 + 4) * sizeof(uint32_t), stream), "instance scratch");
+            rank = flags + slots; ident = rank + slots; out = ident + slots;
+            BK_CUDA(cudaMemsetAsync(out, 0, 4 * sizeof(uint32_t), stream), "instance scratch");
+            BK_CUDA(cudaMemcpyAsync(d_mesh_table.ptr, table.data(), table.size() * sizeof(MeshEntry), cudaMemcpyHostToDevice, stream), "mesh table");
+            for (size_t mesh_id = 0; mesh_id < inst_lists.size(); mesh_id++) {
+                const InstanceList& l = inst_lists[mesh_id];
+                if (!l.present || l.matrices.empty()) continue;
+                BK_CUDA(cudaMemcpyAsync(d_matrices.ptr + (size_t)table[mesh_id].first_slot * 16, l.matrices.data(), l.matrices.size() * sizeof(float), cudaMemcpyHostToDevice, stream),
+                        "instance matrices");
+            }
+            const unsigned blocks = (slots + 127) / 128;
+            k_instance_prepare<<<blocks, 128, 0, stream>>>(d_mesh_table.ptr, (uint32_t)table.size(), d_matrices.ptr, slots, tmp_recs, d_inst_shading.ptr, tmp_lo, tmp_hi, flags, ident);
+            BK_CUDA(cudaMemcpyAsync(rank, flags, (size_t)slots * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream), "instance scan");
+            exclusive_scan_u32(rank, (int)slots, stream);
+            k_instance_compact<<<blocks, 128, 0, stream>>>(slots, flags, rank, ident, tmp_recs, tmp_lo, tmp_hi, d_instances.ptr, lo, hi, out);
+            launch_count += 3;
+            uint32_t h_out[4] = {0, 0, 0, 0};
+            BK_CUDA(cudaMemcpyAsync(h_out, out, sizeof(h_out), cudaMemcpyDeviceToHost, stream), "instance count");
+            BK_CUDA(cudaStreamSynchronize(stream), "instance records");  // the live count sizes the TLAS build
+            live = h_out[0];
+            single_identity = live == 1 && h_out[1] != 0;
+            cudaError_t e = cudaSuccess;
+            if (live > 1) {
+                const BuildParams tlas_params{1.0f, 4.0f, 1, sah_treelet};
+                e = build_wide_bvh(bctx, lo, hi, (int)live, tlas_params, tlas);
+            }
+            cudaFreeAsync(tmp_recs, stream); cudaFreeAsync(tmp_lo, stream); cudaFreeAsync(tmp_hi, stream);
+            cudaFreeAsync(lo, stream); cudaFreeAsync(hi, stream); cudaFreeAsync(flags, stream);
             if (e != cudaSuccess) return cuda_fail(e, "TLAS build");
         }
         BK_CUDA(cudaStreamSynchronize(stream), "instance upload");
@@ -368,15 +469,15 @@ int Backend::synchronize() {
         sv.tlas_refs = tlas.leaf_prims;
         sv.instances = d_instances.ptr;
         sv.two_level = live > 1 ? 1 : 0;
-        sv.single_identity = (live == 1 && single_identity) ? 1 : 0;
+        sv.single_identity = single_identity ? 1 : 0;
         sv.num_live = (int)live;
+        update_l2_policy();
         BK_CUDA(cudaEventRecord(ev1, stream), "event");
         BK_CUDA(cudaEventSynchronize(ev1), "TLAS build");
         cudaEventElapsedTime(&tlas_ms, ev0, ev1);
 
         // ---- stats -------------------------------------------------------------------------------------
         build_stats = RfwBuildStats{};
-        BK_CUDA(cudaMemsetAsync(d_counters3, 0, 8, stream), "checksum");
         for (const MeshRec& m : meshes) {
             if (!m.present) continue;
             build_stats.num_meshes++;
@@ -384,16 +485,8 @@ int Backend::synchronize() {
             build_stats.blas_nodes += m.bvh.num_nodes;
             build_stats.bvh_bytes += (uint64_t)m.bvh.num_nodes * 80 + (uint64_t)m.n * 48;
             if (m.bvh.sah > build_stats.sah_cost) build_stats.sah_cost = m.bvh.sah;
-            if (m.n) {
-                BK_CUDA(buffer_checksum(bctx, reinterpret_cast<const uint32_t*>(m.bvh.nodes), 20, m.bvh.num_nodes, 0x30u, d_counters3), "checksum");
-                BK_CUDA(buffer_checksum(bctx, reinterpret_cast<const uint32_t*>(m.d_ttris), 12, m.n, 0u, d_counters3), "checksum");
-            }
         }
-        if (tlas.num_nodes) BK_CUDA(buffer_checksum(bctx, reinterpret_cast<const uint32_t*>(tlas.nodes), 20, tlas.num_nodes, 0x30u, d_counters3), "checksum");
-        unsigned long long cs = 0;
-        BK_CUDA(cudaMemcpyAsync(&cs, d_counters3, 8, cudaMemcpyDeviceToHost, stream), "checksum");
-        BK_CUDA(cudaStreamSynchronize(stream), "checksum");
-        build_stats.checksum = cs;
+        checksum_dirty = true;  // computed on demand (read_build_stats): a per-frame TLAS rebuild must not re-hash every BLAS
         build_stats.num_instances = live;
         build_stats.tlas_nodes = tlas.num_nodes;
         build_stats.bvh_bytes += (uint64_t)tlas.num_nodes * 80;
@@ -428,6 +521,52 @@ int Backend::synchronize() {
     return RFWB200_OK;
 }
 
+// L2 residency of the acceleration structure: the wide nodes are re-read ~30 times per ray while 50 B/ray of rays and
+// hits stream past them (and, on the host-buffer path, the copy engines push the same bytes through the L2 a second
+// time).  The largest node array (the BLAS of a single-mesh scene, else whichever of TLAS / BLAS is biggest) is pinned
+// with a persisting access-policy window on the compute stream; everything else the kernels touch is a streaming miss.
+void Backend::update_l2_policy() {
+    if (!l2_persist_enabled) return;
+    const void* best = nullptr;
+    size_t best_bytes = 0;
+    auto consider = [&](const DeviceBvh& b) { if (b.nodes && (size_t)b.num_nodes * 80 > best_bytes) { best = b.nodes; best_bytes = (size_t)b.num_nodes * 80; } };
+    consider(tlas);
+    for (const MeshRec& m : meshes) if (m.present) consider(m.bvh);
+    cudaStreamAttrValue attr{};
+    if (best && l2_persist_max > 0 && l2_window_max > 0) {
+        attr.accessPolicyWindow.base_ptr = const_cast<void*>(best);
+        attr.accessPolicyWindow.num_bytes = std::min(best_bytes, l2_window_max);
+        attr.accessPolicyWindow.hitRatio = best_bytes <= l2_persist_max ? 1.0f : (float)((double)l2_persist_max / (double)best_bytes);
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    } else {
+        attr.accessPolicyWindow.num_bytes = 0;
+    }
+    if (cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();  // a hint only
+}
+
+// layout-independent checksum of every acceleration structure (equal across rebuilds and ranks); lazily evaluated
+int Backend::read_build_stats(RfwBuildStats* out) {
+    if (checksum_dirty && synchronized) {
+        DeviceScope device_scope(cfg.device);
+        BK_CUDA(device_scope.status, "cudaSetDevice");
+        BK_CUDA(cudaMemsetAsync(d_counters3, 0, 8, stream), "checksum");
+        for (const MeshRec& m : meshes) {
+            if (!m.present || !m.n) continue;
+            BK_CUDA(buffer_checksum(bctx, reinterpret_cast<const uint32_t*>(m.bvh.nodes), 20, m.bvh.num_nodes, 0x30u, d_counters3), "checksum");
+            BK_CUDA(buffer_checksum(bctx, reinterpret_cast<const uint32_t*>(m.d_ttris), 12, m.n, 0u, d_counters3), "checksum");
+        }
+        if (tlas.num_nodes) BK_CUDA(buffer_checksum(bctx, reinterpret_cast<const uint32_t*>(tlas.nodes), 20, tlas.num_nodes, 0x30u, d_counters3), "checksum");
+        unsigned long long cs = 0;
+        BK_CUDA(cudaMemcpyAsync(&cs, d_counters3, 8, cudaMemcpyDeviceToHost, stream), "checksum");
+        BK_CUDA(cudaStreamSynchronize(stream), "checksum");
+        build_stats.checksum = cs;
+        checksum_dirty = false;
+    }
+    if (out) *out = build_stats;
+    return RFWB200_OK;
+}
+
 int Backend::ensure_synchronized(const char* who) {
     if (!synchronized) return fail(RFWB200_ERR_INVALID, std::string(who) + ": scene changed since the last synchronize()");
     return RFWB200_OK;
@@ -449,6 +588,26 @@ int Backend::trace_closest_device(const RfwRay* d_r, uint64_t num, RfwHit* d_h, 
     DeviceScope device_scope(cfg.device);
     BK_CUDA(device_scope.status, "cudaSetDevice");
     if (int rc = ensure_synchronized("trace_closest")) return rc;
+    if (tcfg.variant == 2 && num < (1ull << 31)) {
+        // diagnostic: the host-streamed kernel variant on rays that are already resident (watermark preset to n) —
+        // separates the cost of its bookkeeping from the effect of the concurrent PCIe traffic
+        const uint32_t n = (uint32_t)num, warps = trace_streamed_warps(tcfg, sv, false, n);
+        uint32_t* state = nullptr; uint32_t* hflags = nullptr; uint32_t* dflags = nullptr;
+        BK_CUDA(cudaMalloc(&state, (16 + (size_t)warps) * 4), "debug");
+        BK_CUDA(cudaHostAlloc(&hflags, (16 + (size_t)warps) * 4, cudaHostAllocMapped), "debug");
+        BK_CUDA(cudaHostGetDevicePointer(&dflags, hflags, 0), "debug");
+        memset(hflags, 0, (16 + (size_t)warps) * 4);
+        BK_CUDA(cudaMemcpy(state, &n, 4, cudaMemcpyHostToDevice), "debug");
+        BK_CUDA(cudaEventRecord(ev0, stream), "event");
+        BK_CUDA(trace_streamed(tcfg, sv, false, d_r, n, d_h, nullptr, d_counter, StreamSync{state, state + 16, dflags, device_deadline_ns(10.0)}), "trace_streamed");
+        BK_CUDA(cudaEventRecord(ev1, stream), "event");
+        BK_CUDA(cudaEventSynchronize(ev1), "trace_streamed");
+        cudaEventElapsedTime(&trace_stats.kernel_ms, ev0, ev1);
+        trace_stats.total_ms = trace_stats.kernel_ms; trace_stats.rays = num;
+        cudaFree(state); cudaFreeHost(hflags);
+        launch_count++;
+        return RFWB200_OK;
+    }
     BK_CUDA(cudaEventRecord(ev0, stream), "event");
     for (uint64_t off = 0; off < num; off += (1ull << 30)) {
         const uint32_t n = (uint32_t)std::min<uint64_t>(num - off, 1ull << 30);
@@ -534,24 +693,181 @@ static cudaError_t pipelined(cudaStream_t compute, cudaStream_t in, cudaStream_t
         if (err != cudaSuccess) return err;
         events.push_back(e);
     }
+    // RFWB200_PIPE_TRACE=1: per-chunk completion times of the three stages on stderr (diagnostic; adds timing events)
+    static const bool trace = getenv("RFWB200_PIPE_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    if (trace) {
+        tev.resize(1 + 3 * n_chunks);
+        for (auto& e : tev) cudaEventCreate(&e);
+        cudaEventRecord(tev[0], in);
+    }
     uint64_t off = 0;
     for (uint64_t c = 0; c < n_chunks; c++) {
         const uint64_t n = sizes[c];
         cudaError_t err = cudaMemcpyAsync(d_rays + off, h_rays + off, n * sizeof(RfwRay), cudaMemcpyHostToDevice, in);
         if (err != cudaSuccess) return err;
         cudaEventRecord(events[2 * c], in);
+        if (trace) cudaEventRecord(tev[1 + 3 * c], in);
         cudaStreamWaitEvent(compute, events[2 * c], 0);
         err = launch(d_rays + off, (uint32_t)n, d_out + off);
         if (err != cudaSuccess) return err;
         cudaEventRecord(events[2 * c + 1], compute);
+        if (trace) cudaEventRecord(tev[2 + 3 * c], compute);
         cudaStreamWaitEvent(out, events[2 * c + 1], 0);
         err = cudaMemcpyAsync(h_out + off, d_out + off, n * sizeof(OutT), cudaMemcpyDeviceToHost, out);
         if (err != cudaSuccess) return err;
+        if (trace) cudaEventRecord(tev[3 + 3 * c], out);
         off += n;
+    }
+    if (trace) {
+        cudaStreamSynchronize(out); cudaStreamSynchronize(compute);
+        fprintf(stderr, "rfwb200 pipeline trace (%llu rays, %llu chunks): chunk rays | H2D done | kernel done | D2H done (ms since start)\n", (unsigned long long)num, (unsigned long long)n_chunks);
+        for (uint64_t c = 0; c < n_chunks; c++) {
+            float a = 0, b = 0, d = 0;
+            cudaEventElapsedTime(&a, tev[0], tev[1 + 3 * c]); cudaEventElapsedTime(&b, tev[0], tev[2 + 3 * c]); cudaEventElapsedTime(&d, tev[0], tev[3 + 3 * c]);
+            fprintf(stderr, "  %8llu | %7.3f | %7.3f | %7.3f\n", (unsigned long long)sizes[c], a, b, d);
+        }
+        for (auto& e : tev) cudaEventDestroy(e);
     }
     cudaError_t err = cudaStreamSynchronize(out);
     if (err != cudaSuccess) return err;
     return cudaStreamSynchronize(compute);
+}
+
+// One persistent launch for the whole host batch: the upload stream feeds rays granule by granule and moves the
+// device-side watermark after each one, the kernel (already running) consumes them as they land, and this thread polls
+// the per-granule completion flags the kernel raises in mapped host memory and queues each granule's download as soon
+// as its hits are complete.  Needs page-locked host buffers (a pageable copy is staged by the driver and may serialise
+// against the running kernel); otherwise the caller falls back to the chunked multi-launch pipeline.
+// %globaltimer (ns) deadline `seconds` from now, read through a one-thread kernel once and extrapolated with the host clock
+__global__ void k_read_globaltimer(unsigned long long* out) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    *out = t;
+}
+unsigned long long Backend::device_deadline_ns(double seconds) {
+    if (timer_base_ns == 0) {
+        unsigned long long* d = nullptr;
+        if (cudaMalloc(&d, 8) == cudaSuccess) {
+            k_read_globaltimer<<<1, 1, 0, stream>>>(d);
+            cudaMemcpyAsync(&timer_base_ns, d, 8, cudaMemcpyDeviceToHost, stream);
+            cudaStreamSynchronize(stream);
+            cudaFree(d);
+            timer_base_host = std::chrono::steady_clock::now();
+        }
+    }
+    const double since = std::chrono::duration<double>(std::chrono::steady_clock::now() - timer_base_host).count();
+    return timer_base_ns + (unsigned long long)((since + seconds) * 1e9);
+}
+
+template <typename OutT>
+int Backend::trace_host_streamed(bool any_hit, const RfwRay* rays, uint64_t num, OutT* out, OutT* d_out, bool& used) {
+    used = false;
+    if (!streamed_enabled || num > 0xFFFFFFFFull - (1u << STREAM_GRANULE_SHIFT)) return RFWB200_OK;
+    cudaPointerAttributes pa{}, pb{};
+    if (cudaPointerGetAttributes(&pa, rays) != cudaSuccess || cudaPointerGetAttributes(&pb, out) != cudaSuccess) { cudaGetLastError(); return RFWB200_OK; }
+    if (pa.type != cudaMemoryTypeHost || pb.type != cudaMemoryTypeHost) return RFWB200_OK;
+    const uint32_t n = (uint32_t)num;
+    const uint32_t G = 1u << STREAM_GRANULE_SHIFT;
+    const uint32_t granules = (n + G - 1) / G;
+    const uint32_t warps = trace_streamed_warps(tcfg, sv, any_hit, n);
+    if (warps == 0) return fail(RFWB200_ERR_CUDA, "trace_streamed: occupancy query failed");
+    if (granules > stream_granules || warps > stream_warps) {
+        if (d_stream_state) cudaFree(d_stream_state);
+        if (h_stream_flags) cudaFreeHost(h_stream_flags);
+        if (h_stream_marks) cudaFreeHost(h_stream_marks);
+        d_stream_state = nullptr; h_stream_flags = nullptr; h_stream_marks = nullptr; stream_granules = 0; stream_warps = 0;
+        const uint32_t gcap = std::max(granules, stream_granules), wcap = std::max(warps, stream_warps);
+        BK_CUDA(cudaMalloc(&d_stream_state, (16 + (size_t)wcap) * sizeof(uint32_t)), "stream state");
+        BK_CUDA(cudaHostAlloc(&h_stream_flags, (16 + (size_t)wcap) * sizeof(uint32_t), cudaHostAllocMapped), "stream flags");
+        BK_CUDA(cudaHostAlloc(&h_stream_marks, (size_t)gcap * sizeof(uint32_t), cudaHostAllocDefault), "stream marks");
+        stream_granules = gcap; stream_warps = wcap;
+    }
+    uint32_t* d_flags = nullptr;
+    BK_CUDA(cudaHostGetDevicePointer(&d_flags, h_stream_flags, 0), "stream flags");
+    memset(h_stream_flags, 0, (16 + (size_t)warps) * sizeof(uint32_t));  // abort flag 0; mirror of the warps' oldest in-flight indices: 0 = nothing complete yet
+    for (uint32_t g = 0; g < granules; g++) h_stream_marks[g] = (uint32_t)std::min<uint64_t>((uint64_t)(g + 1) * G, n);
+    BK_CUDA(cudaMemsetAsync(d_stream_state, 0, (16 + (size_t)warps) * sizeof(uint32_t), stream), "stream state");
+    while (chunk_events.size() < 1) {
+        cudaEvent_t e;
+        BK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event");
+        chunk_events.push_back(e);
+    }
+    BK_CUDA(cudaEventRecord(chunk_events[0], stream), "event");
+    BK_CUDA(cudaStreamWaitEvent(copy_in, chunk_events[0], 0), "event");  // the watermark is reset before the first chunk moves it
+    if (!copy_poll) BK_CUDA(cudaStreamCreateWithFlags(&copy_poll, cudaStreamNonBlocking), "stream");
+    BK_CUDA(cudaStreamWaitEvent(copy_poll, chunk_events[0], 0), "event");  // the first mirror copy must see the reset slots
+    StreamSync ss{d_stream_state, d_stream_state + 16, d_flags, device_deadline_ns(10.0)};
+    BK_CUDA(trace_streamed(tcfg, sv, any_hit, d_rays.ptr, n, any_hit ? nullptr : reinterpret_cast<RfwHit*>(d_out), any_hit ? reinterpret_cast<uint32_t*>(d_out) : nullptr, d_counter, ss),
+            "trace_streamed");
+    launch_count++;
+    // uploads: 1, 1, 2, then 4 granules (32 MiB) per copy — a quick start, then few large DMA transfers (8 MiB copies
+    // with a 4-byte watermark copy after each one cost ~15 % of the PCIe rate)
+    for (uint32_t g = 0, step = 1, k = 0; g < granules; g += step, k++) {
+        step = k < 2 ? 1u : (k == 2 ? 2u : 4u);
+        const uint32_t last = std::min(granules, g + step) - 1;
+        const uint64_t off = (uint64_t)g * G, cnt = h_stream_marks[last] - off;
+        BK_CUDA(cudaMemcpyAsync(d_rays.ptr + off, rays + off, cnt * sizeof(RfwRay), cudaMemcpyHostToDevice, copy_in), "ray upload");
+        BK_CUDA(cudaMemcpyAsync(d_stream_state, h_stream_marks + last, sizeof(uint32_t), cudaMemcpyHostToDevice, copy_in), "watermark");
+    }
+    static const bool trace = getenv("RFWB200_PIPE_TRACE") != nullptr;
+    cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<double> seen;
+    if (trace) {
+        for (auto& e : tev) cudaEventCreate(&e);
+        cudaEventRecord(tev[1], copy_in);   // all uploads done
+        cudaEventRecord(tev[2], stream);    // kernel done
+    }
+    // downloads in granule order: everything below the minimum of the warps' oldest in-flight indices is complete
+    volatile uint32_t* flags = h_stream_flags;
+    const auto t_start = std::chrono::steady_clock::now();
+    uint32_t next = 0, spins = 0;
+    // poll interval: a tight loop of tiny D2H copies slows the concurrent ray upload (measured 13.4 vs 10.6 ms); 30-100 us
+    // between mirrors costs nothing (a granule completes every ~170 us)
+    static const int poll_us = getenv("RFWB200_STREAM_POLL_US") ? atoi(getenv("RFWB200_STREAM_POLL_US")) : 50;
+    while (next < granules && !flags[0]) {
+        if (poll_us > 0) { struct timespec ts = {0, poll_us * 1000L}; nanosleep(&ts, nullptr); }
+        // mirror the warps' slots (19 KB for 4 736 warps) with a small D2H copy on its own stream
+        BK_CUDA(cudaMemcpyAsync(h_stream_flags + 16, d_stream_state + 16, (size_t)warps * sizeof(uint32_t), cudaMemcpyDeviceToHost, copy_poll), "progress mirror");
+        BK_CUDA(cudaStreamSynchronize(copy_poll), "progress mirror");
+        uint32_t bound = 0xFFFFFFFFu;
+        for (uint32_t w = 0; w < warps; w++) { const uint32_t v = flags[16 + w]; bound = v < bound ? v : bound; }
+        uint32_t ready_to = next;
+        while (ready_to < granules && h_stream_marks[ready_to] <= bound) ready_to++;
+        if (ready_to > next) {  // one copy for all newly completed granules
+            const uint64_t off = (uint64_t)next * G, cnt = h_stream_marks[ready_to - 1] - off;
+            if (trace) seen.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() * 1e3);
+            BK_CUDA(cudaMemcpyAsync(out + off, d_out + off, cnt * sizeof(OutT), cudaMemcpyDeviceToHost, copy_out), "hit download");
+            next = ready_to;
+            continue;
+        }
+        if ((++spins & 0xFu) == 0u) {
+            if (cudaStreamQuery(stream) != cudaErrorNotReady) {  // kernel finished: one more mirror must show every warp done
+                BK_CUDA(cudaMemcpyAsync(h_stream_flags + 16, d_stream_state + 16, (size_t)warps * sizeof(uint32_t), cudaMemcpyDeviceToHost, copy_poll), "progress mirror");
+                BK_CUDA(cudaStreamSynchronize(copy_poll), "progress mirror");
+                bool all_done = true;
+                for (uint32_t w = 0; w < warps; w++) all_done = all_done && flags[16 + w] == 0xFFFFFFFFu;
+                if (!all_done) flags[0] = 2u;
+            }
+            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() > 60.0) flags[0] = 3u;
+        }
+    }
+    if (trace) {
+        cudaEventRecord(tev[3], copy_out);
+        cudaStreamSynchronize(copy_out); cudaStreamSynchronize(stream); cudaStreamSynchronize(copy_in);
+        float up = 0, kn = 0, dn = 0;
+        cudaEventElapsedTime(&up, ev0, tev[1]); cudaEventElapsedTime(&kn, ev0, tev[2]); cudaEventElapsedTime(&dn, ev0, tev[3]);
+        fprintf(stderr, "rfwb200 streamed trace (%u rays, %u granules, %u warps): uploads done %.3f ms, kernel done %.3f ms, downloads done %.3f ms; downloads queued by the host at (ms):", n, granules, warps, up, kn, dn);
+        for (size_t i = 0; i < seen.size(); i += std::max<size_t>(1, seen.size() / 16)) fprintf(stderr, " [%zu] %.2f", i, seen[i]);
+        fprintf(stderr, " (%zu copies)\n", seen.size());
+        for (auto& e : tev) if (e) cudaEventDestroy(e);
+    }
+    BK_CUDA(cudaStreamSynchronize(copy_in), "ray upload");
+    BK_CUDA(cudaStreamSynchronize(stream), "trace_streamed");
+    BK_CUDA(cudaStreamSynchronize(copy_out), "hit download");
+    if (flags[0]) return fail(RFWB200_ERR_CUDA, "streamed trace aborted (code " + std::to_string(flags[0]) + ": 1 = upload stalled, 2 = kernel ended early, 3 = host timeout)");
+    used = true;
+    return RFWB200_OK;
 }
 
 int Backend::trace_closest_host(const RfwRay* rays, uint64_t num, RfwHit* out) {
@@ -564,6 +880,17 @@ int Backend::trace_closest_host(const RfwRay* rays, uint64_t num, RfwHit* out) {
     BK_CUDA(d_hits.reserve(num), "hit buffer");
     BK_CUDA(cudaStreamSynchronize(stream), "sync");
     BK_CUDA(cudaEventRecord(ev0, copy_in), "event");
+    {
+        bool used = false;
+        if (int rc = trace_host_streamed<RfwHit>(false, rays, num, out, d_hits.ptr, used)) return rc;
+        if (used) {
+            BK_CUDA(cudaEventRecord(ev1, copy_out), "event");
+            BK_CUDA(cudaEventSynchronize(ev1), "trace_closest");
+            cudaEventElapsedTime(&trace_stats.total_ms, ev0, ev1);
+            trace_stats.rays = num;
+            return RFWB200_OK;
+        }
+    }
     uint64_t n_launch = 0;
     cudaError_t e = pipelined<RfwHit>(stream, copy_in, copy_out, chunk_events, chunk_rays, rays, num, d_rays.ptr, d_hits.ptr, out,
                                       [&](const RfwRay* r, uint32_t n, RfwHit* h) { n_launch++; return trace_closest(tcfg, sv, r, n, h, d_counter); });
@@ -586,6 +913,17 @@ int Backend::trace_any_host(const RfwRay* rays, uint64_t num, uint32_t* out) {
     BK_CUDA(d_occ.reserve(num), "flag buffer");
     BK_CUDA(cudaStreamSynchronize(stream), "sync");
     BK_CUDA(cudaEventRecord(ev0, copy_in), "event");
+    {
+        bool used = false;
+        if (int rc = trace_host_streamed<uint32_t>(true, rays, num, out, d_occ.ptr, used)) return rc;
+        if (used) {
+            BK_CUDA(cudaEventRecord(ev1, copy_out), "event");
+            BK_CUDA(cudaEventSynchronize(ev1), "trace_any");
+            cudaEventElapsedTime(&trace_stats.total_ms, ev0, ev1);
+            trace_stats.rays = num;
+            return RFWB200_OK;
+        }
+    }
     uint64_t n_launch = 0;
     cudaError_t e = pipelined<uint32_t>(stream, copy_in, copy_out, chunk_events, chunk_rays, rays, num, d_rays.ptr, d_occ.ptr, out,
                                         [&](const RfwRay* r, uint32_t n, uint32_t* o) { n_launch++; return trace_any(tcfg, sv, r, n, o, d_counter); });
@@ -761,6 +1099,8 @@ int Backend::set_option(const char* key, int64_t value) {
     else if (k == "refill_below") tcfg.refill_below = (int)value;
     else if (k == "tri_batch") tcfg.tri_batch = (int)value;
     else if (k == "min_blocks") tcfg.min_blocks = (int)value;
+    else if (k == "l2_persist") { l2_persist_enabled = value != 0; if (!l2_persist_enabled) { cudaStreamAttrValue a{}; cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &a); cudaCtxResetPersistingL2Cache(); } else { if (l2_persist_max && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, l2_persist_max) != cudaSuccess) { cudaGetLastError(); l2_persist_max = 0; } update_l2_policy(); } }
+    else if (k == "streamed") streamed_enabled = value != 0;  // host-buffer entry points: single-launch streaming (1) or chunked pipeline (0)
     else if (k == "chunk_rays") chunk_rays = (uint64_t)std::max<int64_t>(1024, value);
     else if (k == "max_depth") cfg.max_depth = (uint32_t)value;
     else if (k == "sah_treelet") { sah_treelet = (int)value; for (auto& m : meshes) if (m.present) m.dirty = true; scene_dirty = true; synchronized = false; }

@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -14,6 +15,8 @@
 #include "wavefront.h"
 
 namespace rfw {
+
+struct MeshEntry;
 
 struct MeshRec {
     bool present = false;
@@ -85,6 +88,7 @@ public:
     int debug_read_queue(uint32_t which, float* o, float* d, float* t, float* s, uint32_t cap, uint32_t* cnt);
 
     RfwBuildStats build_stats{};
+    int read_build_stats(RfwBuildStats* out);
     RfwTraceStats trace_stats{};
     RfwRenderStats render_stats{};
     uint32_t sample_count = 0;
@@ -95,10 +99,13 @@ private:
     int cuda_fail(cudaError_t e, const char* what);
     int ensure_synchronized(const char* who);
     int update_wavefront_scene();
+    void update_l2_policy();
+    size_t l2_persist_max = 0, l2_window_max = 0;
+    bool l2_persist_enabled = false;  // option "l2_persist": measured no effect on C2 (the 16 MB of nodes stay resident anyway), off by default
 
     RfwB200Config cfg;
     int sm_count = 148;
-    cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
+    cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr, copy_poll = nullptr;
     BuilderContext bctx;
     TraceConfig tcfg;
     uint64_t launch_count = 0;
@@ -110,7 +117,7 @@ private:
     std::vector<RfwPointLight> point_lights;
     std::vector<RfwSpotLight> spot_lights;
     std::vector<RfwDirectionalLight> dir_lights;
-    bool scene_dirty = true, shading_dirty = true, synchronized = false;
+    bool scene_dirty = true, shading_dirty = true, synchronized = false, checksum_dirty = false;
     // material textures + skybox: RGBA8 texels in HBM, all mip levels of a texture contiguous
     struct TextureRec {
         DeviceArray<uchar4> texels;
@@ -125,6 +132,8 @@ private:
     DeviceBvh tlas;
     DeviceArray<InstanceRec> d_instances;
     DeviceArray<InstanceShading> d_inst_shading;  // indexed by GLOBAL instance id
+    DeviceArray<struct MeshEntry> d_mesh_table;   // per mesh id: BLAS pointers, bounds, first instance slot
+    DeviceArray<float> d_matrices;                // all instance lists' matrices, slot order
     DeviceArray<RfwDeviceMaterial> d_materials;
     DeviceArray<RfwAreaLight> d_area;
     DeviceArray<RfwPointLight> d_point;
@@ -141,6 +150,18 @@ private:
     unsigned long long* d_counters3 = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> chunk_events;
+    // host-streamed single-launch tracing (trace.h StreamSync): watermark + per-granule completion state
+    uint32_t* d_stream_state = nullptr;     // [0] watermark, [16 ..] per-warp oldest in-flight ray index
+    uint32_t* h_stream_flags = nullptr;     // mapped pinned: [0] abort flag, [16 ..] host mirror of the per-warp slots
+    uint32_t stream_warps = 0;
+    unsigned long long timer_base_ns = 0;   // %globaltimer sampled once, paired with timer_base_host
+    std::chrono::steady_clock::time_point timer_base_host;
+    unsigned long long device_deadline_ns(double seconds);
+    uint32_t* h_stream_marks = nullptr;     // pinned: watermark value after each granule (source of the 4-byte copies)
+    uint32_t stream_granules = 0;
+    int streamed_enabled = 1;               // option "streamed": 0 = chunked multi-launch pipeline
+    template <typename OutT>
+    int trace_host_streamed(bool any_hit, const RfwRay* rays, uint64_t num, OutT* out, OutT* d_out, bool& used);
     uint64_t chunk_rays = 1u << 21;  // largest chunk of the host-buffer pipeline (the schedule ramps up to it and down again)
     float sah_c_prim = 0.8f;  // SAH cost of one triangle test relative to one wide-node visit (BLAS); swept on C2/C4 (scripts/tune_leafcost.py)
     int sah_pmax = 3;         // max triangles per leaf slot

@@ -248,18 +248,22 @@ __device__ void bsdf_sample(const ShadingData& sd, float3 T, float3 B, float3 N,
 
 // ---- shade.comp:372-528 — light sampling (uniform pick; ISLIGHTS is never defined) ----------------------
 __device__ float3 random_barycentrics(float r0) {  // :372-412
+    // 16 steps of base-4 triangle subdivision.  Branch-free restatement of the reference's switch (a 4-way divergent
+    // switch, fully unrolled, was half of the shade kernel's instructions): the three edge midpoints are formed once per
+    // step and the new corners are selected by digit — the same additions in the same order, so bit-identical.
     const uint32_t uf = (uint32_t)(r0 * 4294967295.0f);
     float Ax = 1.0f, Ay = 0.0f, Bx = 0.0f, By = 1.0f, Cx = 0.0f, Cy = 0.0f;
+#pragma unroll 4
     for (int i = 0; i < 16; ++i) {
-        const int d = (int)((uf >> (2u * (15u - i))) & 0x3u);
-        float Anx, Any, Bnx, Bny, Cnx, Cny;
-        switch (d) {
-            case 0: Anx = (Bx + Cx) * 0.5f; Any = (By + Cy) * 0.5f; Bnx = (Ax + Cx) * 0.5f; Bny = (Ay + Cy) * 0.5f; Cnx = (Ax + Bx) * 0.5f; Cny = (Ay + By) * 0.5f; break;
-            case 1: Anx = Ax; Any = Ay; Bnx = (Ax + Bx) * 0.5f; Bny = (Ay + By) * 0.5f; Cnx = (Ax + Cx) * 0.5f; Cny = (Ay + Cy) * 0.5f; break;
-            case 2: Anx = (Bx + Ax) * 0.5f; Any = (By + Ay) * 0.5f; Bnx = Bx; Bny = By; Cnx = (Bx + Cx) * 0.5f; Cny = (By + Cy) * 0.5f; break;
-            default: Anx = (Cx + Ax) * 0.5f; Any = (Cy + Ay) * 0.5f; Bnx = (Cx + Bx) * 0.5f; Bny = (Cy + By) * 0.5f; Cnx = Cx; Cny = Cy; break;
-        }
-        Ax = Anx; Ay = Any; Bx = Bnx; By = Bny; Cx = Cnx; Cy = Cny;
+        const uint32_t d = (uf >> (2u * (15u - i))) & 0x3u;
+        const float abx = (Ax + Bx) * 0.5f, aby = (Ay + By) * 0.5f;  // (A+B)/2 == (B+A)/2 exactly
+        const float acx = (Ax + Cx) * 0.5f, acy = (Ay + Cy) * 0.5f;
+        const float bcx = (Bx + Cx) * 0.5f, bcy = (By + Cy) * 0.5f;
+        // d: 0 -> (bc, ac, ab)   1 -> (A, ab, ac)   2 -> (ab, B, bc)   3 -> (ac, bc, C)
+        const float nAx = d == 0u ? bcx : (d == 1u ? Ax : (d == 2u ? abx : acx)), nAy = d == 0u ? bcy : (d == 1u ? Ay : (d == 2u ? aby : acy));
+        const float nBx = d == 0u ? acx : (d == 1u ? abx : (d == 2u ? Bx : bcx)), nBy = d == 0u ? acy : (d == 1u ? aby : (d == 2u ? By : bcy));
+        const float nCx = d == 0u ? abx : (d == 1u ? acx : (d == 2u ? bcx : Cx)), nCy = d == 0u ? aby : (d == 1u ? acy : (d == 2u ? bcy : Cy));
+        Ax = nAx; Ay = nAy; Bx = nBx; By = nBy; Cx = nCx; Cy = nCy;
     }
     const float rx = (Ax + Bx + Cx) * 0.3333333f, ry = (Ay + By + Cy) * 0.3333333f;
     return f3(rx, ry, 1.0f - rx - ry);

@@ -16,11 +16,23 @@ struct TraceConfig {
     int variant = TRACE_VARIANT_PERSISTENT;
     int blocks_per_sm = 0;   // 0 = as many as fit
     int refill_below = 28;   // refill idle lanes when fewer than this many lanes of a warp are traversing
-    int tri_batch = 1;       // run the triangle phase when this many lanes have pending leaf triangles
+    int tri_batch = 6;       // run the triangle phase when this many lanes have pending leaf triangles
     int min_blocks = 0;      // __launch_bounds__ min CTAs/SM variant of the persistent kernel (3,4,5,6,8); 0 = tuned default
 };
 
 // all pointers are device pointers; d_counter is one zero-initialisable uint32 work counter
+// host-streamed single-launch tracing (trace.cu, StreamedRayIO)
+static constexpr int STREAM_GRANULE_SHIFT = 18;  // 262 144 rays: 8 MiB of rays up, 5 MiB of hits down per granule
+struct StreamSync {
+    const uint32_t* watermark;  // device: rays [0, *watermark) have been uploaded
+    uint32_t* warp_slots;       // device memory, one per warp of the persistent grid (see StreamedRayIO::publish)
+    uint32_t* abort_flag;       // mapped pinned host memory
+    unsigned long long deadline_ns;  // %globaltimer deadline for warps that can only wait (stalled upload)
+};
+// warps the persistent grid of trace_streamed will run with (the host sizes and initialises warp_slots with it)
+uint32_t trace_streamed_warps(const TraceConfig& cfg, const SceneView& sv, bool any_hit, uint32_t n);
+cudaError_t trace_streamed(const TraceConfig& cfg, const SceneView& sv, bool any_hit, const RfwRay* d_rays, uint32_t n, RfwHit* d_hits, uint32_t* d_occluded, uint32_t* d_counter,
+                           const StreamSync& sync);
 cudaError_t trace_closest(const TraceConfig& cfg, const SceneView& sv, const RfwRay* d_rays, uint32_t n, RfwHit* d_hits, uint32_t* d_counter);
 cudaError_t trace_any(const TraceConfig& cfg, const SceneView& sv, const RfwRay* d_rays, uint32_t n, uint32_t* d_occluded, uint32_t* d_counter);
 cudaError_t trace_closest_counted(const TraceConfig& cfg, const SceneView& sv, const RfwRay* d_rays, uint32_t n, RfwHit* d_hits, unsigned long long* d_counters3);

@@ -4,6 +4,12 @@
 // IO policy:  uint32_t count() const;                         rays in this launch (may read device memory)
 //             void load(uint32_t i, float4& o_tmin, float4& d_tmax) const;
 //             void store_closest(uint32_t i, const Hit&) const;   void store_any(uint32_t i, bool occluded) const;
+//             uint32_t landed(int lane) const;                    warp-collective: rays [0, landed) are readable (host-streamed policy)
+//             bool stalled(int lane) const;                       warp-collective: called while a whole warp waits for rays
+//             bool publish_due(bool last, int lane) const;        warp-collective: time to report progress?
+//             static constexpr bool kReportsProgress;  void publish(uint32_t oldest_in_flight, int lane) const;
+//             (ready/stalled/publish are trivial except for the host-streamed policy of trace.cu, where ONE launch
+//              overlaps the PCIe upload of the rays and the download of the hits)
 //
 // Warp-level schedule (every lane owns one ray; all lanes re-converge once per iteration at the ballots):
 //   refill   lanes without a ray take the next indices of a global counter: ONE atomicAdd per warp
@@ -82,53 +88,81 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
     int cur_inst = -1;
     int blas_base_sp = 0;
     uint2 ng = make_uint2(0u, 0u), tg = make_uint2(0u, 0u);
+    // host-streamed policy only (folds away elsewhere): a lane that owns ray index `ray_idx` whose ray has not been
+    // uploaded yet is "waiting", encoded as sp == -1 (no extra register: this kernel sits at its 64-register budget)
+#define RFW_WAITING (IO::kReportsProgress && sp < 0)
+    bool any_waiting = false;
 
     for (;;) {
         // ---- refill idle lanes: one atomicAdd per warp -------------------------------------------------
+        // A lane can also be `waiting`: it owns a ray index whose ray has not landed in HBM yet (host-streamed policy
+        // only: IO::ready() is constant true elsewhere).  Waiting lanes poll here while the rest of the warp keeps
+        // traversing; they are neither idle (no new index) nor active.
         {
-            const uint32_t idle = __ballot_sync(FULL, !active);
+            bool start = false;
+            uint32_t landed = 0xFFFFFFFFu;  // rays [0, landed) are readable: ONE watermark load per warp and refill, not one per ray
+            if (IO::kReportsProgress && any_waiting) {
+                landed = io.landed(lane);
+                if (RFW_WAITING && ray_idx < landed) { sp = 0; start = true; }
+            }
+            const uint32_t idle = __ballot_sync(FULL, !active && !RFW_WAITING && !start);
             if (idle != 0u && more) {
                 const uint32_t cnt = __popc(idle);
                 uint32_t base = 0;
                 if (lane == 0) base = atomicAdd(counter, cnt);
                 base = __shfl_sync(FULL, base, 0);
-                if (!active) {
+                if (IO::kReportsProgress && !any_waiting) landed = io.landed(lane);
+                if (!active && !RFW_WAITING && !start) {
                     const uint32_t my = base + __popc(idle & lanemask_lt);
                     if (my < n) {
-                        float4 r0, r1;
-                        io.load(my, r0, r1);
                         ray_idx = my;
-                        active = true;
-                        tmin = r0.w;
-                        hit.inst = -1; hit.prim = -1; hit.t = r1.w; hit.u = 0.0f; hit.v = 0.0f;
-                        sp = 0;
-                        ng = make_uint2(0u, 0x80000000u);
-                        tg = make_uint2(0u, 0u);
-                        if (sv.num_live == 0) {  // empty scene: nothing to traverse, the ray retires as a miss
-                            ng = make_uint2(0u, 0u);
-                            rc.o = xyz(r0); rc.d = xyz(r1);
-                            in_blas = false;
-                            blas_base_sp = 0;
-                        } else if (TWO_LEVEL) {
-                            wo = xyz(r0); wd = xyz(r1);
-                            rc.o = wo; rc.d = wd;
-                            nodes = sv.tlas_nodes;
-                            in_blas = false;
-                            blas_base_sp = 0;
-                        } else {
-                            const InstanceRec& rec = sv.instances[0];
-                            if (sv.single_identity) { rc.o = xyz(r0); rc.d = xyz(r1); }
-                            else xform_ray(rec, xyz(r0), xyz(r1), rc.o, rc.d);
-                            nodes = rec.nodes; tris = rec.tris; cur_inst = rec.inst_id;
-                            in_blas = true;
-                            ray_setup_tri(rc);
-                        }
-                        ray_setup_box(rc);
+                        if (my < landed) start = true;
+                        else sp = -1;
                     }
                 }
                 if (base + cnt >= n) more = false;
+                if (IO::kReportsProgress && io.publish_due(!more, lane)) {
+                    // every ray this warp owned below its oldest in-flight index has been stored
+                    io.publish(__reduce_min_sync(FULL, (active || RFW_WAITING || start) ? ray_idx : 0xFFFFFFFFu), lane);
+                }
             }
-            if (__ballot_sync(FULL, active) == 0u) break;
+            if (start) {
+                float4 r0, r1;
+                io.load(ray_idx, r0, r1);
+                active = true;
+                tmin = r0.w;
+                hit.inst = -1; hit.prim = -1; hit.t = r1.w; hit.u = 0.0f; hit.v = 0.0f;
+                sp = 0;
+                ng = make_uint2(0u, 0x80000000u);
+                tg = make_uint2(0u, 0u);
+                if (sv.num_live == 0) {  // empty scene: nothing to traverse, the ray retires as a miss
+                    ng = make_uint2(0u, 0u);
+                    rc.o = xyz(r0); rc.d = xyz(r1);
+                    in_blas = false;
+                    blas_base_sp = 0;
+                } else if (TWO_LEVEL) {
+                    wo = xyz(r0); wd = xyz(r1);
+                    rc.o = wo; rc.d = wd;
+                    nodes = sv.tlas_nodes;
+                    in_blas = false;
+                    blas_base_sp = 0;
+                } else {
+                    const InstanceRec& rec = sv.instances[0];
+                    if (sv.single_identity) { rc.o = xyz(r0); rc.d = xyz(r1); }
+                    else xform_ray(rec, xyz(r0), xyz(r1), rc.o, rc.d);
+                    nodes = rec.nodes; tris = rec.tris; cur_inst = rec.inst_id;
+                    in_blas = true;
+                    ray_setup_tri(rc);
+                }
+                ray_setup_box(rc);
+            }
+            any_waiting = IO::kReportsProgress && __ballot_sync(FULL, RFW_WAITING) != 0u;
+            if (__ballot_sync(FULL, active) == 0u) {
+                if (!any_waiting) break;
+                if (io.stalled(lane)) break;  // upload stalled for seconds: give up instead of hanging the GPU
+                __nanosleep(256);
+                continue;
+            }
         }
         // ---- traverse until too few lanes are busy -----------------------------------------------------
         for (;;) {
@@ -211,17 +245,19 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
                 else io.store_closest(ray_idx, hit);
                 active = false;
             }
+            if (IO::kReportsProgress && !more && __any_sync(FULL, done)) {  // tail: no refill will come, report at every retire
+                io.publish(__reduce_min_sync(FULL, (active || RFW_WAITING) ? ray_idx : 0xFFFFFFFFu), lane);
+            }
             const uint32_t act = __ballot_sync(FULL, active);
             if (act == 0u) break;
-            if (more && (int)__popc(act) < tune.refill_below) break;
+            if ((more || any_waiting) && (int)__popc(act) < tune.refill_below) break;
         }
     }
 }
 
-// launch with a persistent grid: min(SMs * resident CTAs, CTAs needed for `n_hint` rays)
+// persistent grid: min(SMs * resident CTAs, CTAs needed for `n_hint` rays)
 template <class IO, bool ANY, bool TWO_LEVEL, int MIN_BLOCKS>
-static cudaError_t launch_persistent_mb(cudaStream_t stream, int sm_count, int blocks_per_sm_limit, TraceTuning tune, const SceneView& sv, const IO& io, uint32_t n_hint,
-                                        uint32_t* counter) {
+static cudaError_t persistent_grid_mb(int sm_count, int blocks_per_sm_limit, uint32_t n_hint, int& grid_out) {
     auto kern = k_trace_persistent<IO, ANY, TWO_LEVEL, PT_THREADS, MIN_BLOCKS, PT_SM_STACK>;
     const size_t smem = (size_t)PT_SM_STACK * PT_THREADS * sizeof(uint2);
     static int bps = 0;  // one static per template instantiation
@@ -236,7 +272,19 @@ static cudaError_t launch_persistent_mb(cudaStream_t stream, int sm_count, int b
     const long long needed = ((long long)n_hint + PT_THREADS - 1) / PT_THREADS;
     if (grid > needed) grid = needed;
     if (grid < 1) grid = 1;
-    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
+    grid_out = (int)grid;
+    return cudaSuccess;
+}
+
+template <class IO, bool ANY, bool TWO_LEVEL, int MIN_BLOCKS>
+static cudaError_t launch_persistent_mb(cudaStream_t stream, int sm_count, int blocks_per_sm_limit, TraceTuning tune, const SceneView& sv, const IO& io, uint32_t n_hint,
+                                        uint32_t* counter) {
+    auto kern = k_trace_persistent<IO, ANY, TWO_LEVEL, PT_THREADS, MIN_BLOCKS, PT_SM_STACK>;
+    const size_t smem = (size_t)PT_SM_STACK * PT_THREADS * sizeof(uint2);
+    int grid = 1;
+    cudaError_t e = persistent_grid_mb<IO, ANY, TWO_LEVEL, MIN_BLOCKS>(sm_count, blocks_per_sm_limit, n_hint, grid);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
     kern<<<(int)grid, PT_THREADS, smem, stream>>>(sv, io, counter, tune);
     return cudaGetLastError();
@@ -252,6 +300,10 @@ static cudaError_t launch_persistent_io(cudaStream_t stream, int sm_count, int b
     // single-level: 64 registers / 32 warps per SM (measured best on C2); the two-level variant carries the world-space
     // ray and the instance context as well and spills at 64, so it gets 80 registers / 24 warps per SM
     return launch_persistent_mb<IO, ANY, TWO_LEVEL, (TWO_LEVEL ? 6 : RFW_PT_MIN_BLOCKS)>(stream, sm_count, blocks_per_sm_limit, tune, sv, io, n_hint, counter);
+}
+template <class IO, bool ANY, bool TWO_LEVEL>
+static cudaError_t persistent_grid_io(int sm_count, int blocks_per_sm_limit, uint32_t n_hint, int& grid) {
+    return persistent_grid_mb<IO, ANY, TWO_LEVEL, (TWO_LEVEL ? 6 : RFW_PT_MIN_BLOCKS)>(sm_count, blocks_per_sm_limit, n_hint, grid);
 }
 
 }  // namespace rfw

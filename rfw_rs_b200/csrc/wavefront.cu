@@ -100,6 +100,11 @@ struct ExtendIO {
         S[i] = f4(__int_as_float(h.inst), __int_as_float(h.prim), h.t, __uint_as_float(bary));
     }
     __device__ __forceinline__ void store_any(uint32_t, bool) const {}
+    __device__ __forceinline__ uint32_t landed(int) const { return 0xFFFFFFFFu; }
+    __device__ __forceinline__ bool stalled(int) const { return false; }
+    static constexpr bool kReportsProgress = false;
+    __device__ __forceinline__ bool publish_due(bool, int) const { return false; }
+    __device__ __forceinline__ void publish(uint32_t, int) const {}
 };
 
 struct ConnectIO {
@@ -123,6 +128,11 @@ struct ConnectIO {
         atomicAdd(a + 1, e.y);
         atomicAdd(a + 2, e.z);
     }
+    __device__ __forceinline__ uint32_t landed(int) const { return 0xFFFFFFFFu; }
+    __device__ __forceinline__ bool stalled(int) const { return false; }
+    static constexpr bool kReportsProgress = false;
+    __device__ __forceinline__ bool publish_due(bool, int) const { return false; }
+    __device__ __forceinline__ void publish(uint32_t, int) const {}
 };
 
 // ---- shade: shade.comp:70-266 ---------------------------------------------------------------------------

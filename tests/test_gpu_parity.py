@@ -139,6 +139,30 @@ def test_instanced_two_level(B, oracle_mod):
     parity.compare_hits(rays, gpu.trace_closest(rays), cpu.trace_closest(rays), parity.lookup_from_desc(desc3), "reused-slot")
 
 
+def test_instance_update_rebuilds_only_the_tlas(B, oracle_mod):
+    """moving instances (new matrices through set_3d_instances + synchronize) re-derives the instance
+    records on the device and rebuilds the TLAS; the BLASes are untouched.  Includes a removed slot (zero matrix)."""
+    desc = scenes.instanced_scene(grid=8, subdiv=2, n_lights=4)
+    gpu, cpu = make_pair(B, oracle_mod, desc)
+    before = gpu.build_stats()
+    rays = scenes.random_rays(60000, lo=-4.0, hi=4.0)
+    rays["origin"][:, 1] = np.abs(rays["origin"][:, 1]) * 0.3 + 0.05
+    for frame in range(2):
+        for m in range(8):
+            M = desc.instances[m].reshape(-1, 4, 4).copy()
+            M[:, 3, 1] += 0.25 * (frame + 1) * np.sin(np.arange(len(M)) + m)   # column-major: translation row
+            if frame == 1 and m == 3:
+                M[1] = 0.0                                                       # removed instance keeps its slot
+            desc.instances[m] = M.reshape(-1, 16)
+            gpu.set_3d_instances(m, desc.instances[m]); cpu.set_3d_instances(m, desc.instances[m])
+        gpu.synchronize(); cpu.synchronize()
+        after = gpu.build_stats()
+        assert after["blas_nodes"] == before["blas_nodes"] and after["num_triangles"] == before["num_triangles"]
+        assert after["checksum"] != before["checksum"]  # the TLAS moved
+        parity.compare_hits(rays, gpu.trace_closest(rays), cpu.trace_closest(rays), parity.lookup_from_desc(desc), f"moved instances frame {frame}")
+    assert after["num_instances"] == before["num_instances"] - 1
+
+
 def test_single_transformed_instance(B, oracle_mod):
     desc = scenes.soup_scene(5000, 0.05)
     desc.instances[0] = scenes.to_column_major([scenes.trs((0.3, -0.2, 0.1), (1, 2, 3), 0.7, (1.5, 0.7, 1.1))])
@@ -181,6 +205,41 @@ def test_direction_scaling_and_determinism_property(B):
     cs = gpu.build_stats()["checksum"]
     gpu2 = B.B200Backend(); desc.apply(gpu2)
     assert gpu2.build_stats()["checksum"] == cs
+
+
+@pytest.mark.parametrize("two_level", [False, True])
+def test_host_streamed_single_launch_matches_chunked_pipeline(B, two_level):
+    """Host-buffer entry points with page-locked buffers: ONE persistent launch consumes rays while they are still being
+    uploaded (device watermark) and hits are downloaded per completed granule (flags in mapped host memory).  Must give
+    bit-identical results to the chunked multi-launch pipeline and to pageable buffers, incl. a ragged last granule."""
+    desc = scenes.instanced_scene(grid=6, subdiv=2, n_lights=2) if two_level else scenes.soup_scene(60000, 0.02)
+    gpu = B.B200Backend(); desc.apply(gpu)
+    n = 3 * (1 << 18) + 12345
+    rays = scenes.random_rays(n, lo=-3.0, hi=3.0) if two_level else scenes.random_rays(n)
+    if two_level:
+        rays["origin"][:, 1] = np.abs(rays["origin"][:, 1]) * 0.3 + 0.05
+    pr = B.PinnedArray(n, wire.RAY); ph = B.PinnedArray(n, wire.HIT); po = B.PinnedArray(n, np.uint32)
+    pr.array[:] = rays
+    gpu.set_option("streamed", 1)
+    ph.array["prim"] = -7
+    gpu.trace_closest(pr.array, out=ph.array)
+    streamed = ph.array.copy()
+    po.array[:] = 9
+    gpu.trace_any(pr.array, out=po.array)
+    occ_streamed = po.array.copy()
+    gpu.set_option("streamed", 0)
+    gpu.trace_closest(pr.array, out=ph.array)
+    assert np.array_equal(streamed, ph.array)
+    gpu.trace_any(pr.array, out=po.array)
+    assert np.array_equal(occ_streamed, po.array)
+    assert np.array_equal(occ_streamed != 0, streamed["inst"] >= 0)
+    assert (streamed["prim"] >= 0).mean() > 0.05
+    gpu.set_option("streamed", 1)
+    pageable = gpu.trace_closest(rays)            # not page-locked: falls back to the chunked pipeline
+    assert np.array_equal(pageable, streamed)
+    for small in (1, 31, 1000):                   # batches smaller than one granule
+        gpu.trace_closest(pr.array[:small], out=ph.array[:small])
+        assert np.array_equal(ph.array[:small], streamed[:small])
 
 
 def test_device_pointer_entry_points_and_counters(B, torch_cuda, oracle_mod):
@@ -287,6 +346,19 @@ def test_wavefront_soup_with_many_lights(B, oracle_mod):
     gpu, acc, ref, st = render_pair(B, oracle_mod, desc, view, w, h, spp, depth)
     assert st["shadow_rays"] > 1000 and ref[..., :3].sum() > 0
     check_image(acc / spp, ref / spp, "soup+lights")
+
+
+def test_all_pixel_rmse_at_converging_sample_count(B, oracle_mod):
+    """north_star bar, literally: fixed-seed image RMSE <= 1e-3 over ALL pixels.  The per-sample divergence rate is a
+    property of float32 (edge / silhouette near-ties, ~1e-4 of the samples), so its contribution to the RMSE falls with
+    1/sqrt(spp): at 256 spp the untrimmed figure meets the bar (the trimmed one of check_image holds at any spp)."""
+    desc = scenes.instanced_scene(grid=6, subdiv=2, n_lights=4)
+    w, h, spp, depth = 96, 54, 256, 4
+    view = scenes.camera_view((0, 3.0, -7.0), (0, -0.4, 1.0), w, h)
+    gpu, acc, ref, st = render_pair(B, oracle_mod, desc, view, w, h, spp, depth, sky=(0.3, 0.35, 0.5))
+    full = rmse(acc / spp, ref / spp)
+    full_sqrt = rmse(np.sqrt(acc / spp), np.sqrt(ref / spp))
+    assert full <= 1e-3 and full_sqrt <= 1e-3, (full, full_sqrt)
 
 
 def test_backend_render_resets_on_camera_change(B):
