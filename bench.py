@@ -339,7 +339,7 @@ def main():
             "metric": "Mrays/s closest-hit (incoherent)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": kernel_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "C2: 1M-triangle random soup (s=0.005), 2^24 incoherent rays per GPU, closest hit", "triangles": N_TRIS, "rays_per_step_per_gpu": N_RAYS,
-                       "l2_policy": "inputs larger than L2: 512 MiB rays + 320 MiB hits streamed per step (evict-first); the 58 MB BVH is the step's reused working set",
+                       "l2_policy": "inputs larger than L2: 512 MiB rays + 320 MiB hits streamed per step (evict-first); the 64 MB BVH is the step's reused working set",
                        "scene": "replicated per GPU", "timing": "CUDA events on the backend stream inside librfwb200, max over ranks"},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": N_RAYS * 32, "d2h_bytes_per_step": N_RAYS * 20,
                     "note": "rfwb200_trace_closest with pinned host buffers: ONE persistent launch consumes rays as the upload lands them (device watermark) while completed 2^18-ray granules are downloaded (per-warp progress slots mirrored to the host); wall clock, max over ranks"},
