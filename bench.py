@@ -151,7 +151,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": host_threads(), "kind": "port", "sample": sample, "bvh_build_s": o.build_seconds},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def path_tracing_extra(backend_mod, scenes, torch, rank, world, spp, dist):
@@ -207,7 +207,27 @@ def path_tracing_extra(backend_mod, scenes, torch, rank, world, spp, dist):
     }
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """The driver reads ONE JSON line from stdout; native libraries (NCCL prints its version banner there) must not
+    interleave with it: fd 1 is pointed at stderr for the whole run and the result line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -354,7 +374,7 @@ def main():
             "wall_ms_timed_region": wall_ms,
             "extra": extra,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

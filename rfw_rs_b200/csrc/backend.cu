@@ -976,7 +976,7 @@ int Backend::render_spp(const RfwCameraView3D* view, uint32_t spp, uint32_t dept
     ss.sky = skybox.desc;
     if (materials.empty()) return fail(RFWB200_ERR_INVALID, "render: no materials set");
     wf.refill_below = tcfg.refill_below;
-    wf.tri_batch = tcfg.tri_batch;
+    wf.tri_batch = tcfg.tri_batch; wf.tri_batch_two_level = tcfg.tri_batch_two_level; wf.tri_blocked = tcfg.tri_blocked;
     const uint64_t before = wf.launches;
     BK_CUDA(wf.ensure_wave(wf.wave_spp_for(spp)), "wavefront queues");  // one-time (grow-only) allocation, outside the timed bracket
     BK_CUDA(cudaEventRecord(ev0, stream), "event");
@@ -1098,6 +1098,8 @@ int Backend::set_option(const char* key, int64_t value) {
     else if (k == "blocks_per_sm") tcfg.blocks_per_sm = (int)value;
     else if (k == "refill_below") tcfg.refill_below = (int)value;
     else if (k == "tri_batch") tcfg.tri_batch = (int)value;
+    else if (k == "tri_batch_two_level") tcfg.tri_batch_two_level = (int)value;
+    else if (k == "tri_blocked") tcfg.tri_blocked = (int)value;
     else if (k == "min_blocks") tcfg.min_blocks = (int)value;
     else if (k == "l2_persist") { l2_persist_enabled = value != 0; if (!l2_persist_enabled) { cudaStreamAttrValue a{}; cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &a); cudaCtxResetPersistingL2Cache(); } else { if (l2_persist_max && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, l2_persist_max) != cudaSuccess) { cudaGetLastError(); l2_persist_max = 0; } update_l2_policy(); } }
     else if (k == "streamed") streamed_enabled = value != 0;  // host-buffer entry points: single-launch streaming (1) or chunked pipeline (0)

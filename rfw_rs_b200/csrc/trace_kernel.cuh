@@ -32,6 +32,11 @@ namespace rfw {
 static constexpr uint32_t FULL = 0xFFFFFFFFu;
 static constexpr int PT_THREADS = 128;
 static constexpr int PT_SM_STACK = 12;
+// Leaf groups a lane may set aside while it keeps traversing (speculative traversal, single-level kernels).  MEASURED AND
+// SWITCHED OFF (0): on C2 every setting lost to the non-speculative kernel (best 1 494 vs 1 557 Mrays/s; 1 229 with deep
+// speculation) — 82 % of the rays hit something, and walking on with a stale (too long) hit distance visits far more
+// nodes than the fuller triangle phase saves; it also needs 72 registers (7 CTAs/SM) to avoid spills.
+static constexpr int PT_DEFER = 0;
 
 // Per-lane traversal stack: the first SM_STACK entries live in shared memory, laid out [entry][thread] so a warp's
 // accesses to one entry are 32 consecutive 8-byte words (conflict-free); deeper entries overflow to local memory.
@@ -59,7 +64,8 @@ static constexpr int PT_L_STACK = 24;
 
 struct TraceTuning {
     int refill_below;  // refill when fewer than this many lanes still traverse
-    int tri_batch;     // run the triangle phase when at least this many lanes have pending triangles
+    int tri_batch;     // run the triangle phase when at least this many lanes have pending triangles ...
+    int tri_blocked;   // ... or when this many of them cannot traverse any further until their triangles are tested
 };
 
 template <class IO, bool ANY, bool TWO_LEVEL, int THREADS, int MIN_BLOCKS, int SM_STACK>
@@ -88,6 +94,15 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
     int cur_inst = -1;
     int blas_base_sp = 0;
     uint2 ng = make_uint2(0u, 0u), tg = make_uint2(0u, 0u);
+    // Speculative traversal (single-level kernels): a lane that found leaf triangles does not stop for them.  The group
+    // at hand stays in `tg`, up to DQ further groups are set aside in shared memory, and the lane keeps walking nodes
+    // with its (possibly stale, i.e. too long) hit distance.  The triangle phase then runs when many lanes have
+    // triangles, instead of every iteration with a handful of lanes (it ran at ~11 of 32 lanes).  The price is a few
+    // node visits a fresher hit distance would have culled.  Two-level kernels keep DQ = 0: deferred triangles would
+    // refer to the object-space ray of an instance the lane may have left.
+    constexpr int DQ = TWO_LEVEL ? 0 : PT_DEFER;
+    const uint32_t dq_base = st_base + (uint32_t)(SM_STACK * THREADS * 8);
+    int dn = 0;  // groups set aside
     // host-streamed policy only (folds away elsewhere): a lane that owns ray index `ray_idx` whose ray has not been
     // uploaded yet is "waiting", encoded as sp == -1 (no extra register: this kernel sits at its 64-register budget)
 #define RFW_WAITING (IO::kReportsProgress && sp < 0)
@@ -133,6 +148,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
                 tmin = r0.w;
                 hit.inst = -1; hit.prim = -1; hit.t = r1.w; hit.u = 0.0f; hit.v = 0.0f;
                 sp = 0;
+                dn = 0;
                 ng = make_uint2(0u, 0x80000000u);
                 tg = make_uint2(0u, 0u);
                 if (sv.num_live == 0) {  // empty scene: nothing to traverse, the ray retires as a miss
@@ -167,7 +183,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
         // ---- traverse until too few lanes are busy -----------------------------------------------------
         for (;;) {
             bool done = false;
-            if (active && tg.y == 0u) {
+            if (active && (tg.y == 0u || (DQ > 0 && dn < DQ))) {
+                uint2 tgn = make_uint2(0u, 0u);  // leaf group found in this step
                 // (a) nothing at hand: pop (leaving the BLAS when its part of the stack is exhausted)
                 if (!RFW_NODE_HITS(ng)) {
                     if (TWO_LEVEL && in_blas && sp == blas_base_sp) {
@@ -176,10 +193,11 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
                         ray_setup_box(rc);
                         nodes = sv.tlas_nodes;
                     }
-                    if (sp == 0) done = true;
-                    else {
+                    if (sp == 0) {
+                        if (tg.y == 0u) done = true;  // (with triangles still pending the lane waits for the triangle phase)
+                    } else {
                         RFW_STACK_POP(ng);
-                        if (!RFW_NODE_HITS(ng)) { tg = ng; ng = make_uint2(0u, 0u); }  // a parked TLAS leaf group
+                        if (!RFW_NODE_HITS(ng)) { tgn = ng; ng = make_uint2(0u, 0u); }  // a parked TLAS leaf group
                     }
                 }
                 // (b) node step
@@ -195,9 +213,13 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
                     const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
                     const uint32_t hm = intersect_wide_node(n0, n1, n2, n3, n4, rc, tmin, hit.t);
                     ng.x = __float_as_uint(n1.x);
-                    tg.x = __float_as_uint(n1.y);
+                    tgn.x = __float_as_uint(n1.y);
                     ng.y = (hm & 0xFF000000u) | (__float_as_uint(n0.w) >> 24);
-                    tg.y = hm & 0x00FFFFFFu;
+                    tgn.y = hm & 0x00FFFFFFu;
+                }
+                if (tgn.y != 0u) {
+                    if (DQ == 0 || tg.y == 0u) tg = tgn;
+                    else { sts_u2(dq_base + (uint32_t)dn * (uint32_t)(THREADS * 8), tgn); dn++; }
                 }
             }
             // (c) TLAS leaves are entered right away: cheap, and they only produce more node work
@@ -221,8 +243,11 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
             const bool pending = active && !done && tg.y != 0u;
             const uint32_t pend = __ballot_sync(FULL, pending);
             if (pend != 0u) {
-                const uint32_t can_node = __ballot_sync(FULL, active && !done && !pending);
-                if ((int)__popc(pend) >= tune.tri_batch || can_node == 0u) {
+                // lanes that can make traversal progress in the next iteration without their triangles being tested
+                const bool can_go = active && !done && (!pending || (DQ > 0 && dn < DQ && (RFW_NODE_HITS(ng) || sp > 0)));
+                const uint32_t can_node = __ballot_sync(FULL, can_go);
+                const int n_blocked = __popc(pend & ~can_node);
+                if ((int)__popc(pend) >= tune.tri_batch || (DQ > 0 && n_blocked >= tune.tri_blocked) || can_node == 0u) {
                     if (pending) {
                         const int tb = 31 - __clz((int)tg.y);
                         tg.y &= ~(1u << tb);
@@ -237,6 +262,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
                                 hit.t = t; hit.u = u; hit.v = v; hit.prim = prim; hit.inst = cur_inst;
                             }
                         }
+                        if (DQ > 0 && tg.y == 0u && dn > 0) { dn--; tg = lds_u2(dq_base + (uint32_t)dn * (uint32_t)(THREADS * 8)); }
                     }
                 }
             }
@@ -259,7 +285,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
 template <class IO, bool ANY, bool TWO_LEVEL, int MIN_BLOCKS>
 static cudaError_t persistent_grid_mb(int sm_count, int blocks_per_sm_limit, uint32_t n_hint, int& grid_out) {
     auto kern = k_trace_persistent<IO, ANY, TWO_LEVEL, PT_THREADS, MIN_BLOCKS, PT_SM_STACK>;
-    const size_t smem = (size_t)PT_SM_STACK * PT_THREADS * sizeof(uint2);
+    const size_t smem = (size_t)(PT_SM_STACK + PT_DEFER) * PT_THREADS * sizeof(uint2);
     static int bps = 0;  // one static per template instantiation
     if (bps == 0) {
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, PT_THREADS, smem);
@@ -280,7 +306,7 @@ template <class IO, bool ANY, bool TWO_LEVEL, int MIN_BLOCKS>
 static cudaError_t launch_persistent_mb(cudaStream_t stream, int sm_count, int blocks_per_sm_limit, TraceTuning tune, const SceneView& sv, const IO& io, uint32_t n_hint,
                                         uint32_t* counter) {
     auto kern = k_trace_persistent<IO, ANY, TWO_LEVEL, PT_THREADS, MIN_BLOCKS, PT_SM_STACK>;
-    const size_t smem = (size_t)PT_SM_STACK * PT_THREADS * sizeof(uint2);
+    const size_t smem = (size_t)(PT_SM_STACK + PT_DEFER) * PT_THREADS * sizeof(uint2);
     int grid = 1;
     cudaError_t e = persistent_grid_mb<IO, ANY, TWO_LEVEL, MIN_BLOCKS>(sm_count, blocks_per_sm_limit, n_hint, grid);
     if (e != cudaSuccess) return e;

@@ -483,7 +483,7 @@ cudaError_t Wavefront::render(cudaStream_t stream, const SceneView& sv, const Sh
     const int shade_blocks = sm_count * 8;
     const uint32_t wave = wave_spp_for(spp);
     WF_CK(ensure_wave(wave));
-    const TraceTuning tune{refill_below, tri_batch};
+    const TraceTuning tune{refill_below, sv.two_level ? tri_batch_two_level : tri_batch, tri_blocked};
     for (uint32_t s = 0; s < spp; s += wave) {
         FrameParams fp = make_params(*this, cam, first_sample + s, 0);
         fp.wave_spp = std::min(wave, spp - s);

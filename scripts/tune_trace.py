@@ -23,16 +23,17 @@ results = []
 mbs = [int(x) for x in os.environ.get("TUNE_MB", "4,5,6,8").split(",")]
 tbs = [int(x) for x in os.environ.get("TUNE_TB", "1,8,12,16,20,24").split(",")]
 rfs = [int(x) for x in os.environ.get("TUNE_RF", "16,24,28").split(",")]
-for mb, tb, rf in itertools.product(mbs, tbs, rfs):
-    be.set_option("min_blocks", mb); be.set_option("tri_batch", tb); be.set_option("refill_below", rf)
+bls = [int(x) for x in os.environ.get("TUNE_BL", "4").split(",")]
+for mb, tb, rf, bl in itertools.product(mbs, tbs, rfs, bls):
+    be.set_option("min_blocks", mb); be.set_option("tri_batch", tb); be.set_option("refill_below", rf); be.set_option("tri_blocked", bl)
     r = run(reps=2)
     h = np.frombuffer(d_hits.cpu().numpy().tobytes(), dtype=wire.HIT)
     if ref is None: ref = h.copy()
     same = np.array_equal(ref["prim"], h["prim"]) and np.array_equal(ref["t"], h["t"])
-    results.append((r, mb, tb, rf, same))
-    print(f"min_blocks {mb} tri_batch {tb:2d} refill_below {rf:2d}: closest {r:8.1f} Mrays/s  same={same}", flush=True)
+    results.append((r, mb, tb, rf, same, bl))
+    print(f"min_blocks {mb} tri_batch {tb:2d} tri_blocked {bl:2d} refill_below {rf:2d}: closest {r:8.1f} Mrays/s  same={same}", flush=True)
 results.sort(reverse=True)
 print("BEST", results[:5])
-r, mb, tb, rf, _ = results[0]
-be.set_option("min_blocks", mb); be.set_option("tri_batch", tb); be.set_option("refill_below", rf)
+r, mb, tb, rf, _, bl = results[0]
+be.set_option("min_blocks", mb); be.set_option("tri_batch", tb); be.set_option("refill_below", rf); be.set_option("tri_blocked", bl)
 print("any-hit at best closest config:", run(True))
