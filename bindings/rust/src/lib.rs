@@ -104,7 +104,14 @@ impl Backend for B200Backend {
         let c = RfwTextureData { width: s.width, height: s.height, mip_levels: s.mip_levels, bytes: s.bytes.as_ptr(), num_bytes: s.bytes.len() as u64, format: s.format as u32 };
         check(unsafe { rfwb200_set_skybox(self.handle, &c) });
     }
-    fn set_skins(&mut self, _s: &[SkinData<'_>], _c: &BitSlice) {}
+    fn set_skins(&mut self, s: &[SkinData<'_>], changed: &BitSlice) {
+        let c: Vec<RfwSkinData> = s.iter().map(|s| RfwSkinData {
+            inverse_bind_matrices: s.inverse_bind_matrices.as_ptr() as *const f32, joint_matrices: s.joint_matrices.as_ptr() as *const f32,
+            num_joints: s.joint_matrices.len() as u32,
+        }).collect();
+        let ch: Vec<u32> = (0..s.len()).map(|i| changed[i] as u32).collect();
+        check(unsafe { rfwb200_set_skins(self.handle, c.as_ptr(), c.len() as u32, ch.as_ptr()) });
+    }
 }
 
 impl Drop for B200Backend { fn drop(&mut self) { unsafe { rfwb200_destroy(self.handle) } } }

@@ -333,8 +333,17 @@ RFWB200_API int rfwb200_set_area_lights(void* handle, const RfwAreaLight* lights
 RFWB200_API int rfwb200_set_directional_lights(void* handle, const RfwDirectionalLight* lights, uint32_t num, const uint32_t* changed);
 /* Backend::set_skybox (lib.rs:78) */
 RFWB200_API int rfwb200_set_skybox(void* handle, const RfwTextureData* skybox);
-/* Backend::set_skins (lib.rs:81) — accepted, ignored (skinning is row (f)2) */
-RFWB200_API int rfwb200_set_skins(void* handle, uint32_t num_skins);
+/* FFI repack of SkinData<'a> (crates/rfw-backend/src/structs.rs:6-11): column-major Mat4 arrays of `num_joints` */
+typedef struct RfwSkinData {
+    const float* inverse_bind_matrices; /* kept for completeness; the joint matrices already include them */
+    const float* joint_matrices;
+    uint32_t num_joints;
+} RfwSkinData;
+/* Backend::set_skins (lib.rs:81).  An instance whose skin id (RfwInstancesData3D::skin_ids) names a skin, of a mesh
+ * that carries per-vertex joint data (RfwMeshData3D::skin_data, 3 per triangle), is traced and shaded with its own
+ * skinned copy of the mesh: SkinnedTriangles3D::apply (structs.rs:820-877) on the device + a BLAS of its own,
+ * rebuilt at synchronize() whenever the skin changed. */
+RFWB200_API int rfwb200_set_skins(void* handle, const RfwSkinData* skins, uint32_t num_skins, const uint32_t* changed);
 /* Backend::set_2d_mesh / set_2d_instances (lib.rs:36-39) — accepted, ignored
  * (gpu-rt precedent: unimplemented!(), backends/gpu-rt/src/lib.rs:1131-1137) */
 RFWB200_API int rfwb200_set_2d_mesh(void* handle, uint32_t id, const void* vertices, uint32_t num_vertices, int32_t tex_id);

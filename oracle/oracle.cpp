@@ -303,6 +303,7 @@ static inline bool mt_intersect(const RfwRTTriangle& tri, V3 origin, V3 directio
 
 struct Mesh {
     std::vector<RfwRTTriangle> tris;
+    std::vector<RfwJointData> skin;  // per vertex (3 per triangle), MeshData3D::skin_data; empty = not skinned
     BVH bvh;
     Box bounds;
     bool dirty = true;
@@ -322,7 +323,48 @@ struct Instance {
     uint32_t mesh;
     int32_t global_id;
     M4 matrix, inverse, normal;
+    const Mesh* geom = nullptr;  // the mesh's own geometry, or this instance's skinned copy
 };
+
+// SkinnedTriangles3D::apply, crates/rfw-backend/src/structs.rs:820-877: per vertex a weighted sum of four joint
+// matrices; positions by the matrix, vertex normals and tangents by its inverse transpose (not renormalised), every
+// tangent's w taken from tangent2 (as the reference does), geometric normal recomputed from the new vertices.
+// Reference defect NOT copied: it indexes the joint data of triangle i as (i / 3, i + 1, i + 2) instead of
+// (3i, 3i + 1, 3i + 2) (:835-837) — with the RTTriangle <-> vertex correspondence of Mesh3D::new
+// (crates/rfw-scene/src/objects_3d/mod.rs:331-383) only the latter deforms a mesh coherently.
+static void apply_skin(const Mesh& src, const std::vector<M4>& joints, Mesh& dst) {
+    dst.tris = src.tris;
+    dst.skin.clear();
+    for (size_t i = 0; i < dst.tris.size(); i++) {
+        RfwRTTriangle& t = dst.tris[i];
+        float* verts[3] = {t.vertex0, t.vertex1, t.vertex2};
+        float* nrms[3] = {t.n0, t.n1, t.n2};
+        float* tans[3] = {t.tangent0, t.tangent1, t.tangent2};
+        const float tw = t.tangent2[3];
+        for (int k = 0; k < 3; k++) {
+            const RfwJointData& jd = src.skin[3 * i + k];
+            if (jd.joint[0] >= joints.size() || jd.joint[1] >= joints.size() || jd.joint[2] >= joints.size() || jd.joint[3] >= joints.size()) continue;
+            M4 M;
+            for (int e = 0; e < 16; e++) {
+                float acc = jd.weight[0] * joints[jd.joint[0]].m[e];
+                acc = acc + jd.weight[1] * joints[jd.joint[1]].m[e];
+                acc = acc + jd.weight[2] * joints[jd.joint[2]].m[e];
+                acc = acc + jd.weight[3] * joints[jd.joint[3]].m[e];
+                M.m[e] = acc;
+            }
+            M4 inv;
+            if (!invert(M, inv)) continue;  // degenerate blend: leave the vertex in bind pose
+            const M4 nM = transpose(inv);
+            const V3 p = xform_point(M, V3(verts[k])), n = xform_vec(nM, V3(nrms[k])), tg = xform_vec(nM, V3(tans[k]));
+            verts[k][0] = p.x; verts[k][1] = p.y; verts[k][2] = p.z;
+            nrms[k][0] = n.x; nrms[k][1] = n.y; nrms[k][2] = n.z;
+            tans[k][0] = tg.x; tans[k][1] = tg.y; tans[k][2] = tg.z; tans[k][3] = tw;
+        }
+        const V3 gn = normalize(cross(V3(t.vertex1) - V3(t.vertex0), V3(t.vertex2) - V3(t.vertex0)));  // RTTriangle::normal, structs.rs:970-974
+        t.normal[0] = gn.x; t.normal[1] = gn.y; t.normal[2] = gn.z;
+    }
+    dst.dirty = true;
+}
 
 struct HitRec {
     int inst = -1, prim = -1;
@@ -396,6 +438,9 @@ struct Scene {
     bool has_sky = false;
     std::map<uint32_t, Mesh> meshes;
     std::map<uint32_t, std::vector<M4>> instance_lists;
+    std::map<uint32_t, std::vector<int32_t>> instance_skins;  // InstancesData3D::skin_ids (-1 = none)
+    std::vector<std::vector<M4>> skins;                        // SkinData::joint_matrices per skin id
+    std::map<std::pair<uint32_t, uint32_t>, Mesh> skinned;     // (mesh id, index in list) -> skinned copy
     std::vector<Instance> instances;  // live ones, TLAS order
     BVH tlas;
     std::vector<RfwDeviceMaterial> materials;
@@ -412,21 +457,31 @@ struct Scene {
 #pragma omp parallel for schedule(dynamic, 1)  // parallel across meshes only (backends/gpu-rt/src/lib.rs:1345-1357)
         for (int i = 0; i < (int)todo.size(); i++) todo[i]->build();
         instances.clear();
+        skinned.clear();
         int32_t gid = 0;
         std::vector<Box> boxes;
         for (auto& kv : instance_lists) {  // ascending mesh id
             auto mit = meshes.find(kv.first);
+            auto sit = instance_skins.find(kv.first);
             for (size_t i = 0; i < kv.second.size(); i++, gid++) {
                 if (mit == meshes.end()) continue;
+                const Mesh* geom = &mit->second;
+                const int32_t skin_id = (sit != instance_skins.end() && i < sit->second.size()) ? sit->second[i] : -1;
+                if (skin_id >= 0 && (size_t)skin_id < skins.size() && !skins[skin_id].empty() && geom->skin.size() == 3 * geom->tris.size() && !geom->tris.empty()) {
+                    Mesh& sm = skinned[std::make_pair(kv.first, (uint32_t)i)];
+                    apply_skin(mit->second, skins[skin_id], sm);
+                    sm.build();
+                    geom = &sm;
+                }
                 const M4& M = kv.second[i];
                 bool zero = true;
                 for (int k = 0; k < 16; k++) zero &= (M.m[k] == 0.0f);
                 if (zero) continue;  // removed slot, instances_3d.rs:79-86
                 Instance in;
-                in.mesh = kv.first; in.global_id = gid; in.matrix = M;
+                in.mesh = kv.first; in.global_id = gid; in.matrix = M; in.geom = geom;
                 if (!invert(M, in.inverse)) continue;
                 in.normal = transpose(in.inverse);
-                const Box& lb = mit->second.bounds;
+                const Box& lb = geom->bounds;
                 Box wb;
                 for (int c = 0; c < 8; c++) {  // culling.comp:58-92
                     V3 p((c & 1) ? lb.hi.x : lb.lo.x, (c & 2) ? lb.hi.y : lb.lo.y, (c & 4) ? lb.hi.z : lb.lo.z);
@@ -526,7 +581,7 @@ struct Scene {
     // ---- TLAS — ray_gen.comp:310-362; object-space ray not renormalised (:339-341) -------------
     template <bool ANY>
     bool enter_instance(const Instance& in, V3 o, V3 d, float t_min, float det_eps, int mode, HitRec& best, Counters* ctr) const {
-        const Mesh& m = meshes.find(in.mesh)->second;
+        const Mesh& m = *in.geom;
         V3 oo = xform_point(in.inverse, o);
         V3 od = xform_vec(in.inverse, d);
         return blas<ANY>(m, oo, od, t_min, det_eps, mode, in.global_id, best, ctr);
@@ -955,7 +1010,7 @@ static V3 trace_path(const Scene& sc, const RfwCameraView3D& cam, int w, int h, 
             break;
         }
         const Instance* in = sc.find_instance(hit.inst);
-        const Mesh& mesh = sc.meshes.find(in->mesh)->second;
+        const Mesh& mesh = *in->geom;
         const RfwRTTriangle& tri = mesh.tris[hit.prim];
         ShadingData sd = extract(sc.materials[tri.mat_id]);
         const RfwDeviceMaterial& mat = sc.materials[tri.mat_id];
@@ -1081,6 +1136,27 @@ void orc_set_instances(void* s, uint32_t mesh, const float* matrices, uint32_t n
     if (n) std::memcpy(v.data(), matrices, (size_t)n * 64);
 }
 void orc_set_materials(void* s, const RfwDeviceMaterial* m, uint32_t n) { ((Scene*)s)->materials.assign(m, m + n); }
+// skinning: joint data per vertex of a mesh, skin ids per instance, joint matrices per skin
+void orc_set_mesh_skin(void* s, uint32_t mesh, const RfwJointData* jd, uint32_t n) {
+    Mesh& m = ((Scene*)s)->meshes[mesh];
+    m.skin.assign(jd, jd + n);
+}
+void orc_set_instance_skins(void* s, uint32_t mesh, const int32_t* ids, uint32_t n) { ((Scene*)s)->instance_skins[mesh].assign(ids, ids + n); }
+void orc_set_num_skins(void* s, uint32_t n) { ((Scene*)s)->skins.resize(n); }
+void orc_set_skin(void* s, uint32_t id, const float* joint_matrices, uint32_t n_joints) {
+    Scene& sc = *(Scene*)s;
+    if (id >= sc.skins.size()) sc.skins.resize(id + 1);
+    sc.skins[id].resize(n_joints);
+    for (uint32_t j = 0; j < n_joints; j++) std::memcpy(sc.skins[id][j].m, joint_matrices + 16 * j, 64);
+}
+// the skinned copy of instance (mesh, index) after orc_build: returns the triangle count, fills `out` if non-null
+uint32_t orc_get_skinned_triangles(void* s, uint32_t mesh, uint32_t index, RfwRTTriangle* out) {
+    const Scene& sc = *(Scene*)s;
+    auto it = sc.skinned.find(std::make_pair(mesh, index));
+    if (it == sc.skinned.end()) return 0;
+    if (out) std::memcpy(out, it->second.tris.data(), it->second.tris.size() * sizeof(RfwRTTriangle));
+    return (uint32_t)it->second.tris.size();
+}
 void orc_set_num_textures(void* s, uint32_t n) { ((Scene*)s)->textures.resize(n); }
 void orc_set_texture(void* s, uint32_t i, uint32_t w, uint32_t h, uint32_t mips, uint32_t format, const uint8_t* bytes, uint64_t nbytes) {
     Scene& sc = *(Scene*)s;

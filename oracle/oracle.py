@@ -42,6 +42,12 @@ def lib():
         L.orc_set_instances.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         for nm in ("materials", "area_lights", "point_lights", "spot_lights", "directional_lights"):
             getattr(L, "orc_set_" + nm).argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.orc_set_mesh_skin.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+        L.orc_set_instance_skins.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+        L.orc_set_num_skins.argtypes = [C.c_void_p, C.c_uint32]
+        L.orc_set_skin.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+        L.orc_get_skinned_triangles.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.orc_get_skinned_triangles.restype = C.c_uint32
         L.orc_set_num_textures.argtypes = [C.c_void_p, C.c_uint32]
         L.orc_set_texture.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64]
         L.orc_set_skybox.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64]
@@ -101,18 +107,37 @@ class OracleBackend:
             pass
 
     # ---- Backend surface -----------------------------------------------------------------------
-    def set_3d_mesh(self, mesh_id, triangles):
+    def set_3d_mesh(self, mesh_id, triangles, vertices=None, flags=3, skin_data=None):
         t = np.ascontiguousarray(triangles)
         assert t.dtype.itemsize == 176
         self.L.orc_set_mesh(self.h, mesh_id, _ptr(t), len(t))
+        sk = np.zeros(0, dtype=np.uint8) if skin_data is None else np.ascontiguousarray(skin_data)
+        assert len(sk) == 0 or sk.dtype.itemsize == 32
+        self.L.orc_set_mesh_skin(self.h, mesh_id, _ptr(sk), len(sk))
 
     def unload_3d_meshes(self, ids):
         for i in ids:
             self.L.orc_unload_mesh(self.h, int(i))
 
-    def set_3d_instances(self, mesh_id, matrices):
+    def set_3d_instances(self, mesh_id, matrices, skin_ids=None, flags=None):
         m = np.ascontiguousarray(matrices, dtype=np.float32).reshape(-1, 16)
         self.L.orc_set_instances(self.h, mesh_id, _ptr(m), len(m))
+        sk = np.zeros(0, dtype=np.int32) if skin_ids is None else np.ascontiguousarray(skin_ids, dtype=np.int32)
+        self.L.orc_set_instance_skins(self.h, mesh_id, _ptr(sk), len(sk))
+
+    def skinned_triangles(self, mesh_id, index, dtype):
+        """RTTriangle records of the skinned copy of instance (mesh, index) (valid after synchronize)."""
+        n = self.L.orc_get_skinned_triangles(self.h, mesh_id, index, None)
+        out = np.zeros(n, dtype=dtype)
+        if n:
+            self.L.orc_get_skinned_triangles(self.h, mesh_id, index, _ptr(out))
+        return out
+
+    def set_skins(self, skins=(), changed=None):
+        self.L.orc_set_num_skins(self.h, len(skins))
+        for k, j in enumerate(skins):
+            a = np.ascontiguousarray(j, dtype=np.float32).reshape(-1, 16)
+            self.L.orc_set_skin(self.h, k, _ptr(a), len(a))
 
     def _set(self, name, arr, size):
         a = np.ascontiguousarray(arr)

@@ -58,7 +58,7 @@ def load_library():
         "rfwb200_set_area_lights": ([vp, vp, u32, vp], i32),
         "rfwb200_set_directional_lights": ([vp, vp, u32, vp], i32),
         "rfwb200_set_skybox": ([vp, vp], i32),
-        "rfwb200_set_skins": ([vp, u32], i32),
+        "rfwb200_set_skins": ([vp, vp, u32, vp], i32),
         "rfwb200_set_2d_mesh": ([vp, u32, vp, u32, C.c_int32], i32),
         "rfwb200_set_2d_instances": ([vp, u32, vp, u32], i32),
         "rfwb200_trace_closest": ([vp, vp, u64, vp], i32),
@@ -163,7 +163,7 @@ class B200Backend:
             raise RfwError(f"{what} failed ({rc}): {self.L.rfwb200_last_error().decode()}")
 
     # ---- Backend trait ---------------------------------------------------------------------------
-    def set_3d_mesh(self, mesh_id, triangles, vertices=None, flags=3):
+    def set_3d_mesh(self, mesh_id, triangles, vertices=None, flags=3, skin_data=None):
         t = np.ascontiguousarray(triangles)
         if len(t) and t.dtype.itemsize != 176:
             raise RfwError("set_3d_mesh: triangles must be 176-byte RTTriangle records")
@@ -172,6 +172,11 @@ class B200Backend:
         if vertices is not None and len(vertices):
             v = np.ascontiguousarray(vertices)
             d.vertices, d.num_vertices = _ptr(v), len(v)
+        if skin_data is not None and len(skin_data):
+            sk = np.ascontiguousarray(skin_data)
+            if sk.dtype.itemsize != 32:
+                raise RfwError("set_3d_mesh: skin_data must be 32-byte JointData records")
+            d.skin_data, d.num_skin_data = _ptr(sk), len(sk)
         d.flags = flags
         self._ck(self.L.rfwb200_set_3d_mesh(self.h, mesh_id, C.addressof(d)), "set_3d_mesh")
 
@@ -183,6 +188,11 @@ class B200Backend:
         m = np.ascontiguousarray(matrices, dtype=np.float32).reshape(-1, 16)
         d = wire.CInstancesData3D()
         d.matrices, d.num_instances = _ptr(m), len(m)
+        if skin_ids is not None:
+            sk = np.ascontiguousarray(skin_ids, dtype=np.int32)
+            if len(sk) != len(m):
+                raise RfwError("set_3d_instances: one skin id per instance")
+            d.skin_ids = _ptr(sk)
         self._ck(self.L.rfwb200_set_3d_instances(self.h, mesh_id, C.addressof(d)), "set_3d_instances")
 
     def _set_array(self, fn, arr, size, what):
@@ -233,7 +243,18 @@ class B200Backend:
         self._ck(self.L.rfwb200_set_skybox(self.h, C.addressof(d)), "set_skybox")
 
     def set_skins(self, skins=(), changed=None):
-        self._ck(self.L.rfwb200_set_skins(self.h, len(skins)), "set_skins")
+        """skins: list of (n_joints, 16) column-major joint matrices (SkinData::joint_matrices)."""
+        skins = [np.ascontiguousarray(j, dtype=np.float32).reshape(-1, 16) for j in skins]
+        if not skins:
+            self._ck(self.L.rfwb200_set_skins(self.h, None, 0, None), "set_skins")
+            return
+        arr = (wire.CSkinData * len(skins))()
+        for k, j in enumerate(skins):
+            arr[k].inverse_bind_matrices = None
+            arr[k].joint_matrices = _ptr(j)
+            arr[k].num_joints = len(j)
+        ch = None if changed is None else np.ascontiguousarray(changed, dtype=np.uint32)
+        self._ck(self.L.rfwb200_set_skins(self.h, C.addressof(arr), len(skins), None if ch is None else _ptr(ch)), "set_skins")
 
     def set_2d_mesh(self, mesh_id, data=None):
         self._ck(self.L.rfwb200_set_2d_mesh(self.h, mesh_id, None, 0, -1), "set_2d_mesh")

@@ -40,7 +40,7 @@ int rfwb200_set_spot_lights(void* handle, const RfwSpotLight* l, uint32_t n, con
 int rfwb200_set_area_lights(void* handle, const RfwAreaLight* l, uint32_t n, const uint32_t*) { RFW_GUARD(handle); return b->set_area_lights(l, n); }
 int rfwb200_set_directional_lights(void* handle, const RfwDirectionalLight* l, uint32_t n, const uint32_t*) { RFW_GUARD(handle); return b->set_directional_lights(l, n); }
 int rfwb200_set_skybox(void* handle, const RfwTextureData* t) { RFW_GUARD(handle); return b->set_skybox(t); }
-int rfwb200_set_skins(void* handle, uint32_t) { RFW_GUARD(handle); return b ? RFWB200_OK : RFWB200_ERR_INVALID; }
+int rfwb200_set_skins(void* handle, const RfwSkinData* skins, uint32_t n, const uint32_t* changed) { RFW_GUARD(handle); return b->set_skins(skins, n, changed); }
 int rfwb200_set_2d_mesh(void* handle, uint32_t, const void*, uint32_t, int32_t) { RFW_GUARD(handle); return b ? RFWB200_OK : RFWB200_ERR_INVALID; }
 int rfwb200_set_2d_instances(void* handle, uint32_t, const float*, uint32_t) { RFW_GUARD(handle); return b ? RFWB200_OK : RFWB200_ERR_INVALID; }
 

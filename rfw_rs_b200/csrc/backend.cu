@@ -11,6 +11,7 @@
 #include <time.h>
 
 #include <algorithm>
+#include <set>
 #include <chrono>
 #include <cstdlib>
 
@@ -106,6 +107,8 @@ Backend::~Backend() {
     d_instances.release(); d_inst_shading.release(); d_materials.release();
     d_area.release(); d_point.release(); d_spot.release(); d_dir.release();
     d_rays.release(); d_hits.release(); d_occ.release();
+    for (auto& sk : skins) sk.joints.release();
+    for (auto& si : skinned) release_skinned(si);
     for (auto& t : textures) t.texels.release();
     skybox.texels.release(); d_tex_desc.release();
     d_mesh_table.release(); d_matrices.release();
@@ -134,6 +137,7 @@ int Backend::set_3d_mesh(uint32_t id, const RfwMeshData3D* data) {
     MeshRec& m = meshes[id];
     BK_CUDA(cudaStreamSynchronize(stream), "sync");
     if (m.d_tris) { cudaFree(m.d_tris); m.d_tris = nullptr; }
+    if (m.d_skin) { cudaFree(m.d_skin); m.d_skin = nullptr; }
     m.n = data->num_triangles;
     m.flags = data->flags;
     m.present = true;
@@ -141,6 +145,10 @@ int Backend::set_3d_mesh(uint32_t id, const RfwMeshData3D* data) {
     if (m.n) {
         BK_CUDA(cudaMalloc(&m.d_tris, (size_t)m.n * sizeof(RfwRTTriangle)), "mesh alloc");
         BK_CUDA(cudaMemcpyAsync(m.d_tris, data->triangles, (size_t)m.n * sizeof(RfwRTTriangle), cudaMemcpyHostToDevice, stream), "mesh upload");
+        if (data->skin_data && data->num_skin_data == 3u * m.n) {  // joint data per vertex, 3 vertices per RTTriangle (objects_3d/mod.rs:331-383)
+            BK_CUDA(cudaMalloc(&m.d_skin, (size_t)m.n * 3 * sizeof(RfwJointData)), "skin alloc");
+            BK_CUDA(cudaMemcpyAsync(m.d_skin, data->skin_data, (size_t)m.n * 3 * sizeof(RfwJointData), cudaMemcpyHostToDevice, stream), "skin upload");
+        }
         BK_CUDA(cudaStreamSynchronize(stream), "mesh upload");  // the slice is only borrowed for this call
     }
     scene_dirty = true;
@@ -158,6 +166,7 @@ int Backend::unload_3d_meshes(const uint32_t* ids, uint32_t num) {
         MeshRec& m = meshes[id];
         if (m.d_tris) cudaFree(m.d_tris);
         if (m.d_ttris) cudaFree(m.d_ttris);
+        if (m.d_skin) cudaFree(m.d_skin);
         m.bvh.release();
         m = MeshRec();
         if (id < inst_lists.size()) inst_lists[id] = InstanceList();  // mesh ids are slots and get reused (collections.rs:87-107)
@@ -174,6 +183,30 @@ int Backend::set_3d_instances(uint32_t mesh, const RfwInstancesData3D* data) {
     InstanceList& l = inst_lists[mesh];
     l.present = true;
     l.matrices.assign(data->matrices, data->matrices + (size_t)data->num_instances * 16);
+    if (data->skin_ids) l.skin_ids.assign(data->skin_ids, data->skin_ids + data->num_instances);
+    else l.skin_ids.clear();
+    scene_dirty = true;
+    synchronized = false;
+    return RFWB200_OK;
+}
+
+int Backend::set_skins(const RfwSkinData* sk, uint32_t num, const uint32_t* changed) {
+    DeviceScope device_scope(cfg.device);
+    BK_CUDA(device_scope.status, "cudaSetDevice");
+    if (num && !sk) return fail(RFWB200_ERR_INVALID, "set_skins: null slice");
+    BK_CUDA(cudaStreamSynchronize(stream), "sync");
+    for (size_t i = num; i < skins.size(); i++) skins[i].joints.release();
+    skins.resize(num);
+    for (uint32_t i = 0; i < num; i++) {
+        if (changed && !changed[i] && skins[i].num_joints == sk[i].num_joints) continue;
+        skins[i].num_joints = sk[i].joint_matrices ? sk[i].num_joints : 0;
+        if (skins[i].num_joints) {
+            BK_CUDA(skins[i].joints.reserve((size_t)skins[i].num_joints * 16), "skin alloc");
+            BK_CUDA(cudaMemcpyAsync(skins[i].joints.ptr, sk[i].joint_matrices, (size_t)skins[i].num_joints * 64, cudaMemcpyHostToDevice, stream), "skin upload");
+        }
+    }
+    BK_CUDA(cudaStreamSynchronize(stream), "skin upload");  // borrowed slices
+    skins_dirty = true;
     scene_dirty = true;
     synchronized = false;
     return RFWB200_OK;
@@ -370,6 +403,94 @@ __global__ void __launch_bounds__(128) k_instance_compact(uint32_t n_slots, cons
     if (gid == n_slots - 1) out[0] = rank[gid] + live_flag[gid];
 }
 
+// SkinnedTriangles3D::apply (crates/rfw-backend/src/structs.rs:820-877) on the device: one thread per triangle, per
+// vertex a weighted sum of four joint matrices; positions by the matrix, vertex normals / tangents by its inverse
+// transpose (not renormalised, every tangent's w from tangent2 as in the reference), geometric normal recomputed.
+// Joint data of triangle i = entries 3i..3i+2 (the reference's i/3, i+1, i+2 is a defect, see oracle.cpp apply_skin).
+__global__ void __launch_bounds__(128) k_skin_triangles(const RfwRTTriangle* __restrict__ src, const RfwJointData* __restrict__ skin, const float* __restrict__ joints,
+                                                        uint32_t num_joints, uint32_t n, RfwRTTriangle* __restrict__ dst) {
+    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n) return;
+    RfwRTTriangle t = src[i];
+    float* verts[3] = {t.vertex0, t.vertex1, t.vertex2};
+    float* nrms[3] = {t.n0, t.n1, t.n2};
+    float* tans[3] = {t.tangent0, t.tangent1, t.tangent2};
+    const float tw = t.tangent2[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const RfwJointData jd = skin[3 * (size_t)i + k];
+        if (jd.joint[0] >= num_joints || jd.joint[1] >= num_joints || jd.joint[2] >= num_joints || jd.joint[3] >= num_joints) continue;
+        float M[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            float acc = __fmul_rn(jd.weight[0], joints[16 * jd.joint[0] + e]);
+            acc = __fadd_rn(acc, __fmul_rn(jd.weight[1], joints[16 * jd.joint[1] + e]));
+            acc = __fadd_rn(acc, __fmul_rn(jd.weight[2], joints[16 * jd.joint[2] + e]));
+            acc = __fadd_rn(acc, __fmul_rn(jd.weight[3], joints[16 * jd.joint[3] + e]));
+            M[e] = acc;
+        }
+        float4 r0, r1, r2, n0, n1, n2;
+        if (!invert_affine(M, r0, r1, r2, n0, n1, n2)) continue;  // degenerate blend: the vertex stays in bind pose
+        const float px = verts[k][0], py = verts[k][1], pz = verts[k][2];
+        verts[k][0] = M[0] * px + M[4] * py + M[8] * pz + M[12];
+        verts[k][1] = M[1] * px + M[5] * py + M[9] * pz + M[13];
+        verts[k][2] = M[2] * px + M[6] * py + M[10] * pz + M[14];
+        const float nx = nrms[k][0], ny = nrms[k][1], nz = nrms[k][2];
+        nrms[k][0] = n0.x * nx + n0.y * ny + n0.z * nz; nrms[k][1] = n1.x * nx + n1.y * ny + n1.z * nz; nrms[k][2] = n2.x * nx + n2.y * ny + n2.z * nz;
+        const float tx = tans[k][0], ty = tans[k][1], tz = tans[k][2];
+        tans[k][0] = n0.x * tx + n0.y * ty + n0.z * tz; tans[k][1] = n1.x * tx + n1.y * ty + n1.z * tz; tans[k][2] = n2.x * tx + n2.y * ty + n2.z * tz;
+        tans[k][3] = tw;
+    }
+    const float ax = t.vertex1[0] - t.vertex0[0], ay = t.vertex1[1] - t.vertex0[1], az = t.vertex1[2] - t.vertex0[2];
+    const float bx = t.vertex2[0] - t.vertex0[0], by = t.vertex2[1] - t.vertex0[1], bz = t.vertex2[2] - t.vertex0[2];
+    const float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+    const float il = 1.0f / sqrtf(cx * cx + cy * cy + cz * cz);
+    t.normal[0] = cx * il; t.normal[1] = cy * il; t.normal[2] = cz * il;  // RTTriangle::normal, structs.rs:970-974
+    dst[i] = t;
+}
+
+// a skinned instance traces and shades its own geometry: patch the records k_instance_prepare derived from the mesh
+struct SkinOverride {
+    uint32_t gid;
+    const float4* nodes;
+    const float4* ttris;
+    const RfwRTTriangle* tris;
+    float lo[3], hi[3];
+};
+__global__ void k_instance_override(const SkinOverride* __restrict__ ov, uint32_t n, const float* __restrict__ matrices, InstanceRec* __restrict__ recs,
+                                    InstanceShading* __restrict__ shading, float4* __restrict__ box_lo, float4* __restrict__ box_hi, const uint32_t* __restrict__ live_flag) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const SkinOverride o = ov[k];
+    if (!live_flag[o.gid]) return;
+    recs[o.gid].nodes = o.nodes; recs[o.gid].tris = o.ttris;
+    shading[o.gid].tris = o.tris;
+    const float* M = matrices + (size_t)o.gid * 16;
+    float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+    for (int c = 0; c < 8; c++) {
+        const float px = (c & 1) ? o.hi[0] : o.lo[0], py = (c & 2) ? o.hi[1] : o.lo[1], pz = (c & 4) ? o.hi[2] : o.lo[2];
+        const float w0 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[0], px), __fmul_rn(M[4], py)), __fmul_rn(M[8], pz)), M[12]);
+        const float w1 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[1], px), __fmul_rn(M[5], py)), __fmul_rn(M[9], pz)), M[13]);
+        const float w2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[2], px), __fmul_rn(M[6], py)), __fmul_rn(M[10], pz)), M[14]);
+        lo[0] = fminf(lo[0], w0); hi[0] = fmaxf(hi[0], w0);
+        lo[1] = fminf(lo[1], w1); hi[1] = fmaxf(hi[1], w1);
+        lo[2] = fminf(lo[2], w2); hi[2] = fmaxf(hi[2], w2);
+    }
+    for (int a = 0; a < 3; a++) {
+        const float pad = 4.0f * 1.1920929e-7f * fmaxf(fabsf(lo[a]), fabsf(hi[a]));
+        lo[a] -= pad; hi[a] += pad;
+    }
+    box_lo[o.gid] = make_float4(lo[0], lo[1], lo[2], 0.0f);
+    box_hi[o.gid] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+}
+
+void Backend::release_skinned(SkinnedInstance& s) {
+    if (s.d_tris) cudaFree(s.d_tris);
+    if (s.d_ttris) cudaFree(s.d_ttris);
+    s.bvh.release();
+    s.d_tris = nullptr; s.d_ttris = nullptr;
+}
+
 int Backend::synchronize() {
     DeviceScope device_scope(cfg.device);
     BK_CUDA(device_scope.status, "cudaSetDevice");
@@ -378,8 +499,10 @@ int Backend::synchronize() {
         // ---- BLAS for dirty meshes ------------------------------------------------------------------
         BK_CUDA(cudaEventRecord(ev0, stream), "event");
         const BuildParams blas_params{1.0f, sah_c_prim, sah_pmax, sah_treelet};
+        std::set<uint32_t> rebuilt_meshes;
         for (MeshRec& m : meshes) {
             if (!m.present || !m.dirty) continue;
+            rebuilt_meshes.insert((uint32_t)(&m - meshes.data()));
             if (m.d_ttris) { cudaFree(m.d_ttris); m.d_ttris = nullptr; }
             m.bvh.release();
             if (m.n) {
@@ -398,6 +521,48 @@ int Backend::synchronize() {
         BK_CUDA(cudaEventRecord(ev1, stream), "event");
         BK_CUDA(cudaEventSynchronize(ev1), "BLAS build");
         cudaEventElapsedTime(&blas_ms, ev0, ev1);
+
+        // ---- skinned instances: deform + BLAS per instance (rebuilt when its skin, its mesh or the skin id changed) ----
+        for (SkinnedInstance& si : skinned) si.fresh = false;
+        std::vector<bool> mesh_was_dirty(meshes.size(), false);
+        for (size_t i = 0; i < meshes.size(); i++) mesh_was_dirty[i] = rebuilt_meshes.count((uint32_t)i) != 0;
+        for (size_t mesh_id = 0; mesh_id < inst_lists.size(); mesh_id++) {
+            const InstanceList& l = inst_lists[mesh_id];
+            if (!l.present || l.skin_ids.empty() || mesh_id >= meshes.size()) continue;
+            MeshRec& m = meshes[mesh_id];
+            if (!m.present || !m.n || !m.d_skin) continue;
+            for (size_t i = 0; i < l.skin_ids.size(); i++) {
+                const int32_t sid = l.skin_ids[i];
+                if (sid < 0 || (size_t)sid >= skins.size() || skins[sid].num_joints == 0) continue;
+                SkinnedInstance* si = nullptr;
+                for (SkinnedInstance& c : skinned) if (c.mesh == mesh_id && c.index == i) si = &c;
+                bool rebuild = skins_dirty || mesh_was_dirty[mesh_id];
+                if (!si) { skinned.emplace_back(); si = &skinned.back(); si->mesh = (uint32_t)mesh_id; si->index = (uint32_t)i; rebuild = true; }
+                if (si->skin != sid) { si->skin = sid; rebuild = true; }
+                si->fresh = true;
+                if (!rebuild && si->d_tris) continue;
+                release_skinned(*si);
+                BK_CUDA(cudaMalloc(&si->d_tris, (size_t)m.n * sizeof(RfwRTTriangle)), "skinned triangles");
+                k_skin_triangles<<<(m.n + 127) / 128, 128, 0, stream>>>(m.d_tris, m.d_skin, skins[sid].joints.ptr, skins[sid].num_joints, m.n, si->d_tris);
+                launch_count++;
+                float4 *lo = nullptr, *hi = nullptr;
+                BK_CUDA(cudaMallocAsync(&lo, (size_t)m.n * sizeof(float4), stream), "box alloc");
+                BK_CUDA(cudaMallocAsync(&hi, (size_t)m.n * sizeof(float4), stream), "box alloc");
+                cudaError_t e = triangle_boxes(bctx, si->d_tris, (int)m.n, lo, hi);
+                if (e == cudaSuccess) e = build_wide_bvh(bctx, lo, hi, (int)m.n, blas_params, si->bvh);
+                cudaFreeAsync(lo, stream); cudaFreeAsync(hi, stream);
+                if (e != cudaSuccess) return cuda_fail(e, "skinned BLAS build");
+                BK_CUDA(cudaMallocAsync(&si->d_ttris, (size_t)m.n * 3 * sizeof(float4), stream), "triangle alloc");
+                BK_CUDA(gather_traversal_triangles(bctx, si->d_tris, si->bvh.leaf_prims, (int)m.n, si->d_ttris), "gather triangles");
+            }
+        }
+        for (size_t k = 0; k < skinned.size();) {  // instances that lost their skin (or their mesh)
+            if (skinned[k].fresh) { k++; continue; }
+            BK_CUDA(cudaStreamSynchronize(stream), "sync");
+            release_skinned(skinned[k]);
+            skinned.erase(skinned.begin() + (long)k);
+        }
+        skins_dirty = false;
 
         // ---- instances + TLAS (rebuilt on every synchronize, as the reference does: lib.rs:1576-1581) ----
         BK_CUDA(cudaEventRecord(ev0, stream), "event");
@@ -446,6 +611,26 @@ int Backend::synchronize() {
             }
             const unsigned blocks = (slots + 127) / 128;
             k_instance_prepare<<<blocks, 128, 0, stream>>>(d_mesh_table.ptr, (uint32_t)table.size(), d_matrices.ptr, slots, tmp_recs, d_inst_shading.ptr, tmp_lo, tmp_hi, flags, ident);
+            if (!skinned.empty()) {
+                std::vector<SkinOverride> ov;
+                for (const SkinnedInstance& si : skinned) {
+                    if (!si.d_tris || si.mesh >= table.size()) continue;
+                    SkinOverride o;
+                    o.gid = table[si.mesh].first_slot + si.index;
+                    o.nodes = si.bvh.nodes; o.ttris = si.d_ttris; o.tris = si.d_tris;
+                    for (int k = 0; k < 3; k++) { o.lo[k] = si.bvh.lo[k]; o.hi[k] = si.bvh.hi[k]; }
+                    ov.push_back(o);
+                }
+                if (!ov.empty()) {
+                    SkinOverride* d_ov = nullptr;
+                    BK_CUDA(cudaMallocAsync(&d_ov, ov.size() * sizeof(SkinOverride), stream), "skin overrides");
+                    BK_CUDA(cudaMemcpyAsync(d_ov, ov.data(), ov.size() * sizeof(SkinOverride), cudaMemcpyHostToDevice, stream), "skin overrides");
+                    k_instance_override<<<(unsigned)((ov.size() + 63) / 64), 64, 0, stream>>>(d_ov, (uint32_t)ov.size(), d_matrices.ptr, tmp_recs, d_inst_shading.ptr, tmp_lo, tmp_hi, flags);
+                    BK_CUDA(cudaStreamSynchronize(stream), "skin overrides");  // `ov` is a local
+                    cudaFreeAsync(d_ov, stream);
+                    launch_count++;
+                }
+            }
             BK_CUDA(cudaMemcpyAsync(rank, flags, (size_t)slots * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream), "instance scan");
             exclusive_scan_u32(rank, (int)slots, stream);
             k_instance_compact<<<blocks, 128, 0, stream>>>(slots, flags, rank, ident, tmp_recs, tmp_lo, tmp_hi, d_instances.ptr, lo, hi, out);

@@ -24,6 +24,7 @@ struct MeshRec {
     uint32_t n = 0;
     uint32_t flags = 0;
     RfwRTTriangle* d_tris = nullptr;  // full 176-byte records (shading reads them)
+    RfwJointData* d_skin = nullptr;   // per-vertex joint data (3 per triangle) when the mesh is skinned, else null
     float4* d_ttris = nullptr;        // traversal triangles in leaf order
     DeviceBvh bvh;
 };
@@ -31,7 +32,19 @@ struct MeshRec {
 struct InstanceList {
     bool present = false;
     std::vector<float> matrices;  // 16 per instance, column-major
+    std::vector<int32_t> skin_ids; // per instance, -1 = none (may be empty)
 };
+
+// One skinned instance: its own deformed triangles and BLAS
+struct SkinnedInstance {
+    uint32_t mesh = 0, index = 0;     // instance = (mesh id, index in the mesh's list)
+    int32_t skin = -1;
+    bool fresh = false;               // rebuilt (or confirmed) during the current synchronize()
+    RfwRTTriangle* d_tris = nullptr;
+    float4* d_ttris = nullptr;
+    DeviceBvh bvh;
+};
+
 
 template <typename T>
 struct DeviceArray {
@@ -48,6 +61,11 @@ struct DeviceArray {
     void release() { if (ptr) cudaFree(ptr); ptr = nullptr; capacity = 0; }
 };
 
+struct SkinRec {
+    DeviceArray<float> joints;        // 16 floats per joint, column-major
+    uint32_t num_joints = 0;
+};
+
 class Backend {
 public:
     explicit Backend(const RfwB200Config& cfg);
@@ -59,6 +77,7 @@ public:
     int set_3d_instances(uint32_t mesh, const RfwInstancesData3D* data);
     int set_materials(const RfwDeviceMaterial* m, uint32_t num);
     int set_textures(const RfwTextureData* t, uint32_t num, const uint32_t* changed);
+    int set_skins(const RfwSkinData* skins, uint32_t num, const uint32_t* changed);
     int set_skybox(const RfwTextureData* t);
     int set_area_lights(const RfwAreaLight* l, uint32_t num);
     int set_point_lights(const RfwPointLight* l, uint32_t num);
@@ -112,6 +131,10 @@ private:
 
     std::vector<MeshRec> meshes;
     std::vector<InstanceList> inst_lists;
+    std::vector<SkinRec> skins;
+    std::vector<SkinnedInstance> skinned;
+    bool skins_dirty = false;
+    void release_skinned(SkinnedInstance& s);
     std::vector<RfwDeviceMaterial> materials;
     std::vector<RfwAreaLight> area_lights;
     std::vector<RfwPointLight> point_lights;

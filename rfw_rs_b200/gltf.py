@@ -2,8 +2,9 @@
 
 Plays the role of the reference's loader glue (crates/rfw-scene/src/loaders/gltf.rs:27-100, which delegates the
 parsing to the third-party `l3d` crate) for plain glTF: external .bin buffers, float32 POSITION / NORMAL, u16 / u32
-indices, triangle lists, node matrices or TRS.  Skins and animation are ignored (bind pose), as the backend only ever
-sees final matrices.  Two ways to hand the asset to the backend:
+indices, triangle lists, node matrices or TRS.  Per-vertex JOINTS_0 / WEIGHTS_0 and the skins' inverse bind matrices
+are read too (the payload of MeshData3D::skin_data / SkinData, SURVEY §8 f2); animation channels are not evaluated —
+the backend only ever sees final joint matrices, which the tests synthesise (pose_joints).  Two ways to hand the asset to the backend:
   * flatten(asset)  -> one mesh, node transforms baked in, identity instance                       (variant C1a)
   * per_mesh(asset) -> one mesh per glTF mesh, one instance per mesh-bearing node with its matrix  (variant C1b:
                        what rfw really does: loaders/gltf.rs:73-79, graph/mod.rs:435-445)
@@ -24,6 +25,8 @@ class Asset:
     def __init__(self):
         self.meshes = []      # list of dict(positions (n,3) f32, normals (n,3) f32 or None, indices (m,3) u32)
         self.mesh_nodes = []  # list of (mesh index, 4x4 float64 world matrix, row-indexed)
+        self.skins = []       # list of (n_joints, 4, 4) float64 inverse bind matrices (row-indexed)
+        self.mesh_skin = {}   # mesh index -> skin index (from the node that instantiates it)
 
 
 def _accessor(g, buffers, idx):
@@ -66,7 +69,7 @@ def load(path):
     buffers = [open(os.path.join(base, b["uri"]), "rb").read() for b in g["buffers"]]
     asset = Asset()
     for m in g["meshes"]:
-        pos, nrm, idx = [], [], []
+        pos, nrm, idx, jnt, wgt = [], [], [], [], []
         voff = 0
         for pr in m["primitives"]:
             if pr.get("mode", 4) != 4:
@@ -78,8 +81,18 @@ def load(path):
             else:
                 i = np.arange(len(p), dtype=np.uint32).reshape(-1, 3)
             pos.append(p); nrm.append(n); idx.append(i + voff)
+            if "JOINTS_0" in pr["attributes"] and "WEIGHTS_0" in pr["attributes"]:
+                jnt.append(_accessor(g, buffers, pr["attributes"]["JOINTS_0"]).astype(np.uint32))
+                w = _accessor(g, buffers, pr["attributes"]["WEIGHTS_0"])
+                wgt.append(w.astype(np.float32) / (1.0 if w.dtype == np.float32 else float(np.iinfo(w.dtype).max)))
             voff += len(p)
-        asset.meshes.append({"positions": np.concatenate(pos), "normals": np.concatenate(nrm), "indices": np.concatenate(idx)})
+        mesh = {"positions": np.concatenate(pos), "normals": np.concatenate(nrm), "indices": np.concatenate(idx)}
+        if jnt and sum(len(j) for j in jnt) == len(mesh["positions"]):
+            mesh["joints"], mesh["weights"] = np.concatenate(jnt), np.concatenate(wgt)
+        asset.meshes.append(mesh)
+    for sk in g.get("skins", []):
+        ibm = _accessor(g, buffers, sk["inverseBindMatrices"]).astype(np.float64).reshape(-1, 4, 4).transpose(0, 2, 1) if "inverseBindMatrices" in sk else np.tile(np.eye(4), (len(sk["joints"]), 1, 1))
+        asset.skins.append(ibm)
     scene = g["scenes"][g.get("scene", 0)]
 
     def walk(ni, parent):
@@ -87,6 +100,8 @@ def load(path):
         M = parent @ _node_matrix(n)
         if "mesh" in n:
             asset.mesh_nodes.append((n["mesh"], M))
+            if "skin" in n:
+                asset.mesh_skin[n["mesh"]] = n["skin"]
         for c in n.get("children", []):
             walk(c, M)
 
@@ -104,7 +119,13 @@ def save_npz(asset, path):
     ioffs = np.cumsum([0] + [len(m["indices"]) for m in asset.meshes]).astype(np.int64)
     nodes_mesh = np.array([mi for mi, _ in asset.mesh_nodes], np.int32)
     nodes_mat = np.array([M for _, M in asset.mesh_nodes], np.float64)
-    np.savez_compressed(path, pos=pos, nrm=nrm, idx=idx if idx.max() > 65535 else idx.astype(np.uint16), voffs=voffs, ioffs=ioffs, nodes_mesh=nodes_mesh, nodes_mat=nodes_mat)
+    extra = {}
+    if asset.skins and all("joints" in m for m in asset.meshes):
+        extra["joints"] = np.concatenate([m["joints"] for m in asset.meshes]).astype(np.uint8 if max(len(s) for s in asset.skins) < 256 else np.uint16)
+        extra["weights"] = np.concatenate([m["weights"] for m in asset.meshes]).astype(np.float16)
+        extra["skin0_ibm"] = asset.skins[0].astype(np.float32)
+        extra["mesh_skin"] = np.array([asset.mesh_skin.get(k, -1) for k in range(len(asset.meshes))], np.int32)
+    np.savez_compressed(path, pos=pos, nrm=nrm, idx=idx if idx.max() > 65535 else idx.astype(np.uint16), voffs=voffs, ioffs=ioffs, nodes_mesh=nodes_mesh, nodes_mat=nodes_mat, **extra)
 
 
 def load_npz(path):
@@ -113,9 +134,47 @@ def load_npz(path):
     for k in range(len(z["voffs"]) - 1):
         v0, v1 = z["voffs"][k], z["voffs"][k + 1]
         i0, i1 = z["ioffs"][k], z["ioffs"][k + 1]
-        asset.meshes.append({"positions": z["pos"][v0:v1].astype(np.float32), "normals": z["nrm"][v0:v1].astype(np.float32), "indices": z["idx"][i0:i1].astype(np.uint32)})
+        mesh = {"positions": z["pos"][v0:v1].astype(np.float32), "normals": z["nrm"][v0:v1].astype(np.float32), "indices": z["idx"][i0:i1].astype(np.uint32)}
+        if "joints" in z.files:
+            w = z["weights"][v0:v1].astype(np.float32)
+            mesh["joints"], mesh["weights"] = z["joints"][v0:v1].astype(np.uint32), w / np.maximum(w.sum(axis=1, keepdims=True), 1e-8)  # f16 storage: renormalise
+        asset.meshes.append(mesh)
     asset.mesh_nodes = [(int(mi), M) for mi, M in zip(z["nodes_mesh"], z["nodes_mat"])]
+    if "skin0_ibm" in z.files:
+        asset.skins = [z["skin0_ibm"].astype(np.float64)]
+        asset.mesh_skin = {k: int(v) for k, v in enumerate(z["mesh_skin"]) if v >= 0}
     return asset
+
+
+def joint_data(mesh):
+    """MeshData3D::skin_data for the triangles _tris() builds: one JointData per triangle vertex, 3 per triangle."""
+    from . import wire
+    i = mesh["indices"].astype(np.int64).reshape(-1)
+    jd = np.zeros(len(i), dtype=wire.JOINT_DATA)
+    jd["joint"], jd["weight"] = mesh["joints"][i], mesh["weights"][i]
+    return jd
+
+
+def pose_joints(ibm, angle=0.35, seed=3):
+    """Synthetic pose: every joint rotates about its own bind position by a seeded axis/angle, composed down a chain of
+    decreasing strength — final joint matrices (world-from-bind), column-major float32 (n, 16).  Stands in for the
+    animation evaluation of the scene graph (crates/rfw-scene/src/graph), which is outside the backend."""
+    n = len(ibm)
+    out = np.zeros((n, 16), np.float32)
+    r = scenes.u01(seed, np.arange(n * 4)).reshape(n, 4).astype(np.float64)
+    for j in range(n):
+        bind = np.linalg.inv(ibm[j])           # joint's bind-pose world matrix
+        c = bind[:3, 3]
+        axis = r[j, :3] - 0.5
+        axis /= max(np.linalg.norm(axis), 1e-9)
+        a = angle * (2.0 * r[j, 3] - 1.0)
+        K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+        R = np.eye(3) + np.sin(a) * K + (1 - np.cos(a)) * (K @ K)
+        M = np.eye(4)
+        M[:3, :3] = R
+        M[:3, 3] = c - R @ c                    # rotate about the joint's bind position
+        out[j] = M.T.reshape(-1)                # column-major
+    return out
 
 
 def _tris(mesh, M=None, mat_id=0):
@@ -167,3 +226,26 @@ def c1_camera(sc, width=1280, height=720):
     centre, ext = (lo + hi) * 0.5, hi - lo
     pos = centre + np.array([0.0, 0.15 * ext[1], -1.2 * np.linalg.norm(ext)])
     return scenes.camera_view(pos, centre - pos, width, height, fov_deg=40.0)
+
+
+def skinned(asset, pose=None, copies=1, spacing=1.5):
+    """Skinned variant: per-mesh BLAS, `copies` instances of every skinned mesh side by side, each with
+    skin id 0 except the last one of several (bind pose, skin id -1); joint matrices from pose_joints() unless given."""
+    sc = per_mesh(asset)
+    for mi, mesh in enumerate(asset.meshes):
+        if "joints" not in mesh or mi not in sc.meshes:
+            continue
+        jd = joint_data(mesh)
+        assert len(jd) == 3 * len(sc.meshes[mi]), "degenerate triangles were dropped: joint data no longer lines up"
+        sc.skin_data[mi] = jd
+        base = np.asarray(sc.instances[mi], np.float32).reshape(-1, 16)[0].reshape(4, 4).copy()
+        mats, ids = [], []
+        for c in range(copies):
+            M = base.copy()
+            M[3, 0] += spacing * c  # column-major: translation lives in the last row of the reshaped array
+            mats.append(M.reshape(-1))
+            ids.append(0 if (copies == 1 or c < copies - 1) else -1)
+        sc.instances[mi] = np.array(mats, np.float32)
+        sc.instance_skins[mi] = np.array(ids, np.int32)
+    sc.skins = [pose_joints(asset.skins[0]) if pose is None else np.asarray(pose, np.float32)]
+    return sc

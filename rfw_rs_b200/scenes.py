@@ -345,12 +345,23 @@ class SceneDesc:
         self.directional_lights = np.zeros(0, dtype=wire.DIRECTIONAL_LIGHT)
         self.textures = []   # list of Texture
         self.skybox = None   # Texture or None
+        self.skin_data = {}        # mesh id -> JOINT_DATA[3 * triangles] (MeshData3D::skin_data)
+        self.instance_skins = {}   # mesh id -> int32 skin id per instance (-1 = none)
+        self.skins = []            # list of (n_joints, 16) column-major joint matrices
 
     def apply(self, backend):
         for mid, tris in self.meshes.items():
-            backend.set_3d_mesh(mid, tris)
+            if mid in self.skin_data:
+                backend.set_3d_mesh(mid, tris, skin_data=self.skin_data[mid])
+            else:
+                backend.set_3d_mesh(mid, tris)
         for mid, mats in self.instances.items():
-            backend.set_3d_instances(mid, mats)
+            if mid in self.instance_skins:
+                backend.set_3d_instances(mid, mats, skin_ids=self.instance_skins[mid])
+            else:
+                backend.set_3d_instances(mid, mats)
+        if self.skins:
+            backend.set_skins(self.skins)
         backend.set_materials(self.materials)
         if self.textures or self.skybox is not None:
             backend.set_textures(self.textures)

@@ -129,3 +129,8 @@ class CRenderStats(C.Structure):
 
 def stats_to_dict(s):
     return {name: getattr(s, name) for name, _ in s._fields_}
+
+
+class CSkinData(C.Structure):
+    """RfwSkinData (include/rfwb200.h): FFI repack of SkinData<'a>, crates/rfw-backend/src/structs.rs:6-11."""
+    _fields_ = [("inverse_bind_matrices", C.c_void_p), ("joint_matrices", C.c_void_p), ("num_joints", C.c_uint32)]
