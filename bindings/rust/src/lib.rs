@@ -14,6 +14,10 @@ struct RfwMeshData3D {
 #[repr(C)]
 struct RfwInstancesData3D { matrices: *const f32, skin_ids: *const i32, flags: *const u32, num_instances: u32, local_aabb: Aabb }
 #[repr(C)]
+struct RfwTextureData { width: u32, height: u32, mip_levels: u32, bytes: *const u8, num_bytes: u64, format: u32 }
+#[repr(C)]
+struct RfwSkinData { inverse_bind_matrices: *const f32, joint_matrices: *const f32, num_joints: u32 }
+#[repr(C)]
 #[derive(Default)]
 struct RfwB200Config { device: i32, width: u32, height: u32, max_depth: u32, clamp_value: f32, tile_size: u32, rank: u32, world: u32, sky: [f32; 3], reserved: [u32; 8] }
 
@@ -24,6 +28,9 @@ extern "C" {
     fn rfwb200_unload_3d_meshes(h: *mut c_void, ids: *const u32, n: u32) -> c_int;
     fn rfwb200_set_3d_instances(h: *mut c_void, mesh: u32, data: *const RfwInstancesData3D) -> c_int;
     fn rfwb200_set_materials(h: *mut c_void, m: *const DeviceMaterial, n: u32, changed: *const u32) -> c_int;
+    fn rfwb200_set_textures(h: *mut c_void, t: *const RfwTextureData, n: u32, changed: *const u32) -> c_int;
+    fn rfwb200_set_skybox(h: *mut c_void, t: *const RfwTextureData) -> c_int;
+    fn rfwb200_set_skins(h: *mut c_void, s: *const RfwSkinData, n: u32, changed: *const u32) -> c_int;
     fn rfwb200_set_point_lights(h: *mut c_void, l: *const PointLight, n: u32, changed: *const u32) -> c_int;
     fn rfwb200_set_spot_lights(h: *mut c_void, l: *const SpotLight, n: u32, changed: *const u32) -> c_int;
     fn rfwb200_set_area_lights(h: *mut c_void, l: *const AreaLight, n: u32, changed: *const u32) -> c_int;
