@@ -88,7 +88,9 @@ RFW_HD void ray_setup_tri(RayCtx& r) {
 // RFW_BYTE2F_MAGIC: one PRMT builds the bit pattern of 2^23 + byte (0x4B0000bb), one FADD removes the 2^23 — keeps the
 // conversion off the (narrower) conversion pipe.
 RFW_HD float byte_to_float(uint32_t w, int j) {
-#if defined(RFW_BYTE2F_MAGIC)
+#if defined(RFW_BYTE2F_EXP15)
+    return u2f(byte_perm(w, 0x3F800000u, 0x7604u | ((uint32_t)j << 4)));  // 1 + q * 2^-15
+#elif defined(RFW_BYTE2F_MAGIC)
     return u2f(byte_perm(w, 0x4B000000u, 0x7650u | (uint32_t)j)) - 8388608.0f;
 #else
     return (float)((w >> (8 * j)) & 0xFFu);
@@ -102,8 +104,16 @@ RFW_HD uint32_t intersect_wide_node(const float4 n0, const float4 n1, const floa
                                     float tmax) {
     const uint32_t e_imask = f2u(n0.w);
     const float sx = u2f((e_imask & 0xFFu) << 23), sy = u2f(((e_imask >> 8) & 0xFFu) << 23), sz = u2f(((e_imask >> 16) & 0xFFu) << 23);
+#if defined(RFW_BYTE2F_EXP15)
+    // experiment: no integer->float conversion at all.  One PRMT drops the byte into mantissa bits 8..15 of 1.0f, giving
+    // 1 + q * 2^-15; the FMA runs on A = 2^15 * (s * idir) and C = (p - o) * idir - A, so f * A + C = q * s * idir + (p - o) * idir.
+    // (C carries a rounding error of up to 2^-9 quantisation steps: a shipped version needs the near planes biased by it.)
+    const float aix = sx * r.idir.x * 32768.0f, aiy = sy * r.idir.y * 32768.0f, aiz = sz * r.idir.z * 32768.0f;
+    const float aox = (n0.x - r.o.x) * r.idir.x - aix, aoy = (n0.y - r.o.y) * r.idir.y - aiy, aoz = (n0.z - r.o.z) * r.idir.z - aiz;
+#else
     const float aix = sx * r.idir.x, aiy = sy * r.idir.y, aiz = sz * r.idir.z;
     const float aox = (n0.x - r.o.x) * r.idir.x, aoy = (n0.y - r.o.y) * r.idir.y, aoz = (n0.z - r.o.z) * r.idir.z;
+#endif
     uint32_t hitmask = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
