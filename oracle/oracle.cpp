@@ -1257,6 +1257,54 @@ double orc_render(void* s, const RfwCameraView3D* cam, uint32_t w, uint32_t h, u
     return dt;
 }
 
+// RenderMode debug views (crates/rfw-backend/src/lib.rs:10-18; G-buffer semantics of backends/wgpu/shaders/deferred.frag:20-56
+// evaluated at the primary hit of the pixel-centre pinhole ray): mode 1 world shading normal (incl. normal map), 2 albedo
+// (material colour x diffuse map | material id), 3 world position | t.  out: w*h*4 floats; misses: 0 (albedo: id -1).
+void orc_debug_view(void* s, const RfwCameraView3D* camp, uint32_t w, uint32_t h, uint32_t mode, float det_eps, float* out) {
+    const Scene& sc = *(Scene*)s;
+    const RfwCameraView3D& cam = *camp;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t p = 0; p < (int64_t)w * h; p++) {
+        const int x = (int)(p % w), y = (int)(p / w);
+        const float u0 = ((float)x + 0.5f) * (1.0f / (float)w), v0 = ((float)y + 0.5f) * (1.0f / (float)h);
+        const V3 O(cam.pos);
+        const V3 D = normalize(V3(cam.p1) + V3(cam.right) * u0 + V3(cam.up) * v0 - O);
+        HitRec hit;
+        sc.trace<false>(O, D, 1e-4f, 1e26f, det_eps, MODE_MBVH, hit);
+        float* o = out + 4 * p;
+        o[0] = o[1] = o[2] = 0.0f; o[3] = mode == 2u ? -1.0f : 0.0f;
+        if (hit.inst < 0) continue;
+        const Instance* in = sc.find_instance(hit.inst);
+        const RfwRTTriangle& tri = in->geom->tris[hit.prim];
+        const RfwDeviceMaterial& mat = sc.materials[tri.mat_id];
+        const uint32_t bu = (uint32_t)(65535.0f * hit.u), bv = (uint32_t)(65535.0f * hit.v);
+        const float u = (float)(bu & 65535u) * (1.0f / 65535.0f), v = (float)(bv & 65535u) * (1.0f / 65535.0f), wgt = 1.0f - u - v;
+        V3 N = V3(tri.n0) * wgt + V3(tri.n1) * u + V3(tri.n2) * v;
+        V3 T3 = V3(tri.tangent0) * wgt + V3(tri.tangent1) * u + V3(tri.tangent2) * v;
+        const float Tw = wgt * tri.tangent0[3] + u * tri.tangent1[3] + v * tri.tangent2[3];
+        N = normalize(xform_vec(in->normal, N));
+        T3 = normalize(xform_vec(in->normal, T3));
+        const V3 B = cross(N, T3) * Tw;
+        V3 color(mat.color);
+        if (mat.flags & 0x3Fu) {
+            const float lambda = std::sqrt(tri.lod) + std::log2(cam.spread_angle * (1.0f / std::fabs(dot(D, N))));
+            const float tu = wgt * tri.u0 + u * tri.u1 + v * tri.u2, tv = wgt * tri.v0 + u * tri.v1 + v * tri.v2;
+            float px[4];
+            if ((mat.flags & 1u) && mat.diffuse_map >= 0 && (size_t)mat.diffuse_map < sc.textures.size()) {
+                sc.textures[mat.diffuse_map].fetch_trilinear(lambda, tu, tv, px);
+                color = color * V3(px[0], px[1], px[2]);
+            }
+            if ((mat.flags & 2u) && mat.normal_map >= 0 && (size_t)mat.normal_map < sc.textures.size()) {
+                sc.textures[mat.normal_map].fetch(tu, tv, (int)lambda, px);
+                N = normalize(T3 * ((px[0] - 0.5f) * 2.0f) + B * ((px[1] - 0.5f) * 2.0f) + N * ((px[2] - 0.5f) * 2.0f));
+            }
+        }
+        if (mode == 1u) { o[0] = N.x; o[1] = N.y; o[2] = N.z; o[3] = 0.0f; }
+        else if (mode == 2u) { o[0] = color.x; o[1] = color.y; o[2] = color.z; o[3] = (float)tri.mat_id; }
+        else { const V3 P = O + D * hit.t; o[0] = P.x; o[1] = P.y; o[2] = P.z; o[3] = hit.t; }
+    }
+}
+
 // debug: per-segment state of one path (24 floats per segment, zero-filled beyond termination)
 void orc_path_probe(void* s, const RfwCameraView3D* cam, uint32_t w, uint32_t h, uint32_t path_id, uint32_t sample, uint32_t depth, float clampv, const float* sky, float det_eps,
                     float* out) {

@@ -61,6 +61,7 @@ def lib():
         L.orc_primary_rays.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         L.orc_render.argtypes = [C.c_void_p, C.c_void_p] + [C.c_uint32] * 9 + [C.c_float, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_render.restype = C.c_double
+        L.orc_debug_view.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p]
         L.orc_path_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p, C.c_float, C.c_void_p]
         L.orc_triangle_test.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
         L.orc_triangle_test.restype = C.c_int
@@ -216,6 +217,13 @@ class OracleBackend:
         secs = self.L.orc_render(self.h, _ptr(v), w, h, x0, y0, x1, y1, first_sample, spp, depth, clamp, _ptr(skya), self.det_eps,
                                  self.threads, _ptr(acc), _ptr(st))
         return acc, {"samples": int(st[0]), "extension_rays": int(st[1]), "shadow_rays": int(st[2]), "segments": int(st[3]), "seconds": secs}
+
+    def debug_view(self, view, w, h, mode):
+        """RenderMode debug views at the primary hit: 1 normal, 2 albedo | material id, 3 world position | t."""
+        out = np.zeros((h, w, 4), dtype=np.float32)
+        v = np.ascontiguousarray(view)
+        self.L.orc_debug_view(self.h, _ptr(v), w, h, mode, self.det_eps, _ptr(out))
+        return out
 
     def path_probe(self, view, w, h, path_id, sample, depth, clamp=10.0, sky=(0, 0, 0)):
         """Debug: per-segment state of one path: rows of [O(3) D(3) inst prim t u v T(3) pdf 1 | nextO(3) nextD(3) acc.x newPdf]."""

@@ -368,5 +368,13 @@ class B200Backend:
         self._ck(self.L.rfwb200_measure_l2_read_gbs(self.h, nbytes, iters, C.addressof(out)), "measure_l2_read_gbs")
         return out.value
 
+    def save_ppm(self, path):
+        """Presentation stand-in for the reference's swap-chain blit (backends/gpu-rt/src/lib.rs:1753-1776): the output
+        buffer (sqrt(acc / spp), blit.comp:22) as an 8-bit binary PPM."""
+        img = np.clip(self.read_output()[..., :3], 0.0, 1.0)
+        with open(path, "wb") as f:
+            f.write(b"P6\n%d %d\n255\n" % (self.width, self.height))
+            f.write((img * 255.0 + 0.5).astype(np.uint8).tobytes())
+
     def launch_count(self):
         return self.L.rfwb200_launch_count(self.h)

@@ -1151,15 +1151,8 @@ int Backend::render_spp(const RfwCameraView3D* view, uint32_t spp, uint32_t dept
     if (!view) return fail(RFWB200_ERR_INVALID, "render: null view");
     if (wf.width == 0 || wf.height == 0) return fail(RFWB200_ERR_INVALID, "render: zero-sized framebuffer");
     if (depth == 0) depth = cfg.max_depth;
-    ShadeScene ss;
-    ss.inst = d_inst_shading.ptr; ss.materials = d_materials.ptr;
-    ss.area = d_area.ptr; ss.point = d_point.ptr; ss.spot = d_spot.ptr; ss.dir = d_dir.ptr;
-    ss.n_area = (int)area_lights.size(); ss.n_point = (int)point_lights.size(); ss.n_spot = (int)spot_lights.size(); ss.n_dir = (int)dir_lights.size();
-    ss.n_materials = (uint32_t)materials.size();
-    ss.textures = d_tex_desc.ptr; ss.n_textures = (uint32_t)textures.size();
-    ss.has_sky = have_skybox ? 1u : 0u;
-    ss.sky = skybox.desc;
     if (materials.empty()) return fail(RFWB200_ERR_INVALID, "render: no materials set");
+    const ShadeScene ss = shade_scene();
     wf.refill_below = tcfg.refill_below;
     wf.tri_batch = tcfg.tri_batch; wf.tri_batch_two_level = tcfg.tri_batch_two_level; wf.tri_blocked = tcfg.tri_blocked;
     const uint64_t before = wf.launches;
@@ -1187,9 +1180,35 @@ int Backend::render_spp(const RfwCameraView3D* view, uint32_t spp, uint32_t dept
     return RFWB200_OK;
 }
 
+ShadeScene Backend::shade_scene() const {
+    ShadeScene ss;
+    ss.inst = d_inst_shading.ptr; ss.materials = d_materials.ptr;
+    ss.area = d_area.ptr; ss.point = d_point.ptr; ss.spot = d_spot.ptr; ss.dir = d_dir.ptr;
+    ss.n_area = (int)area_lights.size(); ss.n_point = (int)point_lights.size(); ss.n_spot = (int)spot_lights.size(); ss.n_dir = (int)dir_lights.size();
+    ss.n_materials = (uint32_t)materials.size();
+    ss.textures = d_tex_desc.ptr; ss.n_textures = (uint32_t)textures.size();
+    ss.has_sky = have_skybox ? 1u : 0u;
+    ss.sky = skybox.desc;
+    return ss;
+}
+
 int Backend::render(const RfwCameraView3D* view, uint32_t mode) {
-    (void)mode;  // RenderMode debug views are SURVEY §8 f4
     if (!view) return fail(RFWB200_ERR_INVALID, "render: null view");
+    if (mode == RFW_RENDER_NORMAL || mode == RFW_RENDER_ALBEDO || mode == RFW_RENDER_GBUFFER) {
+        // debug views: attributes of the primary hit, written to the output buffer; the accumulation is left alone
+        DeviceScope device_scope(cfg.device);
+        BK_CUDA(device_scope.status, "cudaSetDevice");
+        if (int rc = ensure_synchronized("render")) return rc;
+        if (wf.width == 0 || wf.height == 0) return fail(RFWB200_ERR_INVALID, "render: zero-sized framebuffer");
+        if (materials.empty()) return fail(RFWB200_ERR_INVALID, "render: no materials set");
+        const uint64_t before = wf.launches;
+        BK_CUDA(wf.debug_view(stream, sv, shade_scene(), *view, mode), "debug view");
+        BK_CUDA(cudaStreamSynchronize(stream), "debug view");
+        launch_count += wf.launches - before;
+        return RFWB200_OK;
+    }
+    // ScreenSpace / Ssao / FilteredSsao are rasteriser post-processing views (backends/wgpu/shaders/ssao.comp): a path
+    // tracer has no screen-space pass, so they render the default image
     // the trait has no reset signal: restart when the camera bytes changed (or the scene did, see synchronize)
     if (!have_view || memcmp(&last_view, view, sizeof(RfwCameraView3D)) != 0) {
         if (int rc = reset_accumulator()) return rc;

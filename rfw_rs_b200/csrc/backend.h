@@ -118,6 +118,7 @@ private:
     int cuda_fail(cudaError_t e, const char* what);
     int ensure_synchronized(const char* who);
     int update_wavefront_scene();
+    ShadeScene shade_scene() const;
     void update_l2_policy();
     size_t l2_persist_max = 0, l2_window_max = 0;
     bool l2_persist_enabled = false;  // option "l2_persist": measured no effect on C2 (the 16 MB of nodes stay resident anyway), off by default

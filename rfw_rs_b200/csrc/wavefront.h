@@ -78,6 +78,8 @@ struct Wavefront {
     size_t capacity() const { return (size_t)max_paths * wave_capacity; }
     // `spp` frames starting at sample index `first_sample`, `depth` segments each; asynchronous on `stream`
     cudaError_t render(cudaStream_t stream, const SceneView& sv, const ShadeScene& ss, const RfwCameraView3D& cam, uint32_t first_sample, uint32_t spp, uint32_t depth);
+    // RenderMode debug views: primary-hit attributes straight into d_output (mode 1 normal, 2 albedo, 3 g-buffer)
+    cudaError_t debug_view(cudaStream_t stream, const SceneView& sv, const ShadeScene& ss, const RfwCameraView3D& cam, uint32_t mode);
     cudaError_t clear(cudaStream_t stream);
     cudaError_t finalize(cudaStream_t stream, uint32_t sample_count);  // d_output = sqrt(accum / sample_count), own tiles
     cudaError_t export_tiles(cudaStream_t stream, float* d_out);      // own tiles, tile-major

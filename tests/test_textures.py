@@ -114,3 +114,50 @@ def test_gpu_textured_scene_matches_oracle(oracle_mod):
     cpu.set_textures(desc.textures); cpu.set_skybox(None)
     ref2, _ = cpu.render(view, w, h, spp, depth, clamp=10.0, sky=(9, 9, 9))
     check_image(gpu.read_accumulator() / spp, ref2 / spp, "after texture update")
+
+
+def test_oracle_debug_views_known_answers(oracle_mod):
+    """RenderMode Normal / Albedo / GBuffer at the primary hit: a ground quad facing +y seen from above."""
+    sc = scenes.SceneDesc()
+    g = scenes.quad((0, 0, 0), (0, 1, 0), 4.0, 4.0, mat_id=0)
+    if g["normal"][0, 1] < 0:
+        g = scenes.make_triangles(g["vertex0"], g["vertex2"], g["vertex1"], 0)
+    sc.meshes[0] = g
+    sc.instances[0] = scenes.to_column_major([scenes.trs((0, 1.5, 0))])
+    sc.materials = scenes.material(color=(0.2, 0.4, 0.6))
+    o = oracle_mod.OracleBackend(); sc.apply(o)
+    w, h = 32, 24
+    view = scenes.camera_view((0, 5.0, 0.0), (0, -1.0, 1e-3), w, h)
+    n = o.debug_view(view, w, h, 1)[h // 2, w // 2]
+    a = o.debug_view(view, w, h, 2)[h // 2, w // 2]
+    p = o.debug_view(view, w, h, 3)[h // 2, w // 2]
+    np.testing.assert_allclose(n[:3], (0, 1, 0), atol=1e-6)
+    np.testing.assert_allclose(a, (0.2, 0.4, 0.6, 0.0), atol=1e-6)
+    assert abs(p[1] - 1.5) < 1e-4 and abs(p[3] - 3.5) < 1e-2   # hit on the plane y = 1.5, 3.5 below the camera
+
+
+@pytest.mark.gpu
+def test_gpu_debug_views_match_oracle(oracle_mod):
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from rfw_rs_b200 import backend as B
+
+    desc = scenes.textured_scene(grid=4, subdiv=2, tex_size=64)
+    w, h = 160, 90
+    view = scenes.camera_view((0, 2.5, -6.0), (0, -0.3, 1.0), w, h)
+    gpu = B.B200Backend(w, h); desc.apply(gpu)
+    cpu = oracle_mod.OracleBackend(det_eps=0.0); desc.apply(cpu)
+    gpu.render_spp(view, 2, 3)
+    acc_before = gpu.read_accumulator().copy()
+    for mode, tol in ((1, 2e-3), (2, 2e-3), (3, 2e-3)):
+        gpu.render(None, view, mode)
+        got = gpu.read_output()
+        ref = cpu.debug_view(view, w, h, mode)
+        # silhouette pixels may resolve to the neighbouring surface (float32 near-ties): compare all but a handful
+        bad = (np.abs(got - ref).max(axis=2) > tol * np.maximum(1.0, np.abs(ref).max(axis=2)))
+        assert bad.mean() < 5e-3, (mode, bad.mean())
+        assert np.abs(ref[..., :3]).sum() > 0
+    assert np.array_equal(gpu.read_accumulator(), acc_before)   # debug views leave the accumulation alone
+    assert gpu.sample_count == 2
