@@ -264,6 +264,13 @@ def main():
     desc.apply(be)
     sync_wall_ms = (time.time() - t0) * 1e3
     bs = be.build_stats()
+    # warm rebuild of the same BLAS (the first build of a process also pays module loading and allocator growth)
+    warm_build_ms = []
+    for _ in range(3):
+        be.set_option("sah_treelet", 8)   # marks every mesh dirty
+        be.synchronize()
+        warm_build_ms.append(be.build_stats()["blas_build_ms"])
+    assert be.build_stats()["checksum"] == bs["checksum"]  # same tree every time
     rays = scenes.random_rays(N_RAYS, start=rank * N_RAYS)
     pin_rays = backend.PinnedArray(N_RAYS, wire.RAY)
     pin_hits = backend.PinnedArray(N_RAYS, wire.HIT)
@@ -339,7 +346,7 @@ def main():
                                 "achieved_GBps": trav_gbs, "frac": trav_gbs / l2_peak if l2_peak else None,
                                 "note": "traversal bytes = nodes/ray x 80 B + tris/ray x 48 B requested by the SMs; 45% of them hit in L1 (ncu), the rest go to L2"}
         extra["hit_rate"] = hit_rate
-        extra["bvh_build"] = {"blas_build_ms": bs["blas_build_ms"], "synchronize_wall_ms_incl_upload": sync_wall_ms, "wide_nodes": bs["blas_nodes"],
+        extra["bvh_build"] = {"blas_build_ms": min(warm_build_ms), "blas_build_ms_first_in_process": bs["blas_build_ms"], "synchronize_wall_ms_incl_upload": sync_wall_ms, "wide_nodes": bs["blas_nodes"],
                               "bvh_bytes": bs["bvh_bytes"], "sah_cost": bs["sah_cost"]}
     if not args.no_extras:
         try:

@@ -53,15 +53,18 @@ __global__ void __launch_bounds__(TB) k_triangle_boxes(const RfwRTTriangle* __re
 
 // bounds[0..5]: centroid min xyz / max xyz; bounds[6..11]: box min xyz / max xyz (encoded)
 __global__ void __launch_bounds__(TB) k_bounds(const float4* __restrict__ lo, const float4* __restrict__ hi, int n, uint32_t* __restrict__ bounds) {
-    const int i = blockIdx.x * TB + threadIdx.x;
+    // grid-stride: a fixed grid accumulates in registers, then warp shuffle -> shared memory -> 12 atomics per CTA
+    // (one thread per primitive with 12 atomics per warp put 375 k same-address atomics into a 1 M-triangle build)
     float v[12];
-    if (i < n) {
-        const float4 l = lo[i], h = hi[i];
-        v[0] = v[3] = (l.x + h.x) * 0.5f; v[1] = v[4] = (l.y + h.y) * 0.5f; v[2] = v[5] = (l.z + h.z) * 0.5f;
-        v[6] = l.x; v[7] = l.y; v[8] = l.z; v[9] = h.x; v[10] = h.y; v[11] = h.z;
-    } else {
 #pragma unroll
-        for (int k = 0; k < 12; k++) v[k] = ((k % 6) < 3) ? 3.0e38f : -3.0e38f;
+    for (int k = 0; k < 12; k++) v[k] = ((k % 6) < 3) ? 3.0e38f : -3.0e38f;
+    for (int i = blockIdx.x * TB + threadIdx.x; i < n; i += gridDim.x * TB) {
+        const float4 l = lo[i], h = hi[i];
+        const float cx = (l.x + h.x) * 0.5f, cy = (l.y + h.y) * 0.5f, cz = (l.z + h.z) * 0.5f;
+        v[0] = fminf(v[0], cx); v[1] = fminf(v[1], cy); v[2] = fminf(v[2], cz);
+        v[3] = fmaxf(v[3], cx); v[4] = fmaxf(v[4], cy); v[5] = fmaxf(v[5], cz);
+        v[6] = fminf(v[6], l.x); v[7] = fminf(v[7], l.y); v[8] = fminf(v[8], l.z);
+        v[9] = fmaxf(v[9], h.x); v[10] = fmaxf(v[10], h.y); v[11] = fmaxf(v[11], h.z);
     }
 #pragma unroll
     for (int k = 0; k < 12; k++) {
@@ -72,12 +75,19 @@ __global__ void __launch_bounds__(TB) k_bounds(const float4* __restrict__ lo, co
             v[k] = is_min ? fminf(v[k], y) : fmaxf(v[k], y);
         }
     }
+    __shared__ float part[TB / 32][12];
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-        for (int k = 0; k < 12; k++) {
-            if ((k % 6) < 3) atomicMin(&bounds[k], enc_f(v[k]));
-            else atomicMax(&bounds[k], enc_f(v[k]));
-        }
+        for (int k = 0; k < 12; k++) part[threadIdx.x >> 5][k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        const int k = threadIdx.x;
+        const bool is_min = (k % 6) < 3;
+        float r = part[0][k];
+        for (int w = 1; w < TB / 32; w++) r = is_min ? fminf(r, part[w][k]) : fmaxf(r, part[w][k]);
+        if (is_min) atomicMin(&bounds[k], enc_f(r));
+        else atomicMax(&bounds[k], enc_f(r));
     }
 }
 
@@ -564,7 +574,7 @@ cudaError_t build_wide_bvh(BuilderContext& ctx, const float4* prim_lo, const flo
 
     RFW_CK(cudaMemsetAsync(counters, 0, 16 * sizeof(uint32_t), s));
     k_init_bounds<<<1, 32, 0, s>>>(bounds);
-    k_bounds<<<blocks_for(n), TB, 0, s>>>(prim_lo, prim_hi, n, bounds);
+    k_bounds<<<std::min(blocks_for(n), ctx.sm_count * 8), TB, 0, s>>>(prim_lo, prim_hi, n, bounds);
     k_morton<<<blocks_for(n), TB, 0, s>>>(prim_lo, prim_hi, n, bounds, keys, vals);
     ctx.launches += 3;
     RFW_CK(cudaGetLastError());

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256) k_generate_pinhole(RfwCameraView3D cam, u
 template <bool ANY, bool TWO_LEVEL>
 static cudaError_t launch_persistent_dispatch(const TraceConfig& cfg, const SceneView& sv, const RayBufferIO& io, uint32_t n, uint32_t* counter) {
     const TraceTuning tune{cfg.refill_below, TWO_LEVEL ? cfg.tri_batch_two_level : cfg.tri_batch, cfg.tri_blocked};
-    switch (cfg.min_blocks > 0 ? cfg.min_blocks : (TWO_LEVEL ? 6 : 8)) {
+    switch (cfg.min_blocks > 0 ? cfg.min_blocks : (TWO_LEVEL ? RFW_PT_MIN_BLOCKS_TL : RFW_PT_MIN_BLOCKS)) {
         case 3: return launch_persistent_mb<RayBufferIO, ANY, TWO_LEVEL, 3>(cfg.stream, cfg.sm_count, cfg.blocks_per_sm, tune, sv, io, n, counter);
         case 5: return launch_persistent_mb<RayBufferIO, ANY, TWO_LEVEL, 5>(cfg.stream, cfg.sm_count, cfg.blocks_per_sm, tune, sv, io, n, counter);
         case 6: return launch_persistent_mb<RayBufferIO, ANY, TWO_LEVEL, 6>(cfg.stream, cfg.sm_count, cfg.blocks_per_sm, tune, sv, io, n, counter);

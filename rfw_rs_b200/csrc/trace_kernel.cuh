@@ -319,17 +319,21 @@ static cudaError_t launch_persistent_mb(cudaStream_t stream, int sm_count, int b
 #ifndef RFW_PT_MIN_BLOCKS
 #define RFW_PT_MIN_BLOCKS 8
 #endif
+#ifndef RFW_PT_MIN_BLOCKS_TL
+#define RFW_PT_MIN_BLOCKS_TL 7
+#endif
 
 template <class IO, bool ANY, bool TWO_LEVEL>
 static cudaError_t launch_persistent_io(cudaStream_t stream, int sm_count, int blocks_per_sm_limit, TraceTuning tune, const SceneView& sv, const IO& io, uint32_t n_hint,
                                         uint32_t* counter) {
     // single-level: 64 registers / 32 warps per SM (measured best on C2); the two-level variant carries the world-space
-    // ray and the instance context as well and spills at 64, so it gets 80 registers / 24 warps per SM
-    return launch_persistent_mb<IO, ANY, TWO_LEVEL, (TWO_LEVEL ? 6 : RFW_PT_MIN_BLOCKS)>(stream, sm_count, blocks_per_sm_limit, tune, sv, io, n_hint, counter);
+    // ray and the instance context as well and spills at 64: 72 registers / 28 warps per SM (C3: 605 Msamples/s, vs 586
+    // at 80 registers / 24 warps and 592 at 64 registers with spills)
+    return launch_persistent_mb<IO, ANY, TWO_LEVEL, (TWO_LEVEL ? RFW_PT_MIN_BLOCKS_TL : RFW_PT_MIN_BLOCKS)>(stream, sm_count, blocks_per_sm_limit, tune, sv, io, n_hint, counter);
 }
 template <class IO, bool ANY, bool TWO_LEVEL>
 static cudaError_t persistent_grid_io(int sm_count, int blocks_per_sm_limit, uint32_t n_hint, int& grid) {
-    return persistent_grid_mb<IO, ANY, TWO_LEVEL, (TWO_LEVEL ? 6 : RFW_PT_MIN_BLOCKS)>(sm_count, blocks_per_sm_limit, n_hint, grid);
+    return persistent_grid_mb<IO, ANY, TWO_LEVEL, (TWO_LEVEL ? RFW_PT_MIN_BLOCKS_TL : RFW_PT_MIN_BLOCKS)>(sm_count, blocks_per_sm_limit, n_hint, grid);
 }
 
 }  // namespace rfw
