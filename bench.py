@@ -207,6 +207,24 @@ def path_tracing_extra(backend_mod, scenes, torch, rank, world, spp, dist):
     }
 
 
+def bind_to_gpu_numa_node(index):
+    """Host side of the e2e path: run this rank (and first-touch its pinned buffers) on the CPUs NVML reports as local to
+    its GPU, so 8 ranks do not push their 832 MB per step across the socket interconnect."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        if cpus & allowed:
+            os.sched_setaffinity(0, cpus & allowed)
+    except Exception:
+        pass  # a hint only
+
+
 _REAL_STDOUT = None
 
 
@@ -249,6 +267,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the backend has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    bind_to_gpu_numa_node(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -345,6 +364,17 @@ def main():
         extra["l2_roofline"] = {"peak_GBps": l2_peak, "peak_source": "k_l2_read microbenchmark: 32 MiB buffer, L1-bypassing loads, same run",
                                 "achieved_GBps": trav_gbs, "frac": trav_gbs / l2_peak if l2_peak else None,
                                 "note": "traversal bytes = nodes/ray x 80 B + tris/ray x 48 B requested by the SMs; 45% of them hit in L1 (ncu), the rest go to L2"}
+        # issue-side roofline: the kernel is bound by warp-instruction issue, not by bytes (ncu: 73 % of the issue slots busy)
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r1b_traffic.json")))
+            ipr = prof["warp_instructions_per_launch"] / prof["rays_per_launch"]
+            sms = torch.cuda.get_device_properties(0).multi_processor_count
+            peak_issue = sms * 4 * (clocks.get("sm_mhz") or 1965.0) * 1e6   # 4 schedulers per SM, 1 warp instruction per clock each
+            extra["issue_roofline"] = {"warp_instructions_per_ray": ipr, "source": "ncu smsp__inst_executed.sum of the committed capture (profiles/r1b_trace_closest.md)",
+                                       "achieved_Ginst_per_s": ipr * value / max(1, world) * 1e6 / 1e9, "peak_Ginst_per_s": peak_issue / 1e9,
+                                       "frac": ipr * value / max(1, world) * 1e6 / peak_issue, "avg_active_threads_of_32": prof["avg_active_threads_per_warp_instruction"]}
+        except Exception:
+            pass
         extra["hit_rate"] = hit_rate
         extra["bvh_build"] = {"blas_build_ms": min(warm_build_ms), "blas_build_ms_first_in_process": bs["blas_build_ms"], "synchronize_wall_ms_incl_upload": sync_wall_ms, "wide_nodes": bs["blas_nodes"],
                               "bvh_bytes": bs["bvh_bytes"], "sah_cost": bs["sah_cost"]}
