@@ -136,7 +136,10 @@ struct ConnectIO {
 };
 
 // ---- shade: shade.comp:70-266 ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_wf_shade(FrameParams fp, ShadeScene ss, const float4* __restrict__ S, const float4* __restrict__ O, const float4* __restrict__ D,
+#ifndef RFW_SHADE_MIN_BLOCKS
+#define RFW_SHADE_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(128, RFW_SHADE_MIN_BLOCKS) k_wf_shade(FrameParams fp, ShadeScene ss, const float4* __restrict__ S, const float4* __restrict__ O, const float4* __restrict__ D,
                                                   const float4* __restrict__ T, float4* __restrict__ On, float4* __restrict__ Dn, float4* __restrict__ Tn,
                                                   float4* __restrict__ shO, float4* __restrict__ shD, float4* __restrict__ shE, float* __restrict__ accum,
                                                   const uint32_t* __restrict__ count_cur, uint32_t* __restrict__ count_next, uint32_t* __restrict__ count_shadow) {
