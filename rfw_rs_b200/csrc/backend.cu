@@ -642,7 +642,7 @@ int Backend::synchronize() {
             single_identity = live == 1 && h_out[1] != 0;
             cudaError_t e = cudaSuccess;
             if (live > 1) {
-                const BuildParams tlas_params{1.0f, 4.0f, 1, sah_treelet};
+                const BuildParams tlas_params{1.0f, 4.0f, 1, sah_treelet_tlas};
                 e = build_wide_bvh(bctx, lo, hi, (int)live, tlas_params, tlas);
             }
             cudaFreeAsync(tmp_recs, stream); cudaFreeAsync(tmp_lo, stream); cudaFreeAsync(tmp_hi, stream);
@@ -1309,6 +1309,7 @@ int Backend::set_option(const char* key, int64_t value) {
     else if (k == "streamed") streamed_enabled = value != 0;  // host-buffer entry points: single-launch streaming (1) or chunked pipeline (0)
     else if (k == "chunk_rays") chunk_rays = (uint64_t)std::max<int64_t>(1024, value);
     else if (k == "max_depth") cfg.max_depth = (uint32_t)value;
+    else if (k == "sah_treelet_tlas") { sah_treelet_tlas = (int)value; scene_dirty = true; synchronized = false; }
     else if (k == "sah_treelet") { sah_treelet = (int)value; for (auto& m : meshes) if (m.present) m.dirty = true; scene_dirty = true; synchronized = false; }
     else if (k == "sah_c_prim_milli" || k == "sah_pmax") {  // SAH leaf cost (x1000) / max triangles per leaf slot (1..3)
         if (k == "sah_pmax") sah_pmax = (int)std::min<int64_t>(3, std::max<int64_t>(1, value));

@@ -189,6 +189,7 @@ private:
     uint64_t chunk_rays = 1u << 21;  // largest chunk of the host-buffer pipeline (the schedule ramps up to it and down again)
     float sah_c_prim = 0.8f;  // SAH cost of one triangle test relative to one wide-node visit (BLAS); swept on C2/C4 (scripts/tune_leafcost.py)
     int sah_pmax = 3;         // max triangles per leaf slot
+    int sah_treelet_tlas = 0;  // the same for the TLAS over instance boxes: off — refining the 170-instance TLAS of pica (nested, overlapping part boxes) made its primary rays 60 % slower (scripts/exp_c1b.py), the C3 grid TLAS is indifferent
     int sah_treelet = 8;  // binned-SAH refinement above LBVH treelets of this many primitives (0 = plain LBVH)
 
     // wavefront renderer
