@@ -510,7 +510,7 @@ int Backend::synchronize() {
                 BK_CUDA(cudaMallocAsync(&lo, (size_t)m.n * sizeof(float4), stream), "box alloc");
                 BK_CUDA(cudaMallocAsync(&hi, (size_t)m.n * sizeof(float4), stream), "box alloc");
                 cudaError_t e = triangle_boxes(bctx, m.d_tris, (int)m.n, lo, hi);
-                if (e == cudaSuccess) e = build_wide_bvh(bctx, lo, hi, (int)m.n, blas_params, m.bvh);
+                if (e == cudaSuccess) e = build_wide_bvh(bctx, lo, hi, (int)m.n, blas_params, m.bvh, /*deferred=*/true);  // small meshes: no host sync per mesh
                 cudaFreeAsync(lo, stream); cudaFreeAsync(hi, stream);
                 if (e != cudaSuccess) return cuda_fail(e, "BLAS build");
                 BK_CUDA(cudaMallocAsync(&m.d_ttris, (size_t)m.n * 3 * sizeof(float4), stream), "triangle alloc");
@@ -518,6 +518,7 @@ int Backend::synchronize() {
             }
             m.dirty = false;
         }
+        BK_CUDA(finish_pending_builds(bctx), "BLAS build");  // ONE sync for all deferred builds: node counts, bounds, SAH costs
         BK_CUDA(cudaEventRecord(ev1, stream), "event");
         BK_CUDA(cudaEventSynchronize(ev1), "BLAS build");
         cudaEventElapsedTime(&blas_ms, ev0, ev1);
@@ -643,11 +644,12 @@ int Backend::synchronize() {
             cudaError_t e = cudaSuccess;
             if (live > 1) {
                 const BuildParams tlas_params{1.0f, 4.0f, 1, sah_treelet_tlas};
-                e = build_wide_bvh(bctx, lo, hi, (int)live, tlas_params, tlas);
+                e = build_wide_bvh(bctx, lo, hi, (int)live, tlas_params, tlas, /*deferred=*/true);
             }
             cudaFreeAsync(tmp_recs, stream); cudaFreeAsync(tmp_lo, stream); cudaFreeAsync(tmp_hi, stream);
             cudaFreeAsync(lo, stream); cudaFreeAsync(hi, stream); cudaFreeAsync(flags, stream);
             if (e != cudaSuccess) return cuda_fail(e, "TLAS build");
+            BK_CUDA(finish_pending_builds(bctx), "TLAS build");
         }
         BK_CUDA(cudaStreamSynchronize(stream), "instance upload");
         sv.tlas_nodes = tlas.nodes;

@@ -520,9 +520,52 @@ cudaError_t coop_grid(K kernel, int block, int sm_count, long long work_items, i
 }
 }  // namespace
 
-cudaError_t build_wide_bvh(BuilderContext& ctx, const float4* prim_lo, const float4* prim_hi, int n, const BuildParams& params, DeviceBvh& out) {
+// deferred builds: copy the 8-float cost record of the collapse root (SAH top root if it exists) to a fixed place
+__global__ void k_pick_root_cost(const float* __restrict__ cost, const uint32_t* __restrict__ counters, unsigned long long refined_root, int refine,
+                                 uint32_t* __restrict__ out) {
+    const size_t root = (refine && counters[4] >= 2u) ? (size_t)refined_root : 0;
+    if (threadIdx.x < 8) out[threadIdx.x] = __float_as_uint(cost[root * 8 + threadIdx.x]);
+}
+
+BuilderContext::~BuilderContext() {
+    if (h_results) cudaFreeHost(h_results);
+}
+
+
+
+static cudaError_t apply_build_result(const BuildResultSlot& r, int n, bool refined, DeviceBvh& out) {
+    out.num_nodes = r.counters[0];
+    out.num_prims = r.counters[1];
+    out.num_treelets = r.counters[4];
+    if (out.num_prims != (uint32_t)n) {
+        fprintf(stderr, "rfwb200: collapse emitted %u leaf slots for %d primitives\n", out.num_prims, n);
+        return cudaErrorUnknown;
+    }
+    for (int k = 0; k < 3; k++) { out.lo[k] = dec_f(r.bounds[6 + k]); out.hi[k] = dec_f(r.bounds[9 + k]); }
+    (void)refined;
+    out.sah = r.cost[7] > 0.0f ? r.cost[0] / r.cost[7] : 0.0f;
+    return cudaSuccess;
+}
+
+cudaError_t finish_pending_builds(BuilderContext& ctx) {
+    if (ctx.pending.empty()) return cudaSuccess;
+    cudaError_t e = cudaStreamSynchronize(ctx.stream);
+    for (const PendingBuild& p : ctx.pending) {
+        if (e != cudaSuccess) break;
+        e = apply_build_result(ctx.h_results[p.slot], p.n, p.refined, *p.out);
+    }
+    ctx.pending.clear();
+    return e;
+}
+
+cudaError_t build_wide_bvh(BuilderContext& ctx, const float4* prim_lo, const float4* prim_hi, int n, const BuildParams& params, DeviceBvh& out, bool deferred) {
     out.release();
     if (n <= 0) return cudaSuccess;
+    if (deferred && n > BUILD_DEFER_MAX) deferred = false;
+    if (deferred) {
+        if (!ctx.h_results && cudaHostAlloc(&ctx.h_results, sizeof(BuildResultSlot) * BUILD_DEFER_SLOTS, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); ctx.h_results = nullptr; deferred = false; }
+        if (deferred && (int)ctx.pending.size() >= BUILD_DEFER_SLOTS) RFW_CK(finish_pending_builds(ctx));
+    }
     cudaStream_t s = ctx.stream;
     if (ctx.sm_count <= 0) {
         int dev = 0;
@@ -619,29 +662,41 @@ cudaError_t build_wide_bvh(BuilderContext& ctx, const float4* prim_lo, const flo
         RFW_CK(cudaLaunchCooperativeKernel((void*)k_collapse_all, dim3(grid), dim3(128), args, 0, s));
         ctx.launches++;
     }
-    uint32_t h_counters[8];
-    uint32_t h_bounds[12];
-    RFW_CK(cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, s));
-    RFW_CK(cudaMemcpyAsync(h_bounds, bounds, sizeof(h_bounds), cudaMemcpyDeviceToHost, s));
+    const size_t root = refine ? 2 * (size_t)n - 1 : 0;  // SAH cost is read at the root the collapse started from (see k_pick_root_cost)
+    if (deferred) {
+        // no host sync: upper-bound allocation (a tree over n primitives has fewer than n wide nodes), results to a pinned slot
+        const int slot = (int)ctx.pending.size();
+        BuildResultSlot* r = ctx.h_results + slot;
+        RFW_CK(cudaMallocAsync(&out.nodes, (size_t)n * 80, s));
+        RFW_CK(cudaMallocAsync(&out.leaf_prims, (size_t)n * sizeof(uint32_t), s));
+        RFW_CK(cudaMemcpyAsync(out.nodes, tmp_nodes, (size_t)n * 80, cudaMemcpyDeviceToDevice, s));
+        RFW_CK(cudaMemcpyAsync(out.leaf_prims, tmp_leaf, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+        RFW_CK(cudaMemcpyAsync(r->counters, counters, sizeof(r->counters), cudaMemcpyDeviceToHost, s));
+        RFW_CK(cudaMemcpyAsync(r->bounds, bounds, sizeof(r->bounds), cudaMemcpyDeviceToHost, s));
+        // the refined root exists only when the SAH top build had >= 2 treelets: pick the right cost record on the device
+        k_pick_root_cost<<<1, 32, 0, s>>>(cost, counters, (unsigned long long)root, refine ? 1 : 0, counters + 8);
+        RFW_CK(cudaMemcpyAsync(r->cost, counters + 8, sizeof(r->cost), cudaMemcpyDeviceToHost, s));
+        ctx.launches++;
+        ctx.pending.push_back(PendingBuild{&out, slot, n, refine});
+        return cudaSuccess;
+    }
+    BuildResultSlot res;
+    RFW_CK(cudaMemcpyAsync(res.counters, counters, sizeof(res.counters), cudaMemcpyDeviceToHost, s));
+    RFW_CK(cudaMemcpyAsync(res.bounds, bounds, sizeof(res.bounds), cudaMemcpyDeviceToHost, s));
     RFW_CK(cudaStreamSynchronize(s));  // the host sync of the build: the node count sizes the final buffers
-    out.num_nodes = h_counters[0];
-    out.num_prims = h_counters[1];
-    out.num_treelets = h_counters[4];
-    if (out.num_prims != (uint32_t)n) {
-        fprintf(stderr, "rfwb200: collapse emitted %u leaf slots for %d primitives\n", out.num_prims, n);
+    if (res.counters[1] != (uint32_t)n) {
+        fprintf(stderr, "rfwb200: collapse emitted %u leaf slots for %d primitives\n", res.counters[1], n);
         return cudaErrorUnknown;
     }
-    RFW_CK(cudaMallocAsync(&out.nodes, (size_t)out.num_nodes * 80, s));  // stream-ordered pool: no device-wide sync per mesh
+    RFW_CK(cudaMallocAsync(&out.nodes, (size_t)res.counters[0] * 80, s));  // stream-ordered pool: no device-wide sync per mesh
     RFW_CK(cudaMallocAsync(&out.leaf_prims, (size_t)n * sizeof(uint32_t), s));
-    RFW_CK(cudaMemcpyAsync(out.nodes, tmp_nodes, (size_t)out.num_nodes * 80, cudaMemcpyDeviceToDevice, s));
+    RFW_CK(cudaMemcpyAsync(out.nodes, tmp_nodes, (size_t)res.counters[0] * 80, cudaMemcpyDeviceToDevice, s));
     RFW_CK(cudaMemcpyAsync(out.leaf_prims, tmp_leaf, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
     // SAH cost of the tree the collapse started from (root = SAH top root when refined, else Karras node 0 / the only leaf)
-    const size_t root = (refine && out.num_treelets >= 2) ? 2 * (size_t)n - 1 : 0;
-    float h_cost[8];
-    RFW_CK(cudaMemcpyAsync(h_cost, cost + root * 8, sizeof(h_cost), cudaMemcpyDeviceToHost, s));
+    const size_t root_now = (refine && res.counters[4] >= 2) ? root : 0;
+    RFW_CK(cudaMemcpyAsync(res.cost, cost + root_now * 8, sizeof(res.cost), cudaMemcpyDeviceToHost, s));
     RFW_CK(cudaStreamSynchronize(s));
-    for (int k = 0; k < 3; k++) { out.lo[k] = dec_f(h_bounds[6 + k]); out.hi[k] = dec_f(h_bounds[9 + k]); }
-    out.sah = h_cost[7] > 0.0f ? h_cost[0] / h_cost[7] : 0.0f;
+    RFW_CK(apply_build_result(res, n, refine, out));
     return cudaSuccess;
 }
 

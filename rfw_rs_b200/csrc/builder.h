@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "../../include/rfwb200.h"
 #include "bvh_build.h"
 
@@ -33,16 +35,40 @@ struct BuildScratch {
     void* reserve(size_t bytes);
 };
 
+// What a build reports back to the host (node / leaf counts, bounds, SAH cost): written by the device into pinned memory
+struct BuildResultSlot {
+    uint32_t counters[8];
+    uint32_t bounds[12];
+    float cost[8];
+    uint32_t pad[4];
+};
+struct PendingBuild {
+    DeviceBvh* out;
+    int slot, n;
+    bool refined;
+};
+
 struct BuilderContext {
     cudaStream_t stream = nullptr;
     BuildScratch scratch;
     uint64_t launches = 0;
     int sm_count = 0;
+    BuildResultSlot* h_results = nullptr;  // pinned, DEFER_SLOTS entries
+    std::vector<PendingBuild> pending;
+    ~BuilderContext();
 };
 
-// prim_lo / prim_hi: device arrays of n boxes.  Builds the wide BVH into `out` (allocating exact-size buffers).
+// prim_lo / prim_hi: device arrays of n boxes.  Builds the wide BVH into `out`.
+// deferred = false: one host sync (the node count sizes the final buffers exactly), `out` is complete on return.
+// deferred = true (small builds, n <= BUILD_DEFER_MAX): no host sync at all — the node buffer is allocated at its upper
+//   bound (n nodes), the counts / bounds / cost land in a pinned slot, and `out`'s host-side fields are filled by
+//   finish_pending_builds() after ONE sync for any number of builds (a 170-mesh asset paid 170 x 2 syncs before).
+//   `out` must stay where it is until then; its device pointers are valid immediately (stream-ordered).
 // Returns a cudaError_t (cudaSuccess on success).
-cudaError_t build_wide_bvh(BuilderContext& ctx, const float4* prim_lo, const float4* prim_hi, int n, const BuildParams& params, DeviceBvh& out);
+static constexpr int BUILD_DEFER_MAX = 1 << 16;
+static constexpr int BUILD_DEFER_SLOTS = 1024;
+cudaError_t build_wide_bvh(BuilderContext& ctx, const float4* prim_lo, const float4* prim_hi, int n, const BuildParams& params, DeviceBvh& out, bool deferred = false);
+cudaError_t finish_pending_builds(BuilderContext& ctx);
 
 // triangle boxes of a 176-byte RTTriangle array (device pointers)
 cudaError_t triangle_boxes(BuilderContext& ctx, const RfwRTTriangle* tris, int n, float4* prim_lo, float4* prim_hi);
