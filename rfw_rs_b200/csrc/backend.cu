@@ -670,13 +670,13 @@ int Backend::synchronize() {
             build_stats.num_meshes++;
             build_stats.num_triangles += m.n;
             build_stats.blas_nodes += m.bvh.num_nodes;
-            build_stats.bvh_bytes += (uint64_t)m.bvh.num_nodes * 80 + (uint64_t)m.n * 48;
+            build_stats.bvh_bytes += (uint64_t)m.bvh.num_nodes * NODE_BYTES + (uint64_t)m.n * 48;
             if (m.bvh.sah > build_stats.sah_cost) build_stats.sah_cost = m.bvh.sah;
         }
         checksum_dirty = true;  // computed on demand (read_build_stats): a per-frame TLAS rebuild must not re-hash every BLAS
         build_stats.num_instances = live;
         build_stats.tlas_nodes = tlas.num_nodes;
-        build_stats.bvh_bytes += (uint64_t)tlas.num_nodes * 80;
+        build_stats.bvh_bytes += (uint64_t)tlas.num_nodes * NODE_BYTES;
         build_stats.blas_build_ms = blas_ms;
         build_stats.tlas_build_ms = tlas_ms;
         scene_dirty = false;
@@ -716,7 +716,7 @@ void Backend::update_l2_policy() {
     if (!l2_persist_enabled) return;
     const void* best = nullptr;
     size_t best_bytes = 0;
-    auto consider = [&](const DeviceBvh& b) { if (b.nodes && (size_t)b.num_nodes * 80 > best_bytes) { best = b.nodes; best_bytes = (size_t)b.num_nodes * 80; } };
+    auto consider = [&](const DeviceBvh& b) { if (b.nodes && (size_t)b.num_nodes * NODE_BYTES > best_bytes) { best = b.nodes; best_bytes = (size_t)b.num_nodes * NODE_BYTES; } };
     consider(tlas);
     for (const MeshRec& m : meshes) if (m.present) consider(m.bvh);
     cudaStreamAttrValue attr{};
@@ -740,10 +740,10 @@ int Backend::read_build_stats(RfwBuildStats* out) {
         BK_CUDA(cudaMemsetAsync(d_counters3, 0, 8, stream), "checksum");
         for (const MeshRec& m : meshes) {
             if (!m.present || !m.n) continue;
-            BK_CUDA(buffer_checksum(bctx, reinterpret_cast<const uint32_t*>(m.bvh.nodes), 20, m.bvh.num_nodes, 0x30u, d_counters3), "checksum");
+            BK_CUDA(buffer_checksum(bctx, reinterpret_cast<const uint32_t*>(m.bvh.nodes), NODE_WORDS, m.bvh.num_nodes, 0x30u, d_counters3), "checksum");
             BK_CUDA(buffer_checksum(bctx, reinterpret_cast<const uint32_t*>(m.d_ttris), 12, m.n, 0u, d_counters3), "checksum");
         }
-        if (tlas.num_nodes) BK_CUDA(buffer_checksum(bctx, reinterpret_cast<const uint32_t*>(tlas.nodes), 20, tlas.num_nodes, 0x30u, d_counters3), "checksum");
+        if (tlas.num_nodes) BK_CUDA(buffer_checksum(bctx, reinterpret_cast<const uint32_t*>(tlas.nodes), NODE_WORDS, tlas.num_nodes, 0x30u, d_counters3), "checksum");
         unsigned long long cs = 0;
         BK_CUDA(cudaMemcpyAsync(&cs, d_counters3, 8, cudaMemcpyDeviceToHost, stream), "checksum");
         BK_CUDA(cudaStreamSynchronize(stream), "checksum");
@@ -988,14 +988,25 @@ int Backend::trace_host_streamed(bool any_hit, const RfwRay* rays, uint64_t num,
     BK_CUDA(trace_streamed(tcfg, sv, any_hit, d_rays.ptr, n, any_hit ? nullptr : reinterpret_cast<RfwHit*>(d_out), any_hit ? reinterpret_cast<uint32_t*>(d_out) : nullptr, d_counter, ss),
             "trace_streamed");
     launch_count++;
-    // uploads: 1, 1, 2, then 4 granules (32 MiB) per copy — a quick start, then few large DMA transfers (8 MiB copies
-    // with a 4-byte watermark copy after each one cost ~15 % of the PCIe rate)
-    for (uint32_t g = 0, step = 1, k = 0; g < granules; g += step, k++) {
-        step = k < 2 ? 1u : (k == 2 ? 2u : 4u);
-        const uint32_t last = std::min(granules, g + step) - 1;
-        const uint64_t off = (uint64_t)g * G, cnt = h_stream_marks[last] - off;
-        BK_CUDA(cudaMemcpyAsync(d_rays.ptr + off, rays + off, cnt * sizeof(RfwRay), cudaMemcpyHostToDevice, copy_in), "ray upload");
-        BK_CUDA(cudaMemcpyAsync(d_stream_state, h_stream_marks + last, sizeof(uint32_t), cudaMemcpyHostToDevice, copy_in), "watermark");
+    // uploads: 1, 1, 2, then 4 granules (32 MiB) per copy (a quick start, then few large DMA transfers: 8 MiB copies
+    // with a 4-byte watermark copy after each one cost ~15 % of the PCIe rate), and 2, 1, 1 granules at the end: what
+    // the kernel still has to trace after the LAST copy lands is exposed (1.0 ms with a 4-granule last copy, measured)
+    {
+        const uint32_t ramp_down = granules >= 16 ? 4u : 0u;  // granules covered by the 2, 1, 1 tail
+        for (uint32_t g = 0, k = 0; g < granules; k++) {
+            uint32_t step = k < 2 ? 1u : (k == 2 ? 2u : 4u);
+            const uint32_t left = granules - g;
+            if (ramp_down) {
+                if (left <= 2) step = 1;
+                else if (left <= 4) step = left - 2;  // 4 -> 2, 3 -> 1
+                else if (left - step < ramp_down) step = left - ramp_down;
+            }
+            const uint32_t last = std::min(granules, g + step) - 1;
+            const uint64_t off = (uint64_t)g * G, cnt = h_stream_marks[last] - off;
+            BK_CUDA(cudaMemcpyAsync(d_rays.ptr + off, rays + off, cnt * sizeof(RfwRay), cudaMemcpyHostToDevice, copy_in), "ray upload");
+            BK_CUDA(cudaMemcpyAsync(d_stream_state, h_stream_marks + last, sizeof(uint32_t), cudaMemcpyHostToDevice, copy_in), "watermark");
+            g = last + 1;
+        }
     }
     static const bool trace = getenv("RFWB200_PIPE_TRACE") != nullptr;
     cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};

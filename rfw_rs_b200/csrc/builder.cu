@@ -599,7 +599,7 @@ cudaError_t build_wide_bvh(BuilderContext& ctx, const float4* prim_lo, const flo
         cost = cv.take<float>(nn * 8);
         decision = cv.take<uint32_t>(ni);
         q0 = cv.take<int2>(n); q1 = cv.take<int2>(n);
-        tmp_nodes = cv.take<float4>((size_t)n * 5);
+        tmp_nodes = cv.take<float4>((size_t)n * NODE_F4);
         tmp_leaf = cv.take<uint32_t>(n);
         counters = cv.take<uint32_t>(16);
         bounds = cv.take<uint32_t>(16);
@@ -667,9 +667,9 @@ cudaError_t build_wide_bvh(BuilderContext& ctx, const float4* prim_lo, const flo
         // no host sync: upper-bound allocation (a tree over n primitives has fewer than n wide nodes), results to a pinned slot
         const int slot = (int)ctx.pending.size();
         BuildResultSlot* r = ctx.h_results + slot;
-        RFW_CK(cudaMallocAsync(&out.nodes, (size_t)n * 80, s));
+        RFW_CK(cudaMallocAsync(&out.nodes, (size_t)n * NODE_BYTES, s));
         RFW_CK(cudaMallocAsync(&out.leaf_prims, (size_t)n * sizeof(uint32_t), s));
-        RFW_CK(cudaMemcpyAsync(out.nodes, tmp_nodes, (size_t)n * 80, cudaMemcpyDeviceToDevice, s));
+        RFW_CK(cudaMemcpyAsync(out.nodes, tmp_nodes, (size_t)n * NODE_BYTES, cudaMemcpyDeviceToDevice, s));
         RFW_CK(cudaMemcpyAsync(out.leaf_prims, tmp_leaf, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
         RFW_CK(cudaMemcpyAsync(r->counters, counters, sizeof(r->counters), cudaMemcpyDeviceToHost, s));
         RFW_CK(cudaMemcpyAsync(r->bounds, bounds, sizeof(r->bounds), cudaMemcpyDeviceToHost, s));
@@ -688,9 +688,9 @@ cudaError_t build_wide_bvh(BuilderContext& ctx, const float4* prim_lo, const flo
         fprintf(stderr, "rfwb200: collapse emitted %u leaf slots for %d primitives\n", res.counters[1], n);
         return cudaErrorUnknown;
     }
-    RFW_CK(cudaMallocAsync(&out.nodes, (size_t)res.counters[0] * 80, s));  // stream-ordered pool: no device-wide sync per mesh
+    RFW_CK(cudaMallocAsync(&out.nodes, (size_t)res.counters[0] * NODE_BYTES, s));  // stream-ordered pool: no device-wide sync per mesh
     RFW_CK(cudaMallocAsync(&out.leaf_prims, (size_t)n * sizeof(uint32_t), s));
-    RFW_CK(cudaMemcpyAsync(out.nodes, tmp_nodes, (size_t)res.counters[0] * 80, cudaMemcpyDeviceToDevice, s));
+    RFW_CK(cudaMemcpyAsync(out.nodes, tmp_nodes, (size_t)res.counters[0] * NODE_BYTES, cudaMemcpyDeviceToDevice, s));
     RFW_CK(cudaMemcpyAsync(out.leaf_prims, tmp_leaf, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
     // SAH cost of the tree the collapse started from (root = SAH top root when refined, else Karras node 0 / the only leaf)
     const size_t root_now = (refine && res.counters[4] >= 2) ? root : 0;

@@ -324,7 +324,8 @@ RFW_HD void collapse_body(int2 task, const BuildArrays& A, const CollapseOut& O,
         q = ceil(((double)chi.y - (double)plo.y) * isy); qhy[half] |= (uint32_t)(q < 0 ? 0 : (q > 255 ? 255 : q)) << sh;
         q = ceil(((double)chi.z - (double)plo.z) * isz); qhz[half] |= (uint32_t)(q < 0 ? 0 : (q > 255 ? 255 : q)) << sh;
     }
-    float4* out = O.nodes + (size_t)widx * 5;
+    float4* out = O.nodes + (size_t)widx * NODE_F4;
+    if (NODE_F4 > 5) out[5] = f4(0.0f, 0.0f, 0.0f, 0.0f);  // pad of the 32-B aligned stride (hashed by the BVH checksum)
     out[0] = f4(plo.x, plo.y, plo.z, u2f(ex | (ey << 8) | (ez << 16) | (imask << 24)));
     out[1] = f4(u2f(child_base), u2f(prim_base), u2f(meta[0]), u2f(meta[1]));
     out[2] = f4(u2f(qlx[0]), u2f(qlx[1]), u2f(qly[0]), u2f(qly[1]));

@@ -20,7 +20,17 @@
 #define RFW_D inline
 #endif
 
+// wide-node stride in float4 (layout: traverse.h): 6 = 96 B, 32-B aligned (default); 5 = 80 B packed
+#ifndef RFW_NODE_F4
+#define RFW_NODE_F4 6
+#endif
+
 namespace rfw {
+
+static constexpr int NODE_F4 = RFW_NODE_F4;
+static constexpr int NODE_BYTES = RFW_NODE_F4 * 16;
+static constexpr int NODE_WORDS = RFW_NODE_F4 * 4;
+static_assert(NODE_F4 == 5 || NODE_F4 == 6, "node stride: 80 B packed or 96 B (32-B aligned)");
 
 RFW_HD uint32_t f2u(float f) {
 #if defined(__CUDA_ARCH__)

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
     uint32_t ray_idx = 0;
     float3 wo = f3(0, 0, 0), wd = f3(0, 0, 0);  // world-space ray (two-level variant only)
     RayCtx rc;
-    rc.o = wo; rc.d = wd; rc.idir = wo; rc.octinv4 = 0; rc.kx = 0; rc.ky = 1; rc.kz = 2; rc.Sx = rc.Sy = rc.Sz = 0.0f;
+    rc.o = wo; rc.d = wd; rc.idir = wo; rc.octinv4 = 0; rc.kz = 2; rc.Sx = rc.Sy = rc.Sz = 0.0f;
     float tmin = 0.0f;
     Hit hit;
     hit.inst = -1; hit.prim = -1; hit.t = 0.0f; hit.u = hit.v = 0.0f;
@@ -209,8 +209,9 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
                     if (RFW_NODE_HITS(ng)) RFW_STACK_PUSH(ng);
                     const uint32_t slot = (uint32_t)(bit - 24) ^ (rc.octinv4 & 7u);
                     const uint32_t rel = __popc(hits_imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
-                    const float4* np = nodes + (size_t)(base + rel) * 5;
-                    const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+                    const float4* np = nodes + (size_t)(base + rel) * NODE_F4;
+                    float4 n0, n1, n2, n3, n4;
+                    load_wide_node(np, n0, n1, n2, n3, n4);
                     const uint32_t hm = intersect_wide_node(n0, n1, n2, n3, n4, rc, tmin, hit.t);
                     ng.x = __float_as_uint(n1.x);
                     tgn.x = __float_as_uint(n1.y);

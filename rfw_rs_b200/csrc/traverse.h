@@ -7,7 +7,11 @@
 //   BLAS / TLAS stack loops    backends/gpu-rt/shaders/ray_gen.comp:202-250, 310-362;
 //                              ray_shadow.comp:83-132, 191-243; crates/rfw-scene/src/intersector.rs:21-75
 //
-// Node layout (80 B = 5 x 16 B, after Ylitie/Karras/Laine 2017 "compressed wide BVH"):
+// Node layout (80 B of payload = 5 x 16 B, after Ylitie/Karras/Laine 2017 "compressed wide BVH"), stored at a stride of
+// RFW_NODE_F4 x 16 B.  The default stride is 96 B: every node starts on a 32-B boundary, so a visit fetches it with two
+// 256-bit loads + one 128-bit load (sm_100 LDG.E.ENL2.256) = 3 L1 tag look-ups per lane instead of 5 — the divergent
+// node gathers ran the L1 data pipe at 71 % next to 73 % issue utilisation — and it covers exactly 3 L2 sectors
+// (an 80-B stride straddles 3.5 on average).  -DRFW_NODE_F4=5 builds the packed 80-B variant (5 x LDG.128) for A/B runs.
 //   n0 = (p.x, p.y, p.z, [ex | ey<<8 | ez<<16 | imask<<24])   e* = biased float exponents of the grid scale
 //   n1 = (child_base, prim_base, meta[0..3], meta[4..7])
 //   n2 = (qlo_x[0..3], qlo_x[4..7], qlo_y[0..3], qlo_y[4..7])
@@ -53,10 +57,27 @@ struct TraceCounters {
 struct RayCtx {
     float3 o, d, idir;
     uint32_t octinv4;
-    // watertight (Woop, Benthin, Wald 2013) shear constants
-    int kx, ky, kz;
+    // watertight (Woop, Benthin, Wald 2013) shear constants: kz = dominant axis of d, kx = kz+1, ky = kz+2 (mod 3)
+    int kz;
     float Sx, Sy, Sz;
 };
+
+// correctly rounded single operations that the compiler may not contract into FMAs: the edge functions of the
+// triangle test must be EXACTLY antisymmetric in their two vertices (see intersect_tri_wt)
+RFW_HD float mul_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(a, b);
+#else
+    volatile float r = a * b; return r;
+#endif
+}
+RFW_HD float sub_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fsub_rn(a, b);
+#else
+    volatile float r = a - b; return r;
+#endif
+}
 
 RFW_HD float safe_rcp_dir(float d) {
     // |d| below 2^-80 (incl. exact zeros of axis-parallel rays) is replaced by +-2^-80: with an infinite reciprocal
@@ -71,17 +92,22 @@ RFW_HD void ray_setup_box(RayCtx& r) {
     const uint32_t octinv = (r.d.x < 0.0f ? 0u : 4u) | (r.d.y < 0.0f ? 0u : 2u) | (r.d.z < 0.0f ? 0u : 1u);
     r.octinv4 = octinv * 0x01010101u;
 }
+// component k / k+1 / k+2 (mod 3) of v as selects (no data-dependent branches: lanes of a warp differ in k)
+RFW_HD float comp_k0(float3 v, bool k0, bool k1) { return k0 ? v.x : (k1 ? v.y : v.z); }
+RFW_HD float comp_k1(float3 v, bool k0, bool k1) { return k0 ? v.y : (k1 ? v.z : v.x); }
+RFW_HD float comp_k2(float3 v, bool k0, bool k1) { return k0 ? v.z : (k1 ? v.x : v.y); }
+
 RFW_HD void ray_setup_tri(RayCtx& r) {
     const float ax = fabsf(r.d.x), ay = fabsf(r.d.y), az = fabsf(r.d.z);
-    int kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
-    int kx = kz + 1; if (kx == 3) kx = 0;
-    int ky = kx + 1; if (ky == 3) ky = 0;
-    const float dz = comp3(r.d, kz);
-    if (dz < 0.0f) { int t = kx; kx = ky; ky = t; }
-    r.kx = kx; r.ky = ky; r.kz = kz;
-    r.Sx = comp3(r.d, kx) / dz;
-    r.Sy = comp3(r.d, ky) / dz;
-    r.Sz = 1.0f / dz;
+    const int kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
+    const bool k0 = kz == 0, k1 = kz == 1;
+    // Woop et al. swap kx/ky when d[kz] < 0 to preserve the winding; without back-face culling the swap only flips the
+    // sign of all three edge functions and of their sum, which the test below does not care about
+    const float rz = 1.0f / comp_k0(r.d, k0, k1);
+    r.kz = kz;
+    r.Sx = comp_k1(r.d, k0, k1) * rz;
+    r.Sy = comp_k2(r.d, k0, k1) * rz;
+    r.Sz = rz;
 }
 
 // byte j of a word as a float.  Default: the integer->float conversion instruction with a byte selector (I2F.U8).
@@ -94,6 +120,19 @@ RFW_HD float byte_to_float(uint32_t w, int j) {
     return u2f(byte_perm(w, 0x4B000000u, 0x7650u | (uint32_t)j)) - 8388608.0f;
 #else
     return (float)((w >> (8 * j)) & 0xFFu);
+#endif
+}
+
+// fetch one wide node (read-only path)
+RFW_HD void load_wide_node(const float4* np, float4& n0, float4& n1, float4& n2, float4& n3, float4& n4) {
+#if defined(__CUDA_ARCH__) && RFW_NODE_F4 == 6
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(n0.x), "=f"(n0.y), "=f"(n0.z), "=f"(n0.w), "=f"(n1.x), "=f"(n1.y), "=f"(n1.z), "=f"(n1.w) : "l"(np));
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(n2.x), "=f"(n2.y), "=f"(n2.z), "=f"(n2.w), "=f"(n3.x), "=f"(n3.y), "=f"(n3.z), "=f"(n3.w) : "l"(np + 2));
+    n4 = __ldg(np + 4);
+#else
+    n0 = ldg(np + 0); n1 = ldg(np + 1); n2 = ldg(np + 2); n3 = ldg(np + 3); n4 = ldg(np + 4);
 #endif
 }
 
@@ -146,30 +185,32 @@ RFW_HD uint32_t intersect_wide_node(const float4 n0, const float4 n1, const floa
     return hitmask;
 }
 
-// Watertight ray/triangle test.  On acceptance returns true with t and the reference's barycentrics
-// (u weights v1, v weights v2; shade.comp:105-111).  No back-face culling (the reference has none).
+// Watertight ray/triangle test (Woop, Benthin, Wald 2013).  On acceptance returns true with t and the reference's
+// barycentrics (u weights v1, v weights v2; shade.comp:105-111).  No back-face culling (the reference has none).
+//
+// The vertices, relative to the ray origin, are sheared into the space where the ray runs along +kz; the axis
+// permutation is a set of selects (branch-free: the lanes of a warp disagree about kz).  The sheared coordinates of a
+// vertex depend on the ray and that vertex only, and every 2D edge function is round(round(p*q) - round(r*s)), so
+// swapping the two vertices of an edge negates it EXACTLY: two triangles sharing an edge see the same |value| with
+// consistent signs, whichever way each of them orients the edge, and a ray cannot slip between them.  Hits on an edge
+// (value 0) are accepted by both (inclusive edges, intersection.glsl:19,25), which is why the double-precision
+// re-evaluation of zero edge functions of the paper is not needed.
+RFW_HD float edge_fn(float px, float py, float qx, float qy) { return sub_rn(mul_rn(px, qy), mul_rn(py, qx)); }
 RFW_HD bool intersect_tri_wt(const float3 v0, const float3 v1, const float3 v2, const RayCtx& r, float& t_out, float& u_out, float& v_out) {
     const float3 A = v0 - r.o, B = v1 - r.o, C = v2 - r.o;
-    const float Akz = comp3(A, r.kz), Bkz = comp3(B, r.kz), Ckz = comp3(C, r.kz);
-    const float Ax = comp3(A, r.kx) - r.Sx * Akz, Ay = comp3(A, r.ky) - r.Sy * Akz;
-    const float Bx = comp3(B, r.kx) - r.Sx * Bkz, By = comp3(B, r.ky) - r.Sy * Bkz;
-    const float Cx = comp3(C, r.kx) - r.Sx * Ckz, Cy = comp3(C, r.ky) - r.Sy * Ckz;
-    float U = Cx * By - Cy * Bx;
-    float V = Ax * Cy - Ay * Cx;
-    float W = Bx * Ay - By * Ax;
-    if (U == 0.0f || V == 0.0f || W == 0.0f) {  // edge case: redo the edge functions in double
-        const double CxBy = (double)Cx * (double)By, CyBx = (double)Cy * (double)Bx;
-        U = (float)(CxBy - CyBx);
-        const double AxCy = (double)Ax * (double)Cy, AyCx = (double)Ay * (double)Cx;
-        V = (float)(AxCy - AyCx);
-        const double BxAy = (double)Bx * (double)Ay, ByAx = (double)By * (double)Ax;
-        W = (float)(BxAy - ByAx);
-    }
-    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+    const bool k0 = r.kz == 0, k1 = r.kz == 1;
+    const float Akz = comp_k0(A, k0, k1), Bkz = comp_k0(B, k0, k1), Ckz = comp_k0(C, k0, k1);
+    const float Ax = fmaf(-r.Sx, Akz, comp_k1(A, k0, k1)), Ay = fmaf(-r.Sy, Akz, comp_k2(A, k0, k1));
+    const float Bx = fmaf(-r.Sx, Bkz, comp_k1(B, k0, k1)), By = fmaf(-r.Sy, Bkz, comp_k2(B, k0, k1));
+    const float Cx = fmaf(-r.Sx, Ckz, comp_k1(C, k0, k1)), Cy = fmaf(-r.Sy, Ckz, comp_k2(C, k0, k1));
+    const float U = edge_fn(Cx, Cy, Bx, By);  // Cx*By - Cy*Bx
+    const float V = edge_fn(Ax, Ay, Cx, Cy);  // Ax*Cy - Ay*Cx
+    const float W = edge_fn(Bx, By, Ax, Ay);  // Bx*Ay - By*Ax
+    const float lo = fminf(fminf(U, V), W), hi = fmaxf(fmaxf(U, V), W);
+    if (lo < 0.0f && hi > 0.0f) return false;
     const float det = U + V + W;
     if (det == 0.0f) return false;
-    const float Az = r.Sz * Akz, Bz = r.Sz * Bkz, Cz = r.Sz * Ckz;
-    const float T = U * Az + V * Bz + W * Cz;
+    const float T = fmaf(W, Ckz, fmaf(V, Bkz, U * Akz)) * r.Sz;
     const float rdet = 1.0f / det;
     t_out = T * rdet;
     u_out = V * rdet;
@@ -231,8 +272,9 @@ RFW_HD bool trace_ray(const SceneView& sv, const float3 o, const float3 d, const
             if (RFW_NODE_HITS(ng)) { if (sp < STACK) stack[sp++] = ng; }
             const uint32_t slot = (uint32_t)(bit - 24) ^ (rc.octinv4 & 7u);
             const uint32_t rel = popc32(hits_imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
-            const float4* np = nodes + (size_t)(base + rel) * 5;
-            const float4 n0 = ldg(np + 0), n1 = ldg(np + 1), n2 = ldg(np + 2), n3 = ldg(np + 3), n4 = ldg(np + 4);
+            const float4* np = nodes + (size_t)(base + rel) * NODE_F4;
+            float4 n0, n1, n2, n3, n4;
+            load_wide_node(np, n0, n1, n2, n3, n4);
             if (COUNT) ctr->nodes++;
             const uint32_t hm = intersect_wide_node(n0, n1, n2, n3, n4, rc, tmin, hit.t);
             ng.x = f2u(n1.x);

@@ -54,7 +54,7 @@ static void emu_build(const std::vector<float4>& lo, const std::vector<float4>& 
     for (int i = 0; i < n - 1; i++) karras_body(i, n, skeys.data(), parent.data(), children.data(), range.data());
     for (int k = 0; k < n; k++) fit_cost_body(k, A, P);
 
-    out.nodes.assign((size_t)std::max(1, n) * 5, f4(0, 0, 0, 0));
+    out.nodes.assign((size_t)std::max(1, n) * NODE_F4, f4(0, 0, 0, 0));
     out.leaf_prims.assign(n, 0);
     uint32_t node_counter = 1, prim_counter = 0;
     CollapseOut O;
@@ -70,7 +70,7 @@ static void emu_build(const std::vector<float4>& lo, const std::vector<float4>& 
         c0 = c1;
         out.levels++;
     }
-    out.nodes.resize((size_t)node_counter * 5);
+    out.nodes.resize((size_t)node_counter * NODE_F4);
     out.sah = (n > 1 && cost[7] > 0) ? cost[0] / cost[7] : 0.f;
     if ((int)prim_counter != n) fprintf(stderr, "emu: prim_counter %u != n %d\n", prim_counter, n);
 }
@@ -146,7 +146,7 @@ void emu_build(void* s, float c_node, float c_prim, int pmax, uint64_t* stats) {
             m.ttris[(size_t)k * 3 + 1] = f4(t.vertex1[0], t.vertex1[1], t.vertex1[2], 0);
             m.ttris[(size_t)k * 3 + 2] = f4(t.vertex2[0], t.vertex2[1], t.vertex2[2], 0);
         }
-        tot_nodes += m.bvh.nodes.size() / 5;
+        tot_nodes += m.bvh.nodes.size() / NODE_F4;
     }
     sc.recs.clear();
     std::vector<float4> ilo, ihi;
@@ -188,7 +188,7 @@ void emu_build(void* s, float c_node, float c_prim, int pmax, uint64_t* stats) {
         sc.sv.tlas_nodes = sc.tlas.nodes.data();
         sc.sv.tlas_refs = sc.tlas.leaf_prims.data();
     }
-    if (stats) { stats[0] = tot_nodes; stats[1] = sc.tlas.nodes.size() / 5; stats[2] = sc.recs.size(); }
+    if (stats) { stats[0] = tot_nodes; stats[1] = sc.tlas.nodes.size() / NODE_F4; stats[2] = sc.recs.size(); }
 }
 
 void emu_trace(void* s, const RfwRay* rays, uint64_t n, RfwHit* hits, uint32_t* occluded, uint64_t* counters) {
@@ -215,7 +215,7 @@ int emu_validate(void* s, uint32_t mesh_id) {
     EmuScene& sc = *(EmuScene*)s;
     EmuMesh& m = sc.meshes[mesh_id];
     const int n = (int)m.tris.size();
-    const size_t nn = m.bvh.nodes.size() / 5;
+    const size_t nn = m.bvh.nodes.size() / NODE_F4;
     std::vector<int> seen(n, 0), node_seen(nn, 0);
     struct Item { uint32_t node; double lo[3], hi[3]; };
     std::vector<Item> stack;
@@ -227,7 +227,7 @@ int emu_validate(void* s, uint32_t mesh_id) {
         Item it = stack.back(); stack.pop_back();
         if (it.node >= nn) { errors++; continue; }
         if (node_seen[it.node]++) errors++;
-        const float4* np = &m.bvh.nodes[(size_t)it.node * 5];
+        const float4* np = &m.bvh.nodes[(size_t)it.node * NODE_F4];
         const uint32_t e_imask = f2u(np[0].w);
         const double sc3[3] = {ldexp(1.0, (int)(e_imask & 0xFF) - 127), ldexp(1.0, (int)((e_imask >> 8) & 0xFF) - 127), ldexp(1.0, (int)((e_imask >> 16) & 0xFF) - 127)};
         const double p[3] = {np[0].x, np[0].y, np[0].z};

@@ -112,3 +112,25 @@ def test_coincident_triangles_tie_break(emu):
     rays = np.zeros(1, wire.RAY); rays["origin"] = (0.2, 0.2, 1); rays["direction"] = (0, 0, -1); rays["tmin"] = 1e-4; rays["tmax"] = 1e26
     hits, _, _ = e.trace(rays)
     assert hits["inst"][0] == 0 and hits["prim"][0] == 0
+
+
+def test_authored_asset_precision(emu, oracle_mod):
+    """Primary rays at a distance of ~500 triangle sizes (CesiumMan, config C1): the triangle test's t and barycentrics
+    must stay within the parity tolerances there, not only on the unit-cube soups (a triangle test built on
+    un-projected triple products loses (distance / size)^2 ulps and fails this)."""
+    import os
+
+    from rfw_rs_b200 import gltf
+
+    gold_dir = os.path.join(HERE, "golden")
+    asset = gltf.load_npz(os.path.join(gold_dir, "cesium_man.npz"))
+    flat = gltf.flatten(asset)
+    w, h = 1280, 720
+    view = gltf.c1_camera(flat, w, h)
+    o = oracle_mod.OracleBackend(det_eps=0.0); flat.apply(o)
+    rays = np.ascontiguousarray(o.primary_rays(view, w, h).reshape(h, w)[::3, ::3].reshape(-1))
+    e = Emu(emu, flat)
+    hits, occ, _ = e.trace(rays)
+    ref = o.trace_closest(rays, mode=oracle_mod.MODE_BVH2)
+    assert (ref["inst"] >= 0).sum() > 5000
+    parity.compare_hits(rays, hits, ref, parity.lookup_from_desc(flat), "cesium_man/emu", max_fraction=1e-4)
