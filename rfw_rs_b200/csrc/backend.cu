@@ -98,6 +98,11 @@ int Backend::init() {
 Backend::~Backend() {
     DeviceScope device_scope(cfg.device);
     if (stream) cudaStreamSynchronize(stream);
+    for (BuilderContext* c : side_ctx) {
+        if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+        delete c;
+    }
+    side_ctx.clear();
     for (auto& m : meshes) {
         if (m.d_tris) cudaFree(m.d_tris);
         if (m.d_ttris) cudaFree(m.d_ttris);
@@ -500,23 +505,41 @@ int Backend::synchronize() {
         BK_CUDA(cudaEventRecord(ev0, stream), "event");
         const BuildParams blas_params{1.0f, sah_c_prim, sah_pmax, sah_treelet};
         std::set<uint32_t> rebuilt_meshes;
+        // many small dirty meshes: deal them onto the side contexts (see backend.h); big meshes fill the GPU on their own
+        int n_small = 0;
+        for (const MeshRec& m : meshes) n_small += (m.present && m.dirty && m.n > 0 && m.n <= (uint32_t)BUILD_DEFER_MAX) ? 1 : 0;
+        const int n_side = (n_small >= 4 && build_streams > 1) ? std::min(build_streams, n_small) : 0;
+        while ((int)side_ctx.size() < n_side) {
+            BuilderContext* c = new BuilderContext();
+            c->sm_count = sm_count;
+            if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return cuda_fail(cudaGetLastError(), "build stream"); }
+            side_ctx.push_back(c);
+        }
+        if (n_side) BK_CUDA(cudaStreamSynchronize(stream), "sync");  // uploads and frees issued on the main stream precede the side streams' work
+        int next_side = 0;
         for (MeshRec& m : meshes) {
             if (!m.present || !m.dirty) continue;
             rebuilt_meshes.insert((uint32_t)(&m - meshes.data()));
             if (m.d_ttris) { cudaFree(m.d_ttris); m.d_ttris = nullptr; }
             m.bvh.release();
             if (m.n) {
+                BuilderContext& bc = (n_side && m.n <= (uint32_t)BUILD_DEFER_MAX) ? *side_ctx[(next_side++) % n_side] : bctx;
+                cudaStream_t bs = bc.stream;
                 float4 *lo = nullptr, *hi = nullptr;
-                BK_CUDA(cudaMallocAsync(&lo, (size_t)m.n * sizeof(float4), stream), "box alloc");
-                BK_CUDA(cudaMallocAsync(&hi, (size_t)m.n * sizeof(float4), stream), "box alloc");
-                cudaError_t e = triangle_boxes(bctx, m.d_tris, (int)m.n, lo, hi);
-                if (e == cudaSuccess) e = build_wide_bvh(bctx, lo, hi, (int)m.n, blas_params, m.bvh, /*deferred=*/true);  // small meshes: no host sync per mesh
-                cudaFreeAsync(lo, stream); cudaFreeAsync(hi, stream);
+                BK_CUDA(cudaMallocAsync(&lo, (size_t)m.n * sizeof(float4), bs), "box alloc");
+                BK_CUDA(cudaMallocAsync(&hi, (size_t)m.n * sizeof(float4), bs), "box alloc");
+                cudaError_t e = triangle_boxes(bc, m.d_tris, (int)m.n, lo, hi);
+                if (e == cudaSuccess) e = build_wide_bvh(bc, lo, hi, (int)m.n, blas_params, m.bvh, /*deferred=*/true);  // small meshes: no host sync per mesh
+                cudaFreeAsync(lo, bs); cudaFreeAsync(hi, bs);
                 if (e != cudaSuccess) return cuda_fail(e, "BLAS build");
-                BK_CUDA(cudaMallocAsync(&m.d_ttris, (size_t)m.n * 3 * sizeof(float4), stream), "triangle alloc");
-                BK_CUDA(gather_traversal_triangles(bctx, m.d_tris, m.bvh.leaf_prims, (int)m.n, m.d_ttris), "gather triangles");
+                BK_CUDA(cudaMallocAsync(&m.d_ttris, (size_t)m.n * 3 * sizeof(float4), bs), "triangle alloc");
+                BK_CUDA(gather_traversal_triangles(bc, m.d_tris, m.bvh.leaf_prims, (int)m.n, m.d_ttris), "gather triangles");
             }
             m.dirty = false;
+        }
+        for (int k = 0; k < n_side; k++) {
+            BK_CUDA(finish_pending_builds(*side_ctx[k]), "BLAS build");
+            BK_CUDA(cudaStreamSynchronize(side_ctx[k]->stream), "BLAS build");
         }
         BK_CUDA(finish_pending_builds(bctx), "BLAS build");  // ONE sync for all deferred builds: node counts, bounds, SAH costs
         BK_CUDA(cudaEventRecord(ev1, stream), "event");
@@ -1322,6 +1345,7 @@ int Backend::set_option(const char* key, int64_t value) {
     else if (k == "streamed") streamed_enabled = value != 0;  // host-buffer entry points: single-launch streaming (1) or chunked pipeline (0)
     else if (k == "chunk_rays") chunk_rays = (uint64_t)std::max<int64_t>(1024, value);
     else if (k == "max_depth") cfg.max_depth = (uint32_t)value;
+    else if (k == "build_streams") build_streams = (int)std::min<int64_t>(16, std::max<int64_t>(1, value));
     else if (k == "sah_treelet_tlas") { sah_treelet_tlas = (int)value; scene_dirty = true; synchronized = false; }
     else if (k == "sah_treelet") { sah_treelet = (int)value; for (auto& m : meshes) if (m.present) m.dirty = true; scene_dirty = true; synchronized = false; }
     else if (k == "sah_c_prim_milli" || k == "sah_pmax") {  // SAH leaf cost (x1000) / max triangles per leaf slot (1..3)

@@ -111,7 +111,11 @@ public:
     RfwTraceStats trace_stats{};
     RfwRenderStats render_stats{};
     uint32_t sample_count = 0;
-    uint64_t launches() const { return launch_count + bctx.launches; }
+    uint64_t launches() const {
+        uint64_t n = launch_count + bctx.launches;
+        for (const BuilderContext* c : side_ctx) n += c->launches;
+        return n;
+    }
 
 private:
     int fail(int code, const std::string& msg);
@@ -127,6 +131,11 @@ private:
     int sm_count = 148;
     cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr, copy_poll = nullptr;
     BuilderContext bctx;
+    // Many small BLAS builds (an asset submitted as rfw does: one mesh per glTF primitive) are latency-bound chains of tiny
+    // kernels; they are dealt round-robin onto these extra builder contexts (own stream, scratch arena and result slots) so
+    // that several chains are in flight at once.  Option "build_streams" (default 8; 1 = everything on the main stream).
+    std::vector<BuilderContext*> side_ctx;
+    int build_streams = 8;
     TraceConfig tcfg;
     uint64_t launch_count = 0;
 

@@ -217,7 +217,8 @@ def camera_view(pos, direction, width, height, fov_deg=40.0, aperture=1e-4, foca
 
 
 def material(color=(0.8, 0.8, 0.8), metallic=0.0, roughness=1.0, specular_f=0.5, subsurface=0.0, specular=(1, 1, 1), transmission=0.0, eta=1.0,
-             clearcoat=0.0, clearcoat_gloss=0.0, diffuse_map=-1, normal_map=-1):
+             clearcoat=0.0, clearcoat_gloss=0.0, diffuse_map=-1, normal_map=-1, specular_tint=0.0, anisotropic=0.0, sheen=0.0, sheen_tint=0.0,
+             absorption=(0, 0, 0)):
     """into_device_material (material/list.rs:755-814): u8-packed Disney parameters, no textures."""
     def ch(f):
         return int(min(f * 255.0, 255.0)) & 255
@@ -228,7 +229,9 @@ def material(color=(0.8, 0.8, 0.8), metallic=0.0, roughness=1.0, specular_f=0.5,
     m = np.zeros(1, dtype=wire.DEVICE_MATERIAL)
     m["color"][0, :3] = color; m["color"][0, 3] = 1.0
     m["specular"][0, :3] = specular
-    m["parameters"][0] = [pk(metallic, subsurface, specular_f, roughness), pk(0, 0, 0, 0), pk(clearcoat, clearcoat_gloss, transmission, eta), 0]
+    m["absorption"][0, :3] = absorption
+    m["parameters"][0] = [pk(metallic, subsurface, specular_f, roughness), pk(specular_tint, anisotropic, sheen, sheen_tint),
+                          pk(clearcoat, clearcoat_gloss, transmission, eta), 0]
     for k in ("diffuse_map", "normal_map", "metallic_roughness_map", "emissive_map", "sheen_map"):
         m[k] = -1
     # MaterialProps flag bits (crates/rfw-scene/src/material/mod.rs:27-34): bit 0 diffuse map, bit 1 normal map
@@ -516,4 +519,54 @@ def textured_scene(grid=4, subdiv=2, seed=SEED_SCENE, tex_size=64, skybox=True):
     sc.meshes[3] = lt
     sc.instances[3] = to_column_major(lmats)
     sc.area_lights = np.concatenate(lights)
+    return sc
+
+
+# ---- punctual lights (crates/rfw-backend/src/lights.rs:100-108, 199-209, 293-301) ----------------------
+def _energy(radiance):
+    return float(np.linalg.norm(np.asarray(radiance, np.float64)))  # `energy = radiance.length()`, as AreaLight::new does (lights.rs:71-97)
+
+
+def point_light(position, radiance):
+    l = np.zeros(1, dtype=wire.POINT_LIGHT)
+    l["position"] = position; l["radiance"] = radiance; l["energy"] = _energy(radiance)
+    return l
+
+
+def spot_light(position, direction, inner_deg, outer_deg, radiance):
+    """SpotLight::new (lights.rs:239-259): angles in degrees, cosines of the angles as given, |radiance|, normalised direction."""
+    l = np.zeros(1, dtype=wire.SPOT_LIGHT)
+    l["position"] = position; l["direction"] = _norm(np.asarray(direction, np.float64)).astype(np.float32)
+    assert outer_deg > inner_deg
+    l["cos_inner"] = np.cos(np.radians(inner_deg)); l["cos_outer"] = np.cos(np.radians(outer_deg))
+    l["radiance"] = np.abs(radiance); l["energy"] = _energy(radiance)
+    return l
+
+
+def directional_light(direction, radiance):
+    l = np.zeros(1, dtype=wire.DIRECTIONAL_LIGHT)
+    l["direction"] = _norm(np.asarray(direction, np.float64)).astype(np.float32); l["radiance"] = radiance; l["energy"] = _energy(radiance)
+    return l
+
+
+def lights_and_lobes_scene(grid=6, subdiv=2, seed=SEED_SCENE, area_lights=2):
+    """Every light type of RandomPointOnLight (shade.comp:414-528: area, point, spot, directional, in that index order)
+    over instanced spheres whose 8 materials walk through the lobes of the Disney BSDF (disney.glsl:110-266): diffuse,
+    subsurface, GGX metal, tinted dielectric specular, clearcoat, rough and smooth transmission (with absorption)."""
+    sc = instanced_scene(grid=grid, subdiv=subdiv, seed=seed, n_lights=area_lights)
+    mats = [
+        material(color=(0.8, 0.3, 0.25), roughness=1.0),
+        material(color=(0.3, 0.7, 0.4), roughness=0.6, subsurface=0.8),
+        material(color=(0.9, 0.8, 0.5), metallic=1.0, roughness=0.3),
+        material(color=(0.3, 0.4, 0.9), roughness=0.35, specular_f=0.9, specular_tint=0.7),
+        material(color=(0.7, 0.2, 0.6), roughness=0.5, clearcoat=1.0, clearcoat_gloss=0.9),
+        material(color=(0.95, 0.95, 0.95), roughness=0.25, transmission=0.9, eta=0.66, absorption=(0.4, 0.1, 0.05)),
+        material(color=(0.9, 0.95, 1.0), roughness=0.05, transmission=1.0, eta=0.75),
+        material(color=(0.6, 0.6, 0.3), metallic=0.5, roughness=0.15, clearcoat=0.5, clearcoat_gloss=0.3, transmission=0.3, eta=0.8),
+    ]
+    sc.materials = np.concatenate(mats + [sc.materials[8:9], sc.materials[9:10]])
+    h = grid / 2
+    sc.point_lights = np.concatenate([point_light((-0.6 * h, 2.5, -0.5 * h), (30.0, 24.0, 18.0)), point_light((0.7 * h, 1.5, 0.4 * h), (10.0, 16.0, 28.0))])
+    sc.spot_lights = spot_light((0.0, 5.0, -0.8 * h), (0.1, -1.0, 0.35), 25.0, 50.0, (90.0, 90.0, 80.0))
+    sc.directional_lights = directional_light((0.4, -1.0, 0.3), (1.2, 1.1, 1.0))
     return sc

@@ -6,9 +6,16 @@ asset = gltf.load_npz(os.path.join(os.path.dirname(os.path.dirname(os.path.abspa
 desc = gltf.per_mesh(asset)
 be = backend.B200Backend(); desc.apply(be)
 print("cold", be.build_stats()["blas_build_ms"], "ms; meshes", be.build_stats()["num_meshes"], "launches", be.launch_count())
-for k in range(4):
+for k in range(8):
+    be.set_option("build_streams", 1 if k < 4 else int(os.environ.get("BUILD_STREAMS", 8)))  # first four: everything on the main stream
     l0 = be.launch_count()
     be.set_option("sah_treelet", 8); t0 = time.perf_counter(); be.synchronize(); dt = (time.perf_counter() - t0) * 1e3
     print(f"warm rebuild {k}: blas_build_ms {be.build_stats()['blas_build_ms']:.2f} (device events), synchronize wall {dt:.2f} ms, kernel launches {be.launch_count() - l0}")
 sizes = sorted(len(t) for t in desc.meshes.values())
+from rfw_rs_b200 import scenes
+rays = scenes.random_rays(1 << 18, lo=-1.0, hi=1.0)
+h8 = be.trace_closest(rays)
+be.set_option("build_streams", 1); be.set_option("sah_treelet", 8); be.synchronize()
+h1 = be.trace_closest(rays)
+print("hits identical across build_streams:", bool(np.array_equal(h1, h8)), "hit rate", float((h1["inst"] >= 0).mean()))
 print("mesh sizes: min", sizes[0], "median", sizes[len(sizes)//2], "max", sizes[-1])

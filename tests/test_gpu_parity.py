@@ -338,6 +338,31 @@ def test_wavefront_matches_oracle_rmse(B, oracle_mod):
     check_image(gpu.read_accumulator() / (spp + 4), ref2 / (spp + 4), "continued accumulation")
 
 
+def test_wavefront_all_light_types_and_lobes(B, oracle_mod):
+    """SURVEY §8 rows a6 / a15 / a16 in one image: thin-lens eye rays with a wide aperture (ray_gen.comp:124-141), every
+    branch of RandomPointOnLight (area, point, spot, directional: shade.comp:481-527) and every lobe of the Disney BSDF
+    (subsurface, tinted specular, clearcoat, rough / smooth transmission with absorption: disney.glsl:110-266).
+    tests/test_oracle.py::test_lobes_scene_uses_every_light_type_and_lobe shows each ingredient changes the image."""
+    desc = scenes.lights_and_lobes_scene()
+    w, h, spp, depth = 192, 108, 8, 5
+    view = scenes.camera_view((0, 3.0, -7.0), (0, -0.4, 1.0), w, h, aperture=0.05)
+    gpu, acc, ref, st = render_pair(B, oracle_mod, desc, view, w, h, spp, depth, sky=(0.1, 0.1, 0.15))
+    a, r = acc / spp, ref / spp
+    assert np.isfinite(a).all() and a.min() >= 0
+    assert r[..., :3].mean() > 0.05 and st["shadow_rays"] > 0.3 * w * h * spp
+    check_image(a, r, "lights+lobes radiance")
+    check_image(gpu.read_output(), np.sqrt(r), "lights+lobes sqrt image")
+    # each light type on its own (the light index space changes with the counts: :473-475)
+    for keep in ("point_lights", "spot_lights", "directional_lights"):
+        d2 = scenes.lights_and_lobes_scene()
+        for attr in ("area_lights", "point_lights", "spot_lights", "directional_lights"):
+            if attr != keep:
+                setattr(d2, attr, getattr(d2, attr)[:0])
+        _, acc2, ref2, st2 = render_pair(B, oracle_mod, d2, view, w, h, 4, 3, sky=(0.0, 0.0, 0.0))
+        assert st2["shadow_rays"] > 0 and ref2[..., :3].mean() > 1e-3, keep
+        check_image(acc2 / 4, ref2 / 4, keep)
+
+
 def test_wavefront_soup_with_many_lights(B, oracle_mod):
     """C4 flavour: soup + 64 emissive triangles, NEE any-hit rays."""
     desc = scenes.soup_with_lights(20000, 0.03, n_lights=64, light_area=0.05)

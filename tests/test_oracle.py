@@ -191,3 +191,81 @@ def test_render_smoke_energy(oracle_mod):
     # deterministic
     acc2, _ = o.render(view, 32, 18, spp=4, depth=3)
     assert np.array_equal(acc, acc2)
+
+
+def _wall_scene(kind, radiance=(2.0, 1.0, 0.5)):
+    """A Lambert wall at z = 1 facing the camera at the origin, lit by ONE punctual light sitting at the camera."""
+    sc = scenes.SceneDesc()
+    sc.meshes[0] = scenes.quad((0, 0, 1.0), (0, 0, -1), 4.0, 4.0, mat_id=0)
+    sc.instances[0] = scenes.to_column_major([scenes.identity()])
+    sc.materials = scenes.material(color=(0.5, 0.4, 0.3), roughness=1.0, specular_f=0.0)
+    if kind == "point":
+        sc.point_lights = scenes.point_light((0, 0, 0), radiance)
+    elif kind == "spot":
+        sc.spot_lights = scenes.spot_light((0, 0, 0), (0, 0, 1), 20.0, 40.0, radiance)
+    else:
+        sc.directional_lights = scenes.directional_light((0, 0, 1), radiance)
+    return sc
+
+
+def test_punctual_lights_known_answers(oracle_mod):
+    """RandomPointOnLight, point / spot / directional branches (shade.comp:496-527).  The three lights are placed so that
+    they are equivalent for the surface point straight ahead (distance 1, on the spot's axis, N.L = 1), where
+    lightPdf = dist^2/energy, dist^2/(falloff*energy) and 1/energy coincide: identical radiance.  Away from the axis
+    the same RNG streams give  spot/point = falloff(theta) = clamp((cos(theta) - cos_outer)/(cos_inner - cos_outer), 0, 1)
+    (:507-519) and  directional/point = dist^2 * cos(theta)/cos(theta) ... = |P|^2 (the point light's inverse-square term)."""
+    w = h = 257
+    view = scenes.camera_view((0, 0, 0), (0, 0, 1), w, h, fov_deg=90.0)
+    img = {}
+    for kind in ("point", "spot", "dir"):
+        o = oracle_mod.OracleBackend(); _wall_scene(kind).apply(o)
+        acc, st = o.render(view, w, h, spp=1, depth=1)
+        assert st["shadow_rays"] > 0.3 * w * h  # paths whose sampled bounce has pdf <= 1e-4 end before the light is sampled (shade.comp:208)
+        img[kind] = acc[..., :3].astype(np.float64)
+    c = (h // 2, w // 2)
+    assert img["point"][c].min() > 1e-3
+    np.testing.assert_allclose(img["spot"][c], img["point"][c], rtol=1e-5)
+    np.testing.assert_allclose(img["dir"][c], img["point"][c], rtol=2e-3)  # |P|^2 = 1 only at the exact centre of the pixel
+    # off-axis: pixel-centre geometry (the eye ray is jittered inside its pixel: tolerance = one pixel of angle)
+    rays = oracle_mod.OracleBackend().primary_rays(view, w, h)
+    d = rays["direction"].reshape(h, w, 3).astype(np.float64)
+    cos_t = d[..., 2]
+    ci, co = np.cos(np.radians(20.0)), np.cos(np.radians(40.0))
+    falloff = np.clip((cos_t - co) / (ci - co), 0.0, 1.0)
+    lit = img["point"][..., 0] > 1e-4
+    ratio = img["spot"][..., 0][lit] / img["point"][..., 0][lit]
+    assert np.abs(ratio - falloff[lit]).max() < 0.03
+    assert (falloff[lit] == 0).any() and (falloff[lit] == 1).any() and ((falloff[lit] > 0.2) & (falloff[lit] < 0.8)).any()
+    dist2 = 1.0 / cos_t ** 2  # |P|^2 for the wall at z = 1
+    # directional: N.L = 1 everywhere, no inverse-square term; point: N.L = cos(theta), 1/dist^2  =>  dir/point = dist^2 / cos(theta) * (bsdf ratio)
+    # the Lambert lobe with roughness 1 is not constant in the Disney model (Fd depends on N.L), so compare only near the axis
+    near = lit & (cos_t > np.cos(np.radians(6.0)))
+    r2 = img["dir"][..., 0][near] / img["point"][..., 0][near]
+    np.testing.assert_allclose(r2, (dist2 / cos_t)[near], rtol=0.03)
+
+
+def test_lobes_scene_uses_every_light_type_and_lobe(oracle_mod):
+    """The scene of the GPU parity test `test_wavefront_all_light_types_and_lobes` really exercises what it claims: removing
+    any one light type, or flattening the materials to Lambert, changes the image."""
+    w, h, spp, depth = 96, 54, 4, 4
+    view = scenes.camera_view((0, 3.0, -7.0), (0, -0.4, 1.0), w, h, aperture=0.05)
+
+    def render(sc):
+        o = oracle_mod.OracleBackend(); sc.apply(o)
+        acc, _ = o.render(view, w, h, spp, depth, sky=(0.1, 0.1, 0.15))
+        assert np.isfinite(acc).all() and acc.min() >= 0
+        return acc[..., :3] / spp
+
+    base = render(scenes.lights_and_lobes_scene())
+    for attr in ("point_lights", "spot_lights", "directional_lights", "area_lights"):
+        sc = scenes.lights_and_lobes_scene()
+        setattr(sc, attr, getattr(sc, attr)[:0])
+        assert np.abs(render(sc) - base).mean() > 1e-3, attr
+    sc = scenes.lights_and_lobes_scene()
+    for i in range(8):
+        sc.materials[i] = scenes.material(color=sc.materials[i]["color"][:3])[0]
+    assert np.abs(render(sc) - base).mean() > 1e-3
+    # thin-lens camera: a wide aperture changes the image, the default 1e-4 does not (ray_gen.comp:124-141)
+    o = oracle_mod.OracleBackend(); scenes.lights_and_lobes_scene().apply(o)
+    pin, _ = o.render(scenes.camera_view((0, 3.0, -7.0), (0, -0.4, 1.0), w, h), w, h, spp, depth, sky=(0.1, 0.1, 0.15))
+    assert np.abs(pin[..., :3] / spp - base).mean() > 1e-3
