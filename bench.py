@@ -38,7 +38,7 @@ CPU_SAMPLE_RAYS = 1 << 20
 
 def load_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed ncu capture."""
-    p = os.path.join(ROOT, "profiles", "r1b_traffic.json")  # refreshed with every ncu --set full capture of the kernel
+    p = os.path.join(ROOT, "profiles", "r1c_traffic.json")  # refreshed with every ncu --set full capture of the kernel
     try:
         return float(json.load(open(p))["traffic_bytes_per_launch"]) / 1e9
     except Exception:
@@ -56,49 +56,100 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe).  The timed region of the default
+    run is ~50 ms of kernels, shorter than one `nvidia-smi -lms` period, so the samples come from NVML directly (a thread
+    polling every ~2 ms; the traced calls release the GIL); nvidia-smi is the fallback when pynvml cannot be loaded."""
+
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index=0):
         self.index = index
-        self.rows = []
+        self.rows = []       # (sm MHz, max MHz, reasons bitmask)
         self.proc = None
+        self.nvml = None
+        self.handle = None
+        self.stop_flag = False
+        self.thread = None
+        self.source = None
 
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self._sample_nvml()
+            self.rows.clear()
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.source = "nvidia-smi"
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
         try:
-            self.proc.wait(timeout=2)
+            reasons = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
+            reasons = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        self.rows.append((sm, self.max_mhz, reasons))
+
+    def _poll_nvml(self):
+        while not self.stop_flag:
+            try:
+                self._sample_nvml()
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _read_smi(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                mask = 0
+                for (bit, _), v in zip(self.REASONS, f[3:7]):
+                    if v.lower().startswith("active"):
+                        mask |= bit
+                self.rows.append((float(f[0]), float(f[1]), mask))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source (pynvml and nvidia-smi unavailable)"], "samples": 0}
+        if self.source == "nvml":
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+        else:
+            time.sleep(0.05)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        rows = list(self.rows)
+        sm = [r[0] for r in rows]
+        mask = 0
+        for r in rows:
+            mask |= r[2]
+        reasons = sorted(name for bit, name in self.REASONS if mask & bit)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(r[1] for r in rows) if rows else None, "reasons": reasons, "samples": len(sm),
+                "source": self.source}
 
 
 def host_threads():
@@ -329,6 +380,10 @@ def main():
     value = world * args.steps * N_RAYS / (kernel_ms_max / 1e3) / 1e6
 
     # ---- e2e: host buffers through the C-ABI entry point ----------------------------------------------------
+    if os.environ.get("RFWB200_BENCH_STREAMED", "1") == "0":
+        # profiler runs only: ncu serialises kernels and copies, so the single persistent launch that consumes rays WHILE
+        # they are uploaded can never see its watermark advance; fall back to the chunked copy/launch pipeline there
+        be.set_option("streamed", 0)
     for _ in range(max(1, args.warmup - 1)):
         be.trace_closest(pin_rays.array, out=pin_hits.array)
     barrier()
@@ -364,13 +419,13 @@ def main():
         extra["l2_roofline"] = {"peak_GBps": l2_peak, "peak_source": "k_l2_read microbenchmark: 32 MiB buffer, L1-bypassing loads, same run",
                                 "achieved_GBps": trav_gbs, "frac": trav_gbs / l2_peak if l2_peak else None,
                                 "note": "traversal bytes = nodes/ray x 80 B + tris/ray x 48 B requested by the SMs; 45% of them hit in L1 (ncu), the rest go to L2"}
-        # issue-side roofline: the kernel is bound by warp-instruction issue, not by bytes (ncu: 73 % of the issue slots busy)
+        # issue-side roofline: the kernel is bound by warp-instruction issue, not by bytes (ncu: 70 % of the issue slots busy)
         try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r1b_traffic.json")))
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r1c_traffic.json")))
             ipr = prof["warp_instructions_per_launch"] / prof["rays_per_launch"]
             sms = torch.cuda.get_device_properties(0).multi_processor_count
             peak_issue = sms * 4 * (clocks.get("sm_mhz") or 1965.0) * 1e6   # 4 schedulers per SM, 1 warp instruction per clock each
-            extra["issue_roofline"] = {"warp_instructions_per_ray": ipr, "source": "ncu smsp__inst_executed.sum of the committed capture (profiles/r1b_trace_closest.md)",
+            extra["issue_roofline"] = {"warp_instructions_per_ray": ipr, "source": "ncu smsp__inst_executed.sum of the committed capture (profiles/r1c_trace_closest.md)",
                                        "achieved_Ginst_per_s": ipr * value / max(1, world) * 1e6 / 1e9, "peak_Ginst_per_s": peak_issue / 1e9,
                                        "frac": ipr * value / max(1, world) * 1e6 / peak_issue, "avg_active_threads_of_32": prof["avg_active_threads_per_warp_instruction"]}
         except Exception:
@@ -402,7 +457,7 @@ def main():
                     "note": "rfwb200_trace_closest with pinned host buffers: ONE persistent launch consumes rays as the upload lands them (device watermark) while completed 2^18-ray granules are downloaded (per-warp progress slots mirrored to the host); wall clock, max over ranks"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic(), "traffic_unit": "GB per launch (ncu dram__bytes_read+write, profiles/r1b_traffic.json)",
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic(), "traffic_unit": "GB per launch (ncu dram__bytes_read+write, profiles/r1c_traffic.json)",
                          "algorithmic_GB_per_launch": BYTES_PER_RAY_CLOSEST * N_RAYS / 1e9,
                          "kernel": "k_trace_persistent<RayBufferIO, closest, single-level>", "algorithmic_bytes_per_ray": BYTES_PER_RAY_CLOSEST, "peak_source": peak_src,
                          "note": "pointer-chasing traversal over an L2-resident BVH: the HBM fraction is small by construction (SURVEY 8d); see extra.traversal_bytes_per_ray for the L2-side traffic"},

@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
                 dn = 0;
                 ng = make_uint2(0u, 0x80000000u);
                 tg = make_uint2(0u, 0u);
-                if (sv.num_live == 0) {  // empty scene: nothing to traverse, the ray retires as a miss
+                if (sv.num_live == 0 || !ray_is_finite(xyz(r0), xyz(r1))) {  // empty scene / NaN or infinite ray: nothing to traverse, the ray retires as a miss
                     ng = make_uint2(0u, 0u);
                     rc.o = xyz(r0); rc.d = xyz(r1);
                     in_blas = false;

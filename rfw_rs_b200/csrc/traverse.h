@@ -87,6 +87,14 @@ RFW_HD float safe_rcp_dir(float d) {
     return 1.0f / (fabsf(d) > eps ? d : copysignf(eps, d));
 }
 
+// A ray with a NaN or infinite origin / direction component cannot hit anything (every comparison of the reference's
+// tests is false for it: intersection.glsl:19-30,125-129) — but the NaN-dropping min/max of the slab test below would
+// accept EVERY child box for it and walk the whole tree, so such rays retire as misses before traversal starts.
+// (Finite components whose absolute sum overflows float32, i.e. coordinates beyond 1e37, are treated the same way.)
+RFW_HD bool ray_is_finite(const float3 o, const float3 d) {
+    return (fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + fabsf(d.x) + fabsf(d.y) + fabsf(d.z)) < 3.0e38f;
+}
+
 RFW_HD void ray_setup_box(RayCtx& r) {
     r.idir = f3(safe_rcp_dir(r.d.x), safe_rcp_dir(r.d.y), safe_rcp_dir(r.d.z));
     const uint32_t octinv = (r.d.x < 0.0f ? 0u : 4u) | (r.d.y < 0.0f ? 0u : 2u) | (r.d.z < 0.0f ? 0u : 1u);
@@ -241,7 +249,7 @@ RFW_HD bool trace_ray(const SceneView& sv, const float3 o, const float3 d, const
     uint2 stack[STACK];
     int sp = 0;
     hit.inst = -1; hit.prim = -1; hit.t = tmax; hit.u = 0.0f; hit.v = 0.0f;
-    if (sv.num_live == 0) return false;
+    if (sv.num_live == 0 || !ray_is_finite(o, d)) return false;
     RayCtx rc;
     const float4* nodes;
     const float4* tris = nullptr;

@@ -85,6 +85,36 @@ def test_empty_and_ragged_inputs(B, oracle_mod):
         gpu.trace_closest(rays)
 
 
+def test_non_finite_rays_retire_as_misses(B, oracle_mod, torch_cuda):
+    """A whole batch of NaN / infinite rays must come back as misses at once (see traverse.h::ray_is_finite): without the
+    guard each of them is accepted by every node box and walks all 200 000 triangles."""
+    import time
+
+    desc = scenes.soup_scene(200000, 0.01)
+    gpu, cpu = make_pair(B, oracle_mod, desc)
+    rays = scenes.random_rays(1 << 16)
+    good_hits = gpu.trace_closest(rays)
+    bad = rays.copy()
+    k = np.arange(len(bad))
+    bad["origin"][k % 4 == 0, 0] = np.nan
+    bad["direction"][k % 4 == 1, 2] = np.nan
+    bad["origin"][k % 4 == 2, 1] = np.inf
+    bad["direction"][k % 4 == 3, 0] = -np.inf
+    bad[::64] = rays[::64]  # a few good rays in between
+    t0 = time.perf_counter()
+    h = gpu.trace_closest(bad)
+    occ = gpu.trace_any(bad)
+    assert time.perf_counter() - t0 < 2.0
+    isbad = np.ones(len(bad), bool); isbad[::64] = False
+    assert (h["inst"][isbad] == -1).all() and (h["prim"][isbad] == -1).all() and (occ[isbad] == 0).all()
+    assert np.array_equal(h["t"][isbad], bad["tmax"][isbad])
+    assert np.array_equal(h[::64], good_hits[::64])
+    ref = cpu.trace_closest(bad[:4096], mode=oracle_mod.MODE_BVH2)
+    assert np.array_equal(ref["inst"], h["inst"][:4096])
+    gpu.set_option("trace_variant", 1)  # the one-thread-per-ray form
+    assert np.array_equal(gpu.trace_closest(bad)["inst"], h["inst"])
+
+
 def test_soup_200k(B, oracle_mod):
     desc = scenes.soup_scene(200000, 0.01)
     gpu, cpu = make_pair(B, oracle_mod, desc)

@@ -105,6 +105,26 @@ def test_axis_aligned_and_degenerate_rays(emu, oracle_mod):
     assert np.allclose(hits["t"][[0, 1, 4]], [1, 1, 2])
 
 
+def test_non_finite_rays_retire_as_misses(emu, oracle_mod):
+    """NaN / infinite ray components: every comparison of the reference's tests is false for them (a miss).  The wide-node
+    test drops NaN slab operands, so without the guard of traverse.h such a ray would be accepted by every box and walk the
+    whole tree (a batch of them would stall the device for seconds)."""
+    desc = scenes.soup_scene(5000, 0.05)
+    e = Emu(emu, desc)
+    o = oracle_mod.OracleBackend(det_eps=0.0); desc.apply(o)
+    rays = scenes.random_rays(64)
+    good = rays.copy()
+    rays["origin"][0, 0] = np.nan; rays["direction"][1, 1] = np.nan; rays["origin"][2, 2] = np.inf; rays["direction"][3, 0] = -np.inf
+    rays["direction"][4] = 0.0
+    hits, occ, ctr = e.trace(rays)
+    ref = o.trace_closest(rays)
+    assert (hits["inst"][:5] == -1).all() and (ref["inst"][:5] == -1).all() and (occ[:5] == 0).all()
+    assert np.array_equal(hits["t"][:4], rays["tmax"][:4])
+    hits_good, _, ctr_good = e.trace(good)
+    assert np.array_equal(hits[5:], hits_good[5:])
+    assert ctr[0] <= ctr_good[0]  # the bad rays visit no nodes at all
+
+
 def test_coincident_triangles_tie_break(emu):
     t = scenes.make_triangles(np.zeros((3, 3), np.float32), np.tile([[1, 0, 0]], (3, 1)).astype(np.float32), np.tile([[0, 1, 0]], (3, 1)).astype(np.float32))
     desc = scenes.SceneDesc(); desc.meshes[0] = t; desc.instances[0] = scenes.to_column_major([scenes.identity(), scenes.identity()]); desc.materials = scenes.material()
