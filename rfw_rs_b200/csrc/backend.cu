@@ -1190,7 +1190,7 @@ int Backend::render_spp(const RfwCameraView3D* view, uint32_t spp, uint32_t dept
     if (materials.empty()) return fail(RFWB200_ERR_INVALID, "render: no materials set");
     const ShadeScene ss = shade_scene();
     wf.refill_below = tcfg.refill_below;
-    wf.tri_batch = tcfg.tri_batch; wf.tri_batch_two_level = tcfg.tri_batch_two_level; wf.tri_blocked = tcfg.tri_blocked;
+    wf.tri_batch = tcfg.tri_batch; wf.tri_batch_two_level = tcfg.tri_batch_two_level; wf.tri_blocked = tcfg.tri_blocked; wf.inst_batch = tcfg.inst_batch;
     const uint64_t before = wf.launches;
     BK_CUDA(wf.ensure_wave(wf.wave_spp_for(spp)), "wavefront queues");  // one-time (grow-only) allocation, outside the timed bracket
     BK_CUDA(cudaEventRecord(ev0, stream), "event");
@@ -1340,6 +1340,7 @@ int Backend::set_option(const char* key, int64_t value) {
     else if (k == "tri_batch") tcfg.tri_batch = (int)value;
     else if (k == "tri_batch_two_level") tcfg.tri_batch_two_level = (int)value;
     else if (k == "tri_blocked") tcfg.tri_blocked = (int)value;
+    else if (k == "inst_batch") tcfg.inst_batch = (int)std::max<int64_t>(1, value);
     else if (k == "min_blocks") tcfg.min_blocks = (int)value;
     else if (k == "l2_persist") { l2_persist_enabled = value != 0; if (!l2_persist_enabled) { cudaStreamAttrValue a{}; cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &a); cudaCtxResetPersistingL2Cache(); } else { if (l2_persist_max && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, l2_persist_max) != cudaSuccess) { cudaGetLastError(); l2_persist_max = 0; } update_l2_policy(); } }
     else if (k == "streamed") streamed_enabled = value != 0;  // host-buffer entry points: single-launch streaming (1) or chunked pipeline (0)

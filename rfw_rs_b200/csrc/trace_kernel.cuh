@@ -66,6 +66,7 @@ struct TraceTuning {
     int refill_below;  // refill when fewer than this many lanes still traverse
     int tri_batch;     // run the triangle phase when at least this many lanes have pending triangles ...
     int tri_blocked;   // ... or when this many of them cannot traverse any further until their triangles are tested
+    int inst_batch;    // two-level kernels: enter TLAS leaves (instances) when at least this many lanes wait at one
 };
 
 template <class IO, bool ANY, bool TWO_LEVEL, int THREADS, int MIN_BLOCKS, int SM_STACK>
@@ -223,29 +224,39 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
                     else { sts_u2(dq_base + (uint32_t)dn * (uint32_t)(THREADS * 8), tgn); dn++; }
                 }
             }
-            // (c) TLAS leaves are entered right away: cheap, and they only produce more node work
-            if (TWO_LEVEL && active && !in_blas && tg.y != 0u) {
-                const int tb = 31 - __clz((int)tg.y);
-                tg.y &= ~(1u << tb);
-                const InstanceRec* rec = sv.instances + __ldg(sv.tlas_refs + tg.x + (uint32_t)tb);
-                if (tg.y != 0u) RFW_STACK_PUSH(tg);
-                if (RFW_NODE_HITS(ng)) RFW_STACK_PUSH(ng);
-                blas_base_sp = sp;
-                in_blas = true;
-                cur_inst = rec->inst_id;
-                xform_ray(*rec, wo, wd, rc.o, rc.d);
-                ray_setup_box(rc);
-                ray_setup_tri(rc);
-                nodes = rec->nodes; tris = rec->tris;
-                ng = make_uint2(0u, 0x80000000u);
-                tg = make_uint2(0u, 0u);
+            // (c) TLAS leaves (instance entries) are BATCHED like the triangle tests: transforming the ray into object space and
+            // re-deriving its box / shear constants is ~180 instructions, and entered one lane at a time it ran at 4 of 32
+            // lanes in 94 % of the iterations of the C3 extend kernel (profiles/r1c_extend_two_level.md).  A lane that holds a
+            // TLAS leaf parks until `inst_batch` lanes do, or until no lane of the warp can take a node step.
+            if (TWO_LEVEL) {
+                const bool want_enter = active && !done && !in_blas && tg.y != 0u;
+                const uint32_t we = __ballot_sync(FULL, want_enter);
+                if (we != 0u) {
+                    const uint32_t can_step = __ballot_sync(FULL, active && !done && tg.y == 0u);
+                    if (((int)__popc(we) >= tune.inst_batch || can_step == 0u) && want_enter) {
+                        const int tb = 31 - __clz((int)tg.y);
+                        tg.y &= ~(1u << tb);
+                        const InstanceRec* rec = sv.instances + __ldg(sv.tlas_refs + tg.x + (uint32_t)tb);
+                        if (tg.y != 0u) RFW_STACK_PUSH(tg);
+                        if (RFW_NODE_HITS(ng)) RFW_STACK_PUSH(ng);
+                        blas_base_sp = sp;
+                        in_blas = true;
+                        cur_inst = rec->inst_id;
+                        xform_ray(*rec, wo, wd, rc.o, rc.d);
+                        ray_setup_box(rc);
+                        ray_setup_tri(rc);
+                        nodes = rec->nodes; tris = rec->tris;
+                        ng = make_uint2(0u, 0x80000000u);
+                        tg = make_uint2(0u, 0u);
+                    }
+                }
             }
             // (d) batched triangle phase
-            const bool pending = active && !done && tg.y != 0u;
+            const bool pending = active && !done && tg.y != 0u && (!TWO_LEVEL || in_blas);  // (lanes parked at a TLAS leaf are neither)
             const uint32_t pend = __ballot_sync(FULL, pending);
             if (pend != 0u) {
                 // lanes that can make traversal progress in the next iteration without their triangles being tested
-                const bool can_go = active && !done && (!pending || (DQ > 0 && dn < DQ && (RFW_NODE_HITS(ng) || sp > 0)));
+                const bool can_go = active && !done && ((!pending && tg.y == 0u) || (DQ > 0 && pending && dn < DQ && (RFW_NODE_HITS(ng) || sp > 0)));
                 const uint32_t can_node = __ballot_sync(FULL, can_go);
                 const int n_blocked = __popc(pend & ~can_node);
                 if ((int)__popc(pend) >= tune.tri_batch || (DQ > 0 && n_blocked >= tune.tri_blocked) || can_node == 0u) {

@@ -79,12 +79,28 @@ RFW_HD float sub_rn(float a, float b) {
 #endif
 }
 
+// Reciprocals of the ray set-up and of the triangle determinant: one MUFU.RCP (<= 1 ulp) on the device instead of the
+// IEEE-rounded division (range check + MUFU.RCP + 3 fix-up instructions + a slow-path call: ~12 instructions and a
+// divergent branch each; a ray set-up has four of them and runs at ~5 of 32 lanes).  What the tests need is consistency
+// per ray, not correct rounding: every slab of a ray uses the same idir, every triangle the same shear constants.  The
+// up-to-1-ulp scale error per axis is covered by the slab pad of intersect_wide_node (5 ulps).  -DRFW_IEEE_RCP restores
+// the divisions (A/B runs).
+RFW_HD float fast_rcp(float x) {
+#if defined(__CUDA_ARCH__) && !defined(RFW_IEEE_RCP)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+
 RFW_HD float safe_rcp_dir(float d) {
     // |d| below 2^-80 (incl. exact zeros of axis-parallel rays) is replaced by +-2^-80: with an infinite reciprocal
     // the quantised slab expression q*(s*idir) + (p-o)*idir turns into inf - inf = NaN for EVERY child, the slab
     // stops culling and such a ray walks the whole tree.  A huge finite reciprocal keeps the inside/outside sign.
     const float eps = 8.2718061e-25f;  // 2^-80
-    return 1.0f / (fabsf(d) > eps ? d : copysignf(eps, d));
+    return fast_rcp(fabsf(d) > eps ? d : copysignf(eps, d));
 }
 
 // A ray with a NaN or infinite origin / direction component cannot hit anything (every comparison of the reference's
@@ -111,7 +127,7 @@ RFW_HD void ray_setup_tri(RayCtx& r) {
     const bool k0 = kz == 0, k1 = kz == 1;
     // Woop et al. swap kx/ky when d[kz] < 0 to preserve the winding; without back-face culling the swap only flips the
     // sign of all three edge functions and of their sum, which the test below does not care about
-    const float rz = 1.0f / comp_k0(r.d, k0, k1);
+    const float rz = fast_rcp(comp_k0(r.d, k0, k1));
     r.kz = kz;
     r.Sx = comp_k1(r.d, k0, k1) * rz;
     r.Sy = comp_k2(r.d, k0, k1) * rz;
@@ -186,7 +202,7 @@ RFW_HD uint32_t intersect_wide_node(const float4 n0, const float4 n1, const floa
             const float tlz = fmaf(byte_to_float(zmin, j), aiz, aoz), thz = fmaf(byte_to_float(zmax, j), aiz, aoz);
             // fminf/fmaxf drop NaN operands (0 * inf): such a slab simply does not constrain
             const float cmin = fmaxf(fmaxf(tlx, tly), fmaxf(tlz, tmin));
-            const float cmax = fminf(fminf(thx, thy), fminf(thz, tmax)) * 1.0000004f;  // 2-ulp pad: conservative slabs
+            const float cmax = fminf(fminf(thx, thy), fminf(thz, tmax)) * 1.0000006f;  // 5-ulp pad: conservative slabs (FMA rounding + the <= 1 ulp of fast_rcp per axis)
             if (cmin <= cmax) hitmask |= ((child_bits4 >> sh) & 0xFFu) << ((bit_index4 >> sh) & 0xFFu);
         }
     }
@@ -219,7 +235,7 @@ RFW_HD bool intersect_tri_wt(const float3 v0, const float3 v1, const float3 v2, 
     const float det = U + V + W;
     if (det == 0.0f) return false;
     const float T = fmaf(W, Ckz, fmaf(V, Bkz, U * Akz)) * r.Sz;
-    const float rdet = 1.0f / det;
+    const float rdet = fast_rcp(det);
     t_out = T * rdet;
     u_out = V * rdet;
     v_out = W * rdet;

@@ -564,7 +564,7 @@ cudaError_t Wavefront::render(cudaStream_t stream, const SceneView& sv, const Sh
     const int shade_blocks = sm_count * 8;
     const uint32_t wave = wave_spp_for(spp);
     WF_CK(ensure_wave(wave));
-    const TraceTuning tune{refill_below, sv.two_level ? tri_batch_two_level : tri_batch, tri_blocked};
+    const TraceTuning tune{refill_below, sv.two_level ? tri_batch_two_level : tri_batch, tri_blocked, inst_batch};
     for (uint32_t s = 0; s < spp; s += wave) {
         FrameParams fp = make_params(*this, cam, first_sample + s, 0);
         fp.wave_spp = std::min(wave, spp - s);
@@ -596,7 +596,7 @@ cudaError_t Wavefront::debug_view(cudaStream_t stream, const SceneView& sv, cons
     if (max_paths == 0) return cudaSuccess;
     WF_CK(ensure_wave(1));
     FrameParams fp = make_params(*this, cam, 0, 0);
-    const TraceTuning tune{refill_below, sv.two_level ? tri_batch_two_level : tri_batch, tri_blocked};
+    const TraceTuning tune{refill_below, sv.two_level ? tri_batch_two_level : tri_batch, tri_blocked, inst_batch};
     WF_CK(cudaMemsetAsync(d_counts, 0, 8 * sizeof(uint32_t), stream));
     k_wf_generate_centre<<<(max_paths + 255) / 256, 256, 0, stream>>>(fp, d_owned_tiles, d_O[0], d_D[0], d_counts);
     ExtendIO eio{d_O[0], d_D[0], d_counts + 0, d_S};

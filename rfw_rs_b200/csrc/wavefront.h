@@ -68,7 +68,7 @@ struct Wavefront {
     std::vector<uint32_t> morton_tiles;
     int sm_count = 148;
     int refill_below = 28;
-    int tri_batch = 6, tri_batch_two_level = 6, tri_blocked = 4;
+    int tri_batch = 4, tri_batch_two_level = 6, tri_blocked = 4, inst_batch = 6;
     uint64_t launches = 0;
 
     cudaError_t configure(uint32_t w, uint32_t h, uint32_t tile_size, uint32_t rank_, uint32_t world_);

@@ -6,8 +6,11 @@ import csv
 import subprocess
 import sys
 
+import os
 rep = sys.argv[1]
-raw = list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout.splitlines()))
+# a report with several launches: NCU_LAUNCH=k selects the k-th (0-based)
+sel = ["--launch-skip", os.environ["NCU_LAUNCH"], "--launch-count", "1"] if "NCU_LAUNCH" in os.environ else []
+raw = list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"] + sel, capture_output=True, text=True).stdout.splitlines()))
 h, units, v = raw[0], raw[1], raw[-1]
 m = {n: (v[i], units[i]) for i, n in enumerate(h)}
 print(f"## {m['Kernel Name'][0][:150]}\n")
@@ -43,8 +46,18 @@ st = sorted(((float(m[k][0]), k) for k in m if "average_warps_issue_stalled" in 
 for val, k in st[:8]:
     print(f"- {k.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', '')}: {val:.2f}")
 
-src = list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout.splitlines()))
-hdr, data = src[1], src[2:]
+src = list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + sel, capture_output=True, text=True).stdout.splitlines()))
+# one section per launch: a "Kernel Name" row, the header row, then one row per SASS instruction
+sections, cur_sec = [], None
+for r in src:
+    if r and r[0] == "Kernel Name":
+        cur_sec = {"hdr": None, "rows": []}; sections.append(cur_sec)
+    elif cur_sec is not None and cur_sec["hdr"] is None:
+        cur_sec["hdr"] = r
+    elif cur_sec is not None and len(r) == len(cur_sec["hdr"]):
+        cur_sec["rows"].append(r)
+sec = sections[int(os.environ.get("NCU_LAUNCH", len(sections) - 1))]
+hdr, data = sec["hdr"], sec["rows"]
 ci = {n: i for i, n in enumerate(hdr)}
 tot_i = sum(float(r[ci["Instructions Executed"]] or 0) for r in data)
 tot_s = sum(float(r[ci["# Samples"]] or 0) for r in data)
