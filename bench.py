@@ -245,6 +245,16 @@ def path_tracing_extra(backend_mod, scenes, torch, rank, world, spp, dist):
         e1.record()
         torch.cuda.synchronize()
         gather_ms = e0.elapsed_time(e1)
+    # where the frame goes: one more (untimed) render with events between the stage launches
+    stage_ms = None
+    try:
+        be.set_option("stage_timing", 1)
+        be.reset_accumulator()
+        be.render_spp(view, spp, depth)
+        stage_ms = dict(zip(("generate", "extend", "shade", "connect", "reduce_and_bookkeeping"), [round(float(x), 3) for x in be.render_stats()["stage_ms"]]))
+        be.set_option("stage_timing", 0)
+    except Exception:
+        pass
     bs = be.build_stats()
     seg = float(tot[1].item())
     samples = float(tot[0].item())
@@ -254,7 +264,7 @@ def path_tracing_extra(backend_mod, scenes, torch, rank, world, spp, dist):
         "samples_per_s": samples / t_s, "Msamples_per_s": samples / t_s / 1e6, "render_ms": ms.item(), "extension_rays": seg, "shadow_rays": float(tot[2].item()),
         "Mrays_per_s_all_kinds": (seg + float(tot[2].item())) / t_s / 1e6, "mean_segments_per_sample": seg / max(1.0, samples),
         "hbm_roofline_frac_algorithmic": (seg * 320.0 / t_s) / 1e9 / load_peaks()[0] / max(1, world),
-        "gather_ms": gather_ms, "tlas_build_ms": bs["tlas_build_ms"], "blas_build_ms": bs["blas_build_ms"], "instances": bs["num_instances"],
+        "stage_ms_rank0": stage_ms, "gather_ms": gather_ms, "tlas_build_ms": bs["tlas_build_ms"], "blas_build_ms": bs["blas_build_ms"], "instances": bs["num_instances"],
     }
 
 

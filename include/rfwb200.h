@@ -289,6 +289,12 @@ typedef struct RfwRenderStats {
     uint64_t shadow_rays;
     uint64_t segments;
     float render_ms;
+    /* option "stage_timing" = 1: device time per wavefront stage of the last render_spp, CUDA events between the launches
+     * (generate, extend, shade, connect, reduce + bookkeeping); all zero when the option is off (the default: the events
+     * would sit between launches of the timed loop). */
+    float stage_ms[5];
+    uint32_t stage_timing;
+    uint32_t reserved;
 } RfwRenderStats;
 
 enum {

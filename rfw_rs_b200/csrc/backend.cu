@@ -109,7 +109,7 @@ Backend::~Backend() {
         m.bvh.release();
     }
     tlas.release();
-    d_instances.release(); d_inst_shading.release(); d_materials.release();
+    d_instances.release(); d_leaf_instances.release(); d_inst_shading.release(); d_materials.release();
     d_area.release(); d_point.release(); d_spot.release(); d_dir.release();
     d_rays.release(); d_hits.release(); d_occ.release();
     for (auto& sk : skins) sk.joints.release();
@@ -391,6 +391,16 @@ __global__ void __launch_bounds__(128) k_instance_prepare(const MeshEntry* __res
     live_flag[gid] = live ? 1u : 0u;
 }
 
+// instance records gathered into TLAS leaf-slot order: one record = 5 x 16 B
+__global__ void k_gather_instances(const InstanceRec* __restrict__ recs, const uint32_t* __restrict__ leaf_refs, uint32_t n, InstanceRec* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4* src = reinterpret_cast<const float4*>(recs + leaf_refs[i]);
+    float4* dst = reinterpret_cast<float4*>(out + i);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(InstanceRec) / 16); k++) dst[k] = src[k];
+}
+
 // rank = exclusive scan of live_flag; out[3] = {live count, identity flag of the last live slot, ...}
 __global__ void __launch_bounds__(128) k_instance_compact(uint32_t n_slots, const uint32_t* __restrict__ live_flag, const uint32_t* __restrict__ rank,
                                                           const uint32_t* __restrict__ identity_flag, const InstanceRec* __restrict__ recs_in,
@@ -668,6 +678,12 @@ int Backend::synchronize() {
             if (live > 1) {
                 const BuildParams tlas_params{1.0f, 4.0f, 1, sah_treelet_tlas};
                 e = build_wide_bvh(bctx, lo, hi, (int)live, tlas_params, tlas, /*deferred=*/true);
+                if (e == cudaSuccess) e = d_leaf_instances.reserve(live);
+                if (e == cudaSuccess) {  // instance records in leaf-slot order (the leaf_prims pointer is valid stream-ordered)
+                    k_gather_instances<<<(live + 127) / 128, 128, 0, stream>>>(d_instances.ptr, tlas.leaf_prims, live, d_leaf_instances.ptr);
+                    launch_count++;
+                    e = cudaGetLastError();
+                }
             }
             cudaFreeAsync(tmp_recs, stream); cudaFreeAsync(tmp_lo, stream); cudaFreeAsync(tmp_hi, stream);
             cudaFreeAsync(lo, stream); cudaFreeAsync(hi, stream); cudaFreeAsync(flags, stream);
@@ -678,6 +694,7 @@ int Backend::synchronize() {
         sv.tlas_nodes = tlas.nodes;
         sv.tlas_refs = tlas.leaf_prims;
         sv.instances = d_instances.ptr;
+        sv.leaf_instances = live > 1 ? d_leaf_instances.ptr : d_instances.ptr;
         sv.two_level = live > 1 ? 1 : 0;
         sv.single_identity = single_identity ? 1 : 0;
         sv.num_live = (int)live;
@@ -1213,6 +1230,8 @@ int Backend::render_spp(const RfwCameraView3D* view, uint32_t spp, uint32_t dept
     render_stats.extension_rays = st[0];  // cumulative since the last reset
     render_stats.shadow_rays = st[1];
     render_stats.segments = st[2];
+    render_stats.stage_timing = wf.stage_timing ? 1u : 0u;
+    BK_CUDA(wf.stage_times(render_stats.stage_ms), "stage times");
     return RFWB200_OK;
 }
 
@@ -1340,6 +1359,7 @@ int Backend::set_option(const char* key, int64_t value) {
     else if (k == "tri_batch") tcfg.tri_batch = (int)value;
     else if (k == "tri_batch_two_level") tcfg.tri_batch_two_level = (int)value;
     else if (k == "tri_blocked") tcfg.tri_blocked = (int)value;
+    else if (k == "stage_timing") wf.stage_timing = value != 0;
     else if (k == "inst_batch") tcfg.inst_batch = (int)std::max<int64_t>(1, value);
     else if (k == "min_blocks") tcfg.min_blocks = (int)value;
     else if (k == "l2_persist") { l2_persist_enabled = value != 0; if (!l2_persist_enabled) { cudaStreamAttrValue a{}; cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &a); cudaCtxResetPersistingL2Cache(); } else { if (l2_persist_max && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, l2_persist_max) != cudaSuccess) { cudaGetLastError(); l2_persist_max = 0; } update_l2_policy(); } }

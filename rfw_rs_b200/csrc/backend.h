@@ -164,6 +164,7 @@ private:
 
     DeviceBvh tlas;
     DeviceArray<InstanceRec> d_instances;
+    DeviceArray<InstanceRec> d_leaf_instances;  // d_instances gathered into TLAS leaf order (SceneView::leaf_instances)
     DeviceArray<InstanceShading> d_inst_shading;  // indexed by GLOBAL instance id
     DeviceArray<struct MeshEntry> d_mesh_table;   // per mesh id: BLAS pointers, bounds, first instance slot
     DeviceArray<float> d_matrices;                // all instance lists' matrices, slot order

@@ -16,7 +16,7 @@ struct TraceConfig {
     int variant = TRACE_VARIANT_PERSISTENT;
     int blocks_per_sm = 0;   // 0 = as many as fit
     int refill_below = 28;   // refill idle lanes when fewer than this many lanes of a warp are traversing
-    int tri_batch_two_level = 6;  // two-level kernels: triangle phase when this many lanes have pending triangles
+    int tri_batch_two_level = 4;  // two-level kernels: triangle phase when this many lanes have pending triangles
     int tri_blocked = 4;     // speculative traversal only (PT_DEFER > 0): ... or when this many lanes cannot traverse any further
     int inst_batch = 6;      // two-level kernels: enter instances when this many lanes wait at a TLAS leaf (trace_kernel.cuh, step c)
     int tri_batch = 4;       // single-level kernels: run the triangle phase when this many lanes have pending leaf triangles

@@ -48,7 +48,24 @@ __device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
     return v;
 }
+__device__ __forceinline__ void sts_f4(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 static constexpr int PT_L_STACK = 24;
+// Two-level kernels keep the WORLD-space ray of every lane in shared memory (3 x float4 [vector][thread]: origin,
+// direction, reciprocal direction, octant word) instead of six live registers: it is needed only when a lane enters an
+// instance (object-space transform) and when it leaves one — where the three loads also replace re-deriving the slab
+// constants (3 reciprocals + octant) at ~4 of 32 lanes.
+static constexpr int PT_WORLD_RAY_F4 = 3;
+template <bool TWO_LEVEL>
+constexpr size_t persistent_smem_bytes() {
+    return (size_t)(PT_SM_STACK + PT_DEFER) * PT_THREADS * sizeof(uint2) + (TWO_LEVEL ? (size_t)PT_WORLD_RAY_F4 * PT_THREADS * sizeof(float4) : 0);
+}
 #define RFW_STACK_PUSH(v)                                                                   \
     do {                                                                                    \
         if (sp < SM_STACK) sts_u2(st_base + (uint32_t)sp * (uint32_t)(THREADS * 8), (v));  \
@@ -83,9 +100,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
     bool active = false;
     bool more = true;
     uint32_t ray_idx = 0;
-    float3 wo = f3(0, 0, 0), wd = f3(0, 0, 0);  // world-space ray (two-level variant only)
     RayCtx rc;
-    rc.o = wo; rc.d = wd; rc.idir = wo; rc.octinv4 = 0; rc.kz = 2; rc.Sx = rc.Sy = rc.Sz = 0.0f;
+    rc.o = f3(0, 0, 0); rc.d = rc.o; rc.idir = rc.o; rc.octinv4 = 0; rc.kz = 2; rc.Sx = rc.Sy = rc.Sz = 0.0f;
     float tmin = 0.0f;
     Hit hit;
     hit.inst = -1; hit.prim = -1; hit.t = 0.0f; hit.u = hit.v = 0.0f;
@@ -103,6 +119,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
     // refer to the object-space ray of an instance the lane may have left.
     constexpr int DQ = TWO_LEVEL ? 0 : PT_DEFER;
     const uint32_t dq_base = st_base + (uint32_t)(SM_STACK * THREADS * 8);
+    // world-space ray of this lane (two-level kernels): vectors 0..2 at wr_base + k * THREADS * 16
+    const uint32_t wr_base = (uint32_t)__cvta_generic_to_shared(smem_stack) + (uint32_t)((SM_STACK + PT_DEFER) * THREADS * 8) + threadIdx.x * 16u;
     int dn = 0;  // groups set aside
     // host-streamed policy only (folds away elsewhere): a lane that owns ray index `ray_idx` whose ray has not been
     // uploaded yet is "waiting", encoded as sp == -1 (no extra register: this kernel sits at its 64-register budget)
@@ -158,8 +176,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
                     in_blas = false;
                     blas_base_sp = 0;
                 } else if (TWO_LEVEL) {
-                    wo = xyz(r0); wd = xyz(r1);
-                    rc.o = wo; rc.d = wd;
+                    rc.o = xyz(r0); rc.d = xyz(r1);
                     nodes = sv.tlas_nodes;
                     in_blas = false;
                     blas_base_sp = 0;
@@ -172,6 +189,11 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
                     ray_setup_tri(rc);
                 }
                 ray_setup_box(rc);
+                if (TWO_LEVEL) {
+                    sts_f4(wr_base, make_float4(rc.o.x, rc.o.y, rc.o.z, rc.d.x));
+                    sts_f4(wr_base + (uint32_t)(THREADS * 16), make_float4(rc.d.y, rc.d.z, rc.idir.x, rc.idir.y));
+                    sts_f4(wr_base + (uint32_t)(2 * THREADS * 16), make_float4(rc.idir.z, __uint_as_float(rc.octinv4), 0.0f, 0.0f));
+                }
             }
             any_waiting = IO::kReportsProgress && __ballot_sync(FULL, RFW_WAITING) != 0u;
             if (__ballot_sync(FULL, active) == 0u) {
@@ -188,10 +210,11 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
                 uint2 tgn = make_uint2(0u, 0u);  // leaf group found in this step
                 // (a) nothing at hand: pop (leaving the BLAS when its part of the stack is exhausted)
                 if (!RFW_NODE_HITS(ng)) {
-                    if (TWO_LEVEL && in_blas && sp == blas_base_sp) {
+                    if (TWO_LEVEL && in_blas && sp == blas_base_sp) {  // BLAS exhausted: back to the world-space ray
                         in_blas = false;
-                        rc.o = wo; rc.d = wd;
-                        ray_setup_box(rc);
+                        const float4 w0 = lds_f4(wr_base), w1 = lds_f4(wr_base + (uint32_t)(THREADS * 16)), w2 = lds_f4(wr_base + (uint32_t)(2 * THREADS * 16));
+                        rc.o = f3(w0.x, w0.y, w0.z); rc.d = f3(w0.w, w1.x, w1.y);
+                        rc.idir = f3(w1.z, w1.w, w2.x); rc.octinv4 = __float_as_uint(w2.y);
                         nodes = sv.tlas_nodes;
                     }
                     if (sp == 0) {
@@ -236,13 +259,14 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
                     if (((int)__popc(we) >= tune.inst_batch || can_step == 0u) && want_enter) {
                         const int tb = 31 - __clz((int)tg.y);
                         tg.y &= ~(1u << tb);
-                        const InstanceRec* rec = sv.instances + __ldg(sv.tlas_refs + tg.x + (uint32_t)tb);
+                        const InstanceRec* rec = sv.leaf_instances + (tg.x + (uint32_t)tb);
                         if (tg.y != 0u) RFW_STACK_PUSH(tg);
                         if (RFW_NODE_HITS(ng)) RFW_STACK_PUSH(ng);
                         blas_base_sp = sp;
                         in_blas = true;
                         cur_inst = rec->inst_id;
-                        xform_ray(*rec, wo, wd, rc.o, rc.d);
+                        const float4 w0 = lds_f4(wr_base), w1 = lds_f4(wr_base + (uint32_t)(THREADS * 16));
+                        xform_ray(*rec, f3(w0.x, w0.y, w0.z), f3(w0.w, w1.x, w1.y), rc.o, rc.d);
                         ray_setup_box(rc);
                         ray_setup_tri(rc);
                         nodes = rec->nodes; tris = rec->tris;
@@ -297,7 +321,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
 template <class IO, bool ANY, bool TWO_LEVEL, int MIN_BLOCKS>
 static cudaError_t persistent_grid_mb(int sm_count, int blocks_per_sm_limit, uint32_t n_hint, int& grid_out) {
     auto kern = k_trace_persistent<IO, ANY, TWO_LEVEL, PT_THREADS, MIN_BLOCKS, PT_SM_STACK>;
-    const size_t smem = (size_t)(PT_SM_STACK + PT_DEFER) * PT_THREADS * sizeof(uint2);
+    const size_t smem = persistent_smem_bytes<TWO_LEVEL>();
     static int bps = 0;  // one static per template instantiation
     if (bps == 0) {
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, PT_THREADS, smem);
@@ -318,7 +342,7 @@ template <class IO, bool ANY, bool TWO_LEVEL, int MIN_BLOCKS>
 static cudaError_t launch_persistent_mb(cudaStream_t stream, int sm_count, int blocks_per_sm_limit, TraceTuning tune, const SceneView& sv, const IO& io, uint32_t n_hint,
                                         uint32_t* counter) {
     auto kern = k_trace_persistent<IO, ANY, TWO_LEVEL, PT_THREADS, MIN_BLOCKS, PT_SM_STACK>;
-    const size_t smem = (size_t)(PT_SM_STACK + PT_DEFER) * PT_THREADS * sizeof(uint2);
+    const size_t smem = persistent_smem_bytes<TWO_LEVEL>();
     int grid = 1;
     cudaError_t e = persistent_grid_mb<IO, ANY, TWO_LEVEL, MIN_BLOCKS>(sm_count, blocks_per_sm_limit, n_hint, grid);
     if (e != cudaSuccess) return e;
@@ -332,15 +356,15 @@ static cudaError_t launch_persistent_mb(cudaStream_t stream, int sm_count, int b
 #define RFW_PT_MIN_BLOCKS 8
 #endif
 #ifndef RFW_PT_MIN_BLOCKS_TL
-#define RFW_PT_MIN_BLOCKS_TL 7
+#define RFW_PT_MIN_BLOCKS_TL 8
 #endif
 
 template <class IO, bool ANY, bool TWO_LEVEL>
 static cudaError_t launch_persistent_io(cudaStream_t stream, int sm_count, int blocks_per_sm_limit, TraceTuning tune, const SceneView& sv, const IO& io, uint32_t n_hint,
                                         uint32_t* counter) {
-    // single-level: 64 registers / 32 warps per SM (measured best on C2); the two-level variant carries the world-space
-    // ray and the instance context as well and spills at 64: 72 registers / 28 warps per SM (C3: 605 Msamples/s, vs 586
-    // at 80 registers / 24 warps and 592 at 64 registers with spills)
+    // 64 registers / 32 warps per SM for both forms (measured best on C2 and C3).  The two-level variant used to carry the
+    // world-space ray in six registers (72 registers, 28 warps per SM; it spilled at 64); with that ray in shared memory
+    // it fits 64 registers without spills: C3 725 -> 737 Msamples/s.
     return launch_persistent_mb<IO, ANY, TWO_LEVEL, (TWO_LEVEL ? RFW_PT_MIN_BLOCKS_TL : RFW_PT_MIN_BLOCKS)>(stream, sm_count, blocks_per_sm_limit, tune, sv, io, n_hint, counter);
 }
 template <class IO, bool ANY, bool TWO_LEVEL>

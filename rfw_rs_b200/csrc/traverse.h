@@ -44,6 +44,8 @@ struct SceneView {
     const float4* tlas_nodes;
     const uint32_t* tlas_refs;      // TLAS leaf slots -> index into `instances`
     const InstanceRec* instances;
+    const InstanceRec* leaf_instances;  // the same records in TLAS leaf-slot order (leaf_instances[k] = instances[tlas_refs[k]]): the
+                                        // persistent kernels enter an instance without the dependent tlas_refs load
     int two_level;                  // 0: exactly one live instance, traced directly
     int single_identity;            // single instance has an identity transform
     int num_live;

@@ -479,6 +479,8 @@ void Wavefront::release() {
     fr(d_S); fr(d_shO); fr(d_shD); fr(d_shE); fr(d_partial); fr(d_accum); fr(d_output); fr(d_counts); fr(d_stats);
     max_paths = 0;
     wave_capacity = 0;
+    for (cudaEvent_t e : stage_events) cudaEventDestroy(e);
+    stage_events.clear(); stage_marks.clear(); stage_used = 0;
 }
 
 cudaError_t Wavefront::configure(uint32_t w, uint32_t h, uint32_t tile_size, uint32_t rank_, uint32_t world_) {
@@ -559,12 +561,36 @@ cudaError_t Wavefront::clear(cudaStream_t stream) {
     return cudaSuccess;
 }
 
+cudaError_t Wavefront::stage_mark(cudaStream_t stream, int stage) {
+    if (!stage_timing) return cudaSuccess;
+    if (stage_used == stage_events.size()) {
+        cudaEvent_t e;
+        WF_CK(cudaEventCreate(&e));
+        stage_events.push_back(e);
+    }
+    WF_CK(cudaEventRecord(stage_events[stage_used++], stream));
+    stage_marks.push_back(stage);
+    return cudaSuccess;
+}
+
+cudaError_t Wavefront::stage_times(float out_ms[5]) {
+    for (int k = 0; k < 5; k++) out_ms[k] = 0.0f;
+    for (size_t i = 1; i < stage_used; i++) {
+        float ms = 0.0f;
+        WF_CK(cudaEventElapsedTime(&ms, stage_events[i - 1], stage_events[i]));
+        out_ms[stage_marks[i]] += ms;
+    }
+    return cudaSuccess;
+}
+
 cudaError_t Wavefront::render(cudaStream_t stream, const SceneView& sv, const ShadeScene& ss, const RfwCameraView3D& cam, uint32_t first_sample, uint32_t spp, uint32_t depth) {
     if (max_paths == 0) return cudaSuccess;
     const int shade_blocks = sm_count * 8;
     const uint32_t wave = wave_spp_for(spp);
     WF_CK(ensure_wave(wave));
     const TraceTuning tune{refill_below, sv.two_level ? tri_batch_two_level : tri_batch, tri_blocked, inst_batch};
+    stage_used = 0; stage_marks.clear();
+    WF_CK(stage_mark(stream, 4));
     for (uint32_t s = 0; s < spp; s += wave) {
         FrameParams fp = make_params(*this, cam, first_sample + s, 0);
         fp.wave_spp = std::min(wave, spp - s);
@@ -572,22 +598,27 @@ cudaError_t Wavefront::render(cudaStream_t stream, const SceneView& sv, const Sh
         WF_CK(cudaMemsetAsync(d_counts, 0, 8 * sizeof(uint32_t), stream));
         k_wf_generate<<<(cap + 255) / 256, 256, 0, stream>>>(fp, d_owned_tiles, d_O[0], d_D[0], d_counts);
         launches++;
+        WF_CK(stage_mark(stream, 0));
         for (uint32_t b = 0; b < depth; b++) {
             const int cur = b & 1, nxt = cur ^ 1;
             fp.path_length = b;
             ExtendIO eio{d_O[cur], d_D[cur], d_counts + cur, d_S};
             if (sv.two_level) WF_CK((launch_persistent_io<ExtendIO, false, true>(stream, sm_count, 0, tune, sv, eio, cap, d_counts + 3)));
             else WF_CK((launch_persistent_io<ExtendIO, false, false>(stream, sm_count, 0, tune, sv, eio, cap, d_counts + 3)));
+            WF_CK(stage_mark(stream, 1));
             k_wf_shade<<<shade_blocks, 128, 0, stream>>>(fp, ss, d_S, d_O[cur], d_D[cur], d_T[cur], d_O[nxt], d_D[nxt], d_T[nxt], d_shO, d_shD, d_shE,
                                                          reinterpret_cast<float*>(d_partial), d_counts + cur, d_counts + nxt, d_counts + 2);
+            WF_CK(stage_mark(stream, 2));
             ConnectIO cio{d_shO, d_shD, d_shE, d_counts + 2, reinterpret_cast<float*>(d_partial)};
             if (sv.two_level) WF_CK((launch_persistent_io<ConnectIO, true, true>(stream, sm_count, 0, tune, sv, cio, cap, d_counts + 4)));
             else WF_CK((launch_persistent_io<ConnectIO, true, false>(stream, sm_count, 0, tune, sv, cio, cap, d_counts + 4)));
+            WF_CK(stage_mark(stream, 3));
             k_wf_advance<<<1, 1, 0, stream>>>(d_counts, d_stats, cur);
             launches += 4;
         }
         k_wf_reduce<<<(max_paths + 255) / 256, 256, 0, stream>>>(fp, d_owned_tiles, d_partial, d_accum);
         launches++;
+        WF_CK(stage_mark(stream, 4));
     }
     return cudaGetLastError();
 }

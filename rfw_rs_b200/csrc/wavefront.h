@@ -68,8 +68,15 @@ struct Wavefront {
     std::vector<uint32_t> morton_tiles;
     int sm_count = 148;
     int refill_below = 28;
-    int tri_batch = 4, tri_batch_two_level = 6, tri_blocked = 4, inst_batch = 6;
+    int tri_batch = 4, tri_batch_two_level = 4, tri_blocked = 4, inst_batch = 6;
     uint64_t launches = 0;
+    // per-stage device time (option "stage_timing"): events between the launches of render(), summed per stage by stage_times()
+    bool stage_timing = false;
+    std::vector<cudaEvent_t> stage_events;   // pool
+    std::vector<int> stage_marks;            // stage id of the interval ENDING at event i+1 (0 generate, 1 extend, 2 shade, 3 connect, 4 reduce/bookkeeping)
+    size_t stage_used = 0;
+    cudaError_t stage_mark(cudaStream_t stream, int stage);
+    cudaError_t stage_times(float out_ms[5]);   // call after the stream has been synchronised
 
     cudaError_t configure(uint32_t w, uint32_t h, uint32_t tile_size, uint32_t rank_, uint32_t world_);
     void release();

@@ -124,11 +124,12 @@ class CTraceStats(C.Structure):
 
 
 class CRenderStats(C.Structure):
-    _fields_ = [("samples", C.c_uint64), ("extension_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("segments", C.c_uint64), ("render_ms", C.c_float)]
+    _fields_ = [("samples", C.c_uint64), ("extension_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("segments", C.c_uint64), ("render_ms", C.c_float),
+                ("stage_ms", C.c_float * 5), ("stage_timing", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 def stats_to_dict(s):
-    return {name: getattr(s, name) for name, _ in s._fields_}
+    return {name: (list(getattr(s, name)) if isinstance(getattr(s, name), C.Array) else getattr(s, name)) for name, *_ in s._fields_}
 
 
 class CSkinData(C.Structure):

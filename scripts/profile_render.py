@@ -12,4 +12,8 @@ be.render_spp(view, 1, depth); be.reset_accumulator()
 for _ in range(int(os.environ.get("REPS", 2))):
     be.reset_accumulator(); be.render_spp(view, spp, depth)
     rs = be.render_stats(); print(rs, "Msamples/s", rs["samples"] / rs["render_ms"] / 1e3, "Mrays/s", (rs["extension_rays"] + rs["shadow_rays"]) / rs["render_ms"] / 1e3)
+if os.environ.get("STAGES", "1") == "1":
+    be.set_option("stage_timing", 1); be.reset_accumulator(); be.render_spp(view, spp, depth); rs = be.render_stats()
+    print("stage ms [generate, extend, shade, connect, reduce+bookkeeping]:", [round(x, 3) for x in rs["stage_ms"]], "sum", round(sum(rs["stage_ms"]), 3), "render_ms", round(rs["render_ms"], 3))
+    be.set_option("stage_timing", 0)
 if os.environ.get("L2", "0") == "1": print("l2 read GB/s", be.measure_l2_read_gbs(32 << 20, 50), "64MB:", be.measure_l2_read_gbs(64 << 20, 30), "512MB (HBM):", be.measure_l2_read_gbs(512 << 20, 5))
