@@ -17,6 +17,13 @@ namespace rfw {
 #define RFW_INV2PI (1.0f / (2.0f * RFW_PI))
 
 // ---- random.glsl:5-23 --------------------------------------------------------------------------
+// The two BSDF evaluations of a shaded segment (sampled direction, light direction) share ONE copy of bsdf_eval / bsdf_pdf
+// when RFW_SHADE_NOINLINE is set: the shade kernel's top stall is instruction fetch (4 096 SASS instructions).
+#if defined(RFW_SHADE_NOINLINE)
+#define RFW_SHADE_FN __device__ __noinline__
+#else
+#define RFW_SHADE_FN __device__
+#endif
 __device__ __forceinline__ uint32_t wang_hash(uint32_t s) {
     s = (s ^ 61u) ^ (s >> 16u);
     s *= 9u;
@@ -132,7 +139,7 @@ __device__ __forceinline__ float3 safe_normalize(float3 a) {  // :80-87
     if (ls > 0.0f) return a * (1.0f / sqrtf(ls));
     return f3(0.0f, 0.0f, 0.0f);
 }
-__device__ float bsdf_pdf(const ShadingData& sd, float3 N, float3 wo, float3 wi) {  // :89-107
+RFW_SHADE_FN float bsdf_pdf(const ShadingData& sd, float3 N, float3 wo, float3 wi) {  // :89-107
     float bsdfPdf = 0.0f, brdfPdf;
     if (dot3(wi, N) <= 0.0f) {
         brdfPdf = RFW_INV2PI * sd.subsurface * 0.5f;
@@ -148,7 +155,7 @@ __device__ float bsdf_pdf(const ShadingData& sd, float3 N, float3 wo, float3 wi)
     }
     return mixf(brdfPdf, bsdfPdf, sd.transmission);
 }
-__device__ float3 bsdf_eval(const ShadingData& sd, float3 N, float3 wo, float3 wi, float t, bool backfacing) {  // :110-194
+RFW_SHADE_FN float3 bsdf_eval(const ShadingData& sd, float3 N, float3 wo, float3 wi, float t, bool backfacing) {  // :110-194
     const float NDotL = dot3(N, wi);
     const float NDotV = dot3(N, wo);
     const float3 H = normalize3(wi + wo);

@@ -151,7 +151,7 @@ RFW_HD float byte_to_float(uint32_t w, int j) {
 
 // fetch one wide node (read-only path)
 RFW_HD void load_wide_node(const float4* np, float4& n0, float4& n1, float4& n2, float4& n3, float4& n4) {
-#if defined(__CUDA_ARCH__) && RFW_NODE_F4 == 6
+#if defined(__CUDA_ARCH__) && RFW_NODE_F4 == 6 && !defined(RFW_NODE_LD128)
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(n0.x), "=f"(n0.y), "=f"(n0.z), "=f"(n0.w), "=f"(n1.x), "=f"(n1.y), "=f"(n1.z), "=f"(n1.w) : "l"(np));
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
