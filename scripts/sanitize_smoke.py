@@ -15,4 +15,12 @@ be.render_spp(view, 3, 3); be.render(None, view, 1)
 soup = scenes.soup_scene(3000, 0.05); b2 = backend.B200Backend(); soup.apply(b2); b2.trace_closest(scenes.random_rays(5000))
 a = gltf.load_npz(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "cesium_man.npz"))
 sk = gltf.skinned(a, copies=2); b3 = backend.B200Backend(); sk.apply(b3); b3.trace_closest(scenes.random_rays(2000, lo=-1.0, hi=1.0))
+# many small meshes: BLAS builds on the side builder streams; punctual lights + every BSDF lobe; non-finite rays
+from rfw_rs_b200 import scenes as _sc
+many = _sc.SceneDesc(); many.materials = _sc.material()
+for m in range(12):
+    many.meshes[m] = _sc.soup(40 + 7 * m, 0.2, seed=100 + m); many.instances[m] = _sc.to_column_major([_sc.trs((m % 4 - 1.5, 0, m // 4 - 1.0))])
+b4 = backend.B200Backend(); many.apply(b4); r4 = _sc.random_rays(2000, lo=-2.0, hi=2.0); r4["origin"][::7, 0] = np.nan; b4.trace_closest(r4); b4.trace_any(r4)
+lob = _sc.lights_and_lobes_scene(grid=3, subdiv=1); b5 = backend.B200Backend(48, 32); lob.apply(b5)
+b5.render_spp(_sc.camera_view((0, 2.5, -5.0), (0, -0.4, 1.0), 48, 32, aperture=0.05), 2, 4)
 print("sanitize smoke ok", int((h["inst"] >= 0).sum()), int(o.sum()))
