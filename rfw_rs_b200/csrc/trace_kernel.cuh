@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
     // uploaded yet is "waiting", encoded as sp == -1 (no extra register: this kernel sits at its 64-register budget)
 #define RFW_WAITING (IO::kReportsProgress && sp < 0)
     bool any_waiting = false;
+    uint32_t tick = 0;
 
     for (;;) {
         // ---- refill idle lanes: one atomicAdd per warp -------------------------------------------------
@@ -206,6 +207,11 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
         // ---- traverse until too few lanes are busy -----------------------------------------------------
         for (;;) {
             bool done = false;
+            // warp-uniform iteration count: parked lanes (pending triangles / a pending instance entry) are served at the
+            // latest every 16th iteration even if the batch thresholds are not reached — in a sparse scene the other lanes
+            // can churn through thousands of missing rays, and on the host-streamed path the oldest parked ray holds back
+            // the download watermark
+            tick++;
             if (active && (tg.y == 0u || (DQ > 0 && dn < DQ))) {
                 uint2 tgn = make_uint2(0u, 0u);  // leaf group found in this step
                 // (a) nothing at hand: pop (leaving the BLAS when its part of the stack is exhausted)
@@ -256,7 +262,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
                 const uint32_t we = __ballot_sync(FULL, want_enter);
                 if (we != 0u) {
                     const uint32_t can_step = __ballot_sync(FULL, active && !done && tg.y == 0u);
-                    if (((int)__popc(we) >= tune.inst_batch || can_step == 0u) && want_enter) {
+                    if (((int)__popc(we) >= tune.inst_batch || can_step == 0u || (tick & 15u) == 0u) && want_enter) {
                         const int tb = 31 - __clz((int)tg.y);
                         tg.y &= ~(1u << tb);
                         const InstanceRec* rec = sv.leaf_instances + (tg.x + (uint32_t)tb);
@@ -283,7 +289,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
                 const bool can_go = active && !done && ((!pending && tg.y == 0u) || (DQ > 0 && pending && dn < DQ && (RFW_NODE_HITS(ng) || sp > 0)));
                 const uint32_t can_node = __ballot_sync(FULL, can_go);
                 const int n_blocked = __popc(pend & ~can_node);
-                if ((int)__popc(pend) >= tune.tri_batch || (DQ > 0 && n_blocked >= tune.tri_blocked) || can_node == 0u) {
+                if ((int)__popc(pend) >= tune.tri_batch || (DQ > 0 && n_blocked >= tune.tri_blocked) || can_node == 0u || (tick & 15u) == 8u) {
                     if (pending) {
                         const int tb = 31 - __clz((int)tg.y);
                         tg.y &= ~(1u << tb);
