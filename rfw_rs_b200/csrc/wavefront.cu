@@ -70,14 +70,23 @@ __global__ void __launch_bounds__(256) k_wf_generate(FrameParams fp, const uint3
         const float3 p = ld3(fp.cam.p1) + right * u + up * v;
         d = normalize3(p - o);
     }
+    // queue slots: ONE atomicAdd per CTA (a 16-spp 1080p wave is a million warps: one same-address atomic per warp was the
+    // kernel's bound), warp offsets through shared memory
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_base;
     const uint32_t m = __ballot_sync(FULL, valid);
-    if (m == 0u) return;
-    uint32_t base = 0;
-    const int leader = __ffs(m) - 1;
-    if (lane == leader) base = atomicAdd(&counts[0], (uint32_t)__popc(m));
-    base = __shfl_sync(FULL, base, leader);
+    const int warp = threadIdx.x >> 5;
+    if (lane == 0) s_warp[warp] = (uint32_t)__popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { const uint32_t c = s_warp[w]; s_warp[w] = total; total += c; }
+        s_base = total ? atomicAdd(&counts[0], total) : 0u;
+    }
+    __syncthreads();
     if (valid) {
-        const uint32_t k = base + __popc(m & ((1u << lane) - 1u));
+        const uint32_t k = s_base + s_warp[warp] + __popc(m & ((1u << lane) - 1u));
         O[k] = f4(o.x, o.y, o.z, __uint_as_float(pixel));
         D[k] = f4(d.x, d.y, d.z, __uint_as_float(b));
     }
@@ -139,7 +148,10 @@ struct ConnectIO {
 #ifndef RFW_SHADE_MIN_BLOCKS
 #define RFW_SHADE_MIN_BLOCKS 1
 #endif
-__global__ void __launch_bounds__(128, RFW_SHADE_MIN_BLOCKS) k_wf_shade(FrameParams fp, ShadeScene ss, const float4* __restrict__ S, const float4* __restrict__ O, const float4* __restrict__ D,
+#ifndef RFW_SHADE_THREADS
+#define RFW_SHADE_THREADS 128
+#endif
+__global__ void __launch_bounds__(RFW_SHADE_THREADS, RFW_SHADE_MIN_BLOCKS) k_wf_shade(FrameParams fp, ShadeScene ss, const float4* __restrict__ S, const float4* __restrict__ O, const float4* __restrict__ D,
                                                   const float4* __restrict__ T, float4* __restrict__ On, float4* __restrict__ Dn, float4* __restrict__ Tn,
                                                   float4* __restrict__ shO, float4* __restrict__ shD, float4* __restrict__ shE, float* __restrict__ accum,
                                                   const uint32_t* __restrict__ count_cur, uint32_t* __restrict__ count_next, uint32_t* __restrict__ count_shadow) {
@@ -148,8 +160,18 @@ __global__ void __launch_bounds__(128, RFW_SHADE_MIN_BLOCKS) k_wf_shade(FramePar
     const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
     const uint32_t warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lightCount = ss.n_area + ss.n_point + ss.n_spot + ss.n_dir;
+#if !defined(RFW_SHADE_WARP_ATOMICS)
+    __shared__ uint32_t s_cnt[2][2][RFW_SHADE_THREADS / 32];  // [iteration parity][queue][warp]
+    __shared__ uint32_t s_b[2][2];
+    uint32_t parity = 0;
+    const int warp_in_cta = threadIdx.x >> 5;
+    (void)warps_total; (void)warp_id;
+    for (uint32_t cbase = blockIdx.x * blockDim.x; cbase < count; cbase += gridDim.x * blockDim.x, parity ^= 1u) {  // uniform trip count per CTA
+        const uint32_t k = cbase + threadIdx.x;
+#else
     for (uint32_t base = warp_id * 32u; base < count; base += warps_total * 32u) {
         const uint32_t k = base + lane;
+#endif
         const bool valid = k < count;
         bool emit_ext = false, emit_sh = false;
         float3 nO = f3(0, 0, 0), nD = f3(0, 0, 1), nT = f3(0, 0, 0);
@@ -282,30 +304,44 @@ __global__ void __launch_bounds__(128, RFW_SHADE_MIN_BLOCKS) k_wf_shade(FramePar
         }
         // queue compaction: one atomic per warp per queue
         const uint32_t ms = __ballot_sync(FULL, emit_sh);
+        const uint32_t me = __ballot_sync(FULL, emit_ext);
+#if !defined(RFW_SHADE_WARP_ATOMICS)
+        // queue slots: one atomicAdd per CTA and queue instead of one per warp (2.5 M same-address atomics per C3 frame)
+        if (lane == 0) { s_cnt[parity][0][warp_in_cta] = (uint32_t)__popc(ms); s_cnt[parity][1][warp_in_cta] = (uint32_t)__popc(me); }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            const int q = threadIdx.x;
+            uint32_t total = 0;
+#pragma unroll
+            for (int w = 0; w < RFW_SHADE_THREADS / 32; w++) { const uint32_t c = s_cnt[parity][q][w]; s_cnt[parity][q][w] = total; total += c; }
+            s_b[parity][q] = total ? atomicAdd(q == 0 ? count_shadow : count_next, total) : 0u;
+        }
+        __syncthreads();
+        const uint32_t bs = s_b[parity][0] + s_cnt[parity][0][warp_in_cta], be = s_b[parity][1] + s_cnt[parity][1][warp_in_cta];
+#else
+        uint32_t bs = 0, be = 0;
         if (ms) {
             const int leader = __ffs(ms) - 1;
-            uint32_t b = 0;
-            if (lane == leader) b = atomicAdd(count_shadow, (uint32_t)__popc(ms));
-            b = __shfl_sync(FULL, b, leader);
-            if (emit_sh) {
-                const uint32_t j = b + __popc(ms & ((1u << lane) - 1u));
-                shO[j] = f4(sO.x, sO.y, sO.z, 0.0f);
-                shD[j] = f4(sD.x, sD.y, sD.z, sDist);
-                shE[j] = f4(sE.x, sE.y, sE.z, __uint_as_float(wave_b * fp.npix + pixel));  // index into the partial accumulators
-            }
+            if (lane == leader) bs = atomicAdd(count_shadow, (uint32_t)__popc(ms));
+            bs = __shfl_sync(FULL, bs, leader);
         }
-        const uint32_t me = __ballot_sync(FULL, emit_ext);
         if (me) {
             const int leader = __ffs(me) - 1;
-            uint32_t b = 0;
-            if (lane == leader) b = atomicAdd(count_next, (uint32_t)__popc(me));
-            b = __shfl_sync(FULL, b, leader);
-            if (emit_ext) {
-                const uint32_t j = b + __popc(me & ((1u << lane) - 1u));
-                On[j] = f4(nO.x, nO.y, nO.z, __uint_as_float(pixel));
-                Dn[j] = f4(nD.x, nD.y, nD.z, __uint_as_float(wave_b));
-                Tn[j] = f4(nT.x, nT.y, nT.z, nPdf);
-            }
+            if (lane == leader) be = atomicAdd(count_next, (uint32_t)__popc(me));
+            be = __shfl_sync(FULL, be, leader);
+        }
+#endif
+        if (emit_sh) {
+            const uint32_t j = bs + __popc(ms & ((1u << lane) - 1u));
+            shO[j] = f4(sO.x, sO.y, sO.z, 0.0f);
+            shD[j] = f4(sD.x, sD.y, sD.z, sDist);
+            shE[j] = f4(sE.x, sE.y, sE.z, __uint_as_float(wave_b * fp.npix + pixel));  // index into the partial accumulators
+        }
+        if (emit_ext) {
+            const uint32_t j = be + __popc(me & ((1u << lane) - 1u));
+            On[j] = f4(nO.x, nO.y, nO.z, __uint_as_float(pixel));
+            Dn[j] = f4(nD.x, nD.y, nD.z, __uint_as_float(wave_b));
+            Tn[j] = f4(nT.x, nT.y, nT.z, nPdf);
         }
     }
 }
@@ -405,7 +441,20 @@ __global__ void __launch_bounds__(256) k_wf_reduce(FrameParams fp, const uint32_
     uint32_t pixel;
     if (slot >= fp.max_paths || !slot_to_pixel(fp, owned_tiles, slot, pixel)) return;
     float4 a = accum[pixel];
-    for (uint32_t b = 0; b < fp.wave_spp; b++) {
+    // eight samples' loads in flight per thread, then the adds in SAMPLE ORDER (one load -> add -> store round per sample cost a
+    // full memory latency each: 1.0 ms for the 16-sample wave of a 1080p frame)
+    uint32_t b = 0;
+    for (; b + 8 <= fp.wave_spp; b += 8) {
+        float4* p = partial + (size_t)b * fp.npix + pixel;
+        float4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = __ldcs(p + (size_t)k * fp.npix);
+#pragma unroll
+        for (int k = 0; k < 8; k++) { a.x += v[k].x; a.y += v[k].y; a.z += v[k].z; a.w += v[k].w; }
+#pragma unroll
+        for (int k = 0; k < 8; k++) p[(size_t)k * fp.npix] = f4(0, 0, 0, 0);
+    }
+    for (; b < fp.wave_spp; b++) {
         float4* p = partial + (size_t)b * fp.npix + pixel;
         const float4 v = *p;
         a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
@@ -585,7 +634,7 @@ cudaError_t Wavefront::stage_times(float out_ms[5]) {
 
 cudaError_t Wavefront::render(cudaStream_t stream, const SceneView& sv, const ShadeScene& ss, const RfwCameraView3D& cam, uint32_t first_sample, uint32_t spp, uint32_t depth) {
     if (max_paths == 0) return cudaSuccess;
-    const int shade_blocks = sm_count * 8;
+    const int shade_blocks = sm_count * 8 * 128 / RFW_SHADE_THREADS;
     const uint32_t wave = wave_spp_for(spp);
     WF_CK(ensure_wave(wave));
     const TraceTuning tune{refill_below, sv.two_level ? tri_batch_two_level : tri_batch, tri_blocked, inst_batch};
@@ -606,7 +655,7 @@ cudaError_t Wavefront::render(cudaStream_t stream, const SceneView& sv, const Sh
             if (sv.two_level) WF_CK((launch_persistent_io<ExtendIO, false, true>(stream, sm_count, 0, tune, sv, eio, cap, d_counts + 3)));
             else WF_CK((launch_persistent_io<ExtendIO, false, false>(stream, sm_count, 0, tune, sv, eio, cap, d_counts + 3)));
             WF_CK(stage_mark(stream, 1));
-            k_wf_shade<<<shade_blocks, 128, 0, stream>>>(fp, ss, d_S, d_O[cur], d_D[cur], d_T[cur], d_O[nxt], d_D[nxt], d_T[nxt], d_shO, d_shD, d_shE,
+            k_wf_shade<<<shade_blocks, RFW_SHADE_THREADS, 0, stream>>>(fp, ss, d_S, d_O[cur], d_D[cur], d_T[cur], d_O[nxt], d_D[nxt], d_T[nxt], d_shO, d_shD, d_shE,
                                                          reinterpret_cast<float*>(d_partial), d_counts + cur, d_counts + nxt, d_counts + 2);
             WF_CK(stage_mark(stream, 2));
             ConnectIO cio{d_shO, d_shD, d_shE, d_counts + 2, reinterpret_cast<float*>(d_partial)};
