@@ -334,6 +334,8 @@ struct MeshEntry {
     float lo[3], hi[3];
     uint32_t first_slot;  // global id of this mesh's first instance slot
     uint32_t present;     // mesh has triangles and a BLAS
+    uint32_t n_tris;
+    uint32_t pad;
 };
 
 __global__ void __launch_bounds__(128) k_instance_prepare(const MeshEntry* __restrict__ meshes, uint32_t n_meshes, const float* __restrict__ matrices, uint32_t n_slots,
@@ -360,7 +362,8 @@ __global__ void __launch_bounds__(128) k_instance_prepare(const MeshEntry* __res
     memset(&sh, 0, sizeof(sh));
     bool live = me.present && !zero && invert_affine(M, r.inv0, r.inv1, r.inv2, sh.nrm0, sh.nrm1, sh.nrm2);
     if (live) {
-        r.nodes = me.nodes; r.tris = me.ttris; r.inst_id = (int)gid; r.mesh_id = (int)lo_i; r.pad0 = r.pad1 = 0;
+        r.nodes = me.nodes; r.tris = me.ttris; r.inst_id = (int)gid; r.mesh_id = (int)lo_i; r.pad1 = 0;
+        r.direct_tris = (me.n_tris >= 1u && me.n_tris <= (uint32_t)RFW_DIRECT_TRIS) ? (int)me.n_tris : 0;
         sh.tris = me.tris; sh.mesh_id = (int)lo_i; sh.pad = 0;
         float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
 #pragma unroll
@@ -609,7 +612,7 @@ int Backend::synchronize() {
             e.first_slot = gid;
             const MeshRec* m = (mesh_id < meshes.size() && meshes[mesh_id].present && meshes[mesh_id].n) ? &meshes[mesh_id] : nullptr;
             if (m) {
-                e.nodes = m->bvh.nodes; e.ttris = m->d_ttris; e.tris = m->d_tris; e.present = 1;
+                e.nodes = m->bvh.nodes; e.ttris = m->d_ttris; e.tris = m->d_tris; e.present = 1; e.n_tris = m->n;
                 for (int k = 0; k < 3; k++) { e.lo[k] = m->bvh.lo[k]; e.hi[k] = m->bvh.hi[k]; }
             }
             gid += inst_lists[mesh_id].present ? (uint32_t)(inst_lists[mesh_id].matrices.size() / 16) : 0;

@@ -304,8 +304,10 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
                         ray_setup_box(rc);
                         ray_setup_tri(rc);
                         nodes = rec->nodes; tris = rec->tris;
-                        ng = make_uint2(0u, 0x80000000u);
-                        tg = make_uint2(0u, 0u);
+                        // a BLAS of a handful of triangles (ground quad, light quads): straight to its triangles, no root-node visit
+                        const int direct = rec->direct_tris;
+                        ng = make_uint2(0u, direct > 0 ? 0u : 0x80000000u);
+                        tg = make_uint2(0u, direct > 0 ? (1u << direct) - 1u : 0u);
                     }
                 }
             }

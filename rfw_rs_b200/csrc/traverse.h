@@ -24,6 +24,11 @@
 
 namespace rfw {
 
+// meshes of up to this many triangles are entered without a node visit (InstanceRec::direct_tris)
+#ifndef RFW_DIRECT_TRIS
+#define RFW_DIRECT_TRIS 4
+#endif
+
 struct Hit {
     int inst;
     int prim;
@@ -37,7 +42,8 @@ struct InstanceRec {
     const float4* tris;        // BLAS traversal triangles (3 float4 per triangle; v0.w = mesh-local prim id)
     int inst_id;               // global instance index reported in hits
     int mesh_id;
-    int pad0, pad1;
+    int direct_tris;           // 1..RFW_DIRECT_TRIS: the BLAS is that small (a quad, a light) — its triangles 0..n-1 are tested without visiting the root node; 0: traverse
+    int pad1;
 };
 
 struct SceneView {
@@ -342,6 +348,7 @@ RFW_HD bool trace_ray(const SceneView& sv, const float3 o, const float3 d, const
                 nodes = rec.nodes; tris = rec.tris;
                 ng = make_uint2(0u, 0x80000000u);
                 tg = make_uint2(0u, 0u);
+                if (rec.direct_tris > 0) { ng = make_uint2(0u, 0u); tg = make_uint2(0u, (1u << rec.direct_tris) - 1u); continue; }
                 break;
             }
         }

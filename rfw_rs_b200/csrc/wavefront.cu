@@ -92,6 +92,15 @@ __global__ void __launch_bounds__(256) k_wf_generate(FrameParams fp, const uint3
     }
 }
 
+// radiance into a float4 partial accumulator: ONE 16-byte vector reduction (sm_90+) instead of three scalar atomics
+__device__ __forceinline__ void red_add_rgb(float* a, float x, float y, float z) {
+#if defined(RFW_SCALAR_RED)
+    atomicAdd(a + 0, x); atomicAdd(a + 1, y); atomicAdd(a + 2, z);
+#else
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(x), "f"(y), "f"(z), "f"(0.0f) : "memory");
+#endif
+}
+
 // ---- extend / connect I/O policies for the persistent traversal kernel --------------------------------
 struct ExtendIO {
     const float4* O;
@@ -132,10 +141,7 @@ struct ConnectIO {
     __device__ __forceinline__ void store_any(uint32_t i, bool occluded) const {
         if (occluded) return;
         const float4 e = E[i];
-        float* a = accum + 4 * (size_t)__float_as_uint(e.w);
-        atomicAdd(a + 0, e.x);
-        atomicAdd(a + 1, e.y);
-        atomicAdd(a + 2, e.z);
+        red_add_rgb(accum + 4 * (size_t)__float_as_uint(e.w), e.x, e.y, e.z);
     }
     __device__ __forceinline__ uint32_t landed(int) const { return 0xFFFFFFFFu; }
     __device__ __forceinline__ bool stalled(int) const { return false; }
@@ -296,10 +302,7 @@ __global__ void __launch_bounds__(RFW_SHADE_THREADS, RFW_SHADE_MIN_BLOCKS) k_wf_
                 }
             }
             if (add && (contrib.x != 0.0f || contrib.y != 0.0f || contrib.z != 0.0f)) {
-                float* a = accum + 4 * ((size_t)wave_b * fp.npix + pixel);
-                atomicAdd(a + 0, contrib.x);
-                atomicAdd(a + 1, contrib.y);
-                atomicAdd(a + 2, contrib.z);
+                red_add_rgb(accum + 4 * ((size_t)wave_b * fp.npix + pixel), contrib.x, contrib.y, contrib.z);
             }
         }
         // queue compaction: one atomic per warp per queue

@@ -164,7 +164,9 @@ void emu_build(void* s, float c_node, float c_prim, int pmax, uint64_t* stats) {
             InstanceRec r;
             if (!invert_affine(M, r.inv0, r.inv1, r.inv2)) continue;
             r.nodes = mit->second.bvh.nodes.data(); r.tris = mit->second.ttris.data();
-            r.inst_id = gid; r.mesh_id = (int)kv.first; r.pad0 = r.pad1 = 0;
+            r.inst_id = gid; r.mesh_id = (int)kv.first; r.pad1 = 0;
+            const size_t ntris = mit->second.tris.size();
+            r.direct_tris = (ntris >= 1 && ntris <= (size_t)RFW_DIRECT_TRIS) ? (int)ntris : 0;
             float3 l = f3(FLT_MAX, FLT_MAX, FLT_MAX), h = f3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
             for (int c = 0; c < 8; c++) {
                 float3 p = f3((c & 1) ? mit->second.hi.x : mit->second.lo.x, (c & 2) ? mit->second.hi.y : mit->second.lo.y, (c & 4) ? mit->second.hi.z : mit->second.lo.z);
