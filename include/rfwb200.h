@@ -401,6 +401,7 @@ RFWB200_API int rfwb200_render_stats(void* handle, RfwRenderStats* out);
 /* tuning knobs (string key, integer value); unknown key -> RFWB200_ERR_INVALID.  Defaults are the measured optima.
  *   traversal:  trace_variant (0 persistent, 1 one thread per ray), min_blocks, blocks_per_sm, refill_below (28), tri_batch (4),
  *               tri_batch_two_level (4), inst_batch (6: two-level kernels enter instances when this many lanes wait at a TLAS leaf)
+ *               sort_rays (0; 1 = device-pointer batches traced in Morton order of the ray origins), sort_min_bvh_mb
  *   host path:  streamed (1: single persistent launch overlapping upload and download), chunk_rays, l2_persist
  *   builder:    sah_treelet, sah_treelet_tlas, sah_c_prim_milli, sah_pmax, build_streams (8: small BLAS builds in flight at once)
  *   wavefront:  max_depth, wave_paths, sample_count, stage_timing (1: RfwRenderStats.stage_ms is filled) */

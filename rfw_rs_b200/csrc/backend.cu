@@ -111,7 +111,7 @@ Backend::~Backend() {
     tlas.release();
     d_instances.release(); d_leaf_instances.release(); d_inst_shading.release(); d_materials.release();
     d_area.release(); d_point.release(); d_spot.release(); d_dir.release();
-    d_rays.release(); d_hits.release(); d_occ.release();
+    d_rays.release(); d_hits.release(); d_occ.release(); ray_sort.release();
     for (auto& sk : skins) sk.joints.release();
     for (auto& si : skinned) release_skinned(si);
     for (auto& t : textures) t.texels.release();
@@ -638,6 +638,8 @@ int Backend::synchronize() {
             BK_CUDA(cudaMallocAsync(&hi, (size_t)slots * sizeof(float4), stream), "instance scratch");
             BK_CUDA(cudaMallocAsync(&flags, ((size_t)slots * 3 + 4) * sizeof(uint32_t), stream), "instance scratch");
             rank = flags + slots; ident = rank + slots; out = ident + slots;
+            BK_CUDA(cudaMemsetAsync(lo, 0, sizeof(float4), stream), "instance scratch");  // box of the first live instance is read back below even if there is none
+            BK_CUDA(cudaMemsetAsync(hi, 0, sizeof(float4), stream), "instance scratch");
             BK_CUDA(cudaMemsetAsync(out, 0, 4 * sizeof(uint32_t), stream), "instance scratch");
             BK_CUDA(cudaMemcpyAsync(d_mesh_table.ptr, table.data(), table.size() * sizeof(MeshEntry), cudaMemcpyHostToDevice, stream), "mesh table");
             for (size_t mesh_id = 0; mesh_id < inst_lists.size(); mesh_id++) {
@@ -673,9 +675,14 @@ int Backend::synchronize() {
             k_instance_compact<<<blocks, 128, 0, stream>>>(slots, flags, rank, ident, tmp_recs, tmp_lo, tmp_hi, d_instances.ptr, lo, hi, out);
             launch_count += 3;
             uint32_t h_out[4] = {0, 0, 0, 0};
+            float4 h_box[2] = {make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0)};  // world box of the first live instance (the scene's, if it is the only one)
             BK_CUDA(cudaMemcpyAsync(h_out, out, sizeof(h_out), cudaMemcpyDeviceToHost, stream), "instance count");
+            BK_CUDA(cudaMemcpyAsync(&h_box[0], lo, sizeof(float4), cudaMemcpyDeviceToHost, stream), "instance box");
+            BK_CUDA(cudaMemcpyAsync(&h_box[1], hi, sizeof(float4), cudaMemcpyDeviceToHost, stream), "instance box");
             BK_CUDA(cudaStreamSynchronize(stream), "instance records");  // the live count sizes the TLAS build
             live = h_out[0];
+            scene_lo[0] = h_box[0].x; scene_lo[1] = h_box[0].y; scene_lo[2] = h_box[0].z;
+            scene_hi[0] = h_box[1].x; scene_hi[1] = h_box[1].y; scene_hi[2] = h_box[1].z;
             single_identity = live == 1 && h_out[1] != 0;
             cudaError_t e = cudaSuccess;
             if (live > 1) {
@@ -694,6 +701,7 @@ int Backend::synchronize() {
             BK_CUDA(finish_pending_builds(bctx), "TLAS build");
         }
         BK_CUDA(cudaStreamSynchronize(stream), "instance upload");
+        if (live > 1) for (int k = 0; k < 3; k++) { scene_lo[k] = tlas.lo[k]; scene_hi[k] = tlas.hi[k]; }  // world bounds (ray binning)
         sv.tlas_nodes = tlas.nodes;
         sv.tlas_refs = tlas.leaf_prims;
         sv.instances = d_instances.ptr;
@@ -814,6 +822,15 @@ int Backend::resize(uint32_t w, uint32_t h) {
 }
 
 // ---- ray casting ---------------------------------------------------------------------------------------
+// Ray binning pays when the acceleration structure does not fit the L2 and the batch is large enough to amortise the sort
+// (option "sort_rays": -1 auto, 0 never, 1 always).
+bool Backend::bin_rays(uint32_t n) const {
+    if (tcfg.variant != TRACE_VARIANT_PERSISTENT || sv.num_live == 0) return false;
+    if (sort_rays == 0) return false;
+    if (sort_rays > 0) return true;
+    return build_stats.bvh_bytes > sort_min_bvh_bytes && n >= (1u << 20);
+}
+
 int Backend::trace_closest_device(const RfwRay* d_r, uint64_t num, RfwHit* d_h, int sync) {
     DeviceScope device_scope(cfg.device);
     BK_CUDA(device_scope.status, "cudaSetDevice");
@@ -841,6 +858,12 @@ int Backend::trace_closest_device(const RfwRay* d_r, uint64_t num, RfwHit* d_h, 
     BK_CUDA(cudaEventRecord(ev0, stream), "event");
     for (uint64_t off = 0; off < num; off += (1ull << 30)) {
         const uint32_t n = (uint32_t)std::min<uint64_t>(num - off, 1ull << 30);
+        if (bin_rays(n)) {
+            const uint64_t before = ray_sort.launches;
+            BK_CUDA(trace_sorted(tcfg, sv, false, d_r + off, n, d_h + off, nullptr, d_counter, scene_lo, scene_hi, ray_sort), "trace_closest (binned)");
+            launch_count += ray_sort.launches - before;
+            continue;
+        }
         BK_CUDA(trace_closest(tcfg, sv, d_r + off, n, d_h + off, d_counter), "trace_closest");
         launch_count++;
     }
@@ -861,6 +884,12 @@ int Backend::trace_any_device(const RfwRay* d_r, uint64_t num, uint32_t* d_o, in
     BK_CUDA(cudaEventRecord(ev0, stream), "event");
     for (uint64_t off = 0; off < num; off += (1ull << 30)) {
         const uint32_t n = (uint32_t)std::min<uint64_t>(num - off, 1ull << 30);
+        if (bin_rays(n)) {
+            const uint64_t before = ray_sort.launches;
+            BK_CUDA(trace_sorted(tcfg, sv, true, d_r + off, n, nullptr, d_o + off, d_counter, scene_lo, scene_hi, ray_sort), "trace_any (binned)");
+            launch_count += ray_sort.launches - before;
+            continue;
+        }
         BK_CUDA(trace_any(tcfg, sv, d_r + off, n, d_o + off, d_counter), "trace_any");
         launch_count++;
     }
@@ -1362,6 +1391,8 @@ int Backend::set_option(const char* key, int64_t value) {
     else if (k == "tri_batch") tcfg.tri_batch = (int)value;
     else if (k == "tri_batch_two_level") tcfg.tri_batch_two_level = (int)value;
     else if (k == "tri_blocked") tcfg.tri_blocked = (int)value;
+    else if (k == "sort_rays") sort_rays = (int)value;
+    else if (k == "sort_min_bvh_mb") sort_min_bvh_bytes = (uint64_t)std::max<int64_t>(0, value) << 20;
     else if (k == "stage_timing") wf.stage_timing = value != 0;
     else if (k == "inst_batch") tcfg.inst_batch = (int)std::max<int64_t>(1, value);
     else if (k == "min_blocks") tcfg.min_blocks = (int)value;

@@ -137,6 +137,11 @@ private:
     std::vector<BuilderContext*> side_ctx;
     int build_streams = 8;
     TraceConfig tcfg;
+    RaySortScratch ray_sort;          // ray binning for scenes beyond the L2 (trace.h::trace_sorted)
+    int sort_rays = 0;                // 0 never (default: measured break-even, see trace.h), 1 always, -1 auto (BVH > sort_min_bvh_bytes and >= 2^20 rays)
+    uint64_t sort_min_bvh_bytes = 160ull << 20;
+    float scene_lo[3] = {0, 0, 0}, scene_hi[3] = {0, 0, 0};  // world bounds of the live instances
+    bool bin_rays(uint32_t n) const;
     uint64_t launch_count = 0;
 
     std::vector<MeshRec> meshes;

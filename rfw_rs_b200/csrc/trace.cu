@@ -13,6 +13,7 @@
 #include <stdint.h>
 
 #include "trace.h"
+#include "builder.h"
 #include "trace_kernel.cuh"
 
 namespace rfw {
@@ -37,6 +38,21 @@ struct RayBufferIO {
         __stcs(out + 4, h.v);
     }
     __device__ __forceinline__ void store_any(uint32_t i, bool occ) const { __stcs(occluded + i, occ ? 1u : 0u); }
+    __device__ __forceinline__ uint32_t landed(int) const { return 0xFFFFFFFFu; }
+    __device__ __forceinline__ bool stalled(int) const { return false; }
+    static constexpr bool kReportsProgress = false;
+    __device__ __forceinline__ bool publish_due(bool, int) const { return false; }
+    __device__ __forceinline__ void publish(uint32_t, int) const {}
+};
+
+// The same buffers visited through an index permutation (ray binning, see trace.h::trace_sorted)
+struct PermutedRayIO {
+    RayBufferIO base;
+    const uint32_t* perm;
+    __device__ __forceinline__ uint32_t count() const { return base.n; }
+    __device__ __forceinline__ void load(uint32_t i, float4& r0, float4& r1) const { base.load(__ldg(perm + i), r0, r1); }
+    __device__ __forceinline__ void store_closest(uint32_t i, const Hit& h) const { base.store_closest(__ldg(perm + i), h); }
+    __device__ __forceinline__ void store_any(uint32_t i, bool occ) const { base.store_any(__ldg(perm + i), occ); }
     __device__ __forceinline__ uint32_t landed(int) const { return 0xFFFFFFFFu; }
     __device__ __forceinline__ bool stalled(int) const { return false; }
     static constexpr bool kReportsProgress = false;
@@ -163,6 +179,64 @@ template <bool ANY, bool TWO_LEVEL>
 static cudaError_t launch_persistent(const TraceConfig& cfg, const SceneView& sv, const float4* rays, uint32_t n, RfwHit* hits, uint32_t* occ, uint32_t* counter) {
     RayBufferIO io{rays, n, hits, occ};
     return launch_persistent_dispatch<ANY, TWO_LEVEL>(cfg, sv, io, n, counter);
+}
+
+// ---- ray binning (trace_sorted) ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t spread3_5(uint32_t v) {  // 5 bits -> every third bit
+    v &= 31u;
+    v = (v | (v << 8)) & 0x0000100Fu;
+    v = (v | (v << 4)) & 0x000010C3u;
+    return (v | (v << 2)) & 0x00001249u;
+}
+__global__ void __launch_bounds__(256) k_ray_keys(const float4* __restrict__ rays, uint32_t n, float3 lo, float3 scale, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const float4 o = __ldg(rays + 2 * (size_t)i);
+    // fminf / fmaxf drop NaNs: a non-finite origin lands in cell 0 and retires at once in the kernel
+    const uint32_t qx = (uint32_t)fminf(fmaxf((o.x - lo.x) * scale.x, 0.0f), 31.0f);
+    const uint32_t qy = (uint32_t)fminf(fmaxf((o.y - lo.y) * scale.y, 0.0f), 31.0f);
+    const uint32_t qz = (uint32_t)fminf(fmaxf((o.z - lo.z) * scale.z, 0.0f), 31.0f);
+    keys[i] = (uint64_t)((spread3_5(qx) << 2) | (spread3_5(qy) << 1) | spread3_5(qz));
+    vals[i] = i;
+}
+
+cudaError_t RaySortScratch::reserve(size_t n) {
+    if (n <= capacity) return cudaSuccess;
+    release();
+    cudaError_t e = cudaMalloc(&keys, 2 * n * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&vals, 2 * n * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&hist, (size_t)256 * radix_sort_tiles((int)n) * sizeof(uint32_t));
+    if (e != cudaSuccess) { release(); return e; }
+    capacity = n;
+    return cudaSuccess;
+}
+void RaySortScratch::release() {
+    if (keys) cudaFree(keys);
+    if (vals) cudaFree(vals);
+    if (hist) cudaFree(hist);
+    keys = nullptr; vals = nullptr; hist = nullptr; capacity = 0;
+}
+
+cudaError_t trace_sorted(const TraceConfig& cfg, const SceneView& sv, bool any_hit, const RfwRay* d_rays, uint32_t n, RfwHit* d_hits, uint32_t* d_occluded, uint32_t* d_counter,
+                         const float lo[3], const float hi[3], RaySortScratch& sc) {
+    if (n == 0) return cudaSuccess;
+    cudaError_t e = sc.reserve(n);
+    if (e != cudaSuccess) return e;
+    auto inv = [](float a, float b) { return b > a ? 32.0f / (b - a) : 0.0f; };
+    const float3 l = make_float3(lo[0], lo[1], lo[2]), scale = make_float3(inv(lo[0], hi[0]), inv(lo[1], hi[1]), inv(lo[2], hi[2]));
+    const float4* rays = reinterpret_cast<const float4*>(d_rays);
+    k_ray_keys<<<(n + 255) / 256, 256, 0, cfg.stream>>>(rays, n, l, scale, sc.keys, sc.vals);
+    sc.launches++;
+    const int flip = radix_sort_pairs(sc.keys, sc.vals, sc.keys + sc.capacity, sc.vals + sc.capacity, sc.hist, (int)n, 0, 16, cfg.stream, &sc.launches);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const PermutedRayIO io{RayBufferIO{rays, n, d_hits, d_occluded}, flip ? sc.vals + sc.capacity : sc.vals};
+    const TraceTuning tune{cfg.refill_below, sv.two_level ? cfg.tri_batch_two_level : cfg.tri_batch, cfg.tri_blocked, cfg.inst_batch};
+    sc.launches++;
+    if (any_hit) return sv.two_level ? launch_persistent_io<PermutedRayIO, true, true>(cfg.stream, cfg.sm_count, cfg.blocks_per_sm, tune, sv, io, n, d_counter)
+                                     : launch_persistent_io<PermutedRayIO, true, false>(cfg.stream, cfg.sm_count, cfg.blocks_per_sm, tune, sv, io, n, d_counter);
+    return sv.two_level ? launch_persistent_io<PermutedRayIO, false, true>(cfg.stream, cfg.sm_count, cfg.blocks_per_sm, tune, sv, io, n, d_counter)
+                        : launch_persistent_io<PermutedRayIO, false, false>(cfg.stream, cfg.sm_count, cfg.blocks_per_sm, tune, sv, io, n, d_counter);
 }
 
 cudaError_t trace_closest(const TraceConfig& cfg, const SceneView& sv, const RfwRay* d_rays, uint32_t n, RfwHit* d_hits, uint32_t* d_counter) {

@@ -6,6 +6,7 @@ n_tris = int(os.environ.get("TUNE_TRIS", 1000000)); s = float(os.environ.get("TU
 desc = scenes.soup_scene(n_tris, s)
 be = backend.B200Backend(); desc.apply(be)
 print("build", be.build_stats())
+if "SORT_RAYS" in os.environ: be.set_option("sort_rays", int(os.environ["SORT_RAYS"]))
 rays = scenes.random_rays(n_rays)
 d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1).copy()).cuda()
 d_hits = torch.empty(n_rays * 20, dtype=torch.uint8, device="cuda")

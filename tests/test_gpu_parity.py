@@ -115,6 +115,33 @@ def test_non_finite_rays_retire_as_misses(B, oracle_mod, torch_cuda):
     assert np.array_equal(gpu.trace_closest(bad)["inst"], h["inst"])
 
 
+@pytest.mark.parametrize("two_level", [False, True])
+def test_ray_binning_is_transparent(B, torch_cuda, two_level):
+    """Option sort_rays (off by default; meant for scenes whose BVH exceeds the L2): rays are traced in Morton order of their origins
+    through an index permutation — the hits must land at the rays' own slots, bit-identical to the unsorted launch,
+    including rays outside the scene bounds and non-finite rays."""
+    torch = torch_cuda
+    desc = scenes.instanced_scene(grid=8, subdiv=2, n_lights=2) if two_level else scenes.soup_scene(80000, 0.015)
+    gpu = B.B200Backend(); desc.apply(gpu)
+    n = (1 << 20) + 4321
+    rays = scenes.random_rays(n, lo=-6.0, hi=6.0) if two_level else scenes.random_rays(n, lo=-0.3, hi=1.3)
+    rays["origin"][5::1001, 1] = np.nan
+    d_rays = dev_buf(torch, rays)
+    d_hits = torch.empty(n * 20, dtype=torch.uint8, device="cuda")
+    d_occ = torch.empty(n, dtype=torch.int32, device="cuda")
+    out = {}
+    for mode in (0, 1):
+        gpu.set_option("sort_rays", mode)
+        d_hits.fill_(0xAB); d_occ.fill_(7)
+        gpu.trace_closest_device(d_rays.data_ptr(), n, d_hits.data_ptr())
+        gpu.trace_any_device(d_rays.data_ptr(), n, d_occ.data_ptr())
+        out[mode] = (np.frombuffer(d_hits.cpu().numpy().tobytes(), dtype=wire.HIT).copy(), d_occ.cpu().numpy().copy())
+    assert np.array_equal(out[0][0].view(np.uint8), out[1][0].view(np.uint8))
+    assert np.array_equal(out[0][1], out[1][1])
+    assert (out[1][0]["inst"] >= 0).mean() > 0.05 and np.array_equal(out[1][1] != 0, out[1][0]["inst"] >= 0)
+    gpu.set_option("sort_rays", 0)
+
+
 def test_soup_200k(B, oracle_mod):
     desc = scenes.soup_scene(200000, 0.01)
     gpu, cpu = make_pair(B, oracle_mod, desc)
