@@ -10,6 +10,7 @@
 // with the watertight test of traverse.h.  k_trace_simple: one thread per ray, private stack — the
 // reference form used by the instrumented entry point and as a cross-check in the tests.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <stdint.h>
 
 #include "trace.h"
@@ -182,39 +183,58 @@ static cudaError_t launch_persistent(const TraceConfig& cfg, const SceneView& sv
 }
 
 // ---- ray binning (trace_sorted) ------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t spread3_5(uint32_t v) {  // 5 bits -> every third bit
-    v &= 31u;
-    v = (v | (v << 8)) & 0x0000100Fu;
-    v = (v | (v << 4)) & 0x000010C3u;
-    return (v | (v << 2)) & 0x00001249u;
+// One-pass counting sort into 4 096 origin cells (4 bits per axis): count (shared-memory histograms, the cell of every ray
+// kept as a u16), scan of the 4 096 counters, scatter of the ray indices through per-cell cursors.  The order inside a cell
+// is the arrival order of the atomics — it changes the order rays are traced in, not their results.
+static constexpr int BIN_BITS = 4;                       // per axis
+static constexpr int BIN_CELLS = 1 << (3 * BIN_BITS);   // 4 096
+__device__ __forceinline__ uint32_t spread3_4(uint32_t v) {  // 4 bits -> every third bit
+    v &= 15u;
+    v = (v | (v << 4)) & 0x000000C3u;
+    return (v | (v << 2)) & 0x00000249u;
 }
-__global__ void __launch_bounds__(256) k_ray_keys(const float4* __restrict__ rays, uint32_t n, float3 lo, float3 scale, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+__global__ void __launch_bounds__(256) k_bin_count(const float4* __restrict__ rays, uint32_t n, float3 lo, float3 scale, uint16_t* __restrict__ cells, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[BIN_CELLS];
+    for (int k = threadIdx.x; k < BIN_CELLS; k += 256) sh[k] = 0u;
+    __syncthreads();
+    const float top = (float)((1 << BIN_BITS) - 1);
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const float4 o = __ldg(rays + 2 * (size_t)i);
+        // fminf / fmaxf drop NaNs: a non-finite origin lands in cell 0 and retires at once in the kernel
+        const uint32_t qx = (uint32_t)fminf(fmaxf((o.x - lo.x) * scale.x, 0.0f), top);
+        const uint32_t qy = (uint32_t)fminf(fmaxf((o.y - lo.y) * scale.y, 0.0f), top);
+        const uint32_t qz = (uint32_t)fminf(fmaxf((o.z - lo.z) * scale.z, 0.0f), top);
+        const uint32_t c = (spread3_4(qx) << 2) | (spread3_4(qy) << 1) | spread3_4(qz);
+        cells[i] = (uint16_t)c;
+        atomicAdd(&sh[c], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < BIN_CELLS; k += 256) {
+        const uint32_t c = sh[k];
+        if (c) atomicAdd(&hist[k], c);
+    }
+}
+__global__ void __launch_bounds__(256) k_bin_scatter(const uint16_t* __restrict__ cells, uint32_t n, uint32_t* __restrict__ cursor, uint32_t* __restrict__ perm) {
     const uint32_t i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
-    const float4 o = __ldg(rays + 2 * (size_t)i);
-    // fminf / fmaxf drop NaNs: a non-finite origin lands in cell 0 and retires at once in the kernel
-    const uint32_t qx = (uint32_t)fminf(fmaxf((o.x - lo.x) * scale.x, 0.0f), 31.0f);
-    const uint32_t qy = (uint32_t)fminf(fmaxf((o.y - lo.y) * scale.y, 0.0f), 31.0f);
-    const uint32_t qz = (uint32_t)fminf(fmaxf((o.z - lo.z) * scale.z, 0.0f), 31.0f);
-    keys[i] = (uint64_t)((spread3_5(qx) << 2) | (spread3_5(qy) << 1) | spread3_5(qz));
-    vals[i] = i;
+    perm[atomicAdd(&cursor[cells[i]], 1u)] = i;
 }
 
 cudaError_t RaySortScratch::reserve(size_t n) {
     if (n <= capacity) return cudaSuccess;
     release();
-    cudaError_t e = cudaMalloc(&keys, 2 * n * sizeof(uint64_t));
-    if (e == cudaSuccess) e = cudaMalloc(&vals, 2 * n * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&hist, (size_t)256 * radix_sort_tiles((int)n) * sizeof(uint32_t));
+    cudaError_t e = cudaMalloc(&perm, n * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&cells, n * sizeof(uint16_t));
+    if (e == cudaSuccess) e = cudaMalloc(&hist, (size_t)BIN_CELLS * sizeof(uint32_t));
     if (e != cudaSuccess) { release(); return e; }
     capacity = n;
     return cudaSuccess;
 }
 void RaySortScratch::release() {
-    if (keys) cudaFree(keys);
-    if (vals) cudaFree(vals);
+    if (perm) cudaFree(perm);
+    if (cells) cudaFree(cells);
     if (hist) cudaFree(hist);
-    keys = nullptr; vals = nullptr; hist = nullptr; capacity = 0;
+    perm = nullptr; cells = nullptr; hist = nullptr; capacity = 0;
 }
 
 cudaError_t trace_sorted(const TraceConfig& cfg, const SceneView& sv, bool any_hit, const RfwRay* d_rays, uint32_t n, RfwHit* d_hits, uint32_t* d_occluded, uint32_t* d_counter,
@@ -222,15 +242,20 @@ cudaError_t trace_sorted(const TraceConfig& cfg, const SceneView& sv, bool any_h
     if (n == 0) return cudaSuccess;
     cudaError_t e = sc.reserve(n);
     if (e != cudaSuccess) return e;
-    auto inv = [](float a, float b) { return b > a ? 32.0f / (b - a) : 0.0f; };
+    const float cells_per_axis = (float)(1 << BIN_BITS);
+    auto inv = [&](float a, float b) { return b > a ? cells_per_axis / (b - a) : 0.0f; };
     const float3 l = make_float3(lo[0], lo[1], lo[2]), scale = make_float3(inv(lo[0], hi[0]), inv(lo[1], hi[1]), inv(lo[2], hi[2]));
     const float4* rays = reinterpret_cast<const float4*>(d_rays);
-    k_ray_keys<<<(n + 255) / 256, 256, 0, cfg.stream>>>(rays, n, l, scale, sc.keys, sc.vals);
-    sc.launches++;
-    const int flip = radix_sort_pairs(sc.keys, sc.vals, sc.keys + sc.capacity, sc.vals + sc.capacity, sc.hist, (int)n, 0, 16, cfg.stream, &sc.launches);
+    e = cudaMemsetAsync(sc.hist, 0, (size_t)BIN_CELLS * sizeof(uint32_t), cfg.stream);
+    if (e != cudaSuccess) return e;
+    const unsigned count_blocks = (unsigned)std::min<uint64_t>(((uint64_t)n + 255) / 256, (uint64_t)cfg.sm_count * 8);
+    k_bin_count<<<count_blocks, 256, 0, cfg.stream>>>(rays, n, l, scale, sc.cells, sc.hist);
+    exclusive_scan_u32(sc.hist, BIN_CELLS, cfg.stream);
+    k_bin_scatter<<<(n + 255) / 256, 256, 0, cfg.stream>>>(sc.cells, n, sc.hist, sc.perm);
+    sc.launches += 3;
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    const PermutedRayIO io{RayBufferIO{rays, n, d_hits, d_occluded}, flip ? sc.vals + sc.capacity : sc.vals};
+    const PermutedRayIO io{RayBufferIO{rays, n, d_hits, d_occluded}, sc.perm};
     const TraceTuning tune{cfg.refill_below, sv.two_level ? cfg.tri_batch_two_level : cfg.tri_batch, cfg.tri_blocked, cfg.inst_batch};
     sc.launches++;
     if (any_hit) return sv.two_level ? launch_persistent_io<PermutedRayIO, true, true>(cfg.stream, cfg.sm_count, cfg.blocks_per_sm, tune, sv, io, n, d_counter)

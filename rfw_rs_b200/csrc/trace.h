@@ -37,15 +37,16 @@ uint32_t trace_streamed_warps(const TraceConfig& cfg, const SceneView& sv, bool 
 cudaError_t trace_streamed(const TraceConfig& cfg, const SceneView& sv, bool any_hit, const RfwRay* d_rays, uint32_t n, RfwHit* d_hits, uint32_t* d_occluded, uint32_t* d_counter,
                            const StreamSync& sync);
 // Ray binning for scenes whose acceleration structure does not fit the L2 (C4 / C5 sizes): rays are traced in the order of
-// a 15-bit Morton key of their origin (5 bits per axis inside `lo`..`hi`) through an index permutation; hits land at the
+// a 12-bit Morton cell of their origin (4 bits per axis inside `lo`..`hi`) through an index permutation; hits land at the
 // rays' own slots.  10 M-triangle soup: L2 hit rate 44 % and 2.7 KB of HBM traffic per ray unsorted; the KERNEL is 13 % faster on
-// pre-binned rays (scripts/exp_sorted_big.py), but the two radix passes over (u64 key, u32 index) pairs cost ~0.5 ms per 2^23
-// rays, which is what the binning saves: 1 127 vs 1 135 Mrays/s end to end.  OFF by default (option sort_rays); a one-pass
-// 4 096-bin counting sort is what would make it pay.
+// pre-binned rays (scripts/exp_sorted_big.py).  Device-side binning, measured end to end: two radix passes over (u64 key, u32
+// index) pairs 1 127 vs 1 135 Mrays/s (a wash); the one-pass counting sort used now 1 159 vs 1 133 on 10 M triangles, 1 408 vs
+// 1 374 on 5 M, but 1 564 vs 1 700 on the L2-resident 1 M-triangle scene (count + scatter + permuted I/O cost ~0.4 ms per 2^23
+// rays).  Hence option sort_rays: 0 off (default), 1 on, -1 automatic for acceleration structures beyond sort_min_bvh_mb.
 struct RaySortScratch {
-    uint64_t* keys = nullptr;     // 2 * capacity
-    uint32_t* vals = nullptr;     // 2 * capacity
-    uint32_t* hist = nullptr;
+    uint32_t* perm = nullptr;     // ray indices in cell order
+    uint16_t* cells = nullptr;    // origin cell of every ray
+    uint32_t* hist = nullptr;     // 4 096 counters, then cursors
     size_t capacity = 0;
     uint64_t launches = 0;
     cudaError_t reserve(size_t n);
