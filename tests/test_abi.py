@@ -49,6 +49,14 @@ def test_wire_layout_matches_c_header(tmp_path):
     for st, fs in fields.items():
         for f in fs:
             src.append(f'printf("{st}.{f} %zu\\n", offsetof({st}, {f}));')
+    # the ctypes repacks of the non-POD reference types and of the stats / config records
+    repacks = {"RfwAabb": wire.CAabb, "RfwMeshData3D": wire.CMeshData3D, "RfwInstancesData3D": wire.CInstancesData3D, "RfwTextureData": wire.CTextureData,
+               "RfwB200Config": wire.CConfig, "RfwBuildStats": wire.CBuildStats, "RfwTraceStats": wire.CTraceStats, "RfwRenderStats": wire.CRenderStats,
+               "RfwSkinData": wire.CSkinData}
+    for st, ct in repacks.items():
+        src.append(f'printf("sizeof:{st} %zu\\n", sizeof({st}));')
+        for name, *_ in ct._fields_:
+            src.append(f'printf("{st}.{name} %zu\\n", offsetof({st}, {name}));')
     src.append("return 0;}")
     c = tmp_path / "layout.c"
     c.write_text("\n".join(src))
@@ -61,8 +69,12 @@ def test_wire_layout_matches_c_header(tmp_path):
         dt = wire.EXPECTED_SIZES[st][0]
         for f in fs:
             assert int(out[f"{st}.{f}"]) == dt.fields[f][1], (st, f)
-    # ctypes repacks agree with the header too
+    # ctypes repacks agree with the header too: size and every field offset
     assert C.sizeof(wire.CAabb) == 32
+    for st, ct in repacks.items():
+        assert int(out[f"sizeof:{st}"]) == C.sizeof(ct), st
+        for name, *_ in ct._fields_:
+            assert int(out[f"{st}.{name}"]) == getattr(ct, name).offset, (st, name)
 
 
 def test_create_fails_loudly_without_gpu(lib):
