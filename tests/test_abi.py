@@ -77,6 +77,47 @@ def test_wire_layout_matches_c_header(tmp_path):
             assert int(out[f"{st}.{name}"]) == getattr(ct, name).offset, (st, name)
 
 
+def test_wire_layout_matches_the_reference_ffi_headers(tmp_path):
+    """Golden fixture from the reference itself: sizeof / offsetof of the C structs of its own FFI boundary
+    (backends/metal/cpp/src/structs.h + library.h, compiled where they lie by tests/golden/make_ref_layout.py) — the C side of
+    the reference's only ABI test (`test_layout`, backends/metal/src/lib.rs:270-348), which pins them to the Rust #[repr(C)]
+    types.  include/rfwb200.h must lay the same seven structs out identically, field by field."""
+    import json
+
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_metal_layout.json")))["layout"]
+    # reference C struct -> (our struct, {reference field: our field})
+    same = lambda names: {n: n for n in names}
+    mapping = {
+        "RTTriangle": ("RfwRTTriangle", same(["vertex0", "u0", "vertex1", "u1", "vertex2", "u2", "normal", "v0", "n0", "v1", "n1", "v2", "n2", "id", "tangent0", "tangent1",
+                                             "tangent2", "light_id", "mat_id", "lod", "area"])),
+        "CameraView3D": ("RfwCameraView3D", same(["pos", "right", "up", "p1", "direction", "lens_size", "spread_angle", "epsilon", "inv_width", "inv_height", "near_plane",
+                                                 "far_plane", "aspect_ratio", "fov", "custom0", "custom1"])),
+        "DeviceMaterial": ("RfwDeviceMaterial", {"c_r": "color", "a_r": "absorption", "s_r": "specular", "params_x": "parameters", "flags": "flags", "diffuse_map": "diffuse_map",
+                                                 "normal_map": "normal_map", "metallic_roughness_map": "metallic_roughness_map", "emissive_map": "emissive_map",
+                                                 "sheen_map": "sheen_map"}),
+        "Vertex3D": ("RfwVertex3D", {"v_x": "vertex", "n_x": "normal", "mat_id": "mat_id", "u": "uv", "t_x": "tangent"}),
+        "Aabb": ("RfwAabb", {"bmin": "min", "bmax": "max"}),
+        "VertexRange": ("RfwVertexMesh", same(["bounds", "first", "last", "mat_id", "padding"])),
+        "JointData": ("RfwJointData", {"j_x": "joint", "weight": "weight"}),
+    }
+    src = ['#include <stdio.h>', '#include "rfwb200.h"', "int main(void){"]
+    for ref, (ours, fields) in mapping.items():
+        src.append(f'printf("{ref} %zu\\n", sizeof({ours}));')
+        for rf, of in fields.items():
+            src.append(f'printf("{ref}.{rf} %zu\\n", offsetof({ours}, {of}));')
+    src.append("return 0;}")
+    c = tmp_path / "ref_layout.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "ref_layout"
+    subprocess.check_call(["/usr/bin/gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)])
+    out = {k: int(v) for k, v in (line.split() for line in subprocess.check_output([str(exe)]).decode().splitlines())}
+    assert len(out) >= 60
+    for k, v in out.items():
+        assert gold[k] == v, (k, gold[k], v)
+    # the fixture covers every field the reference header declares for these structs (the generator lists them all)
+    assert set(out) == set(gold)
+
+
 def test_create_fails_loudly_without_gpu(lib):
     import torch
 
