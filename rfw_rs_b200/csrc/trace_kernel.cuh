@@ -31,7 +31,10 @@ namespace rfw {
 
 static constexpr uint32_t FULL = 0xFFFFFFFFu;
 static constexpr int PT_THREADS = 128;
-static constexpr int PT_SM_STACK = 12;
+#ifndef RFW_PT_SM_STACK
+#define RFW_PT_SM_STACK 12
+#endif
+static constexpr int PT_SM_STACK = RFW_PT_SM_STACK;
 // Leaf groups a lane may set aside while it keeps traversing (speculative traversal, single-level kernels).  MEASURED AND
 // SWITCHED OFF (0): on C2 every setting lost to the non-speculative kernel (best 1 494 vs 1 557 Mrays/s; 1 229 with deep
 // speculation) — 82 % of the rays hit something, and walking on with a stale (too long) hit distance visits far more
