@@ -1321,6 +1321,32 @@ int orc_triangle_test(const RfwRTTriangle* tri, const RfwRay* ray, float det_eps
     tuv[0] = t; tuv[1] = u; tuv[2] = v;
     return 1;
 }
+// batch hooks for tests/test_hostemu.py::test_shading_functions_match_the_oracle — 12 floats out per item:
+// eval(N, wo, wi) rgb | pdf(N, wo, wi) | sampled wi xyz | sample pdf | eval with t / back-facing (absorption path) rgb | 0
+void orc_bsdf_batch(const RfwDeviceMaterial* mats, uint32_t n, const float* N, const float* T, const float* B, const float* wo, const float* wi, const float* r, float* out) {
+    for (uint32_t i = 0; i < n; i++) {
+        const ShadingData sd = extract(mats[i]);
+        const V3 n3(N + 3 * i), t3(T + 3 * i), b3(B + 3 * i), o3(wo + 3 * i), i3(wi + 3 * i);
+        const V3 e = BSDFEval(sd, n3, o3, i3, 0.0f, false);
+        V3 s(0.0f); float spdf = 0.0f; int type = 0;
+        BSDFSample(sd, t3, b3, n3, o3, s, spdf, type, r[2 * i], r[2 * i + 1]);
+        const V3 eb = BSDFEval(sd, n3, o3, i3, 0.7f, true);
+        float* q = out + 12 * (size_t)i;
+        q[0] = e.x; q[1] = e.y; q[2] = e.z; q[3] = BSDFPdf(sd, n3, o3, i3);
+        q[4] = s.x; q[5] = s.y; q[6] = s.z; q[7] = spdf;
+        q[8] = eb.x; q[9] = eb.y; q[10] = eb.z; q[11] = 0.0f;
+    }
+}
+// 8 floats out per item: sampled point xyz | pickProb | lightPdf | light colour rgb
+void orc_light_batch(void* sp, uint32_t n, const float* r0, const float* I, const float* N, float* out) {
+    const Scene& sc = *(Scene*)sp;
+    for (uint32_t i = 0; i < n; i++) {
+        float pick = 0.0f, lpdf = 0.0f; V3 col(0.0f);
+        const V3 P = random_point_on_light(sc, r0[i], 0.0f, V3(I + 3 * i), V3(N + 3 * i), pick, lpdf, col);
+        float* q = out + 8 * (size_t)i;
+        q[0] = P.x; q[1] = P.y; q[2] = P.z; q[3] = pick; q[4] = lpdf; q[5] = col.x; q[6] = col.y; q[7] = col.z;
+    }
+}
 uint32_t orc_wang_hash(uint32_t s) { return wang_hash(s); }
 float orc_randf(uint32_t* s) { return randf(*s); }
 void orc_random_barycentrics(float r0, float* out) { V3 b = random_barycentrics(r0); out[0] = b.x; out[1] = b.y; out[2] = b.z; }

@@ -1,0 +1,67 @@
+// Host logic harness, part 2: the PRODUCT's shading functions (rfw_rs_b200/csrc/shading.cuh — Disney BSDF evaluation /
+// pdf / sampling, light sampling, RandomBarycentrics, safe_origin, the RNG) compiled for the CPU, unmodified, so that the
+// CPU test tier can hold them against the oracle's independent restatement of the same reference shaders on random
+// inputs.  Test infrastructure only: librfwb200.so contains no host execution path for any of this.
+//
+// shading.cuh is device code; the few device-only spellings it uses are given host meanings here, before it is included.
+#include <cuda_runtime.h>  // float3 / float4 vector types (usable from plain g++)
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#undef __device__
+#undef __forceinline__
+#undef __noinline__
+#define __device__
+#define __forceinline__ inline
+#define __noinline__
+template <typename T>
+static inline T __ldg(const T* p) { return *p; }
+static inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
+static inline int __float_as_int(float f) { int v; memcpy(&v, &f, 4); return v; }
+static inline float __uint_as_float(uint32_t v) { float f; memcpy(&f, &v, 4); return f; }
+static inline uint32_t __float_as_uint(float f) { uint32_t v; memcpy(&v, &f, 4); return v; }
+static inline int min(int a, int b) { return a < b ? a : b; }   // CUDA's global integer min / max
+static inline int max(int a, int b) { return a > b ? a : b; }
+
+#include "../../rfw_rs_b200/csrc/shading.cuh"
+
+using namespace rfw;
+
+extern "C" {
+// same record layout as orc_bsdf_batch (oracle/oracle.cpp)
+void emu_bsdf_batch(const RfwDeviceMaterial* mats, uint32_t n, const float* N, const float* T, const float* B, const float* wo, const float* wi, const float* r, float* out) {
+    for (uint32_t i = 0; i < n; i++) {
+        const ShadingData sd = extract_material(mats + i);
+        const float3 n3 = ld3(N + 3 * i), t3 = ld3(T + 3 * i), b3 = ld3(B + 3 * i), o3 = ld3(wo + 3 * i), i3 = ld3(wi + 3 * i);
+        const float3 e = bsdf_eval(sd, n3, o3, i3, 0.0f, false);
+        float3 s = f3(0, 0, 0);
+        float spdf = 0.0f;
+        bsdf_sample(sd, t3, b3, n3, o3, s, spdf, r[2 * i], r[2 * i + 1]);
+        const float3 eb = bsdf_eval(sd, n3, o3, i3, 0.7f, true);
+        float* q = out + 12 * (size_t)i;
+        q[0] = e.x; q[1] = e.y; q[2] = e.z; q[3] = bsdf_pdf(sd, n3, o3, i3);
+        q[4] = s.x; q[5] = s.y; q[6] = s.z; q[7] = spdf;
+        q[8] = eb.x; q[9] = eb.y; q[10] = eb.z; q[11] = 0.0f;
+    }
+}
+// same record layout as orc_light_batch
+void emu_light_batch(const RfwAreaLight* area, uint32_t na, const RfwPointLight* point, uint32_t np, const RfwSpotLight* spot, uint32_t ns, const RfwDirectionalLight* dir,
+                     uint32_t nd, uint32_t n, const float* r0, const float* I, const float* N, float* out) {
+    ShadeScene ss;
+    memset(&ss, 0, sizeof(ss));
+    ss.area = area; ss.point = point; ss.spot = spot; ss.dir = dir;
+    ss.n_area = (int)na; ss.n_point = (int)np; ss.n_spot = (int)ns; ss.n_dir = (int)nd;
+    for (uint32_t i = 0; i < n; i++) {
+        float pick = 0.0f, lpdf = 0.0f;
+        float3 col = f3(0, 0, 0);
+        const float3 P = random_point_on_light(ss, r0[i], ld3(I + 3 * i), ld3(N + 3 * i), pick, lpdf, col);
+        float* q = out + 8 * (size_t)i;
+        q[0] = P.x; q[1] = P.y; q[2] = P.z; q[3] = pick; q[4] = lpdf; q[5] = col.x; q[6] = col.y; q[7] = col.z;
+    }
+}
+uint32_t emu_wang_hash(uint32_t s) { return wang_hash(s); }
+float emu_randf(uint32_t* s) { return randf(*s); }
+void emu_random_barycentrics(float r0, float* out) { const float3 b = random_barycentrics(r0); out[0] = b.x; out[1] = b.y; out[2] = b.z; }
+void emu_safe_origin(const float* O, const float* R, const float* N, float* out) { const float3 p = safe_origin(ld3(O), ld3(R), ld3(N)); out[0] = p.x; out[1] = p.y; out[2] = p.z; }
+}

@@ -154,3 +154,93 @@ def test_authored_asset_precision(emu, oracle_mod):
     ref = o.trace_closest(rays, mode=oracle_mod.MODE_BVH2)
     assert (ref["inst"] >= 0).sum() > 5000
     parity.compare_hits(rays, hits, ref, parity.lookup_from_desc(flat), "cesium_man/emu", max_fraction=1e-4)
+
+
+# ---- the product's shading functions (rfw_rs_b200/csrc/shading.cuh) on the CPU tier ---------------------------------------
+@pytest.fixture(scope="module")
+def shade_emu():
+    subprocess.check_call(["make", "-C", os.path.join(HERE, "hostemu"), "-s"])
+    L = C.CDLL(os.path.join(HERE, "hostemu", "libshade_emu.so"))
+    vp = C.c_void_p
+    L.emu_bsdf_batch.argtypes = [vp, C.c_uint32, vp, vp, vp, vp, vp, vp, vp]
+    L.emu_light_batch.argtypes = [vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
+    L.emu_wang_hash.argtypes = [C.c_uint32]; L.emu_wang_hash.restype = C.c_uint32
+    L.emu_randf.argtypes = [vp]; L.emu_randf.restype = C.c_float
+    L.emu_random_barycentrics.argtypes = [C.c_float, vp]
+    L.emu_safe_origin.argtypes = [vp, vp, vp, vp]
+    return L
+
+
+def _unit(v):
+    return (v / np.linalg.norm(v, axis=1, keepdims=True)).astype(np.float32)
+
+
+def _close(a, b, rtol, atol):
+    return np.abs(a.astype(np.float64) - b.astype(np.float64)) <= atol + rtol * np.maximum(np.abs(a), np.abs(b))
+
+
+def test_shading_functions_match_the_oracle(shade_emu, oracle_mod):
+    """SURVEY §8 rows a7 / a15 / a16 without a GPU: the PRODUCT's shading source (shading.cuh, compiled for the host unmodified by
+    tests/hostemu/shade_emu.cpp) against the oracle's independent restatement of the same reference shaders (disney.glsl,
+    shade.comp:283-528, random.glsl, utils.glsl:83-92) on random inputs: every Disney lobe (random u8-packed parameters),
+    BSDF evaluation front- and back-facing (absorption), pdf, sampling, all four light types, RandomBarycentrics, safe_origin
+    and the RNG.  The two are different code bases compiled with different floating-point contraction, so values agree to
+    rounding; a value that differs belongs to an input sitting on a branch threshold (lobe pick, hemisphere test) and such
+    inputs must be rare."""
+    n = 40000
+    rng = np.random.default_rng(20260101)
+    lib = oracle_mod.lib()
+    # --- BSDF -------------------------------------------------------------------------------------------------------------
+    mats = np.concatenate([scenes.material(color=rng.uniform(0.05, 1.0, 3), metallic=rng.choice([0.0, 1.0, rng.uniform()]), roughness=rng.uniform(0.02, 1.0),
+                                           specular_f=rng.uniform(), subsurface=rng.choice([0.0, rng.uniform()]), specular=rng.uniform(0.2, 1.0, 3),
+                                           transmission=rng.choice([0.0, 1.0, rng.uniform()]), eta=rng.uniform(0.4, 1.0), clearcoat=rng.choice([0.0, rng.uniform()]),
+                                           clearcoat_gloss=rng.uniform(), specular_tint=rng.uniform(), absorption=rng.uniform(0.0, 1.0, 3)) for _ in range(256)])
+    mats = np.ascontiguousarray(mats[rng.integers(0, len(mats), n)])
+    N = _unit(rng.normal(size=(n, 3)))
+    T = _unit(np.cross(N, _unit(rng.normal(size=(n, 3)))))
+    B = np.cross(N, T).astype(np.float32)
+    wo = _unit(rng.normal(size=(n, 3))); wo = np.where((np.einsum("ij,ij->i", wo, N) < 0)[:, None], -wo, wo).astype(np.float32)  # the viewer is above the surface
+    wi = _unit(rng.normal(size=(n, 3)))                                                                                          # the light anywhere (reflection and transmission)
+    r = rng.uniform(size=(n, 2)).astype(np.float32)
+    out_e = np.zeros((n, 12), np.float32); out_o = np.zeros((n, 12), np.float32)
+    args = [np.ascontiguousarray(a) for a in (N, T, B, wo, wi, r)]
+    shade_emu.emu_bsdf_batch(mats.ctypes.data, n, *[a.ctypes.data for a in args], out_e.ctypes.data)
+    lib.orc_bsdf_batch(C.c_void_p(mats.ctypes.data), C.c_uint32(n), *[C.c_void_p(a.ctypes.data) for a in args], C.c_void_p(out_o.ctypes.data))
+    assert np.isfinite(out_o[:, :4]).all() and (out_o[:, :3] >= 0).all() and (out_o[:, :3].max(axis=1) > 0).mean() > 0.5
+    for name, cols in (("eval", slice(0, 3)), ("pdf", slice(3, 4)), ("sampled direction", slice(4, 7)), ("sample pdf", slice(7, 8)), ("eval back-facing", slice(8, 11))):
+        a, b = out_e[:, cols], out_o[:, cols]
+        both_nan = np.isnan(a) & np.isnan(b)
+        ok = (_close(a, b, 2e-4, 1e-6) | both_nan).all(axis=1)
+        assert ok.mean() > 0.998, (name, float(ok.mean()), a[~ok][:3], b[~ok][:3])
+    # --- lights -----------------------------------------------------------------------------------------------------------
+    desc = scenes.lights_and_lobes_scene(grid=3, subdiv=1)
+    o = oracle_mod.OracleBackend(); desc.apply(o)
+    r0 = rng.uniform(size=n).astype(np.float32)
+    I = rng.uniform(-3.0, 3.0, size=(n, 3)).astype(np.float32); I[:, 1] = rng.uniform(0.0, 1.0, n)
+    Nl = _unit(rng.normal(size=(n, 3)) + np.array([0.0, 1.5, 0.0]))
+    lo_e = np.zeros((n, 8), np.float32); lo_o = np.zeros((n, 8), np.float32)
+    al, pl, sl, dl = (np.ascontiguousarray(x) for x in (desc.area_lights, desc.point_lights, desc.spot_lights, desc.directional_lights))
+    assert len(al) and len(pl) and len(sl) and len(dl)
+    shade_emu.emu_light_batch(al.ctypes.data, len(al), pl.ctypes.data, len(pl), sl.ctypes.data, len(sl), dl.ctypes.data, len(dl), n, r0.ctypes.data, I.ctypes.data,
+                              Nl.ctypes.data, lo_e.ctypes.data)
+    lib.orc_light_batch(o.h, C.c_uint32(n), C.c_void_p(r0.ctypes.data), C.c_void_p(I.ctypes.data), C.c_void_p(Nl.ctypes.data), C.c_void_p(lo_o.ctypes.data))
+    assert (lo_o[:, 4] > 0).mean() > 0.3                       # many samples face their light
+    assert len(np.unique(np.round(lo_o[:, 5:8], 3), axis=0)) >= 4  # every light type was picked (distinct radiances)
+    ok = _close(lo_e, lo_o, 2e-4, 1e-5).all(axis=1)
+    assert ok.mean() > 0.999, (float(ok.mean()), lo_e[~ok][:3], lo_o[~ok][:3])
+    # --- RNG, RandomBarycentrics, safe_origin: bit-exact ---------------------------------------------------------------------
+    for s in (0, 1, 12345, 0xDEADBEEF, 0xFFFFFFFF):
+        assert shade_emu.emu_wang_hash(s) == lib.orc_wang_hash(C.c_uint32(s))
+        se, so = C.c_uint32(s | 1), C.c_uint32(s | 1)
+        lib.orc_randf.restype = C.c_float
+        for _ in range(8):
+            assert shade_emu.emu_randf(C.addressof(se)) == lib.orc_randf(C.byref(so)) and se.value == so.value
+    be, bo = np.zeros(3, np.float32), np.zeros(3, np.float32)
+    for x in rng.uniform(size=2000).astype(np.float32):
+        shade_emu.emu_random_barycentrics(float(x), be.ctypes.data); lib.orc_random_barycentrics(C.c_float(float(x)), C.c_void_p(bo.ctypes.data))
+        assert np.allclose(be, bo, rtol=0, atol=2e-7) and abs(float(bo.sum()) - 1.0) < 1e-5
+    for k in range(2000):
+        O3 = (rng.normal(size=3) * 10.0 ** rng.integers(-3, 3)).astype(np.float32); R3 = _unit(rng.normal(size=(1, 3)))[0]; N3 = _unit(rng.normal(size=(1, 3)))[0]
+        shade_emu.emu_safe_origin(O3.ctypes.data, R3.ctypes.data, N3.ctypes.data, be.ctypes.data)
+        lib.orc_safe_origin(C.c_void_p(O3.ctypes.data), C.c_void_p(R3.ctypes.data), C.c_void_p(N3.ctypes.data), C.c_void_p(bo.ctypes.data))
+        assert np.array_equal(be, bo), (O3, R3, N3, be, bo)
