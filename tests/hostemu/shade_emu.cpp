@@ -60,6 +60,18 @@ void emu_light_batch(const RfwAreaLight* area, uint32_t na, const RfwPointLight*
         q[0] = P.x; q[1] = P.y; q[2] = P.z; q[3] = pick; q[4] = lpdf; q[5] = col.x; q[6] = col.y; q[7] = col.z;
     }
 }
+// texture.cuh samplers on an RGBA8 mip chain (the layout Backend::set_textures produces: BGRA inputs already swizzled).
+// mode 0 fetchTexel(level), 1 trilinear(lambda), 2 skybox level (clamp, bilinear), 3 sky_sample(direction = (u, v, lod) normalised, level 0)
+void emu_sample_texture(const uint8_t* rgba, uint32_t w, uint32_t h, uint32_t mips, int mode, float u, float v, float lod, float* out) {
+    TexDesc t;
+    t.texels = reinterpret_cast<const uchar4*>(rgba); t.width = w; t.height = h; t.mip_levels = mips; t.pad = 0;
+    float4 c = f4(0, 0, 0, 0);
+    if (mode == 0) c = tex_fetch(t, u, v, (int)lod);
+    else if (mode == 1) c = tex_fetch_trilinear(t, lod, u, v);
+    else if (mode == 2) c = tex_sample_level(t, u, v, (int)lod, false, true);
+    else { const float3 d = sky_sample(t, normalize3(f3(u, v, lod)), 0); c = f4(d.x, d.y, d.z, 1.0f); }
+    out[0] = c.x; out[1] = c.y; out[2] = c.z; out[3] = c.w;
+}
 uint32_t emu_wang_hash(uint32_t s) { return wang_hash(s); }
 float emu_randf(uint32_t* s) { return randf(*s); }
 void emu_random_barycentrics(float r0, float* out) { const float3 b = random_barycentrics(r0); out[0] = b.x; out[1] = b.y; out[2] = b.z; }
