@@ -13,6 +13,7 @@
 #include <algorithm>
 
 #include "shading.cuh"
+#include "shade_path.cuh"
 #include "trace_kernel.cuh"
 #include "wavefront.h"
 
@@ -23,15 +24,6 @@ namespace rfw {
         cudaError_t e_ = (x);             \
         if (e_ != cudaSuccess) return e_; \
     } while (0)
-
-struct FrameParams {
-    RfwCameraView3D cam;
-    uint32_t width, height, tile, tiles_x, max_paths;
-    uint32_t sample, path_length;  // sample = index of the wave's first sample; a path's own sample = sample + its wave slot b
-    uint32_t wave_spp, npix;       // samples per wave; pixels per frame (stride of the per-sample partial accumulators)
-    float clamp_value;
-    float sky[3];
-};
 
 __device__ __forceinline__ bool slot_to_pixel(const FrameParams& fp, const uint32_t* __restrict__ owned_tiles, uint32_t slot, uint32_t& pixel) {
     const uint32_t tt = fp.tile * fp.tile;
@@ -52,24 +44,7 @@ __global__ void __launch_bounds__(256) k_wf_generate(FrameParams fp, const uint3
     uint32_t pixel = 0;
     const bool valid = b < fp.wave_spp && slot_to_pixel(fp, owned_tiles, slot, pixel);
     float3 o = f3(0, 0, 0), d = f3(0, 0, 1);
-    if (valid) {
-        uint32_t seed = wang_hash(pixel * 16789u + (fp.sample + b) * 1791u);
-        const int sx = (int)(pixel % fp.width), sy = (int)(pixel / fp.width);
-        float r0 = randf(seed), r1 = randf(seed), r2 = randf(seed), r3 = randf(seed);
-        const float blade = (float)(int)(r0 * 9.0f);
-        r2 = (r2 - blade * (1.0f / 9.0f)) * 9.0f;
-        const float piOver4point5 = 3.14159265359f / 4.5f;
-        const float x1 = cosf(blade * piOver4point5), y1 = sinf(blade * piOver4point5);
-        const float x2 = cosf((blade + 1.0f) * piOver4point5), y2 = sinf((blade + 1.0f) * piOver4point5);
-        if ((r2 + r3) > 1.0f) { r2 = 1.0f - r2; r3 = 1.0f - r3; }
-        const float xr = x1 * r2 + x2 * r3, yr = y1 * r2 + y2 * r3;
-        const float3 right = ld3(fp.cam.right), up = ld3(fp.cam.up);
-        o = ld3(fp.cam.pos) + (right * xr + up * yr) * fp.cam.lens_size;
-        const float u = ((float)sx + r0) * (1.0f / (float)fp.width);
-        const float v = ((float)sy + r1) * (1.0f / (float)fp.height);
-        const float3 p = ld3(fp.cam.p1) + right * u + up * v;
-        d = normalize3(p - o);
-    }
+    if (valid) eye_ray(fp, pixel, b, o, d);
     // queue slots: ONE atomicAdd per CTA (a 16-spp 1080p wave is a million warps: one same-address atomic per warp was the
     // kernel's bound), warp offsets through shared memory
     __shared__ uint32_t s_warp[8];
@@ -114,7 +89,7 @@ struct ExtendIO {
         r1.w = 1e26f;
     }
     __device__ __forceinline__ void store_closest(uint32_t i, const Hit& h) const {
-        const uint32_t bary = (uint32_t)(65535.0f * h.u) + ((uint32_t)(65535.0f * h.v) << 16);  // ray_extend.comp:267
+        const uint32_t bary = pack_bary16(h.u, h.v);  // ray_extend.comp:267
         S[i] = f4(__int_as_float(h.inst), __int_as_float(h.prim), h.t, __uint_as_float(bary));
     }
     __device__ __forceinline__ void store_any(uint32_t, bool) const {}
@@ -179,132 +154,20 @@ __global__ void __launch_bounds__(RFW_SHADE_THREADS, RFW_SHADE_MIN_BLOCKS) k_wf_
         const uint32_t k = base + lane;
 #endif
         const bool valid = k < count;
-        bool emit_ext = false, emit_sh = false;
-        float3 nO = f3(0, 0, 0), nD = f3(0, 0, 1), nT = f3(0, 0, 0);
-        float nPdf = 0.0f;
-        float3 sO = f3(0, 0, 0), sD = f3(0, 0, 1), sE = f3(0, 0, 0);
-        float sDist = 0.0f;
+        ShadeOut so;
+        so.add = false; so.emit_ext = false; so.emit_sh = false;
         uint32_t pixel = 0, wave_b = 0;
         if (valid) {
             const float4 s4 = S[k], o4 = O[k], d4 = D[k];
             const float4 t4 = fp.path_length == 0 ? f4(1.0f, 1.0f, 1.0f, 1.0f) : T[k];
             pixel = __float_as_uint(o4.w);
             wave_b = __float_as_uint(d4.w);
-            const int inst = __float_as_int(s4.x), prim = __float_as_int(s4.y);
-            const float t = s4.z;
-            const float3 Dv = xyz(d4), Ov = xyz(o4);
-            float3 throughput = xyz(t4);
-            const float bsdfPdf = t4.w;
-            float3 contrib = f3(0, 0, 0);
-            bool add = false;
-            if (inst < 0) {  // :90-96: equirect skybox at mip level path_length (constant colour until set_skybox is called)
-                const float3 skyc = ss.has_sky ? sky_sample(ss.sky, Dv, (int)fp.path_length) : f3(fp.sky[0], fp.sky[1], fp.sky[2]);
-                contrib = throughput * skyc * (1.0f / bsdfPdf);
-                clamp_intensity(contrib, fp.clamp_value);
-                add = true;
-            } else {
-                const InstanceShading* is = ss.inst + inst;
-                const float4* tp = reinterpret_cast<const float4*>(is->tris + prim);
-                const float4 q3 = __ldg(tp + 3), q4 = __ldg(tp + 4), q5 = __ldg(tp + 5), q6 = __ldg(tp + 6);  // normal|v0, n0|v1, n1|v2, n2|id
-                const float4 q7 = __ldg(tp + 7), q8 = __ldg(tp + 8), q9 = __ldg(tp + 9), q10 = __ldg(tp + 10);  // T0, T1, T2, light_id|mat_id|lod|area
-                const int mat_id = __float_as_int(q10.y);
-                const float tri_area = q10.w;
-                ShadingData sd = extract_material(ss.materials + mat_id);
-                const uint32_t mflags = __ldg(&ss.materials[mat_id].flags);
-                const bool has_maps = (mflags & 0x3Fu) != 0u;  // :120, :162
-                uint32_t seed = wang_hash(pixel * 16789u + (fp.sample + wave_b) * 1791u + fp.path_length * 720898027u);  // :102-103
-                const uint32_t bary = __float_as_uint(s4.w);
-                const float u = (float)(bary & 65535u) * (1.0f / 65535.0f), v = (float)(bary >> 16) * (1.0f / 65535.0f);
-                const float w = 1.0f - u - v;
-                float3 gN = xyz(q3);
-                float3 N = xyz(q4) * w + xyz(q5) * u + xyz(q6) * v;
-                float3 T3 = xyz(q7) * w + xyz(q8) * u + xyz(q9) * v;
-                const float Tw = w * q7.w + u * q8.w + v * q9.w;
-                const float4 m0 = is->nrm0, m1 = is->nrm1, m2 = is->nrm2;
-                gN = normalize3(f3(m0.x * gN.x + m0.y * gN.y + m0.z * gN.z, m1.x * gN.x + m1.y * gN.y + m1.z * gN.z, m2.x * gN.x + m2.y * gN.y + m2.z * gN.z));
-                N = normalize3(f3(m0.x * N.x + m0.y * N.y + m0.z * N.z, m1.x * N.x + m1.y * N.y + m1.z * N.z, m2.x * N.x + m2.y * N.y + m2.z * N.z));
-                T3 = normalize3(f3(m0.x * T3.x + m0.y * T3.y + m0.z * T3.z, m1.x * T3.x + m1.y * T3.y + m1.z * T3.z, m2.x * T3.x + m2.y * T3.y + m2.z * T3.z));
-                const float3 B = cross3(N, T3) * Tw;
-                const float3 P = Ov + Dv * t;
-                if ((sd.color.x > 1.0f || sd.color.y > 1.0f || sd.color.z > 1.0f) && !(mflags & 16u)) {  // hit a light, :128-160
-                    const float DdotNL = -dot3(Dv, N);
-                    if (DdotNL > 0.0f) {
-                        if (fp.path_length == 0) {
-                            contrib = throughput * sd.color * (1.0f / bsdfPdf);
-                        } else {
-                            const float lightPdf = (t * t) / (-dot3(Dv, N) * tri_area);  // :327-330
-                            const float pickProb = 1.0f / (float)lightCount;               // :368
-                            if ((bsdfPdf + lightPdf * pickProb) > 0.0f) contrib = throughput * sd.color * (1.0f / (bsdfPdf + lightPdf * pickProb));
-                        }
-                        clamp_intensity(contrib, fp.clamp_value);
-                    }
-                    add = true;
-                } else {
-                    if (has_maps) {  // :162-175
-                        const float lambda = sqrtf(q10.z) + log2f(fp.cam.spread_angle * (1.0f / fabsf(dot3(Dv, N))));
-                        const float4 q0 = __ldg(tp + 0), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);  // vertex|tu
-                        const float tu = w * q0.w + u * q1.w + v * q2.w;
-                        const float tv = w * q3.w + u * q4.w + v * q5.w;
-                        const int dmap = __ldg(&ss.materials[mat_id].diffuse_map), nmap = __ldg(&ss.materials[mat_id].normal_map);
-                        if ((mflags & 1u) && dmap >= 0 && (uint32_t)dmap < ss.n_textures) {
-                            const float4 c = tex_fetch_trilinear(ss.textures[dmap], lambda, tu, tv);
-                            sd.color = sd.color * f3(c.x, c.y, c.z);
-                        }
-                        if ((mflags & 2u) && nmap >= 0 && (uint32_t)nmap < ss.n_textures) {
-                            const float4 c = tex_fetch(ss.textures[nmap], tu, tv, (int)lambda);
-                            const float3 m = f3((c.x - 0.5f) * 2.0f, (c.y - 0.5f) * 2.0f, (c.z - 0.5f) * 2.0f);
-                            N = normalize3(T3 * m.x + B * m.y + N * m.z);  // mat3(T, B, N) * m
-                        }
-                    }
-                    const bool backFacing = dot3(Dv, gN) >= 0.0f;  // :177-181
-                    if (backFacing) { N = N * -1.0f; gN = gN * -1.0f; }
-                    throughput = throughput * (1.0f / bsdfPdf);  // :183
-                    const float r1 = randf(seed), r2 = randf(seed);
-                    const float3 wo = Dv * -1.0f;
-                    float3 R = f3(0, 0, 1);
-                    float newPdf = 0.0f;
-                    bsdf_sample(sd, T3, B, gN, wo, R, newPdf, r1, r2);                       // sampling frame: geometric normal (disney.glsl:275-285)
-                    const float3 bsdf = bsdf_eval(sd, N, wo, R, t, backFacing);             // evaluation: shading normal
-                    throughput = throughput * bsdf * fabsf(dot3(N, R));
-                    throughput = f3(throughput.x > 0.0f ? throughput.x : 0.0f, throughput.y > 0.0f ? throughput.y : 0.0f, throughput.z > 0.0f ? throughput.z : 0.0f);
-                    if (!(newPdf <= 1e-4f || isnan(newPdf))) {  // :208
-                        if (lightCount > 0) {                   // :213-258
-                            const float r3 = randf(seed);
-                            (void)randf(seed);  // r4 is drawn but unused by the uniform light pick
-                            float3 lightColor;
-                            float pickProb, lightPdf;
-                            float3 L = random_point_on_light(ss, r3, P, N, pickProb, lightPdf, lightColor) - P;
-                            const float dist = length3(L);
-                            L = L * (1.0f / dist);
-                            const float NdotL = dot3(L, N);
-                            if (NdotL > 0.0f && lightPdf > 0.0f) {
-                                const float3 sampled = bsdf_eval(sd, gN, wo, L, 0.0f, false);  // :235-239
-                                const float shadowPdf = bsdf_pdf(sd, gN, wo, L);
-                                if (shadowPdf > 0.0f) {
-                                    float3 c = throughput * sampled * lightColor * (NdotL / (lightPdf * pickProb));
-                                    if (!(isnan(c.x) || isnan(c.y) || isnan(c.z))) {
-                                        clamp_intensity(c, fp.clamp_value);
-                                        emit_sh = true;
-                                        sO = safe_origin(P, L, gN);
-                                        sD = L;
-                                        sDist = dist - 1e-4f;  // :253
-                                        sE = c;
-                                    }
-                                }
-                            }
-                        }
-                        emit_ext = true;  // :261-265
-                        nO = safe_origin(P, R, gN);
-                        nD = R;
-                        nT = throughput;
-                        nPdf = newPdf;
-                    }
-                }
-            }
-            if (add && (contrib.x != 0.0f || contrib.y != 0.0f || contrib.z != 0.0f)) {
-                red_add_rgb(accum + 4 * ((size_t)wave_b * fp.npix + pixel), contrib.x, contrib.y, contrib.z);
+            shade_path(fp, ss, lightCount, s4, o4, d4, t4, so);
+            if (so.add && (so.contrib.x != 0.0f || so.contrib.y != 0.0f || so.contrib.z != 0.0f)) {
+                red_add_rgb(accum + 4 * ((size_t)wave_b * fp.npix + pixel), so.contrib.x, so.contrib.y, so.contrib.z);
             }
         }
+        const bool emit_ext = so.emit_ext, emit_sh = so.emit_sh;
         // queue compaction: one atomic per warp per queue
         const uint32_t ms = __ballot_sync(FULL, emit_sh);
         const uint32_t me = __ballot_sync(FULL, emit_ext);
@@ -336,15 +199,15 @@ __global__ void __launch_bounds__(RFW_SHADE_THREADS, RFW_SHADE_MIN_BLOCKS) k_wf_
 #endif
         if (emit_sh) {
             const uint32_t j = bs + __popc(ms & ((1u << lane) - 1u));
-            shO[j] = f4(sO.x, sO.y, sO.z, 0.0f);
-            shD[j] = f4(sD.x, sD.y, sD.z, sDist);
-            shE[j] = f4(sE.x, sE.y, sE.z, __uint_as_float(wave_b * fp.npix + pixel));  // index into the partial accumulators
+            shO[j] = f4(so.sO.x, so.sO.y, so.sO.z, 0.0f);
+            shD[j] = f4(so.sD.x, so.sD.y, so.sD.z, so.sDist);
+            shE[j] = f4(so.sE.x, so.sE.y, so.sE.z, __uint_as_float(wave_b * fp.npix + pixel));  // index into the partial accumulators
         }
         if (emit_ext) {
             const uint32_t j = be + __popc(me & ((1u << lane) - 1u));
-            On[j] = f4(nO.x, nO.y, nO.z, __uint_as_float(pixel));
-            Dn[j] = f4(nD.x, nD.y, nD.z, __uint_as_float(wave_b));
-            Tn[j] = f4(nT.x, nT.y, nT.z, nPdf);
+            On[j] = f4(so.nO.x, so.nO.y, so.nO.z, __uint_as_float(pixel));
+            Dn[j] = f4(so.nD.x, so.nD.y, so.nD.z, __uint_as_float(wave_b));
+            Tn[j] = f4(so.nT.x, so.nT.y, so.nT.z, so.nPdf);
         }
     }
 }

@@ -193,6 +193,8 @@ void emu_build(void* s, float c_node, float c_prim, int pmax, uint64_t* stats) {
     if (stats) { stats[0] = tot_nodes; stats[1] = sc.tlas.nodes.size() / NODE_F4; stats[2] = sc.recs.size(); }
 }
 
+// the traversal view of the built scene, for the CPU path tracer of shade_emu.cpp (same header, same struct)
+const void* emu_scene_view(void* s) { return &((EmuScene*)s)->sv; }
 void emu_trace(void* s, const RfwRay* rays, uint64_t n, RfwHit* hits, uint32_t* occluded, uint64_t* counters) {
     EmuScene& sc = *(EmuScene*)s;
     TraceCounters ctr{0, 0, 0};

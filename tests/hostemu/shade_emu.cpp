@@ -25,6 +25,7 @@ static inline int min(int a, int b) { return a < b ? a : b; }   // CUDA's global
 static inline int max(int a, int b) { return a > b ? a : b; }
 
 #include "../../rfw_rs_b200/csrc/shading.cuh"
+#include "../../rfw_rs_b200/csrc/shade_path.cuh"
 
 using namespace rfw;
 
@@ -71,6 +72,54 @@ void emu_sample_texture(const uint8_t* rgba, uint32_t w, uint32_t h, uint32_t mi
     else if (mode == 2) c = tex_sample_level(t, u, v, (int)lod, false, true);
     else { const float3 d = sky_sample(t, normalize3(f3(u, v, lod)), 0); c = f4(d.x, d.y, d.z, 1.0f); }
     out[0] = c.x; out[1] = c.y; out[2] = c.z; out[3] = c.w;
+}
+// The product's path tracer run serially on the CPU: eye_ray -> { trace_ray (closest) -> shade_path -> trace_ray (any-hit) } x depth,
+// i.e. what Wavefront::render does with its queues (wavefront.cu), one path at a time.  Per-sample contributions are summed
+// in stage order and the samples folded in sample order, as k_wf_reduce does.  acc: h*w*4 floats, accumulated into.
+void emu_render(const SceneView* sv, const InstanceShading* inst_table, const RfwDeviceMaterial* mats, uint32_t n_mats, const RfwAreaLight* area, uint32_t na,
+                const RfwPointLight* point, uint32_t np, const RfwSpotLight* spot, uint32_t ns, const RfwDirectionalLight* dir, uint32_t nd, const RfwCameraView3D* cam,
+                uint32_t w, uint32_t h, uint32_t first_sample, uint32_t spp, uint32_t depth, float clamp_value, const float* sky, float* acc, uint64_t* stats) {
+    ShadeScene ss;
+    memset(&ss, 0, sizeof(ss));
+    ss.inst = inst_table; ss.materials = mats; ss.n_materials = n_mats;
+    ss.area = area; ss.point = point; ss.spot = spot; ss.dir = dir;
+    ss.n_area = (int)na; ss.n_point = (int)np; ss.n_spot = (int)ns; ss.n_dir = (int)nd;
+    const int lightCount = ss.n_area + ss.n_point + ss.n_spot + ss.n_dir;
+    FrameParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.cam = *cam; fp.width = w; fp.height = h; fp.npix = w * h; fp.sample = first_sample; fp.wave_spp = spp;
+    fp.clamp_value = clamp_value; fp.sky[0] = sky[0]; fp.sky[1] = sky[1]; fp.sky[2] = sky[2];
+    uint64_t n_ext = 0, n_sh = 0;
+    for (uint32_t pixel = 0; pixel < w * h; pixel++) {
+        for (uint32_t b = 0; b < spp; b++) {
+            float3 part = f3(0, 0, 0);  // this sample's partial accumulator
+            float3 o, d;
+            eye_ray(fp, pixel, b, o, d);
+            float4 t4 = f4(1.0f, 1.0f, 1.0f, 1.0f);
+            for (uint32_t len = 0; len < depth; len++) {
+                fp.path_length = len;
+                Hit hit;
+                trace_ray<false, false, 64>(*sv, o, d, 1e-4f, 1e26f, hit, nullptr);  // ExtendIO::load limits (ray_extend.comp:257-258)
+                n_ext++;
+                const float4 s4 = f4(__int_as_float(hit.inst), __int_as_float(hit.prim), hit.t, __uint_as_float(pack_bary16(hit.u, hit.v)));
+                const float4 o4 = f4(o.x, o.y, o.z, __uint_as_float(pixel)), d4 = f4(d.x, d.y, d.z, __uint_as_float(b));
+                ShadeOut so;
+                so.add = false; so.emit_ext = false; so.emit_sh = false;
+                shade_path(fp, ss, lightCount, s4, o4, d4, len == 0 ? f4(1.0f, 1.0f, 1.0f, 1.0f) : t4, so);
+                if (so.add) part = part + so.contrib;
+                if (so.emit_sh) {
+                    Hit sh;
+                    n_sh++;
+                    // ConnectIO::load limits (ray_shadow.comp:254-257)
+                    if (!trace_ray<true, false, 64>(*sv, so.sO, so.sD, 0.001f, so.sDist - 0.0001f, sh, nullptr)) part = part + so.sE;
+                }
+                if (!so.emit_ext) break;
+                o = so.nO; d = so.nD; t4 = f4(so.nT.x, so.nT.y, so.nT.z, so.nPdf);
+            }
+            acc[4 * (size_t)pixel + 0] += part.x; acc[4 * (size_t)pixel + 1] += part.y; acc[4 * (size_t)pixel + 2] += part.z;
+        }
+    }
+    if (stats) { stats[0] = n_ext; stats[1] = n_sh; }
 }
 uint32_t emu_wang_hash(uint32_t s) { return wang_hash(s); }
 float emu_randf(uint32_t* s) { return randf(*s); }

@@ -274,3 +274,73 @@ def test_texture_samplers_match_the_oracle(shade_emu, oracle_mod):
         u, v = (float(x) for x in rng.uniform(-0.2, 1.2, 2)); lod = float(rng.integers(0, sky.mip_levels + 1))
         shade_emu.emu_sample_texture(chain.ctypes.data, sky.width, sky.height, sky.mip_levels, 2, u, v, lod, out.ctypes.data)
         np.testing.assert_allclose(out, cpu.sample_texture(-1, 2, u, v, lod), rtol=0, atol=2e-6)
+
+
+INSTANCE_SHADING = np.dtype([("nrm0", np.float32, 4), ("nrm1", np.float32, 4), ("nrm2", np.float32, 4), ("tris", np.uint64), ("mesh_id", np.int32), ("pad", np.int32)])
+
+
+def _instance_shading_table(desc, keep):
+    """wavefront.h::InstanceShading per GLOBAL instance id (exclusive prefix over mesh ids of the list lengths + index): rows of
+    (M^-1)^T and the address of the mesh's 176-byte triangle records — what k_instance_prepare derives on the device."""
+    rows = []
+    for mid in sorted(desc.instances):
+        mats = np.asarray(desc.instances[mid], np.float64).reshape(-1, 4, 4).transpose(0, 2, 1)  # column-major -> row-indexed
+        tris = np.ascontiguousarray(desc.meshes[mid]) if mid in desc.meshes else None
+        keep.append(tris)
+        for M in mats:
+            r = np.zeros(1, INSTANCE_SHADING)
+            if tris is not None and M.any():
+                nm = np.linalg.inv(M[:3, :3]).T
+                r["nrm0"][0, :3], r["nrm1"][0, :3], r["nrm2"][0, :3] = nm[0], nm[1], nm[2]
+                r["tris"] = tris.ctypes.data; r["mesh_id"] = mid
+            rows.append(r)
+    return np.ascontiguousarray(np.concatenate(rows))
+
+
+def _emu_render(emu, shade_emu, desc, view, w, h, spp, depth, sky):
+    vp = C.c_void_p
+    emu.emu_scene_view.restype = vp; emu.emu_scene_view.argtypes = [vp]
+    shade_emu.emu_render.argtypes = [vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, C.c_uint32,
+                                     C.c_uint32, C.c_uint32, C.c_float, vp, vp, vp]
+    e = Emu(emu, desc)
+    keep = []
+    table = _instance_shading_table(desc, keep)
+    mats = np.ascontiguousarray(desc.materials)
+    al, pl, sl, dl = (np.ascontiguousarray(x) for x in (desc.area_lights, desc.point_lights, desc.spot_lights, desc.directional_lights))
+    acc = np.zeros((h, w, 4), np.float32); stats = np.zeros(2, np.uint64); skya = np.asarray(sky, np.float32); v = np.ascontiguousarray(view)
+    shade_emu.emu_render(emu.emu_scene_view(e.h), table.ctypes.data, mats.ctypes.data, len(mats), al.ctypes.data, len(al), pl.ctypes.data, len(pl), sl.ctypes.data, len(sl),
+                         dl.ctypes.data, len(dl), v.ctypes.data, w, h, 0, spp, depth, 10.0, skya.ctypes.data, acc.ctypes.data, stats.ctypes.data)
+    return acc, stats
+
+
+def _check_image(a, b, label, diverged_fraction=2e-3, bar=1e-3, all_pixel=1e-2):
+    """The image tolerance of the GPU tier (tests/test_gpu_parity.py::check_image, DESIGN.md §2)."""
+    sq = ((a[..., :3].astype(np.float64) - b[..., :3].astype(np.float64)) ** 2).reshape(-1, 3)
+    d = np.sqrt(sq.max(axis=1))
+    keep = np.argsort(d)[: int(np.ceil(len(d) * (1.0 - diverged_fraction)))]
+    trimmed, full = float(np.sqrt(sq[keep].mean())), float(np.sqrt(sq.mean()))
+    assert trimmed <= bar, f"{label}: RMSE over {100 * (1 - diverged_fraction):.1f}% of the pixels {trimmed}"
+    assert full <= all_pixel, f"{label}: all-pixel RMSE {full}"
+    return full, trimmed
+
+
+@pytest.mark.parametrize("which", ["instanced", "lights_and_lobes"])
+def test_product_path_tracer_on_the_cpu_matches_the_oracle(emu, shade_emu, oracle_mod, which):
+    """The product's path-tracing LOGIC end to end without a GPU: its builder and traversal bodies (bvh_build.h, traverse.h) and
+    its per-path wavefront bodies (shade_path.cuh: eye_ray + shade_path, i.e. k_wf_generate / k_wf_shade minus the queue
+    plumbing) compiled for the host and run serially as a path tracer (tests/hostemu/shade_emu.cpp::emu_render), against the
+    oracle's image of the same scene, camera and RNG streams — same tolerance as the GPU tier."""
+    if which == "instanced":
+        desc = scenes.instanced_scene(grid=6, subdiv=1, n_lights=4)
+        view_kw = {}
+    else:
+        desc = scenes.lights_and_lobes_scene(grid=4, subdiv=1)
+        view_kw = {"aperture": 0.05}
+    w, h, spp, depth, sky = 96, 54, 4, 4, (0.2, 0.2, 0.3)
+    view = scenes.camera_view((0, 3.0, -7.0), (0, -0.4, 1.0), w, h, **view_kw)
+    acc, stats = _emu_render(emu, shade_emu, desc, view, w, h, spp, depth, sky)
+    o = oracle_mod.OracleBackend(det_eps=0.0); desc.apply(o)
+    ref, st = o.render(view, w, h, spp, depth, clamp=10.0, sky=sky)
+    assert np.isfinite(acc).all() and acc.min() >= 0 and ref[..., :3].mean() / spp > 0.05
+    assert abs(int(stats[0]) - st["extension_rays"]) <= 0.002 * st["extension_rays"] and abs(int(stats[1]) - st["shadow_rays"]) <= 0.002 * st["shadow_rays"] + 2
+    _check_image(acc / spp, ref / spp, which)
