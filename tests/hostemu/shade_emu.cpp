@@ -78,12 +78,15 @@ void emu_sample_texture(const uint8_t* rgba, uint32_t w, uint32_t h, uint32_t mi
 // in stage order and the samples folded in sample order, as k_wf_reduce does.  acc: h*w*4 floats, accumulated into.
 void emu_render(const SceneView* sv, const InstanceShading* inst_table, const RfwDeviceMaterial* mats, uint32_t n_mats, const RfwAreaLight* area, uint32_t na,
                 const RfwPointLight* point, uint32_t np, const RfwSpotLight* spot, uint32_t ns, const RfwDirectionalLight* dir, uint32_t nd, const RfwCameraView3D* cam,
-                uint32_t w, uint32_t h, uint32_t first_sample, uint32_t spp, uint32_t depth, float clamp_value, const float* sky, float* acc, uint64_t* stats) {
+                uint32_t w, uint32_t h, uint32_t first_sample, uint32_t spp, uint32_t depth, float clamp_value, const float* sky, float* acc, uint64_t* stats,
+                const TexDesc* textures, uint32_t n_textures, const TexDesc* skybox) {
     ShadeScene ss;
     memset(&ss, 0, sizeof(ss));
     ss.inst = inst_table; ss.materials = mats; ss.n_materials = n_mats;
     ss.area = area; ss.point = point; ss.spot = spot; ss.dir = dir;
     ss.n_area = (int)na; ss.n_point = (int)np; ss.n_spot = (int)ns; ss.n_dir = (int)nd;
+    ss.textures = textures; ss.n_textures = n_textures;  // RGBA8 mip chains, as Backend::set_textures keeps them
+    if (skybox) { ss.has_sky = 1u; ss.sky = *skybox; }
     const int lightCount = ss.n_area + ss.n_point + ss.n_spot + ss.n_dir;
     FrameParams fp;
     memset(&fp, 0, sizeof(fp));

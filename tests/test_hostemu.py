@@ -276,6 +276,7 @@ def test_texture_samplers_match_the_oracle(shade_emu, oracle_mod):
         np.testing.assert_allclose(out, cpu.sample_texture(-1, 2, u, v, lod), rtol=0, atol=2e-6)
 
 
+TEX_DESC = np.dtype([("texels", np.uint64), ("width", np.uint32), ("height", np.uint32), ("mip_levels", np.uint32), ("pad", np.uint32)])
 INSTANCE_SHADING = np.dtype([("nrm0", np.float32, 4), ("nrm1", np.float32, 4), ("nrm2", np.float32, 4), ("tris", np.uint64), ("mesh_id", np.int32), ("pad", np.int32)])
 
 
@@ -301,15 +302,23 @@ def _emu_render(emu, shade_emu, desc, view, w, h, spp, depth, sky):
     vp = C.c_void_p
     emu.emu_scene_view.restype = vp; emu.emu_scene_view.argtypes = [vp]
     shade_emu.emu_render.argtypes = [vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, C.c_uint32,
-                                     C.c_uint32, C.c_uint32, C.c_float, vp, vp, vp]
+                                     C.c_uint32, C.c_uint32, C.c_float, vp, vp, vp, vp, C.c_uint32, vp]
     e = Emu(emu, desc)
     keep = []
     table = _instance_shading_table(desc, keep)
     mats = np.ascontiguousarray(desc.materials)
     al, pl, sl, dl = (np.ascontiguousarray(x) for x in (desc.area_lights, desc.point_lights, desc.spot_lights, desc.directional_lights))
     acc = np.zeros((h, w, 4), np.float32); stats = np.zeros(2, np.uint64); skya = np.asarray(sky, np.float32); v = np.ascontiguousarray(view)
+    # texture.cuh::TexDesc records over RGBA8 mip chains (what Backend::set_textures keeps in HBM: BGRA inputs swizzled once)
+    def tex_desc(t):
+        chain = np.ascontiguousarray(np.concatenate([(l[:, :, [2, 1, 0, 3]] if t.format == 0 else l).reshape(-1) for l in t.levels])); keep.append(chain)
+        r = np.zeros(1, TEX_DESC); r["texels"] = chain.ctypes.data; r["width"] = t.width; r["height"] = t.height; r["mip_levels"] = t.mip_levels
+        return r
+    texs = np.ascontiguousarray(np.concatenate([tex_desc(t) for t in desc.textures])) if desc.textures else np.zeros(1, TEX_DESC)
+    skyd = tex_desc(desc.skybox) if desc.skybox is not None else None
     shade_emu.emu_render(emu.emu_scene_view(e.h), table.ctypes.data, mats.ctypes.data, len(mats), al.ctypes.data, len(al), pl.ctypes.data, len(pl), sl.ctypes.data, len(sl),
-                         dl.ctypes.data, len(dl), v.ctypes.data, w, h, 0, spp, depth, 10.0, skya.ctypes.data, acc.ctypes.data, stats.ctypes.data)
+                         dl.ctypes.data, len(dl), v.ctypes.data, w, h, 0, spp, depth, 10.0, skya.ctypes.data, acc.ctypes.data, stats.ctypes.data,
+                         texs.ctypes.data, len(desc.textures), skyd.ctypes.data if skyd is not None else None)
     return acc, stats
 
 
@@ -324,7 +333,7 @@ def _check_image(a, b, label, diverged_fraction=2e-3, bar=1e-3, all_pixel=1e-2):
     return full, trimmed
 
 
-@pytest.mark.parametrize("which", ["instanced", "lights_and_lobes"])
+@pytest.mark.parametrize("which", ["instanced", "lights_and_lobes", "textured"])
 def test_product_path_tracer_on_the_cpu_matches_the_oracle(emu, shade_emu, oracle_mod, which):
     """The product's path-tracing LOGIC end to end without a GPU: its builder and traversal bodies (bvh_build.h, traverse.h) and
     its per-path wavefront bodies (shade_path.cuh: eye_ray + shade_path, i.e. k_wf_generate / k_wf_shade minus the queue
@@ -333,9 +342,12 @@ def test_product_path_tracer_on_the_cpu_matches_the_oracle(emu, shade_emu, oracl
     if which == "instanced":
         desc = scenes.instanced_scene(grid=6, subdiv=1, n_lights=4)
         view_kw = {}
-    else:
+    elif which == "lights_and_lobes":
         desc = scenes.lights_and_lobes_scene(grid=4, subdiv=1)
         view_kw = {"aperture": 0.05}
+    else:  # diffuse maps (trilinear), normal maps, equirect skybox: texture.cuh
+        desc = scenes.textured_scene(grid=3, subdiv=1, tex_size=32)
+        view_kw = {}
     w, h, spp, depth, sky = 96, 54, 4, 4, (0.2, 0.2, 0.3)
     view = scenes.camera_view((0, 3.0, -7.0), (0, -0.4, 1.0), w, h, **view_kw)
     acc, stats = _emu_render(emu, shade_emu, desc, view, w, h, spp, depth, sky)
