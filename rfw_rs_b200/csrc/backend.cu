@@ -5,6 +5,7 @@
 // and render()/trace_*() launch the kernels of trace.cu / wavefront.cu.  No CPU fallback exists:
 // every path either runs on the CUDA device selected at create() or returns an error.
 #include "backend.h"
+#include "instance_build.h"
 
 #include <math.h>
 #include <string.h>
@@ -292,52 +293,11 @@ int Backend::set_spot_lights(const RfwSpotLight* l, uint32_t num) { spot_lights.
 int Backend::set_directional_lights(const RfwDirectionalLight* l, uint32_t num) { dir_lights.assign(l, l + num); shading_dirty = true; synchronized = false; return RFWB200_OK; }
 
 // ---- synchronize -----------------------------------------------------------------------------------
-__host__ __device__ static bool invert_affine(const float* m, float4& r0, float4& r1, float4& r2, float4& n0, float4& n1, float4& n2) {
-    // column-major 4x4 -> rows of the inverse (3x4) and rows of the normal matrix (inverse transposed, 3x3)
-    double a[16], inv[16];
-    for (int i = 0; i < 16; i++) a[i] = m[i];
-    inv[0] = a[5] * a[10] * a[15] - a[5] * a[11] * a[14] - a[9] * a[6] * a[15] + a[9] * a[7] * a[14] + a[13] * a[6] * a[11] - a[13] * a[7] * a[10];
-    inv[4] = -a[4] * a[10] * a[15] + a[4] * a[11] * a[14] + a[8] * a[6] * a[15] - a[8] * a[7] * a[14] - a[12] * a[6] * a[11] + a[12] * a[7] * a[10];
-    inv[8] = a[4] * a[9] * a[15] - a[4] * a[11] * a[13] - a[8] * a[5] * a[15] + a[8] * a[7] * a[13] + a[12] * a[5] * a[11] - a[12] * a[7] * a[9];
-    inv[12] = -a[4] * a[9] * a[14] + a[4] * a[10] * a[13] + a[8] * a[5] * a[14] - a[8] * a[6] * a[13] - a[12] * a[5] * a[10] + a[12] * a[6] * a[9];
-    inv[1] = -a[1] * a[10] * a[15] + a[1] * a[11] * a[14] + a[9] * a[2] * a[15] - a[9] * a[3] * a[14] - a[13] * a[2] * a[11] + a[13] * a[3] * a[10];
-    inv[5] = a[0] * a[10] * a[15] - a[0] * a[11] * a[14] - a[8] * a[2] * a[15] + a[8] * a[3] * a[14] + a[12] * a[2] * a[11] - a[12] * a[3] * a[10];
-    inv[9] = -a[0] * a[9] * a[15] + a[0] * a[11] * a[13] + a[8] * a[1] * a[15] - a[8] * a[3] * a[13] - a[12] * a[1] * a[11] + a[12] * a[3] * a[9];
-    inv[13] = a[0] * a[9] * a[14] - a[0] * a[10] * a[13] - a[8] * a[1] * a[14] + a[8] * a[2] * a[13] + a[12] * a[1] * a[10] - a[12] * a[2] * a[9];
-    inv[2] = a[1] * a[6] * a[15] - a[1] * a[7] * a[14] - a[5] * a[2] * a[15] + a[5] * a[3] * a[14] + a[13] * a[2] * a[7] - a[13] * a[3] * a[6];
-    inv[6] = -a[0] * a[6] * a[15] + a[0] * a[7] * a[14] + a[4] * a[2] * a[15] - a[4] * a[3] * a[14] - a[12] * a[2] * a[7] + a[12] * a[3] * a[6];
-    inv[10] = a[0] * a[5] * a[15] - a[0] * a[7] * a[13] - a[4] * a[1] * a[15] + a[4] * a[3] * a[13] + a[12] * a[1] * a[7] - a[12] * a[3] * a[5];
-    inv[14] = -a[0] * a[5] * a[14] + a[0] * a[6] * a[13] + a[4] * a[1] * a[14] - a[4] * a[2] * a[13] - a[12] * a[1] * a[6] + a[12] * a[2] * a[5];
-    const double det = a[0] * inv[0] + a[1] * inv[4] + a[2] * inv[8] + a[3] * inv[12];
-    if (det == 0.0 || !isfinite(det)) return false;
-    const double id = 1.0 / det;
-    r0 = make_float4((float)(inv[0] * id), (float)(inv[4] * id), (float)(inv[8] * id), (float)(inv[12] * id));
-    r1 = make_float4((float)(inv[1] * id), (float)(inv[5] * id), (float)(inv[9] * id), (float)(inv[13] * id));
-    r2 = make_float4((float)(inv[2] * id), (float)(inv[6] * id), (float)(inv[10] * id), (float)(inv[14] * id));
-    // normal = transpose(inverse): row i of normal = column i of inverse
-    n0 = make_float4(r0.x, r1.x, r2.x, 0.0f);
-    n1 = make_float4(r0.y, r1.y, r2.y, 0.0f);
-    n2 = make_float4(r0.z, r1.z, r2.z, 0.0f);
-    return true;
-}
-
-
 // ---- instance records on the device (reference: the host-side flatten of backends/gpu-rt/src/lib.rs:1571-1632) ------
 // One thread per instance SLOT (global instance id = exclusive prefix over mesh ids of the list lengths + index in the
 // list): inverse + normal matrix in double, world box of the 8 transformed BLAS corners (culling.comp:58-92), shading
 // record; removed slots (all-zero matrix, instances_3d.rs:79-86), singular matrices and slots of absent meshes are
 // flagged dead and compacted away in slot order, so the TLAS sees the live instances in a deterministic order.
-struct MeshEntry {
-    const float4* nodes;
-    const float4* ttris;
-    const RfwRTTriangle* tris;
-    float lo[3], hi[3];
-    uint32_t first_slot;  // global id of this mesh's first instance slot
-    uint32_t present;     // mesh has triangles and a BLAS
-    uint32_t n_tris;
-    uint32_t pad;
-};
-
 __global__ void __launch_bounds__(128) k_instance_prepare(const MeshEntry* __restrict__ meshes, uint32_t n_meshes, const float* __restrict__ matrices, uint32_t n_slots,
                                                           InstanceRec* __restrict__ recs, InstanceShading* __restrict__ shading, float4* __restrict__ box_lo,
                                                           float4* __restrict__ box_hi, uint32_t* __restrict__ live_flag, uint32_t* __restrict__ identity_flag) {
@@ -359,35 +319,13 @@ __global__ void __launch_bounds__(128) k_instance_prepare(const MeshEntry* __res
     }
     InstanceRec r;
     InstanceShading sh;
-    memset(&sh, 0, sizeof(sh));
-    bool live = me.present && !zero && invert_affine(M, r.inv0, r.inv1, r.inv2, sh.nrm0, sh.nrm1, sh.nrm2);
+    float lo[3], hi[3];
+    bool ident = false;
+    const bool live = instance_record(me, M, zero, gid, lo_i, r, sh, lo, hi, ident);
     if (live) {
-        r.nodes = me.nodes; r.tris = me.ttris; r.inst_id = (int)gid; r.mesh_id = (int)lo_i; r.pad1 = 0;
-        r.direct_tris = (me.n_tris >= 1u && me.n_tris <= (uint32_t)RFW_DIRECT_TRIS) ? (int)me.n_tris : 0;
-        sh.tris = me.tris; sh.mesh_id = (int)lo_i; sh.pad = 0;
-        float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
-#pragma unroll
-        for (int c = 0; c < 8; c++) {
-            const float px = (c & 1) ? me.hi[0] : me.lo[0], py = (c & 2) ? me.hi[1] : me.lo[1], pz = (c & 4) ? me.hi[2] : me.lo[2];
-            // no FMA contraction: the same roundings as a plain host evaluation, on every rank
-            const float w0 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[0], px), __fmul_rn(M[4], py)), __fmul_rn(M[8], pz)), M[12]);
-            const float w1 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[1], px), __fmul_rn(M[5], py)), __fmul_rn(M[9], pz)), M[13]);
-            const float w2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[2], px), __fmul_rn(M[6], py)), __fmul_rn(M[10], pz)), M[14]);
-            lo[0] = fminf(lo[0], w0); hi[0] = fmaxf(hi[0], w0);
-            lo[1] = fminf(lo[1], w1); hi[1] = fmaxf(hi[1], w1);
-            lo[2] = fminf(lo[2], w2); hi[2] = fmaxf(hi[2], w2);
-        }
-#pragma unroll
-        for (int k = 0; k < 3; k++) {  // pad: the object-space BLAS boxes are exact, the world box is rounded
-            const float pad = 4.0f * 1.1920929e-7f * fmaxf(fabsf(lo[k]), fabsf(hi[k]));
-            lo[k] -= pad; hi[k] += pad;
-        }
         recs[gid] = r;
         box_lo[gid] = make_float4(lo[0], lo[1], lo[2], 0.0f);
         box_hi[gid] = make_float4(hi[0], hi[1], hi[2], 0.0f);
-        bool ident = true;
-#pragma unroll
-        for (int k = 0; k < 16; k++) ident = ident && M[k] == ((k % 5 == 0) ? 1.0f : 0.0f);
         identity_flag[gid] = ident ? 1u : 0u;
     }
     shading[gid] = sh;

@@ -9,8 +9,11 @@
 #include <map>
 #include <vector>
 
+#include "device_shims.h"
+
 #include "../../include/rfwb200.h"
 #include "../../rfw_rs_b200/csrc/bvh_build.h"
+#include "../../rfw_rs_b200/csrc/instance_build.h"
 #include "../../rfw_rs_b200/csrc/traverse.h"
 
 using namespace rfw;
@@ -85,34 +88,10 @@ struct EmuScene {
     std::map<uint32_t, EmuMesh> meshes;
     std::map<uint32_t, std::vector<float>> inst;
     std::vector<InstanceRec> recs;
+    std::vector<InstanceShading> shading;  // per GLOBAL instance id (what k_instance_prepare writes for k_wf_shade)
     EmuBvh tlas;
     SceneView sv;
 };
-
-static bool invert_affine(const float* m, float4& r0, float4& r1, float4& r2) {
-    // column-major 4x4 -> rows of the inverse 3x4 (double)
-    double a[16], inv[16];
-    for (int i = 0; i < 16; i++) a[i] = m[i];
-    inv[0] = a[5] * a[10] * a[15] - a[5] * a[11] * a[14] - a[9] * a[6] * a[15] + a[9] * a[7] * a[14] + a[13] * a[6] * a[11] - a[13] * a[7] * a[10];
-    inv[4] = -a[4] * a[10] * a[15] + a[4] * a[11] * a[14] + a[8] * a[6] * a[15] - a[8] * a[7] * a[14] - a[12] * a[6] * a[11] + a[12] * a[7] * a[10];
-    inv[8] = a[4] * a[9] * a[15] - a[4] * a[11] * a[13] - a[8] * a[5] * a[15] + a[8] * a[7] * a[13] + a[12] * a[5] * a[11] - a[12] * a[7] * a[9];
-    inv[12] = -a[4] * a[9] * a[14] + a[4] * a[10] * a[13] + a[8] * a[5] * a[14] - a[8] * a[6] * a[13] - a[12] * a[5] * a[10] + a[12] * a[6] * a[9];
-    inv[1] = -a[1] * a[10] * a[15] + a[1] * a[11] * a[14] + a[9] * a[2] * a[15] - a[9] * a[3] * a[14] - a[13] * a[2] * a[11] + a[13] * a[3] * a[10];
-    inv[5] = a[0] * a[10] * a[15] - a[0] * a[11] * a[14] - a[8] * a[2] * a[15] + a[8] * a[3] * a[14] + a[12] * a[2] * a[11] - a[12] * a[3] * a[10];
-    inv[9] = -a[0] * a[9] * a[15] + a[0] * a[11] * a[13] + a[8] * a[1] * a[15] - a[8] * a[3] * a[13] - a[12] * a[1] * a[11] + a[12] * a[3] * a[9];
-    inv[13] = a[0] * a[9] * a[14] - a[0] * a[10] * a[13] - a[8] * a[1] * a[14] + a[8] * a[2] * a[13] + a[12] * a[1] * a[10] - a[12] * a[2] * a[9];
-    inv[2] = a[1] * a[6] * a[15] - a[1] * a[7] * a[14] - a[5] * a[2] * a[15] + a[5] * a[3] * a[14] + a[13] * a[2] * a[7] - a[13] * a[3] * a[6];
-    inv[6] = -a[0] * a[6] * a[15] + a[0] * a[7] * a[14] + a[4] * a[2] * a[15] - a[4] * a[3] * a[14] - a[12] * a[2] * a[7] + a[12] * a[3] * a[6];
-    inv[10] = a[0] * a[5] * a[15] - a[0] * a[7] * a[13] - a[4] * a[1] * a[15] + a[4] * a[3] * a[13] + a[12] * a[1] * a[7] - a[12] * a[3] * a[5];
-    inv[14] = -a[0] * a[5] * a[14] + a[0] * a[6] * a[13] + a[4] * a[1] * a[14] - a[4] * a[2] * a[13] - a[12] * a[1] * a[6] + a[12] * a[2] * a[5];
-    double det = a[0] * inv[0] + a[1] * inv[4] + a[2] * inv[8] + a[3] * inv[12];
-    if (det == 0.0 || !std::isfinite(det)) return false;
-    double id = 1.0 / det;
-    r0 = f4((float)(inv[0] * id), (float)(inv[4] * id), (float)(inv[8] * id), (float)(inv[12] * id));
-    r1 = f4((float)(inv[1] * id), (float)(inv[5] * id), (float)(inv[9] * id), (float)(inv[13] * id));
-    r2 = f4((float)(inv[2] * id), (float)(inv[6] * id), (float)(inv[10] * id), (float)(inv[14] * id));
-    return true;
-}
 
 extern "C" {
 void* emu_create() { return new EmuScene(); }
@@ -149,6 +128,7 @@ void emu_build(void* s, float c_node, float c_prim, int pmax, uint64_t* stats) {
         tot_nodes += m.bvh.nodes.size() / NODE_F4;
     }
     sc.recs.clear();
+    sc.shading.clear();
     std::vector<float4> ilo, ihi;
     int gid = 0;
     bool identity_single = false;
@@ -156,27 +136,29 @@ void emu_build(void* s, float c_node, float c_prim, int pmax, uint64_t* stats) {
         auto mit = sc.meshes.find(kv.first);
         const size_t cnt = kv.second.size() / 16;
         for (size_t i = 0; i < cnt; i++, gid++) {
+            if ((size_t)gid >= sc.shading.size()) sc.shading.resize((size_t)gid + 1);
             if (mit == sc.meshes.end() || mit->second.tris.empty()) continue;
             const float* M = &kv.second[i * 16];
             bool zero = true;
             for (int k = 0; k < 16; k++) zero &= (M[k] == 0.0f);
-            if (zero) continue;
+            // the product's own per-slot body (instance_build.h, the body of k_instance_prepare)
+            MeshEntry me;
+            memset(&me, 0, sizeof(me));
+            me.nodes = mit->second.bvh.nodes.data(); me.ttris = mit->second.ttris.data(); me.tris = mit->second.tris.data();
+            me.lo[0] = mit->second.lo.x; me.lo[1] = mit->second.lo.y; me.lo[2] = mit->second.lo.z;
+            me.hi[0] = mit->second.hi.x; me.hi[1] = mit->second.hi.y; me.hi[2] = mit->second.hi.z;
+            me.present = 1; me.n_tris = (uint32_t)mit->second.tris.size();
             InstanceRec r;
-            if (!invert_affine(M, r.inv0, r.inv1, r.inv2)) continue;
-            r.nodes = mit->second.bvh.nodes.data(); r.tris = mit->second.ttris.data();
-            r.inst_id = gid; r.mesh_id = (int)kv.first; r.pad1 = 0;
-            const size_t ntris = mit->second.tris.size();
-            r.direct_tris = (ntris >= 1 && ntris <= (size_t)RFW_DIRECT_TRIS) ? (int)ntris : 0;
-            float3 l = f3(FLT_MAX, FLT_MAX, FLT_MAX), h = f3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
-            for (int c = 0; c < 8; c++) {
-                float3 p = f3((c & 1) ? mit->second.hi.x : mit->second.lo.x, (c & 2) ? mit->second.hi.y : mit->second.lo.y, (c & 4) ? mit->second.hi.z : mit->second.lo.z);
-                float3 w = f3(M[0] * p.x + M[4] * p.y + M[8] * p.z + M[12], M[1] * p.x + M[5] * p.y + M[9] * p.z + M[13], M[2] * p.x + M[6] * p.y + M[10] * p.z + M[14]);
-                l = min3(l, w); h = max3(h, w);
-            }
-            ilo.push_back(f4(l.x, l.y, l.z, 0)); ihi.push_back(f4(h.x, h.y, h.z, 0));
+            InstanceShading sh;
+            float blo[3], bhi[3];
+            bool ident = false;
+            const bool live = instance_record(me, M, zero, (uint32_t)gid, kv.first, r, sh, blo, bhi, ident);
+            if ((size_t)gid >= sc.shading.size()) sc.shading.resize((size_t)gid + 1);
+            sc.shading[(size_t)gid] = sh;
+            if (!live) continue;
+            ilo.push_back(f4(blo[0], blo[1], blo[2], 0)); ihi.push_back(f4(bhi[0], bhi[1], bhi[2], 0));
+            identity_single = ident;
             sc.recs.push_back(r);
-            static const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-            identity_single = memcmp(M, I, 64) == 0;
         }
     }
     sc.sv.instances = sc.recs.data();
@@ -195,6 +177,8 @@ void emu_build(void* s, float c_node, float c_prim, int pmax, uint64_t* stats) {
 
 // the traversal view of the built scene, for the CPU path tracer of shade_emu.cpp (same header, same struct)
 const void* emu_scene_view(void* s) { return &((EmuScene*)s)->sv; }
+// the per-instance shading table the product derives next to the traversal records (indexed by global instance id)
+const void* emu_instance_shading(void* s, uint32_t* count) { EmuScene& sc = *(EmuScene*)s; if (count) *count = (uint32_t)sc.shading.size(); return sc.shading.data(); }
 void emu_trace(void* s, const RfwRay* rays, uint64_t n, RfwHit* hits, uint32_t* occluded, uint64_t* counters) {
     EmuScene& sc = *(EmuScene*)s;
     TraceCounters ctr{0, 0, 0};

@@ -4,25 +4,7 @@
 // inputs.  Test infrastructure only: librfwb200.so contains no host execution path for any of this.
 //
 // shading.cuh is device code; the few device-only spellings it uses are given host meanings here, before it is included.
-#include <cuda_runtime.h>  // float3 / float4 vector types (usable from plain g++)
-#include <math.h>
-#include <stdint.h>
-#include <string.h>
-
-#undef __device__
-#undef __forceinline__
-#undef __noinline__
-#define __device__
-#define __forceinline__ inline
-#define __noinline__
-template <typename T>
-static inline T __ldg(const T* p) { return *p; }
-static inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
-static inline int __float_as_int(float f) { int v; memcpy(&v, &f, 4); return v; }
-static inline float __uint_as_float(uint32_t v) { float f; memcpy(&f, &v, 4); return f; }
-static inline uint32_t __float_as_uint(float f) { uint32_t v; memcpy(&v, &f, 4); return v; }
-static inline int min(int a, int b) { return a < b ? a : b; }   // CUDA's global integer min / max
-static inline int max(int a, int b) { return a > b ? a : b; }
+#include "device_shims.h"
 
 #include "../../rfw_rs_b200/csrc/shading.cuh"
 #include "../../rfw_rs_b200/csrc/shade_path.cuh"

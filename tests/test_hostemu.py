@@ -280,9 +280,9 @@ TEX_DESC = np.dtype([("texels", np.uint64), ("width", np.uint32), ("height", np.
 INSTANCE_SHADING = np.dtype([("nrm0", np.float32, 4), ("nrm1", np.float32, 4), ("nrm2", np.float32, 4), ("tris", np.uint64), ("mesh_id", np.int32), ("pad", np.int32)])
 
 
-def _instance_shading_table(desc, keep):
-    """wavefront.h::InstanceShading per GLOBAL instance id (exclusive prefix over mesh ids of the list lengths + index): rows of
-    (M^-1)^T and the address of the mesh's 176-byte triangle records — what k_instance_prepare derives on the device."""
+def _instance_shading_table_numpy(desc, keep):
+    """wavefront.h::InstanceShading per GLOBAL instance id computed independently in numpy (float64 inverse): rows of (M^-1)^T and
+    the address of the mesh's 176-byte triangle records.  Used to cross-check the table the product's instance_record derives."""
     rows = []
     for mid in sorted(desc.instances):
         mats = np.asarray(desc.instances[mid], np.float64).reshape(-1, 4, 4).transpose(0, 2, 1)  # column-major -> row-indexed
@@ -304,8 +304,18 @@ def _emu_render(emu, shade_emu, desc, view, w, h, spp, depth, sky):
     shade_emu.emu_render.argtypes = [vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, C.c_uint32,
                                      C.c_uint32, C.c_uint32, C.c_float, vp, vp, vp, vp, C.c_uint32, vp]
     e = Emu(emu, desc)
-    keep = []
-    table = _instance_shading_table(desc, keep)
+    keep = [e]
+    # the per-instance shading table as the PRODUCT derives it (instance_build.h::instance_record, the body of k_instance_prepare),
+    # cross-checked against an independent numpy derivation
+    emu.emu_instance_shading.restype = vp; emu.emu_instance_shading.argtypes = [vp, vp]
+    cnt = C.c_uint32(0)
+    ptr = emu.emu_instance_shading(e.h, C.addressof(cnt))
+    table = np.ctypeslib.as_array((C.c_uint8 * (cnt.value * INSTANCE_SHADING.itemsize)).from_address(ptr)).view(INSTANCE_SHADING)
+    ref_table = _instance_shading_table_numpy(desc, keep)
+    assert len(table) == len(ref_table)
+    for f in ("nrm0", "nrm1", "nrm2"):
+        np.testing.assert_allclose(table[f], ref_table[f], rtol=2e-6, atol=1e-7)
+    assert np.array_equal(table["mesh_id"], ref_table["mesh_id"]) and ((table["tris"] != 0) == (ref_table["tris"] != 0)).all()
     mats = np.ascontiguousarray(desc.materials)
     al, pl, sl, dl = (np.ascontiguousarray(x) for x in (desc.area_lights, desc.point_lights, desc.spot_lights, desc.directional_lights))
     acc = np.zeros((h, w, 4), np.float32); stats = np.zeros(2, np.uint64); skya = np.asarray(sky, np.float32); v = np.ascontiguousarray(view)
