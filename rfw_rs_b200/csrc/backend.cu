@@ -368,40 +368,7 @@ __global__ void __launch_bounds__(128) k_skin_triangles(const RfwRTTriangle* __r
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
     if (i >= n) return;
     RfwRTTriangle t = src[i];
-    float* verts[3] = {t.vertex0, t.vertex1, t.vertex2};
-    float* nrms[3] = {t.n0, t.n1, t.n2};
-    float* tans[3] = {t.tangent0, t.tangent1, t.tangent2};
-    const float tw = t.tangent2[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        const RfwJointData jd = skin[3 * (size_t)i + k];
-        if (jd.joint[0] >= num_joints || jd.joint[1] >= num_joints || jd.joint[2] >= num_joints || jd.joint[3] >= num_joints) continue;
-        float M[16];
-#pragma unroll
-        for (int e = 0; e < 16; e++) {
-            float acc = __fmul_rn(jd.weight[0], joints[16 * jd.joint[0] + e]);
-            acc = __fadd_rn(acc, __fmul_rn(jd.weight[1], joints[16 * jd.joint[1] + e]));
-            acc = __fadd_rn(acc, __fmul_rn(jd.weight[2], joints[16 * jd.joint[2] + e]));
-            acc = __fadd_rn(acc, __fmul_rn(jd.weight[3], joints[16 * jd.joint[3] + e]));
-            M[e] = acc;
-        }
-        float4 r0, r1, r2, n0, n1, n2;
-        if (!invert_affine(M, r0, r1, r2, n0, n1, n2)) continue;  // degenerate blend: the vertex stays in bind pose
-        const float px = verts[k][0], py = verts[k][1], pz = verts[k][2];
-        verts[k][0] = M[0] * px + M[4] * py + M[8] * pz + M[12];
-        verts[k][1] = M[1] * px + M[5] * py + M[9] * pz + M[13];
-        verts[k][2] = M[2] * px + M[6] * py + M[10] * pz + M[14];
-        const float nx = nrms[k][0], ny = nrms[k][1], nz = nrms[k][2];
-        nrms[k][0] = n0.x * nx + n0.y * ny + n0.z * nz; nrms[k][1] = n1.x * nx + n1.y * ny + n1.z * nz; nrms[k][2] = n2.x * nx + n2.y * ny + n2.z * nz;
-        const float tx = tans[k][0], ty = tans[k][1], tz = tans[k][2];
-        tans[k][0] = n0.x * tx + n0.y * ty + n0.z * tz; tans[k][1] = n1.x * tx + n1.y * ty + n1.z * tz; tans[k][2] = n2.x * tx + n2.y * ty + n2.z * tz;
-        tans[k][3] = tw;
-    }
-    const float ax = t.vertex1[0] - t.vertex0[0], ay = t.vertex1[1] - t.vertex0[1], az = t.vertex1[2] - t.vertex0[2];
-    const float bx = t.vertex2[0] - t.vertex0[0], by = t.vertex2[1] - t.vertex0[1], bz = t.vertex2[2] - t.vertex0[2];
-    const float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
-    const float il = 1.0f / sqrtf(cx * cx + cy * cy + cz * cz);
-    t.normal[0] = cx * il; t.normal[1] = cy * il; t.normal[2] = cz * il;  // RTTriangle::normal, structs.rs:970-974
+    skin_triangle(t, skin + 3 * (size_t)i, joints, num_joints);
     dst[i] = t;
 }
 

@@ -97,4 +97,49 @@ RFW_HD bool instance_record(const MeshEntry& me, const float* M, bool zero, uint
     return true;
 }
 
+// SkinnedTriangles3D::apply (crates/rfw-backend/src/structs.rs:820-877) for ONE triangle (the body of k_skin_triangles): per vertex
+// a weighted sum of four joint matrices; positions by the matrix, vertex normals / tangents by its inverse transpose (not
+// renormalised, every tangent's w from tangent2 as in the reference), geometric normal recomputed.  jd3 = the triangle's three
+// JointData records (entries 3i..3i+2; the reference's i/3, i+1, i+2 is a defect, see oracle.cpp apply_skin).
+RFW_HD void skin_triangle(RfwRTTriangle& t, const RfwJointData* jd3, const float* joints, uint32_t num_joints) {
+    float* verts[3] = {t.vertex0, t.vertex1, t.vertex2};
+    float* nrms[3] = {t.n0, t.n1, t.n2};
+    float* tans[3] = {t.tangent0, t.tangent1, t.tangent2};
+    const float tw = t.tangent2[3];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 3; k++) {
+        const RfwJointData jd = jd3[k];
+        if (jd.joint[0] >= num_joints || jd.joint[1] >= num_joints || jd.joint[2] >= num_joints || jd.joint[3] >= num_joints) continue;
+        float M[16];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int e = 0; e < 16; e++) {
+            float acc = mul_rn(jd.weight[0], joints[16 * jd.joint[0] + e]);
+            acc = add_rn(acc, mul_rn(jd.weight[1], joints[16 * jd.joint[1] + e]));
+            acc = add_rn(acc, mul_rn(jd.weight[2], joints[16 * jd.joint[2] + e]));
+            acc = add_rn(acc, mul_rn(jd.weight[3], joints[16 * jd.joint[3] + e]));
+            M[e] = acc;
+        }
+        float4 r0, r1, r2, n0, n1, n2;
+        if (!invert_affine(M, r0, r1, r2, n0, n1, n2)) continue;  // degenerate blend: the vertex stays in bind pose
+        const float px = verts[k][0], py = verts[k][1], pz = verts[k][2];
+        verts[k][0] = M[0] * px + M[4] * py + M[8] * pz + M[12];
+        verts[k][1] = M[1] * px + M[5] * py + M[9] * pz + M[13];
+        verts[k][2] = M[2] * px + M[6] * py + M[10] * pz + M[14];
+        const float nx = nrms[k][0], ny = nrms[k][1], nz = nrms[k][2];
+        nrms[k][0] = n0.x * nx + n0.y * ny + n0.z * nz; nrms[k][1] = n1.x * nx + n1.y * ny + n1.z * nz; nrms[k][2] = n2.x * nx + n2.y * ny + n2.z * nz;
+        const float tx = tans[k][0], ty = tans[k][1], tz = tans[k][2];
+        tans[k][0] = n0.x * tx + n0.y * ty + n0.z * tz; tans[k][1] = n1.x * tx + n1.y * ty + n1.z * tz; tans[k][2] = n2.x * tx + n2.y * ty + n2.z * tz;
+        tans[k][3] = tw;
+    }
+    const float ax = t.vertex1[0] - t.vertex0[0], ay = t.vertex1[1] - t.vertex0[1], az = t.vertex1[2] - t.vertex0[2];
+    const float bx = t.vertex2[0] - t.vertex0[0], by = t.vertex2[1] - t.vertex0[1], bz = t.vertex2[2] - t.vertex0[2];
+    const float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+    const float il = 1.0f / sqrtf(cx * cx + cy * cy + cz * cz);
+    t.normal[0] = cx * il; t.normal[1] = cy * il; t.normal[2] = cz * il;  // RTTriangle::normal, structs.rs:970-974
+}
+
 }  // namespace rfw

@@ -175,6 +175,14 @@ void emu_build(void* s, float c_node, float c_prim, int pmax, uint64_t* stats) {
     if (stats) { stats[0] = tot_nodes; stats[1] = sc.tlas.nodes.size() / NODE_F4; stats[2] = sc.recs.size(); }
 }
 
+// the product's skinning body (instance_build.h::skin_triangle, the body of k_skin_triangles) over a whole mesh
+void emu_skin_triangles(const RfwRTTriangle* src, const RfwJointData* skin, const float* joints, uint32_t num_joints, uint32_t n, RfwRTTriangle* dst) {
+    for (uint32_t i = 0; i < n; i++) {
+        RfwRTTriangle t = src[i];
+        skin_triangle(t, skin + 3 * (size_t)i, joints, num_joints);
+        dst[i] = t;
+    }
+}
 // the traversal view of the built scene, for the CPU path tracer of shade_emu.cpp (same header, same struct)
 const void* emu_scene_view(void* s) { return &((EmuScene*)s)->sv; }
 // the per-instance shading table the product derives next to the traversal records (indexed by global instance id)

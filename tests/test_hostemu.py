@@ -366,3 +366,31 @@ def test_product_path_tracer_on_the_cpu_matches_the_oracle(emu, shade_emu, oracl
     assert np.isfinite(acc).all() and acc.min() >= 0 and ref[..., :3].mean() / spp > 0.05
     assert abs(int(stats[0]) - st["extension_rays"]) <= 0.002 * st["extension_rays"] and abs(int(stats[1]) - st["shadow_rays"]) <= 0.002 * st["shadow_rays"] + 2
     _check_image(acc / spp, ref / spp, which)
+
+
+def test_skinning_body_matches_the_oracle(emu, oracle_mod):
+    """SURVEY §8 (f)2 on the CPU tier: the product's skinning body (instance_build.h::skin_triangle = the body of k_skin_triangles,
+    SkinnedTriangles3D::apply of structs.rs:820-877) over the CesiumMan fixture with its real JOINTS_0 / WEIGHTS_0 and a
+    deforming pose, against the oracle's restatement: positions, normals, tangents and the recomputed face normal."""
+    from rfw_rs_b200 import gltf
+
+    asset = gltf.load_npz(os.path.join(HERE, "golden", "cesium_man.npz"))
+    sc = gltf.skinned(asset)                       # instance 0 of mesh 0 carries skin 0 with a deforming pose
+    o = oracle_mod.OracleBackend(); sc.apply(o)
+    ref = o.skinned_triangles(0, 0, wire.RT_TRIANGLE)
+    src = np.ascontiguousarray(sc.meshes[0]); jd = np.ascontiguousarray(sc.skin_data[0]); joints = np.ascontiguousarray(sc.skins[0], np.float32)
+    assert len(ref) == len(src) and len(jd) == 3 * len(src)
+    dst = np.zeros_like(src)
+    emu.emu_skin_triangles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    emu.emu_skin_triangles(src.ctypes.data, jd.ctypes.data, joints.ctypes.data, len(joints), len(src), dst.ctypes.data)
+    moved = np.linalg.norm(dst["vertex0"] - src["vertex0"], axis=1)
+    assert moved.max() > 1e-3                      # the pose really deforms
+    for f in ("vertex0", "vertex1", "vertex2"):
+        np.testing.assert_allclose(dst[f], ref[f], rtol=0, atol=2e-6)
+    for f in ("n0", "n1", "n2"):
+        np.testing.assert_allclose(dst[f], ref[f], rtol=0, atol=1e-5)
+    for f in ("tangent0", "tangent1", "tangent2"):
+        np.testing.assert_allclose(dst[f], ref[f], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(dst["normal"], ref["normal"], rtol=0, atol=2e-4)   # a float32 cross product of small edges
+    for f in ("id", "mat_id", "light_id"):
+        assert np.array_equal(dst[f], ref[f])
