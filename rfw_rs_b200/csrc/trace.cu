@@ -150,13 +150,10 @@ __global__ void __launch_bounds__(128) k_trace_simple(SceneView sv, const float4
 __global__ void __launch_bounds__(256) k_generate_pinhole(RfwCameraView3D cam, uint32_t w, uint32_t h, float4* __restrict__ rays) {
     const uint32_t i = blockIdx.x * 256 + threadIdx.x;
     if (i >= w * h) return;
-    const uint32_t x = i % w, y = i / w;
-    const float u = (float)x * cam.inv_width, v = (float)y * cam.inv_height;
-    const float3 pos = f3(cam.pos[0], cam.pos[1], cam.pos[2]);
-    const float3 p = f3(cam.p1[0], cam.p1[1], cam.p1[2]) + u * f3(cam.right[0], cam.right[1], cam.right[2]) + v * f3(cam.up[0], cam.up[1], cam.up[2]);
-    const float3 d = normalize3(p - pos);
-    rays[2 * (size_t)i] = f4(pos.x, pos.y, pos.z, 1e-4f);
-    rays[2 * (size_t)i + 1] = f4(d.x, d.y, d.z, 1e26f);
+    float4 r0, r1;
+    pinhole_ray(cam, i % w, i / w, r0, r1);
+    rays[2 * (size_t)i] = r0;
+    rays[2 * (size_t)i + 1] = r1;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -20,6 +20,7 @@
 // meta[i]: 0 = empty; inner child in slot i: 0b001_11000 + i; leaf: (unary prim count) << 5 | offset from prim_base.
 // Traversal order is by ray octant: an inner child in slot s gets priority bit 24 + (s ^ octinv).
 #pragma once
+#include "../../include/rfwb200.h"
 #include "hd.h"
 
 namespace rfw {
@@ -256,6 +257,17 @@ RFW_HD void xform_ray(const InstanceRec& rec, const float3 o, const float3 d, fl
             rec.inv2.x * o.x + rec.inv2.y * o.y + rec.inv2.z * o.z + rec.inv2.w);
     od = f3(rec.inv0.x * d.x + rec.inv0.y * d.y + rec.inv0.z * d.z, rec.inv1.x * d.x + rec.inv1.y * d.y + rec.inv1.z * d.z,
             rec.inv2.x * d.x + rec.inv2.y * d.y + rec.inv2.z * d.z);
+}
+
+// pinhole primary ray of pixel (x, y) with the closest-hit limits of the extend stage: CameraView3D::generate_ray,
+// crates/rfw-backend/src/structs.rs:549-556 (the body of k_generate_pinhole, trace.cu)
+RFW_HD void pinhole_ray(const RfwCameraView3D& cam, uint32_t x, uint32_t y, float4& o_tmin, float4& d_tmax) {
+    const float u = (float)x * cam.inv_width, v = (float)y * cam.inv_height;
+    const float3 pos = f3(cam.pos[0], cam.pos[1], cam.pos[2]);
+    const float3 p = f3(cam.p1[0], cam.p1[1], cam.p1[2]) + u * f3(cam.right[0], cam.right[1], cam.right[2]) + v * f3(cam.up[0], cam.up[1], cam.up[2]);
+    const float3 d = normalize3(p - pos);
+    o_tmin = f4(pos.x, pos.y, pos.z, 1e-4f);
+    d_tmax = f4(d.x, d.y, d.z, 1e26f);
 }
 
 #define RFW_NODE_HITS(g) ((g).y > 0x00FFFFFFu)

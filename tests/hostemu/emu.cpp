@@ -175,6 +175,15 @@ void emu_build(void* s, float c_node, float c_prim, int pmax, uint64_t* stats) {
     if (stats) { stats[0] = tot_nodes; stats[1] = sc.tlas.nodes.size() / NODE_F4; stats[2] = sc.recs.size(); }
 }
 
+// the product's pinhole camera body (traverse.h::pinhole_ray, the body of k_generate_pinhole / rfwb200_cast_primary)
+void emu_pinhole_rays(const RfwCameraView3D* cam, uint32_t w, uint32_t h, RfwRay* out) {
+    for (uint32_t i = 0; i < w * h; i++) {
+        float4 r0, r1;
+        pinhole_ray(*cam, i % w, i / w, r0, r1);
+        out[i].origin[0] = r0.x; out[i].origin[1] = r0.y; out[i].origin[2] = r0.z; out[i].tmin = r0.w;
+        out[i].direction[0] = r1.x; out[i].direction[1] = r1.y; out[i].direction[2] = r1.z; out[i].tmax = r1.w;
+    }
+}
 // the product's skinning body (instance_build.h::skin_triangle, the body of k_skin_triangles) over a whole mesh
 void emu_skin_triangles(const RfwRTTriangle* src, const RfwJointData* skin, const float* joints, uint32_t num_joints, uint32_t n, RfwRTTriangle* dst) {
     for (uint32_t i = 0; i < n; i++) {

@@ -394,3 +394,18 @@ def test_skinning_body_matches_the_oracle(emu, oracle_mod):
     np.testing.assert_allclose(dst["normal"], ref["normal"], rtol=0, atol=2e-4)   # a float32 cross product of small edges
     for f in ("id", "mat_id", "light_id"):
         assert np.array_equal(dst[f], ref[f])
+
+
+def test_pinhole_camera_body_matches_the_oracle(emu, oracle_mod):
+    """Row a6 on the CPU tier: the product's pinhole ray body (traverse.h::pinhole_ray = the body of k_generate_pinhole behind
+    rfwb200_cast_primary; CameraView3D::generate_ray, structs.rs:549-556) against the oracle's primary rays for the C1 camera
+    set-up and an off-centre one: same origins and limits, directions to rounding."""
+    emu.emu_pinhole_rays.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    for (pos, look, w, h, fov) in (((0.0, 0.15, -1.2), (0.0, -0.1, 1.0), 160, 90, 40.0), ((3.0, 2.0, -4.0), (-0.5, -0.3, 0.8), 97, 61, 75.0)):
+        view = np.ascontiguousarray(scenes.camera_view(pos, look, w, h, fov_deg=fov))
+        ref = oracle_mod.OracleBackend().primary_rays(view, w, h).reshape(-1)
+        out = np.zeros(w * h, wire.RAY)
+        emu.emu_pinhole_rays(view.ctypes.data, w, h, out.ctypes.data)
+        assert np.array_equal(out["origin"], ref["origin"]) and np.array_equal(out["tmin"], ref["tmin"]) and np.array_equal(out["tmax"], ref["tmax"])
+        np.testing.assert_allclose(out["direction"], ref["direction"], rtol=0, atol=1e-6)  # the harness build contracts FMAs like nvcc, the oracle does not
+        np.testing.assert_allclose(np.linalg.norm(out["direction"].astype(np.float64), axis=1), 1.0, atol=1e-6)
