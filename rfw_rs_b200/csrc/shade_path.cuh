@@ -173,4 +173,54 @@ __device__ __forceinline__ void shade_path(const FrameParams& fp, const ShadeSce
     }
 }
 
+// pixel-centre pinhole ray of the debug views (CameraView3D::generate_ray with x + 0.5, y + 0.5): the body of k_wf_generate_centre
+__device__ __forceinline__ void centre_ray(const FrameParams& fp, uint32_t pixel, float3& o, float3& d) {
+    const float u = ((float)(pixel % fp.width) + 0.5f) * (1.0f / (float)fp.width), v = ((float)(pixel / fp.width) + 0.5f) * (1.0f / (float)fp.height);
+    o = ld3(fp.cam.pos);
+    d = normalize3(ld3(fp.cam.p1) + ld3(fp.cam.right) * u + ld3(fp.cam.up) * v - o);
+}
+
+// RenderMode debug views at the primary hit (the body of k_wf_debug_view): mode 1 world shading normal incl. normal map,
+// 2 albedo (material colour x diffuse map) | material id, 3 world position | t.  s4 / o4 / d4 as in shade_path.
+__device__ __forceinline__ float4 debug_view_value(const FrameParams& fp, const ShadeScene& ss, const uint32_t mode, const float4 s4, const float4 o4, const float4 d4) {
+    const int inst = __float_as_int(s4.x), prim = __float_as_int(s4.y);
+    float4 res = f4(0.0f, 0.0f, 0.0f, mode == 2u ? -1.0f : 0.0f);
+    if (inst >= 0) {
+        const InstanceShading* is = ss.inst + inst;
+        const float4* tp = reinterpret_cast<const float4*>(is->tris + prim);
+        const float4 q0 = __ldg(tp + 0), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2), q3 = __ldg(tp + 3), q4 = __ldg(tp + 4), q5 = __ldg(tp + 5), q6 = __ldg(tp + 6);
+        const float4 q7 = __ldg(tp + 7), q8 = __ldg(tp + 8), q9 = __ldg(tp + 9), q10 = __ldg(tp + 10);
+        const int mat_id = __float_as_int(q10.y);
+        const uint32_t bary = __float_as_uint(s4.w);
+        const float u = (float)(bary & 65535u) * (1.0f / 65535.0f), v = (float)(bary >> 16) * (1.0f / 65535.0f), w = 1.0f - u - v;
+        const float3 Dv = xyz(d4);
+        float3 N = xyz(q4) * w + xyz(q5) * u + xyz(q6) * v;
+        float3 T3 = xyz(q7) * w + xyz(q8) * u + xyz(q9) * v;
+        const float Tw = w * q7.w + u * q8.w + v * q9.w;
+        const float4 m0 = is->nrm0, m1 = is->nrm1, m2 = is->nrm2;
+        N = normalize3(f3(m0.x * N.x + m0.y * N.y + m0.z * N.z, m1.x * N.x + m1.y * N.y + m1.z * N.z, m2.x * N.x + m2.y * N.y + m2.z * N.z));
+        T3 = normalize3(f3(m0.x * T3.x + m0.y * T3.y + m0.z * T3.z, m1.x * T3.x + m1.y * T3.y + m1.z * T3.z, m2.x * T3.x + m2.y * T3.y + m2.z * T3.z));
+        const float3 B = cross3(N, T3) * Tw;
+        const uint32_t mflags = __ldg(&ss.materials[mat_id].flags);
+        float3 color = xyz(__ldg(reinterpret_cast<const float4*>(ss.materials[mat_id].color)));
+        if (mflags & 0x3Fu) {
+            const float lambda = sqrtf(q10.z) + log2f(fp.cam.spread_angle * (1.0f / fabsf(dot3(Dv, N))));
+            const float tu = w * q0.w + u * q1.w + v * q2.w, tv = w * q3.w + u * q4.w + v * q5.w;
+            const int dmap = __ldg(&ss.materials[mat_id].diffuse_map), nmap = __ldg(&ss.materials[mat_id].normal_map);
+            if ((mflags & 1u) && dmap >= 0 && (uint32_t)dmap < ss.n_textures) {
+                const float4 c = tex_fetch_trilinear(ss.textures[dmap], lambda, tu, tv);
+                color = color * f3(c.x, c.y, c.z);
+            }
+            if ((mflags & 2u) && nmap >= 0 && (uint32_t)nmap < ss.n_textures) {
+                const float4 c = tex_fetch(ss.textures[nmap], tu, tv, (int)lambda);
+                N = normalize3(T3 * ((c.x - 0.5f) * 2.0f) + B * ((c.y - 0.5f) * 2.0f) + N * ((c.z - 0.5f) * 2.0f));
+            }
+        }
+        if (mode == 1u) res = f4(N.x, N.y, N.z, 0.0f);
+        else if (mode == 2u) res = f4(color.x, color.y, color.z, (float)mat_id);
+        else { const float3 P = xyz(o4) + Dv * s4.z; res = f4(P.x, P.y, P.z, s4.z); }
+    }
+    return res;
+}
+
 }  // namespace rfw

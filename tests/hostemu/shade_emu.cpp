@@ -106,6 +106,25 @@ void emu_render(const SceneView* sv, const InstanceShading* inst_table, const Rf
     }
     if (stats) { stats[0] = n_ext; stats[1] = n_sh; }
 }
+// RenderMode debug views (k_wf_generate_centre -> extend -> k_wf_debug_view) one pixel at a time: out = h*w*4 floats
+void emu_debug_view(const SceneView* sv, const InstanceShading* inst_table, const RfwDeviceMaterial* mats, uint32_t n_mats, const TexDesc* textures, uint32_t n_textures,
+                    const RfwCameraView3D* cam, uint32_t w, uint32_t h, uint32_t mode, float* out) {
+    ShadeScene ss;
+    memset(&ss, 0, sizeof(ss));
+    ss.inst = inst_table; ss.materials = mats; ss.n_materials = n_mats; ss.textures = textures; ss.n_textures = n_textures;
+    FrameParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.cam = *cam; fp.width = w; fp.height = h; fp.npix = w * h;
+    for (uint32_t pixel = 0; pixel < w * h; pixel++) {
+        float3 o, d;
+        centre_ray(fp, pixel, o, d);
+        Hit hit;
+        trace_ray<false, false, 64>(*sv, o, d, 1e-4f, 1e26f, hit, nullptr);
+        const float4 s4 = f4(__int_as_float(hit.inst), __int_as_float(hit.prim), hit.t, __uint_as_float(pack_bary16(hit.u, hit.v)));
+        const float4 r = debug_view_value(fp, ss, mode, s4, f4(o.x, o.y, o.z, __uint_as_float(pixel)), f4(d.x, d.y, d.z, 0.0f));
+        out[4 * (size_t)pixel + 0] = r.x; out[4 * (size_t)pixel + 1] = r.y; out[4 * (size_t)pixel + 2] = r.z; out[4 * (size_t)pixel + 3] = r.w;
+    }
+}
 uint32_t emu_wang_hash(uint32_t s) { return wang_hash(s); }
 float emu_randf(uint32_t* s) { return randf(*s); }
 void emu_random_barycentrics(float r0, float* out) { const float3 b = random_barycentrics(r0); out[0] = b.x; out[1] = b.y; out[2] = b.z; }

@@ -298,11 +298,10 @@ def _instance_shading_table_numpy(desc, keep):
     return np.ascontiguousarray(np.concatenate(rows))
 
 
-def _emu_render(emu, shade_emu, desc, view, w, h, spp, depth, sky):
+def _emu_scene(emu, desc):
+    """Builds the scene with the harness (product builder + instance_record) and returns what the shading hooks need."""
     vp = C.c_void_p
     emu.emu_scene_view.restype = vp; emu.emu_scene_view.argtypes = [vp]
-    shade_emu.emu_render.argtypes = [vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, C.c_uint32,
-                                     C.c_uint32, C.c_uint32, C.c_float, vp, vp, vp, vp, C.c_uint32, vp]
     e = Emu(emu, desc)
     keep = [e]
     # the per-instance shading table as the PRODUCT derives it (instance_build.h::instance_record, the body of k_instance_prepare),
@@ -316,9 +315,8 @@ def _emu_render(emu, shade_emu, desc, view, w, h, spp, depth, sky):
     for f in ("nrm0", "nrm1", "nrm2"):
         np.testing.assert_allclose(table[f], ref_table[f], rtol=2e-6, atol=1e-7)
     assert np.array_equal(table["mesh_id"], ref_table["mesh_id"]) and ((table["tris"] != 0) == (ref_table["tris"] != 0)).all()
-    mats = np.ascontiguousarray(desc.materials)
-    al, pl, sl, dl = (np.ascontiguousarray(x) for x in (desc.area_lights, desc.point_lights, desc.spot_lights, desc.directional_lights))
-    acc = np.zeros((h, w, 4), np.float32); stats = np.zeros(2, np.uint64); skya = np.asarray(sky, np.float32); v = np.ascontiguousarray(view)
+    mats = np.ascontiguousarray(desc.materials); keep.append(mats)
+
     # texture.cuh::TexDesc records over RGBA8 mip chains (what Backend::set_textures keeps in HBM: BGRA inputs swizzled once)
     def tex_desc(t):
         chain = np.ascontiguousarray(np.concatenate([(l[:, :, [2, 1, 0, 3]] if t.format == 0 else l).reshape(-1) for l in t.levels])); keep.append(chain)
@@ -326,9 +324,20 @@ def _emu_render(emu, shade_emu, desc, view, w, h, spp, depth, sky):
         return r
     texs = np.ascontiguousarray(np.concatenate([tex_desc(t) for t in desc.textures])) if desc.textures else np.zeros(1, TEX_DESC)
     skyd = tex_desc(desc.skybox) if desc.skybox is not None else None
-    shade_emu.emu_render(emu.emu_scene_view(e.h), table.ctypes.data, mats.ctypes.data, len(mats), al.ctypes.data, len(al), pl.ctypes.data, len(pl), sl.ctypes.data, len(sl),
+    keep += [texs, skyd]
+    return {"sv": emu.emu_scene_view(e.h), "table": table, "mats": mats, "texs": texs, "n_tex": len(desc.textures), "sky": skyd, "keep": keep}
+
+
+def _emu_render(emu, shade_emu, desc, view, w, h, spp, depth, sky):
+    vp = C.c_void_p
+    shade_emu.emu_render.argtypes = [vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, C.c_uint32,
+                                     C.c_uint32, C.c_uint32, C.c_float, vp, vp, vp, vp, C.c_uint32, vp]
+    sc = _emu_scene(emu, desc)
+    al, pl, sl, dl = (np.ascontiguousarray(x) for x in (desc.area_lights, desc.point_lights, desc.spot_lights, desc.directional_lights))
+    acc = np.zeros((h, w, 4), np.float32); stats = np.zeros(2, np.uint64); skya = np.asarray(sky, np.float32); v = np.ascontiguousarray(view)
+    shade_emu.emu_render(sc["sv"], sc["table"].ctypes.data, sc["mats"].ctypes.data, len(sc["mats"]), al.ctypes.data, len(al), pl.ctypes.data, len(pl), sl.ctypes.data, len(sl),
                          dl.ctypes.data, len(dl), v.ctypes.data, w, h, 0, spp, depth, 10.0, skya.ctypes.data, acc.ctypes.data, stats.ctypes.data,
-                         texs.ctypes.data, len(desc.textures), skyd.ctypes.data if skyd is not None else None)
+                         sc["texs"].ctypes.data, sc["n_tex"], sc["sky"].ctypes.data if sc["sky"] is not None else None)
     return acc, stats
 
 
@@ -409,3 +418,24 @@ def test_pinhole_camera_body_matches_the_oracle(emu, oracle_mod):
         assert np.array_equal(out["origin"], ref["origin"]) and np.array_equal(out["tmin"], ref["tmin"]) and np.array_equal(out["tmax"], ref["tmax"])
         np.testing.assert_allclose(out["direction"], ref["direction"], rtol=0, atol=1e-6)  # the harness build contracts FMAs like nvcc, the oracle does not
         np.testing.assert_allclose(np.linalg.norm(out["direction"].astype(np.float64), axis=1), 1.0, atol=1e-6)
+
+
+def test_debug_views_on_the_cpu_match_the_oracle(emu, shade_emu, oracle_mod):
+    """SURVEY §8 (f)4 on the CPU tier: the RenderMode debug views (shade_path.cuh::centre_ray + debug_view_value = the bodies of
+    k_wf_generate_centre / k_wf_debug_view, on the product's traversal body) against the oracle's: world shading normal incl. the
+    normal map, albedo x diffuse map | material id, world position | t — same tolerance as the GPU test."""
+    vp = C.c_void_p
+    shade_emu.emu_debug_view.argtypes = [vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp]
+    desc = scenes.textured_scene(grid=4, subdiv=2, tex_size=64)
+    w, h = 160, 90
+    view = np.ascontiguousarray(scenes.camera_view((0, 2.5, -6.0), (0, -0.3, 1.0), w, h))
+    sc = _emu_scene(emu, desc)
+    cpu = oracle_mod.OracleBackend(det_eps=0.0); desc.apply(cpu)
+    for mode, tol in ((1, 2e-3), (2, 2e-3), (3, 2e-3)):
+        got = np.zeros((h, w, 4), np.float32)
+        shade_emu.emu_debug_view(sc["sv"], sc["table"].ctypes.data, sc["mats"].ctypes.data, len(sc["mats"]), sc["texs"].ctypes.data, sc["n_tex"], view.ctypes.data, w, h, mode,
+                                 got.ctypes.data)
+        ref = cpu.debug_view(view, w, h, mode)
+        bad = (np.abs(got - ref).max(axis=2) > tol * np.maximum(1.0, np.abs(ref).max(axis=2)))
+        assert bad.mean() < 5e-3, (mode, bad.mean())
+        assert np.abs(ref[..., :3]).sum() > 0
