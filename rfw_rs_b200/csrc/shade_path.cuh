@@ -29,6 +29,18 @@ struct ShadeOut {
     float sDist;
 };
 
+// path slot -> pixel of this rank's owned tiles (slots walk the owned tiles one after the other, row-major inside a tile): generate,
+// reduce, finalize and export all go through it
+__device__ __forceinline__ bool slot_to_pixel(const FrameParams& fp, const uint32_t* __restrict__ owned_tiles, uint32_t slot, uint32_t& pixel) {
+    const uint32_t tt = fp.tile * fp.tile;
+    const uint32_t tl = slot / tt, within = slot % tt;
+    const uint32_t tile = owned_tiles[tl];
+    const uint32_t x = (tile % fp.tiles_x) * fp.tile + within % fp.tile;
+    const uint32_t y = (tile / fp.tiles_x) * fp.tile + within / fp.tile;
+    pixel = x + y * fp.width;
+    return x < fp.width && y < fp.height;
+}
+
 // hit barycentrics as the reference stores them: 16 bits each (ray_gen.comp:66-69, ray_extend.comp:267)
 __device__ __forceinline__ uint32_t pack_bary16(float u, float v) { return (uint32_t)(65535.0f * u) + ((uint32_t)(65535.0f * v) << 16); }
 

@@ -25,16 +25,6 @@ namespace rfw {
         if (e_ != cudaSuccess) return e_; \
     } while (0)
 
-__device__ __forceinline__ bool slot_to_pixel(const FrameParams& fp, const uint32_t* __restrict__ owned_tiles, uint32_t slot, uint32_t& pixel) {
-    const uint32_t tt = fp.tile * fp.tile;
-    const uint32_t tl = slot / tt, within = slot % tt;
-    const uint32_t tile = owned_tiles[tl];
-    const uint32_t x = (tile % fp.tiles_x) * fp.tile + within % fp.tile;
-    const uint32_t y = (tile / fp.tiles_x) * fp.tile + within / fp.tile;
-    pixel = x + y * fp.width;
-    return x < fp.width && y < fp.height;
-}
-
 // ---- generate: ray_gen.comp:103-146 ------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_wf_generate(FrameParams fp, const uint32_t* __restrict__ owned_tiles, float4* __restrict__ O, float4* __restrict__ D,
                                                      uint32_t* __restrict__ counts) {

@@ -125,6 +125,17 @@ void emu_debug_view(const SceneView* sv, const InstanceShading* inst_table, cons
         out[4 * (size_t)pixel + 0] = r.x; out[4 * (size_t)pixel + 1] = r.y; out[4 * (size_t)pixel + 2] = r.z; out[4 * (size_t)pixel + 3] = r.w;
     }
 }
+// k_wf_export one slot at a time: this rank's accumulator tiles, tile-major (the product's slot_to_pixel index math)
+void emu_export_tiles(uint32_t w, uint32_t h, uint32_t tile, const uint32_t* owned_tiles, uint32_t n_owned, const float* accum, float* out) {
+    FrameParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.width = w; fp.height = h; fp.tile = tile; fp.tiles_x = (w + tile - 1) / tile; fp.max_paths = n_owned * tile * tile; fp.npix = w * h;
+    for (uint32_t slot = 0; slot < fp.max_paths; slot++) {
+        uint32_t pixel = 0;
+        const bool in = slot_to_pixel(fp, owned_tiles, slot, pixel);
+        for (int c = 0; c < 4; c++) out[4 * (size_t)slot + c] = in ? accum[4 * (size_t)pixel + c] : 0.0f;
+    }
+}
 uint32_t emu_wang_hash(uint32_t s) { return wang_hash(s); }
 float emu_randf(uint32_t* s) { return randf(*s); }
 void emu_random_barycentrics(float r0, float* out) { const float3 b = random_barycentrics(r0); out[0] = b.x; out[1] = b.y; out[2] = b.z; }

@@ -439,3 +439,26 @@ def test_debug_views_on_the_cpu_match_the_oracle(emu, shade_emu, oracle_mod):
         bad = (np.abs(got - ref).max(axis=2) > tol * np.maximum(1.0, np.abs(ref).max(axis=2)))
         assert bad.mean() < 5e-3, (mode, bad.mean())
         assert np.abs(ref[..., :3]).sum() > 0
+
+
+@pytest.mark.parametrize("world,w,h,tile", [(1, 70, 50, 16), (2, 200, 120, 32), (3, 130, 70, 16), (4, 64, 64, 64)])
+def test_tile_export_index_math_reassembles(shade_emu, world, w, h, tile):
+    """Row (e) on the CPU tier: the product's slot -> pixel index math (shade_path.cuh::slot_to_pixel, behind k_wf_generate / reduce /
+    finalize / export) exports every rank's tiles tile-major; gathered in rank order and put back by the documented layout
+    (sharding.assemble_host, the numpy mirror of k_wf_assemble) they give the full frame back exactly — ragged edge tiles, more
+    ranks than tiles, one tile per frame included."""
+    from rfw_rs_b200 import sharding
+
+    shade_emu.emu_export_tiles.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    frame = np.zeros((h, w, 4), np.float32)
+    frame[..., 0] = np.arange(w * h, dtype=np.float32).reshape(h, w); frame[..., 1] = 1.0; frame[..., 3] = 7.0
+    tpr = sharding.tiles_per_rank(w, h, tile, world)
+    gathered = np.zeros((world, tpr * tile * tile, 4), np.float32)
+    for r in range(world):
+        mine = np.ascontiguousarray(sharding.owned_tiles(w, h, tile, r, world), np.uint32)
+        out = np.zeros((max(1, len(mine)) * tile * tile, 4), np.float32)
+        if len(mine):
+            shade_emu.emu_export_tiles(w, h, tile, mine.ctypes.data, len(mine), frame.ctypes.data, out.ctypes.data)
+            gathered[r, : len(mine) * tile * tile] = out[: len(mine) * tile * tile]
+    img = sharding.assemble_host(gathered.reshape(-1, 4), w, h, tile, world, tpr)
+    assert np.array_equal(img, frame)
