@@ -48,11 +48,14 @@ def t_tolerance(rays, t):
     return REL_T * np.abs(t) + ULPS_T * 2.0 ** -24 * scale / dlen
 
 
-def compare_hits(rays, gpu, ref, scene_lookup, label="", max_fraction=MAX_MISMATCH_FRACTION):
+def compare_hits(rays, gpu, ref, scene_lookup, label="", max_fraction=MAX_MISMATCH_FRACTION, oracle_artefacts=False):
     """max_fraction bounds the number of CLASSIFIED near-ties (unclassified ones are never allowed).  Authored assets
     with coplanar duplicated faces (pica) need a looser count bound than the synthetic scenes: every pixel looking at
     such a face pair is an exact-depth tie between two different triangles."""
-    """scene_lookup(inst) -> (tris, 4x4 inverse matrix as float64 row-indexed) for the global instance id."""
+    """scene_lookup(inst) -> (tris, 4x4 inverse matrix as float64 row-indexed) for the global instance id.
+    oracle_artefacts=True (stress tests on ill-conditioned inputs only): a hit the ORACLE reports whose float64-exact t lies outside
+    the ray's (tmin, tmax) — its float32 Moller-Trumbore on a sliver triangle with the origin on the surface — explains a
+    mismatch as well; the product's answer is then checked to be exact-valid (or a miss)."""
     n = len(rays)
     assert len(gpu) == n and len(ref) == n
     same = (gpu["inst"] == ref["inst"]) & (gpu["prim"] == ref["prim"])
@@ -116,6 +119,9 @@ def compare_hits(rays, gpu, ref, scene_lookup, label="", max_fraction=MAX_MISMAT
                     ok = True
             if min(u, v, 1.0 - u - v) <= EDGE_EPS:
                 ok = True  # edge graze: MT and the watertight test may disagree about inside/outside
+        if not ok and oracle_artefacts and cand[1] is not None and not (float(rays["tmin"][i]) < cand[1][0] < float(rays["tmax"][i])):
+            # the oracle's hit does not exist in exact arithmetic; the product must then report a miss or an exact-valid hit
+            ok = cand[0] is None or (float(rays["tmin"][i]) < cand[0][0] < float(rays["tmax"][i]) and min(cand[0][1], cand[0][2], 1.0 - cand[0][1] - cand[0][2]) >= -EDGE_EPS)
         if not ok:
             unexplained.append((int(i), gpu[i], ref[i], cand))
     assert not unexplained, f"{label}: unexplained mismatches {unexplained[:3]}"
