@@ -523,3 +523,29 @@ def test_builder_and_traversal_stress_against_brute_force(emu, oracle_mod, seed)
     # rays starting ON a surface hit it at t ~ 0 +- rounding, i.e. around tmin: a documented near-tie class (3) of tests/parity.py
     parity.compare_hits(rays, hits, ref, parity.lookup_from_desc(desc), f"stress{seed}", max_fraction=5e-3, oracle_artefacts=True)
     assert (occ != o.trace_any(rays, mode=oracle_mod.MODE_BRUTE)).sum() <= max(3, int(5e-3 * m))
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_product_path_tracer_random_materials_and_lights(emu, shade_emu, oracle_mod, seed):
+    """The CPU-tier path tracer comparison again with the scene's eight materials and its punctual lights drawn at random (every
+    Disney parameter the packing carries, random light positions / cones / radiances, random aperture): the product's shade
+    step and the oracle must keep taking the same discrete decisions."""
+    rng = np.random.default_rng(500 + seed)
+    desc = scenes.lights_and_lobes_scene(grid=4, subdiv=1)
+    mats = [scenes.material(color=rng.uniform(0.05, 1.0, 3), metallic=rng.choice([0.0, 1.0, rng.uniform()]), roughness=rng.uniform(0.02, 1.0), specular_f=rng.uniform(),
+                            subsurface=rng.choice([0.0, rng.uniform()]), specular=rng.uniform(0.2, 1.0, 3), transmission=rng.choice([0.0, 1.0, rng.uniform()]),
+                            eta=rng.uniform(0.4, 1.0), clearcoat=rng.choice([0.0, rng.uniform()]), clearcoat_gloss=rng.uniform(), specular_tint=rng.uniform(),
+                            absorption=rng.uniform(0.0, 1.0, 3)) for _ in range(8)]
+    desc.materials = np.concatenate(mats + [desc.materials[8:9], desc.materials[9:10]])
+    desc.point_lights = np.concatenate([scenes.point_light(tuple(rng.uniform(-2, 2, 3) + (0, 3, 0)), tuple(rng.uniform(5, 40, 3))) for _ in range(int(rng.integers(1, 4)))])
+    desc.spot_lights = scenes.spot_light(tuple(rng.uniform(-1, 1, 3) + (0, 5, 0)), (rng.uniform(-0.3, 0.3), -1.0, rng.uniform(-0.3, 0.3)), float(rng.uniform(10, 30)),
+                                         float(rng.uniform(35, 60)), tuple(rng.uniform(30, 120, 3)))
+    desc.directional_lights = scenes.directional_light((rng.uniform(-0.5, 0.5), -1.0, rng.uniform(-0.5, 0.5)), tuple(rng.uniform(0.3, 1.5, 3)))
+    w, h, spp, depth, sky = 80, 45, 4, 5, tuple(rng.uniform(0.0, 0.4, 3))
+    view = scenes.camera_view((float(rng.uniform(-1, 1)), 3.0, -7.0), (0, -0.4, 1.0), w, h, aperture=float(rng.choice([1e-4, 0.03, 0.1])))
+    acc, stats = _emu_render(emu, shade_emu, desc, view, w, h, spp, depth, sky)
+    o = oracle_mod.OracleBackend(det_eps=0.0); desc.apply(o)
+    ref, st = o.render(view, w, h, spp, depth, clamp=10.0, sky=sky)
+    assert np.isfinite(acc).all() and acc.min() >= 0 and ref[..., :3].mean() / spp > 0.02
+    assert abs(int(stats[0]) - st["extension_rays"]) <= 0.003 * st["extension_rays"] + 2 and abs(int(stats[1]) - st["shadow_rays"]) <= 0.003 * st["shadow_rays"] + 2
+    _check_image(acc / spp, ref / spp, f"random materials {seed}", diverged_fraction=4e-3)
