@@ -86,7 +86,14 @@ def compare_hits(rays, gpu, ref, scene_lookup, label="", max_fraction=MAX_MISMAT
             pr = (1 - ref["u"][i] - ref["v"][i]) * v0 + ref["u"][i] * v1 + ref["v"][i] * v2
             oo = inv[:3, :3] @ rays["origin"][i].astype(np.float64) + inv[:3, 3]
             scale = max(np.abs(oo).max(), np.abs(pr).max(), 1e-6)
-            assert np.abs(pg - pr).max() <= 256 * 2.0 ** -24 * scale, f"{label}: barycentric err {duv[j]} = point err {np.abs(pg - pr).max()} at scale {scale}"
+            bound = 256 * 2.0 ** -24 * scale
+            if oracle_artefacts:
+                # stress tests: a grazing ray's in-plane hit position is ill-conditioned by 1 / cos(incidence) on BOTH sides
+                nrm = np.cross(v1 - v0, v2 - v0)
+                dd = inv[:3, :3] @ rays["direction"][i].astype(np.float64)
+                cos = abs(np.dot(nrm, dd)) / max(np.linalg.norm(nrm) * np.linalg.norm(dd), 1e-30)
+                bound /= max(cos, 1e-4)
+            assert np.abs(pg - pr).max() <= bound, f"{label}: barycentric err {duv[j]} = point err {np.abs(pg - pr).max()} at scale {scale}"
     miss = same & (ref["inst"] < 0)
     if miss.any():
         assert np.array_equal(gpu["t"][miss], ref["t"][miss]), f"{label}: miss records must carry tmax"
@@ -122,6 +129,9 @@ def compare_hits(rays, gpu, ref, scene_lookup, label="", max_fraction=MAX_MISMAT
         if not ok and oracle_artefacts and cand[1] is not None and not (float(rays["tmin"][i]) < cand[1][0] < float(rays["tmax"][i])):
             # the oracle's hit does not exist in exact arithmetic; the product must then report a miss or an exact-valid hit
             ok = cand[0] is None or (float(rays["tmin"][i]) < cand[0][0] < float(rays["tmax"][i]) and min(cand[0][1], cand[0][2], 1.0 - cand[0][1] - cand[0][2]) >= -EDGE_EPS)
+        if not ok and oracle_artefacts and cand[1] is None and cand[0] is not None:
+            # the oracle's float32 Moller-Trumbore missed a (sub-resolution) triangle that exact arithmetic says the ray hits
+            ok = float(rays["tmin"][i]) < cand[0][0] < float(rays["tmax"][i]) and min(cand[0][1], cand[0][2], 1.0 - cand[0][1] - cand[0][2]) >= -EDGE_EPS
         if not ok:
             unexplained.append((int(i), gpu[i], ref[i], cand))
     assert not unexplained, f"{label}: unexplained mismatches {unexplained[:3]}"

@@ -549,3 +549,49 @@ def test_product_path_tracer_random_materials_and_lights(emu, shade_emu, oracle_
     assert np.isfinite(acc).all() and acc.min() >= 0 and ref[..., :3].mean() / spp > 0.02
     assert abs(int(stats[0]) - st["extension_rays"]) <= 0.003 * st["extension_rays"] + 2 and abs(int(stats[1]) - st["shadow_rays"]) <= 0.003 * st["shadow_rays"] + 2
     _check_image(acc / spp, ref / spp, f"random materials {seed}", diverged_fraction=4e-3)
+
+
+@pytest.mark.parametrize("dist", ["identical", "two_points", "line", "plane_grid", "exponential", "huge_and_tiny"])
+@pytest.mark.parametrize("n", [2, 9, 257, 5000])
+def test_builder_structure_on_degenerate_distributions(emu, oracle_mod, dist, n):
+    """The product's builder bodies on inputs that stress the Morton / Karras / collapse logic: all centroids identical (every Morton
+    key equal: the radix tree degenerates to index splits), two clusters, centroids on a line or a planar grid (two Morton axes
+    constant), exponentially spread sizes, a huge triangle among tiny ones (root box dominated by one primitive: the 8-bit
+    quantisation grid is very coarse for the rest).  Structural validation (every primitive exactly once, every dequantised
+    child box encloses its subtree) plus hit parity with the brute force."""
+    rng = np.random.default_rng(n * 31 + len(dist))
+    if dist == "identical":
+        c = np.tile(rng.uniform(0, 1, (1, 3)), (n, 1))
+    elif dist == "two_points":
+        c = np.where((np.arange(n) % 2 == 0)[:, None], np.array([[0.1, 0.2, 0.3]]), np.array([[0.9, 0.8, 0.7]]))
+    elif dist == "line":
+        c = np.outer(rng.uniform(0, 1, n), np.array([1.0, 0.0, 0.0])) + np.array([0.0, 0.5, 0.5])
+    elif dist == "plane_grid":
+        g = int(np.ceil(np.sqrt(n)))
+        c = np.stack([(np.arange(n) % g) / g, np.full(n, 0.5), (np.arange(n) // g) / g], axis=1)
+    else:
+        c = rng.uniform(0, 1, (n, 3))
+    size = np.full(n, 0.02)
+    if dist == "exponential":
+        size = 10.0 ** rng.uniform(-5, -1, n)
+    if dist == "huge_and_tiny":
+        size = np.full(n, 1e-4); size[0] = 50.0
+    e1 = rng.normal(size=(n, 3)); e2 = rng.normal(size=(n, 3))
+    e1 /= np.linalg.norm(e1, axis=1, keepdims=True); e2 /= np.linalg.norm(e2, axis=1, keepdims=True)
+    tris = scenes.make_triangles(c.astype(np.float32), (c + e1 * size[:, None]).astype(np.float32), (c + e2 * size[:, None]).astype(np.float32))
+    desc = scenes.SceneDesc(); desc.meshes[0] = tris; desc.instances[0] = scenes.to_column_major([scenes.identity()]); desc.materials = scenes.material()
+    e = Emu(emu, desc)
+    assert emu.emu_validate(e.h, 0) == 0
+    o = oracle_mod.OracleBackend(det_eps=0.0); desc.apply(o)
+    rays = scenes.random_rays(1500, seed=n, lo=-0.2, hi=1.2)
+    # aim half of the rays at primitives so the small ones are hit at all
+    k = rng.integers(0, n, len(rays))
+    aim = (np.arange(len(rays)) % 2 == 0)
+    tgt = (tris["vertex0"][k] + tris["vertex1"][k] + tris["vertex2"][k]) / 3.0
+    dirs = tgt - rays["origin"]
+    dirs /= np.maximum(np.linalg.norm(dirs, axis=1, keepdims=True), 1e-20)
+    rays["direction"][aim] = dirs[aim].astype(np.float32)
+    hits, occ, _ = e.trace(rays)
+    ref = o.trace_closest(rays, mode=oracle_mod.MODE_BRUTE)
+    assert (ref["inst"] >= 0).mean() > 0.05
+    parity.compare_hits(rays, hits, ref, parity.lookup_from_desc(desc), f"{dist}/{n}", max_fraction=2e-2, oracle_artefacts=True)
