@@ -49,6 +49,14 @@ static constexpr int PT_FETCH = RFW_PT_FETCH;  // ray indices a warp reserves pe
 // accesses to one entry are 32 consecutive 8-byte words (conflict-free); deeper entries overflow to local memory.
 // Shared memory is addressed through its 32-bit window address with st/ld.shared (a generic pointer kept in a struct
 // made the compiler emit generic ST.E/LD.E and keep the stack pointer in local memory).
+#if defined(RFW_HOST_SIMT)
+// tests/hostemu/simt_emu.cpp: this kernel compiled for the HOST with one std::thread per lane (warp collectives = barriers),
+// so the CPU test tier can run the warp-level schedule itself; shared memory is a byte array of the harness
+__device__ __forceinline__ void sts_u2(uint32_t addr, uint2 v) { *reinterpret_cast<uint2*>(rfw_host_smem + addr) = v; }
+__device__ __forceinline__ uint2 lds_u2(uint32_t addr) { return *reinterpret_cast<const uint2*>(rfw_host_smem + addr); }
+__device__ __forceinline__ void sts_f4(uint32_t addr, float4 v) { *reinterpret_cast<float4*>(rfw_host_smem + addr) = v; }
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) { return *reinterpret_cast<const float4*>(rfw_host_smem + addr); }
+#else
 __device__ __forceinline__ void sts_u2(uint32_t addr, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory"); }
 __device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
     uint2 v;
@@ -63,6 +71,7 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
     return v;
 }
+#endif
 static constexpr int PT_L_STACK = 24;
 // Two-level kernels keep the WORLD-space ray of every lane in shared memory (3 x float4 [vector][thread]: origin,
 // direction, reciprocal direction, octant word) instead of six live registers: it is needed only when a lane enters an
@@ -356,6 +365,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
     }
 }
 
+#if !defined(RFW_HOST_SIMT)  // (the host SIMT harness calls the kernel body directly)
 // persistent grid: min(SMs * resident CTAs, CTAs needed for `n_hint` rays)
 template <class IO, bool ANY, bool TWO_LEVEL, int MIN_BLOCKS>
 static cudaError_t persistent_grid_mb(int sm_count, int blocks_per_sm_limit, uint32_t n_hint, int& grid_out) {
@@ -410,5 +420,7 @@ template <class IO, bool ANY, bool TWO_LEVEL>
 static cudaError_t persistent_grid_io(int sm_count, int blocks_per_sm_limit, uint32_t n_hint, int& grid) {
     return persistent_grid_mb<IO, ANY, TWO_LEVEL, (TWO_LEVEL ? RFW_PT_MIN_BLOCKS_TL : RFW_PT_MIN_BLOCKS)>(sm_count, blocks_per_sm_limit, n_hint, grid);
 }
+
+#endif  // !RFW_HOST_SIMT
 
 }  // namespace rfw

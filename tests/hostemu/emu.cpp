@@ -88,6 +88,7 @@ struct EmuScene {
     std::map<uint32_t, EmuMesh> meshes;
     std::map<uint32_t, std::vector<float>> inst;
     std::vector<InstanceRec> recs;
+    std::vector<InstanceRec> leaf_recs;    // recs in TLAS leaf-slot order (SceneView::leaf_instances, what k_gather_instances produces)
     std::vector<InstanceShading> shading;  // per GLOBAL instance id (what k_instance_prepare writes for k_wf_shade)
     EmuBvh tlas;
     SceneView sv;
@@ -171,7 +172,10 @@ void emu_build(void* s, float c_node, float c_prim, int pmax, uint64_t* stats) {
         emu_build(ilo, ihi, PT, sc.tlas);
         sc.sv.tlas_nodes = sc.tlas.nodes.data();
         sc.sv.tlas_refs = sc.tlas.leaf_prims.data();
+        sc.leaf_recs.resize(sc.tlas.leaf_prims.size());
+        for (size_t k = 0; k < sc.leaf_recs.size(); k++) sc.leaf_recs[k] = sc.recs[sc.tlas.leaf_prims[k]];
     }
+    sc.sv.leaf_instances = sc.sv.two_level ? sc.leaf_recs.data() : sc.recs.data();
     if (stats) { stats[0] = tot_nodes; stats[1] = sc.tlas.nodes.size() / NODE_F4; stats[2] = sc.recs.size(); }
 }
 

@@ -595,3 +595,45 @@ def test_builder_structure_on_degenerate_distributions(emu, oracle_mod, dist, n)
     ref = o.trace_closest(rays, mode=oracle_mod.MODE_BRUTE)
     assert (ref["inst"] >= 0).mean() > 0.05
     parity.compare_hits(rays, hits, ref, parity.lookup_from_desc(desc), f"{dist}/{n}", max_fraction=2e-2, oracle_artefacts=True)
+
+
+# ---- the persistent kernel's warp-level schedule on the CPU (tests/hostemu/simt_emu.cpp) ----------------------------------------
+@pytest.fixture(scope="module")
+def simt():
+    subprocess.check_call(["make", "-C", os.path.join(HERE, "hostemu"), "-s"])
+    L = C.CDLL(os.path.join(HERE, "hostemu", "libsimt_emu.so"))
+    L.simt_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.simt_trace.restype = C.c_int
+    return L
+
+
+@pytest.mark.parametrize("two_level", [False, True])
+@pytest.mark.parametrize("knobs", [(28, 4, 6), (31, 1, 1), (8, 32, 32), (28, 6, 3)])
+def test_persistent_kernel_schedule_on_the_cpu(emu, simt, two_level, knobs):
+    """k_trace_persistent ITSELF (trace_kernel.cuh: warp-level work fetch, refill, batched triangle phase, batched instance
+    entries with the world ray parked in shared memory, starvation bound, chunked fetch) compiled for the host and run with one
+    thread per lane, 4 warps sharing one work counter.  Whatever the schedule knobs (refill threshold, triangle batch, instance
+    batch — including values that park lanes until nobody can step), every ray must get exactly the hit the plain per-ray loop
+    (trace_ray) finds, closest and any-hit, ragged ray counts included; a lane that missed a warp collective would hang
+    (return code -1)."""
+    refill, tri_batch, inst_batch = knobs
+    desc = scenes.instanced_scene(grid=5, subdiv=1, n_lights=4) if two_level else scenes.soup_scene(3000, 0.05)
+    e = Emu(emu, desc)
+    emu.emu_scene_view.restype = C.c_void_p; emu.emu_scene_view.argtypes = [C.c_void_p]
+    sv = emu.emu_scene_view(e.h)
+    for n in (1, 37, 1500):
+        rays = scenes.random_rays(n, seed=n, lo=-3.0, hi=3.0) if two_level else scenes.random_rays(n, seed=n)
+        if two_level:
+            rays["origin"][:, 1] = np.abs(rays["origin"][:, 1]) * 0.4 + 0.05
+        if n > 100:
+            rays["origin"][::97, 0] = np.nan           # non-finite rays retire at once
+            rays["direction"][5::131] = (0.0, -1.0, 0.0)  # axis-parallel
+        ref_hits, ref_occ, _ = e.trace(rays)
+        hits = np.zeros(n, wire.HIT); hits["prim"] = -7
+        occ = np.full(n, 9, np.uint32)
+        assert simt.simt_trace(sv, rays.ctypes.data, n, hits.ctypes.data, None, 0, refill, tri_batch, inst_batch) == 0
+        assert simt.simt_trace(sv, rays.ctypes.data, n, None, occ.ctypes.data, 1, refill, tri_batch, inst_batch) == 0
+        assert np.array_equal(hits.view(np.uint8), ref_hits.view(np.uint8)), (n, np.nonzero(hits["prim"] != ref_hits["prim"])[0][:5])
+        assert np.array_equal(occ, ref_occ)
+        if n > 100:
+            assert (ref_hits["inst"] >= 0).mean() > 0.1
