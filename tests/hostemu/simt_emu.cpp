@@ -81,9 +81,20 @@ static inline size_t __cvta_generic_to_shared(const void*) { return 0; }  // sha
 #define __shared__
 #define __restrict__
 
+template <typename T>
+static inline T __ldcs(const T* p) { return *p; }
+template <typename T, typename V>
+static inline void __stcs(T* p, V v) { *p = (T)v; }
+static inline void __syncwarp() { (void)warp_exchange(0u); }  // all lanes of the warp call it (publish is warp-collective)
+static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline unsigned long long rfw_host_globaltimer() {
+    return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 static unsigned char* rfw_host_smem = nullptr;
 #define RFW_HOST_SIMT 1
 #include "../../rfw_rs_b200/csrc/trace_kernel.cuh"
+#include "../../rfw_rs_b200/csrc/ray_io.cuh"
 
 namespace rfw {
 alignas(16) uint2 smem_stack[8192];  // what `extern __shared__ uint2 smem_stack[]` of the kernel refers to (one CTA at a time)
@@ -107,8 +118,8 @@ struct HostRayIO {
     void publish(uint32_t, int) const {}
 };
 
-template <bool ANY, bool TWO_LEVEL>
-static int run_cta(const SceneView& sv, const HostRayIO& io, TraceTuning tune, int warps) {
+template <bool ANY, bool TWO_LEVEL, class IO>
+static int run_cta(const SceneView& sv, const IO& io, TraceTuning tune, int warps) {
     rfw_host_smem = reinterpret_cast<unsigned char*>(smem_stack);
     if (persistent_smem_bytes<TWO_LEVEL>() > sizeof(smem_stack)) return -2;
     g_blockDim = {(unsigned)(32 * warps), 1, 1}; g_gridDim = {1, 1, 1};
@@ -120,7 +131,7 @@ static int run_cta(const SceneView& sv, const HostRayIO& io, TraceTuning tune, i
         threads.emplace_back([&, t]() {
             tls_threadIdx = {(unsigned)t, 0, 0}; tls_blockIdx = {0, 0, 0};
             tls_warp = &ctx[t / 32]; tls_lane = t % 32;
-            k_trace_persistent<HostRayIO, ANY, TWO_LEVEL, PT_THREADS, 8, PT_SM_STACK>(sv, io, &counter, tune);
+            k_trace_persistent<IO, ANY, TWO_LEVEL, PT_THREADS, 8, PT_SM_STACK>(sv, io, &counter, tune);
         });
     }
     for (auto& th : threads) th.join();
@@ -135,5 +146,51 @@ int simt_trace(const void* scene_view, const RfwRay* rays, uint32_t n, RfwHit* h
     const TraceTuning tune{refill_below, tri_batch, 4, inst_batch};
     if (any_hit) return sv.two_level ? run_cta<true, true>(sv, io, tune, PT_THREADS / 32) : run_cta<true, false>(sv, io, tune, PT_THREADS / 32);
     return sv.two_level ? run_cta<false, true>(sv, io, tune, PT_THREADS / 32) : run_cta<false, false>(sv, io, tune, PT_THREADS / 32);
+}
+
+// The HOST-STREAMED policy (ray_io.cuh::StreamedRayIO, the product's own) under the same harness: a feeder thread plays the upload
+// stream (advances the watermark by `chunk` rays every `delay_us`), a monitor thread plays the download side: it takes the minimum
+// of the warps' progress slots and checks that every ray below it HAS been stored (hits must be pre-filled with prim = -7) — the
+// invariant the product's host loop relies on when it downloads a granule.  out[0] = violations, out[1] = monitor rounds,
+// out[2] = largest bound seen below n, out[3] = abort flag.
+int simt_trace_streamed(const void* scene_view, const RfwRay* rays, uint32_t n, RfwHit* hits, uint32_t chunk, uint32_t delay_us, int refill_below, int tri_batch,
+                        int inst_batch, uint64_t* out) {
+    const SceneView& sv = *reinterpret_cast<const SceneView*>(scene_view);
+    const int warps = PT_THREADS / 32;
+    uint32_t watermark = 0, abort_flag = 0;
+    std::vector<uint32_t> slots(warps, 0u);
+    const StreamedRayIO io{RayBufferIO{reinterpret_cast<const float4*>(rays), n, hits, nullptr}, &watermark, slots.data(), &abort_flag,
+                           rfw_host_globaltimer() + 20000000000ull};
+    const TraceTuning tune{refill_below, tri_batch, 4, inst_batch};
+    std::atomic<bool> done{false};
+    uint64_t violations = 0, rounds = 0, best = 0;
+    std::thread feeder([&]() {
+        uint32_t wm = 0;
+        while (wm < n && !done.load()) {
+            std::this_thread::sleep_for(std::chrono::microseconds(delay_us));
+            wm = wm + chunk < n ? wm + chunk : n;
+            __atomic_store_n(&watermark, wm, __ATOMIC_RELEASE);
+        }
+    });
+    std::thread monitor([&]() {
+        uint32_t checked = 0;
+        while (!done.load()) {
+            uint32_t bound = 0xFFFFFFFFu;
+            for (int w = 0; w < warps; w++) { const uint32_t v = __atomic_load_n(&slots[w], __ATOMIC_ACQUIRE); bound = v < bound ? v : bound; }
+            const uint32_t upto = bound < n ? bound : n;
+            for (uint32_t i = checked; i < upto; i++) if (__atomic_load_n(&hits[i].prim, __ATOMIC_ACQUIRE) == -7) violations++;
+            if (upto > checked) checked = upto;
+            if (bound < n && bound > best) best = bound;
+            rounds++;
+            std::this_thread::yield();
+        }
+    });
+    const int rc = sv.two_level ? run_cta<false, true>(sv, io, tune, warps) : run_cta<false, false>(sv, io, tune, warps);
+    done.store(true);
+    feeder.join(); monitor.join();
+    // at the end every warp must have published "nothing in flight"
+    for (int w = 0; w < warps; w++) if (slots[w] != 0xFFFFFFFFu) violations += 1000000;
+    if (out) { out[0] = violations; out[1] = rounds; out[2] = best; out[3] = abort_flag; }
+    return rc;
 }
 }

@@ -637,3 +637,32 @@ def test_persistent_kernel_schedule_on_the_cpu(emu, simt, two_level, knobs):
         assert np.array_equal(occ, ref_occ)
         if n > 100:
             assert (ref_hits["inst"] >= 0).mean() > 0.1
+
+
+@pytest.mark.parametrize("two_level", [False, True])
+@pytest.mark.parametrize("chunk,delay_us", [(64, 200), (500, 50), (4096, 0)])
+def test_host_streamed_policy_on_the_cpu(emu, simt, two_level, chunk, delay_us):
+    """The product's host-streamed I/O policy (ray_io.cuh::StreamedRayIO behind rfwb200_trace_closest with pinned buffers) under
+    the lane-thread harness: a feeder thread advances the upload watermark chunk by chunk while the kernel runs (lanes whose ray
+    has not landed wait while the rest of their warp traverses), a monitor thread takes the minimum of the per-warp progress
+    slots and checks the invariant the product's download loop relies on — every ray below that bound HAS been stored.  Slow
+    trickle (kernel mostly waiting), fast trickle, everything landed at once; results bit-identical to the per-ray loop."""
+    simt.simt_trace_streamed.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    simt.simt_trace_streamed.restype = C.c_int
+    desc = scenes.instanced_scene(grid=5, subdiv=1, n_lights=4) if two_level else scenes.soup_scene(3000, 0.05)
+    e = Emu(emu, desc)
+    emu.emu_scene_view.restype = C.c_void_p; emu.emu_scene_view.argtypes = [C.c_void_p]
+    sv = emu.emu_scene_view(e.h)
+    n = 3001
+    rays = scenes.random_rays(n, seed=5, lo=-3.0, hi=3.0) if two_level else scenes.random_rays(n, seed=5)
+    if two_level:
+        rays["origin"][:, 1] = np.abs(rays["origin"][:, 1]) * 0.4 + 0.05
+    ref_hits, _, _ = e.trace(rays)
+    hits = np.zeros(n, wire.HIT); hits["prim"] = -7
+    out = np.zeros(4, np.uint64)
+    rc = simt.simt_trace_streamed(sv, rays.ctypes.data, n, hits.ctypes.data, chunk, delay_us, 28, 4, 6, out.ctypes.data)
+    assert rc == 0 and out[3] == 0, (rc, out)
+    assert out[0] == 0, f"{int(out[0])} rays below the published bound were not stored yet"
+    assert np.array_equal(hits.view(np.uint8), ref_hits.view(np.uint8))
+    if delay_us > 0:
+        assert out[2] > 0   # the monitor did see intermediate bounds: granules would have been downloaded while the kernel ran
