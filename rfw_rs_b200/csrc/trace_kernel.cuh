@@ -104,7 +104,11 @@ struct TraceTuning {
 
 template <class IO, bool ANY, bool TWO_LEVEL, int THREADS, int MIN_BLOCKS, int SM_STACK>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneView sv, IO io, uint32_t* __restrict__ counter, TraceTuning tune) {
+#if defined(RFW_HOST_SIMT)
+    uint2* const smem_stack = reinterpret_cast<uint2*>(rfw_host_smem);  // (the host SIMT harness: shared memory is a byte array)
+#else
     extern __shared__ uint2 smem_stack[];
+#endif
     const uint32_t n = io.count();
     const int lane = threadIdx.x & 31;
     const uint32_t lanemask_lt = (1u << lane) - 1u;

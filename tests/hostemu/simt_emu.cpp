@@ -5,100 +5,16 @@
 // of a warp; shared memory is a byte array; atomics are host atomics.  All lanes of a warp must reach the same sequence of
 // collectives — exactly the convergence requirement of the *_sync intrinsics — so a divergent collective hangs here (the
 // harness times out) instead of being undefined behaviour.  One CTA (4 warps = 128 threads) runs at a time.
-#include <atomic>
-#include <chrono>
-#include <cstdio>
-#include <thread>
-#include <vector>
-
 #include "device_shims.h"
 
-// ---- the SIMT machine --------------------------------------------------------------------------------------------------
-struct EmuDim3 { unsigned x, y, z; };
-static thread_local EmuDim3 tls_threadIdx, tls_blockIdx;
-static EmuDim3 g_blockDim, g_gridDim;
-#define threadIdx tls_threadIdx
-#define blockIdx tls_blockIdx
-#define blockDim g_blockDim
-#define gridDim g_gridDim
-
-struct WarpCtx {
-    std::atomic<unsigned> arrived{0};
-    std::atomic<unsigned> generation{0};
-    uint32_t slot[2][32];
-    unsigned phase_of_lane[32] = {0};
-};
-static thread_local WarpCtx* tls_warp = nullptr;
-static thread_local int tls_lane = 0;
-static std::atomic<bool> g_abort{false};
-
-// sense-reversing barrier over the 32 lanes of a warp; gives up (sets g_abort) when a lane never arrives
-static inline void warp_barrier(WarpCtx* w) {
-    const unsigned gen = w->generation.load(std::memory_order_acquire);
-    if (w->arrived.fetch_add(1, std::memory_order_acq_rel) + 1 == 32) {
-        w->arrived.store(0, std::memory_order_relaxed);
-        w->generation.store(gen + 1, std::memory_order_release);
-        return;
-    }
-    auto t0 = std::chrono::steady_clock::now();
-    unsigned spins = 0;
-    while (w->generation.load(std::memory_order_acquire) == gen) {
-        if ((++spins & 1023u) == 0) {
-            std::this_thread::yield();
-            if (g_abort.load() || std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) { g_abort.store(true); return; }
-        }
-    }
-}
-// every lane contributes one word, then reads all 32 (double-buffered: one barrier per collective)
-static inline const uint32_t* warp_exchange(uint32_t v) {
-    WarpCtx* w = tls_warp;
-    const unsigned ph = w->phase_of_lane[tls_lane]++ & 1u;
-    w->slot[ph][tls_lane] = v;
-    warp_barrier(w);
-    return w->slot[ph];
-}
-static inline uint32_t __ballot_sync(uint32_t, bool pred) {
-    const uint32_t* s = warp_exchange(pred ? 1u : 0u);
-    uint32_t m = 0;
-    for (int i = 0; i < 32; i++) m |= (s[i] & 1u) << i;
-    return m;
-}
-static inline bool __any_sync(uint32_t mask, bool pred) { return __ballot_sync(mask, pred) != 0u; }
-static inline uint32_t __shfl_sync(uint32_t, uint32_t v, int src) { return warp_exchange(v)[src & 31]; }
-static inline uint32_t __reduce_min_sync(uint32_t, uint32_t v) {
-    const uint32_t* s = warp_exchange(v);
-    uint32_t m = 0xFFFFFFFFu;
-    for (int i = 0; i < 32; i++) m = s[i] < m ? s[i] : m;
-    return m;
-}
-static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
-static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
-static inline void __nanosleep(unsigned) { std::this_thread::yield(); }
-static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL); }
-static inline size_t __cvta_generic_to_shared(const void*) { return 0; }  // shared "addresses" are offsets into rfw_host_smem
-#define __global__
-#define __launch_bounds__(...)
-#define __shared__
-#define __restrict__
-
-template <typename T>
-static inline T __ldcs(const T* p) { return *p; }
-template <typename T, typename V>
-static inline void __stcs(T* p, V v) { *p = (T)v; }
-static inline void __syncwarp() { (void)warp_exchange(0u); }  // all lanes of the warp call it (publish is warp-collective)
-static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
-static inline unsigned long long rfw_host_globaltimer() {
-    return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
-}
+#include "simt_machine.h"
 
 static unsigned char* rfw_host_smem = nullptr;
 #define RFW_HOST_SIMT 1
 #include "../../rfw_rs_b200/csrc/trace_kernel.cuh"
 #include "../../rfw_rs_b200/csrc/ray_io.cuh"
 
-namespace rfw {
-alignas(16) uint2 smem_stack[8192];  // what `extern __shared__ uint2 smem_stack[]` of the kernel refers to (one CTA at a time)
-}
+alignas(16) static unsigned char g_smem[65536];  // the CTA's shared memory (one CTA at a time)
 using namespace rfw;
 
 // plain ray-buffer I/O policy (the role of trace.cu::RayBufferIO)
@@ -120,8 +36,8 @@ struct HostRayIO {
 
 template <bool ANY, bool TWO_LEVEL, class IO>
 static int run_cta(const SceneView& sv, const IO& io, TraceTuning tune, int warps) {
-    rfw_host_smem = reinterpret_cast<unsigned char*>(smem_stack);
-    if (persistent_smem_bytes<TWO_LEVEL>() > sizeof(smem_stack)) return -2;
+    rfw_host_smem = g_smem;
+    if (persistent_smem_bytes<TWO_LEVEL>() > sizeof(g_smem)) return -2;
     g_blockDim = {(unsigned)(32 * warps), 1, 1}; g_gridDim = {1, 1, 1};
     g_abort.store(false);
     uint32_t counter = 0;
