@@ -666,3 +666,43 @@ def test_host_streamed_policy_on_the_cpu(emu, simt, two_level, chunk, delay_us):
     assert np.array_equal(hits.view(np.uint8), ref_hits.view(np.uint8))
     if delay_us > 0:
         assert out[2] > 0   # the monitor did see intermediate bounds: granules would have been downloaded while the kernel ran
+
+
+@pytest.mark.parametrize("which", ["instanced", "lights_and_lobes", "textured"])
+def test_wavefront_kernels_on_the_cpu(emu, shade_emu, oracle_mod, which):
+    """The wavefront path tracer's KERNELS themselves on the CPU tier (tests/hostemu/wf_emu.cpp): k_wf_generate, the persistent
+    traversal kernel behind ExtendIO / ConnectIO, k_wf_shade with its per-CTA queue-slot reservation, k_wf_advance and
+    k_wf_reduce, launched in the order Wavefront::render launches them on the lane-thread SIMT machine, with the queues, the
+    shadow queue and the per-sample partial accumulators as host arrays.  The image must equal, BIT FOR BIT, what the same
+    per-path bodies produce one path at a time (emu_render) — the queues, compaction and atomics add nothing and lose nothing,
+    whatever the arrival order of the threads — and agree with the oracle within the image tolerance."""
+    from rfw_rs_b200 import sharding
+
+    subprocess.check_call(["make", "-C", os.path.join(HERE, "hostemu"), "-s"])
+    W = C.CDLL(os.path.join(HERE, "hostemu", "libwf_emu.so"))
+    vp = C.c_void_p
+    W.wf_render.argtypes = [vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32,
+                            vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, vp, C.c_int, vp, vp]
+    W.wf_render.restype = C.c_int
+    if which == "instanced":
+        desc, view_kw = scenes.instanced_scene(grid=5, subdiv=1, n_lights=4), {}
+    elif which == "lights_and_lobes":
+        desc, view_kw = scenes.lights_and_lobes_scene(grid=3, subdiv=1), {"aperture": 0.05}
+    else:
+        desc, view_kw = scenes.textured_scene(grid=3, subdiv=1, tex_size=32), {}
+    w, h, spp, depth, sky, tile = 60, 34, 3, 4, (0.2, 0.2, 0.3), 16     # ragged edge tiles: 60 and 34 are not multiples of 16
+    view = np.ascontiguousarray(scenes.camera_view((0, 3.0, -7.0), (0, -0.4, 1.0), w, h, **view_kw))
+    sc = _emu_scene(emu, desc)
+    al, pl, sl, dl = (np.ascontiguousarray(x) for x in (desc.area_lights, desc.point_lights, desc.spot_lights, desc.directional_lights))
+    owned = np.ascontiguousarray(sharding.owned_tiles(w, h, tile, 0, 1), np.uint32)
+    acc = np.zeros((h, w, 4), np.float32); stats = np.zeros(2, np.uint64); skya = np.asarray(sky, np.float32)
+    rc = W.wf_render(sc["sv"], sc["table"].ctypes.data, sc["mats"].ctypes.data, len(sc["mats"]), al.ctypes.data, len(al), pl.ctypes.data, len(pl), sl.ctypes.data, len(sl),
+                     dl.ctypes.data, len(dl), sc["texs"].ctypes.data, sc["n_tex"], sc["sky"].ctypes.data if sc["sky"] is not None else None, view.ctypes.data, w, h, tile,
+                     owned.ctypes.data, len(owned), 0, spp, depth, 10.0, skya.ctypes.data, 3, acc.ctypes.data, stats.ctypes.data)
+    assert rc == 0
+    serial, sstats = _emu_render(emu, shade_emu, desc, view, w, h, spp, depth, sky)
+    assert int(stats[0]) == int(sstats[0]) and int(stats[1]) == int(sstats[1])       # same extension / shadow ray counts
+    assert np.array_equal(acc[..., :3], serial[..., :3])                               # bit for bit
+    o = oracle_mod.OracleBackend(det_eps=0.0); desc.apply(o)
+    ref, _ = o.render(view, w, h, spp, depth, clamp=10.0, sky=sky)
+    _check_image(acc / spp, ref / spp, which, diverged_fraction=4e-3)
