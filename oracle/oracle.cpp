@@ -822,7 +822,7 @@ static V3 BSDFEval(const ShadingData& sd, V3 N, V3 wo, V3 wi, float t, bool back
             const float Dr = GTR1(NDotH, mixf(.1f, .001f, sd.clearcoat_gloss));
             const float Fc = mixf(.04f, 1.0f, FH);
             const float Gr = SmithGGX(NDotL, .25f) * SmithGGX(NDotV, .25f);
-            brdf = Cdlin * (INVPI * Fd) * (1.0f - sd.metallic) * (1.0f - sd.subsurface) + Fs * (Gs * Ds) + V3(sd.clearcoat * Gr * Fc * Dr);
+            brdf = Cdlin * (INVPI * Fd) * (1.0f - sd.metallic) * (1.0f - sd.subsurface) + (Fs * Gs) * Ds + V3(sd.clearcoat * Gr * Fc * Dr);  // `Gs * Fs * Ds` associates left to right
         }
     }
     const V3 fin = mix(brdf, bsdf, sd.transmission);
@@ -1176,6 +1176,15 @@ void orc_sample_texture(void* s, int tex, int mode, float u, float v, float lod,
     else if (mode == 1) t.fetch_trilinear(lod, u, v, out);
     else t.sample_level(u, v, (int)lod, false, true, out);
 }
+// texture-unit call-back for oracle/_ref (signature ref_texture_fn of oracle/ref_glsl/glsl_host.h): the reference's shaders
+// sample through fixed-function units, which are not shader source; the harness plugs the oracle's sampler in.
+// layer < 0: skybox (ClampToEdge, bilinear, integer level); else the material texture array (fetchTexel semantics)
+void orc_texture_callback(void* s, int layer, float u, float v, float lod, float* out) {
+    const Scene& sc = *(Scene*)s;
+    out[0] = out[1] = out[2] = out[3] = 0.0f;
+    if (layer < 0) { if (sc.has_sky) sc.skybox.sample_level(u, v, (int)lod, false, true, out); return; }
+    if ((size_t)layer < sc.textures.size()) sc.textures[layer].fetch(u, v, (int)lod, out);
+}
 void orc_set_area_lights(void* s, const RfwAreaLight* l, uint32_t n) { ((Scene*)s)->area_lights.assign(l, l + n); }
 void orc_set_point_lights(void* s, const RfwPointLight* l, uint32_t n) { ((Scene*)s)->point_lights.assign(l, l + n); }
 void orc_set_spot_lights(void* s, const RfwSpotLight* l, uint32_t n) { ((Scene*)s)->spot_lights.assign(l, l + n); }
@@ -1347,6 +1356,48 @@ void orc_light_batch(void* sp, uint32_t n, const float* r0, const float* I, cons
         q[0] = P.x; q[1] = P.y; q[2] = P.z; q[3] = pick; q[4] = lpdf; q[5] = col.x; q[6] = col.y; q[7] = col.z;
     }
 }
+
+// batch hooks for tests/test_ref_glsl.py (the oracle's device-function restatements held against oracle/_ref):
+// triangle i against ray i: hit[i] (closest form, accepted iff tmin < t < tmax), tuv[3i..] = t (tmax on a miss), u, v; occl[i] = any-hit form
+void orc_triangle_batch(const RfwRTTriangle* tris, const RfwRay* rays, uint64_t n, float det_eps, int* hit, float* tuv, int* occl) {
+    for (uint64_t i = 0; i < n; i++) {
+        float t, u, v;
+        const bool cand = mt_intersect(tris[i], V3(rays[i].origin), V3(rays[i].direction), det_eps, t, u, v);
+        const bool h = cand && t > rays[i].tmin && t < rays[i].tmax;
+        hit[i] = h ? 1 : 0;
+        tuv[3 * i] = h ? t : rays[i].tmax; tuv[3 * i + 1] = h ? u : 0.0f; tuv[3 * i + 2] = h ? v : 0.0f;
+        if (occl) occl[i] = h ? 1 : 0;
+    }
+}
+// node i against ray i: out2[3i..] = hit, tmin of the BVH2 test; out4[9i..] = any | result[4] | sorted tmin bit patterns (intersect_mnode)
+void orc_node_batch(const BVHNode* b2, const MBVHNode* b4, const RfwRay* rays, uint64_t n, float* out2, uint32_t* out4) {
+    for (uint64_t i = 0; i < n; i++) {
+        const V3 o(rays[i].origin), d(rays[i].direction);
+        const V3 di(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+        if (b2) {
+            float tmn = 0.0f;
+            const bool h = intersect_node(b2[i], o, di, rays[i].tmax, tmn);
+            out2[3 * i] = h ? 1.0f : 0.0f; out2[3 * i + 1] = tmn; out2[3 * i + 2] = 0.0f;
+        }
+        if (b4) {
+            float srt[4] = {0, 0, 0, 0};
+            const int mask = intersect_mnode(b4[i], o, di, rays[i].tmax, srt);
+            uint32_t* q = out4 + 9 * i;
+            q[0] = mask ? 1u : 0u;
+            for (int k = 0; k < 4; k++) { q[1 + k] = (mask >> k) & 1u; q[5 + k] = f2u(srt[k]); }
+        }
+    }
+}
+// thin-lens eye rays (ray_gen.comp:103-146, hash RNG branch) of pixels [0, n) at sample index `sample`: 6 floats each
+void orc_eye_rays(const RfwCameraView3D* cam, uint32_t w, uint32_t h, uint32_t n, uint32_t sample, float* out) {
+    for (uint32_t p = 0; p < n; p++) {
+        uint32_t seed = wang_hash(p * 16789u + sample * 1791u);
+        V3 O, D;
+        eye_ray(*cam, (int)w, (int)h, (int)(p % w), (int)(p / w), seed, O, D);
+        float* q = out + 6 * (size_t)p;
+        q[0] = O.x; q[1] = O.y; q[2] = O.z; q[3] = D.x; q[4] = D.y; q[5] = D.z;
+    }
+}
 uint32_t orc_wang_hash(uint32_t s) { return wang_hash(s); }
 float orc_randf(uint32_t* s) { return randf(*s); }
 void orc_random_barycentrics(float r0, float* out) { V3 b = random_barycentrics(r0); out[0] = b.x; out[1] = b.y; out[2] = b.z; }
@@ -1358,4 +1409,55 @@ void orc_bvh_stats(void* s, uint32_t mesh, uint64_t* out) {
     out[0] = it->second.bvh.nodes.size(); out[1] = it->second.bvh.mnodes.size();
 }
 uint32_t orc_num_live_instances(void* s) { return (uint32_t)((Scene*)s)->instances.size(); }
+
+// The scene in the reference's GPU buffer layout (backends/gpu-rt/src/lib.rs:1387-1553 per-mesh concatenation with offsets,
+// :1571-1632 instance descriptors + TLAS): lets oracle/_ref (the reference's own traversal / shading kernels compiled for
+// the host) run on exactly the trees the oracle walks.  Two-call protocol: with out == nullptr the counts are returned in
+// counts[0..7] = triangles, prim indices, BVH2 nodes, MBVH nodes, instances, TLAS BVH2 nodes, TLAS MBVH nodes, TLAS indices;
+// otherwise the eleven arrays are filled.  instances: 256-byte InstanceDescriptor records (structs.glsl:110-122) in the
+// oracle's live-instance order; global_ids[i] / tri_offsets[i]: what maps a reference hit (instance index, GLOBAL triangle
+// index) back to (global instance id, mesh-local primitive).
+struct OrcFlat {
+    RfwRTTriangle* triangles; uint32_t* prim_indices; BVHNode* bvh_nodes; MBVHNode* mbvh_nodes; uint8_t* instances;
+    BVHNode* top_bvh_nodes; MBVHNode* top_mbvh_nodes; uint32_t* instance_indices; int32_t* global_ids; uint32_t* tri_offsets;
+};
+void orc_flatten(void* s, uint64_t* counts, const OrcFlat* out) {
+    const Scene& sc = *(Scene*)s;
+    std::map<const Mesh*, uint32_t> slot;  // unique geometries in first-use order
+    std::vector<const Mesh*> geoms;
+    for (const Instance& in : sc.instances)
+        if (!slot.count(in.geom)) { slot[in.geom] = (uint32_t)geoms.size(); geoms.push_back(in.geom); }
+    std::vector<uint32_t> tri_off(geoms.size()), prim_off(geoms.size()), bvh_off(geoms.size()), mbvh_off(geoms.size());
+    uint64_t nt = 0, np = 0, nb = 0, nm = 0;
+    for (size_t g = 0; g < geoms.size(); g++) {
+        tri_off[g] = (uint32_t)nt; prim_off[g] = (uint32_t)np; bvh_off[g] = (uint32_t)nb; mbvh_off[g] = (uint32_t)nm;
+        nt += geoms[g]->tris.size(); np += geoms[g]->bvh.prim_indices.size(); nb += geoms[g]->bvh.nodes.size(); nm += geoms[g]->bvh.mnodes.size();
+    }
+    counts[0] = nt; counts[1] = np; counts[2] = nb; counts[3] = nm; counts[4] = sc.instances.size();
+    counts[5] = sc.tlas.nodes.size(); counts[6] = sc.tlas.mnodes.size(); counts[7] = sc.tlas.prim_indices.size();
+    if (!out) return;
+    for (size_t g = 0; g < geoms.size(); g++) {
+        const Mesh& m = *geoms[g];
+        if (!m.tris.empty()) std::memcpy(out->triangles + tri_off[g], m.tris.data(), m.tris.size() * sizeof(RfwRTTriangle));
+        if (!m.bvh.prim_indices.empty()) std::memcpy(out->prim_indices + prim_off[g], m.bvh.prim_indices.data(), m.bvh.prim_indices.size() * 4);
+        if (!m.bvh.nodes.empty()) std::memcpy(out->bvh_nodes + bvh_off[g], m.bvh.nodes.data(), m.bvh.nodes.size() * sizeof(BVHNode));
+        if (!m.bvh.mnodes.empty()) std::memcpy(out->mbvh_nodes + mbvh_off[g], m.bvh.mnodes.data(), m.bvh.mnodes.size() * sizeof(MBVHNode));
+    }
+    for (size_t i = 0; i < sc.instances.size(); i++) {
+        const Instance& in = sc.instances[i];
+        const uint32_t g = slot[in.geom];
+        uint8_t* d = out->instances + 256 * i;
+        std::memset(d, 0, 256);
+        const uint32_t offs[4] = {bvh_off[g], mbvh_off[g], tri_off[g], prim_off[g]};  // bvh_offset, mbvh_offset, triangle_offset, prim_index_offset
+        std::memcpy(d, offs, 16);
+        std::memcpy(d + 64, in.matrix.m, 64);
+        std::memcpy(d + 128, in.inverse.m, 64);
+        std::memcpy(d + 192, in.normal.m, 64);
+        out->global_ids[i] = in.global_id;
+        out->tri_offsets[i] = tri_off[g];
+    }
+    if (!sc.tlas.nodes.empty()) std::memcpy(out->top_bvh_nodes, sc.tlas.nodes.data(), sc.tlas.nodes.size() * sizeof(BVHNode));
+    if (!sc.tlas.mnodes.empty()) std::memcpy(out->top_mbvh_nodes, sc.tlas.mnodes.data(), sc.tlas.mnodes.size() * sizeof(MBVHNode));
+    if (!sc.tlas.prim_indices.empty()) std::memcpy(out->instance_indices, sc.tlas.prim_indices.data(), sc.tlas.prim_indices.size() * 4);
+}
 }

@@ -44,10 +44,14 @@ struct M4 {
     float m[16];
     float at(int r, int c) const { return m[c * 4 + r]; }
 };
+// M * (p, 1).  Summation order (c0 x + c1 y) + (c2 z + c3): the order of `mat4 * vec4` is not specified by GLSL; this is the
+// one glm (the library the reference vendors, and what oracle/_ref compiles the shaders against) evaluates, so object-space
+// ray origins (ray_gen.comp:340) are bit-identical to the reference-as-compiled-here.  glam sums left to right; the two differ
+// in the last bit only.
 static inline V3 xform_point(const M4& M, V3 p) {
-    return V3(M.at(0, 0) * p.x + M.at(0, 1) * p.y + M.at(0, 2) * p.z + M.at(0, 3),
-              M.at(1, 0) * p.x + M.at(1, 1) * p.y + M.at(1, 2) * p.z + M.at(1, 3),
-              M.at(2, 0) * p.x + M.at(2, 1) * p.y + M.at(2, 2) * p.z + M.at(2, 3));
+    return V3((M.at(0, 0) * p.x + M.at(0, 1) * p.y) + (M.at(0, 2) * p.z + M.at(0, 3)),
+              (M.at(1, 0) * p.x + M.at(1, 1) * p.y) + (M.at(1, 2) * p.z + M.at(1, 3)),
+              (M.at(2, 0) * p.x + M.at(2, 1) * p.y) + (M.at(2, 2) * p.z + M.at(2, 3)));
 }
 static inline V3 xform_vec(const M4& M, V3 p) {
     return V3(M.at(0, 0) * p.x + M.at(0, 1) * p.y + M.at(0, 2) * p.z,

@@ -48,11 +48,19 @@ def t_tolerance(rays, t):
     return REL_T * np.abs(t) + ULPS_T * 2.0 ** -24 * scale / dlen
 
 
-def compare_hits(rays, gpu, ref, scene_lookup, label="", max_fraction=MAX_MISMATCH_FRACTION, oracle_artefacts=False):
+def mt_determinant(o, d, v0, v1, v2):
+    """float64 value of the determinant the reference compares with its epsilon (intersection.glsl:10-12): dot(edge1, cross(d, edge2))"""
+    return float(np.dot(v1 - v0, np.cross(d, v2 - v0)))
+
+
+def compare_hits(rays, gpu, ref, scene_lookup, label="", max_fraction=MAX_MISMATCH_FRACTION, oracle_artefacts=False, reference_epsilon=0.0):
     """max_fraction bounds the number of CLASSIFIED near-ties (unclassified ones are never allowed).  Authored assets
     with coplanar duplicated faces (pica) need a looser count bound than the synthetic scenes: every pixel looking at
     such a face pair is an exact-depth tie between two different triangles."""
     """scene_lookup(inst) -> (tris, 4x4 inverse matrix as float64 row-indexed) for the global instance id.
+    reference_epsilon > 0 (comparisons with hits produced by the reference's own intersection.glsl, which rejects triangles whose
+    Möller-Trumbore determinant is below 1e-4 in magnitude — small or grazing triangles): a product hit that is exact-valid, not
+    farther than the reference's, on a triangle whose float64 determinant is below that epsilon is explained by it.
     oracle_artefacts=True (stress tests on ill-conditioned inputs only): a hit the ORACLE reports whose float64-exact t lies outside
     the ray's (tmin, tmax) — its float32 Moller-Trumbore on a sliver triangle with the origin on the surface — explains a
     mismatch as well; the product's answer is then checked to be exact-valid (or a miss)."""
@@ -132,6 +140,13 @@ def compare_hits(rays, gpu, ref, scene_lookup, label="", max_fraction=MAX_MISMAT
         if not ok and oracle_artefacts and cand[1] is None and cand[0] is not None:
             # the oracle's float32 Moller-Trumbore missed a (sub-resolution) triangle that exact arithmetic says the ray hits
             ok = float(rays["tmin"][i]) < cand[0][0] < float(rays["tmax"][i]) and min(cand[0][1], cand[0][2], 1.0 - cand[0][1] - cand[0][2]) >= -EDGE_EPS
+        if not ok and reference_epsilon > 0.0 and cand[0] is not None:
+            tris, inv = scene_lookup(int(gpu[i]["inst"]))
+            det = mt_determinant(inv[:3, :3] @ o + inv[:3, 3], inv[:3, :3] @ d, *_tri_f64(tris, int(gpu[i]["prim"])))
+            tg, ug, vg = cand[0]
+            valid = float(rays["tmin"][i]) < tg < float(rays["tmax"][i]) and min(ug, vg, 1.0 - ug - vg) >= -EDGE_EPS
+            closer = cand[1] is None or tg <= cand[1][0] * (1.0 + REL_T)
+            ok = valid and closer and abs(det) < reference_epsilon * 1.001
         if not ok:
             unexplained.append((int(i), gpu[i], ref[i], cand))
     assert not unexplained, f"{label}: unexplained mismatches {unexplained[:3]}"

@@ -13,8 +13,7 @@ from tests import parity
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.fixture(scope="module")
-def emu():
+def load_emu():
     subprocess.check_call(["make", "-C", os.path.join(HERE, "hostemu"), "-s"])
     L = C.CDLL(os.path.join(HERE, "hostemu", "libemu.so"))
     L.emu_create.restype = C.c_void_p
@@ -28,6 +27,11 @@ def emu():
     L.emu_sah.argtypes = [C.c_void_p, C.c_uint32]
     L.emu_sah.restype = C.c_float
     return L
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return load_emu()
 
 
 class Emu:
