@@ -1,13 +1,20 @@
 // oracle/oracle.cpp — CPU restatement of the rfw-rs ray-casting / wavefront path-tracing path.
 //
-// *** TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED. ***
+// *** TEST INFRASTRUCTURE ONLY. ***
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
 // this library; the product (rfw_rs_b200/csrc, librfwb200.so) never includes, links or calls it.
-// "Parity unpinned": the reference ships no golden vectors, known-answer tests or fixtures for this
-// path and cannot be built here (no Rust toolchain; the BVH arithmetic lives in
-// the un-vendored crates.io dependency `rtbvh = "0.6"`, crates/rfw-backend/Cargo.toml:17).  The
-// oracle is therefore pinned only against analytic known-answer cases and against its own brute
-// force (tests/test_oracle.py).
+//
+// How it is pinned.  The reference ships no golden vectors or known-answer tests for this path and
+// its Rust host side cannot be built here (no toolchain; the BVH builder lives in the un-vendored crates.io dependency
+// `rtbvh = "0.6"`, crates/rfw-backend/Cargo.toml:17).  But the path's ARITHMETIC is the reference's GLSL, and that
+// compiles: oracle/_ref/libref_glsl.so is backends/gpu-rt/shaders/{intersection,disney,lambert,utils,random,structs}.glsl
+// and the kernels {ray_gen,ray_extend,shade,ray_shadow,blit}.comp built for the host where they lie against the glm the
+// reference vendors (recipe oracle/ref_glsl/Makefile).  tests/test_ref_glsl.py holds this file against it: triangle test,
+// node tests, BLAS/TLAS traversal loops (hits bit-identical), BSDF / light sampling / RNG / camera (bit-identical up to
+// libm calls), whole frames under the reference's host loop (equal to rounding, identical ray counts); golden vectors made
+// from it (tests/golden/ref_glsl_golden.npz) repeat the checks where /root/reference is absent (tests/test_ref_golden.py).
+// NOT pinned by reference code: the BVH *builder* (rtbvh; restated as textbook binned SAH — topology does not change
+// closest hits except at exact ties) and glam's Mat4 inverse (cofactor expansion, evaluated in double here).
 //
 // What is restated, and from where (paths relative to /root/reference):
 //   triangle test        backends/gpu-rt/shaders/intersection.glsl:1-38 (closest), :40-70 (any-hit);

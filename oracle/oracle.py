@@ -1,6 +1,6 @@
 """ctypes front-end of the CPU oracle (oracle/liboracle.so).
 
-TEST INFRASTRUCTURE ONLY — PARITY UNPINNED (see the header of oracle.cpp).  May be imported only by
+TEST INFRASTRUCTURE ONLY (pinned against the reference's own shader sources: see the header of oracle.cpp).  May be imported only by
 tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs; nothing under
 rfw_rs_b200/ imports it.  Exposes the same method names as the backend boundary
 (crates/rfw-backend/src/lib.rs:35-82) so a scene description can be replayed on both.
