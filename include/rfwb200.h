@@ -256,7 +256,7 @@ typedef struct RfwB200Config {
     float clamp_value;       /* per-contribution clamp (reference: 10.0, backends/gpu-rt/src/lib.rs:205) */
     uint32_t tile_size;      /* multi-GPU tile edge in pixels (0 = 64) */
     uint32_t rank, world;    /* this process renders tiles with morton_rank(tile) % world == rank */
-    float sky[3];            /* constant sky radiance used until set_skybox is implemented */
+    float sky[3];            /* constant sky radiance of a miss while no skybox is set (rfwb200_set_skybox) */
     uint32_t reserved[8];
 } RfwB200Config;
 
@@ -272,6 +272,8 @@ typedef struct RfwBuildStats {
     float upload_ms;
     float sah_cost;                /* SAH cost of the largest BLAS after collapse */
     uint64_t checksum;             /* order-independent checksum of node+triangle buffers */
+    uint32_t tlas_depth;           /* levels of the 8-wide TLAS (0: single-level scene) and of the deepest BLAS: what the per-ray */
+    uint32_t blas_depth;           /* traversal stack (36 entries) must hold; synchronize() fails with RFWB200_ERR_STACK beyond it */
 } RfwBuildStats;
 
 typedef struct RfwTraceStats {
@@ -281,6 +283,8 @@ typedef struct RfwTraceStats {
     uint64_t instances_entered;
     float kernel_ms;               /* device time of the last trace call's kernel(s) */
     float total_ms;                /* incl. copies for the host-buffer entry points */
+    uint32_t stack_overflows;      /* != 0: a traversal-stack push was dropped in the last call (it then returns RFWB200_ERR_STACK) */
+    uint32_t reserved;
 } RfwTraceStats;
 
 typedef struct RfwRenderStats {
@@ -294,7 +298,7 @@ typedef struct RfwRenderStats {
      * would sit between launches of the timed loop). */
     float stage_ms[5];
     uint32_t stage_timing;
-    uint32_t reserved;
+    uint32_t stack_overflows;      /* != 0: a traversal-stack push was dropped during the last render_spp (it returns RFWB200_ERR_STACK) */
 } RfwRenderStats;
 
 enum {
@@ -302,7 +306,9 @@ enum {
     RFWB200_ERR_NO_DEVICE = -1,
     RFWB200_ERR_CUDA = -2,
     RFWB200_ERR_INVALID = -3,
-    RFWB200_ERR_OOM = -4
+    RFWB200_ERR_OOM = -4,
+    RFWB200_ERR_STACK = -5  /* the acceleration structure is deeper than the per-ray traversal stack: rejected at synchronize(), or
+                               (should the bound ever be wrong) detected by the kernels — results of that call are not to be used */
 };
 
 /* ------------------------------------------------------------------------------------------

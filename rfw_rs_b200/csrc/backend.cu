@@ -85,6 +85,8 @@ int Backend::init() {
     }
     BK_CUDA(cudaMalloc(&d_counter, 64), "counter");
     BK_CUDA(cudaMalloc(&d_counters3, 64), "counters");
+    BK_CUDA(cudaMalloc(&d_overflow, 4), "overflow flag");
+    BK_CUDA(cudaMemset(d_overflow, 0, 4), "overflow flag");
     bctx.stream = stream;
     bctx.sm_count = sm_count;
     tcfg.stream = stream;
@@ -107,6 +109,7 @@ Backend::~Backend() {
     for (auto& m : meshes) {
         if (m.d_tris) cudaFree(m.d_tris);
         if (m.d_ttris) cudaFree(m.d_ttris);
+        if (m.d_skin) cudaFree(m.d_skin);
         m.bvh.release();
     }
     tlas.release();
@@ -124,6 +127,7 @@ Backend::~Backend() {
     if (h_stream_marks) cudaFreeHost(h_stream_marks);
     if (d_counter) cudaFree(d_counter);
     if (d_counters3) cudaFree(d_counters3);
+    if (d_overflow) cudaFree(d_overflow);
     for (auto ev : chunk_events) cudaEventDestroy(ev);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -137,6 +141,7 @@ Backend::~Backend() {
 int Backend::set_3d_mesh(uint32_t id, const RfwMeshData3D* data) {
     if (!data) return fail(RFWB200_ERR_INVALID, "set_3d_mesh: null data");
     if (data->num_triangles && !data->triangles) return fail(RFWB200_ERR_INVALID, "set_3d_mesh: null triangles");
+    if (id >= MAX_MESH_SLOTS) return fail(RFWB200_ERR_INVALID, "set_3d_mesh: mesh id " + std::to_string(id) + " beyond the supported " + std::to_string(MAX_MESH_SLOTS) + " slots");
     DeviceScope device_scope(cfg.device);
     BK_CUDA(device_scope.status, "cudaSetDevice");
     if (id >= meshes.size()) meshes.resize(id + 1);
@@ -166,6 +171,7 @@ int Backend::unload_3d_meshes(const uint32_t* ids, uint32_t num) {
     DeviceScope device_scope(cfg.device);
     BK_CUDA(device_scope.status, "cudaSetDevice");
     BK_CUDA(cudaStreamSynchronize(stream), "sync");
+    if (num && !ids) return fail(RFWB200_ERR_INVALID, "unload_3d_meshes: null ids");
     for (uint32_t i = 0; i < num; i++) {
         const uint32_t id = ids[i];
         if (id >= meshes.size()) continue;
@@ -185,6 +191,7 @@ int Backend::unload_3d_meshes(const uint32_t* ids, uint32_t num) {
 int Backend::set_3d_instances(uint32_t mesh, const RfwInstancesData3D* data) {
     if (!data) return fail(RFWB200_ERR_INVALID, "set_3d_instances: null data");
     if (data->num_instances && !data->matrices) return fail(RFWB200_ERR_INVALID, "set_3d_instances: null matrices");
+    if (mesh >= MAX_MESH_SLOTS) return fail(RFWB200_ERR_INVALID, "set_3d_instances: mesh id beyond the supported slots");
     if (mesh >= inst_lists.size()) inst_lists.resize(mesh + 1);
     InstanceList& l = inst_lists[mesh];
     l.present = true;
@@ -219,6 +226,7 @@ int Backend::set_skins(const RfwSkinData* sk, uint32_t num, const uint32_t* chan
 }
 
 int Backend::set_materials(const RfwDeviceMaterial* m, uint32_t num) {
+    if (num && !m) return fail(RFWB200_ERR_INVALID, "set_materials: null slice");
     materials.assign(m, m + num);
     shading_dirty = true;
     synchronized = false;
@@ -287,10 +295,10 @@ int Backend::set_skybox(const RfwTextureData* t) {
     return RFWB200_OK;
 }
 
-int Backend::set_area_lights(const RfwAreaLight* l, uint32_t num) { area_lights.assign(l, l + num); shading_dirty = true; synchronized = false; return RFWB200_OK; }
-int Backend::set_point_lights(const RfwPointLight* l, uint32_t num) { point_lights.assign(l, l + num); shading_dirty = true; synchronized = false; return RFWB200_OK; }
-int Backend::set_spot_lights(const RfwSpotLight* l, uint32_t num) { spot_lights.assign(l, l + num); shading_dirty = true; synchronized = false; return RFWB200_OK; }
-int Backend::set_directional_lights(const RfwDirectionalLight* l, uint32_t num) { dir_lights.assign(l, l + num); shading_dirty = true; synchronized = false; return RFWB200_OK; }
+int Backend::set_area_lights(const RfwAreaLight* l, uint32_t num) { if (num && !l) return fail(RFWB200_ERR_INVALID, "set_area_lights: null slice"); area_lights.assign(l, l + num); shading_dirty = true; synchronized = false; return RFWB200_OK; }
+int Backend::set_point_lights(const RfwPointLight* l, uint32_t num) { if (num && !l) return fail(RFWB200_ERR_INVALID, "set_point_lights: null slice"); point_lights.assign(l, l + num); shading_dirty = true; synchronized = false; return RFWB200_OK; }
+int Backend::set_spot_lights(const RfwSpotLight* l, uint32_t num) { if (num && !l) return fail(RFWB200_ERR_INVALID, "set_spot_lights: null slice"); spot_lights.assign(l, l + num); shading_dirty = true; synchronized = false; return RFWB200_OK; }
+int Backend::set_directional_lights(const RfwDirectionalLight* l, uint32_t num) { if (num && !l) return fail(RFWB200_ERR_INVALID, "set_directional_lights: null slice"); dir_lights.assign(l, l + num); shading_dirty = true; synchronized = false; return RFWB200_OK; }
 
 // ---- synchronize -----------------------------------------------------------------------------------
 // ---- instance records on the device (reference: the host-side flatten of backends/gpu-rt/src/lib.rs:1571-1632) ------
@@ -614,6 +622,19 @@ int Backend::synchronize() {
         sv.two_level = live > 1 ? 1 : 0;
         sv.single_identity = single_identity ? 1 : 0;
         sv.num_live = (int)live;
+        sv.overflow = d_overflow;
+        {   // the per-ray traversal stack bounds the depth of what can be traced (trace_kernel.cuh)
+            uint32_t blas_depth = 0;
+            for (const MeshRec& m : meshes) if (m.present && m.n) blas_depth = std::max(blas_depth, m.bvh.depth);
+            for (const SkinnedInstance& si : skinned) blas_depth = std::max(blas_depth, si.bvh.depth);
+            // per TLAS level one continuation (the visited node's remaining siblings) + the leaf group and node group parked at
+            // the instance entry; per BLAS level one continuation; + 1 of margin
+            const uint32_t need = (live > 1 ? tlas.depth + 1 : 0) + blas_depth + 1;
+            build_stats_depth[0] = tlas.depth; build_stats_depth[1] = blas_depth;
+            if (need > (uint32_t)TRAVERSAL_STACK_ENTRIES)
+                return fail(RFWB200_ERR_STACK, "synchronize: acceleration structure too deep for the traversal stack (TLAS depth " + std::to_string(tlas.depth) + ", BLAS depth " +
+                                                   std::to_string(blas_depth) + ": " + std::to_string(need) + " entries needed, " + std::to_string(TRAVERSAL_STACK_ENTRIES) + " available)");
+        }
         update_l2_policy();
         BK_CUDA(cudaEventRecord(ev1, stream), "event");
         BK_CUDA(cudaEventSynchronize(ev1), "TLAS build");
@@ -635,6 +656,8 @@ int Backend::synchronize() {
         build_stats.bvh_bytes += (uint64_t)tlas.num_nodes * NODE_BYTES;
         build_stats.blas_build_ms = blas_ms;
         build_stats.tlas_build_ms = tlas_ms;
+        build_stats.tlas_depth = build_stats_depth[0];
+        build_stats.blas_depth = build_stats_depth[1];
         scene_dirty = false;
         shading_dirty = true;  // instance shading table changed
     }
@@ -710,6 +733,18 @@ int Backend::read_build_stats(RfwBuildStats* out) {
     return RFWB200_OK;
 }
 
+// The traversal kernels set *d_overflow when a push found the per-ray stack full.  synchronize() rejects trees that could do
+// that, so this is a second line of defence: a call that waited for its kernels reads the flag, clears it, and fails loudly.
+int Backend::check_stack_overflow(const char* who, uint32_t* out_flag) {
+    uint32_t f = 0;
+    BK_CUDA(cudaMemcpyAsync(&f, d_overflow, 4, cudaMemcpyDeviceToHost, stream), "overflow flag");
+    BK_CUDA(cudaStreamSynchronize(stream), "overflow flag");
+    if (out_flag) *out_flag = f;
+    if (f == 0) return RFWB200_OK;
+    BK_CUDA(cudaMemsetAsync(d_overflow, 0, 4, stream), "overflow flag");
+    return fail(RFWB200_ERR_STACK, std::string(who) + ": traversal stack overflow (a push was dropped; the results of this call are unreliable)");
+}
+
 int Backend::ensure_synchronized(const char* who) {
     if (!synchronized) return fail(RFWB200_ERR_INVALID, std::string(who) + ": scene changed since the last synchronize()");
     return RFWB200_OK;
@@ -745,6 +780,10 @@ int Backend::trace_closest_device(const RfwRay* d_r, uint64_t num, RfwHit* d_h, 
         // separates the cost of its bookkeeping from the effect of the concurrent PCIe traffic
         const uint32_t n = (uint32_t)num, warps = trace_streamed_warps(tcfg, sv, false, n);
         uint32_t* state = nullptr; uint32_t* hflags = nullptr; uint32_t* dflags = nullptr;
+        struct Scratch {  // freed on every exit path
+            uint32_t*& s; uint32_t*& h;
+            ~Scratch() { if (s) cudaFree(s); if (h) cudaFreeHost(h); }
+        } scratch{state, hflags};
         BK_CUDA(cudaMalloc(&state, (16 + (size_t)warps) * 4), "debug");
         BK_CUDA(cudaHostAlloc(&hflags, (16 + (size_t)warps) * 4, cudaHostAllocMapped), "debug");
         BK_CUDA(cudaHostGetDevicePointer(&dflags, hflags, 0), "debug");
@@ -756,7 +795,6 @@ int Backend::trace_closest_device(const RfwRay* d_r, uint64_t num, RfwHit* d_h, 
         BK_CUDA(cudaEventSynchronize(ev1), "trace_streamed");
         cudaEventElapsedTime(&trace_stats.kernel_ms, ev0, ev1);
         trace_stats.total_ms = trace_stats.kernel_ms; trace_stats.rays = num;
-        cudaFree(state); cudaFreeHost(hflags);
         launch_count++;
         return RFWB200_OK;
     }
@@ -778,6 +816,7 @@ int Backend::trace_closest_device(const RfwRay* d_r, uint64_t num, RfwHit* d_h, 
         cudaEventElapsedTime(&trace_stats.kernel_ms, ev0, ev1);
         trace_stats.total_ms = trace_stats.kernel_ms;
         trace_stats.rays = num;
+        return check_stack_overflow("trace_closest", &trace_stats.stack_overflows);
     }
     return RFWB200_OK;
 }
@@ -804,6 +843,7 @@ int Backend::trace_any_device(const RfwRay* d_r, uint64_t num, uint32_t* d_o, in
         cudaEventElapsedTime(&trace_stats.kernel_ms, ev0, ev1);
         trace_stats.total_ms = trace_stats.kernel_ms;
         trace_stats.rays = num;
+        return check_stack_overflow("trace_any", &trace_stats.stack_overflows);
     }
     return RFWB200_OK;
 }
@@ -824,8 +864,9 @@ int Backend::trace_closest_counted(const RfwRay* d_r, uint64_t num, RfwHit* d_h,
     trace_stats.rays = num; trace_stats.nodes_visited = c[0]; trace_stats.tris_tested = c[1]; trace_stats.instances_entered = c[2];
     cudaEventElapsedTime(&trace_stats.kernel_ms, ev0, ev1);
     trace_stats.total_ms = trace_stats.kernel_ms;
+    const int rc = check_stack_overflow("trace_closest_counted", &trace_stats.stack_overflows);
     if (out) *out = trace_stats;
-    return RFWB200_OK;
+    return rc;
 }
 
 // host buffers: chunked, the H2D copy of chunk c+1 and the D2H copy of chunk c-1 overlap the kernel of chunk c
@@ -940,8 +981,8 @@ int Backend::trace_host_streamed(bool any_hit, const RfwRay* rays, uint64_t num,
         if (d_stream_state) cudaFree(d_stream_state);
         if (h_stream_flags) cudaFreeHost(h_stream_flags);
         if (h_stream_marks) cudaFreeHost(h_stream_marks);
+        const uint32_t gcap = std::max(granules, stream_granules), wcap = std::max(warps, stream_warps);  // grow-only
         d_stream_state = nullptr; h_stream_flags = nullptr; h_stream_marks = nullptr; stream_granules = 0; stream_warps = 0;
-        const uint32_t gcap = std::max(granules, stream_granules), wcap = std::max(warps, stream_warps);
         BK_CUDA(cudaMalloc(&d_stream_state, (16 + (size_t)wcap) * sizeof(uint32_t)), "stream state");
         BK_CUDA(cudaHostAlloc(&h_stream_flags, (16 + (size_t)wcap) * sizeof(uint32_t), cudaHostAllocMapped), "stream flags");
         BK_CUDA(cudaHostAlloc(&h_stream_marks, (size_t)gcap * sizeof(uint32_t), cudaHostAllocDefault), "stream marks");
@@ -961,6 +1002,19 @@ int Backend::trace_host_streamed(bool any_hit, const RfwRay* rays, uint64_t num,
     BK_CUDA(cudaStreamWaitEvent(copy_in, chunk_events[0], 0), "event");  // the watermark is reset before the first chunk moves it
     if (!copy_poll) BK_CUDA(cudaStreamCreateWithFlags(&copy_poll, cudaStreamNonBlocking), "stream");
     BK_CUDA(cudaStreamWaitEvent(copy_poll, chunk_events[0], 0), "event");  // the first mirror copy must see the reset slots
+    // From here on the persistent kernel and the copies target the caller's pinned buffers: an error must not return
+    // while they are in flight.  STREAM_CK raises the abort flag (the kernel's waiting warps read it), drains the four
+    // streams and only then reports.
+#define STREAM_CK(x, what)                                                                         \
+    do {                                                                                           \
+        cudaError_t e_ = (x);                                                                      \
+        if (e_ != cudaSuccess) {                                                                   \
+            h_stream_flags[0] = 4u;                                                                \
+            cudaStreamSynchronize(copy_in); cudaStreamSynchronize(stream);                         \
+            cudaStreamSynchronize(copy_out); if (copy_poll) cudaStreamSynchronize(copy_poll);      \
+            return cuda_fail(e_, what);                                                            \
+        }                                                                                          \
+    } while (0)
     StreamSync ss{d_stream_state, d_stream_state + 16, d_flags, device_deadline_ns(10.0)};
     BK_CUDA(trace_streamed(tcfg, sv, any_hit, d_rays.ptr, n, any_hit ? nullptr : reinterpret_cast<RfwHit*>(d_out), any_hit ? reinterpret_cast<uint32_t*>(d_out) : nullptr, d_counter, ss),
             "trace_streamed");
@@ -980,8 +1034,8 @@ int Backend::trace_host_streamed(bool any_hit, const RfwRay* rays, uint64_t num,
             }
             const uint32_t last = std::min(granules, g + step) - 1;
             const uint64_t off = (uint64_t)g * G, cnt = h_stream_marks[last] - off;
-            BK_CUDA(cudaMemcpyAsync(d_rays.ptr + off, rays + off, cnt * sizeof(RfwRay), cudaMemcpyHostToDevice, copy_in), "ray upload");
-            BK_CUDA(cudaMemcpyAsync(d_stream_state, h_stream_marks + last, sizeof(uint32_t), cudaMemcpyHostToDevice, copy_in), "watermark");
+            STREAM_CK(cudaMemcpyAsync(d_rays.ptr + off, rays + off, cnt * sizeof(RfwRay), cudaMemcpyHostToDevice, copy_in), "ray upload");
+            STREAM_CK(cudaMemcpyAsync(d_stream_state, h_stream_marks + last, sizeof(uint32_t), cudaMemcpyHostToDevice, copy_in), "watermark");
             g = last + 1;
         }
     }
@@ -1003,8 +1057,8 @@ int Backend::trace_host_streamed(bool any_hit, const RfwRay* rays, uint64_t num,
     while (next < granules && !flags[0]) {
         if (poll_us > 0) { struct timespec ts = {0, poll_us * 1000L}; nanosleep(&ts, nullptr); }
         // mirror the warps' slots (19 KB for 4 736 warps) with a small D2H copy on its own stream
-        BK_CUDA(cudaMemcpyAsync(h_stream_flags + 16, d_stream_state + 16, (size_t)warps * sizeof(uint32_t), cudaMemcpyDeviceToHost, copy_poll), "progress mirror");
-        BK_CUDA(cudaStreamSynchronize(copy_poll), "progress mirror");
+        STREAM_CK(cudaMemcpyAsync(h_stream_flags + 16, d_stream_state + 16, (size_t)warps * sizeof(uint32_t), cudaMemcpyDeviceToHost, copy_poll), "progress mirror");
+        STREAM_CK(cudaStreamSynchronize(copy_poll), "progress mirror");
         uint32_t bound = 0xFFFFFFFFu;
         for (uint32_t w = 0; w < warps; w++) { const uint32_t v = flags[16 + w]; bound = v < bound ? v : bound; }
         uint32_t ready_to = next;
@@ -1012,14 +1066,14 @@ int Backend::trace_host_streamed(bool any_hit, const RfwRay* rays, uint64_t num,
         if (ready_to > next) {  // one copy for all newly completed granules
             const uint64_t off = (uint64_t)next * G, cnt = h_stream_marks[ready_to - 1] - off;
             if (trace) seen.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() * 1e3);
-            BK_CUDA(cudaMemcpyAsync(out + off, d_out + off, cnt * sizeof(OutT), cudaMemcpyDeviceToHost, copy_out), "hit download");
+            STREAM_CK(cudaMemcpyAsync(out + off, d_out + off, cnt * sizeof(OutT), cudaMemcpyDeviceToHost, copy_out), "hit download");
             next = ready_to;
             continue;
         }
         if ((++spins & 0xFu) == 0u) {
             if (cudaStreamQuery(stream) != cudaErrorNotReady) {  // kernel finished: one more mirror must show every warp done
-                BK_CUDA(cudaMemcpyAsync(h_stream_flags + 16, d_stream_state + 16, (size_t)warps * sizeof(uint32_t), cudaMemcpyDeviceToHost, copy_poll), "progress mirror");
-                BK_CUDA(cudaStreamSynchronize(copy_poll), "progress mirror");
+                STREAM_CK(cudaMemcpyAsync(h_stream_flags + 16, d_stream_state + 16, (size_t)warps * sizeof(uint32_t), cudaMemcpyDeviceToHost, copy_poll), "progress mirror");
+                STREAM_CK(cudaStreamSynchronize(copy_poll), "progress mirror");
                 bool all_done = true;
                 for (uint32_t w = 0; w < warps; w++) all_done = all_done && flags[16 + w] == 0xFFFFFFFFu;
                 if (!all_done) flags[0] = 2u;
@@ -1037,12 +1091,13 @@ int Backend::trace_host_streamed(bool any_hit, const RfwRay* rays, uint64_t num,
         fprintf(stderr, " (%zu copies)\n", seen.size());
         for (auto& e : tev) if (e) cudaEventDestroy(e);
     }
-    BK_CUDA(cudaStreamSynchronize(copy_in), "ray upload");
-    BK_CUDA(cudaStreamSynchronize(stream), "trace_streamed");
-    BK_CUDA(cudaStreamSynchronize(copy_out), "hit download");
+    STREAM_CK(cudaStreamSynchronize(copy_in), "ray upload");
+    STREAM_CK(cudaStreamSynchronize(stream), "trace_streamed");
+    STREAM_CK(cudaStreamSynchronize(copy_out), "hit download");
     if (flags[0]) return fail(RFWB200_ERR_CUDA, "streamed trace aborted (code " + std::to_string(flags[0]) + ": 1 = upload stalled, 2 = kernel ended early, 3 = host timeout)");
     used = true;
     return RFWB200_OK;
+#undef STREAM_CK
 }
 
 int Backend::trace_closest_host(const RfwRay* rays, uint64_t num, RfwHit* out) {
@@ -1063,7 +1118,7 @@ int Backend::trace_closest_host(const RfwRay* rays, uint64_t num, RfwHit* out) {
             BK_CUDA(cudaEventSynchronize(ev1), "trace_closest");
             cudaEventElapsedTime(&trace_stats.total_ms, ev0, ev1);
             trace_stats.rays = num;
-            return RFWB200_OK;
+            return check_stack_overflow("trace (host buffers)", &trace_stats.stack_overflows);
         }
     }
     uint64_t n_launch = 0;
@@ -1075,7 +1130,7 @@ int Backend::trace_closest_host(const RfwRay* rays, uint64_t num, RfwHit* out) {
     BK_CUDA(cudaEventSynchronize(ev1), "trace_closest");
     cudaEventElapsedTime(&trace_stats.total_ms, ev0, ev1);
     trace_stats.rays = num;
-    return RFWB200_OK;
+    return check_stack_overflow("trace (host buffers)", &trace_stats.stack_overflows);
 }
 
 int Backend::trace_any_host(const RfwRay* rays, uint64_t num, uint32_t* out) {
@@ -1096,7 +1151,7 @@ int Backend::trace_any_host(const RfwRay* rays, uint64_t num, uint32_t* out) {
             BK_CUDA(cudaEventSynchronize(ev1), "trace_any");
             cudaEventElapsedTime(&trace_stats.total_ms, ev0, ev1);
             trace_stats.rays = num;
-            return RFWB200_OK;
+            return check_stack_overflow("trace (host buffers)", &trace_stats.stack_overflows);
         }
     }
     uint64_t n_launch = 0;
@@ -1108,7 +1163,7 @@ int Backend::trace_any_host(const RfwRay* rays, uint64_t num, uint32_t* out) {
     BK_CUDA(cudaEventSynchronize(ev1), "trace_any");
     cudaEventElapsedTime(&trace_stats.total_ms, ev0, ev1);
     trace_stats.rays = num;
-    return RFWB200_OK;
+    return check_stack_overflow("trace (host buffers)", &trace_stats.stack_overflows);
 }
 
 int Backend::cast_primary(const RfwCameraView3D* view, RfwHit* out_hits) {
@@ -1130,7 +1185,7 @@ int Backend::cast_primary(const RfwCameraView3D* view, RfwHit* out_hits) {
     cudaEventElapsedTime(&trace_stats.kernel_ms, ev0, ev1);
     trace_stats.total_ms = trace_stats.kernel_ms;
     trace_stats.rays = n;
-    return RFWB200_OK;
+    return check_stack_overflow("cast_primary", &trace_stats.stack_overflows);
 }
 
 // ---- rendering ---------------------------------------------------------------------------------------------
@@ -1169,7 +1224,7 @@ int Backend::render_spp(const RfwCameraView3D* view, uint32_t spp, uint32_t dept
     render_stats.segments = st[2];
     render_stats.stage_timing = wf.stage_timing ? 1u : 0u;
     BK_CUDA(wf.stage_times(render_stats.stage_ms), "stage times");
-    return RFWB200_OK;
+    return check_stack_overflow("render", &render_stats.stack_overflows);
 }
 
 ShadeScene Backend::shade_scene() const {

@@ -128,6 +128,8 @@ private:
     bool l2_persist_enabled = false;  // option "l2_persist": measured no effect on C2 (the 16 MB of nodes stay resident anyway), off by default
 
     RfwB200Config cfg;
+    uint32_t build_stats_depth[2] = {0, 0};  // TLAS depth, deepest BLAS (wide-tree levels) of the last synchronize()
+    static constexpr uint32_t MAX_MESH_SLOTS = 1u << 24;  // mesh ids are slot indices (collections.rs:87-107); anything beyond is a caller bug, not a 64 GB table
     int sm_count = 148;
     cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr, copy_poll = nullptr;
     BuilderContext bctx;
@@ -186,6 +188,8 @@ private:
     DeviceArray<RfwHit> d_hits;
     DeviceArray<uint32_t> d_occ;
     uint32_t* d_counter = nullptr;          // work counter of the persistent kernels
+    uint32_t* d_overflow = nullptr;         // SceneView::overflow: set by a traversal kernel whose stack was full
+    int check_stack_overflow(const char* who, uint32_t* out_flag);  // reads + clears the flag (the stream must be idle)
     unsigned long long* d_counters3 = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> chunk_events;

@@ -400,8 +400,10 @@ __global__ void __launch_bounds__(128) k_collapse_all(BuildArrays A, CollapseOut
     grid.sync();
     uint32_t count = 1;
     int ping = 0;
+    uint32_t levels = 0;
     int2 *qin = q0, *qout = q1;
     while (count > 0) {
+        levels++;
         uint32_t* next = counters + 2 + ping;
         for (uint32_t t = tid; t < count; t += n_threads) collapse_body(qin[t], A, O, qout, next);
         __threadfence();
@@ -413,6 +415,7 @@ __global__ void __launch_bounds__(128) k_collapse_all(BuildArrays A, CollapseOut
         int2* t = qin; qin = qout; qout = t;
         ping ^= 1;
     }
+    if (tid == 0) counters[5] = levels;  // depth of the wide tree (counters[5] was the SAH top build's node counter, done by now)
 }
 
 __global__ void __launch_bounds__(TB) k_gather_tris(const RfwRTTriangle* __restrict__ tris, const uint32_t* __restrict__ leaf_prims, int n, float4* __restrict__ out) {
@@ -537,6 +540,7 @@ static cudaError_t apply_build_result(const BuildResultSlot& r, int n, bool refi
     out.num_nodes = r.counters[0];
     out.num_prims = r.counters[1];
     out.num_treelets = r.counters[4];
+    out.depth = r.counters[5];
     if (out.num_prims != (uint32_t)n) {
         fprintf(stderr, "rfwb200: collapse emitted %u leaf slots for %d primitives\n", out.num_prims, n);
         return cudaErrorUnknown;

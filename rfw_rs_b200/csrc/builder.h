@@ -22,6 +22,7 @@ struct DeviceBvh {
     uint32_t num_nodes = 0;
     uint32_t num_prims = 0;
     uint32_t num_treelets = 0;      // items of the SAH top build (0 = plain LBVH)
+    uint32_t depth = 0;             // levels of the wide tree (root = 1): what bounds the traversal stack (trace_kernel.cuh)
     float sah = 0.0f;
     float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};  // bounds of all primitive boxes
     void release();

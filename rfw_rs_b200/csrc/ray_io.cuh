@@ -80,6 +80,7 @@ struct StreamedRayIO {
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
 #endif
             if (now > deadline_ns) { *(volatile uint32_t*)abort_flag = 1u; give_up = true; }
+            else if (*(volatile uint32_t*)abort_flag != 0u) give_up = true;  // the host gave up (error on its side): stop waiting for rays that will not come
         }
         return __shfl_sync(FULL, give_up, 0);
     }

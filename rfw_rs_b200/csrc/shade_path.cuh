@@ -89,7 +89,9 @@ __device__ __forceinline__ void shade_path(const FrameParams& fp, const ShadeSce
         const float4* tp = reinterpret_cast<const float4*>(is->tris + prim);
         const float4 q3 = __ldg(tp + 3), q4 = __ldg(tp + 4), q5 = __ldg(tp + 5), q6 = __ldg(tp + 6);  // normal|v0, n0|v1, n1|v2, n2|id
         const float4 q7 = __ldg(tp + 7), q8 = __ldg(tp + 8), q9 = __ldg(tp + 9), q10 = __ldg(tp + 10);  // T0, T1, T2, light_id|mat_id|lod|area
-        const int mat_id = __float_as_int(q10.y);
+        // an id outside the material list (a mesh uploaded before its materials) reads material 0 instead of faulting: the
+        // reference's storage buffers are bounds-checked (robust buffer access), an illegal address here would poison the context
+        const int mat_id = (uint32_t)__float_as_int(q10.y) < ss.n_materials ? __float_as_int(q10.y) : 0;
         const float tri_area = q10.w;
         ShadingData sd = extract_material(ss.materials + mat_id);
         const uint32_t mflags = __ldg(&ss.materials[mat_id].flags);
@@ -202,7 +204,7 @@ __device__ __forceinline__ float4 debug_view_value(const FrameParams& fp, const 
         const float4* tp = reinterpret_cast<const float4*>(is->tris + prim);
         const float4 q0 = __ldg(tp + 0), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2), q3 = __ldg(tp + 3), q4 = __ldg(tp + 4), q5 = __ldg(tp + 5), q6 = __ldg(tp + 6);
         const float4 q7 = __ldg(tp + 7), q8 = __ldg(tp + 8), q9 = __ldg(tp + 9), q10 = __ldg(tp + 10);
-        const int mat_id = __float_as_int(q10.y);
+        const int mat_id = (uint32_t)__float_as_int(q10.y) < ss.n_materials ? __float_as_int(q10.y) : 0;  // (as in shade_path)
         const uint32_t bary = __float_as_uint(s4.w);
         const float u = (float)(bary & 65535u) * (1.0f / 65535.0f), v = (float)(bary >> 16) * (1.0f / 65535.0f), w = 1.0f - u - v;
         const float3 Dv = xyz(d4);

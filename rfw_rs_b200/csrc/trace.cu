@@ -78,9 +78,23 @@ static cudaError_t launch_persistent_dispatch(const TraceConfig& cfg, const Scen
     }
 }
 
+// trace_variant 3 (tests only): the same kernel with a 2 + 2 entry stack, which any non-trivial tree overflows — shows that the
+// overflow is reported (RfwTraceStats::stack_overflows, RFWB200_ERR_STACK) instead of returning silently wrong hits
+template <bool ANY, bool TWO_LEVEL>
+static cudaError_t launch_persistent_tiny_stack(const TraceConfig& cfg, const SceneView& sv, const RayBufferIO& io, uint32_t n, uint32_t* counter) {
+    const TraceTuning tune{cfg.refill_below, TWO_LEVEL ? cfg.tri_batch_two_level : cfg.tri_batch, cfg.tri_blocked, cfg.inst_batch};
+    auto kern = k_trace_persistent<RayBufferIO, ANY, TWO_LEVEL, PT_THREADS, 4, 2, 2>;
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), cfg.stream);
+    if (e != cudaSuccess) return e;
+    const int grid = (int)std::max<uint32_t>(1u, std::min<uint32_t>((n + PT_THREADS - 1) / PT_THREADS, (uint32_t)cfg.sm_count * 4u));
+    kern<<<grid, PT_THREADS, persistent_smem_bytes<TWO_LEVEL>(), cfg.stream>>>(sv, io, counter, tune);
+    return cudaGetLastError();
+}
+
 template <bool ANY, bool TWO_LEVEL>
 static cudaError_t launch_persistent(const TraceConfig& cfg, const SceneView& sv, const float4* rays, uint32_t n, RfwHit* hits, uint32_t* occ, uint32_t* counter) {
     RayBufferIO io{rays, n, hits, occ};
+    if (cfg.variant == TRACE_VARIANT_TINY_STACK) return launch_persistent_tiny_stack<ANY, TWO_LEVEL>(cfg, sv, io, n, counter);
     return launch_persistent_dispatch<ANY, TWO_LEVEL>(cfg, sv, io, n, counter);
 }
 

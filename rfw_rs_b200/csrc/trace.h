@@ -8,7 +8,7 @@
 
 namespace rfw {
 
-enum { TRACE_VARIANT_PERSISTENT = 0, TRACE_VARIANT_SIMPLE = 1 };
+enum { TRACE_VARIANT_PERSISTENT = 0, TRACE_VARIANT_SIMPLE = 1, TRACE_VARIANT_STREAMED_RESIDENT = 2, TRACE_VARIANT_TINY_STACK = 3 };
 
 struct TraceConfig {
     cudaStream_t stream = nullptr;

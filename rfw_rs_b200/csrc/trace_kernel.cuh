@@ -31,10 +31,7 @@ namespace rfw {
 
 static constexpr uint32_t FULL = 0xFFFFFFFFu;
 static constexpr int PT_THREADS = 128;
-#ifndef RFW_PT_SM_STACK
-#define RFW_PT_SM_STACK 12
-#endif
-static constexpr int PT_SM_STACK = RFW_PT_SM_STACK;
+static constexpr int PT_SM_STACK = RFW_PT_SM_STACK;  // (traverse.h)
 // Leaf groups a lane may set aside while it keeps traversing (speculative traversal, single-level kernels).  MEASURED AND
 // SWITCHED OFF (0): on C2 every setting lost to the non-speculative kernel (best 1 494 vs 1 557 Mrays/s; 1 229 with deep
 // speculation) — 82 % of the rays hit something, and walking on with a stale (too long) hit distance visits far more
@@ -72,7 +69,7 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
     return v;
 }
 #endif
-static constexpr int PT_L_STACK = 24;
+static constexpr int PT_L_STACK = RFW_PT_L_STACK;
 // Two-level kernels keep the WORLD-space ray of every lane in shared memory (3 x float4 [vector][thread]: origin,
 // direction, reciprocal direction, octant word) instead of six live registers: it is needed only when a lane enters an
 // instance (object-space transform) and when it leaves one — where the three loads also replace re-deriving the slab
@@ -85,14 +82,15 @@ constexpr size_t persistent_smem_bytes() {
 #define RFW_STACK_PUSH(v)                                                                   \
     do {                                                                                    \
         if (sp < SM_STACK) sts_u2(st_base + (uint32_t)sp * (uint32_t)(THREADS * 8), (v));  \
-        else if (sp - SM_STACK < PT_L_STACK) lstack[sp - SM_STACK] = (v);                   \
+        else if (sp - SM_STACK < L_STACK) lstack[sp - SM_STACK] = (v);                      \
+        else note_stack_overflow(sv); /* entry dropped: reported, never silent */           \
         sp++;                                                                               \
     } while (0)
 #define RFW_STACK_POP(dst)                                                                          \
     do {                                                                                            \
         sp--;                                                                                       \
         if (sp < SM_STACK) (dst) = lds_u2(st_base + (uint32_t)sp * (uint32_t)(THREADS * 8));       \
-        else (dst) = lstack[(sp - SM_STACK) < PT_L_STACK ? (sp - SM_STACK) : (PT_L_STACK - 1)];     \
+        else (dst) = lstack[(sp - SM_STACK) < L_STACK ? (sp - SM_STACK) : (L_STACK - 1)];           \
     } while (0)
 
 struct TraceTuning {
@@ -102,7 +100,12 @@ struct TraceTuning {
     int inst_batch;    // two-level kernels: enter TLAS leaves (instances) when at least this many lanes wait at one
 };
 
-template <class IO, bool ANY, bool TWO_LEVEL, int THREADS, int MIN_BLOCKS, int SM_STACK>
+// SM_STACK + L_STACK entries per ray: 12 in shared memory + 24 in local memory by default.  A wide tree of depth d needs at most d
+// entries per level of the hierarchy (one continuation per ancestor) plus two per TLAS level in the two-level kernels; the
+// builder reports d (DeviceBvh::depth) and Backend::synchronize refuses scenes that could exceed the stack.  Pushes beyond it
+// are dropped AND flagged (SceneView::overflow).  L_STACK is a template parameter so that a test can build a 2 + 2 entry
+// variant that overflows on any scene (option trace_variant 3).
+template <class IO, bool ANY, bool TWO_LEVEL, int THREADS, int MIN_BLOCKS, int SM_STACK, int L_STACK = PT_L_STACK>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneView sv, IO io, uint32_t* __restrict__ counter, TraceTuning tune) {
 #if defined(RFW_HOST_SIMT)
     uint2* const smem_stack = reinterpret_cast<uint2*>(rfw_host_smem);  // (the host SIMT harness: shared memory is a byte array)
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
     const uint32_t lanemask_lt = (1u << lane) - 1u;
 
     const uint32_t st_base = (uint32_t)__cvta_generic_to_shared(smem_stack) + threadIdx.x * 8u;
-    uint2 lstack[PT_L_STACK];
+    uint2 lstack[L_STACK];
     int sp = 0;
 
     bool active = false;

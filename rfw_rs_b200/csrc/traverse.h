@@ -25,6 +25,16 @@
 
 namespace rfw {
 
+// Entries of the per-ray traversal stack of the persistent kernels: RFW_PT_SM_STACK in shared memory + RFW_PT_L_STACK in local
+// memory (trace_kernel.cuh).  Host-visible because Backend::synchronize checks the depth of what it built against it.
+#ifndef RFW_PT_SM_STACK
+#define RFW_PT_SM_STACK 12
+#endif
+#ifndef RFW_PT_L_STACK
+#define RFW_PT_L_STACK 24
+#endif
+static constexpr int TRAVERSAL_STACK_ENTRIES = RFW_PT_SM_STACK + RFW_PT_L_STACK;
+
 // meshes of up to this many triangles are entered without a node visit (InstanceRec::direct_tris)
 #ifndef RFW_DIRECT_TRIS
 #define RFW_DIRECT_TRIS 4
@@ -56,7 +66,14 @@ struct SceneView {
     int two_level;                  // 0: exactly one live instance, traced directly
     int single_identity;            // single instance has an identity transform
     int num_live;
+    uint32_t* overflow;             // one word the traversal kernels set when a push finds the per-ray stack full (the entry is
+                                    // dropped, the ray's result is then unreliable): checked by the host after every launch it waits for
 };
+
+// a traversal-stack push that does not fit (cold path)
+RFW_HD void note_stack_overflow(const SceneView& sv) {
+    if (sv.overflow) *sv.overflow = 1u;
+}
 
 struct TraceCounters {
     unsigned long long nodes, tris, instances;
@@ -313,7 +330,7 @@ RFW_HD bool trace_ray(const SceneView& sv, const float3 o, const float3 d, const
             const int bit = bfind32(hits_imask);
             const uint32_t base = ng.x;
             ng.y &= ~(1u << bit);
-            if (RFW_NODE_HITS(ng)) { if (sp < STACK) stack[sp++] = ng; }
+            if (RFW_NODE_HITS(ng)) { if (sp < STACK) stack[sp++] = ng; else note_stack_overflow(sv); }
             const uint32_t slot = (uint32_t)(bit - 24) ^ (rc.octinv4 & 7u);
             const uint32_t rel = popc32(hits_imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
             const float4* np = nodes + (size_t)(base + rel) * NODE_F4;
@@ -349,8 +366,8 @@ RFW_HD bool trace_ray(const SceneView& sv, const float3 o, const float3 d, const
                 // TLAS leaf: enter the instance; the TLAS continuation goes on the stack below the BLAS part
                 const InstanceRec& rec = sv.instances[ldg(sv.tlas_refs + idx)];
                 if (COUNT) ctr->instances++;
-                if (tg.y != 0u) { if (sp < STACK) stack[sp++] = tg; }
-                if (RFW_NODE_HITS(ng)) { if (sp < STACK) stack[sp++] = ng; }
+                if (tg.y != 0u) { if (sp < STACK) stack[sp++] = tg; else note_stack_overflow(sv); }
+                if (RFW_NODE_HITS(ng)) { if (sp < STACK) stack[sp++] = ng; else note_stack_overflow(sv); }
                 blas_base_sp = sp;
                 in_blas = true;
                 cur_inst = rec.inst_id;

@@ -112,20 +112,20 @@ class CBuildStats(C.Structure):
     _fields_ = [
         ("num_meshes", C.c_uint32), ("num_instances", C.c_uint32), ("num_triangles", C.c_uint64), ("blas_nodes", C.c_uint64),
         ("tlas_nodes", C.c_uint64), ("bvh_bytes", C.c_uint64), ("blas_build_ms", C.c_float), ("tlas_build_ms", C.c_float),
-        ("upload_ms", C.c_float), ("sah_cost", C.c_float), ("checksum", C.c_uint64),
+        ("upload_ms", C.c_float), ("sah_cost", C.c_float), ("checksum", C.c_uint64), ("tlas_depth", C.c_uint32), ("blas_depth", C.c_uint32),
     ]
 
 
 class CTraceStats(C.Structure):
     _fields_ = [
         ("rays", C.c_uint64), ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("instances_entered", C.c_uint64),
-        ("kernel_ms", C.c_float), ("total_ms", C.c_float),
+        ("kernel_ms", C.c_float), ("total_ms", C.c_float), ("stack_overflows", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 
 class CRenderStats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("extension_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("segments", C.c_uint64), ("render_ms", C.c_float),
-                ("stage_ms", C.c_float * 5), ("stage_timing", C.c_uint32), ("reserved", C.c_uint32)]
+                ("stage_ms", C.c_float * 5), ("stage_timing", C.c_uint32), ("stack_overflows", C.c_uint32)]
 
 
 def stats_to_dict(s):

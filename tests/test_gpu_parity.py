@@ -116,6 +116,62 @@ def test_non_finite_rays_retire_as_misses(B, oracle_mod, torch_cuda):
 
 
 @pytest.mark.parametrize("two_level", [False, True])
+def test_traversal_stack_overflow_is_reported_never_silent(B, oracle_mod, two_level):
+    """The per-ray traversal stack holds 12 + 24 entries.  (1) synchronize() reports the depth of what it built and every
+    config's trees fit with a wide margin; (2) a build of the same kernel with a 2 + 2 entry stack (option trace_variant 3)
+    overflows on any real tree: the call must fail with RFWB200_ERR_STACK and say so in the stats — a dropped push is never
+    silent; (3) the next call with the production kernel is clean again (the flag is cleared when it is reported)."""
+    desc = scenes.instanced_scene(grid=8, subdiv=2, n_lights=4) if two_level else scenes.soup_scene(50000, 0.02)
+    gpu, cpu = make_pair(B, oracle_mod, desc)
+    bs = gpu.build_stats()
+    assert 1 <= bs["blas_depth"] <= 12 and (bs["tlas_depth"] >= 1) == two_level
+    assert (bs["tlas_depth"] + 1 if two_level else 0) + bs["blas_depth"] + 1 <= 36
+    rays = scenes.random_rays(40000, lo=-4.0, hi=4.0) if two_level else scenes.random_rays(40000)
+    hits = gpu.trace_closest(rays)
+    assert gpu.trace_stats()["stack_overflows"] == 0
+    gpu.set_option("trace_variant", 3)
+    gpu.set_option("streamed", 0)
+    with pytest.raises(B.RfwError, match="stack overflow"):
+        gpu.trace_closest(rays)
+    assert gpu.trace_stats()["stack_overflows"] != 0
+    gpu.set_option("trace_variant", 0)
+    again = gpu.trace_closest(rays)
+    assert gpu.trace_stats()["stack_overflows"] == 0 and np.array_equal(again["prim"], hits["prim"]) and np.array_equal(again["t"], hits["t"])
+
+
+def test_out_of_range_material_and_mesh_ids_do_not_fault(B):
+    """A triangle whose mat_id lies outside the material list reads material 0 (the reference's storage buffers are
+    bounds-checked; an illegal address here would poison the CUDA context of the whole process); absurd mesh ids and null
+    slices are refused with an error instead of being dereferenced."""
+    desc = scenes.instanced_scene(grid=3, subdiv=1, n_lights=2)
+    w, h = 64, 36
+    view = scenes.camera_view((0, 3.0, -7.0), (0, -0.4, 1.0), w, h)
+    gpu = B.B200Backend(w, h); desc.apply(gpu)
+    gpu.render_spp(view, 2, 3)
+    good = gpu.read_accumulator()
+    import copy
+
+    bad = copy.copy(desc)
+    bad.meshes = {k: v.copy() for k, v in desc.meshes.items()}
+    first = sorted(bad.meshes)[0]
+    bad.meshes[first]["mat_id"][::2] = 1_000_000
+    bad.meshes[first]["mat_id"][1::2] = -7
+    gpu2 = B.B200Backend(w, h); bad.apply(gpu2)
+    gpu2.render_spp(view, 2, 3)                       # must not fault
+    acc = gpu2.read_accumulator()
+    assert np.isfinite(acc).all()
+    gpu.reset_accumulator(); gpu.render_spp(view, 2, 3)
+    assert np.array_equal(gpu.read_accumulator(), good)  # the context is healthy: the first backend still renders bit-identically
+    with pytest.raises(B.RfwError):
+        gpu.set_3d_mesh(0xFFFFFFFF, desc.meshes[first])
+    with pytest.raises(B.RfwError):
+        gpu.set_3d_mesh(1 << 30, desc.meshes[first])
+    L = gpu.L
+    assert L.rfwb200_set_materials(gpu.h, None, 3, None) != 0 and L.rfwb200_set_area_lights(gpu.h, None, 2, None) != 0
+    assert L.rfwb200_unload_3d_meshes(gpu.h, None, 1) != 0
+
+
+@pytest.mark.parametrize("two_level", [False, True])
 def test_ray_binning_is_transparent(B, torch_cuda, two_level):
     """Option sort_rays (off by default; meant for scenes whose BVH exceeds the L2): rays are traced in Morton order of their origins
     through an index permutation — the hits must land at the rays' own slots, bit-identical to the unsorted launch,
