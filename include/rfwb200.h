@@ -299,6 +299,8 @@ typedef struct RfwRenderStats {
     float stage_ms[5];
     uint32_t stage_timing;
     uint32_t stack_overflows;      /* != 0: a traversal-stack push was dropped during the last render_spp (it returns RFWB200_ERR_STACK) */
+    float gather_ms;               /* device time of the last rfwb200_gather_image on this rank: export + NCCL + assemble (incl. waiting for peers) */
+    float frame_ms;                /* host wall time of the last rfwb200_render_gather (render_spp + gather, both waited for) */
 } RfwRenderStats;
 
 enum {
@@ -345,6 +347,12 @@ RFWB200_API int rfwb200_set_area_lights(void* handle, const RfwAreaLight* lights
 RFWB200_API int rfwb200_set_directional_lights(void* handle, const RfwDirectionalLight* lights, uint32_t num, const uint32_t* changed);
 /* Backend::set_skybox (lib.rs:78) */
 RFWB200_API int rfwb200_set_skybox(void* handle, const RfwTextureData* skybox);
+/* Sampler tables of the first 256 samples per pixel (blueNoiseSampler, backends/gpu-rt/shaders/ray_gen.comp:72-91 and
+ * shade.comp:530-549): the u32 buffer create_blue_noise_buffer() builds (backends/gpu-rt/src/blue_noise.rs:40970-41004,
+ * 5 * 65536 entries: Sobol sequence | scrambling keys | ranking keys).  The reference compiles the tables into its backend
+ * crate; this backend takes them from the host (the Rust shim calls create_blue_noise_buffer once after init).
+ * Without them (never called, or NULL / 0) every sample uses the hash RNG the reference switches to at sample 256. */
+RFWB200_API int rfwb200_set_blue_noise(void* handle, const uint32_t* table, uint32_t num_entries);
 /* FFI repack of SkinData<'a> (crates/rfw-backend/src/structs.rs:6-11): column-major Mat4 arrays of `num_joints` */
 typedef struct RfwSkinData {
     const float* inverse_bind_matrices; /* kept for completeness; the joint matrices already include them */
@@ -398,6 +406,23 @@ RFWB200_API int rfwb200_assemble_tiles_device(void* handle, const float* d_gathe
 /* host-only, needs no device: all tile ids of the width x height framebuffer in Morton order.  Entry k belongs to rank
  * k % world and is that rank's tile number k / world (the layout export/assemble use).  Returns the tile count. */
 RFWB200_API uint32_t rfwb200_tile_layout(uint32_t width, uint32_t height, uint32_t tile, uint32_t* out_morton_tiles, uint32_t capacity);
+/* ---- multi-GPU: one process per GPU, scene replicated on every rank, tiles sharded (tile k in Morton order belongs to rank
+ * k % world), ONE collective per frame: the accumulator gather over NCCL (NVLink / NVSwitch).  No reference counterpart (the
+ * reference is single-GPU); shape per SURVEY §8e.  NCCL is bound at run time (libnccl.so.2; a host process that already
+ * carries one, e.g. PyTorch, shares it).
+ *   rank 0:      rfwb200_comm_unique_id(id)  -> distribute the 128 bytes to every rank by any means (MPI, a file, a socket)
+ *   every rank:  rfwb200_comm_init(handle, id, rank, world)   (collective; also sets the tile sharding of this backend)
+ *   per frame:   rfwb200_render_spp(...) on every rank, then rfwb200_gather_image(handle, root, d_image) on every rank
+ *                (collective): root < world gathers on that rank, root >= world on all ranks.  The receiver's image
+ *                (sqrt(acc / spp), row-major RGBA32F) lands in `d_image` (device, width*height*4 floats) or, with NULL, in the
+ *                backend's output buffer (rfwb200_read_output).  rfwb200_render_gather = both steps, timed as one frame. */
+#define RFWB200_COMM_ID_BYTES 128
+RFWB200_API int rfwb200_comm_unique_id(uint8_t* out_id /* RFWB200_COMM_ID_BYTES */);
+RFWB200_API int rfwb200_comm_init(void* handle, const uint8_t* unique_id, uint32_t rank, uint32_t world);
+RFWB200_API int rfwb200_comm_destroy(void* handle);
+RFWB200_API int rfwb200_gather_image(void* handle, uint32_t root, float* d_image);
+RFWB200_API int rfwb200_render_gather(void* handle, const RfwCameraView3D* view, uint32_t spp, uint32_t depth, uint32_t root, float* d_image);
+RFWB200_API int rfwb200_nccl_version(void);  /* e.g. 22809; 0 when no NCCL can be loaded (rfwb200_last_error says why) */
 RFWB200_API uint32_t rfwb200_sample_count(void* handle);
 RFWB200_API uint32_t rfwb200_tiles_per_rank(void* handle);
 

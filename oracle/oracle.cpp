@@ -455,6 +455,7 @@ struct Scene {
     std::vector<RfwPointLight> point_lights;
     std::vector<RfwSpotLight> spot_lights;
     std::vector<RfwDirectionalLight> dir_lights;
+    std::vector<uint32_t> blue_noise;  // sampler tables of the first 256 samples (create_blue_noise_buffer layout); empty = hash RNG
     uint32_t total_instance_slots = 0;
     std::vector<int> gid_to_live;  // global instance index -> index in `instances` (-1: removed / never sent)
 
@@ -962,8 +963,26 @@ static void pinhole_ray(const RfwCameraView3D& c, uint32_t x, uint32_t y, V3& O,
     O = V3(c.pos);
     D = normalize(p - O);
 }
-static void eye_ray(const RfwCameraView3D& c, int w, int h, int sx, int sy, uint32_t& seed, V3& O, V3& D) {
-    float r0 = randf(seed), r1 = randf(seed), r2 = randf(seed), r3 = randf(seed);
+// blueNoiseSampler — ray_gen.comp:72-91 (= shade.comp:530-549); reads beyond the table return 0 (bounds-checked storage buffer)
+static float blue_noise_sample(const std::vector<uint32_t>& bn, int x, int y, int sampleDimension, uint32_t sample_count) {
+    x &= 127;
+    y &= 127;
+    const int sampleIdx = (int)((sample_count + 1u) & 255u);
+    sampleDimension &= 255;
+    auto at = [&](size_t i) -> int { return i < bn.size() ? (int)bn[i] : 0; };
+    const int rankedSampleIndex = sampleIdx ^ at((size_t)sampleDimension + (size_t)(x + y * 128) * 8 + 65536 * 3);
+    int value = at((size_t)sampleDimension + (size_t)rankedSampleIndex * 256);
+    value ^= at((size_t)(sampleDimension & 7) + (size_t)(x + y * 128) * 8 + 65536);
+    return (0.5f + (float)value) * (1.0f / 256.0f);
+}
+static void eye_ray(const RfwCameraView3D& c, int w, int h, int sx, int sy, uint32_t& seed, V3& O, V3& D, const std::vector<uint32_t>* bn = nullptr, uint32_t sample = 256) {
+    float r0, r1, r2, r3;
+    if (bn && !bn->empty() && sample < 256u) {  // ray_gen.comp:109-115
+        r0 = blue_noise_sample(*bn, sx, sy, 0, sample); r1 = blue_noise_sample(*bn, sx, sy, 1, sample);
+        r2 = blue_noise_sample(*bn, sx, sy, 2, sample); r3 = blue_noise_sample(*bn, sx, sy, 3, sample);
+    } else {
+        r0 = randf(seed); r1 = randf(seed); r2 = randf(seed); r3 = randf(seed);
+    }
     const float blade = (float)(int)(r0 * 9);
     r2 = (r2 - blade * (1.0f / 9.0f)) * 9.0f;
     const float piOver4point5 = 3.14159265359f / 4.5f;
@@ -988,7 +1007,8 @@ static V3 trace_path(const Scene& sc, const RfwCameraView3D& cam, int w, int h, 
     const int lightCount = (int)(sc.area_lights.size() + sc.point_lights.size() + sc.spot_lights.size() + sc.dir_lights.size());
     uint32_t seed = wang_hash((uint32_t)path_id * 16789u + sample * 1791u + 0u * 720898027u);  // ray_gen.comp:54
     V3 O, D;
-    eye_ray(cam, w, h, path_id % w, path_id / w, seed, O, D);
+    const bool bn = !sc.blue_noise.empty() && sample < 256u;  // ray_gen.comp:109, shade.comp:190,216
+    eye_ray(cam, w, h, path_id % w, path_id / w, seed, O, D, &sc.blue_noise, sample);
     V3 throughput(1.0f);
     float bsdfPdf = 1.0f;
     for (int path_length = 0; path_length < depth; path_length++) {
@@ -1072,7 +1092,11 @@ static V3 trace_path(const Scene& sc, const RfwCameraView3D& cam, int w, int h, 
         const bool backFacing = dot(D, gN) >= 0.0f;  // :177-181
         if (backFacing) { N = N * -1.0f; gN = gN * -1.0f; }
         throughput = throughput * (1.0f / bsdfPdf);
-        const float r1 = randf(seed), r2 = randf(seed);
+        float r1, r2;
+        if (bn) {  // shade.comp:190-196
+            r1 = blue_noise_sample(sc.blue_noise, path_id % w, path_id / w, 4 + 4 * path_length, sample);
+            r2 = blue_noise_sample(sc.blue_noise, path_id % w, path_id / w, 5 + 4 * path_length, sample);
+        } else { r1 = randf(seed); r2 = randf(seed); }
         V3 R; float newPdf = 0; int type;
         const V3 wo = D * -1.0f;
         BSDFSample(sd, T3, B, gN, wo, R, newPdf, type, r1, r2);           // disney.glsl:275-285: sampling frame uses gN
@@ -1081,7 +1105,11 @@ static V3 trace_path(const Scene& sc, const RfwCameraView3D& cam, int w, int h, 
         throughput = V3(throughput.x > 0.0f ? throughput.x : 0.0f, throughput.y > 0.0f ? throughput.y : 0.0f, throughput.z > 0.0f ? throughput.z : 0.0f);  // max(throughput, 0) drops NaN
         if (newPdf <= 1e-4f || std::isnan(newPdf)) break;  // :208
         if (lightCount > 0) {                              // :213-258
-            const float r3 = randf(seed), r4 = randf(seed);
+            float r3, r4;
+            if (bn) {  // shade.comp:216-222
+                r3 = blue_noise_sample(sc.blue_noise, path_id % w, path_id / w, 6 + 4 * path_length, sample);
+                r4 = blue_noise_sample(sc.blue_noise, path_id % w, path_id / w, 7 + 4 * path_length, sample);
+            } else { r3 = randf(seed); r4 = randf(seed); }
             V3 lightColor; float pickProb, lightPdf;
             V3 L = random_point_on_light(sc, r3, r4, P, N, pickProb, lightPdf, lightColor) - P;
             const float dist = length(L);
@@ -1192,6 +1220,11 @@ void orc_texture_callback(void* s, int layer, float u, float v, float lod, float
     if (layer < 0) { if (sc.has_sky) sc.skybox.sample_level(u, v, (int)lod, false, true, out); return; }
     if ((size_t)layer < sc.textures.size()) sc.textures[layer].fetch(u, v, (int)lod, out);
 }
+void orc_set_blue_noise(void* s, const uint32_t* table, uint32_t n) {
+    if (table && n) ((Scene*)s)->blue_noise.assign(table, table + n);
+    else ((Scene*)s)->blue_noise.clear();
+}
+float orc_blue_noise_sample(void* s, int x, int y, int dim, uint32_t sample_count) { return blue_noise_sample(((Scene*)s)->blue_noise, x, y, dim, sample_count); }
 void orc_set_area_lights(void* s, const RfwAreaLight* l, uint32_t n) { ((Scene*)s)->area_lights.assign(l, l + n); }
 void orc_set_point_lights(void* s, const RfwPointLight* l, uint32_t n) { ((Scene*)s)->point_lights.assign(l, l + n); }
 void orc_set_spot_lights(void* s, const RfwSpotLight* l, uint32_t n) { ((Scene*)s)->spot_lights.assign(l, l + n); }

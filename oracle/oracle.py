@@ -134,6 +134,11 @@ class OracleBackend:
             self.L.orc_get_skinned_triangles(self.h, mesh_id, index, _ptr(out))
         return out
 
+    def set_blue_noise(self, table=None):
+        t = np.zeros(0, dtype=np.uint32) if table is None else np.ascontiguousarray(table, dtype=np.uint32)
+        self.L.orc_set_blue_noise.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        self.L.orc_set_blue_noise(self.h, _ptr(t), len(t))
+
     def set_skins(self, skins=(), changed=None):
         self.L.orc_set_num_skins(self.h, len(skins))
         for k, j in enumerate(skins):

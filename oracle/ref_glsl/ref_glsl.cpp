@@ -118,8 +118,11 @@ void ref_bind_lights(const void* area, int na, const void* point, int np, const 
 }
 void ref_set_texture_callback(ref_texture_fn fn, void* user) { g_ref_texture_fn = fn; g_ref_texture_user = user; }
 // the blue-noise tables the host appends to the camera block (lib.rs: `blueNoise[]` after the 128-byte CameraView)
+// (zero-padded: the shader's ranking index `dim + pixel * 8 + 3 * 65536` is not masked to 8 dimensions and runs past the
+// buffer for the last pixels; the reference's storage buffer is bounds-checked — reads beyond it return 0)
 void ref_set_blue_noise(const int* table, uint64_t n) {
     g_blue.assign(table, table + n);
+    g_blue.resize(n + 65536 + 512, 0);
     blueNoise = g_blue.data();
 }
 

@@ -59,6 +59,7 @@ def load_library():
         "rfwb200_set_directional_lights": ([vp, vp, u32, vp], i32),
         "rfwb200_set_skybox": ([vp, vp], i32),
         "rfwb200_set_skins": ([vp, vp, u32, vp], i32),
+        "rfwb200_set_blue_noise": ([vp, vp, u32], i32),
         "rfwb200_set_2d_mesh": ([vp, u32, vp, u32, C.c_int32], i32),
         "rfwb200_set_2d_instances": ([vp, u32, vp, u32], i32),
         "rfwb200_trace_closest": ([vp, vp, u64, vp], i32),
@@ -73,6 +74,12 @@ def load_library():
         "rfwb200_read_output": ([vp, f32p], i32),
         "rfwb200_export_tiles_device": ([vp, vp, u32, vp], i32),
         "rfwb200_assemble_tiles_device": ([vp, vp, u32, u32, vp], i32),
+        "rfwb200_comm_unique_id": ([vp], i32),
+        "rfwb200_comm_init": ([vp, vp, u32, u32], i32),
+        "rfwb200_comm_destroy": ([vp], i32),
+        "rfwb200_gather_image": ([vp, u32, vp], i32),
+        "rfwb200_render_gather": ([vp, vp, u32, u32, u32, vp], i32),
+        "rfwb200_nccl_version": ([], i32),
         "rfwb200_sample_count": ([vp], u32),
         "rfwb200_tiles_per_rank": ([vp], u32),
         "rfwb200_build_stats": ([vp, vp], i32),
@@ -242,6 +249,14 @@ class B200Backend:
         d, _keep = self._texture_data(skybox)
         self._ck(self.L.rfwb200_set_skybox(self.h, C.addressof(d)), "set_skybox")
 
+    def set_blue_noise(self, table=None):
+        """u32 sampler tables in create_blue_noise_buffer's layout (None: hash RNG for every sample)."""
+        if table is None:
+            self._ck(self.L.rfwb200_set_blue_noise(self.h, None, 0), "set_blue_noise")
+            return
+        t = np.ascontiguousarray(table, dtype=np.uint32)
+        self._ck(self.L.rfwb200_set_blue_noise(self.h, _ptr(t), len(t)), "set_blue_noise")
+
     def set_skins(self, skins=(), changed=None):
         """skins: list of (n_joints, 16) column-major joint matrices (SkinData::joint_matrices)."""
         skins = [np.ascontiguousarray(j, dtype=np.float32).reshape(-1, 16) for j in skins]
@@ -328,6 +343,32 @@ class B200Backend:
 
     def assemble_tiles_device(self, d_gathered_ptr, tiles_per_rank, world, d_image_ptr):
         self._ck(self.L.rfwb200_assemble_tiles_device(self.h, d_gathered_ptr, tiles_per_rank, world, d_image_ptr), "assemble_tiles_device")
+
+    # ---- multi-GPU: NCCL accumulator gather inside the library (rfwb200.h, "multi-GPU") ---------------------------
+    @staticmethod
+    def comm_unique_id():
+        """128 bytes from ncclGetUniqueId (rank 0 calls this and distributes them)."""
+        L = load_library()
+        buf = (C.c_uint8 * 128)()
+        rc = L.rfwb200_comm_unique_id(C.addressof(buf))
+        if rc != 0:
+            raise RfwError(f"comm_unique_id failed ({rc}): {L.rfwb200_last_error().decode()}")
+        return bytes(buf)
+
+    def comm_init(self, unique_id, rank, world):
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        self._ck(self.L.rfwb200_comm_init(self.h, C.addressof(buf), rank, world), "comm_init")
+
+    def comm_destroy(self):
+        self._ck(self.L.rfwb200_comm_destroy(self.h), "comm_destroy")
+
+    def gather_image(self, root=0, d_image_ptr=None):
+        """Collective: every rank calls it after render_spp.  root < world: that rank receives; root >= world: all do."""
+        self._ck(self.L.rfwb200_gather_image(self.h, root, d_image_ptr), "gather_image")
+
+    def render_gather(self, view, spp, depth=0, root=0, d_image_ptr=None):
+        v = np.ascontiguousarray(view)
+        self._ck(self.L.rfwb200_render_gather(self.h, _ptr(v), spp, depth, root, d_image_ptr), "render_gather")
 
     @property
     def sample_count(self):

@@ -40,6 +40,7 @@ int rfwb200_set_spot_lights(void* handle, const RfwSpotLight* l, uint32_t n, con
 int rfwb200_set_area_lights(void* handle, const RfwAreaLight* l, uint32_t n, const uint32_t*) { RFW_GUARD(handle); return b->set_area_lights(l, n); }
 int rfwb200_set_directional_lights(void* handle, const RfwDirectionalLight* l, uint32_t n, const uint32_t*) { RFW_GUARD(handle); return b->set_directional_lights(l, n); }
 int rfwb200_set_skybox(void* handle, const RfwTextureData* t) { RFW_GUARD(handle); return b->set_skybox(t); }
+int rfwb200_set_blue_noise(void* handle, const uint32_t* table, uint32_t n) { RFW_GUARD(handle); return b->set_blue_noise(table, n); }
 int rfwb200_set_skins(void* handle, const RfwSkinData* skins, uint32_t n, const uint32_t* changed) { RFW_GUARD(handle); return b->set_skins(skins, n, changed); }
 int rfwb200_set_2d_mesh(void* handle, uint32_t, const void*, uint32_t, int32_t) { RFW_GUARD(handle); return b ? RFWB200_OK : RFWB200_ERR_INVALID; }
 int rfwb200_set_2d_instances(void* handle, uint32_t, const float*, uint32_t) { RFW_GUARD(handle); return b ? RFWB200_OK : RFWB200_ERR_INVALID; }
@@ -57,6 +58,25 @@ int rfwb200_read_accumulator(void* handle, float* out) { RFW_GUARD(handle); retu
 int rfwb200_read_output(void* handle, float* out) { RFW_GUARD(handle); return b->read_output(out); }
 int rfwb200_export_tiles_device(void* handle, float* d_out, uint32_t cap, uint32_t* out_tiles) { RFW_GUARD(handle); return b->export_tiles_device(d_out, cap, out_tiles); }
 int rfwb200_assemble_tiles_device(void* handle, const float* d_g, uint32_t tpr, uint32_t world, float* d_img) { RFW_GUARD(handle); return b->assemble_tiles_device(d_g, tpr, world, d_img); }
+int rfwb200_comm_unique_id(uint8_t* out_id) {
+    if (!out_id) { rfw::set_last_error("rfwb200_comm_unique_id: null buffer"); return RFWB200_ERR_INVALID; }
+    const std::string err = rfw::comm_unique_id(out_id);
+    if (!err.empty()) { rfw::set_last_error("rfwb200_comm_unique_id: " + err); return RFWB200_ERR_CUDA; }
+    return RFWB200_OK;
+}
+int rfwb200_comm_init(void* handle, const uint8_t* id, uint32_t rank, uint32_t world) { RFW_GUARD(handle); return b->comm_init(id, rank, world); }
+int rfwb200_comm_destroy(void* handle) { RFW_GUARD(handle); return b->comm_destroy(); }
+int rfwb200_gather_image(void* handle, uint32_t root, float* d_image) { RFW_GUARD(handle); return b->gather_image(root, d_image); }
+int rfwb200_render_gather(void* handle, const RfwCameraView3D* view, uint32_t spp, uint32_t depth, uint32_t root, float* d_image) {
+    RFW_GUARD(handle);
+    return b->render_gather(view, spp, depth, root, d_image);
+}
+int rfwb200_nccl_version(void) {
+    int v = 0;
+    const std::string err = rfw::comm_version(&v);
+    if (!err.empty()) { rfw::set_last_error(err); return 0; }
+    return v;
+}
 uint32_t rfwb200_sample_count(void* handle) { return handle ? static_cast<Backend*>(handle)->sample_count : 0; }
 uint32_t rfwb200_tiles_per_rank(void* handle) { return handle ? static_cast<Backend*>(handle)->tiles_per_rank() : 0; }
 

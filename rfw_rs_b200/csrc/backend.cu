@@ -67,11 +67,19 @@ int Backend::init() {
     BK_CUDA(cudaGetDeviceProperties(&prop, cfg.device), "cudaGetDeviceProperties");
     if (prop.major < 10) return fail(RFWB200_ERR_NO_DEVICE, "librfwb200 is built for sm_100a only; found compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor));
     sm_count = prop.multiProcessorCount;
-    BK_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "stream");
+    {   // the main stream carries the dependency chain extend -> shade -> extend ...; the connect stage runs beside it on a
+        // lower-priority stream (wavefront.h): CTA slots freed in a kernel's tail go to the main chain first
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        BK_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_hi), "stream");
+        BK_CUDA(cudaStreamCreateWithPriority(&wf.side, cudaStreamNonBlocking, prio_lo), "stream");
+    }
     BK_CUDA(cudaStreamCreateWithFlags(&copy_in, cudaStreamNonBlocking), "stream");
     BK_CUDA(cudaStreamCreateWithFlags(&copy_out, cudaStreamNonBlocking), "stream");
     BK_CUDA(cudaEventCreate(&ev0), "event");
     BK_CUDA(cudaEventCreate(&ev1), "event");
+    BK_CUDA(cudaEventCreate(&ev_g0), "event");
+    BK_CUDA(cudaEventCreate(&ev_g1), "event");
     {   // keep freed blocks of the stream-ordered allocator cached: BLAS builds of many small meshes reuse them
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, cfg.device) == cudaSuccess) {
@@ -101,6 +109,7 @@ int Backend::init() {
 Backend::~Backend() {
     DeviceScope device_scope(cfg.device);
     if (stream) cudaStreamSynchronize(stream);
+    if (wf.side) cudaStreamSynchronize(wf.side);
     for (BuilderContext* c : side_ctx) {
         if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
         delete c;
@@ -119,9 +128,13 @@ Backend::~Backend() {
     for (auto& sk : skins) sk.joints.release();
     for (auto& si : skinned) release_skinned(si);
     for (auto& t : textures) t.texels.release();
-    skybox.texels.release(); d_tex_desc.release();
+    skybox.texels.release(); d_tex_desc.release(); d_blue_noise.release();
     d_mesh_table.release(); d_matrices.release();
     wf.release();
+    comm_destroy();
+    d_send.release(); d_gathered.release();
+    if (ev_g0) cudaEventDestroy(ev_g0);
+    if (ev_g1) cudaEventDestroy(ev_g1);
     if (d_stream_state) cudaFree(d_stream_state);
     if (h_stream_flags) cudaFreeHost(h_stream_flags);
     if (h_stream_marks) cudaFreeHost(h_stream_marks);
@@ -132,6 +145,7 @@ Backend::~Backend() {
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
+    if (wf.side) { cudaStreamDestroy(wf.side); wf.side = nullptr; }
     if (copy_in) cudaStreamDestroy(copy_in);
     if (copy_poll) cudaStreamDestroy(copy_poll);
     if (copy_out) cudaStreamDestroy(copy_out);
@@ -292,6 +306,25 @@ int Backend::set_skybox(const RfwTextureData* t) {
     }
     shading_dirty = true;
     synchronized = false;
+    return RFWB200_OK;
+}
+
+// The sampler tables of the first 256 samples (ray_gen.comp:72-91).  The reference keeps them inside its backend crate
+// (backends/gpu-rt/src/blue_noise.rs, create_blue_noise_buffer); here they are data the host hands over once — a host that
+// never calls this renders every sample with the hash RNG the reference switches to from sample 256 on.
+int Backend::set_blue_noise(const uint32_t* table, uint32_t n) {
+    DeviceScope device_scope(cfg.device);
+    BK_CUDA(device_scope.status, "cudaSetDevice");
+    BK_CUDA(cudaStreamSynchronize(stream), "sync");
+    if (!table || n == 0) {
+        wf.d_blue_noise = nullptr; wf.blue_noise_n = 0;
+    } else {
+        BK_CUDA(d_blue_noise.reserve(n), "blue noise");
+        BK_CUDA(cudaMemcpyAsync(d_blue_noise.ptr, table, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, stream), "blue noise");
+        BK_CUDA(cudaStreamSynchronize(stream), "blue noise");  // borrowed slice
+        wf.d_blue_noise = d_blue_noise.ptr; wf.blue_noise_n = n;
+    }
+    have_view = false;  // the sample sequence changed: accumulation restarts at the next render()
     return RFWB200_OK;
 }
 
@@ -1315,6 +1348,76 @@ int Backend::assemble_tiles_device(const float* d_gathered, uint32_t tpr, uint32
     return RFWB200_OK;
 }
 
+// ---- multi-GPU: the accumulator gather -----------------------------------------------------------------------
+// One process per GPU; every rank replays the same set_* calls (replicated scene, identical deterministic build), renders the
+// tiles it owns (tile k in Morton order -> rank k mod world) and the frame is completed by ONE collective over NCCL: every rank
+// writes its tiles tile-major into its send buffer, the blocks are gathered on `root` (ncclSend / ncclRecv in one group; all
+// ranks with root >= world: ncclAllGather), and the receiver de-tiles + applies sqrt(acc / spp) (blit.comp:22) in one pass.
+// Everything is enqueued on the backend's own stream, so export -> collective -> assemble are ordered without host syncs.
+int Backend::comm_init(const uint8_t* unique_id, uint32_t rank, uint32_t world) {
+    if (!unique_id) return fail(RFWB200_ERR_INVALID, "comm_init: null unique id");
+    if (world == 0 || rank >= world) return fail(RFWB200_ERR_INVALID, "comm_init: rank out of range");
+    DeviceScope device_scope(cfg.device);
+    BK_CUDA(device_scope.status, "cudaSetDevice");
+    BK_CUDA(cudaStreamSynchronize(stream), "sync");
+    const std::string err = rfw::comm_init(comm, unique_id, rank, world);
+    if (!err.empty()) return fail(RFWB200_ERR_CUDA, "comm_init: " + err);
+    if (rank != cfg.rank || world != cfg.world) {  // the communicator defines the sharding
+        cfg.rank = rank; cfg.world = world;
+        if (cfg.width && cfg.height) BK_CUDA(wf.configure(cfg.width, cfg.height, cfg.tile_size, rank, world), "framebuffer");
+        sample_count = 0; have_view = false;
+    }
+    return RFWB200_OK;
+}
+
+int Backend::comm_destroy() {
+    if (comm.active()) {
+        DeviceScope device_scope(cfg.device);
+        if (stream) cudaStreamSynchronize(stream);
+        rfw::comm_destroy(comm);
+    }
+    return RFWB200_OK;
+}
+
+int Backend::gather_image(uint32_t root, float* d_image) {
+    DeviceScope device_scope(cfg.device);
+    BK_CUDA(device_scope.status, "cudaSetDevice");
+    if (wf.width == 0 || wf.height == 0) return fail(RFWB200_ERR_INVALID, "gather_image: zero-sized framebuffer");
+    const bool receiver = wf.world == 1 || root >= wf.world || root == wf.rank;
+    float* image = d_image ? d_image : reinterpret_cast<float*>(wf.d_output);
+    BK_CUDA(cudaEventRecord(ev_g0, stream), "event");
+    if (wf.world == 1) {
+        // single rank: the "gather" is the finalize pass (already in d_output after render_spp); honour a caller buffer
+        if (d_image) BK_CUDA(cudaMemcpyAsync(d_image, wf.d_output, (size_t)wf.width * wf.height * sizeof(float4), cudaMemcpyDeviceToDevice, stream), "gather_image");
+    } else {
+        if (!comm.active()) return fail(RFWB200_ERR_INVALID, "gather_image: world > 1 needs rfwb200_comm_init first");
+        if (comm.world != wf.world || comm.rank != wf.rank) return fail(RFWB200_ERR_INVALID, "gather_image: communicator and tile sharding disagree");
+        const size_t count = (size_t)wf.tiles_per_rank * wf.tile * wf.tile * 4;
+        BK_CUDA(d_send.reserve(count), "send buffer");
+        if (receiver) BK_CUDA(d_gathered.reserve(count * wf.world), "gather buffer");
+        const size_t own = (size_t)wf.n_owned_tiles * wf.tile * wf.tile * 4;
+        if (own < count) BK_CUDA(cudaMemsetAsync(d_send.ptr + own, 0, (count - own) * sizeof(float), stream), "send buffer");  // ranks with one tile fewer pad
+        BK_CUDA(wf.export_tiles(stream, d_send.ptr), "export_tiles");
+        const std::string err = comm_gather(comm, d_send.ptr, receiver ? d_gathered.ptr : nullptr, count, root, stream);
+        if (!err.empty()) return fail(RFWB200_ERR_CUDA, "gather_image: " + err);
+        if (receiver) BK_CUDA(wf.assemble(stream, d_gathered.ptr, wf.tiles_per_rank, wf.world, sample_count, image), "assemble");
+        launch_count += receiver ? 2 : 1;
+    }
+    BK_CUDA(cudaEventRecord(ev_g1, stream), "event");
+    BK_CUDA(cudaEventSynchronize(ev_g1), "gather_image");
+    cudaEventElapsedTime(&render_stats.gather_ms, ev_g0, ev_g1);
+    return RFWB200_OK;
+}
+
+// one frame of the sharded renderer: `spp` samples of the owned tiles, then the gather — the unit bench.py times at N > 1
+int Backend::render_gather(const RfwCameraView3D* view, uint32_t spp, uint32_t depth, uint32_t root, float* d_image) {
+    const auto t0 = std::chrono::steady_clock::now();
+    if (int rc = render_spp(view, spp, depth)) return rc;
+    if (int rc = gather_image(root, d_image)) return rc;
+    render_stats.frame_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return RFWB200_OK;
+}
+
 int Backend::debug_read_queue(uint32_t which, float* o, float* d, float* t, float* s, uint32_t cap, uint32_t* cnt) {
     DeviceScope device_scope(cfg.device);
     BK_CUDA(device_scope.status, "cudaSetDevice");
@@ -1323,7 +1426,7 @@ int Backend::debug_read_queue(uint32_t which, float* o, float* d, float* t, floa
     uint32_t counts[8];
     BK_CUDA(cudaMemcpy(counts, wf.d_counts, sizeof(counts), cudaMemcpyDeviceToHost), "counts");
     // which = 0/1: the live count of that queue; which + 2: the same buffers with the count the last extend/shade consumed
-    const uint32_t live = which < 2 ? counts[which] : counts[5];
+    const uint32_t live = which < 2 ? counts[which] : counts[6];
     which &= 1u;
     const uint32_t n = (uint32_t)std::min<size_t>(std::min(live, cap), wf.capacity());
     if (o) BK_CUDA(cudaMemcpy(o, wf.d_O[which], (size_t)n * 16, cudaMemcpyDeviceToHost), "queue");
@@ -1354,6 +1457,7 @@ int Backend::set_option(const char* key, int64_t value) {
     else if (k == "sort_rays") sort_rays = (int)value;
     else if (k == "sort_min_bvh_mb") sort_min_bvh_bytes = (uint64_t)std::max<int64_t>(0, value) << 20;
     else if (k == "stage_timing") wf.stage_timing = value != 0;
+    else if (k == "wf_overlap") wf.overlap = value != 0;  // connect(b) beside extend(b + 1) on a second stream (1, default) or everything on one stream (0)
     else if (k == "inst_batch") tcfg.inst_batch = (int)std::max<int64_t>(1, value);
     else if (k == "min_blocks") tcfg.min_blocks = (int)value;
     else if (k == "l2_persist") { l2_persist_enabled = value != 0; if (!l2_persist_enabled) { cudaStreamAttrValue a{}; cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &a); cudaCtxResetPersistingL2Cache(); } else { if (l2_persist_max && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, l2_persist_max) != cudaSuccess) { cudaGetLastError(); l2_persist_max = 0; } update_l2_policy(); } }

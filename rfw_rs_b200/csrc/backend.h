@@ -11,6 +11,7 @@
 
 #include "../../include/rfwb200.h"
 #include "builder.h"
+#include "comm.h"
 #include "trace.h"
 #include "wavefront.h"
 
@@ -79,6 +80,7 @@ public:
     int set_textures(const RfwTextureData* t, uint32_t num, const uint32_t* changed);
     int set_skins(const RfwSkinData* skins, uint32_t num, const uint32_t* changed);
     int set_skybox(const RfwTextureData* t);
+    int set_blue_noise(const uint32_t* table, uint32_t n);
     int set_area_lights(const RfwAreaLight* l, uint32_t num);
     int set_point_lights(const RfwPointLight* l, uint32_t num);
     int set_spot_lights(const RfwSpotLight* l, uint32_t num);
@@ -101,6 +103,11 @@ public:
     int export_tiles_device(float* d_out, uint32_t capacity_tiles, uint32_t* out_tiles);
     int assemble_tiles_device(const float* d_gathered, uint32_t tiles_per_rank, uint32_t world, float* d_image);
     uint32_t tiles_per_rank() const;
+    // multi-GPU: one process per GPU, scene replicated, tiles sharded, ONE collective — the accumulator gather
+    int comm_init(const uint8_t* unique_id, uint32_t rank, uint32_t world);
+    int comm_destroy();
+    int gather_image(uint32_t root, float* d_image);
+    int render_gather(const RfwCameraView3D* view, uint32_t spp, uint32_t depth, uint32_t root, float* d_image);
 
     int set_option(const char* key, int64_t value);
     int measure_l2(uint64_t bytes, uint32_t iters, float* out_gbs);
@@ -167,6 +174,7 @@ private:
     TextureRec skybox;
     bool have_skybox = false;
     DeviceArray<TexDesc> d_tex_desc;
+    DeviceArray<uint32_t> d_blue_noise;
     int upload_texture(TextureRec& rec, const RfwTextureData& t, const char* what);
 
     DeviceBvh tlas;
@@ -210,6 +218,11 @@ private:
     int sah_pmax = 3;         // max triangles per leaf slot
     int sah_treelet_tlas = 0;  // the same for the TLAS over instance boxes: off — refining the 170-instance TLAS of pica (nested, overlapping part boxes) made its primary rays 60 % slower (scripts/exp_c1b.py), the C3 grid TLAS is indifferent
     int sah_treelet = 8;  // binned-SAH refinement above LBVH treelets of this many primitives (0 = plain LBVH)
+
+    // accumulator gather over NCCL (comm.h)
+    Comm comm;
+    DeviceArray<float> d_send, d_gathered;
+    cudaEvent_t ev_g0 = nullptr, ev_g1 = nullptr;
 
     // wavefront renderer
     Wavefront wf;

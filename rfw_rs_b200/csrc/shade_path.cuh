@@ -15,7 +15,31 @@ struct FrameParams {
     uint32_t wave_spp, npix;       // samples per wave; pixels per frame (stride of the per-sample partial accumulators)
     float clamp_value;
     float sky[3];
+    // blue-noise sampler tables (rfwb200_set_blue_noise): used for samples 0..255, nullptr = hash RNG throughout
+    const uint32_t* blue_noise;
+    uint32_t blue_noise_n;
 };
+
+// The reference's sampler for the first 256 samples (ray_gen.comp:72-91 = shade.comp:530-549): a 128 x 128 tile of
+// 256-sample, 256-dimension Sobol points with per-pixel ranking and scrambling keys (Heitz et al. 2019), laid out by the host
+// as create_blue_noise_buffer does (backends/gpu-rt/src/blue_noise.rs:40970-41004): [0, 65536) the sequence, [65536, +131072)
+// scrambling keys, [3 * 65536, +131072) ranking keys.  The tables are DATA the host hands over; reads beyond them return 0 like
+// the reference's bounds-checked storage buffer (the ranking index `dim + pixel * 8` is not masked to 8 dimensions there).
+__device__ __forceinline__ float blue_noise_sample(const uint32_t* __restrict__ bn, uint32_t n, int x, int y, int dim, uint32_t sample_count) {
+    x &= 127;
+    y &= 127;
+    const int sample_idx = (int)((sample_count + 1u) & 255u);
+    dim &= 255;
+    const uint32_t pix = (uint32_t)(x + y * 128) * 8u;
+    const uint32_t i_rank = (uint32_t)dim + pix + 65536u * 3u;
+    const int ranked = sample_idx ^ (i_rank < n ? (int)__ldg(bn + i_rank) : 0);
+    const uint32_t i_seq = (uint32_t)dim + (uint32_t)ranked * 256u;
+    int value = i_seq < n ? (int)__ldg(bn + i_seq) : 0;
+    const uint32_t i_scr = (uint32_t)(dim & 7) + pix + 65536u;
+    value ^= i_scr < n ? (int)__ldg(bn + i_scr) : 0;
+    return (0.5f + (float)value) * (1.0f / 256.0f);
+}
+__device__ __forceinline__ bool use_blue_noise(const FrameParams& fp, uint32_t sample) { return fp.blue_noise != nullptr && sample < 256u; }  // ray_gen.comp:109, shade.comp:190,216
 
 // what one shaded path segment produces
 struct ShadeOut {
@@ -48,7 +72,15 @@ __device__ __forceinline__ uint32_t pack_bary16(float u, float v) { return (uint
 __device__ __forceinline__ void eye_ray(const FrameParams& fp, uint32_t pixel, uint32_t b, float3& o, float3& d) {
     uint32_t seed = wang_hash(pixel * 16789u + (fp.sample + b) * 1791u);
     const int sx = (int)(pixel % fp.width), sy = (int)(pixel / fp.width);
-    float r0 = randf(seed), r1 = randf(seed), r2 = randf(seed), r3 = randf(seed);
+    float r0, r1, r2, r3;
+    if (use_blue_noise(fp, fp.sample + b)) {  // :109-115
+        r0 = blue_noise_sample(fp.blue_noise, fp.blue_noise_n, sx, sy, 0, fp.sample + b);
+        r1 = blue_noise_sample(fp.blue_noise, fp.blue_noise_n, sx, sy, 1, fp.sample + b);
+        r2 = blue_noise_sample(fp.blue_noise, fp.blue_noise_n, sx, sy, 2, fp.sample + b);
+        r3 = blue_noise_sample(fp.blue_noise, fp.blue_noise_n, sx, sy, 3, fp.sample + b);
+    } else {
+        r0 = randf(seed); r1 = randf(seed); r2 = randf(seed); r3 = randf(seed);
+    }
     const float blade = (float)(int)(r0 * 9.0f);
     r2 = (r2 - blade * (1.0f / 9.0f)) * 9.0f;
     const float piOver4point5 = 3.14159265359f / 4.5f;
@@ -143,7 +175,15 @@ __device__ __forceinline__ void shade_path(const FrameParams& fp, const ShadeSce
             const bool backFacing = dot3(Dv, gN) >= 0.0f;  // :177-181
             if (backFacing) { N = N * -1.0f; gN = gN * -1.0f; }
             throughput = throughput * (1.0f / bsdfPdf);  // :183
-            const float r1 = randf(seed), r2 = randf(seed);
+            const bool bn = use_blue_noise(fp, fp.sample + wave_b);
+            const int px = (int)(pixel % fp.width), py = (int)(pixel / fp.width);
+            float r1, r2;
+            if (bn) {  // :190-196
+                r1 = blue_noise_sample(fp.blue_noise, fp.blue_noise_n, px, py, (int)(4u + 4u * fp.path_length), fp.sample + wave_b);
+                r2 = blue_noise_sample(fp.blue_noise, fp.blue_noise_n, px, py, (int)(5u + 4u * fp.path_length), fp.sample + wave_b);
+            } else {
+                r1 = randf(seed); r2 = randf(seed);
+            }
             const float3 wo = Dv * -1.0f;
             float3 R = f3(0, 0, 1);
             float newPdf = 0.0f;
@@ -153,8 +193,9 @@ __device__ __forceinline__ void shade_path(const FrameParams& fp, const ShadeSce
             throughput = f3(throughput.x > 0.0f ? throughput.x : 0.0f, throughput.y > 0.0f ? throughput.y : 0.0f, throughput.z > 0.0f ? throughput.z : 0.0f);
             if (!(newPdf <= 1e-4f || isnan(newPdf))) {  // :208
                 if (lightCount > 0) {                   // :213-258
-                    const float r3 = randf(seed);
-                    (void)randf(seed);  // r4 is drawn but unused by the uniform light pick
+                    float r3;
+                    if (bn) r3 = blue_noise_sample(fp.blue_noise, fp.blue_noise_n, px, py, (int)(6u + 4u * fp.path_length), fp.sample + wave_b);  // :216-222 (r4, dimension 7 + 4 len, is unused by the uniform light pick)
+                    else { r3 = randf(seed); (void)randf(seed); }
                     float3 lightColor;
                     float pickProb, lightPdf;
                     float3 L = random_point_on_light(ss, r3, P, N, pickProb, lightPdf, lightColor) - P;

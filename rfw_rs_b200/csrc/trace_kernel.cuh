@@ -79,18 +79,21 @@ template <bool TWO_LEVEL>
 constexpr size_t persistent_smem_bytes() {
     return (size_t)(PT_SM_STACK + PT_DEFER) * PT_THREADS * sizeof(uint2) + (TWO_LEVEL ? (size_t)PT_WORLD_RAY_F4 * PT_THREADS * sizeof(float4) : 0);
 }
-#define RFW_STACK_PUSH(v)                                                                   \
-    do {                                                                                    \
-        if (sp < SM_STACK) sts_u2(st_base + (uint32_t)sp * (uint32_t)(THREADS * 8), (v));  \
-        else if (sp - SM_STACK < L_STACK) lstack[sp - SM_STACK] = (v);                      \
-        else note_stack_overflow(sv); /* entry dropped: reported, never silent */           \
-        sp++;                                                                               \
+// A push that finds the stack full is dropped WHOLE (sp does not move): the stack stays consistent, every pop returns an entry
+// that was really pushed, the ray ends after finitely many steps with a subtree missing — and the drop is flagged, never
+// silent.  (Counting the dropped entry in sp made the matching pop re-read the top slot: a subtree re-walked once per dropped
+// sibling, exponential in the depth — the 2 + 2 entry test variant ran for minutes.)
+#define RFW_STACK_PUSH(v)                                                                                    \
+    do {                                                                                                     \
+        if (sp < SM_STACK) { sts_u2(st_base + (uint32_t)sp * (uint32_t)(THREADS * 8), (v)); sp++; }          \
+        else if (sp - SM_STACK < L_STACK) { lstack[sp - SM_STACK] = (v); sp++; }                             \
+        else note_stack_overflow(sv);                                                                        \
     } while (0)
 #define RFW_STACK_POP(dst)                                                                          \
     do {                                                                                            \
         sp--;                                                                                       \
         if (sp < SM_STACK) (dst) = lds_u2(st_base + (uint32_t)sp * (uint32_t)(THREADS * 8));       \
-        else (dst) = lstack[(sp - SM_STACK) < L_STACK ? (sp - SM_STACK) : (L_STACK - 1)];           \
+        else (dst) = lstack[sp - SM_STACK];                                                         \
     } while (0)
 
 struct TraceTuning {

@@ -54,11 +54,14 @@ void Wavefront::release() {
     auto fr = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
     fr(d_owned_tiles); fr(d_morton_tiles);
     for (int i = 0; i < 2; i++) { fr(d_O[i]); fr(d_D[i]); fr(d_T[i]); }
-    fr(d_S); fr(d_shO); fr(d_shD); fr(d_shE); fr(d_partial); fr(d_accum); fr(d_output); fr(d_counts); fr(d_stats);
+    for (int i = 0; i < 2; i++) { fr(d_shO[i]); fr(d_shD[i]); fr(d_shE[i]); }
+    fr(d_S); fr(d_partial); fr(d_term); fr(d_accum); fr(d_output); fr(d_counts); fr(d_stats);
     max_paths = 0;
     wave_capacity = 0;
     for (cudaEvent_t e : stage_events) cudaEventDestroy(e);
     stage_events.clear(); stage_marks.clear(); stage_used = 0;
+    for (cudaEvent_t e : sync_events) cudaEventDestroy(e);
+    sync_events.clear();
 }
 
 cudaError_t Wavefront::configure(uint32_t w, uint32_t h, uint32_t tile_size, uint32_t rank_, uint32_t world_) {
@@ -92,8 +95,8 @@ cudaError_t Wavefront::configure(uint32_t w, uint32_t h, uint32_t tile_size, uin
 cudaError_t Wavefront::ensure_wave(uint32_t b) {
     if (b <= wave_capacity) return cudaSuccess;
     auto fr = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
-    for (int i = 0; i < 2; i++) { fr(d_O[i]); fr(d_D[i]); fr(d_T[i]); }
-    fr(d_S); fr(d_shO); fr(d_shD); fr(d_shE); fr(d_partial);
+    for (int i = 0; i < 2; i++) { fr(d_O[i]); fr(d_D[i]); fr(d_T[i]); fr(d_shO[i]); fr(d_shD[i]); fr(d_shE[i]); }
+    fr(d_S); fr(d_partial); fr(d_term);
     wave_capacity = 0;
     const size_t mp = (size_t)std::max<uint32_t>(1, max_paths) * b;
     for (int i = 0; i < 2; i++) {
@@ -102,12 +105,16 @@ cudaError_t Wavefront::ensure_wave(uint32_t b) {
         WF_CK(cudaMalloc(&d_T[i], mp * sizeof(float4)));
     }
     WF_CK(cudaMalloc(&d_S, mp * sizeof(float4)));
-    WF_CK(cudaMalloc(&d_shO, mp * sizeof(float4)));
-    WF_CK(cudaMalloc(&d_shD, mp * sizeof(float4)));
-    WF_CK(cudaMalloc(&d_shE, mp * sizeof(float4)));
+    for (int i = 0; i < 2; i++) {
+        WF_CK(cudaMalloc(&d_shO[i], mp * sizeof(float4)));
+        WF_CK(cudaMalloc(&d_shD[i], mp * sizeof(float4)));
+        WF_CK(cudaMalloc(&d_shE[i], mp * sizeof(float4)));
+    }
     const size_t pb = (size_t)width * height * b * sizeof(float4);
     WF_CK(cudaMalloc(&d_partial, pb));
     WF_CK(cudaMemset(d_partial, 0, pb));
+    WF_CK(cudaMalloc(&d_term, pb));
+    WF_CK(cudaMemset(d_term, 0, pb));
     wave_capacity = b;
     return cudaSuccess;
 }
@@ -129,6 +136,7 @@ static FrameParams make_params(const Wavefront& wf, const RfwCameraView3D& cam, 
     fp.wave_spp = 1; fp.npix = wf.width * wf.height;
     fp.clamp_value = wf.clamp_value;
     fp.sky[0] = wf.sky[0]; fp.sky[1] = wf.sky[1]; fp.sky[2] = wf.sky[2];
+    fp.blue_noise = wf.d_blue_noise; fp.blue_noise_n = wf.blue_noise_n;
     return fp;
 }
 
@@ -168,33 +176,52 @@ cudaError_t Wavefront::render(cudaStream_t stream, const SceneView& sv, const Sh
     WF_CK(ensure_wave(wave));
     const TraceTuning tune{refill_below, sv.two_level ? tri_batch_two_level : tri_batch, tri_blocked, inst_batch};
     stage_used = 0; stage_marks.clear();
+    // per-stage timing needs the stages one after the other: the overlap is switched off for that (diagnostic) run
+    const bool two_streams = overlap && side != nullptr && !stage_timing;
+    cudaStream_t conn = two_streams ? side : stream;
+    while (sync_events.size() < 2 * (size_t)depth + 2) {
+        cudaEvent_t e;
+        WF_CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        sync_events.push_back(e);
+    }
     WF_CK(stage_mark(stream, 4));
     for (uint32_t s = 0; s < spp; s += wave) {
         FrameParams fp = make_params(*this, cam, first_sample + s, 0);
         fp.wave_spp = std::min(wave, spp - s);
         const uint32_t cap = max_paths * fp.wave_spp;
+        if (two_streams && s > 0) WF_CK(cudaStreamWaitEvent(stream, sync_events[2 * (depth - 1) + 1], 0));  // the previous wave's last connect read the counters
         WF_CK(cudaMemsetAsync(d_counts, 0, 8 * sizeof(uint32_t), stream));
         k_wf_generate<<<(cap + 255) / 256, 256, 0, stream>>>(fp, d_owned_tiles, d_O[0], d_D[0], d_counts);
         launches++;
         WF_CK(stage_mark(stream, 0));
         for (uint32_t b = 0; b < depth; b++) {
-            const int cur = b & 1, nxt = cur ^ 1;
+            const int cur = b & 1, nxt = cur ^ 1, sb = b & 1;
             fp.path_length = b;
+            // ---- main stream: extend(b) -> shade(b) ------------------------------------------------------------------
             ExtendIO eio{d_O[cur], d_D[cur], d_counts + cur, d_S};
-            if (sv.two_level) WF_CK((launch_persistent_io<ExtendIO, false, true>(stream, sm_count, 0, tune, sv, eio, cap, d_counts + 3)));
-            else WF_CK((launch_persistent_io<ExtendIO, false, false>(stream, sm_count, 0, tune, sv, eio, cap, d_counts + 3)));
+            if (sv.two_level) WF_CK((launch_persistent_io<ExtendIO, false, true>(stream, sm_count, 0, tune, sv, eio, cap, d_counts + 4)));
+            else WF_CK((launch_persistent_io<ExtendIO, false, false>(stream, sm_count, 0, tune, sv, eio, cap, d_counts + 4)));
             WF_CK(stage_mark(stream, 1));
-            k_wf_shade<<<shade_blocks, RFW_SHADE_THREADS, 0, stream>>>(fp, ss, d_S, d_O[cur], d_D[cur], d_T[cur], d_O[nxt], d_D[nxt], d_T[nxt], d_shO, d_shD, d_shE,
-                                                         reinterpret_cast<float*>(d_partial), d_counts + cur, d_counts + nxt, d_counts + 2);
+            if (two_streams && b >= 2) WF_CK(cudaStreamWaitEvent(stream, sync_events[2 * (b - 2) + 1], 0));  // shadow queue `sb` is free again: connect(b - 2) is done
+            k_wf_shade<<<shade_blocks, RFW_SHADE_THREADS, 0, stream>>>(fp, ss, d_S, d_O[cur], d_D[cur], d_T[cur], d_O[nxt], d_D[nxt], d_T[nxt], d_shO[sb], d_shD[sb], d_shE[sb],
+                                                         d_term, d_counts + cur, d_counts + nxt, d_counts + 2 + sb);
+            k_wf_advance_paths<<<1, 1, 0, stream>>>(d_counts, d_stats, cur);
             WF_CK(stage_mark(stream, 2));
-            ConnectIO cio{d_shO, d_shD, d_shE, d_counts + 2, reinterpret_cast<float*>(d_partial)};
-            if (sv.two_level) WF_CK((launch_persistent_io<ConnectIO, true, true>(stream, sm_count, 0, tune, sv, cio, cap, d_counts + 4)));
-            else WF_CK((launch_persistent_io<ConnectIO, true, false>(stream, sm_count, 0, tune, sv, cio, cap, d_counts + 4)));
+            if (two_streams) {
+                WF_CK(cudaEventRecord(sync_events[2 * b], stream));
+                WF_CK(cudaStreamWaitEvent(conn, sync_events[2 * b], 0));
+            }
+            // ---- connect(b): beside extend(b + 1) / shade(b + 1) -------------------------------------------------------
+            ConnectIO cio{d_shO[sb], d_shD[sb], d_shE[sb], d_counts + 2 + sb, reinterpret_cast<float*>(d_partial)};
+            if (sv.two_level) WF_CK((launch_persistent_io<ConnectIO, true, true>(conn, sm_count, 0, tune, sv, cio, cap, d_counts + 5)));
+            else WF_CK((launch_persistent_io<ConnectIO, true, false>(conn, sm_count, 0, tune, sv, cio, cap, d_counts + 5)));
+            k_wf_advance_shadow<<<1, 1, 0, conn>>>(d_counts, d_stats, sb);
+            if (two_streams) WF_CK(cudaEventRecord(sync_events[2 * b + 1], conn));
             WF_CK(stage_mark(stream, 3));
-            k_wf_advance<<<1, 1, 0, stream>>>(d_counts, d_stats, cur);
-            launches += 4;
+            launches += 5;
         }
-        k_wf_reduce<<<(max_paths + 255) / 256, 256, 0, stream>>>(fp, d_owned_tiles, d_partial, d_accum);
+        if (two_streams) WF_CK(cudaStreamWaitEvent(stream, sync_events[2 * (depth - 1) + 1], 0));  // (connects are ordered among themselves: the last one covers all)
+        k_wf_reduce<<<(max_paths + 255) / 256, 256, 0, stream>>>(fp, d_owned_tiles, d_partial, d_term, d_accum);
         launches++;
         WF_CK(stage_mark(stream, 4));
     }
@@ -209,8 +236,8 @@ cudaError_t Wavefront::debug_view(cudaStream_t stream, const SceneView& sv, cons
     WF_CK(cudaMemsetAsync(d_counts, 0, 8 * sizeof(uint32_t), stream));
     k_wf_generate_centre<<<(max_paths + 255) / 256, 256, 0, stream>>>(fp, d_owned_tiles, d_O[0], d_D[0], d_counts);
     ExtendIO eio{d_O[0], d_D[0], d_counts + 0, d_S};
-    if (sv.two_level) WF_CK((launch_persistent_io<ExtendIO, false, true>(stream, sm_count, 0, tune, sv, eio, max_paths, d_counts + 3)));
-    else WF_CK((launch_persistent_io<ExtendIO, false, false>(stream, sm_count, 0, tune, sv, eio, max_paths, d_counts + 3)));
+    if (sv.two_level) WF_CK((launch_persistent_io<ExtendIO, false, true>(stream, sm_count, 0, tune, sv, eio, max_paths, d_counts + 4)));
+    else WF_CK((launch_persistent_io<ExtendIO, false, false>(stream, sm_count, 0, tune, sv, eio, max_paths, d_counts + 4)));
     k_wf_debug_view<<<sm_count * 8, 128, 0, stream>>>(fp, ss, mode, d_S, d_O[0], d_D[0], d_counts + 0, d_output);
     launches += 3;
     return cudaGetLastError();

@@ -57,13 +57,22 @@ struct Wavefront {
     float4* d_D[2] = {nullptr, nullptr};
     float4* d_T[2] = {nullptr, nullptr};
     float4* d_S = nullptr;               // hit state: inst, prim, t, packed bary
-    float4* d_shO = nullptr;             // shadow queue
-    float4* d_shD = nullptr;
-    float4* d_shE = nullptr;
-    float4* d_partial = nullptr;         // per-sample partial accumulators of the current wave: wave_capacity * width*height
+    float4* d_shO[2] = {nullptr, nullptr};  // shadow queues, double-buffered by bounce parity: connect(b) runs beside extend(b + 1) / shade(b + 1)
+    float4* d_shD[2] = {nullptr, nullptr};
+    float4* d_shE[2] = {nullptr, nullptr};
+    float4* d_partial = nullptr;         // per-sample partial accumulators of the current wave (connect stage, atomics): wave_capacity * width*height
+    float4* d_term = nullptr;            // per-sample terminal accumulators (shade stage: one plain store per slot), same shape
     float4* d_accum = nullptr;           // width*height
     float4* d_output = nullptr;          // width*height
-    uint32_t* d_counts = nullptr;        // [0],[1] path counts (ping/pong), [2] shadow count, [3..5] work counters
+    uint32_t* d_counts = nullptr;        // [0],[1] path counts (ping/pong), [2],[3] shadow counts (bounce parity), [4],[5] work counters (extend, connect), [6] debug
+    // Second stream for the connect stage: connect(b) only reads the shadow queue shade(b) wrote and adds into the partial
+    // accumulators, so it runs BESIDE extend(b + 1) / shade(b + 1) of the main stream instead of between them — the tail of
+    // one persistent launch (a few long rays keep a handful of warps busy) is filled by the other kernel's body.
+    cudaStream_t side = nullptr;         // created by the owner (Backend); nullptr = everything on the main stream
+    bool overlap = true;                 // option "wf_overlap"
+    std::vector<cudaEvent_t> sync_events;  // [2 b] shade(b) done, [2 b + 1] connect(b) done
+    uint32_t* d_blue_noise = nullptr;    // blue-noise sampler tables (owned by Backend, rfwb200_set_blue_noise); nullptr = hash RNG
+    uint32_t blue_noise_n = 0;
     unsigned long long* d_stats = nullptr;  // [0] extension rays, [1] shadow rays, [2] segments(shaded)
     std::vector<uint32_t> morton_tiles;
     int sm_count = 148;

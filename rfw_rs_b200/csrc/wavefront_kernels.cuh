@@ -109,7 +109,7 @@ struct ConnectIO {
 #endif
 __global__ void __launch_bounds__(RFW_SHADE_THREADS, RFW_SHADE_MIN_BLOCKS) k_wf_shade(FrameParams fp, ShadeScene ss, const float4* __restrict__ S, const float4* __restrict__ O, const float4* __restrict__ D,
                                                   const float4* __restrict__ T, float4* __restrict__ On, float4* __restrict__ Dn, float4* __restrict__ Tn,
-                                                  float4* __restrict__ shO, float4* __restrict__ shD, float4* __restrict__ shE, float* __restrict__ accum,
+                                                  float4* __restrict__ shO, float4* __restrict__ shD, float4* __restrict__ shE, float4* __restrict__ term,
                                                   const uint32_t* __restrict__ count_cur, uint32_t* __restrict__ count_next, uint32_t* __restrict__ count_shadow) {
     const uint32_t count = *count_cur;
     const int lane = threadIdx.x & 31;
@@ -138,8 +138,12 @@ __global__ void __launch_bounds__(RFW_SHADE_THREADS, RFW_SHADE_MIN_BLOCKS) k_wf_
             pixel = __float_as_uint(o4.w);
             wave_b = __float_as_uint(d4.w);
             shade_path(fp, ss, lightCount, s4, o4, d4, t4, so);
+            // A path adds radiance in the shade stage exactly once — when it ends on a miss or on a light (shade_path) — and a
+            // (sample, pixel) slot has exactly one path: a plain store into the slot's TERMINAL accumulator, no atomic.  (The
+            // connect stage's contributions go to the partial accumulators with atomics; keeping the two apart also makes the
+            // sum independent of how connect(b) and shade(b + 1) overlap in time: Wavefront::render runs them concurrently.)
             if (so.add && (so.contrib.x != 0.0f || so.contrib.y != 0.0f || so.contrib.z != 0.0f)) {
-                red_add_rgb(accum + 4 * ((size_t)wave_b * fp.npix + pixel), so.contrib.x, so.contrib.y, so.contrib.z);
+                term[(size_t)wave_b * fp.npix + pixel] = f4(so.contrib.x, so.contrib.y, so.contrib.z, 0.0f);
             }
         }
         const bool emit_ext = so.emit_ext, emit_sh = so.emit_sh;
@@ -227,41 +231,48 @@ __global__ void __launch_bounds__(256) k_wf_generate_centre(FrameParams fp, cons
     }
 }
 
-// bookkeeping between bounces: stats += counts, retire the consumed queues
-__global__ void k_wf_advance(uint32_t* counts, unsigned long long* stats, int cur) {
+// bookkeeping between bounces: stats += counts, retire the consumed queues.  counts: [0], [1] path queues (ping / pong),
+// [2], [3] shadow queues (even / odd bounce), [4] extend work counter, [5] connect work counter, [6] debug
+__global__ void k_wf_advance_paths(uint32_t* counts, unsigned long long* stats, int cur) {  // after shade(b): the path queue it consumed
     stats[0] += counts[cur];
-    stats[1] += counts[2];
     stats[2] += counts[cur];
-    counts[5] = counts[cur];  // debug: size of the queue the last extend/shade consumed
+    counts[6] = counts[cur];  // debug: size of the queue the last extend/shade consumed
     counts[cur] = 0;
-    counts[2] = 0;
+}
+__global__ void k_wf_advance_shadow(uint32_t* counts, unsigned long long* stats, int sb) {  // after connect(b): the shadow queue it consumed
+    stats[1] += counts[2 + sb];
+    counts[2 + sb] = 0;
 }
 
-// fold the wave's per-sample partial accumulators into the frame accumulator in SAMPLE ORDER (the image is then
-// independent of how many samples a wave carried and of the atomics' arrival order) and re-zero them for the next wave
-__global__ void __launch_bounds__(256) k_wf_reduce(FrameParams fp, const uint32_t* __restrict__ owned_tiles, float4* __restrict__ partial, float4* __restrict__ accum) {
+// fold the wave's per-sample accumulators (partial: connect stage, atomics; term: shade stage, one store per slot) into the
+// frame accumulator in SAMPLE ORDER (the image is then independent of how many samples a wave carried and of the atomics'
+// arrival order) and re-zero them for the next wave
+__global__ void __launch_bounds__(256) k_wf_reduce(FrameParams fp, const uint32_t* __restrict__ owned_tiles, float4* __restrict__ partial, float4* __restrict__ term,
+                                                   float4* __restrict__ accum) {
     const uint32_t slot = blockIdx.x * 256 + threadIdx.x;
     uint32_t pixel;
     if (slot >= fp.max_paths || !slot_to_pixel(fp, owned_tiles, slot, pixel)) return;
     float4 a = accum[pixel];
-    // eight samples' loads in flight per thread, then the adds in SAMPLE ORDER (one load -> add -> store round per sample cost a
-    // full memory latency each: 1.0 ms for the 16-sample wave of a 1080p frame)
+    // four samples' loads (2 buffers each) in flight per thread, then the adds in SAMPLE ORDER (one load -> add -> store round per
+    // sample cost a full memory latency each)
     uint32_t b = 0;
-    for (; b + 8 <= fp.wave_spp; b += 8) {
+    for (; b + 4 <= fp.wave_spp; b += 4) {
         float4* p = partial + (size_t)b * fp.npix + pixel;
-        float4 v[8];
+        float4* q = term + (size_t)b * fp.npix + pixel;
+        float4 v[4], t[4];
 #pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = __ldcs(p + (size_t)k * fp.npix);
+        for (int k = 0; k < 4; k++) { v[k] = __ldcs(p + (size_t)k * fp.npix); t[k] = __ldcs(q + (size_t)k * fp.npix); }
 #pragma unroll
-        for (int k = 0; k < 8; k++) { a.x += v[k].x; a.y += v[k].y; a.z += v[k].z; a.w += v[k].w; }
+        for (int k = 0; k < 4; k++) { a.x += v[k].x + t[k].x; a.y += v[k].y + t[k].y; a.z += v[k].z + t[k].z; a.w += v[k].w + t[k].w; }
 #pragma unroll
-        for (int k = 0; k < 8; k++) p[(size_t)k * fp.npix] = f4(0, 0, 0, 0);
+        for (int k = 0; k < 4; k++) { p[(size_t)k * fp.npix] = f4(0, 0, 0, 0); q[(size_t)k * fp.npix] = f4(0, 0, 0, 0); }
     }
     for (; b < fp.wave_spp; b++) {
         float4* p = partial + (size_t)b * fp.npix + pixel;
-        const float4 v = *p;
-        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-        *p = f4(0, 0, 0, 0);
+        float4* q = term + (size_t)b * fp.npix + pixel;
+        const float4 v = *p, t = *q;
+        a.x += v.x + t.x; a.y += v.y + t.y; a.z += v.z + t.z; a.w += v.w + t.w;
+        *p = f4(0, 0, 0, 0); *q = f4(0, 0, 0, 0);
     }
     accum[pixel] = a;
 }

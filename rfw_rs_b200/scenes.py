@@ -477,6 +477,22 @@ def soup_with_lights(n, s, n_lights=256, seed=SEED_SCENE, light_area=1e-2, radiu
     return sc
 
 
+def c5_scene(n_tris=10_000_000):
+    """BASELINE.json configs[4] (SURVEY §8d C5): soup of `n_tris` triangles (s = 0.002) + ground quad + 64 area-light triangles;
+    rendered at 3840x2160, 64 spp, depth 5 from `c5_view`."""
+    desc = soup_with_lights(n_tris, 0.002, n_lights=64, light_area=2e-2, radius=2.0)
+    g = quad((0.5, -0.2, 0.5), (0, 1, 0), 6.0, 6.0, mat_id=0)
+    if g["normal"][0, 1] < 0:
+        g = make_triangles(g["vertex0"], g["vertex2"], g["vertex1"], 0)
+    desc.meshes[2] = g
+    desc.instances[2] = to_column_major([identity()])
+    return desc
+
+
+def c5_view(w=3840, h=2160):
+    return camera_view((0.5, 0.9, -2.2), (0.0, -0.15, 1.0), w, h)
+
+
 def textured_scene(grid=4, subdiv=2, seed=SEED_SCENE, tex_size=64, skybox=True):
     """(f)1 flavour: a ground quad with a diffuse map + normal map, spheres with a diffuse map (one BGRA8, one RGBA8
     texture), plain GGX spheres, two emissive quads and an equirect skybox."""

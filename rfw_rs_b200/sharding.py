@@ -1,8 +1,8 @@
 """Host-side plumbing of the multi-GPU path: one process per GPU, scene replicated, work sharded, ONE collective.
 
 Path tracing shards by image tile (64x64, Morton order, tile k -> rank k mod n); ray batches shard
-by contiguous range.  The only collective is the final accumulator gather (`torch.distributed.all_gather_into_tensor`
-over NCCL on the GPU box, gloo in the CPU tests).  The tile layout itself comes from the library
+by contiguous range.  The only collective is the final accumulator gather: NCCL inside librfwb200 (`rfwb200_comm_init` /
+`rfwb200_gather_image`); the CPU tests exercise the same tile layout with gloo and the numpy mirror `assemble_host`.  The tile layout itself comes from the library
 (`rfwb200_tile_layout`, host-only) so this file, the export kernel and the assemble kernel cannot disagree.
 """
 import numpy as np
@@ -50,13 +50,18 @@ def assemble_host(gathered, width, height, tile, world, tiles_per_rank_):
     return img
 
 
-def gather_image(be, dist, torch, width, height, tile, world):
-    """Device-side gather used by bench.py: export this rank's tiles, all_gather, assemble + sqrt(acc/spp) on the device."""
-    tpr = be.tiles_per_rank
-    send = torch.zeros(tpr * tile * tile * 4, dtype=torch.float32, device="cuda")
-    recv = torch.empty(world * tpr * tile * tile * 4, dtype=torch.float32, device="cuda")
-    image = torch.empty(height * width * 4, dtype=torch.float32, device="cuda")
-    be.export_tiles_device(send.data_ptr(), tpr)
-    dist.all_gather_into_tensor(recv, send)
-    be.assemble_tiles_device(recv.data_ptr(), tpr, world, image.data_ptr())
-    return image.view(height, width, 4)
+def broadcast_unique_id(dist, torch, rank):
+    """Distributes rank 0's ncclGetUniqueId bytes over an existing torch.distributed group (any backend): the bootstrap of the
+    library's own communicator.  A host without torch distributes the 128 bytes by any other means (tests/multi_gpu_worker.py
+    uses a file)."""
+    uid = backend.B200Backend.comm_unique_id() if rank == 0 else bytes(128)
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor(list(uid), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=0)
+    return bytes(t.cpu().tolist())
+
+
+def gather_image(be, root=0, d_image_ptr=None):
+    """The frame's one collective, inside the library: rfwb200_gather_image (export tiles -> NCCL -> de-tile + sqrt(acc / spp)),
+    all on the backend's own stream.  The receiver's image lands in its output buffer (be.read_output()) or in d_image_ptr."""
+    be.gather_image(root, d_image_ptr)

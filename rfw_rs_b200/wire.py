@@ -125,7 +125,8 @@ class CTraceStats(C.Structure):
 
 class CRenderStats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("extension_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("segments", C.c_uint64), ("render_ms", C.c_float),
-                ("stage_ms", C.c_float * 5), ("stage_timing", C.c_uint32), ("stack_overflows", C.c_uint32)]
+                ("stage_ms", C.c_float * 5), ("stage_timing", C.c_uint32), ("stack_overflows", C.c_uint32),
+                ("gather_ms", C.c_float), ("frame_ms", C.c_float)]
 
 
 def stats_to_dict(s):

@@ -4,7 +4,7 @@
   C1  primary-ray closest hit of the glTF assets (fixtures in tests/golden) at 1280x720, variants C1a / C1b
   C4  5M-triangle soup + 256 emissive triangles: closest hits of 2^24 rays, then one NEE any-hit ray per hit
   C5  3840x2160, 64 spp, depth 5, 10M-triangle soup + ground + 64 area lights, tile-sharded over the ranks
-      (launch with torchrun for N > 1; the final gather is one NCCL all_gather)
+      (launch with torchrun for N > 1; the final gather is rfwb200_gather_image: NCCL inside the library)
 
 usage: python scripts/run_configs.py --configs c1,c4,c5 [--c5-spp 64] [--c5-tris 10000000]
 """
@@ -102,16 +102,13 @@ def run_c4(out, n_tris, n_rays):
 
 def run_c5(out, n_tris, spp, rank, world, dist):
     w, h, depth, tile = 3840, 2160, 5, 64
-    desc = scenes.soup_with_lights(n_tris, 0.002, n_lights=64, light_area=2e-2, radius=2.0)
-    g = scenes.quad((0.5, -0.2, 0.5), (0, 1, 0), 6.0, 6.0, mat_id=0)
-    if g["normal"][0, 1] < 0:
-        g = scenes.make_triangles(g["vertex0"], g["vertex2"], g["vertex1"], 0)
-    desc.meshes[2] = g
-    desc.instances[2] = scenes.to_column_major([scenes.identity()])
+    desc = scenes.c5_scene(n_tris)
     be = backend.B200Backend(w, h, device=torch.cuda.current_device(), tile_size=tile, rank=rank, world=world, sky=(0.3, 0.35, 0.5))
     t0 = time.time(); desc.apply(be); sync_ms = (time.time() - t0) * 1e3
     bs = be.build_stats()
-    view = scenes.camera_view((0.5, 0.9, -2.2), (0.0, -0.15, 1.0), w, h)
+    view = scenes.c5_view(w, h)
+    if dist is not None:
+        be.comm_init(sharding.broadcast_unique_id(dist, torch, rank), rank, world)
     be.render_spp(view, 1, depth)
     be.reset_accumulator()
     if dist is not None:
@@ -128,12 +125,10 @@ def run_c5(out, n_tris, spp, rank, world, dist):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot)
         dist.all_reduce(cs_min, op=dist.ReduceOp.MIN); dist.all_reduce(cs_max, op=dist.ReduceOp.MAX)
-        sharding.gather_image(be, dist, torch, w, h, tile, world)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize(); e0.record()
-        img = sharding.gather_image(be, dist, torch, w, h, tile, world)
-        e1.record(); torch.cuda.synchronize()
-        gather_ms = e0.elapsed_time(e1)
+        be.gather_image(0)  # warm-up of the communicator and the buffers
+        dist.barrier()
+        be.gather_image(0)  # export tiles -> NCCL gather to rank 0 -> assemble + sqrt(acc/spp), inside librfwb200
+        gather_ms = be.render_stats()["gather_ms"]
     if rank == 0:
         t_s = ms.item() / 1e3
         out({"config": "C5", "n_gpus": world, "triangles": int(bs["num_triangles"]), "resolution": [w, h], "spp": spp, "depth": depth,

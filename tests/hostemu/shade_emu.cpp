@@ -58,6 +58,11 @@ void emu_sample_texture(const uint8_t* rgba, uint32_t w, uint32_t h, uint32_t mi
 // The product's path tracer run serially on the CPU: eye_ray -> { trace_ray (closest) -> shade_path -> trace_ray (any-hit) } x depth,
 // i.e. what Wavefront::render does with its queues (wavefront.cu), one path at a time.  Per-sample contributions are summed
 // in stage order and the samples folded in sample order, as k_wf_reduce does.  acc: h*w*4 floats, accumulated into.
+// sampler tables for the next emu_render calls (rfwb200_set_blue_noise of the product); nullptr / 0 = hash RNG
+static const uint32_t* g_blue_noise = nullptr;
+static uint32_t g_blue_noise_n = 0;
+void emu_set_blue_noise(const uint32_t* table, uint32_t n) { g_blue_noise = n ? table : nullptr; g_blue_noise_n = n; }
+float emu_blue_noise_sample(int x, int y, int dim, uint32_t sample_count) { return blue_noise_sample(g_blue_noise, g_blue_noise_n, x, y, dim, sample_count); }
 void emu_render(const SceneView* sv, const InstanceShading* inst_table, const RfwDeviceMaterial* mats, uint32_t n_mats, const RfwAreaLight* area, uint32_t na,
                 const RfwPointLight* point, uint32_t np, const RfwSpotLight* spot, uint32_t ns, const RfwDirectionalLight* dir, uint32_t nd, const RfwCameraView3D* cam,
                 uint32_t w, uint32_t h, uint32_t first_sample, uint32_t spp, uint32_t depth, float clamp_value, const float* sky, float* acc, uint64_t* stats,
@@ -74,6 +79,7 @@ void emu_render(const SceneView* sv, const InstanceShading* inst_table, const Rf
     memset(&fp, 0, sizeof(fp));
     fp.cam = *cam; fp.width = w; fp.height = h; fp.npix = w * h; fp.sample = first_sample; fp.wave_spp = spp;
     fp.clamp_value = clamp_value; fp.sky[0] = sky[0]; fp.sky[1] = sky[1]; fp.sky[2] = sky[2];
+    fp.blue_noise = g_blue_noise; fp.blue_noise_n = g_blue_noise_n;
     uint64_t n_ext = 0, n_sh = 0;
     for (uint32_t pixel = 0; pixel < w * h; pixel++) {
         for (uint32_t b = 0; b < spp; b++) {

@@ -34,7 +34,7 @@ struct HostRayIO {
     void publish(uint32_t, int) const {}
 };
 
-template <bool ANY, bool TWO_LEVEL, class IO>
+template <bool ANY, bool TWO_LEVEL, class IO, int SM_STACK = PT_SM_STACK, int L_STACK = PT_L_STACK>
 static int run_cta(const SceneView& sv, const IO& io, TraceTuning tune, int warps) {
     rfw_host_smem = g_smem;
     if (persistent_smem_bytes<TWO_LEVEL>() > sizeof(g_smem)) return -2;
@@ -47,7 +47,7 @@ static int run_cta(const SceneView& sv, const IO& io, TraceTuning tune, int warp
         threads.emplace_back([&, t]() {
             tls_threadIdx = {(unsigned)t, 0, 0}; tls_blockIdx = {0, 0, 0};
             tls_warp = &ctx[t / 32]; tls_lane = t % 32;
-            k_trace_persistent<IO, ANY, TWO_LEVEL, PT_THREADS, 8, PT_SM_STACK>(sv, io, &counter, tune);
+            k_trace_persistent<IO, ANY, TWO_LEVEL, PT_THREADS, 8, SM_STACK, L_STACK>(sv, io, &counter, tune);
         });
     }
     for (auto& th : threads) th.join();
@@ -55,6 +55,14 @@ static int run_cta(const SceneView& sv, const IO& io, TraceTuning tune, int warp
 }
 
 extern "C" {
+// the 2 + 2 entry stack build of the kernel (the product's option trace_variant 3): *overflowed != 0 when a push was dropped
+int simt_trace_tiny_stack(const void* scene_view, const RfwRay* rays, uint32_t n, RfwHit* hits, uint32_t* overflowed) {
+    SceneView sv = *reinterpret_cast<const SceneView*>(scene_view);
+    sv.overflow = overflowed;
+    const HostRayIO io{reinterpret_cast<const float4*>(rays), n, hits, nullptr};
+    const TraceTuning tune{28, 4, 4, 6};
+    return sv.two_level ? run_cta<false, true, HostRayIO, 2, 2>(sv, io, tune, PT_THREADS / 32) : run_cta<false, false, HostRayIO, 2, 2>(sv, io, tune, PT_THREADS / 32);
+}
 // runs the persistent kernel on one CTA of 4 warps.  Returns 0, -1 on a hang (a lane missed a warp collective), -2 on bad set-up.
 int simt_trace(const void* scene_view, const RfwRay* rays, uint32_t n, RfwHit* hits, uint32_t* occluded, int any_hit, int refill_below, int tri_batch, int inst_batch) {
     const SceneView& sv = *reinterpret_cast<const SceneView*>(scene_view);

@@ -42,28 +42,38 @@ int wf_render(const void* scene_view, const InstanceShading* inst_table, const R
     fp.sample = first_sample; fp.path_length = 0; fp.wave_spp = spp; fp.npix = w * h;
     fp.clamp_value = clamp_value; fp.sky[0] = sky[0]; fp.sky[1] = sky[1]; fp.sky[2] = sky[2];
     const uint32_t cap = fp.max_paths * spp;
-    std::vector<float4> O[2], D[2], T[2], S(cap), shO(cap), shD(cap), shE(cap), partial((size_t)fp.npix * spp, f4(0, 0, 0, 0));
-    for (int i = 0; i < 2; i++) { O[i].resize(cap); D[i].resize(cap); T[i].resize(cap); }
+    std::vector<float4> O[2], D[2], T[2], S(cap), shO[2], shD[2], shE[2], partial((size_t)fp.npix * spp, f4(0, 0, 0, 0)), term((size_t)fp.npix * spp, f4(0, 0, 0, 0));
+    for (int i = 0; i < 2; i++) { O[i].resize(cap); D[i].resize(cap); T[i].resize(cap); shO[i].resize(cap); shD[i].resize(cap); shE[i].resize(cap); }
     uint32_t counts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     unsigned long long st[4] = {0, 0, 0, 0};
     const TraceTuning tune{28, sv.two_level ? 4 : 4, 4, 6};
     g_abort.store(false);
     // generate
     if (!simt_launch((cap + 255) / 256, 256, [&]() { k_wf_generate(fp, owned_tiles, O[0].data(), D[0].data(), counts); })) return -1;
+    // Wavefront::render's launch order; connect(b) is issued on a second stream there (beside extend(b + 1) / shade(b + 1)) and
+    // runs here at the LATEST point its dependencies allow — after shade(b + 1), right before shade(b + 2) re-uses its shadow
+    // queue — so the serial schedule exercises the double buffering the concurrent one relies on
+    auto connect = [&](uint32_t b) -> bool {
+        const int sb = (int)(b & 1u);
+        const ConnectIO cio{shO[sb].data(), shD[sb].data(), shE[sb].data(), counts + 2 + sb, reinterpret_cast<float*>(partial.data())};
+        if (!run_trace<ConnectIO, true>(sv, cio, counts + 5, tune)) return false;
+        return simt_launch(1, 1, [&]() { k_wf_advance_shadow(counts, st, sb); });
+    };
     for (uint32_t b = 0; b < depth; b++) {
-        const int cur = (int)(b & 1u), nxt = cur ^ 1;
+        const int cur = (int)(b & 1u), nxt = cur ^ 1, sb = (int)(b & 1u);
         fp.path_length = b;
         const ExtendIO eio{O[cur].data(), D[cur].data(), counts + cur, S.data()};
-        if (!run_trace<ExtendIO, false>(sv, eio, counts + 3, tune)) return -1;
+        if (!run_trace<ExtendIO, false>(sv, eio, counts + 4, tune)) return -1;
+        if (b >= 2 && !connect(b - 2)) return -1;
         if (!simt_launch((unsigned)shade_ctas, RFW_SHADE_THREADS, [&]() {
-                k_wf_shade(fp, ss, S.data(), O[cur].data(), D[cur].data(), T[cur].data(), O[nxt].data(), D[nxt].data(), T[nxt].data(), shO.data(), shD.data(), shE.data(),
-                           reinterpret_cast<float*>(partial.data()), counts + cur, counts + nxt, counts + 2);
+                k_wf_shade(fp, ss, S.data(), O[cur].data(), D[cur].data(), T[cur].data(), O[nxt].data(), D[nxt].data(), T[nxt].data(), shO[sb].data(), shD[sb].data(), shE[sb].data(),
+                           term.data(), counts + cur, counts + nxt, counts + 2 + sb);
             })) return -1;
-        const ConnectIO cio{shO.data(), shD.data(), shE.data(), counts + 2, reinterpret_cast<float*>(partial.data())};
-        if (!run_trace<ConnectIO, true>(sv, cio, counts + 4, tune)) return -1;
-        if (!simt_launch(1, 1, [&]() { k_wf_advance(counts, st, cur); })) return -1;
+        if (!simt_launch(1, 1, [&]() { k_wf_advance_paths(counts, st, cur); })) return -1;
     }
-    if (!simt_launch((fp.max_paths + 255) / 256, 256, [&]() { k_wf_reduce(fp, owned_tiles, partial.data(), reinterpret_cast<float4*>(acc)); })) return -1;
+    for (uint32_t b = depth >= 2 ? depth - 2 : 0; b < depth; b++)
+        if (!connect(b)) return -1;
+    if (!simt_launch((fp.max_paths + 255) / 256, 256, [&]() { k_wf_reduce(fp, owned_tiles, partial.data(), term.data(), reinterpret_cast<float4*>(acc)); })) return -1;
     if (stats) { stats[0] = st[0]; stats[1] = st[1]; }
     return 0;
 }

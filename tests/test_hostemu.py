@@ -3,6 +3,7 @@ compiled for the host by tests/hostemu, against the oracle.  Not a product path:
 import ctypes as C
 import os
 import subprocess
+import time
 
 import numpy as np
 import pytest
@@ -641,6 +642,37 @@ def test_persistent_kernel_schedule_on_the_cpu(emu, simt, two_level, knobs):
         assert np.array_equal(occ, ref_occ)
         if n > 100:
             assert (ref_hits["inst"] >= 0).mean() > 0.1
+
+
+@pytest.mark.parametrize("two_level", [False, True])
+def test_tiny_stack_kernel_terminates_and_flags_the_overflow(emu, simt, two_level):
+    """The 2 + 2 entry stack build of k_trace_persistent (the product's option trace_variant 3) on the lane-thread harness: a push
+    that finds the stack full is dropped whole, so every ray still ends after finitely many steps (the build that counted the
+    dropped entry re-walked subtrees exponentially and hung the GPU test), the overflow word is set, and what is lost is only
+    subtrees: a stored hit is either the true closest hit or a farther one / a miss — never closer, never a fabricated id."""
+    simt.simt_trace_tiny_stack.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    simt.simt_trace_tiny_stack.restype = C.c_int
+    desc = scenes.instanced_scene(grid=8, subdiv=2, n_lights=4) if two_level else scenes.soup_scene(60000, 0.03)
+    e = Emu(emu, desc)
+    emu.emu_scene_view.restype = C.c_void_p; emu.emu_scene_view.argtypes = [C.c_void_p]
+    sv = emu.emu_scene_view(e.h)
+    n = 1500
+    rays = scenes.random_rays(n, seed=3, lo=-3.0, hi=3.0) if two_level else scenes.random_rays(n, seed=3)
+    if two_level:
+        rays["origin"][:, 1] = np.abs(rays["origin"][:, 1]) * 0.4 + 0.05
+    ref_hits, _, _ = e.trace(rays)
+    hits = np.zeros(n, wire.HIT); hits["prim"] = -7
+    flag = np.zeros(1, np.uint32)
+    t0 = time.perf_counter()
+    assert simt.simt_trace_tiny_stack(sv, rays.ctypes.data, n, hits.ctypes.data, flag.ctypes.data) == 0
+    assert time.perf_counter() - t0 < 20.0
+    assert flag[0] != 0
+    assert (hits["prim"] != -7).all()                                   # every ray retired
+    same = hits.view(np.uint8).reshape(n, -1) == ref_hits.view(np.uint8).reshape(n, -1)
+    same = same.all(axis=1)
+    assert 0.2 < same.mean() < 1.0                                      # some subtrees were lost — and not everything
+    assert (hits["t"][~same] >= ref_hits["t"][~same]).all()
+    assert (ref_hits["inst"][~same] >= 0).all()                         # a ray that truly misses cannot gain a hit
 
 
 @pytest.mark.parametrize("two_level", [False, True])

@@ -365,3 +365,93 @@ def test_rendered_image_matches_the_reference_kernels(ref, oracle_mod, which):
     assert rel.max() <= 2e-2
     # blit.comp: sqrt(acc / (sample_count + 1)) with the sample index of the last frame
     assert np.allclose(img_r[..., :3][~bad], np.sqrt(acc_r[..., :3] / (256 + spp))[~bad], rtol=1e-6, atol=1e-7)
+
+
+# ---- the blue-noise sampler of the first 256 samples -------------------------------------------------------------------------
+def reference_blue_noise_table():
+    """The u32 buffer create_blue_noise_buffer() builds (backends/gpu-rt/src/blue_noise.rs:40970-41004) from the three u64 tables of
+    that file, reproduced from the DATA where it lies: each table is viewed as bytes, and only the first len * size_of::<u32>()
+    bytes of it are used (the function's own slice length), repeated to fill the region.  None when /root/reference is absent."""
+    path = "/root/reference/backends/gpu-rt/src/blue_noise.rs"
+    if not os.path.exists(path):
+        return None
+    import re
+
+    text = open(path).read()
+    tables = {}
+    for name, n in (("SOB256_64", 8192), ("SCR256_64", 16384), ("RNK256_64", 16384)):
+        body = text[text.index(f"static {name}: [u64; {n}] = ["):]
+        body = body[body.index("= [") + 3:body.index("];")]
+        vals = np.array([int(v, 16) for v in re.findall(r"0x[0-9a-fA-F]+", body)], dtype=np.uint64)
+        assert len(vals) == n, (name, len(vals))
+        tables[name] = vals.view(np.uint8)[: n * 4]   # from_raw_parts(ptr as *const u8, len * size_of::<u32>())
+    buf = np.zeros(65536 * 5, np.uint32)
+    buf[:65536] = tables["SOB256_64"][np.arange(65536) % len(tables["SOB256_64"])]
+    k = np.arange(128 * 128 * 8)
+    buf[65536:65536 + len(k)] = tables["SCR256_64"][k % len(tables["SCR256_64"])]
+    buf[3 * 65536:3 * 65536 + len(k)] = tables["RNK256_64"][k % len(tables["RNK256_64"])]
+    return buf
+
+
+def synthetic_blue_noise_table(seed=77):
+    """A table of the same shape with seeded random bytes: what the GPU-tier tests use (the real table is reference data and
+    is not copied into the repository); the sampler's index arithmetic is exercised all the same."""
+    return np.random.default_rng(seed).integers(0, 256, 65536 * 5).astype(np.uint32)
+
+
+@pytest.mark.parametrize("table", ["reference", "synthetic"])
+def test_blue_noise_sampler_matches_the_reference(ref, oracle_mod, shade_emu_lib, table):
+    """blueNoiseSampler (ray_gen.comp:72-91) for every dimension a depth-5 path uses, all 128 x 128 pixels' corners and random
+    ones, sample counts 0..255: reference shader == oracle == the product's shade_path.cuh body, bit for bit."""
+    bn = reference_blue_noise_table() if table == "reference" else synthetic_blue_noise_table()
+    if bn is None:
+        pytest.skip("/root/reference absent")
+    L, O, E = ref.lib(), oracle_mod.lib(), shade_emu_lib
+    o = oracle_mod.OracleBackend(); o.set_blue_noise(bn)
+    bn_i32 = np.ascontiguousarray(bn.astype(np.int32))  # (kept alive across the call: _vp only carries the address)
+    L.ref_set_blue_noise(_vp(bn_i32), len(bn_i32))
+    E.emu_set_blue_noise.argtypes = [C.c_void_p, C.c_uint32]
+    E.emu_blue_noise_sample.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint32]; E.emu_blue_noise_sample.restype = C.c_float
+    O.orc_blue_noise_sample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32]; O.orc_blue_noise_sample.restype = C.c_float
+    keep = np.ascontiguousarray(bn)
+    E.emu_set_blue_noise(_vp(keep), len(keep))
+    rng = np.random.default_rng(5)
+    pts = [(0, 0), (127, 127), (127, 0), (0, 127), (128, 129), (1919, 1079)] + [tuple(int(v) for v in rng.integers(0, 4096, 2)) for _ in range(300)]
+    seen = set()
+    for (x, y) in pts:
+        for dim in list(range(24)) + [255, 256, 300]:
+            for sc in (0, 1, 17, 128, 254, 255):
+                a = L.ref_blue_noise_sample(x, y, dim, sc)
+                b = O.orc_blue_noise_sample(o.h, x, y, dim, sc)
+                c = E.emu_blue_noise_sample(x, y, dim, sc)
+                assert a == b == c, (x, y, dim, sc, a, b, c)
+                seen.add(a)
+    assert len(seen) > 200 and all(0.0 < v < 1.0 for v in seen)
+    E.emu_set_blue_noise(None, 0)
+
+
+@pytest.mark.parametrize("table", ["reference", "synthetic"])
+def test_blue_noise_frames_match_the_reference_kernels(ref, oracle_mod, table):
+    """Frames 0..3 (sample_count < 256: the blue-noise branch of ray_gen.comp:109-115 and shade.comp:190-196,216-222) rendered by
+    the reference's kernels against the oracle with the same tables — and a frame straddling sample 256, where both switch to
+    the hash RNG."""
+    bn = reference_blue_noise_table() if table == "reference" else synthetic_blue_noise_table()
+    if bn is None:
+        pytest.skip("/root/reference absent")
+    w, h, depth = 96, 54, 3
+    desc = scenes.instanced_scene(grid=6, subdiv=1, n_lights=4)
+    view = scenes.camera_view((0, 3.0, -7.0), (0, -0.4, 1.0), w, h)
+    rb = ref.RefBackend(); desc.apply(rb); rb.set_blue_noise(bn.astype(np.int32))
+    o = oracle_mod.OracleBackend(det_eps=1e-4); desc.apply(o); o.set_blue_noise(bn)
+    hashed, _ = oracle_mod.OracleBackend(det_eps=1e-4), None
+    for first, spp in ((0, 4), (254, 4)):
+        acc_r, _, ctr = rb.render(view, w, h, spp, depth=depth, first_sample=first, acc=np.zeros((h, w, 4), np.float32))
+        acc_o, st = o.render(view, w, h, spp, depth, sky=(0.0, 0.0, 0.0), first_sample=first)
+        assert ctr["extension_rays"] == st["extension_rays"] and ctr["shadow_rays"] == st["shadow_rays"], (first, ctr, st)
+        d = (acc_r[..., :3] - acc_o[..., :3]).astype(np.float64) / spp
+        assert float(np.sqrt(np.mean(d ** 2))) <= 2e-5, (first, float(np.sqrt(np.mean(d ** 2))))
+    # and the tables do change the image (the test would pass vacuously if neither side used them)
+    o2 = oracle_mod.OracleBackend(det_eps=1e-4); desc.apply(o2)
+    acc_h, _ = o2.render(view, w, h, 4, depth, sky=(0.0, 0.0, 0.0), first_sample=0)
+    acc_b, _ = o.render(view, w, h, 4, depth, sky=(0.0, 0.0, 0.0), first_sample=0)
+    assert float(np.abs(acc_h - acc_b).mean()) > 1e-2
