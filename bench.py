@@ -248,10 +248,11 @@ def _ranks_ok(err, torch, dist):
     return ok.item() == 1
 
 
-def path_tracing_block(backend_mod, scenes, sharding, torch, rank, world, dist, uid, frames, n_tris, spp):
+def path_tracing_block(backend_mod, scenes, sharding, torch, rank, world, dist, frames, n_tris, spp):
     """C5 (BASELINE.json configs[4]): tile-sharded path tracing, strong scaling; the gather is inside the timed region."""
     w, h, depth, tile = 3840, 2160, 5, 64
     err, be = None, None
+    uid = sharding.broadcast_unique_id(dist, torch, rank) if dist is not None else None   # (an NCCL id serves ONE communicator)
     try:
         desc = scenes.c5_scene(n_tris)
         be = backend_mod.B200Backend(w, h, device=torch.cuda.current_device(), tile_size=tile, rank=rank, world=world, sky=(0.3, 0.35, 0.5))
@@ -291,10 +292,11 @@ def path_tracing_block(backend_mod, scenes, sharding, torch, rank, world, dist, 
     }
 
 
-def path_tracing_extra(backend_mod, scenes, torch, rank, world, spp, dist, uid):
+def path_tracing_extra(backend_mod, scenes, sharding, torch, rank, world, spp, dist):
     """C3: 10k-instance scene, 1920x1080, `spp` spp, depth 5 — tile-sharded over the ranks, gather inside the frame time."""
     w, h, depth, tile = 1920, 1080, 5, 64
     err, be = None, None
+    uid = sharding.broadcast_unique_id(dist, torch, rank) if dist is not None else None
     try:  # the rank-local part first; a failure here must not leave the other ranks waiting in a collective
         desc = scenes.instanced_scene(grid=100, subdiv=3, n_lights=16)
         be = backend_mod.B200Backend(w, h, device=torch.cuda.current_device(), tile_size=tile, rank=rank, world=world, sky=(0.3, 0.35, 0.5))
@@ -406,7 +408,6 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=600))
     # torch.distributed is the plumbing (barriers, max-over-ranks of the timings, distributing the 128-byte NCCL id); the
     # data-path collective — the accumulator gather — is the library's own NCCL communicator (rfwb200_comm_init)
-    uid = sharding.broadcast_unique_id(dist, torch, rank) if dist is not None else None
 
     # ---- scene (replicated) and this rank's rays -------------------------------------------------------
     desc = scenes.soup_scene(N_TRIS, SOUP_S)
@@ -516,7 +517,7 @@ def main():
                               "bvh_bytes": bs["bvh_bytes"], "sah_cost": bs["sah_cost"]}
     if not args.no_extras:
         try:
-            pt = path_tracing_extra(backend, scenes, torch, rank, world, args.pt_spp, dist, uid)
+            pt = path_tracing_extra(backend, scenes, sharding, torch, rank, world, args.pt_spp, dist)
             if rank == 0:
                 extra["path_tracing_c3"] = pt
         except Exception as ex:  # the headline metric must still be reported
@@ -529,7 +530,7 @@ def main():
         pin_rays.free(); pin_hits.free()
         torch.cuda.empty_cache()
         try:
-            pt_block = path_tracing_block(backend, scenes, sharding, torch, rank, world, dist, uid, args.c5_frames, args.c5_tris, args.c5_spp)
+            pt_block = path_tracing_block(backend, scenes, sharding, torch, rank, world, dist, args.c5_frames, args.c5_tris, args.c5_spp)
         except Exception as ex:
             pt_block = {"error": repr(ex)}
 

@@ -249,6 +249,20 @@ typedef struct RfwHit {
     float v;
 } RfwHit;
 
+/* rtbvh's RayPacket4 as rfw fills it (crates/rfw-backend/src/structs.rs:656-667, 701-712): four rays, one SoA lane each.
+ * `t` is the current far limit / closest distance (1e34 when generated); inv_direction_* are carried for layout fidelity, the
+ * backend derives its own reciprocals. */
+typedef struct RfwRayPacket4 {
+    float origin_x[4], origin_y[4], origin_z[4];
+    float direction_x[4], direction_y[4], direction_z[4];
+    float t[4];
+    float inv_direction_x[4], inv_direction_y[4], inv_direction_z[4];
+} RfwRayPacket4;
+
+#if defined(__cplusplus)
+static_assert(sizeof(RfwRayPacket4) == 160, "RfwRayPacket4");
+#endif
+
 typedef struct RfwB200Config {
     int32_t device;          /* CUDA device ordinal */
     uint32_t width, height;  /* framebuffer */
@@ -386,6 +400,17 @@ RFWB200_API int rfwb200_trace_any_device(void* handle, const RfwRay* d_rays, uin
 RFWB200_API int rfwb200_trace_closest_counted(void* handle, const RfwRay* d_rays, uint64_t num, RfwHit* d_hits, RfwTraceStats* out);
 /* primary rays for every pixel of the framebuffer: pinhole generate_ray (structs.rs:549-556) + closest hit,
  * row-major; `out_hits` is a host buffer of width*height records */
+/* The remaining methods of the CPU twin TIntersector (crates/rfw-scene/src/intersector.rs), host buffers, blocking:
+ *   intersect_t  (:77-101)   closest-hit distance only: out_t[i] = t, or -1 where the reference returns None
+ *   depth_test   (:103-127)  out_t[i] = closest t (ray.tmax on a miss), out_depth[i] = acceleration-structure nodes the ray
+ *                            visited (TLAS + every BLAS entered): the reference's BVH heat-map quantity
+ *   intersect4   (:133-166)  ray packets; t_min[4] applies per lane to every packet of the call (the reference passes one
+ *                            [f32; 4] per call); out_inst / out_prim [4 * num_packets] (-1 = miss), packet.t lowered to the hit
+ *   occludes4    (:129-131)  the reference's body is a stub returning [true; 4]; this one answers: any hit in (t_min, packet.t) */
+RFWB200_API int rfwb200_intersect_t(void* handle, const RfwRay* rays, uint64_t num, float* out_t);
+RFWB200_API int rfwb200_depth_test(void* handle, const RfwRay* rays, uint64_t num, float* out_t, uint32_t* out_depth);
+RFWB200_API int rfwb200_intersect4(void* handle, RfwRayPacket4* packets, uint64_t num_packets, const float* t_min4, int32_t* out_inst, int32_t* out_prim);
+RFWB200_API int rfwb200_occludes4(void* handle, const RfwRayPacket4* packets, uint64_t num_packets, const float* t_min4, uint32_t* out_occluded);
 RFWB200_API int rfwb200_cast_primary(void* handle, const RfwCameraView3D* view, RfwHit* out_hits);
 
 /* `spp` wavefront frames of `depth` segments (generate, extend, shade, connect, accumulate) */

@@ -64,6 +64,10 @@ def load_library():
         "rfwb200_set_2d_instances": ([vp, u32, vp, u32], i32),
         "rfwb200_trace_closest": ([vp, vp, u64, vp], i32),
         "rfwb200_trace_any": ([vp, vp, u64, vp], i32),
+        "rfwb200_intersect_t": ([vp, vp, u64, vp], i32),
+        "rfwb200_depth_test": ([vp, vp, u64, vp, vp], i32),
+        "rfwb200_intersect4": ([vp, vp, u64, vp, vp, vp], i32),
+        "rfwb200_occludes4": ([vp, vp, u64, vp, vp], i32),
         "rfwb200_trace_closest_device": ([vp, vp, u64, vp, i32], i32),
         "rfwb200_trace_any_device": ([vp, vp, u64, vp, i32], i32),
         "rfwb200_trace_closest_counted": ([vp, vp, u64, vp, vp], i32),
@@ -300,6 +304,38 @@ class B200Backend:
         rays = np.ascontiguousarray(rays)
         occ = np.empty(len(rays), dtype=np.uint32) if out is None else out
         self._ck(self.L.rfwb200_trace_any(self.h, _ptr(rays), len(rays), _ptr(occ)), "trace_any")
+        return occ
+
+    # ---- the rest of TIntersector (crates/rfw-scene/src/intersector.rs:77-166) --------------------------------------
+    def intersect_t(self, rays):
+        """Closest-hit distance per ray; -1 where the reference returns None."""
+        rays = np.ascontiguousarray(rays)
+        t = np.empty(len(rays), np.float32)
+        self._ck(self.L.rfwb200_intersect_t(self.h, _ptr(rays), len(rays), _ptr(t)), "intersect_t")
+        return t
+
+    def depth_test(self, rays):
+        """(t, depth): closest t (ray.tmax on a miss) and the number of acceleration-structure nodes the ray visited."""
+        rays = np.ascontiguousarray(rays)
+        t = np.empty(len(rays), np.float32)
+        depth = np.empty(len(rays), np.uint32)
+        self._ck(self.L.rfwb200_depth_test(self.h, _ptr(rays), len(rays), _ptr(t), _ptr(depth)), "depth_test")
+        return t, depth
+
+    def intersect4(self, packets, t_min=(1e-4,) * 4):
+        """packets: array of wire.RAY_PACKET4 (updated in place: t of the lanes that hit).  Returns (inst[n, 4], prim[n, 4])."""
+        assert packets.dtype.itemsize == 160 and packets.flags["C_CONTIGUOUS"]
+        tm = np.asarray(t_min, np.float32)
+        inst = np.empty((len(packets), 4), np.int32)
+        prim = np.empty((len(packets), 4), np.int32)
+        self._ck(self.L.rfwb200_intersect4(self.h, _ptr(packets), len(packets), _ptr(tm), _ptr(inst), _ptr(prim)), "intersect4")
+        return inst, prim
+
+    def occludes4(self, packets, t_min=(1e-3,) * 4):
+        assert packets.dtype.itemsize == 160 and packets.flags["C_CONTIGUOUS"]
+        tm = np.asarray(t_min, np.float32)
+        occ = np.empty((len(packets), 4), np.uint32)
+        self._ck(self.L.rfwb200_occludes4(self.h, _ptr(packets), len(packets), _ptr(tm), _ptr(occ)), "occludes4")
         return occ
 
     def trace_closest_device(self, d_rays_ptr, n, d_hits_ptr, sync=True):

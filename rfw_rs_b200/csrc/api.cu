@@ -50,6 +50,20 @@ int rfwb200_trace_any(void* handle, const RfwRay* rays, uint64_t num, uint32_t* 
 int rfwb200_trace_closest_device(void* handle, const RfwRay* d_rays, uint64_t num, RfwHit* d_hits, int sync) { RFW_GUARD(handle); return b->trace_closest_device(d_rays, num, d_hits, sync); }
 int rfwb200_trace_any_device(void* handle, const RfwRay* d_rays, uint64_t num, uint32_t* d_occ, int sync) { RFW_GUARD(handle); return b->trace_any_device(d_rays, num, d_occ, sync); }
 int rfwb200_trace_closest_counted(void* handle, const RfwRay* d_rays, uint64_t num, RfwHit* d_hits, RfwTraceStats* out) { RFW_GUARD(handle); return b->trace_closest_counted(d_rays, num, d_hits, out); }
+int rfwb200_intersect_t(void* handle, const RfwRay* rays, uint64_t num, float* out_t) { RFW_GUARD(handle); return b->trace_t_host(rays, num, out_t, nullptr); }
+int rfwb200_depth_test(void* handle, const RfwRay* rays, uint64_t num, float* out_t, uint32_t* out_depth) {
+    RFW_GUARD(handle);
+    if (num && !out_depth) { rfw::set_last_error("rfwb200_depth_test: null depth buffer"); return RFWB200_ERR_INVALID; }
+    return b->trace_t_host(rays, num, out_t, out_depth);
+}
+int rfwb200_intersect4(void* handle, RfwRayPacket4* packets, uint64_t n, const float* t_min4, int32_t* out_inst, int32_t* out_prim) {
+    RFW_GUARD(handle);
+    return b->trace_packets4_host(false, packets, n, t_min4, out_inst, out_prim, nullptr);
+}
+int rfwb200_occludes4(void* handle, const RfwRayPacket4* packets, uint64_t n, const float* t_min4, uint32_t* out_occ) {
+    RFW_GUARD(handle);
+    return b->trace_packets4_host(true, const_cast<RfwRayPacket4*>(packets), n, t_min4, nullptr, nullptr, out_occ);
+}
 int rfwb200_cast_primary(void* handle, const RfwCameraView3D* view, RfwHit* out) { RFW_GUARD(handle); return b->cast_primary(view, out); }
 
 int rfwb200_render_spp(void* handle, const RfwCameraView3D* view, uint32_t spp, uint32_t depth) { RFW_GUARD(handle); return b->render_spp(view, spp, depth); }

@@ -656,6 +656,7 @@ int Backend::synchronize() {
         sv.single_identity = single_identity ? 1 : 0;
         sv.num_live = (int)live;
         sv.overflow = d_overflow;
+        sv.tri_mt = tri_mt;
         {   // the per-ray traversal stack bounds the depth of what can be traced (trace_kernel.cuh)
             uint32_t blas_depth = 0;
             for (const MeshRec& m : meshes) if (m.present && m.n) blas_depth = std::max(blas_depth, m.bvh.depth);
@@ -1221,6 +1222,63 @@ int Backend::cast_primary(const RfwCameraView3D* view, RfwHit* out_hits) {
     return check_stack_overflow("cast_primary", &trace_stats.stack_overflows);
 }
 
+// TIntersector::intersect_t / depth_test (intersector.rs:77-127): host buffers in, one value (two for depth_test) per ray out.
+// Batches of at most 2^26 rays through the ray / hit scratch buffers (the t values reuse the hit buffer, the depths the flag buffer).
+int Backend::trace_t_host(const RfwRay* rays, uint64_t num, float* out_t, uint32_t* out_depth) {
+    DeviceScope device_scope(cfg.device);
+    BK_CUDA(device_scope.status, "cudaSetDevice");
+    if (int rc = ensure_synchronized("intersect_t")) return rc;
+    if (num == 0) return RFWB200_OK;
+    if (!rays || !out_t) return fail(RFWB200_ERR_INVALID, "intersect_t / depth_test: null buffer");
+    const uint64_t batch = std::min<uint64_t>(num, 1ull << 26);
+    BK_CUDA(d_rays.reserve(batch), "ray buffer");
+    BK_CUDA(d_hits.reserve(batch), "hit buffer");
+    if (out_depth) BK_CUDA(d_occ.reserve(batch), "flag buffer");
+    float* d_t = reinterpret_cast<float*>(d_hits.ptr);
+    for (uint64_t off = 0; off < num; off += batch) {
+        const uint32_t n = (uint32_t)std::min<uint64_t>(batch, num - off);
+        BK_CUDA(cudaMemcpyAsync(d_rays.ptr, rays + off, (size_t)n * sizeof(RfwRay), cudaMemcpyHostToDevice, stream), "ray upload");
+        BK_CUDA(trace_t(tcfg, sv, d_rays.ptr, n, d_t, out_depth ? d_occ.ptr : nullptr), "trace_t");
+        launch_count++;
+        BK_CUDA(cudaMemcpyAsync(out_t + off, d_t, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, stream), "t download");
+        if (out_depth) BK_CUDA(cudaMemcpyAsync(out_depth + off, d_occ.ptr, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "depth download");
+        BK_CUDA(cudaStreamSynchronize(stream), "intersect_t");
+    }
+    trace_stats.rays = num;
+    return check_stack_overflow("intersect_t / depth_test", &trace_stats.stack_overflows);
+}
+
+// TIntersector::intersect4 / occludes4 (intersector.rs:129-166): rtbvh ray packets (4 rays, SoA) from host memory
+int Backend::trace_packets4_host(bool any_hit, RfwRayPacket4* packets, uint64_t num_packets, const float* t_min4, int32_t* out_inst, int32_t* out_prim, uint32_t* out_occ) {
+    DeviceScope device_scope(cfg.device);
+    BK_CUDA(device_scope.status, "cudaSetDevice");
+    if (int rc = ensure_synchronized("intersect4")) return rc;
+    if (num_packets == 0) return RFWB200_OK;
+    if (!packets || !t_min4 || (any_hit ? !out_occ : (!out_inst || !out_prim))) return fail(RFWB200_ERR_INVALID, "intersect4 / occludes4: null buffer");
+    const uint64_t batch = std::min<uint64_t>(num_packets, 1ull << 24);
+    BK_CUDA(d_rays.reserve(batch * 5), "packet buffer");  // 160-byte packets in the 32-byte ray scratch
+    BK_CUDA(d_occ.reserve(batch * 8), "id buffer");       // inst[4 n] | prim[4 n]  (or occluded[4 n])
+    RfwRayPacket4* d_pk = reinterpret_cast<RfwRayPacket4*>(d_rays.ptr);
+    int32_t* d_inst = reinterpret_cast<int32_t*>(d_occ.ptr);
+    for (uint64_t off = 0; off < num_packets; off += batch) {
+        const uint32_t n = (uint32_t)std::min<uint64_t>(batch, num_packets - off);
+        int32_t* d_prim = d_inst + 4 * (size_t)n;
+        BK_CUDA(cudaMemcpyAsync(d_pk, packets + off, (size_t)n * sizeof(RfwRayPacket4), cudaMemcpyHostToDevice, stream), "packet upload");
+        BK_CUDA(trace_packets4(tcfg, sv, any_hit, d_pk, n, t_min4, d_inst, d_prim, d_occ.ptr), "trace_packets4");
+        launch_count++;
+        if (any_hit) {
+            BK_CUDA(cudaMemcpyAsync(out_occ + 4 * off, d_occ.ptr, 4 * (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "flag download");
+        } else {
+            BK_CUDA(cudaMemcpyAsync(out_inst + 4 * off, d_inst, 4 * (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, stream), "id download");
+            BK_CUDA(cudaMemcpyAsync(out_prim + 4 * off, d_prim, 4 * (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, stream), "id download");
+            BK_CUDA(cudaMemcpyAsync(packets + off, d_pk, (size_t)n * sizeof(RfwRayPacket4), cudaMemcpyDeviceToHost, stream), "packet download");  // packet.t of the hit lanes
+        }
+        BK_CUDA(cudaStreamSynchronize(stream), "intersect4");
+    }
+    trace_stats.rays = 4 * num_packets;
+    return check_stack_overflow("intersect4 / occludes4", &trace_stats.stack_overflows);
+}
+
 // ---- rendering ---------------------------------------------------------------------------------------------
 int Backend::render_spp(const RfwCameraView3D* view, uint32_t spp, uint32_t depth) {
     DeviceScope device_scope(cfg.device);
@@ -1456,6 +1514,7 @@ int Backend::set_option(const char* key, int64_t value) {
     else if (k == "tri_blocked") tcfg.tri_blocked = (int)value;
     else if (k == "sort_rays") sort_rays = (int)value;
     else if (k == "sort_min_bvh_mb") sort_min_bvh_bytes = (uint64_t)std::max<int64_t>(0, value) << 20;
+    else if (k == "tri_test") { tri_mt = value != 0 ? 1 : 0; sv.tri_mt = tri_mt; }  // 0: watertight (default); 1: the reference's Moller-Trumbore arithmetic (parity runs)
     else if (k == "stage_timing") wf.stage_timing = value != 0;
     else if (k == "wf_overlap") wf.overlap = value != 0;  // connect(b) beside extend(b + 1) on a second stream (1, default) or everything on one stream (0)
     else if (k == "inst_batch") tcfg.inst_batch = (int)std::max<int64_t>(1, value);

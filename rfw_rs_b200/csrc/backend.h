@@ -92,6 +92,8 @@ public:
     int trace_any_host(const RfwRay* rays, uint64_t num, uint32_t* out);
     int trace_closest_device(const RfwRay* d_rays, uint64_t num, RfwHit* d_hits, int sync);
     int trace_any_device(const RfwRay* d_rays, uint64_t num, uint32_t* d_occ, int sync);
+    int trace_t_host(const RfwRay* rays, uint64_t num, float* out_t, uint32_t* out_depth);
+    int trace_packets4_host(bool any_hit, RfwRayPacket4* packets, uint64_t num_packets, const float* t_min4, int32_t* out_inst, int32_t* out_prim, uint32_t* out_occ);
     int trace_closest_counted(const RfwRay* d_rays, uint64_t num, RfwHit* d_hits, RfwTraceStats* out);
     int cast_primary(const RfwCameraView3D* view, RfwHit* out_hits);
 
@@ -217,6 +219,7 @@ private:
     float sah_c_prim = 0.8f;  // SAH cost of one triangle test relative to one wide-node visit (BLAS); swept on C2/C4 (scripts/tune_leafcost.py)
     int sah_pmax = 3;         // max triangles per leaf slot
     int sah_treelet_tlas = 0;  // the same for the TLAS over instance boxes: off — refining the 170-instance TLAS of pica (nested, overlapping part boxes) made its primary rays 60 % slower (scripts/exp_c1b.py), the C3 grid TLAS is indifferent
+    int tri_mt = 0;       // option "tri_test": 1 = the reference's Moller-Trumbore triangle arithmetic in every traversal kernel (SceneView::tri_mt)
     int sah_treelet = 8;  // binned-SAH refinement above LBVH treelets of this many primitives (0 = plain LBVH)
 
     // accumulator gather over NCCL (comm.h)

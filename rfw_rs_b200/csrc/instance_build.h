@@ -9,13 +9,7 @@
 
 namespace rfw {
 
-RFW_HD float add_rn(float a, float b) {
-#if defined(__CUDA_ARCH__)
-    return __fadd_rn(a, b);
-#else
-    volatile float r = a + b; return r;
-#endif
-}
+// (add_rn: traverse.h)
 
 struct MeshEntry {
     const float4* nodes;

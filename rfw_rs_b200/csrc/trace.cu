@@ -51,6 +51,42 @@ __global__ void __launch_bounds__(128) k_trace_simple(SceneView sv, const float4
     }
 }
 
+// TIntersector::intersect_t / depth_test (crates/rfw-scene/src/intersector.rs:77-127): closest-hit distance per ray and, for
+// depth_test, the number of acceleration-structure nodes the ray visited (TLAS + every BLAS it entered) — the value the
+// reference's BVH heat-map view plots.  One thread per ray, the instrumented per-ray loop.
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_trace_t(SceneView sv, const float4* __restrict__ rays, uint32_t n, float* __restrict__ t_out, uint32_t* __restrict__ depth_out) {
+    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n) return;
+    TraceCounters ctr{0, 0, 0};
+    const float4 r0 = __ldcs(rays + 2 * (size_t)i), r1 = __ldcs(rays + 2 * (size_t)i + 1);
+    Hit h;
+    trace_ray<false, COUNT, 48>(sv, xyz(r0), xyz(r1), r0.w, r1.w, h, &ctr);
+    if (COUNT) { t_out[i] = h.t; depth_out[i] = (uint32_t)ctr.nodes; }  // depth_test: (t, depth), t = t_max on a miss
+    else t_out[i] = h.prim >= 0 ? h.t : -1.0f;                            // intersect_t: Option<f32>, None = -1
+}
+
+// TIntersector::intersect4 / occludes4 (intersector.rs:129-166): four rays in the SoA packet of rtbvh (RfwRayPacket4, 160 B).
+// One thread per ray; lane k of packet p is ray 4 p + k.  Closest hit: instance / primitive ids out, packet.t lowered to the
+// hit distance (intersector.rs:152-156).  Any hit: packet.t is the far limit, one flag per lane out.
+template <bool ANY>
+__global__ void __launch_bounds__(128) k_trace_packet4(SceneView sv, RfwRayPacket4* __restrict__ packets, uint32_t n_rays, float4 t_min4, int32_t* __restrict__ inst_out,
+                                                       int32_t* __restrict__ prim_out, uint32_t* __restrict__ occ_out) {
+    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n_rays) return;
+    RfwRayPacket4& pk = packets[i >> 2];
+    const int k = (int)(i & 3u);
+    const float3 o = f3(pk.origin_x[k], pk.origin_y[k], pk.origin_z[k]), d = f3(pk.direction_x[k], pk.direction_y[k], pk.direction_z[k]);
+    const float tmin = k == 0 ? t_min4.x : (k == 1 ? t_min4.y : (k == 2 ? t_min4.z : t_min4.w));
+    Hit h;
+    const bool occ = trace_ray<ANY, false, 48>(sv, o, d, tmin, pk.t[k], h, nullptr);
+    if (ANY) occ_out[i] = occ ? 1u : 0u;
+    else {
+        inst_out[i] = h.inst; prim_out[i] = h.prim;
+        if (h.prim >= 0) pk.t[k] = h.t;
+    }
+}
+
 // pinhole primary rays: CameraView3D::generate_ray, crates/rfw-backend/src/structs.rs:549-556
 __global__ void __launch_bounds__(256) k_generate_pinhole(RfwCameraView3D cam, uint32_t w, uint32_t h, float4* __restrict__ rays) {
     const uint32_t i = blockIdx.x * 256 + threadIdx.x;
@@ -269,6 +305,22 @@ cudaError_t generate_pinhole_rays(cudaStream_t stream, const RfwCameraView3D& ca
     const uint32_t n = w * h;
     if (n == 0) return cudaSuccess;
     k_generate_pinhole<<<(n + 255) / 256, 256, 0, stream>>>(cam, w, h, reinterpret_cast<float4*>(d_rays));
+    return cudaGetLastError();
+}
+
+cudaError_t trace_t(const TraceConfig& cfg, const SceneView& sv, const RfwRay* d_rays, uint32_t n, float* d_t, uint32_t* d_depth) {
+    if (n == 0) return cudaSuccess;
+    if (d_depth) k_trace_t<true><<<(n + 127) / 128, 128, 0, cfg.stream>>>(sv, reinterpret_cast<const float4*>(d_rays), n, d_t, d_depth);
+    else k_trace_t<false><<<(n + 127) / 128, 128, 0, cfg.stream>>>(sv, reinterpret_cast<const float4*>(d_rays), n, d_t, nullptr);
+    return cudaGetLastError();
+}
+cudaError_t trace_packets4(const TraceConfig& cfg, const SceneView& sv, bool any_hit, RfwRayPacket4* d_packets, uint32_t n_packets, const float t_min[4], int32_t* d_inst, int32_t* d_prim,
+                           uint32_t* d_occ) {
+    if (n_packets == 0) return cudaSuccess;
+    const uint32_t n = n_packets * 4u;
+    const float4 tm = make_float4(t_min[0], t_min[1], t_min[2], t_min[3]);
+    if (any_hit) k_trace_packet4<true><<<(n + 127) / 128, 128, 0, cfg.stream>>>(sv, d_packets, n, tm, nullptr, nullptr, d_occ);
+    else k_trace_packet4<false><<<(n + 127) / 128, 128, 0, cfg.stream>>>(sv, d_packets, n, tm, d_inst, d_prim, nullptr);
     return cudaGetLastError();
 }
 

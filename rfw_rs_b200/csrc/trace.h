@@ -57,6 +57,10 @@ cudaError_t trace_sorted(const TraceConfig& cfg, const SceneView& sv, bool any_h
 cudaError_t trace_closest(const TraceConfig& cfg, const SceneView& sv, const RfwRay* d_rays, uint32_t n, RfwHit* d_hits, uint32_t* d_counter);
 cudaError_t trace_any(const TraceConfig& cfg, const SceneView& sv, const RfwRay* d_rays, uint32_t n, uint32_t* d_occluded, uint32_t* d_counter);
 cudaError_t trace_closest_counted(const TraceConfig& cfg, const SceneView& sv, const RfwRay* d_rays, uint32_t n, RfwHit* d_hits, unsigned long long* d_counters3);
+// TIntersector::intersect_t (d_depth == nullptr: t or -1) / depth_test (t or t_max, nodes visited) and the rtbvh ray packets
+cudaError_t trace_t(const TraceConfig& cfg, const SceneView& sv, const RfwRay* d_rays, uint32_t n, float* d_t, uint32_t* d_depth);
+cudaError_t trace_packets4(const TraceConfig& cfg, const SceneView& sv, bool any_hit, RfwRayPacket4* d_packets, uint32_t n_packets, const float t_min[4], int32_t* d_inst, int32_t* d_prim,
+                           uint32_t* d_occ);
 cudaError_t measure_l2_read(cudaStream_t stream, int sm_count, size_t bytes, int iters, float* out_gbs);
 cudaError_t generate_pinhole_rays(cudaStream_t stream, const RfwCameraView3D& cam, uint32_t w, uint32_t h, RfwRay* d_rays);
 

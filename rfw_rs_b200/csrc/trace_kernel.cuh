@@ -70,6 +70,12 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
 }
 #endif
 static constexpr int PT_L_STACK = RFW_PT_L_STACK;
+#ifndef RFW_PREFETCH
+#define RFW_PREFETCH 0
+#endif
+#ifndef RFW_NODE_STEPS
+#define RFW_NODE_STEPS 1
+#endif
 // Two-level kernels keep the WORLD-space ray of every lane in shared memory (3 x float4 [vector][thread]: origin,
 // direction, reciprocal direction, octant word) instead of six live registers: it is needed only when a lane enters an
 // instance (object-space transform) and when it leaves one — where the three loads also replace re-deriving the slab
@@ -108,7 +114,8 @@ struct TraceTuning {
 // builder reports d (DeviceBvh::depth) and Backend::synchronize refuses scenes that could exceed the stack.  Pushes beyond it
 // are dropped AND flagged (SceneView::overflow).  L_STACK is a template parameter so that a test can build a 2 + 2 entry
 // variant that overflows on any scene (option trace_variant 3).
-template <class IO, bool ANY, bool TWO_LEVEL, int THREADS, int MIN_BLOCKS, int SM_STACK, int L_STACK = PT_L_STACK>
+// TRI_MT: the reference's Moller-Trumbore test instead of the watertight one (traverse.h::intersect_tri_mt, option "tri_test").
+template <class IO, bool ANY, bool TWO_LEVEL, int THREADS, int MIN_BLOCKS, int SM_STACK, int L_STACK = PT_L_STACK, bool TRI_MT = false>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneView sv, IO io, uint32_t* __restrict__ counter, TraceTuning tune) {
 #if defined(RFW_HOST_SIMT)
     uint2* const smem_stack = reinterpret_cast<uint2*>(rfw_host_smem);  // (the host SIMT harness: shared memory is a byte array)
@@ -234,6 +241,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
                 } else {
                     const InstanceRec& rec = sv.instances[0];
                     if (sv.single_identity) { rc.o = xyz(r0); rc.d = xyz(r1); }
+                    else if (TRI_MT) xform_ray_ref(rec, xyz(r0), xyz(r1), rc.o, rc.d);
                     else xform_ray(rec, xyz(r0), xyz(r1), rc.o, rc.d);
                     nodes = rec.nodes; tris = rec.tris; cur_inst = rec.inst_id;
                     in_blas = true;
@@ -262,7 +270,13 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
             // can churn through thousands of missing rays, and on the host-streamed path the oldest parked ray holds back
             // the download watermark
             tick++;
-            if (active && (tg.y == 0u || (DQ > 0 && dn < DQ))) {
+            // RFW_NODE_STEPS node steps per iteration (a real loop, not unrolled): the ballots, the refill test and the phase
+            // bookkeeping of an iteration (~70 instructions) are paid once per RFW_NODE_STEPS node visits
+#if RFW_NODE_STEPS > 1
+#pragma unroll 1
+            for (int rep = 0; rep < RFW_NODE_STEPS; rep++)
+#endif
+            if (active && !done && (tg.y == 0u || (DQ > 0 && dn < DQ))) {
                 uint2 tgn = make_uint2(0u, 0u);  // leaf group found in this step
                 // (a) nothing at hand: pop (leaving the BLAS when its part of the stack is exhausted)
                 if (!RFW_NODE_HITS(ng)) {
@@ -297,6 +311,18 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
                     tgn.x = __float_as_uint(n1.y);
                     ng.y = (hm & 0xFF000000u) | (__float_as_uint(n0.w) >> 24);
                     tgn.y = hm & 0x00FFFFFFu;
+#if RFW_PREFETCH > 0
+                    // the node this lane visits next is known now (the nearest hit child), its fetch is ~100 instructions of
+                    // bookkeeping, triangle tests and ballots away: start it into the L1 already
+                    if (RFW_NODE_HITS(ng)) {
+                        const int bit2 = 31 - __clz((int)ng.y);
+                        const uint32_t slot2 = (uint32_t)(bit2 - 24) ^ (rc.octinv4 & 7u);
+                        const uint32_t rel2 = __popc(ng.y & ~(0xFFFFFFFFu << slot2) & 0xFFu);
+                        const float4* pp = nodes + (size_t)(ng.x + rel2) * NODE_F4;
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(pp));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(pp + 4));
+                    }
+#endif
                 }
                 if (tgn.y != 0u) {
                     if (DQ == 0 || tg.y == 0u) tg = tgn;
@@ -322,7 +348,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
                         in_blas = true;
                         cur_inst = rec->inst_id;
                         const float4 w0 = lds_f4(wr_base), w1 = lds_f4(wr_base + (uint32_t)(THREADS * 16));
-                        xform_ray(*rec, f3(w0.x, w0.y, w0.z), f3(w0.w, w1.x, w1.y), rc.o, rc.d);
+                        if (TRI_MT) xform_ray_ref(*rec, f3(w0.x, w0.y, w0.z), f3(w0.w, w1.x, w1.y), rc.o, rc.d);
+                        else xform_ray(*rec, f3(w0.x, w0.y, w0.z), f3(w0.w, w1.x, w1.y), rc.o, rc.d);
                         ray_setup_box(rc);
                         ray_setup_tri(rc);
                         nodes = rec->nodes; tris = rec->tris;
@@ -348,7 +375,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
                         const float4* tp = tris + (size_t)(tg.x + (uint32_t)tb) * 3;
                         const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
                         float t, u, v;
-                        if (intersect_tri_wt(xyz(a), xyz(b), xyz(c), rc, t, u, v) && t > tmin) {
+                        if ((TRI_MT ? intersect_tri_mt(xyz(a), xyz(b), xyz(c), rc.o, rc.d, t, u, v) : intersect_tri_wt(xyz(a), xyz(b), xyz(c), rc, t, u, v)) && t > tmin) {
                             const int prim = (int)__float_as_uint(a.w);
                             if (ANY) {
                                 if (t < hit.t) { done = true; hit.prim = prim; }
@@ -375,6 +402,12 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
     }
 }
 
+#ifndef RFW_PT_MIN_BLOCKS
+#define RFW_PT_MIN_BLOCKS 8
+#endif
+#ifndef RFW_PT_MIN_BLOCKS_TL
+#define RFW_PT_MIN_BLOCKS_TL 8
+#endif
 #if !defined(RFW_HOST_SIMT)  // (the host SIMT harness calls the kernel body directly)
 // persistent grid: min(SMs * resident CTAs, CTAs needed for `n_hint` rays)
 template <class IO, bool ANY, bool TWO_LEVEL, int MIN_BLOCKS>
@@ -400,23 +433,22 @@ static cudaError_t persistent_grid_mb(int sm_count, int blocks_per_sm_limit, uin
 template <class IO, bool ANY, bool TWO_LEVEL, int MIN_BLOCKS>
 static cudaError_t launch_persistent_mb(cudaStream_t stream, int sm_count, int blocks_per_sm_limit, TraceTuning tune, const SceneView& sv, const IO& io, uint32_t n_hint,
                                         uint32_t* counter) {
-    auto kern = k_trace_persistent<IO, ANY, TWO_LEVEL, PT_THREADS, MIN_BLOCKS, PT_SM_STACK>;
     const size_t smem = persistent_smem_bytes<TWO_LEVEL>();
     int grid = 1;
     cudaError_t e = persistent_grid_mb<IO, ANY, TWO_LEVEL, MIN_BLOCKS>(sm_count, blocks_per_sm_limit, n_hint, grid);
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
-    kern<<<(int)grid, PT_THREADS, smem, stream>>>(sv, io, counter, tune);
+    if (sv.tri_mt) {  // parity runs (option "tri_test" 1): the reference's triangle arithmetic; one build per IO policy, at the default register budget
+        if constexpr (MIN_BLOCKS == (TWO_LEVEL ? RFW_PT_MIN_BLOCKS_TL : RFW_PT_MIN_BLOCKS))
+            k_trace_persistent<IO, ANY, TWO_LEVEL, PT_THREADS, MIN_BLOCKS, PT_SM_STACK, PT_L_STACK, true><<<(int)grid, PT_THREADS, smem, stream>>>(sv, io, counter, tune);
+        else return cudaErrorNotSupported;
+    } else {
+        k_trace_persistent<IO, ANY, TWO_LEVEL, PT_THREADS, MIN_BLOCKS, PT_SM_STACK><<<(int)grid, PT_THREADS, smem, stream>>>(sv, io, counter, tune);
+    }
     return cudaGetLastError();
 }
 
-#ifndef RFW_PT_MIN_BLOCKS
-#define RFW_PT_MIN_BLOCKS 8
-#endif
-#ifndef RFW_PT_MIN_BLOCKS_TL
-#define RFW_PT_MIN_BLOCKS_TL 8
-#endif
 
 template <class IO, bool ANY, bool TWO_LEVEL>
 static cudaError_t launch_persistent_io(cudaStream_t stream, int sm_count, int blocks_per_sm_limit, TraceTuning tune, const SceneView& sv, const IO& io, uint32_t n_hint,

@@ -66,6 +66,8 @@ struct SceneView {
     int two_level;                  // 0: exactly one live instance, traced directly
     int single_identity;            // single instance has an identity transform
     int num_live;
+    int tri_mt;                     // triangle test: 0 = watertight (intersect_tri_wt, the product's), 1 = the reference's Moller-Trumbore
+                                    // arithmetic operation for operation (intersect_tri_mt; option "tri_test"): parity runs
     uint32_t* overflow;             // one word the traversal kernels set when a push finds the per-ray stack full (the entry is
                                     // dropped, the ray's result is then unreliable): checked by the host after every launch it waits for
 };
@@ -268,12 +270,68 @@ RFW_HD bool intersect_tri_wt(const float3 v0, const float3 v1, const float3 v2, 
     return true;
 }
 
+// The REFERENCE's triangle test, operation for operation (intersection.glsl:1-38, Moller-Trumbore): every product, sum and the
+// division rounded on its own, in the reference's order — no FMA contraction — so that t and the accept / reject decisions are
+// bit-identical to the oracle's mt_intersect (oracle.cpp, pinned against the reference's shader in tests/test_ref_glsl.py).
+// Option "tri_test" = 1 selects it in every traversal kernel: a fixed-seed image then differs from the oracle's only by the
+// float32 rounding of the shading arithmetic, and the literal all-pixel RMSE bar of the north star is asserted with it
+// (tests/test_gpu_parity.py).  Differences to the shader, both shared with the oracle's parity configuration: the determinant
+// reject is a == 0 (the shader's |a| < 1e-4 would reject every triangle of the small-triangle configs), and (u, v)
+// are not scaled by 1 / dot(gn, gn) (gn is unit length: the factor is 1 within an ulp, and only the final hit's (u, v) is used).
+RFW_HD float add_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(a, b);
+#else
+    volatile float r = a + b; return r;
+#endif
+}
+RFW_HD float div_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdiv_rn(a, b);
+#else
+    volatile float r = a / b; return r;
+#endif
+}
+RFW_HD float dot_rn(float3 a, float3 b) { return add_rn(add_rn(mul_rn(a.x, b.x), mul_rn(a.y, b.y)), mul_rn(a.z, b.z)); }
+RFW_HD float3 cross_rn(float3 a, float3 b) {
+    return f3(sub_rn(mul_rn(a.y, b.z), mul_rn(a.z, b.y)), sub_rn(mul_rn(a.z, b.x), mul_rn(a.x, b.z)), sub_rn(mul_rn(a.x, b.y), mul_rn(a.y, b.x)));
+}
+RFW_HD bool intersect_tri_mt(const float3 v0, const float3 v1, const float3 v2, const float3 origin, const float3 direction, float& t_out, float& u_out, float& v_out) {
+    const float3 edge1 = f3(sub_rn(v1.x, v0.x), sub_rn(v1.y, v0.y), sub_rn(v1.z, v0.z));
+    const float3 edge2 = f3(sub_rn(v2.x, v0.x), sub_rn(v2.y, v0.y), sub_rn(v2.z, v0.z));
+    const float3 h = cross_rn(direction, edge2);
+    const float a = dot_rn(edge1, h);
+    if (a == 0.0f) return false;
+    const float f = div_rn(1.0f, a);
+    const float3 s = f3(sub_rn(origin.x, v0.x), sub_rn(origin.y, v0.y), sub_rn(origin.z, v0.z));
+    const float u = mul_rn(f, dot_rn(s, h));
+    if (u < 0.0f || u > 1.0f) return false;
+    const float3 q = cross_rn(s, edge1);
+    const float v = mul_rn(f, dot_rn(direction, q));
+    if (v < 0.0f || add_rn(u, v) > 1.0f) return false;
+    t_out = mul_rn(f, dot_rn(edge2, q));
+    u_out = u;
+    v_out = v;
+    return true;
+}
+
 RFW_HD void xform_ray(const InstanceRec& rec, const float3 o, const float3 d, float3& oo, float3& od) {
     // object-space ray, direction NOT renormalised so t is shared between spaces (ray_gen.comp:339-341)
     oo = f3(rec.inv0.x * o.x + rec.inv0.y * o.y + rec.inv0.z * o.z + rec.inv0.w, rec.inv1.x * o.x + rec.inv1.y * o.y + rec.inv1.z * o.z + rec.inv1.w,
             rec.inv2.x * o.x + rec.inv2.y * o.y + rec.inv2.z * o.z + rec.inv2.w);
     od = f3(rec.inv0.x * d.x + rec.inv0.y * d.y + rec.inv0.z * d.z, rec.inv1.x * d.x + rec.inv1.y * d.y + rec.inv1.z * d.z,
             rec.inv2.x * d.x + rec.inv2.y * d.y + rec.inv2.z * d.z);
+}
+
+// The same transform in the oracle's (= glm's mat4 * vec4) operation order, every operation rounded on its own: with option
+// "tri_test" = 1 the object-space ray — and with it t — is bit-identical to the oracle's in instanced scenes as well.
+RFW_HD void xform_ray_ref(const InstanceRec& rec, const float3 o, const float3 d, float3& oo, float3& od) {
+    oo = f3(add_rn(add_rn(mul_rn(rec.inv0.x, o.x), mul_rn(rec.inv0.y, o.y)), add_rn(mul_rn(rec.inv0.z, o.z), rec.inv0.w)),
+            add_rn(add_rn(mul_rn(rec.inv1.x, o.x), mul_rn(rec.inv1.y, o.y)), add_rn(mul_rn(rec.inv1.z, o.z), rec.inv1.w)),
+            add_rn(add_rn(mul_rn(rec.inv2.x, o.x), mul_rn(rec.inv2.y, o.y)), add_rn(mul_rn(rec.inv2.z, o.z), rec.inv2.w)));
+    od = f3(add_rn(add_rn(mul_rn(rec.inv0.x, d.x), mul_rn(rec.inv0.y, d.y)), mul_rn(rec.inv0.z, d.z)),
+            add_rn(add_rn(mul_rn(rec.inv1.x, d.x), mul_rn(rec.inv1.y, d.y)), mul_rn(rec.inv1.z, d.z)),
+            add_rn(add_rn(mul_rn(rec.inv2.x, d.x), mul_rn(rec.inv2.y, d.y)), mul_rn(rec.inv2.z, d.z)));
 }
 
 // pinhole primary ray of pixel (x, y) with the closest-hit limits of the extend stage: CameraView3D::generate_ray,
@@ -316,6 +374,7 @@ RFW_HD bool trace_ray(const SceneView& sv, const float3 o, const float3 d, const
     } else {
         const InstanceRec& rec = sv.instances[0];
         if (sv.single_identity) { rc.o = o; rc.d = d; }
+        else if (sv.tri_mt) xform_ray_ref(rec, o, d, rc.o, rc.d);
         else xform_ray(rec, o, d, rc.o, rc.d);
         nodes = rec.nodes; tris = rec.tris; cur_inst = rec.inst_id;
         in_blas = true;
@@ -354,7 +413,7 @@ RFW_HD bool trace_ray(const SceneView& sv, const float3 o, const float3 d, const
                 const float4 a = ldg(tris + (size_t)idx * 3 + 0), b = ldg(tris + (size_t)idx * 3 + 1), c = ldg(tris + (size_t)idx * 3 + 2);
                 if (COUNT) ctr->tris++;
                 float t, u, v;
-                if (intersect_tri_wt(xyz(a), xyz(b), xyz(c), rc, t, u, v) && t > tmin) {
+                if ((sv.tri_mt ? intersect_tri_mt(xyz(a), xyz(b), xyz(c), rc.o, rc.d, t, u, v) : intersect_tri_wt(xyz(a), xyz(b), xyz(c), rc, t, u, v)) && t > tmin) {
                     const int prim = (int)f2u(a.w);
                     if (ANY) {
                         if (t < hit.t) { hit.inst = cur_inst; hit.prim = prim; hit.t = t; return true; }
@@ -371,7 +430,8 @@ RFW_HD bool trace_ray(const SceneView& sv, const float3 o, const float3 d, const
                 blas_base_sp = sp;
                 in_blas = true;
                 cur_inst = rec.inst_id;
-                xform_ray(rec, o, d, rc.o, rc.d);
+                if (sv.tri_mt) xform_ray_ref(rec, o, d, rc.o, rc.d);
+                else xform_ray(rec, o, d, rc.o, rc.d);
                 ray_setup_box(rc);
                 ray_setup_tri(rc);
                 nodes = rec.nodes; tris = rec.tris;

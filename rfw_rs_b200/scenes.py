@@ -477,6 +477,50 @@ def soup_with_lights(n, s, n_lights=256, seed=SEED_SCENE, light_area=1e-2, radiu
     return sc
 
 
+def random_barycentrics_np(r0):
+    """Vectorised RandomBarycentrics (shade.comp:372-412): 16 steps of base-4 triangle subdivision driven by the bits of r0."""
+    uf = (r0.astype(np.float64) * 4294967295.0).astype(np.uint64).astype(np.uint32)
+    A = np.stack([np.ones_like(r0), np.zeros_like(r0)], 1).astype(np.float32)
+    B = np.stack([np.zeros_like(r0), np.ones_like(r0)], 1).astype(np.float32)
+    C = np.zeros_like(A)
+    for i in range(16):
+        d = ((uf >> np.uint32(2 * (15 - i))) & np.uint32(3))[:, None]
+        An = np.where(d == 0, (B + C) * 0.5, np.where(d == 1, A, np.where(d == 2, (B + A) * 0.5, (C + A) * 0.5)))
+        Bn = np.where(d == 0, (A + C) * 0.5, np.where(d == 1, (A + B) * 0.5, np.where(d == 2, B, (C + B) * 0.5)))
+        Cn = np.where(d == 0, (A + B) * 0.5, np.where(d == 1, (A + C) * 0.5, np.where(d == 2, (B + C) * 0.5, C)))
+        A, B, C = An.astype(np.float32), Bn.astype(np.float32), Cn.astype(np.float32)
+    r = (A + B + C) * np.float32(0.3333333)
+    return np.stack([r[:, 0], r[:, 1], 1 - r[:, 0] - r[:, 1]], 1)
+
+
+def c4_scene(n_tris=5_000_000):
+    """BASELINE.json configs[3]: soup of `n_tris` triangles (s = 0.003) + 256 emissive triangles (area 1e-2) on a
+    radius-2 sphere around the cube, facing inward."""
+    return soup_with_lights(n_tris, 0.003, n_lights=256, light_area=1e-2, radius=2.0)
+
+
+def c4_shadow_rays(desc, rays, hits):
+    """The C4 workload: for every closest hit on the soup pick light floor(r0 * n_lights), sample a point on it with
+    RandomBarycentrics (r0 re-scaled as shade.comp:474-475 does) and build the next-event-estimation any-hit ray
+    t in (1e-3, dist - 2e-4) (ray_shadow.comp:254-257, shade.comp:253).  Returns (shadow rays, indices of the shading rays)."""
+    from . import wire
+
+    ok = hits["inst"] == 0  # shading points on the soup (not on the lights)
+    idx = np.nonzero(ok)[0]
+    P = rays["origin"][ok] + rays["direction"][ok] * hits["t"][ok][:, None]
+    r0 = u01(SEED_LIGHTS + 1, idx)
+    L = desc.area_lights
+    li = np.minimum((r0 * len(L)).astype(np.int64), len(L) - 1)
+    rb = (r0 - li.astype(np.float32) / np.float32(len(L))) * np.float32(len(L))
+    bary = random_barycentrics_np(np.clip(rb, 0, 1).astype(np.float32))
+    Q = L["vertex0"][li] * bary[:, :1] + L["vertex1"][li] * bary[:, 1:2] + L["vertex2"][li] * bary[:, 2:3]
+    D = Q - P
+    dist = np.linalg.norm(D, axis=1).astype(np.float32)
+    sh = np.zeros(len(P), dtype=wire.RAY)
+    sh["origin"] = P; sh["direction"] = D / dist[:, None]; sh["tmin"] = 1e-3; sh["tmax"] = dist - np.float32(2e-4)
+    return sh, idx
+
+
 def c5_scene(n_tris=10_000_000):
     """BASELINE.json configs[4] (SURVEY §8d C5): soup of `n_tris` triangles (s = 0.002) + ground quad + 64 area-light triangles;
     rendered at 3840x2160, 64 spp, depth 5 from `c5_view`."""

@@ -67,12 +67,28 @@ DIRECTIONAL_LIGHT = np.dtype([("direction", f4, 3), ("energy", f4), ("radiance",
 
 RAY = np.dtype([("origin", f4, 3), ("tmin", f4), ("direction", f4, 3), ("tmax", f4)])
 HIT = np.dtype([("inst", np.int32), ("prim", np.int32), ("t", f4), ("u", f4), ("v", f4)])
+# rtbvh RayPacket4 as rfw fills it (crates/rfw-backend/src/structs.rs:656-667): ten SoA lanes of four floats
+RAY_PACKET4 = np.dtype([(n, f4, 4) for n in ("origin_x", "origin_y", "origin_z", "direction_x", "direction_y", "direction_z", "t",
+                                             "inv_direction_x", "inv_direction_y", "inv_direction_z")])
+
+
+def rays_to_packets4(rays):
+    """Groups rays (wire.RAY, count a multiple of 4) into RAY_PACKET4 records; packet.t = ray.tmax."""
+    n = len(rays) // 4
+    pk = np.zeros(n, RAY_PACKET4)
+    o = rays["origin"][: 4 * n].reshape(n, 4, 3); d = rays["direction"][: 4 * n].reshape(n, 4, 3)
+    for k, a in enumerate("xyz"):
+        pk["origin_" + a] = o[:, :, k]; pk["direction_" + a] = d[:, :, k]
+        with np.errstate(divide="ignore"):
+            pk["inv_direction_" + a] = np.float32(1.0) / d[:, :, k]
+    pk["t"] = rays["tmax"][: 4 * n].reshape(n, 4)
+    return pk
 
 EXPECTED_SIZES = {
     "RfwAabb": (AABB, 32), "RfwRTTriangle": (RT_TRIANGLE, 176), "RfwVertex3D": (VERTEX3D, 64), "RfwVertexMesh": (VERTEX_MESH, 48),
     "RfwJointData": (JOINT_DATA, 32), "RfwDeviceMaterial": (DEVICE_MATERIAL, 96), "RfwCameraView3D": (CAMERA_VIEW3D, 128),
     "RfwAreaLight": (AREA_LIGHT, 96), "RfwSpotLight": (SPOT_LIGHT, 48), "RfwPointLight": (POINT_LIGHT, 32),
-    "RfwDirectionalLight": (DIRECTIONAL_LIGHT, 32), "RfwRay": (RAY, 32), "RfwHit": (HIT, 20),
+    "RfwDirectionalLight": (DIRECTIONAL_LIGHT, 32), "RfwRay": (RAY, 32), "RfwHit": (HIT, 20), "RfwRayPacket4": (RAY_PACKET4, 160),
 }
 for _name, (_dt, _sz) in EXPECTED_SIZES.items():
     assert _dt.itemsize == _sz, (_name, _dt.itemsize, _sz)

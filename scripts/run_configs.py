@@ -23,22 +23,6 @@ import torch  # noqa: E402
 from rfw_rs_b200 import backend, gltf, scenes, sharding, wire  # noqa: E402
 
 
-def random_barycentrics_np(r0):
-    """Vectorised shade.comp:372-412 (host-side generation of the C4 shadow rays)."""
-    uf = (r0.astype(np.float64) * 4294967295.0).astype(np.uint64).astype(np.uint32)
-    A = np.stack([np.ones_like(r0), np.zeros_like(r0)], 1).astype(np.float32)
-    B = np.stack([np.zeros_like(r0), np.ones_like(r0)], 1).astype(np.float32)
-    C = np.zeros_like(A)
-    for i in range(16):
-        d = ((uf >> np.uint32(2 * (15 - i))) & np.uint32(3))[:, None]
-        An = np.where(d == 0, (B + C) * 0.5, np.where(d == 1, A, np.where(d == 2, (B + A) * 0.5, (C + A) * 0.5)))
-        Bn = np.where(d == 0, (A + C) * 0.5, np.where(d == 1, (A + B) * 0.5, np.where(d == 2, B, (C + B) * 0.5)))
-        Cn = np.where(d == 0, (A + B) * 0.5, np.where(d == 1, (A + C) * 0.5, np.where(d == 2, (B + C) * 0.5, C)))
-        A, B, C = An.astype(np.float32), Bn.astype(np.float32), Cn.astype(np.float32)
-    r = (A + B + C) * np.float32(0.3333333)
-    return np.stack([r[:, 0], r[:, 1], 1 - r[:, 0] - r[:, 1]], 1)
-
-
 def dev(arr):
     return torch.from_numpy(arr.view(np.uint8).reshape(-1).copy()).cuda()
 
@@ -63,7 +47,7 @@ def run_c1(out):
 
 
 def run_c4(out, n_tris, n_rays):
-    desc = scenes.soup_with_lights(n_tris, 0.003, n_lights=256, light_area=1e-2, radius=2.0)
+    desc = scenes.c4_scene(n_tris)
     be = backend.B200Backend()
     t0 = time.time(); desc.apply(be); sync_ms = (time.time() - t0) * 1e3
     bs = be.build_stats()
@@ -75,18 +59,8 @@ def run_c4(out, n_tris, n_rays):
         be.trace_closest_device(d_rays.data_ptr(), n_rays, d_hits.data_ptr())
         best_c = min(best_c, be.trace_stats()["kernel_ms"])
     hits = np.frombuffer(d_hits.cpu().numpy().tobytes(), dtype=wire.HIT)
-    ok = hits["inst"] == 0  # shading points on the soup (not on the lights)
-    P = rays["origin"][ok] + rays["direction"][ok] * hits["t"][ok][:, None]
-    r0 = scenes.u01(scenes.SEED_LIGHTS + 1, np.nonzero(ok)[0])
+    sh, _ = scenes.c4_shadow_rays(desc, rays, hits)
     L = desc.area_lights
-    li = np.minimum((r0 * len(L)).astype(np.int64), len(L) - 1)
-    rb = (r0 - li.astype(np.float32) / np.float32(len(L))) * np.float32(len(L))  # shade.comp:474-475 reuses r0
-    bary = random_barycentrics_np(np.clip(rb, 0, 1).astype(np.float32))
-    Q = L["vertex0"][li] * bary[:, :1] + L["vertex1"][li] * bary[:, 1:2] + L["vertex2"][li] * bary[:, 2:3]
-    D = Q - P
-    dist = np.linalg.norm(D, axis=1).astype(np.float32)
-    sh = np.zeros(len(P), dtype=wire.RAY)
-    sh["origin"] = P; sh["direction"] = D / dist[:, None]; sh["tmin"] = 1e-3; sh["tmax"] = dist - np.float32(2e-4)
     d_sh = dev(sh)
     d_occ = torch.empty(len(sh), dtype=torch.int32, device="cuda")
     best_a = 1e9

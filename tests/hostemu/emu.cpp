@@ -91,7 +91,7 @@ struct EmuScene {
     std::vector<InstanceRec> leaf_recs;    // recs in TLAS leaf-slot order (SceneView::leaf_instances, what k_gather_instances produces)
     std::vector<InstanceShading> shading;  // per GLOBAL instance id (what k_instance_prepare writes for k_wf_shade)
     EmuBvh tlas;
-    SceneView sv;
+    SceneView sv{};
 };
 
 extern "C" {
@@ -197,6 +197,8 @@ void emu_skin_triangles(const RfwRTTriangle* src, const RfwJointData* skin, cons
     }
 }
 // the traversal view of the built scene, for the CPU path tracer of shade_emu.cpp (same header, same struct)
+// option "tri_test" of the product: 1 = the reference's Moller-Trumbore arithmetic (traverse.h::intersect_tri_mt)
+void emu_set_tri_mt(void* s, int on) { ((EmuScene*)s)->sv.tri_mt = on ? 1 : 0; }
 const void* emu_scene_view(void* s) { return &((EmuScene*)s)->sv; }
 // the per-instance shading table the product derives next to the traversal records (indexed by global instance id)
 const void* emu_instance_shading(void* s, uint32_t* count) { EmuScene& sc = *(EmuScene*)s; if (count) *count = (uint32_t)sc.shading.size(); return sc.shading.data(); }
