@@ -267,7 +267,7 @@ def path_tracing_block(backend_mod, scenes, sharding, torch, rank, world, dist, 
     if not _ranks_ok(err, torch, dist):
         return {"error": err or "another rank failed"}
     try:
-        _render_frames(be, view, 4, depth, 1, torch, dist)          # warm-up: allocates the wave queues, the NCCL buffers, warms the L2
+        _render_frames(be, view, spp, depth, 1, torch, dist)        # warm-up frame of the SAME shape: the wave queues are sized by the samples per wave (a 4 spp warm-up left their allocation inside the first timed frame), NCCL buffers, L2
         times, rs = _render_frames(be, view, spp, depth, frames, torch, dist)
     except Exception as ex:
         err = repr(ex)

@@ -1315,6 +1315,7 @@ int Backend::render_spp(const RfwCameraView3D* view, uint32_t spp, uint32_t dept
     render_stats.segments = st[2];
     render_stats.stage_timing = wf.stage_timing ? 1u : 0u;
     BK_CUDA(wf.stage_times(render_stats.stage_ms), "stage times");
+    wf.dump_trace();  // (RFWB200_WF_TRACE=1 only)
     return check_stack_overflow("render", &render_stats.stack_overflows);
 }
 
@@ -1516,6 +1517,8 @@ int Backend::set_option(const char* key, int64_t value) {
     else if (k == "sort_min_bvh_mb") sort_min_bvh_bytes = (uint64_t)std::max<int64_t>(0, value) << 20;
     else if (k == "tri_test") { tri_mt = value != 0 ? 1 : 0; sv.tri_mt = tri_mt; }  // 0: watertight (default); 1: the reference's Moller-Trumbore arithmetic (parity runs)
     else if (k == "stage_timing") wf.stage_timing = value != 0;
+    else if (k == "grid_rays_per_thread") wf.grid_rays_per_thread = (int)std::max<int64_t>(0, value);
+    else if (k == "wf_split") wf.split_waves = value != 0;  // two sub-waves in flight (1, default) or one wave at a time (0)
     else if (k == "wf_overlap") wf.overlap = value != 0;  // connect(b) beside extend(b + 1) on a second stream (1, default) or everything on one stream (0)
     else if (k == "inst_batch") tcfg.inst_batch = (int)std::max<int64_t>(1, value);
     else if (k == "min_blocks") tcfg.min_blocks = (int)value;

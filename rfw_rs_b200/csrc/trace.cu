@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) k_generate_pinhole(RfwCameraView3D cam, u
 // MIN_BLOCKS (the register budget / occupancy trade-off) is selectable at run time for tuning sweeps
 template <bool ANY, bool TWO_LEVEL>
 static cudaError_t launch_persistent_dispatch(const TraceConfig& cfg, const SceneView& sv, const RayBufferIO& io, uint32_t n, uint32_t* counter) {
-    const TraceTuning tune{cfg.refill_below, TWO_LEVEL ? cfg.tri_batch_two_level : cfg.tri_batch, cfg.tri_blocked, cfg.inst_batch};
+    const TraceTuning tune{cfg.refill_below, TWO_LEVEL ? cfg.tri_batch_two_level : cfg.tri_batch, cfg.tri_blocked, cfg.inst_batch, 0};
     switch (cfg.min_blocks > 0 ? cfg.min_blocks : (TWO_LEVEL ? RFW_PT_MIN_BLOCKS_TL : RFW_PT_MIN_BLOCKS)) {
         case 3: return launch_persistent_mb<RayBufferIO, ANY, TWO_LEVEL, 3>(cfg.stream, cfg.sm_count, cfg.blocks_per_sm, tune, sv, io, n, counter);
         case 5: return launch_persistent_mb<RayBufferIO, ANY, TWO_LEVEL, 5>(cfg.stream, cfg.sm_count, cfg.blocks_per_sm, tune, sv, io, n, counter);
@@ -118,7 +118,7 @@ static cudaError_t launch_persistent_dispatch(const TraceConfig& cfg, const Scen
 // overflow is reported (RfwTraceStats::stack_overflows, RFWB200_ERR_STACK) instead of returning silently wrong hits
 template <bool ANY, bool TWO_LEVEL>
 static cudaError_t launch_persistent_tiny_stack(const TraceConfig& cfg, const SceneView& sv, const RayBufferIO& io, uint32_t n, uint32_t* counter) {
-    const TraceTuning tune{cfg.refill_below, TWO_LEVEL ? cfg.tri_batch_two_level : cfg.tri_batch, cfg.tri_blocked, cfg.inst_batch};
+    const TraceTuning tune{cfg.refill_below, TWO_LEVEL ? cfg.tri_batch_two_level : cfg.tri_batch, cfg.tri_blocked, cfg.inst_batch, 0};
     auto kern = k_trace_persistent<RayBufferIO, ANY, TWO_LEVEL, PT_THREADS, 4, 2, 2>;
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), cfg.stream);
     if (e != cudaSuccess) return e;
@@ -208,7 +208,7 @@ cudaError_t trace_sorted(const TraceConfig& cfg, const SceneView& sv, bool any_h
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const PermutedRayIO io{RayBufferIO{rays, n, d_hits, d_occluded}, sc.perm};
-    const TraceTuning tune{cfg.refill_below, sv.two_level ? cfg.tri_batch_two_level : cfg.tri_batch, cfg.tri_blocked, cfg.inst_batch};
+    const TraceTuning tune{cfg.refill_below, sv.two_level ? cfg.tri_batch_two_level : cfg.tri_batch, cfg.tri_blocked, cfg.inst_batch, 0};
     sc.launches++;
     if (any_hit) return sv.two_level ? launch_persistent_io<PermutedRayIO, true, true>(cfg.stream, cfg.sm_count, cfg.blocks_per_sm, tune, sv, io, n, d_counter)
                                      : launch_persistent_io<PermutedRayIO, true, false>(cfg.stream, cfg.sm_count, cfg.blocks_per_sm, tune, sv, io, n, d_counter);
@@ -250,7 +250,7 @@ cudaError_t trace_streamed(const TraceConfig& cfg, const SceneView& sv, bool any
                            uint32_t* d_counter, const StreamSync& sync) {
     if (n == 0) return cudaSuccess;
     StreamedRayIO io{RayBufferIO{reinterpret_cast<const float4*>(d_rays), n, d_hits, d_occluded}, sync.watermark, sync.warp_slots, sync.abort_flag, sync.deadline_ns};
-    const TraceTuning tune{cfg.refill_below, sv.two_level ? cfg.tri_batch_two_level : cfg.tri_batch, cfg.tri_blocked, cfg.inst_batch};
+    const TraceTuning tune{cfg.refill_below, sv.two_level ? cfg.tri_batch_two_level : cfg.tri_batch, cfg.tri_blocked, cfg.inst_batch, 0};
     if (any_hit) {
         return sv.two_level ? launch_persistent_io<StreamedRayIO, true, true>(cfg.stream, cfg.sm_count, cfg.blocks_per_sm, tune, sv, io, n, d_counter)
                             : launch_persistent_io<StreamedRayIO, true, false>(cfg.stream, cfg.sm_count, cfg.blocks_per_sm, tune, sv, io, n, d_counter);

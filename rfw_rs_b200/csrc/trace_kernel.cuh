@@ -107,6 +107,10 @@ struct TraceTuning {
     int tri_batch;     // run the triangle phase when at least this many lanes have pending triangles ...
     int tri_blocked;   // ... or when this many of them cannot traverse any further until their triangles are tested
     int inst_batch;    // two-level kernels: enter TLAS leaves (instances) when at least this many lanes wait at one
+    int rays_per_thread;  // experiment knob, 0 = off (default): CTAs beyond ceil(count / (THREADS * rays_per_thread)) exit at once, so a short
+                          // wavefront queue is traced by as many CTAs as it can feed and the rest of the GPU stays free for kernels launched
+                          // beside it.  Measured slower at every setting (wavefront.h::grid_rays_per_thread): short launches are bound by
+                          // per-warp latency, not by SM slots.
 };
 
 // SM_STACK + L_STACK entries per ray: 12 in shared memory + 24 in local memory by default.  A wide tree of depth d needs at most d
@@ -123,6 +127,10 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
     extern __shared__ uint2 smem_stack[];
 #endif
     const uint32_t n = io.count();
+    if (!IO::kReportsProgress && tune.rays_per_thread > 0) {  // (the host-streamed policy sizes its progress slots for the whole grid)
+        const uint32_t per_cta = (uint32_t)THREADS * (uint32_t)tune.rays_per_thread;
+        if (blockIdx.x > 0 && blockIdx.x >= (n + per_cta - 1) / per_cta) return;
+    }
     const int lane = threadIdx.x & 31;
     const uint32_t lanemask_lt = (1u << lane) - 1u;
 

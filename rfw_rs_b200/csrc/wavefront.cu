@@ -10,6 +10,8 @@
 //   host loop src/lib.rs:1706-1729 -> Wavefront::render: no per-bounce host read-back; counts stay in HBM.
 // Path state is 64 B/path (4 x float4 SoA), shadow jobs 48 B — the reference's record sizes
 // (structs.glsl:4-9, 172-176) so the algorithmic byte counts of SURVEY §8d apply.
+#include <stdio.h>
+#include <stdlib.h>
 #include <algorithm>
 
 #include "shading.cuh"
@@ -62,6 +64,8 @@ void Wavefront::release() {
     stage_events.clear(); stage_marks.clear(); stage_used = 0;
     for (cudaEvent_t e : sync_events) cudaEventDestroy(e);
     sync_events.clear();
+    if (main2) { cudaStreamDestroy(main2); main2 = nullptr; }
+    if (side2) { cudaStreamDestroy(side2); side2 = nullptr; }
 }
 
 cudaError_t Wavefront::configure(uint32_t w, uint32_t h, uint32_t tile_size, uint32_t rank_, uint32_t world_) {
@@ -82,11 +86,11 @@ cudaError_t Wavefront::configure(uint32_t w, uint32_t h, uint32_t tile_size, uin
     WF_CK(cudaMemcpy(d_morton_tiles, morton_tiles.data(), sizeof(uint32_t) * n_tiles, cudaMemcpyHostToDevice));
     WF_CK(cudaMalloc(&d_accum, (size_t)w * h * sizeof(float4)));
     WF_CK(cudaMalloc(&d_output, (size_t)w * h * sizeof(float4)));
-    WF_CK(cudaMalloc(&d_counts, 8 * sizeof(uint32_t)));
+    WF_CK(cudaMalloc(&d_counts, 16 * sizeof(uint32_t)));  // 8 per sub-wave lane
     WF_CK(cudaMalloc(&d_stats, 4 * sizeof(unsigned long long)));
     WF_CK(cudaMemset(d_accum, 0, (size_t)w * h * sizeof(float4)));
     WF_CK(cudaMemset(d_output, 0, (size_t)w * h * sizeof(float4)));
-    WF_CK(cudaMemset(d_counts, 0, 8 * sizeof(uint32_t)));
+    WF_CK(cudaMemset(d_counts, 0, 16 * sizeof(uint32_t)));
     WF_CK(cudaMemset(d_stats, 0, 4 * sizeof(unsigned long long)));
     return ensure_wave(1);
 }
@@ -169,61 +173,133 @@ cudaError_t Wavefront::stage_times(float out_ms[5]) {
     return cudaSuccess;
 }
 
-cudaError_t Wavefront::render(cudaStream_t stream, const SceneView& sv, const ShadeScene& ss, const RfwCameraView3D& cam, uint32_t first_sample, uint32_t spp, uint32_t depth) {
-    if (max_paths == 0) return cudaSuccess;
+// RFWB200_WF_TRACE=1 (diagnostic): a timing event after every kernel of every lane; Wavefront::dump_trace prints when each one
+// completed relative to the start of the frame (the streams must have been synchronised)
+static const bool g_wf_trace = getenv("RFWB200_WF_TRACE") != nullptr;
+cudaError_t Wavefront::trace_mark(cudaStream_t st, const char* what, int lane, int bounce) {
+    if (!g_wf_trace) return cudaSuccess;
+    cudaEvent_t e;
+    WF_CK(cudaEventCreate(&e));
+    WF_CK(cudaEventRecord(e, st));
+    trace_events.push_back({e, what, lane, bounce});
+    return cudaSuccess;
+}
+void Wavefront::dump_trace() {
+    if (trace_events.size() < 2) return;
+    fprintf(stderr, "rfwb200 wavefront trace (ms since the first mark; completion times):\n");
+    for (size_t i = 1; i < trace_events.size(); i++) {
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, trace_events[0].ev, trace_events[i].ev);
+        fprintf(stderr, "  lane %d bounce %d %-10s done at %8.3f\n", trace_events[i].lane, trace_events[i].bounce, trace_events[i].what, ms);
+    }
+    for (auto& t : trace_events) cudaEventDestroy(t.ev);
+    trace_events.clear();
+}
+
+// One SUB-WAVE: `n_spp` samples of every owned pixel (sample indices first_sample .. first_sample + n_spp - 1) through generate and
+// `depth` x { extend -> shade -> connect } on the lane's own pair of streams, queue halves and counters.  `slot0` = first path slot
+// of the lane inside the wave queues, `acc0` = first per-sample accumulator plane of the lane.
+cudaError_t Wavefront::enqueue_subwave(int lane, cudaStream_t m, cudaStream_t c, bool two_streams, const SceneView& sv, const ShadeScene& ss, const RfwCameraView3D& cam, uint32_t first_sample,
+                                       uint32_t n_spp, uint32_t depth, size_t slot0, size_t acc0) {
     const int shade_blocks = sm_count * 8 * 128 / RFW_SHADE_THREADS;
+    const TraceTuning tune{refill_below, sv.two_level ? tri_batch_two_level : tri_batch, tri_blocked, inst_batch, grid_rays_per_thread};
+    FrameParams fp = make_params(*this, cam, first_sample, 0);
+    fp.wave_spp = n_spp;
+    const uint32_t cap = max_paths * n_spp;
+    uint32_t* counts = d_counts + 8 * lane;
+    float4 *O[2] = {d_O[0] + slot0, d_O[1] + slot0}, *D[2] = {d_D[0] + slot0, d_D[1] + slot0}, *T[2] = {d_T[0] + slot0, d_T[1] + slot0}, *S = d_S + slot0;
+    float4 *shO[2] = {d_shO[0] + slot0, d_shO[1] + slot0}, *shD[2] = {d_shD[0] + slot0, d_shD[1] + slot0}, *shE[2] = {d_shE[0] + slot0, d_shE[1] + slot0};
+    float4* partial = d_partial + acc0 * fp.npix;
+    float4* term = d_term + acc0 * fp.npix;
+    cudaEvent_t* ev = sync_events.data() + (size_t)lane * (2 * (size_t)depth + 2);  // [2 b] shade(b) done, [2 b + 1] connect(b) done
+    cudaStream_t conn = two_streams ? c : m;
+    WF_CK(cudaMemsetAsync(counts, 0, 8 * sizeof(uint32_t), m));
+    k_wf_generate<<<(cap + 255) / 256, 256, 0, m>>>(fp, d_owned_tiles, O[0], D[0], counts);
+    launches++;
+    if (lane == 0) WF_CK(stage_mark(m, 0));
+    WF_CK(trace_mark(m, "generate", lane, -1));
+    for (uint32_t b = 0; b < depth; b++) {
+        const int cur = b & 1, nxt = cur ^ 1, sb = b & 1;
+        fp.path_length = b;
+        // ---- main stream: extend(b) -> shade(b) ------------------------------------------------------------------
+        ExtendIO eio{O[cur], D[cur], counts + cur, S};
+        if (sv.two_level) WF_CK((launch_persistent_io<ExtendIO, false, true>(m, sm_count, 0, tune, sv, eio, cap, counts + 4)));
+        else WF_CK((launch_persistent_io<ExtendIO, false, false>(m, sm_count, 0, tune, sv, eio, cap, counts + 4)));
+        if (lane == 0) WF_CK(stage_mark(m, 1));
+        WF_CK(trace_mark(m, "extend", lane, (int)b));
+        if (two_streams && b >= 2) WF_CK(cudaStreamWaitEvent(m, ev[2 * (b - 2) + 1], 0));  // shadow queue `sb` is free again: connect(b - 2) is done
+        k_wf_shade<<<shade_blocks, RFW_SHADE_THREADS, 0, m>>>(fp, ss, S, O[cur], D[cur], T[cur], O[nxt], D[nxt], T[nxt], shO[sb], shD[sb], shE[sb], term, counts + cur, counts + nxt,
+                                                              counts + 2 + sb);
+        k_wf_advance_paths<<<1, 1, 0, m>>>(counts, d_stats, cur);
+        if (lane == 0) WF_CK(stage_mark(m, 2));
+        WF_CK(trace_mark(m, "shade", lane, (int)b));
+        if (two_streams) {
+            WF_CK(cudaEventRecord(ev[2 * b], m));
+            WF_CK(cudaStreamWaitEvent(conn, ev[2 * b], 0));
+        }
+        // ---- connect(b): beside extend(b + 1) / shade(b + 1) -------------------------------------------------------
+        ConnectIO cio{shO[sb], shD[sb], shE[sb], counts + 2 + sb, reinterpret_cast<float*>(partial)};
+        if (sv.two_level) WF_CK((launch_persistent_io<ConnectIO, true, true>(conn, sm_count, 0, tune, sv, cio, cap, counts + 5)));
+        else WF_CK((launch_persistent_io<ConnectIO, true, false>(conn, sm_count, 0, tune, sv, cio, cap, counts + 5)));
+        k_wf_advance_shadow<<<1, 1, 0, conn>>>(counts, d_stats, sb);
+        if (two_streams) WF_CK(cudaEventRecord(ev[2 * b + 1], conn));
+        if (lane == 0) WF_CK(stage_mark(m, 3));
+        WF_CK(trace_mark(conn, "connect", lane, (int)b));
+        launches += 5;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t Wavefront::render(cudaStream_t stream, const SceneView& sv, const ShadeScene& ss, const RfwCameraView3D& cam, uint32_t first_sample, uint32_t spp, uint32_t depth) {
+    if (max_paths == 0 || depth == 0) return cudaSuccess;
     const uint32_t wave = wave_spp_for(spp);
     WF_CK(ensure_wave(wave));
-    const TraceTuning tune{refill_below, sv.two_level ? tri_batch_two_level : tri_batch, tri_blocked, inst_batch};
     stage_used = 0; stage_marks.clear();
-    // per-stage timing needs the stages one after the other: the overlap is switched off for that (diagnostic) run
+    // per-stage timing needs the stages one after the other: every overlap is switched off for that (diagnostic) run
     const bool two_streams = overlap && side != nullptr && !stage_timing;
-    cudaStream_t conn = two_streams ? side : stream;
-    while (sync_events.size() < 2 * (size_t)depth + 2) {
+    // Two sub-waves in flight: a persistent traversal launch ends on its few longest rays (0.2 - 0.3 ms with a handful of warps
+    // busy), and the bounces of ONE wave are a dependency chain — nothing of that wave can fill the hole.  A wave of >= 2
+    // samples per pixel is therefore split into two halves (samples [0, h) and [h, n)), each with its own half of the queues,
+    // its own counters and its own pair of streams: while one half drains a tail, the other half's kernels fill the SMs.  The
+    // per-sample accumulators keep the image independent of the split (k_wf_reduce folds all samples in sample order).
+    const bool split = two_streams && split_waves;
+    if (split && !main2) {
+        int prio_lo = 0, prio_hi = 0;
+        WF_CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        WF_CK(cudaStreamCreateWithPriority(&main2, cudaStreamNonBlocking, prio_hi));
+        WF_CK(cudaStreamCreateWithPriority(&side2, cudaStreamNonBlocking, prio_lo));
+    }
+    while (sync_events.size() < 2 * (2 * (size_t)depth + 2) + 2) {
         cudaEvent_t e;
         WF_CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         sync_events.push_back(e);
     }
+    cudaEvent_t ev_fork = sync_events[sync_events.size() - 2], ev_join = sync_events[sync_events.size() - 1];
+    const size_t lane_events = 2 * (size_t)depth + 2;
     WF_CK(stage_mark(stream, 4));
+    WF_CK(trace_mark(stream, "start", 0, -1));
     for (uint32_t s = 0; s < spp; s += wave) {
-        FrameParams fp = make_params(*this, cam, first_sample + s, 0);
-        fp.wave_spp = std::min(wave, spp - s);
-        const uint32_t cap = max_paths * fp.wave_spp;
-        if (two_streams && s > 0) WF_CK(cudaStreamWaitEvent(stream, sync_events[2 * (depth - 1) + 1], 0));  // the previous wave's last connect read the counters
-        WF_CK(cudaMemsetAsync(d_counts, 0, 8 * sizeof(uint32_t), stream));
-        k_wf_generate<<<(cap + 255) / 256, 256, 0, stream>>>(fp, d_owned_tiles, d_O[0], d_D[0], d_counts);
-        launches++;
-        WF_CK(stage_mark(stream, 0));
-        for (uint32_t b = 0; b < depth; b++) {
-            const int cur = b & 1, nxt = cur ^ 1, sb = b & 1;
-            fp.path_length = b;
-            // ---- main stream: extend(b) -> shade(b) ------------------------------------------------------------------
-            ExtendIO eio{d_O[cur], d_D[cur], d_counts + cur, d_S};
-            if (sv.two_level) WF_CK((launch_persistent_io<ExtendIO, false, true>(stream, sm_count, 0, tune, sv, eio, cap, d_counts + 4)));
-            else WF_CK((launch_persistent_io<ExtendIO, false, false>(stream, sm_count, 0, tune, sv, eio, cap, d_counts + 4)));
-            WF_CK(stage_mark(stream, 1));
-            if (two_streams && b >= 2) WF_CK(cudaStreamWaitEvent(stream, sync_events[2 * (b - 2) + 1], 0));  // shadow queue `sb` is free again: connect(b - 2) is done
-            k_wf_shade<<<shade_blocks, RFW_SHADE_THREADS, 0, stream>>>(fp, ss, d_S, d_O[cur], d_D[cur], d_T[cur], d_O[nxt], d_D[nxt], d_T[nxt], d_shO[sb], d_shD[sb], d_shE[sb],
-                                                         d_term, d_counts + cur, d_counts + nxt, d_counts + 2 + sb);
-            k_wf_advance_paths<<<1, 1, 0, stream>>>(d_counts, d_stats, cur);
-            WF_CK(stage_mark(stream, 2));
-            if (two_streams) {
-                WF_CK(cudaEventRecord(sync_events[2 * b], stream));
-                WF_CK(cudaStreamWaitEvent(conn, sync_events[2 * b], 0));
-            }
-            // ---- connect(b): beside extend(b + 1) / shade(b + 1) -------------------------------------------------------
-            ConnectIO cio{d_shO[sb], d_shD[sb], d_shE[sb], d_counts + 2 + sb, reinterpret_cast<float*>(d_partial)};
-            if (sv.two_level) WF_CK((launch_persistent_io<ConnectIO, true, true>(conn, sm_count, 0, tune, sv, cio, cap, d_counts + 5)));
-            else WF_CK((launch_persistent_io<ConnectIO, true, false>(conn, sm_count, 0, tune, sv, cio, cap, d_counts + 5)));
-            k_wf_advance_shadow<<<1, 1, 0, conn>>>(d_counts, d_stats, sb);
-            if (two_streams) WF_CK(cudaEventRecord(sync_events[2 * b + 1], conn));
-            WF_CK(stage_mark(stream, 3));
-            launches += 5;
+        const uint32_t wspp = std::min(wave, spp - s);
+        const uint32_t half0 = (split && wspp >= 2) ? (wspp + 1) / 2 : wspp;
+        // (the previous wave's reduce on `stream` came after all of its connects: queues, counters and accumulators are free)
+        if (half0 < wspp) {
+            WF_CK(cudaEventRecord(ev_fork, stream));
+            WF_CK(cudaStreamWaitEvent(main2, ev_fork, 0));
         }
-        if (two_streams) WF_CK(cudaStreamWaitEvent(stream, sync_events[2 * (depth - 1) + 1], 0));  // (connects are ordered among themselves: the last one covers all)
+        WF_CK(enqueue_subwave(0, stream, side, two_streams, sv, ss, cam, first_sample + s, half0, depth, 0, 0));
+        if (half0 < wspp) {
+            WF_CK(enqueue_subwave(1, main2, side2, true, sv, ss, cam, first_sample + s + half0, wspp - half0, depth, (size_t)max_paths * half0, half0));
+            WF_CK(cudaStreamWaitEvent(stream, sync_events[lane_events + 2 * (depth - 1) + 1], 0));  // lane 1's last connect (its connects are ordered among themselves)
+            WF_CK(cudaEventRecord(ev_join, main2));                                                // ... and its last shade (terminal accumulators)
+            WF_CK(cudaStreamWaitEvent(stream, ev_join, 0));
+        }
+        if (two_streams) WF_CK(cudaStreamWaitEvent(stream, sync_events[2 * (depth - 1) + 1], 0));  // lane 0's last connect
+        FrameParams fp = make_params(*this, cam, first_sample + s, 0);
+        fp.wave_spp = wspp;
         k_wf_reduce<<<(max_paths + 255) / 256, 256, 0, stream>>>(fp, d_owned_tiles, d_partial, d_term, d_accum);
         launches++;
         WF_CK(stage_mark(stream, 4));
+        WF_CK(trace_mark(stream, "reduce", 0, -1));
     }
     return cudaGetLastError();
 }
@@ -232,7 +308,7 @@ cudaError_t Wavefront::debug_view(cudaStream_t stream, const SceneView& sv, cons
     if (max_paths == 0) return cudaSuccess;
     WF_CK(ensure_wave(1));
     FrameParams fp = make_params(*this, cam, 0, 0);
-    const TraceTuning tune{refill_below, sv.two_level ? tri_batch_two_level : tri_batch, tri_blocked, inst_batch};
+    const TraceTuning tune{refill_below, sv.two_level ? tri_batch_two_level : tri_batch, tri_blocked, inst_batch, 0};
     WF_CK(cudaMemsetAsync(d_counts, 0, 8 * sizeof(uint32_t), stream));
     k_wf_generate_centre<<<(max_paths + 255) / 256, 256, 0, stream>>>(fp, d_owned_tiles, d_O[0], d_D[0], d_counts);
     ExtendIO eio{d_O[0], d_D[0], d_counts + 0, d_S};

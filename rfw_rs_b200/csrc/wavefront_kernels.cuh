@@ -234,13 +234,14 @@ __global__ void __launch_bounds__(256) k_wf_generate_centre(FrameParams fp, cons
 // bookkeeping between bounces: stats += counts, retire the consumed queues.  counts: [0], [1] path queues (ping / pong),
 // [2], [3] shadow queues (even / odd bounce), [4] extend work counter, [5] connect work counter, [6] debug
 __global__ void k_wf_advance_paths(uint32_t* counts, unsigned long long* stats, int cur) {  // after shade(b): the path queue it consumed
-    stats[0] += counts[cur];
-    stats[2] += counts[cur];
+    // (atomic: the two sub-wave lanes of Wavefront::render run their bookkeeping kernels concurrently)
+    atomicAdd(stats + 0, (unsigned long long)counts[cur]);
+    atomicAdd(stats + 2, (unsigned long long)counts[cur]);
     counts[6] = counts[cur];  // debug: size of the queue the last extend/shade consumed
     counts[cur] = 0;
 }
 __global__ void k_wf_advance_shadow(uint32_t* counts, unsigned long long* stats, int sb) {  // after connect(b): the shadow queue it consumed
-    stats[1] += counts[2 + sb];
+    atomicAdd(stats + 1, (unsigned long long)counts[2 + sb]);
     counts[2 + sb] = 0;
 }
 

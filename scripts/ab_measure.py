@@ -31,11 +31,14 @@ del be, d_rays, d_hits, d_occ
 if not os.environ.get("AB_SKIP_C3"):
     w, hh, spp, depth = 1920, 1080, 16, 5
     d3 = scenes.instanced_scene(grid=100, subdiv=3, n_lights=16)
-    b3 = backend.B200Backend(w, hh, tile_size=64, sky=(0.3, 0.35, 0.5)); d3.apply(b3)
+    b3 = backend.B200Backend(w, hh, tile_size=64, sky=(0.3, 0.35, 0.5), rank=int(os.environ.get("AB_RANK", 0)), world=int(os.environ.get("AB_WORLD", 1))); d3.apply(b3)
+    for kv in os.environ.get("AB_OPTS", "").split(","):
+        if "=" in kv:
+            k, v = kv.split("="); b3.set_option(k, int(v))
     view = scenes.camera_view((0.0, 14.0, -62.0), (0.0, -0.25, 1.0), w, hh)
     best = 1e9
     for _ in range(4):
         b3.reset_accumulator(); b3.render_spp(view, spp, depth); best = min(best, b3.render_stats()["render_ms"])
     acc = b3.read_accumulator()
-    line += f" | C3 frame {best:6.2f} ms = {w * hh * spp / best / 1e3:6.1f} Msamples/s crc {zlib.crc32(acc.tobytes()):08x}"
+    line += f" | C3 frame {best:6.2f} ms = {b3.render_stats()['samples'] / best / 1e3:6.1f} Msamples/s crc {zlib.crc32(acc.tobytes()):08x} opts {os.environ.get('AB_OPTS', '')} world {os.environ.get('AB_WORLD', 1)}"
 print(line, flush=True)

@@ -60,14 +60,14 @@ int simt_trace_tiny_stack(const void* scene_view, const RfwRay* rays, uint32_t n
     SceneView sv = *reinterpret_cast<const SceneView*>(scene_view);
     sv.overflow = overflowed;
     const HostRayIO io{reinterpret_cast<const float4*>(rays), n, hits, nullptr};
-    const TraceTuning tune{28, 4, 4, 6};
+    const TraceTuning tune{28, 4, 4, 6, 0};
     return sv.two_level ? run_cta<false, true, HostRayIO, 2, 2>(sv, io, tune, PT_THREADS / 32) : run_cta<false, false, HostRayIO, 2, 2>(sv, io, tune, PT_THREADS / 32);
 }
 // runs the persistent kernel on one CTA of 4 warps.  Returns 0, -1 on a hang (a lane missed a warp collective), -2 on bad set-up.
 int simt_trace(const void* scene_view, const RfwRay* rays, uint32_t n, RfwHit* hits, uint32_t* occluded, int any_hit, int refill_below, int tri_batch, int inst_batch) {
     const SceneView& sv = *reinterpret_cast<const SceneView*>(scene_view);
     const HostRayIO io{reinterpret_cast<const float4*>(rays), n, hits, occluded};
-    const TraceTuning tune{refill_below, tri_batch, 4, inst_batch};
+    const TraceTuning tune{refill_below, tri_batch, 4, inst_batch, 0};
     if (any_hit) return sv.two_level ? run_cta<true, true>(sv, io, tune, PT_THREADS / 32) : run_cta<true, false>(sv, io, tune, PT_THREADS / 32);
     return sv.two_level ? run_cta<false, true>(sv, io, tune, PT_THREADS / 32) : run_cta<false, false>(sv, io, tune, PT_THREADS / 32);
 }
@@ -85,7 +85,7 @@ int simt_trace_streamed(const void* scene_view, const RfwRay* rays, uint32_t n, 
     std::vector<uint32_t> slots(warps, 0u);
     const StreamedRayIO io{RayBufferIO{reinterpret_cast<const float4*>(rays), n, hits, nullptr}, &watermark, slots.data(), &abort_flag,
                            rfw_host_globaltimer() + 20000000000ull};
-    const TraceTuning tune{refill_below, tri_batch, 4, inst_batch};
+    const TraceTuning tune{refill_below, tri_batch, 4, inst_batch, 0};
     std::atomic<bool> done{false};
     uint64_t violations = 0, rounds = 0, best = 0;
     std::thread feeder([&]() {

@@ -70,6 +70,7 @@ static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline void __nanosleep(unsigned) { std::this_thread::yield(); }
 static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL); }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL); }
 static inline size_t __cvta_generic_to_shared(const void*) { return 0; }  // shared "addresses" are offsets into rfw_host_smem
 #define __global__
 #define __launch_bounds__(...)

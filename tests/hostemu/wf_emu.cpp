@@ -46,7 +46,7 @@ int wf_render(const void* scene_view, const InstanceShading* inst_table, const R
     for (int i = 0; i < 2; i++) { O[i].resize(cap); D[i].resize(cap); T[i].resize(cap); shO[i].resize(cap); shD[i].resize(cap); shE[i].resize(cap); }
     uint32_t counts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     unsigned long long st[4] = {0, 0, 0, 0};
-    const TraceTuning tune{28, sv.two_level ? 4 : 4, 4, 6};
+    const TraceTuning tune{28, sv.two_level ? 4 : 4, 4, 6, 0};
     g_abort.store(false);
     // generate
     if (!simt_launch((cap + 255) / 256, 256, [&]() { k_wf_generate(fp, owned_tiles, O[0].data(), D[0].data(), counts); })) return -1;

@@ -823,7 +823,7 @@ def test_c5_full_size_properties(B, oracle_mod):
     pacc = part.read_accumulator()
     assert abs(part.render_stats()["samples"] * 4 / (w * h * spp) - 1.0) < 0.02  # 2 040 tiles, 510 per rank (the last tile row is ragged: 2160 = 33.75 x 64)
     touched = (pacc[..., :3] != 0).any(axis=2)
-    assert 0.2 < touched.mean() <= 0.25
+    assert 0.2 < touched.mean() <= 0.26
     assert np.array_equal(pacc[touched], acc[touched])                        # shard == full on its tiles
     del part, pacc
     cpu = oracle_mod.OracleBackend(det_eps=0.0); desc.apply(cpu)              # (10 M-triangle binned-SAH build: ~40 s)
