@@ -41,7 +41,7 @@ CPU_SAMPLE_RAYS = 1 << 20
 
 def load_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed ncu capture."""
-    p = os.path.join(ROOT, "profiles", "r1c_traffic.json")  # refreshed with every ncu --set full capture of the kernel
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")  # refreshed with every ncu --set full capture of the kernel
     try:
         return float(json.load(open(p))["traffic_bytes_per_launch"]) / 1e9
     except Exception:
@@ -412,6 +412,9 @@ def main():
     # ---- scene (replicated) and this rank's rays -------------------------------------------------------
     desc = scenes.soup_scene(N_TRIS, SOUP_S)
     be = backend.B200Backend(device=local_rank)
+    for kv in os.environ.get("RFWB200_BENCH_OPTS", "").split(","):  # profiling runs only (e.g. l2_persist=1); the driver's runs set nothing
+        if "=" in kv:
+            be.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     t0 = time.time()
     desc.apply(be)
     sync_wall_ms = (time.time() - t0) * 1e3
@@ -478,6 +481,20 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * args.steps * N_RAYS / t.item() / 1e6
+    # the same leg with the reference's own 16-byte hit record (rfwb200_trace_closest_packed): 48 instead of 52 bytes per ray on the host link
+    pin_packed = backend.PinnedArray(N_RAYS, wire.HIT_PACKED)
+    be.trace_closest_packed(pin_rays.array, out=pin_packed.array)
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        be.trace_closest_packed(pin_rays.array, out=pin_packed.array)
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - e0], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_packed_value = world * args.steps * N_RAYS / t.item() / 1e6
+    packed_same = bool(np.array_equal(pin_packed.array["prim"], pin_hits.array["prim"]) and np.array_equal(pin_packed.array["t"], pin_hits.array["t"]))
+    pin_packed.free()
     launches += 0  # e2e launches are counted separately below
     hit_rate = float((pin_hits.array["inst"] >= 0).mean())
 
@@ -503,11 +520,11 @@ def main():
                                 "note": "traversal bytes = nodes/ray x 96 B (the stride a visit fetches) + tris/ray x 48 B requested by the SMs, counted by the instrumented kernel in this run; part of them hit in L1 (ncu: profiles/), the rest go to L2"}
         # issue-side roofline: the kernel is bound by warp-instruction issue, not by bytes (ncu: 70 % of the issue slots busy)
         try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r1c_traffic.json")))
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
             ipr = prof["warp_instructions_per_launch"] / prof["rays_per_launch"]
             sms = torch.cuda.get_device_properties(0).multi_processor_count
             peak_issue = sms * 4 * (clocks.get("sm_mhz") or 1965.0) * 1e6   # 4 schedulers per SM, 1 warp instruction per clock each
-            extra["issue_roofline"] = {"warp_instructions_per_ray": ipr, "source": "STATIC, not measured in this run: ncu smsp__inst_executed.sum / rays of the committed capture named in profiles/r1c_traffic.json (refreshed with every capture of the kernel); only the rate it is multiplied with is live",
+            extra["issue_roofline"] = {"warp_instructions_per_ray": ipr, "source": "STATIC, not measured in this run: ncu smsp__inst_executed.sum / rays of the committed capture named in profiles/r2_traffic.json (refreshed with every capture of the kernel); only the rate it is multiplied with is live",
                                        "achieved_Ginst_per_s": ipr * value / max(1, world) * 1e6 / 1e9, "peak_Ginst_per_s": peak_issue / 1e9,
                                        "frac": ipr * value / max(1, world) * 1e6 / peak_issue, "avg_active_threads_of_32": prof["avg_active_threads_per_warp_instruction"]}
         except Exception:
@@ -547,9 +564,11 @@ def main():
                        "scene": "replicated per GPU", "timing": "CUDA events on the backend stream inside librfwb200, max over ranks"},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": N_RAYS * 32, "d2h_bytes_per_step": N_RAYS * 20,
                     "note": "rfwb200_trace_closest with pinned host buffers: ONE persistent launch consumes rays as the upload lands them (device watermark) while completed 2^18-ray granules are downloaded (per-warp progress slots mirrored to the host); wall clock, max over ranks"},
+            "e2e_packed_hits": {"value": e2e_packed_value, "unit": "Mrays/s", "h2d_bytes_per_step": N_RAYS * 32, "d2h_bytes_per_step": N_RAYS * 16, "same_hits_as_e2e": packed_same,
+                                "note": "rfwb200_trace_closest_packed: the reference's own 16-byte hit record (inst, prim, t, 2 x 16-bit barycentrics; ray_extend.comp:267) instead of the 20-byte RfwHit"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic(), "traffic_unit": "GB per launch (ncu dram__bytes_read+write, profiles/r1c_traffic.json)",
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic(), "traffic_unit": "GB per launch (ncu dram__bytes_read+write, profiles/r2_traffic.json)",
                          "algorithmic_GB_per_launch": BYTES_PER_RAY_CLOSEST * N_RAYS / 1e9,
                          "kernel": "k_trace_persistent<RayBufferIO, closest, single-level>", "algorithmic_bytes_per_ray": BYTES_PER_RAY_CLOSEST, "peak_source": peak_src,
                          "note": "pointer-chasing traversal over an L2-resident BVH: the HBM fraction is small by construction (SURVEY 8d); see extra.traversal_bytes_per_ray for the L2-side traffic"},

@@ -249,6 +249,17 @@ typedef struct RfwHit {
     float v;
 } RfwHit;
 
+/* The reference's own 16-byte hit record: PathState.state as ray_extend.comp:267-268 / ray_gen.comp:66-69 write it —
+ * (inst, prim, t, bary) with bary = uint(65535 u) + (uint(65535 v) << 16) (unpacked in shade.comp:41-46).  Miss: inst = prim = -1,
+ * t = ray.tmax, bary = 0.  rfwb200_trace_closest_packed returns these instead of RfwHit: 16 instead of 20 bytes per ray over the
+ * host link, one 128-bit store per ray on the device. */
+typedef struct RfwHitPacked {
+    int32_t inst;
+    int32_t prim;
+    float t;
+    uint32_t bary;
+} RfwHitPacked;
+
 /* rtbvh's RayPacket4 as rfw fills it (crates/rfw-backend/src/structs.rs:656-667, 701-712): four rays, one SoA lane each.
  * `t` is the current far limit / closest distance (1e34 when generated); inv_direction_* are carried for layout fidelity, the
  * backend derives its own reciprocals. */
@@ -261,6 +272,7 @@ typedef struct RfwRayPacket4 {
 
 #if defined(__cplusplus)
 static_assert(sizeof(RfwRayPacket4) == 160, "RfwRayPacket4");
+static_assert(sizeof(RfwHitPacked) == 16, "RfwHitPacked");
 #endif
 
 typedef struct RfwB200Config {
@@ -394,6 +406,9 @@ RFWB200_API int rfwb200_trace_closest(void* handle, const RfwRay* rays, uint64_t
 RFWB200_API int rfwb200_trace_any(void* handle, const RfwRay* rays, uint64_t num, uint32_t* out_occluded);
 /* same, rays and results already resident in device memory (HBM); asynchronous on the backend's stream
  * unless `sync` != 0 */
+/* the same casts with 16-byte RfwHitPacked output (host buffers / device buffers, at most 2^30 rays per device call) */
+RFWB200_API int rfwb200_trace_closest_packed(void* handle, const RfwRay* rays, uint64_t num, RfwHitPacked* out_hits);
+RFWB200_API int rfwb200_trace_closest_packed_device(void* handle, const RfwRay* d_rays, uint64_t num, RfwHitPacked* d_hits, int sync);
 RFWB200_API int rfwb200_trace_closest_device(void* handle, const RfwRay* d_rays, uint64_t num, RfwHit* d_hits, int sync);
 RFWB200_API int rfwb200_trace_any_device(void* handle, const RfwRay* d_rays, uint64_t num, uint32_t* d_occluded, int sync);
 /* instrumented closest-hit (counts node visits / triangle tests per ray; slower; device buffers) */

@@ -64,6 +64,8 @@ def load_library():
         "rfwb200_set_2d_instances": ([vp, u32, vp, u32], i32),
         "rfwb200_trace_closest": ([vp, vp, u64, vp], i32),
         "rfwb200_trace_any": ([vp, vp, u64, vp], i32),
+        "rfwb200_trace_closest_packed": ([vp, vp, u64, vp], i32),
+        "rfwb200_trace_closest_packed_device": ([vp, vp, u64, vp, i32], i32),
         "rfwb200_intersect_t": ([vp, vp, u64, vp], i32),
         "rfwb200_depth_test": ([vp, vp, u64, vp, vp], i32),
         "rfwb200_intersect4": ([vp, vp, u64, vp, vp, vp], i32),
@@ -299,6 +301,16 @@ class B200Backend:
         hits = np.empty(len(rays), dtype=wire.HIT) if out is None else out
         self._ck(self.L.rfwb200_trace_closest(self.h, _ptr(rays), len(rays), _ptr(hits)), "trace_closest")
         return hits
+
+    def trace_closest_packed(self, rays, out=None):
+        """Closest hits as 16-byte wire.HIT_PACKED records (the reference's own hit record; wire.unpack_hits expands them)."""
+        rays = np.ascontiguousarray(rays)
+        hits = np.empty(len(rays), dtype=wire.HIT_PACKED) if out is None else out
+        self._ck(self.L.rfwb200_trace_closest_packed(self.h, _ptr(rays), len(rays), _ptr(hits)), "trace_closest_packed")
+        return hits
+
+    def trace_closest_packed_device(self, d_rays_ptr, n, d_hits_ptr, sync=True):
+        self._ck(self.L.rfwb200_trace_closest_packed_device(self.h, d_rays_ptr, n, d_hits_ptr, int(sync)), "trace_closest_packed_device")
 
     def trace_any(self, rays, out=None):
         rays = np.ascontiguousarray(rays)

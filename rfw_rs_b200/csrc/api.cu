@@ -47,6 +47,8 @@ int rfwb200_set_2d_instances(void* handle, uint32_t, const float*, uint32_t) { R
 
 int rfwb200_trace_closest(void* handle, const RfwRay* rays, uint64_t num, RfwHit* out) { RFW_GUARD(handle); return b->trace_closest_host(rays, num, out); }
 int rfwb200_trace_any(void* handle, const RfwRay* rays, uint64_t num, uint32_t* out) { RFW_GUARD(handle); return b->trace_any_host(rays, num, out); }
+int rfwb200_trace_closest_packed(void* handle, const RfwRay* rays, uint64_t num, RfwHitPacked* out) { RFW_GUARD(handle); return b->trace_closest_packed_host(rays, num, out); }
+int rfwb200_trace_closest_packed_device(void* handle, const RfwRay* d_rays, uint64_t num, RfwHitPacked* d_hits, int sync) { RFW_GUARD(handle); return b->trace_closest_packed_device(d_rays, num, d_hits, sync); }
 int rfwb200_trace_closest_device(void* handle, const RfwRay* d_rays, uint64_t num, RfwHit* d_hits, int sync) { RFW_GUARD(handle); return b->trace_closest_device(d_rays, num, d_hits, sync); }
 int rfwb200_trace_any_device(void* handle, const RfwRay* d_rays, uint64_t num, uint32_t* d_occ, int sync) { RFW_GUARD(handle); return b->trace_any_device(d_rays, num, d_occ, sync); }
 int rfwb200_trace_closest_counted(void* handle, const RfwRay* d_rays, uint64_t num, RfwHit* d_hits, RfwTraceStats* out) { RFW_GUARD(handle); return b->trace_closest_counted(d_rays, num, d_hits, out); }

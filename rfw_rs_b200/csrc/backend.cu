@@ -1134,19 +1134,27 @@ int Backend::trace_host_streamed(bool any_hit, const RfwRay* rays, uint64_t num,
 #undef STREAM_CK
 }
 
-int Backend::trace_closest_host(const RfwRay* rays, uint64_t num, RfwHit* out) {
+// OutT = RfwHit (20 B) or RfwHitPacked (16 B, the reference's own hit record): the kernels write whichever tcfg.packed_hits selects
+template <typename OutT>
+int Backend::trace_closest_host_t(const RfwRay* rays, uint64_t num, OutT* out) {
     DeviceScope device_scope(cfg.device);
     BK_CUDA(device_scope.status, "cudaSetDevice");
     if (int rc = ensure_synchronized("trace_closest")) return rc;
     if (num == 0) return RFWB200_OK;
     if (!rays || !out) return fail(RFWB200_ERR_INVALID, "trace_closest: null buffer");
+    struct PackedScope {  // (reset on every exit path)
+        TraceConfig& c;
+        ~PackedScope() { c.packed_hits = false; }
+    } packed_scope{tcfg};
+    tcfg.packed_hits = sizeof(OutT) == sizeof(RfwHitPacked);
     BK_CUDA(d_rays.reserve(num), "ray buffer");
     BK_CUDA(d_hits.reserve(num), "hit buffer");
+    OutT* d_out = reinterpret_cast<OutT*>(d_hits.ptr);
     BK_CUDA(cudaStreamSynchronize(stream), "sync");
     BK_CUDA(cudaEventRecord(ev0, copy_in), "event");
     {
         bool used = false;
-        if (int rc = trace_host_streamed<RfwHit>(false, rays, num, out, d_hits.ptr, used)) return rc;
+        if (int rc = trace_host_streamed<OutT>(false, rays, num, out, d_out, used)) return rc;
         if (used) {
             BK_CUDA(cudaEventRecord(ev1, copy_out), "event");
             BK_CUDA(cudaEventSynchronize(ev1), "trace_closest");
@@ -1156,8 +1164,8 @@ int Backend::trace_closest_host(const RfwRay* rays, uint64_t num, RfwHit* out) {
         }
     }
     uint64_t n_launch = 0;
-    cudaError_t e = pipelined<RfwHit>(stream, copy_in, copy_out, chunk_events, chunk_rays, rays, num, d_rays.ptr, d_hits.ptr, out,
-                                      [&](const RfwRay* r, uint32_t n, RfwHit* h) { n_launch++; return trace_closest(tcfg, sv, r, n, h, d_counter); });
+    cudaError_t e = pipelined<OutT>(stream, copy_in, copy_out, chunk_events, chunk_rays, rays, num, d_rays.ptr, d_out, out,
+                                    [&](const RfwRay* r, uint32_t n, OutT* h) { n_launch++; return trace_closest(tcfg, sv, r, n, reinterpret_cast<RfwHit*>(h), d_counter); });
     if (e != cudaSuccess) return cuda_fail(e, "trace_closest");
     launch_count += n_launch;
     BK_CUDA(cudaEventRecord(ev1, copy_out), "event");
@@ -1165,6 +1173,16 @@ int Backend::trace_closest_host(const RfwRay* rays, uint64_t num, RfwHit* out) {
     cudaEventElapsedTime(&trace_stats.total_ms, ev0, ev1);
     trace_stats.rays = num;
     return check_stack_overflow("trace (host buffers)", &trace_stats.stack_overflows);
+}
+int Backend::trace_closest_host(const RfwRay* rays, uint64_t num, RfwHit* out) { return trace_closest_host_t<RfwHit>(rays, num, out); }
+int Backend::trace_closest_packed_host(const RfwRay* rays, uint64_t num, RfwHitPacked* out) { return trace_closest_host_t<RfwHitPacked>(rays, num, out); }
+int Backend::trace_closest_packed_device(const RfwRay* d_r, uint64_t num, RfwHitPacked* d_h, int sync) {
+    if (num > (1ull << 30)) return fail(RFWB200_ERR_INVALID, "trace_closest_packed_device: at most 2^30 rays per call");
+    if (tcfg.variant == TRACE_VARIANT_STREAMED_RESIDENT) return fail(RFWB200_ERR_INVALID, "trace_closest_packed_device: not with trace_variant 2");
+    tcfg.packed_hits = true;
+    const int rc = trace_closest_device(d_r, num, reinterpret_cast<RfwHit*>(d_h), sync);
+    tcfg.packed_hits = false;
+    return rc;
 }
 
 int Backend::trace_any_host(const RfwRay* rays, uint64_t num, uint32_t* out) {

@@ -89,6 +89,9 @@ public:
     int resize(uint32_t w, uint32_t h);
 
     int trace_closest_host(const RfwRay* rays, uint64_t num, RfwHit* out);
+    int trace_closest_packed_host(const RfwRay* rays, uint64_t num, RfwHitPacked* out);
+    int trace_closest_packed_device(const RfwRay* d_rays, uint64_t num, RfwHitPacked* d_hits, int sync);
+    template <typename OutT> int trace_closest_host_t(const RfwRay* rays, uint64_t num, OutT* out);
     int trace_any_host(const RfwRay* rays, uint64_t num, uint32_t* out);
     int trace_closest_device(const RfwRay* d_rays, uint64_t num, RfwHit* d_hits, int sync);
     int trace_any_device(const RfwRay* d_rays, uint64_t num, uint32_t* d_occ, int sync);

@@ -7,18 +7,29 @@
 
 namespace rfw {
 
+// barycentrics as two 16-bit fixed-point numbers, ray_extend.comp:267 (uint(65535 u) + (uint(65535 v) << 16)); clamped to [0, 1]
+// first: the watertight test can return -1 ulp on an edge, and a negative float -> uint conversion is not defined in C++
+__device__ __forceinline__ uint32_t pack_bary16_sat(float u, float v) {
+    return (uint32_t)(65535.0f * fminf(fmaxf(u, 0.0f), 1.0f)) + ((uint32_t)(65535.0f * fminf(fmaxf(v, 0.0f), 1.0f)) << 16);
+}
+
 // C-ABI ray buffers: RfwRay (32 B) in, RfwHit (20 B) / uint32 flag out; streamed (evict-first) accesses
 struct RayBufferIO {
     const float4* rays;
     uint32_t n;
     RfwHit* hits;
     uint32_t* occluded;
+    float4* packed;  // != nullptr: 16-byte RfwHitPacked records instead of `hits` (one STG.128 per ray; the reference's own hit record, ray_extend.comp:267)
     __device__ __forceinline__ uint32_t count() const { return n; }
     __device__ __forceinline__ void load(uint32_t i, float4& r0, float4& r1) const {
         r0 = __ldcs(rays + 2 * (size_t)i);
         r1 = __ldcs(rays + 2 * (size_t)i + 1);
     }
     __device__ __forceinline__ void store_closest(uint32_t i, const Hit& h) const {
+        if (packed) {
+            __stcs(packed + i, make_float4(__int_as_float(h.inst), __int_as_float(h.prim), h.t, __uint_as_float(pack_bary16_sat(h.u, h.v))));
+            return;
+        }
         float* out = reinterpret_cast<float*>(hits + i);
         __stcs(reinterpret_cast<int*>(out) + 0, h.inst);
         __stcs(reinterpret_cast<int*>(out) + 1, h.prim);

@@ -22,7 +22,7 @@ namespace rfw {
 
 template <bool ANY, bool COUNT>
 __global__ void __launch_bounds__(128) k_trace_simple(SceneView sv, const float4* __restrict__ rays, uint32_t n, RfwHit* __restrict__ hits, uint32_t* __restrict__ occluded,
-                                                      unsigned long long* __restrict__ counters) {
+                                                      unsigned long long* __restrict__ counters, bool packed = false) {
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
     TraceCounters ctr{0, 0, 0};
     if (i < n) {
@@ -30,7 +30,9 @@ __global__ void __launch_bounds__(128) k_trace_simple(SceneView sv, const float4
         Hit h;
         const bool occ = trace_ray<ANY, COUNT, 48>(sv, xyz(r0), xyz(r1), r0.w, r1.w, h, &ctr);
         if (ANY) occluded[i] = occ ? 1u : 0u;
-        else {
+        else if (packed) {
+            reinterpret_cast<float4*>(hits)[i] = make_float4(__int_as_float(h.inst), __int_as_float(h.prim), h.t, __uint_as_float(pack_bary16_sat(h.u, h.v)));
+        } else {
             RfwHit out;
             out.inst = h.inst; out.prim = h.prim; out.t = h.t; out.u = h.u; out.v = h.v;
             hits[i] = out;
@@ -129,7 +131,7 @@ static cudaError_t launch_persistent_tiny_stack(const TraceConfig& cfg, const Sc
 
 template <bool ANY, bool TWO_LEVEL>
 static cudaError_t launch_persistent(const TraceConfig& cfg, const SceneView& sv, const float4* rays, uint32_t n, RfwHit* hits, uint32_t* occ, uint32_t* counter) {
-    RayBufferIO io{rays, n, hits, occ};
+    RayBufferIO io{rays, n, cfg.packed_hits ? nullptr : hits, occ, cfg.packed_hits ? reinterpret_cast<float4*>(hits) : nullptr};
     if (cfg.variant == TRACE_VARIANT_TINY_STACK) return launch_persistent_tiny_stack<ANY, TWO_LEVEL>(cfg, sv, io, n, counter);
     return launch_persistent_dispatch<ANY, TWO_LEVEL>(cfg, sv, io, n, counter);
 }
@@ -207,7 +209,7 @@ cudaError_t trace_sorted(const TraceConfig& cfg, const SceneView& sv, bool any_h
     sc.launches += 3;
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    const PermutedRayIO io{RayBufferIO{rays, n, d_hits, d_occluded}, sc.perm};
+    const PermutedRayIO io{RayBufferIO{rays, n, cfg.packed_hits ? nullptr : d_hits, d_occluded, cfg.packed_hits ? reinterpret_cast<float4*>(d_hits) : nullptr}, sc.perm};
     const TraceTuning tune{cfg.refill_below, sv.two_level ? cfg.tri_batch_two_level : cfg.tri_batch, cfg.tri_blocked, cfg.inst_batch, 0};
     sc.launches++;
     if (any_hit) return sv.two_level ? launch_persistent_io<PermutedRayIO, true, true>(cfg.stream, cfg.sm_count, cfg.blocks_per_sm, tune, sv, io, n, d_counter)
@@ -220,7 +222,7 @@ cudaError_t trace_closest(const TraceConfig& cfg, const SceneView& sv, const Rfw
     if (n == 0) return cudaSuccess;
     const float4* rays = reinterpret_cast<const float4*>(d_rays);
     if (cfg.variant == TRACE_VARIANT_SIMPLE) {
-        k_trace_simple<false, false><<<(n + 127) / 128, 128, 0, cfg.stream>>>(sv, rays, n, d_hits, nullptr, nullptr);
+        k_trace_simple<false, false><<<(n + 127) / 128, 128, 0, cfg.stream>>>(sv, rays, n, d_hits, nullptr, nullptr, cfg.packed_hits);
         return cudaGetLastError();
     }
     return sv.two_level ? launch_persistent<false, true>(cfg, sv, rays, n, d_hits, nullptr, d_counter)
@@ -249,7 +251,7 @@ uint32_t trace_streamed_warps(const TraceConfig& cfg, const SceneView& sv, bool 
 cudaError_t trace_streamed(const TraceConfig& cfg, const SceneView& sv, bool any_hit, const RfwRay* d_rays, uint32_t n, RfwHit* d_hits, uint32_t* d_occluded,
                            uint32_t* d_counter, const StreamSync& sync) {
     if (n == 0) return cudaSuccess;
-    StreamedRayIO io{RayBufferIO{reinterpret_cast<const float4*>(d_rays), n, d_hits, d_occluded}, sync.watermark, sync.warp_slots, sync.abort_flag, sync.deadline_ns};
+    StreamedRayIO io{RayBufferIO{reinterpret_cast<const float4*>(d_rays), n, cfg.packed_hits ? nullptr : d_hits, d_occluded, cfg.packed_hits ? reinterpret_cast<float4*>(d_hits) : nullptr}, sync.watermark, sync.warp_slots, sync.abort_flag, sync.deadline_ns};
     const TraceTuning tune{cfg.refill_below, sv.two_level ? cfg.tri_batch_two_level : cfg.tri_batch, cfg.tri_blocked, cfg.inst_batch, 0};
     if (any_hit) {
         return sv.two_level ? launch_persistent_io<StreamedRayIO, true, true>(cfg.stream, cfg.sm_count, cfg.blocks_per_sm, tune, sv, io, n, d_counter)

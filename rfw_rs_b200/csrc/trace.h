@@ -20,6 +20,7 @@ struct TraceConfig {
     int tri_blocked = 4;     // speculative traversal only (PT_DEFER > 0): ... or when this many lanes cannot traverse any further
     int inst_batch = 6;      // two-level kernels: enter instances when this many lanes wait at a TLAS leaf (trace_kernel.cuh, step c)
     int tri_batch = 4;       // single-level kernels: run the triangle phase when this many lanes have pending leaf triangles
+    bool packed_hits = false;  // closest-hit output as 16-byte RfwHitPacked records (the d_hits pointers then address those)
     int min_blocks = 0;      // __launch_bounds__ min CTAs/SM variant of the persistent kernel (3,4,5,6,8); 0 = tuned default
 };
 

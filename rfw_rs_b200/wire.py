@@ -67,6 +67,19 @@ DIRECTIONAL_LIGHT = np.dtype([("direction", f4, 3), ("energy", f4), ("radiance",
 
 RAY = np.dtype([("origin", f4, 3), ("tmin", f4), ("direction", f4, 3), ("tmax", f4)])
 HIT = np.dtype([("inst", np.int32), ("prim", np.int32), ("t", f4), ("u", f4), ("v", f4)])
+# the reference's 16-byte hit record (PathState.state, ray_extend.comp:267): bary = u16(65535 u) | u16(65535 v) << 16
+HIT_PACKED = np.dtype([("inst", np.int32), ("prim", np.int32), ("t", f4), ("bary", np.uint32)])
+
+
+def unpack_hits(packed):
+    """RfwHitPacked -> RfwHit with the reference's unpacking (shade.comp:41-46: (bary & 65535) / 65535, (bary >> 16) / 65535)."""
+    h = np.zeros(len(packed), HIT)
+    h["inst"], h["prim"], h["t"] = packed["inst"], packed["prim"], packed["t"]
+    h["u"] = (packed["bary"] & np.uint32(65535)).astype(f4) / f4(65535.0)
+    h["v"] = (packed["bary"] >> np.uint32(16)).astype(f4) / f4(65535.0)
+    return h
+
+
 # rtbvh RayPacket4 as rfw fills it (crates/rfw-backend/src/structs.rs:656-667): ten SoA lanes of four floats
 RAY_PACKET4 = np.dtype([(n, f4, 4) for n in ("origin_x", "origin_y", "origin_z", "direction_x", "direction_y", "direction_z", "t",
                                              "inv_direction_x", "inv_direction_y", "inv_direction_z")])
@@ -88,7 +101,7 @@ EXPECTED_SIZES = {
     "RfwAabb": (AABB, 32), "RfwRTTriangle": (RT_TRIANGLE, 176), "RfwVertex3D": (VERTEX3D, 64), "RfwVertexMesh": (VERTEX_MESH, 48),
     "RfwJointData": (JOINT_DATA, 32), "RfwDeviceMaterial": (DEVICE_MATERIAL, 96), "RfwCameraView3D": (CAMERA_VIEW3D, 128),
     "RfwAreaLight": (AREA_LIGHT, 96), "RfwSpotLight": (SPOT_LIGHT, 48), "RfwPointLight": (POINT_LIGHT, 32),
-    "RfwDirectionalLight": (DIRECTIONAL_LIGHT, 32), "RfwRay": (RAY, 32), "RfwHit": (HIT, 20), "RfwRayPacket4": (RAY_PACKET4, 160),
+    "RfwDirectionalLight": (DIRECTIONAL_LIGHT, 32), "RfwRay": (RAY, 32), "RfwHit": (HIT, 20), "RfwRayPacket4": (RAY_PACKET4, 160), "RfwHitPacked": (HIT_PACKED, 16),
 }
 for _name, (_dt, _sz) in EXPECTED_SIZES.items():
     assert _dt.itemsize == _sz, (_name, _dt.itemsize, _sz)

@@ -5,11 +5,17 @@ from oracle import oracle as orc
 from rfw_rs_b200 import backend, scenes, wire
 np.set_printoptions(precision=9, linewidth=220)
 sky = (0.3, 0.35, 0.5)
-w, h, depth = 256, 144, 5
-view = scenes.camera_view((0, 3.5, -9.0), (0, -0.35, 1.0), w, h)
-desc = scenes.instanced_scene(grid=10, subdiv=2, n_lights=16)
+w, h, depth = int(os.environ.get("DBG_W", 256)), int(os.environ.get("DBG_H", 144)), 5
+if os.environ.get("DBG_SCENE", "").startswith("c5:"):   # DBG_SCENE=c5:<triangles>: the C5 soup (+ ground + 64 lights) from the C5 camera
+    desc = scenes.c5_scene(int(os.environ["DBG_SCENE"][3:])); view = scenes.c5_view(w, h)
+else:
+    view = scenes.camera_view((0, 3.5, -9.0), (0, -0.35, 1.0), w, h)
+    desc = scenes.instanced_scene(grid=10, subdiv=2, n_lights=16)
+orc.build()
 cpu = orc.OracleBackend(det_eps=0.0); desc.apply(cpu)
 gpu = backend.B200Backend(w, h, sky=sky); desc.apply(gpu)
+for kv in os.environ.get("DBG_OPTS", "").split(","):   # e.g. DBG_OPTS=tri_test=1
+    if "=" in kv: gpu.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 found = 0
 for s in range(4):
     gpu.reset_accumulator(); gpu.set_option("sample_count", s); gpu.render_spp(view, 1, depth)
@@ -17,6 +23,7 @@ for s in range(4):
     r, st = cpu.render(view, w, h, 1, depth, sky=sky, first_sample=s); r = r[..., :3]
     d = np.abs(a - r).max(axis=2)
     ys, xs = np.nonzero(d > 1e-3 * np.maximum(1.0, r.max(axis=2)))
+    print(f"sample {s}: {len(ys)} of {w * h} pixels differ by more than 1e-3 (relative to max(1, radiance)); all-pixel RMSE {float(np.sqrt(((a - r) ** 2).mean())):.3e}", flush=True)
     for y, x in zip(ys, xs):
         pid = x + y * w
         probe = cpu.path_probe(view, w, h, pid, s, depth, sky=sky)

@@ -83,7 +83,7 @@ int simt_trace_streamed(const void* scene_view, const RfwRay* rays, uint32_t n, 
     const int warps = PT_THREADS / 32;
     uint32_t watermark = 0, abort_flag = 0;
     std::vector<uint32_t> slots(warps, 0u);
-    const StreamedRayIO io{RayBufferIO{reinterpret_cast<const float4*>(rays), n, hits, nullptr}, &watermark, slots.data(), &abort_flag,
+    const StreamedRayIO io{RayBufferIO{reinterpret_cast<const float4*>(rays), n, hits, nullptr, nullptr}, &watermark, slots.data(), &abort_flag,
                            rfw_host_globaltimer() + 20000000000ull};
     const TraceTuning tune{refill_below, tri_batch, 4, inst_batch, 0};
     std::atomic<bool> done{false};

@@ -3,6 +3,7 @@ Geometry comes from the committed fixtures tests/golden/{cesium_man,pica}.npz (m
 tests/golden/make_c1_fixtures.py; the GPU box has no /root/reference).  CPU tier: the oracle reproduces its golden hits
 bit-exactly and the two submission variants (C1a flattened / C1b BLAS per mesh + TLAS) agree.  GPU tier: the CUDA path
 matches the oracle on all 921 600 pixels for both variants."""
+import json
 import os
 
 import numpy as np
@@ -47,6 +48,11 @@ def test_c1_oracle_reproduces_golden_and_variants_agree(oracle_mod, name, ntris,
     assert np.allclose(h2["t"][both], hits["t"][both], rtol=2e-4, atol=1e-5)
 
 
+# pica's classified near-ties under the watertight test (coplanar duplicated faces: every pixel looking at such a pair is an exact-depth
+# tie between two triangles): bound = twice the measured count (1 364 of 921 600 rays = 1.48e-3, profiles/r2_image_parity.md)
+PICA_TIE_FRACTION = 3e-3
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["cesium_man", "pica"])
 def test_c1_gpu_primary_cast_both_variants(oracle_mod, name):
@@ -71,8 +77,24 @@ def test_c1_gpu_primary_cast_both_variants(oracle_mod, name):
         hits = gpu.cast_primary(view)
         # pica has coplanar duplicated faces (exact depth ties between different triangles): looser COUNT bound, every
         # disagreement must still classify as a near-tie
-        parity.compare_hits(rays, hits, ref, parity.lookup_from_desc(desc), f"{name}/{label}", max_fraction=5e-3 if name == "pica" else 2e-5)
+        nbad = parity.compare_hits(rays, hits, ref, parity.lookup_from_desc(desc), f"{name}/{label}", max_fraction=PICA_TIE_FRACTION if name == "pica" else 2e-5)
+        if os.environ.get("RFWB200_IMAGE_LOG"):
+            with open(os.environ["RFWB200_IMAGE_LOG"], "a") as f:
+                f.write(json.dumps({"label": f"{name}/{label} classified near-ties", "rays": len(rays), "count": int(nbad), "fraction": nbad / len(rays)}) + "\n")
         results[label] = hits
+        # ... and with the reference's own triangle arithmetic (option tri_test = 1) t is the oracle's bit for bit wherever the ids
+        # agree, and they agree everywhere on CesiumMan.  pica keeps ~20 of 921 600 rays (from 1 364): coplanar duplicated faces
+        # whose two t values differ in the last bit — which of the two survives then depends on which the (conservative, but
+        # float32) box tests of the two different trees let through; every one of them still classifies as a near-tie.
+        gpu.set_option("tri_test", 1)
+        exact = gpu.trace_closest(rays)   # (the oracle's own primary rays: cast_primary generates them on the device with contracted FMAs, an ulp apart)
+        gpu.set_option("tri_test", 0)
+        agree = (exact["inst"] == ref["inst"]) & (exact["prim"] == ref["prim"])
+        assert np.array_equal(exact["t"][agree].view(np.uint32), ref["t"][agree].view(np.uint32)), label
+        if name == "pica":
+            assert parity.compare_hits(rays, exact, ref, parity.lookup_from_desc(desc), f"{name}/{label}/tri_test=1", max_fraction=1e-4) <= 92
+        else:
+            assert agree.all(), (label, int((~agree).sum()))
         st = gpu.build_stats()
         assert st["num_triangles"] == len(flat.meshes[0])
         if label == "C1b":

@@ -146,6 +146,46 @@ def test_reference_triangle_arithmetic_option_bit_exact_on_the_gpu(B, oracle_mod
 
 
 @pytest.mark.parametrize("two_level", [False, True])
+def test_packed_hit_records(B, torch_cuda, two_level):
+    """rfwb200_trace_closest_packed: the reference's own 16-byte hit record (inst, prim, t, bary16 | bary16 << 16; ray_extend.comp:267)
+    through every path that writes hits — pinned host buffers (one persistent launch fed by the upload), pageable host buffers
+    (chunked pipeline), device buffers, the one-thread-per-ray kernel and the origin-binned order: ids and t bit-identical to the
+    20-byte records, barycentrics equal after the reference's 16-bit quantisation (shade.comp:41-46)."""
+    desc = scenes.instanced_scene(grid=8, subdiv=2, n_lights=4) if two_level else scenes.soup_scene(100000, 0.015)
+    gpu = B.B200Backend(); desc.apply(gpu)
+    n = (1 << 19) + 77
+    rays = scenes.random_rays(n, lo=-4.0, hi=4.0) if two_level else scenes.random_rays(n)
+    full = gpu.trace_closest(rays)
+
+    def check(p, label):
+        assert np.array_equal(p["inst"], full["inst"]) and np.array_equal(p["prim"], full["prim"]), label
+        assert np.array_equal(p["t"].view(np.uint32), full["t"].view(np.uint32)), label
+        u = np.floor(np.float32(65535.0) * np.clip(full["u"], 0, 1)).astype(np.uint32)
+        v = np.floor(np.float32(65535.0) * np.clip(full["v"], 0, 1)).astype(np.uint32)
+        assert np.array_equal(p["bary"], u + (v << np.uint32(16))), label
+        h = wire.unpack_hits(p)
+        assert np.abs(h["u"] - full["u"]).max() <= 1.6e-5 and np.abs(h["v"] - full["v"]).max() <= 1.6e-5
+
+    check(gpu.trace_closest_packed(rays), "pageable host buffers")
+    pr = B.PinnedArray(n, wire.RAY); pp = B.PinnedArray(n, wire.HIT_PACKED)
+    pr.array[:] = rays
+    check(gpu.trace_closest_packed(pr.array, out=pp.array).copy(), "pinned host buffers (streamed launch)")
+    d_rays = dev_buf(torch_cuda, rays)
+    d_p = torch_cuda.empty(n * 16, dtype=torch_cuda.uint8, device="cuda")
+    for opt in ({}, {"trace_variant": 1}, {"sort_rays": 1}):
+        for k, val in opt.items():
+            gpu.set_option(k, val)
+        d_p.zero_()
+        gpu.trace_closest_packed_device(d_rays.data_ptr(), n, d_p.data_ptr())
+        check(np.frombuffer(d_p.cpu().numpy().tobytes(), dtype=wire.HIT_PACKED), f"device buffers {opt}")
+        for k in opt:
+            gpu.set_option(k, 0)
+    # and the 20-byte path is untouched by the calls above
+    assert np.array_equal(gpu.trace_closest(rays).view(np.uint8), full.view(np.uint8))
+    pr.free(); pp.free()
+
+
+@pytest.mark.parametrize("two_level", [False, True])
 def test_tintersector_twin_methods(B, oracle_mod, torch_cuda, two_level):
     """The rest of the CPU twin TIntersector (crates/rfw-scene/src/intersector.rs:77-166) through the C ABI: intersect_t (t or None),
     depth_test ((t, nodes visited)), intersect4 (rtbvh ray packets: ids out, packet.t lowered to the hit) and occludes4 — against
@@ -681,6 +721,33 @@ def test_literal_rmse_bar_with_the_reference_triangle_arithmetic(B, oracle_mod):
     check_image(acc / 16, ref / 16, "instanced, reference triangle arithmetic, 16 spp")
 
 
+def test_blue_noise_render_matches_the_oracle(B, oracle_mod):
+    """The sampler of the first 256 samples per pixel (blueNoiseSampler, ray_gen.comp:72-91,109-115; shade.comp:190-196,216-222)
+    with tables handed over through rfwb200_set_blue_noise — a synthetic table of the reference's shape here (the real one is
+    reference data; tests/test_ref_glsl.py pins the sampler against it in the container).  Frames 0..3 use the tables on both
+    sides; continuing to 258 samples crosses sample 256, where both switch to the hash RNG; without tables the image differs."""
+    table = np.random.default_rng(77).integers(0, 256, 65536 * 5).astype(np.uint32)
+    desc = scenes.instanced_scene(grid=6, subdiv=1, n_lights=4)
+    w, h, depth, sky = 64, 36, 4, (0.2, 0.2, 0.3)
+    view = scenes.camera_view((0, 3.0, -7.0), (0, -0.4, 1.0), w, h, aperture=0.03)
+    gpu = B.B200Backend(w, h, sky=sky); desc.apply(gpu); gpu.set_blue_noise(table)
+    cpu = oracle_mod.OracleBackend(det_eps=0.0); desc.apply(cpu); cpu.set_blue_noise(table)
+    gpu.render_spp(view, 4, depth)
+    ref4, st4 = cpu.render(view, w, h, 4, depth, clamp=10.0, sky=sky)
+    rs = gpu.render_stats()
+    assert abs(rs["extension_rays"] - st4["extension_rays"]) <= 2 and abs(rs["shadow_rays"] - st4["shadow_rays"]) <= 2
+    check_image(gpu.read_accumulator() / 4, ref4 / 4, "blue noise, samples 0..3")
+    gpu.render_spp(view, 254, depth)                          # samples 4..257: crosses the switch to the hash RNG at 256
+    assert gpu.sample_count == 258
+    ref258, _ = cpu.render(view, w, h, 258, depth, clamp=10.0, sky=sky)
+    check_image(gpu.read_accumulator() / 258, ref258 / 258, "blue noise, samples 0..257")
+    plain = B.B200Backend(w, h, sky=sky); desc.apply(plain)   # no tables: the hash RNG from sample 0
+    plain.render_spp(view, 4, depth)
+    assert np.abs(plain.read_accumulator() - ref4).mean() > 1e-2
+    gpu.set_blue_noise(None); gpu.reset_accumulator(); gpu.render_spp(view, 4, depth)
+    assert np.array_equal(gpu.read_accumulator(), plain.read_accumulator())    # tables withdrawn: the hash RNG again
+
+
 def test_backend_render_resets_on_camera_change(B):
     desc = scenes.instanced_scene(grid=4, subdiv=1, n_lights=2)
     w, h = 64, 48
@@ -826,12 +893,34 @@ def test_c5_full_size_properties(B, oracle_mod):
     assert 0.2 < touched.mean() <= 0.26
     assert np.array_equal(pacc[touched], acc[touched])                        # shard == full on its tiles
     del part, pacc
+    # The oracle on three 96x64 windows of the same frame.  10 M triangles of ~4 mm: every ray passes within float32 resolution of
+    # some triangle edge with probability ~1e-4 per segment, so ~0.7 % of the pixels (16 spp x 1.6 segments) hold a path that went
+    # the other way at an edge.  scripts/dbg_diverge.py (DBG_SCENE=c5:10000000, profiles/r2_image_parity.md) shows where: given the
+    # SAME ray both sides return the same hit bit for bit (option tri_test = 1) — what differs is the ray itself, by one ulp, from
+    # the rounding of the lens / BSDF sampling arithmetic (contracted FMAs, CUDA's vs glibc's sinf / cosf; GLSL leaves both
+    # implementation-defined, so two conforming runs of the reference differ the same way).  The 0.2 % trimming of check_image is
+    # sized for the instanced scenes; stated bars here, for either triangle test: all-pixel RMSE <= 1e-2 and <= 2 % of the pixels
+    # off by more than 1e-3.  (The sparse 20 k-triangle flavour of the same scene meets the literal bar:
+    # test_literal_rmse_bar_with_the_reference_triangle_arithmetic.)
     cpu = oracle_mod.OracleBackend(det_eps=0.0); desc.apply(cpu)              # (10 M-triangle binned-SAH build: ~40 s)
+    gpu.set_option("tri_test", 1)
+    gpu.reset_accumulator(); gpu.render_spp(view, spp, depth)
+    acc_mt = gpu.read_accumulator()
+    gpu.set_option("tri_test", 0)
     for (x0, y0) in ((1900, 1100), (700, 1500), (2900, 800)):
         x1, y1 = x0 + 96, y0 + 64
         ref, _ = cpu.render(view, w, h, spp, depth, clamp=10.0, sky=sky, window=(x0, y0, x1, y1))
-        assert ref[y0:y1, x0:x1, :3].mean() > 0.01
-        check_image(acc[y0:y1, x0:x1] / spp, ref[y0:y1, x0:x1] / spp, f"C5 window ({x0},{y0})")
+        r = ref[y0:y1, x0:x1] / spp
+        assert r[..., :3].mean() > 0.01
+        for label, img in (("watertight", acc), ("tri_test=1", acc_mt)):
+            a = img[y0:y1, x0:x1] / spp
+            d = np.abs(a[..., :3] - r[..., :3]).max(axis=2)
+            assert rmse(a, r) <= ALL_PIXEL_RMSE and (d > 1e-3).mean() <= 0.02, (x0, y0, label, rmse(a, r), float((d > 1e-3).mean()))
+            assert np.median(d) <= 1e-5                                       # the bulk of the pixels agrees to rounding
+            if os.environ.get("RFWB200_IMAGE_LOG"):
+                with open(os.environ["RFWB200_IMAGE_LOG"], "a") as f:
+                    f.write(json.dumps({"label": f"C5 window ({x0},{y0}) {label}", "pixels": int(d.size), "all_pixel_rmse": rmse(a, r), "pixels_off_1e-3": float((d > 1e-3).mean()),
+                                        "median_abs_diff": float(np.median(d))}) + "\n")
 
 
 def test_tile_sharding_is_invariant(B, torch_cuda):
