@@ -3,6 +3,9 @@
 use rfw::prelude::*;
 use std::os::raw::{c_char, c_int, c_void};
 
+// the reference's sampler tables, moved over unchanged from backends/gpu-rt/src/blue_noise.rs (data + create_blue_noise_buffer)
+mod blue_noise;
+
 #[repr(C)]
 struct RfwMeshData3D {
     triangles: *const RTTriangle, num_triangles: u32,
@@ -38,6 +41,13 @@ extern "C" {
     fn rfwb200_synchronize(h: *mut c_void) -> c_int;
     fn rfwb200_render(h: *mut c_void, view: *const CameraView3D, mode: u32) -> c_int;
     fn rfwb200_resize(h: *mut c_void, w: u32, hgt: u32, scale: f64) -> c_int;
+    fn rfwb200_set_blue_noise(h: *mut c_void, table: *const u32, n: u32) -> c_int;
+    // multi-GPU (one process per GPU; the accumulator gather over NCCL lives inside the library)
+    pub fn rfwb200_comm_unique_id(out_id: *mut u8) -> c_int;
+    pub fn rfwb200_comm_init(h: *mut c_void, unique_id: *const u8, rank: u32, world: u32) -> c_int;
+    pub fn rfwb200_comm_destroy(h: *mut c_void) -> c_int;
+    pub fn rfwb200_gather_image(h: *mut c_void, root: u32, d_image: *mut f32) -> c_int;
+    pub fn rfwb200_render_gather(h: *mut c_void, view: *const CameraView3D, spp: u32, depth: u32, root: u32, d_image: *mut f32) -> c_int;
     fn rfwb200_last_error() -> *const c_char;
 }
 
@@ -60,6 +70,9 @@ impl FromWindowHandle for B200Backend {
             let msg = unsafe { std::ffi::CStr::from_ptr(rfwb200_last_error()) }.to_string_lossy().into_owned();
             return Err(msg.into());
         }
+        // the sampler tables of the first 256 samples: reference data (backends/gpu-rt/src/blue_noise.rs:40970-41004), handed over once
+        let tables: Vec<u32> = blue_noise::create_blue_noise_buffer();
+        check(unsafe { rfwb200_set_blue_noise(handle, tables.as_ptr(), tables.len() as u32) });
         Ok(Box::new(Self { handle }))
     }
 }

@@ -907,7 +907,7 @@ def test_c5_full_size_properties(B, oracle_mod):
     gpu.reset_accumulator(); gpu.render_spp(view, spp, depth)
     acc_mt = gpu.read_accumulator()
     gpu.set_option("tri_test", 0)
-    for (x0, y0) in ((1900, 1100), (700, 1500), (2900, 800)):
+    for (x0, y0) in ((1900, 1100), (700, 1500), (2300, 900)):
         x1, y1 = x0 + 96, y0 + 64
         ref, _ = cpu.render(view, w, h, spp, depth, clamp=10.0, sky=sky, window=(x0, y0, x1, y1))
         r = ref[y0:y1, x0:x1] / spp
