@@ -12,7 +12,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+# RFWB200_ORACLE_LIB: another build of the same source (bench.py's CPU arm compiles one with -march=native on the box it runs on)
+_LIB_PATH = os.environ.get("RFWB200_ORACLE_LIB") or os.path.join(_HERE, "liboracle.so")
 
 MODE_MBVH, MODE_BVH2, MODE_BRUTE = 0, 1, 2
 
@@ -21,6 +22,8 @@ HIT = np.dtype([("inst", np.int32), ("prim", np.int32), ("t", np.float32), ("u",
 
 
 def build(force=False):
+    if os.environ.get("RFWB200_ORACLE_LIB"):
+        return _LIB_PATH
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(os.path.join(_HERE, "oracle.cpp")):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _LIB_PATH

@@ -4,11 +4,12 @@ import numpy as np
 from rfw_rs_b200 import backend, scenes
 w, h = int(os.environ.get("W", 1920)), int(os.environ.get("H", 1080))
 spp, depth, grid = int(os.environ.get("SPP", 4)), int(os.environ.get("DEPTH", 5)), int(os.environ.get("GRID", 100))
-desc = scenes.instanced_scene(grid=grid, subdiv=3, n_lights=16)
+c5 = os.environ.get("SCENE", "").startswith("c5:")   # SCENE=c5:<triangles>: the C5 soup from the C5 camera (use W=3840 H=2160)
+desc = scenes.c5_scene(int(os.environ["SCENE"][3:])) if c5 else scenes.instanced_scene(grid=grid, subdiv=3, n_lights=16)
 be = backend.B200Backend(w, h, sky=(0.3, 0.35, 0.5), tile_size=64, rank=int(os.environ.get("RANK_", 0)), world=int(os.environ.get("WORLD_", 1))); desc.apply(be)
 for kv in os.environ.get("OPTS", "").split(","):
     if "=" in kv: be.set_option(kv.split("=")[0], int(kv.split("=")[1]))
-view = scenes.camera_view((0.0, 14.0, -62.0), (0.0, -0.25, 1.0), w, h)
+view = scenes.c5_view(w, h) if c5 else scenes.camera_view((0.0, 14.0, -62.0), (0.0, -0.25, 1.0), w, h)
 if "WAVE_PATHS" in os.environ: be.set_option("wave_paths", int(os.environ["WAVE_PATHS"]))
 be.render_spp(view, 1, depth); be.reset_accumulator()
 for _ in range(int(os.environ.get("REPS", 2))):
