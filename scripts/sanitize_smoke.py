@@ -23,4 +23,23 @@ for m in range(12):
 b4 = backend.B200Backend(); many.apply(b4); r4 = _sc.random_rays(2000, lo=-2.0, hi=2.0); r4["origin"][::7, 0] = np.nan; b4.trace_closest(r4); b4.trace_any(r4)
 lob = _sc.lights_and_lobes_scene(grid=3, subdiv=1); b5 = backend.B200Backend(48, 32); lob.apply(b5)
 b5.render_spp(_sc.camera_view((0, 2.5, -5.0), (0, -0.4, 1.0), 48, 32, aperture=0.05), 2, 4)
+# round 2: the rest of TIntersector, packed hit records (pageable, pinned / streamed, device), the reference's triangle arithmetic
+# (TRI_MT builds of the persistent kernels, single- and two-level), the blue-noise sampler, split sub-waves, the tiny-stack build
+t = be.intersect_t(rays); t2, dep = be.depth_test(rays)
+assert np.array_equal(t >= 0, h["inst"] >= 0) and dep.max() > 0
+pk = wire.rays_to_packets4(rays[:2000]); inst4, prim4 = be.intersect4(pk); occ4 = be.occludes4(wire.rays_to_packets4(rays[:2000]))
+assert np.array_equal(prim4.ravel(), h["prim"][:2000])
+pp = backend.PinnedArray(3000, wire.HIT_PACKED); be.trace_closest_packed(pr.array, out=pp.array); hp = be.trace_closest_packed(rays)
+assert np.array_equal(pp.array["prim"], h["prim"]) and np.array_equal(hp["t"], h["t"])
+for b in (be, b2):
+    b.set_option("tri_test", 1); b.trace_closest(rays); b.trace_any(rays); b.set_option("tri_test", 0)
+be.set_option("tri_test", 1); be.reset_accumulator(); be.render_spp(view, 2, 3); be.set_option("tri_test", 0)
+be.set_blue_noise(np.random.default_rng(1).integers(0, 256, 65536 * 5).astype(np.uint32)); be.reset_accumulator(); be.render_spp(view, 4, 3); be.set_blue_noise(None)
+be.set_option("wf_split", 1); be.reset_accumulator(); be.render_spp(view, 4, 4); be.set_option("wf_split", 0)
+b2.set_option("trace_variant", 3); b2.set_option("streamed", 0)
+try:
+    b2.trace_closest(scenes.random_rays(5000))
+except backend.RfwError as e:
+    assert "stack overflow" in str(e)
+b2.set_option("trace_variant", 0)
 print("sanitize smoke ok", int((h["inst"] >= 0).sum()), int(o.sum()))
