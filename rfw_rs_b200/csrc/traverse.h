@@ -175,6 +175,13 @@ RFW_HD float byte_to_float(uint32_t w, int j) {
 #endif
 }
 
+// 48 = the two z plane sets (16 of the 48 conversions of a node test): measured best on the B200 (C2 closest 1 697 -> 1 735 Mrays/s, any-hit 2 033 -> 2 100,
+// C3 frame 40.94 -> 40.59 ms, identical results; 8 conversions: no gain; 24 or 48: slower — the ALU pipe takes over as the busiest)
+#ifndef RFW_B2F_PRMT_PLANES
+#define RFW_B2F_PRMT_PLANES 48
+#endif
+RFW_HD float byte_to_float_exp15(uint32_t w, int j) { return u2f(byte_perm(w, 0x3F800000u, 0x7604u | ((uint32_t)j << 4))); }  // 1 + q * 2^-15
+
 // fetch one wide node (read-only path)
 RFW_HD void load_wide_node(const float4* np, float4& n0, float4& n1, float4& n2, float4& n3, float4& n4) {
 #if defined(__CUDA_ARCH__) && RFW_NODE_F4 == 6 && !defined(RFW_NODE_LD128)
@@ -205,6 +212,14 @@ RFW_HD uint32_t intersect_wide_node(const float4 n0, const float4 n1, const floa
     const float aix = sx * r.idir.x, aiy = sy * r.idir.y, aiz = sz * r.idir.z;
     const float aox = (n0.x - r.o.x) * r.idir.x, aoy = (n0.y - r.o.y) * r.idir.y, aoz = (n0.z - r.o.z) * r.idir.z;
 #endif
+    // RFW_B2F_PRMT_PLANES (bit mask over the six plane sets x near, x far, y near, y far, z near, z far): the byte -> float conversions of the
+    // chosen sets leave the conversion (XU) pipe — the busiest pipe of the closest-hit kernel with all 48 on it (72 %, profiles/r2_trace_closest.md) —
+    // for the ALU pipe: one PRMT drops the byte into mantissa bits 8..15 of 1.0f (f = 1 + q 2^-15), and the slab FMA runs on A' = 2^15 A and
+    // C' = B - A' (f A' + C' = q A + B).  C' is rounded — up to 2^-9 of a quantisation step — so near planes are biased down and far planes up
+    // by 2^-22 |A'| (= 2^-7 of a step): conservative.  Unused constants fold away.
+    const float pax = aix * 32768.0f, pcx0 = aox - pax, pcxn = fmaf(-fabsf(pax), 2.3841858e-7f, pcx0), pcxf = fmaf(fabsf(pax), 2.3841858e-7f, pcx0);
+    const float pay = aiy * 32768.0f, pcy0 = aoy - pay, pcyn = fmaf(-fabsf(pay), 2.3841858e-7f, pcy0), pcyf = fmaf(fabsf(pay), 2.3841858e-7f, pcy0);
+    const float paz = aiz * 32768.0f, pcz0 = aoz - paz, pczn = fmaf(-fabsf(paz), 2.3841858e-7f, pcz0), pczf = fmaf(fabsf(paz), 2.3841858e-7f, pcz0);
     uint32_t hitmask = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -225,9 +240,13 @@ RFW_HD uint32_t intersect_wide_node(const float4 n0, const float4 n1, const floa
 #endif
         for (int j = 0; j < 4; j++) {
             const int sh = 8 * j;
-            const float tlx = fmaf(byte_to_float(xmin, j), aix, aox), thx = fmaf(byte_to_float(xmax, j), aix, aox);
-            const float tly = fmaf(byte_to_float(ymin, j), aiy, aoy), thy = fmaf(byte_to_float(ymax, j), aiy, aoy);
-            const float tlz = fmaf(byte_to_float(zmin, j), aiz, aoz), thz = fmaf(byte_to_float(zmax, j), aiz, aoz);
+            // (RFW_B2F_PRMT_PLANES bit k set: the 8 conversions of plane set k = x near, x far, y near, y far, z near, z far go through PRMT)
+            const float tlx = (RFW_B2F_PRMT_PLANES & 1) ? fmaf(byte_to_float_exp15(xmin, j), pax, pcxn) : fmaf(byte_to_float(xmin, j), aix, aox);
+            const float thx = (RFW_B2F_PRMT_PLANES & 2) ? fmaf(byte_to_float_exp15(xmax, j), pax, pcxf) : fmaf(byte_to_float(xmax, j), aix, aox);
+            const float tly = (RFW_B2F_PRMT_PLANES & 4) ? fmaf(byte_to_float_exp15(ymin, j), pay, pcyn) : fmaf(byte_to_float(ymin, j), aiy, aoy);
+            const float thy = (RFW_B2F_PRMT_PLANES & 8) ? fmaf(byte_to_float_exp15(ymax, j), pay, pcyf) : fmaf(byte_to_float(ymax, j), aiy, aoy);
+            const float tlz = (RFW_B2F_PRMT_PLANES & 16) ? fmaf(byte_to_float_exp15(zmin, j), paz, pczn) : fmaf(byte_to_float(zmin, j), aiz, aoz);
+            const float thz = (RFW_B2F_PRMT_PLANES & 32) ? fmaf(byte_to_float_exp15(zmax, j), paz, pczf) : fmaf(byte_to_float(zmax, j), aiz, aoz);
             // fminf/fmaxf drop NaN operands (0 * inf): such a slab simply does not constrain
             const float cmin = fmaxf(fmaxf(tlx, tly), fmaxf(tlz, tmin));
             const float cmax = fminf(fminf(thx, thy), fminf(thz, tmax)) * 1.0000006f;  // 5-ulp pad: conservative slabs (FMA rounding + the <= 1 ulp of fast_rcp per axis)
