@@ -455,7 +455,9 @@ RFWB200_API uint32_t rfwb200_tile_layout(uint32_t width, uint32_t height, uint32
  *   per frame:   rfwb200_render_spp(...) on every rank, then rfwb200_gather_image(handle, root, d_image) on every rank
  *                (collective): root < world gathers on that rank, root >= world on all ranks.  The receiver's image
  *                (sqrt(acc / spp), row-major RGBA32F) lands in `d_image` (device, width*height*4 floats) or, with NULL, in the
- *                backend's output buffer (rfwb200_read_output).  rfwb200_render_gather = both steps, timed as one frame. */
+ *                backend's output buffer (rfwb200_read_output).  rfwb200_render_gather = both steps, timed as one frame.
+ * A peer that never joins the gather does not hang the caller: after `gather_timeout_s` seconds (rfwb200_set_option, default 120; 0 = wait for ever) the
+ * communicator is aborted (ncclCommAbort) and the call returns RFWB200_ERR_CUDA; rfwb200_comm_init with a fresh id resumes. */
 #define RFWB200_COMM_ID_BYTES 128
 RFWB200_API int rfwb200_comm_unique_id(uint8_t* out_id /* RFWB200_COMM_ID_BYTES */);
 RFWB200_API int rfwb200_comm_init(void* handle, const uint8_t* unique_id, uint32_t rank, uint32_t world);

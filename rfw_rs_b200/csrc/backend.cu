@@ -14,6 +14,8 @@
 #include <algorithm>
 #include <set>
 #include <chrono>
+#include <future>
+#include <thread>
 #include <cstdlib>
 
 namespace rfw {
@@ -1475,13 +1477,57 @@ int Backend::gather_image(uint32_t root, float* d_image) {
         const size_t own = (size_t)wf.n_owned_tiles * wf.tile * wf.tile * 4;
         if (own < count) BK_CUDA(cudaMemsetAsync(d_send.ptr + own, 0, (count - own) * sizeof(float), stream), "send buffer");  // ranks with one tile fewer pad
         BK_CUDA(wf.export_tiles(stream, d_send.ptr), "export_tiles");
-        const std::string err = comm_gather(comm, d_send.ptr, receiver ? d_gathered.ptr : nullptr, count, root, stream);
+        std::string err;
+        if (!comm.warmed && gather_timeout_s > 0) {
+            // The FIRST collective of a communicator sets up its peer-to-peer connections inside the NCCL call and blocks there until the
+            // peers call too — a missing peer would hang this thread before the deadline loop below is reached.  That one call therefore runs
+            // on a helper thread; on expiry this thread aborts the communicator (ncclCommAbort is what unblocks a hung NCCL call).
+            void* const nccl_before = comm.nccl_comm;
+            auto fut = std::async(std::launch::async, [&]() {
+                cudaSetDevice(cfg.device);
+                return comm_gather(comm, d_send.ptr, receiver ? d_gathered.ptr : nullptr, count, root, stream);
+            });
+            if (fut.wait_for(std::chrono::seconds(gather_timeout_s)) != std::future_status::ready) {
+                Comm doomed = comm;                 // (the helper thread still reads comm.nccl_comm: abort a copy of the handle, then join)
+                comm_abort(doomed);
+                fut.wait();
+                comm.nccl_comm = nullptr; comm.rank = 0; comm.world = 1; comm.warmed = false;
+                cudaStreamSynchronize(stream);
+                cudaGetLastError();
+                (void)nccl_before;
+                return fail(RFWB200_ERR_CUDA, "gather_image: no answer from the other ranks within " + std::to_string(gather_timeout_s) +
+                                                  " s (option gather_timeout_s); the communicator was aborted — rfwb200_comm_init again to continue");
+            }
+            err = fut.get();
+        } else {
+            err = comm_gather(comm, d_send.ptr, receiver ? d_gathered.ptr : nullptr, count, root, stream);
+        }
         if (!err.empty()) return fail(RFWB200_ERR_CUDA, "gather_image: " + err);
         if (receiver) BK_CUDA(wf.assemble(stream, d_gathered.ptr, wf.tiles_per_rank, wf.world, sample_count, image), "assemble");
         launch_count += receiver ? 2 : 1;
     }
     BK_CUDA(cudaEventRecord(ev_g1, stream), "event");
-    BK_CUDA(cudaEventSynchronize(ev_g1), "gather_image");
+    if (wf.world > 1 && gather_timeout_s > 0) {
+        // A collective with a peer that died (or never called) would block this thread for ever: wait with a deadline instead, and on
+        // expiry abort the communicator (ncclCommAbort: the outstanding kernels are torn down, the stream becomes usable again).
+        const auto t0 = std::chrono::steady_clock::now();
+        for (;;) {
+            const cudaError_t q = cudaEventQuery(ev_g1);
+            if (q == cudaSuccess) break;
+            if (q != cudaErrorNotReady) return cuda_fail(q, "gather_image");
+            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > (double)gather_timeout_s) {
+                comm_abort(comm);
+                cudaStreamSynchronize(stream);
+                cudaGetLastError();
+                return fail(RFWB200_ERR_CUDA, "gather_image: no answer from the other ranks within " + std::to_string(gather_timeout_s) +
+                                                  " s (option gather_timeout_s); the communicator was aborted — rfwb200_comm_init again to continue");
+            }
+            std::this_thread::yield();
+        }
+    } else {
+        BK_CUDA(cudaEventSynchronize(ev_g1), "gather_image");
+    }
+    if (wf.world > 1) comm.warmed = true;
     cudaEventElapsedTime(&render_stats.gather_ms, ev_g0, ev_g1);
     return RFWB200_OK;
 }
@@ -1536,6 +1582,7 @@ int Backend::set_option(const char* key, int64_t value) {
     else if (k == "tri_test") { tri_mt = value != 0 ? 1 : 0; sv.tri_mt = tri_mt; }  // 0: watertight (default); 1: the reference's Moller-Trumbore arithmetic (parity runs)
     else if (k == "stage_timing") wf.stage_timing = value != 0;
     else if (k == "grid_rays_per_thread") wf.grid_rays_per_thread = (int)std::max<int64_t>(0, value);
+    else if (k == "gather_timeout_s") gather_timeout_s = (int)std::max<int64_t>(0, value);  // 0: wait for ever
     else if (k == "wf_split") wf.split_waves = value != 0;  // two sub-waves in flight (1, default) or one wave at a time (0)
     else if (k == "wf_overlap") wf.overlap = value != 0;  // connect(b) beside extend(b + 1) on a second stream (1, default) or everything on one stream (0)
     else if (k == "inst_batch") tcfg.inst_batch = (int)std::max<int64_t>(1, value);

@@ -227,6 +227,7 @@ private:
 
     // accumulator gather over NCCL (comm.h)
     Comm comm;
+    int gather_timeout_s = 120;  // option "gather_timeout_s": deadline of the gather collective (a dead peer must not hang the caller); 0 = none
     DeviceArray<float> d_send, d_gathered;
     cudaEvent_t ev_g0 = nullptr, ev_g1 = nullptr;
 

@@ -18,6 +18,7 @@ struct NcclApi {
     nccl_result_t (*GetUniqueId)(NcclUniqueId*) = nullptr;
     nccl_result_t (*CommInitRank)(void**, int, NcclUniqueId, int) = nullptr;
     nccl_result_t (*CommDestroy)(void*) = nullptr;
+    nccl_result_t (*CommAbort)(void*) = nullptr;
     nccl_result_t (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     nccl_result_t (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     nccl_result_t (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
@@ -46,6 +47,7 @@ static NcclApi& api() {
         a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(sym("ncclGetUniqueId"));
         a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(sym("ncclCommInitRank"));
         a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(sym("ncclCommDestroy"));
+        a.CommAbort = reinterpret_cast<decltype(a.CommAbort)>(sym("ncclCommAbort"));
         a.AllGather = reinterpret_cast<decltype(a.AllGather)>(sym("ncclAllGather"));
         a.Send = reinterpret_cast<decltype(a.Send)>(sym("ncclSend"));
         a.Recv = reinterpret_cast<decltype(a.Recv)>(sym("ncclRecv"));
@@ -91,13 +93,18 @@ std::string comm_init(Comm& c, const uint8_t idb[COMM_UNIQUE_ID_BYTES], uint32_t
     memcpy(id.internal, idb, COMM_UNIQUE_ID_BYTES);
     void* comm = nullptr;
     NCCL_CK(a.CommInitRank(&comm, (int)world, id, (int)rank), "ncclCommInitRank");
-    c.nccl_comm = comm; c.rank = rank; c.world = world;
+    c.nccl_comm = comm; c.rank = rank; c.world = world; c.warmed = false;
     return "";
 }
 
 void comm_destroy(Comm& c) {
     if (c.nccl_comm && api().CommDestroy) api().CommDestroy(c.nccl_comm);
-    c.nccl_comm = nullptr; c.rank = 0; c.world = 1;
+    c.nccl_comm = nullptr; c.rank = 0; c.world = 1; c.warmed = false;
+}
+
+void comm_abort(Comm& c) {
+    if (c.nccl_comm && api().CommAbort) api().CommAbort(c.nccl_comm);
+    c.nccl_comm = nullptr; c.rank = 0; c.world = 1; c.warmed = false;
 }
 
 std::string comm_gather(Comm& c, const float* d_send, float* d_recv, size_t count, uint32_t root, cudaStream_t stream) {

@@ -15,6 +15,7 @@ static constexpr int COMM_UNIQUE_ID_BYTES = 128;  // sizeof(ncclUniqueId)
 struct Comm {
     void* nccl_comm = nullptr;  // ncclComm_t
     uint32_t rank = 0, world = 1;
+    bool warmed = false;        // a gather has completed: the peer-to-peer connections exist (NCCL sets them up inside the first call, blocking)
     bool active() const { return nccl_comm != nullptr; }
 };
 
@@ -26,5 +27,7 @@ void comm_destroy(Comm& c);
 // r's block at r * count; the root's own block is copied device-to-device), with root >= world every rank receives (all-gather)
 std::string comm_gather(Comm& c, const float* d_send, float* d_recv, size_t count, uint32_t root, cudaStream_t stream);
 std::string comm_version(int* out_version);
+// a peer died or never called: tears the communicator down without waiting for the outstanding collective (ncclCommAbort)
+void comm_abort(Comm& c);
 
 }  // namespace rfw

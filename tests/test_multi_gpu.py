@@ -40,3 +40,30 @@ def test_gather_image_over_nccl_matches_single_gpu(tmp_path):
     assert sum(s[0] for s in st) == 320 * 192 * 4             # the ranks' samples partition the frame
     # gather_ms measured (the first gather of a communicator includes NCCL's lazy connection set-up: up to seconds); frame_ms covers render + gather
     assert all(0.0 < s[1] < 20000.0 and s[2] >= 0.9 * s[3] for s in st), [list(s) for s in st]
+
+
+@pytest.mark.gpu
+def test_gather_with_a_missing_peer_returns_an_error_not_a_hang(tmp_path):
+    """A rank that never joins the frame's collective (crashed, or a host bug) must not hang the others: rfwb200_gather_image waits with
+    a deadline (option gather_timeout_s, default 120 s; 3 s here), aborts the communicator (ncclCommAbort) and returns an error; the backend
+    stays usable."""
+    import torch
+
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "multi_gpu_worker.py"), str(r), "2", str(tmp_path), "deadline"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = []
+    for p in procs:
+        try:
+            o, _ = p.communicate(timeout=120)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        outs.append(o)
+    assert all(p.returncode == 0 for p in procs), outs
+    secs, msg = open(tmp_path / "deadline.txt").read().split("\n")[:2]
+    assert "no answer from the other ranks" in msg, (msg, outs)
+    assert 2.5 <= float(secs) < 20.0
+    assert open(tmp_path / "deadline_after.txt").read() == "2"
