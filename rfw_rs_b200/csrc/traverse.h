@@ -180,7 +180,19 @@ RFW_HD float byte_to_float(uint32_t w, int j) {
 #ifndef RFW_B2F_PRMT_PLANES
 #define RFW_B2F_PRMT_PLANES 48
 #endif
-RFW_HD float byte_to_float_exp15(uint32_t w, int j) { return u2f(byte_perm(w, 0x3F800000u, 0x7604u | ((uint32_t)j << 4))); }  // 1 + q * 2^-15
+// 1 + q * 2^-15: byte j of w into mantissa bits 8..15 of 1.0f with ONE PRMT.  SASS PRMT takes one immediate: with the literal 0x3F800000 ptxas keeps
+// that as the immediate and moves the selector into a register before every PRMT (16 extra IMAD.U32 per node test); read from constant memory the bit
+// pattern of 1.0f sits in a uniform register and the selector is the immediate.
+#if defined(__CUDACC__)
+static __constant__ uint32_t rfw_one_bits = 0x3F800000u;  // (one copy per translation unit)
+#endif
+RFW_HD float byte_to_float_exp15(uint32_t w, int j) {
+#if defined(__CUDA_ARCH__)
+    return u2f(byte_perm(w, rfw_one_bits, 0x7604u | ((uint32_t)j << 4)));
+#else
+    return u2f(byte_perm(w, 0x3F800000u, 0x7604u | ((uint32_t)j << 4)));
+#endif
+}
 
 // fetch one wide node (read-only path)
 RFW_HD void load_wide_node(const float4* np, float4& n0, float4& n1, float4& n2, float4& n3, float4& n4) {
