@@ -145,6 +145,15 @@ def test_reference_triangle_arithmetic_option_bit_exact_on_the_gpu(B, oracle_mod
     parity.compare_hits(rays, gpu.trace_closest(rays), ref, parity.lookup_from_desc(desc), "wt-after-mt")
 
 
+def test_randomised_stress_against_brute_force_on_the_gpu(B, oracle_mod):
+    """The randomised stress of the CPU tier (tests/test_hostemu.py: scales 1e-3 ... 1e3, far from the origin, flat / duplicate / sliver
+    triangles, non-uniformly scaled instances, axis-parallel and on-surface rays) with the GPU library in the harness's place, against the
+    oracle's brute force over all triangles: 16 seeds here (scripts/stress_gpu.py ran 400 once without a failure)."""
+    from scripts import stress_gpu
+
+    assert stress_gpu.run(0, 16) == 0
+
+
 @pytest.mark.parametrize("two_level", [False, True])
 def test_packed_hit_records(B, torch_cuda, two_level):
     """rfwb200_trace_closest_packed: the reference's own 16-byte hit record (inst, prim, t, bary16 | bary16 << 16; ray_extend.comp:267)
