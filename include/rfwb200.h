@@ -476,8 +476,13 @@ RFWB200_API int rfwb200_render_stats(void* handle, RfwRenderStats* out);
  *               tri_batch_two_level (4), inst_batch (6: two-level kernels enter instances when this many lanes wait at a TLAS leaf)
  *               sort_rays (0; 1 = device-pointer batches traced in Morton order of the ray origins), sort_min_bvh_mb
  *   host path:  streamed (1: single persistent launch overlapping upload and download), chunk_rays, l2_persist
- *   builder:    sah_treelet, sah_treelet_tlas, sah_c_prim_milli, sah_pmax, build_streams (8: small BLAS builds in flight at once)
- *   wavefront:  max_depth, wave_paths, sample_count, stage_timing (1: RfwRenderStats.stage_ms is filled) */
+ *               tri_test (0 watertight; 1 = the reference's Moller-Trumbore arithmetic, operation for operation: parity runs)
+ *   builder:    sah_treelet, sah_treelet_tlas, sah_c_prim_milli, sah_pmax, build_streams (8: small BLAS builds in flight at once),
+ *               split_budget (0 = off; percent of extra triangle references for SPATIAL SPLITS — triangle pre-splitting ahead of the
+ *               Morton sort, the reference's "Spatial BVH" (backends/gpu-rt/README.md:10); 30 is a good value for authored assets)
+ *   wavefront:  max_depth, wave_paths, sample_count, stage_timing (1: RfwRenderStats.stage_ms is filled), wf_overlap (1: connect stage on a
+ *               second stream), wf_split, grid_rays_per_thread (experiments, off)
+ *   multi-GPU:  gather_timeout_s (120) */
 RFWB200_API int rfwb200_set_option(void* handle, const char* key, int64_t value);
 /* debug: copy wavefront queue `which` (0/1) to host: O, D, T (4 floats per path each; any may be NULL), the hit
  * state S of the last extend, and the queue's current count */

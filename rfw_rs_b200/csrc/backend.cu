@@ -490,6 +490,26 @@ int Backend::synchronize() {
                 BK_CUDA(cudaMallocAsync(&lo, (size_t)m.n * sizeof(float4), bs), "box alloc");
                 BK_CUDA(cudaMallocAsync(&hi, (size_t)m.n * sizeof(float4), bs), "box alloc");
                 cudaError_t e = triangle_boxes(bc, m.d_tris, (int)m.n, lo, hi);
+                m.n_refs = m.n;
+                if (e == cudaSuccess && split_budget > 0 && m.n > (uint32_t)RFW_DIRECT_TRIS) {
+                    // spatial splits (option "split_budget", percent of extra references): the BVH is built over clipped reference boxes,
+                    // the leaf-ordered traversal triangles repeat a split triangle once per reference (tri_split.h)
+                    SplitRefs refs;
+                    e = split_triangle_refs(bc, m.d_tris, (int)m.n, lo, hi, (float)split_budget * 0.01f, refs);
+                    if (e == cudaSuccess) e = build_wide_bvh(bc, refs.lo, refs.hi, refs.n_refs, blas_params, m.bvh, /*deferred=*/refs.n_refs <= BUILD_DEFER_MAX);
+                    cudaFreeAsync(lo, bs); cudaFreeAsync(hi, bs);
+                    if (e == cudaSuccess) {
+                        m.n_refs = (uint32_t)refs.n_refs;
+                        e = cudaMallocAsync(&m.d_ttris, (size_t)m.n_refs * 3 * sizeof(float4), bs);
+                        if (e == cudaSuccess) e = gather_traversal_triangles_refs(bc, m.d_tris, m.bvh.leaf_prims, refs.prim, refs.n_refs, m.d_ttris);
+                    }
+                    if (refs.lo) cudaFreeAsync(refs.lo, bs);
+                    if (refs.hi) cudaFreeAsync(refs.hi, bs);
+                    if (refs.prim) cudaFreeAsync(refs.prim, bs);
+                    if (e != cudaSuccess) return cuda_fail(e, "BLAS build (spatial splits)");
+                    m.dirty = false;
+                    continue;
+                }
                 if (e == cudaSuccess) e = build_wide_bvh(bc, lo, hi, (int)m.n, blas_params, m.bvh, /*deferred=*/true);  // small meshes: no host sync per mesh
                 cudaFreeAsync(lo, bs); cudaFreeAsync(hi, bs);
                 if (e != cudaSuccess) return cuda_fail(e, "BLAS build");
@@ -756,7 +776,7 @@ int Backend::read_build_stats(RfwBuildStats* out) {
         for (const MeshRec& m : meshes) {
             if (!m.present || !m.n) continue;
             BK_CUDA(buffer_checksum(bctx, reinterpret_cast<const uint32_t*>(m.bvh.nodes), NODE_WORDS, m.bvh.num_nodes, 0x30u, d_counters3), "checksum");
-            BK_CUDA(buffer_checksum(bctx, reinterpret_cast<const uint32_t*>(m.d_ttris), 12, m.n, 0u, d_counters3), "checksum");
+            BK_CUDA(buffer_checksum(bctx, reinterpret_cast<const uint32_t*>(m.d_ttris), 12, m.n_refs ? m.n_refs : m.n, 0u, d_counters3), "checksum");
         }
         if (tlas.num_nodes) BK_CUDA(buffer_checksum(bctx, reinterpret_cast<const uint32_t*>(tlas.nodes), NODE_WORDS, tlas.num_nodes, 0x30u, d_counters3), "checksum");
         unsigned long long cs = 0;
@@ -1582,6 +1602,11 @@ int Backend::set_option(const char* key, int64_t value) {
     else if (k == "tri_test") { tri_mt = value != 0 ? 1 : 0; sv.tri_mt = tri_mt; }  // 0: watertight (default); 1: the reference's Moller-Trumbore arithmetic (parity runs)
     else if (k == "stage_timing") wf.stage_timing = value != 0;
     else if (k == "grid_rays_per_thread") wf.grid_rays_per_thread = (int)std::max<int64_t>(0, value);
+    else if (k == "split_budget") {  // spatial splits: percent of extra triangle references the BLAS builds may spend (0 = off, default); rebuilds every mesh
+        split_budget = (int)std::min<int64_t>(400, std::max<int64_t>(0, value));
+        for (MeshRec& m : meshes) if (m.present) m.dirty = true;
+        scene_dirty = true; synchronized = false;
+    }
     else if (k == "gather_timeout_s") gather_timeout_s = (int)std::max<int64_t>(0, value);  // 0: wait for ever
     else if (k == "wf_split") wf.split_waves = value != 0;  // two sub-waves in flight (1, default) or one wave at a time (0)
     else if (k == "wf_overlap") wf.overlap = value != 0;  // connect(b) beside extend(b + 1) on a second stream (1, default) or everything on one stream (0)
@@ -1591,7 +1616,7 @@ int Backend::set_option(const char* key, int64_t value) {
     else if (k == "streamed") streamed_enabled = value != 0;  // host-buffer entry points: single-launch streaming (1) or chunked pipeline (0)
     else if (k == "chunk_rays") chunk_rays = (uint64_t)std::max<int64_t>(1024, value);
     else if (k == "max_depth") cfg.max_depth = (uint32_t)value;
-    else if (k == "build_streams") build_streams = (int)std::min<int64_t>(16, std::max<int64_t>(1, value));
+    else if (k == "build_streams") build_streams = (int)std::min<int64_t>(64, std::max<int64_t>(1, value));
     else if (k == "sah_treelet_tlas") { sah_treelet_tlas = (int)value; scene_dirty = true; synchronized = false; }
     else if (k == "sah_treelet") { sah_treelet = (int)value; for (auto& m : meshes) if (m.present) m.dirty = true; scene_dirty = true; synchronized = false; }
     else if (k == "sah_c_prim_milli" || k == "sah_pmax") {  // SAH leaf cost (x1000) / max triangles per leaf slot (1..3)

@@ -23,6 +23,7 @@ struct MeshRec {
     bool present = false;
     bool dirty = false;
     uint32_t n = 0;
+    uint32_t n_refs = 0;              // traversal triangles (= n, or more with spatial splits: a split triangle appears once per reference)
     uint32_t flags = 0;
     RfwRTTriangle* d_tris = nullptr;  // full 176-byte records (shading reads them)
     RfwJointData* d_skin = nullptr;   // per-vertex joint data (3 per triangle) when the mesh is skinned, else null
@@ -222,6 +223,7 @@ private:
     float sah_c_prim = 0.8f;  // SAH cost of one triangle test relative to one wide-node visit (BLAS); swept on C2/C4 (scripts/tune_leafcost.py)
     int sah_pmax = 3;         // max triangles per leaf slot
     int sah_treelet_tlas = 0;  // the same for the TLAS over instance boxes: off — refining the 170-instance TLAS of pica (nested, overlapping part boxes) made its primary rays 60 % slower (scripts/exp_c1b.py), the C3 grid TLAS is indifferent
+    int split_budget = 0; // option "split_budget": spatial splits (triangle pre-splitting, tri_split.h), percent of extra references; 0 = off
     int tri_mt = 0;       // option "tri_test": 1 = the reference's Moller-Trumbore triangle arithmetic in every traversal kernel (SceneView::tri_mt)
     int sah_treelet = 8;  // binned-SAH refinement above LBVH treelets of this many primitives (0 = plain LBVH)
 

@@ -12,6 +12,7 @@
 #include <stdio.h>
 
 #include "builder.h"
+#include "tri_split.h"
 
 namespace cg = cooperative_groups;
 
@@ -475,6 +476,107 @@ void* BuildScratch::reserve(size_t bytes) {
 cudaError_t triangle_boxes(BuilderContext& ctx, const RfwRTTriangle* tris, int n, float4* prim_lo, float4* prim_hi) {
     if (n == 0) return cudaSuccess;
     k_triangle_boxes<<<blocks_for(n), TB, 0, ctx.stream>>>(tris, n, prim_lo, prim_hi);
+    ctx.launches++;
+    return cudaGetLastError();
+}
+
+// ---- spatial splits: triangle pre-splitting ahead of the Morton sort (tri_split.h) -----------------------------------------------
+static constexpr float SPLIT_PRIO_FIXED = 16777216.0f;  // priorities are summed as 2^24 fixed point: integer adds are associative, so the
+                                                        // reference counts (and with them the tree) are the same on every run and rank
+__device__ __forceinline__ SplitGrid split_grid_from_bounds(const uint32_t* __restrict__ bounds) {
+    return make_split_grid(f3(dec_f(bounds[6]), dec_f(bounds[7]), dec_f(bounds[8])), f3(dec_f(bounds[9]), dec_f(bounds[10]), dec_f(bounds[11])));
+}
+__global__ void __launch_bounds__(TB) k_split_priority(const RfwRTTriangle* __restrict__ tris, int n, const uint32_t* __restrict__ bounds, uint32_t* __restrict__ prio,
+                                                       unsigned long long* __restrict__ sum) {
+    const int i = blockIdx.x * TB + threadIdx.x;
+    unsigned long long mine = 0;
+    if (i < n) {
+        const float4* p = reinterpret_cast<const float4*>(tris + i);
+        const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+        const float pr = split_priority(split_grid_from_bounds(bounds), f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z));
+        const uint32_t q = (uint32_t)fminf(fmaxf(pr, 0.0f) * SPLIT_PRIO_FIXED, 4.0e9f);
+        prio[i] = q;
+        mine = q;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(FULLMASK, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(sum, mine);
+}
+// references of triangle i: 1 + its share of the budget (budget_refs extra references in total, in proportion to the priorities)
+__global__ void __launch_bounds__(TB) k_split_counts(const uint32_t* __restrict__ prio, int n, const unsigned long long* __restrict__ sum, unsigned long long budget_refs,
+                                                     uint32_t* __restrict__ counts) {
+    const int i = blockIdx.x * TB + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long total = *sum;
+    unsigned long long extra = total ? (unsigned long long)prio[i] * budget_refs / total : 0ull;
+    if (extra > (unsigned long long)SPLIT_MAX_EXTRA) extra = SPLIT_MAX_EXTRA;
+    counts[i] = 1u + (uint32_t)extra;
+}
+__global__ void __launch_bounds__(TB) k_split_emit(const RfwRTTriangle* __restrict__ tris, int n, const uint32_t* __restrict__ bounds, const uint32_t* __restrict__ counts,
+                                                   const uint32_t* __restrict__ offsets, float4* __restrict__ ref_lo, float4* __restrict__ ref_hi, uint32_t* __restrict__ ref_prim) {
+    const int i = blockIdx.x * TB + threadIdx.x;
+    if (i >= n) return;
+    const float4* p = reinterpret_cast<const float4*>(tris + i);
+    const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    const SplitGrid g = split_grid_from_bounds(bounds);
+    const uint32_t off = offsets[i], cnt = counts[i];
+    // pad: a few float32 ulps of the largest coordinate of the mesh (the edge / plane intersections are computed in float32)
+    const float big = fmaxf(fmaxf(fabsf(dec_f(bounds[6])), fabsf(dec_f(bounds[7]))), fmaxf(fmaxf(fabsf(dec_f(bounds[8])), fabsf(dec_f(bounds[9]))), fmaxf(fabsf(dec_f(bounds[10])), fabsf(dec_f(bounds[11])))));
+    const float pad = cnt > 1u ? 2.0e-6f * big : 0.0f;
+    split_triangle(g, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), (int)cnt, pad, ref_lo + off, ref_hi + off);
+    for (uint32_t k = 0; k < cnt; k++) ref_prim[off + k] = (uint32_t)i;
+}
+__global__ void __launch_bounds__(TB) k_gather_tris_refs(const RfwRTTriangle* __restrict__ tris, const uint32_t* __restrict__ leaf_refs, const uint32_t* __restrict__ ref_prim, int n_refs,
+                                                         float4* __restrict__ out) {
+    const int k = blockIdx.x * TB + threadIdx.x;
+    if (k >= n_refs) return;
+    const uint32_t prim = ref_prim[leaf_refs[k]];
+    const float4* p = reinterpret_cast<const float4*>(tris + prim);
+    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    a.w = __uint_as_float(prim);
+    b.w = 0.0f; c.w = 0.0f;
+    out[(size_t)k * 3 + 0] = a;
+    out[(size_t)k * 3 + 1] = b;
+    out[(size_t)k * 3 + 2] = c;
+}
+
+cudaError_t split_triangle_refs(BuilderContext& ctx, const RfwRTTriangle* tris, int n, const float4* prim_lo, const float4* prim_hi, float budget, SplitRefs& out) {
+    out = SplitRefs{};
+    if (n <= 0) return cudaSuccess;
+    cudaStream_t s = ctx.stream;
+    uint32_t *bounds = nullptr, *prio = nullptr, *counts = nullptr, *offsets = nullptr;
+    unsigned long long* sum = nullptr;
+    RFW_CK(cudaMallocAsync(&bounds, 16 * sizeof(uint32_t), s));
+    RFW_CK(cudaMallocAsync(&sum, sizeof(unsigned long long), s));
+    RFW_CK(cudaMallocAsync(&prio, (size_t)n * sizeof(uint32_t), s));
+    RFW_CK(cudaMallocAsync(&counts, (size_t)n * sizeof(uint32_t), s));
+    RFW_CK(cudaMallocAsync(&offsets, (size_t)n * sizeof(uint32_t), s));
+    RFW_CK(cudaMemsetAsync(sum, 0, sizeof(unsigned long long), s));
+    k_init_bounds<<<1, 32, 0, s>>>(bounds);
+    k_bounds<<<std::min(blocks_for(n), 148 * 8), TB, 0, s>>>(prim_lo, prim_hi, n, bounds);
+    k_split_priority<<<blocks_for(n), TB, 0, s>>>(tris, n, bounds, prio, sum);
+    const unsigned long long budget_refs = (unsigned long long)((double)budget * (double)n);
+    k_split_counts<<<blocks_for(n), TB, 0, s>>>(prio, n, sum, budget_refs, counts);
+    RFW_CK(cudaMemcpyAsync(offsets, counts, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    exclusive_scan_u32(offsets, n, s);
+    uint32_t last[2] = {0, 0};
+    RFW_CK(cudaMemcpyAsync(&last[0], offsets + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    RFW_CK(cudaMemcpyAsync(&last[1], counts + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    RFW_CK(cudaStreamSynchronize(s));  // the reference count sizes the build
+    const int n_refs = (int)(last[0] + last[1]);
+    RFW_CK(cudaMallocAsync(&out.lo, (size_t)n_refs * sizeof(float4), s));
+    RFW_CK(cudaMallocAsync(&out.hi, (size_t)n_refs * sizeof(float4), s));
+    RFW_CK(cudaMallocAsync(&out.prim, (size_t)n_refs * sizeof(uint32_t), s));
+    k_split_emit<<<blocks_for(n), TB, 0, s>>>(tris, n, bounds, counts, offsets, out.lo, out.hi, out.prim);
+    out.n_refs = n_refs;
+    ctx.launches += 6;
+    cudaFreeAsync(bounds, s); cudaFreeAsync(sum, s); cudaFreeAsync(prio, s); cudaFreeAsync(counts, s); cudaFreeAsync(offsets, s);
+    return cudaGetLastError();
+}
+
+cudaError_t gather_traversal_triangles_refs(BuilderContext& ctx, const RfwRTTriangle* tris, const uint32_t* leaf_refs, const uint32_t* ref_prim, int n_refs, float4* out) {
+    if (n_refs == 0) return cudaSuccess;
+    k_gather_tris_refs<<<blocks_for(n_refs), TB, 0, ctx.stream>>>(tris, leaf_refs, ref_prim, n_refs, out);
     ctx.launches++;
     return cudaGetLastError();
 }

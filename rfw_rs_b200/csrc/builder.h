@@ -75,6 +75,18 @@ cudaError_t finish_pending_builds(BuilderContext& ctx);
 cudaError_t triangle_boxes(BuilderContext& ctx, const RfwRTTriangle* tris, int n, float4* prim_lo, float4* prim_hi);
 // traversal triangles: out[3k..3k+2] = vertices of tris[leaf_prims[k]], v0.w = prim index bits
 cudaError_t gather_traversal_triangles(BuilderContext& ctx, const RfwRTTriangle* tris, const uint32_t* leaf_prims, int n, float4* out);
+// Spatial splits (tri_split.h): replaces the n triangle boxes by n_refs >= n reference boxes — triangle i gets 1 + (its share of
+// budget * n extra references, by priority) clipped boxes — allocated stream-ordered on ctx.stream (the caller frees them with cudaFreeAsync);
+// `prim[r]` = the triangle of reference r.  One host sync (the reference count).  The wide BVH is then built over the references, and the
+// traversal triangles are gathered through `prim`.
+struct SplitRefs {
+    float4* lo = nullptr;
+    float4* hi = nullptr;
+    uint32_t* prim = nullptr;
+    int n_refs = 0;
+};
+cudaError_t split_triangle_refs(BuilderContext& ctx, const RfwRTTriangle* tris, int n, const float4* prim_lo, const float4* prim_hi, float budget, SplitRefs& out);
+cudaError_t gather_traversal_triangles_refs(BuilderContext& ctx, const RfwRTTriangle* tris, const uint32_t* leaf_refs, const uint32_t* ref_prim, int n_refs, float4* out);
 // layout-independent checksum: sum over records of a hash of each record's words (skip_mask: words left out)
 cudaError_t buffer_checksum(BuilderContext& ctx, const uint32_t* words, int record_words, size_t n_records, uint32_t skip_mask, unsigned long long* d_accum);
 

@@ -477,6 +477,24 @@ def soup_with_lights(n, s, n_lights=256, seed=SEED_SCENE, light_area=1e-2, radiu
     return sc
 
 
+def mixed_scale_scene(n_small=100000, n_long=300, n_big=30, s=0.008, seed=SEED_SCENE):
+    """One mesh mixing triangle scales the way authored assets do (a room's walls around its furniture): a soup of small triangles,
+    long thin needles crossing the whole cube and a few cube-sized triangles — the case spatial splits exist for."""
+    base = soup(n_small, s, seed=seed)
+    k = np.arange(n_long + n_big)
+    r = u01(seed + 17, k[:, None] * 9 + np.arange(9)[None, :]).astype(np.float32)
+    a = r[:, 0:3]
+    b = r[:, 3:6]
+    c = np.where((k < n_long)[:, None], a + (b - a) * 0.5 + (r[:, 6:9] - 0.5) * np.float32(0.01), r[:, 6:9])   # needles: third vertex near the middle of a-b
+    extra = make_triangles(a, b, c.astype(np.float32), 0)
+    sc = SceneDesc()
+    sc.materials = material()
+    sc.meshes[0] = np.concatenate([base, extra])
+    sc.meshes[0]["id"] = np.arange(len(sc.meshes[0]), dtype=np.int32)
+    sc.instances[0] = to_column_major([identity()])
+    return sc
+
+
 def random_barycentrics_np(r0):
     """Vectorised RandomBarycentrics (shade.comp:372-412): 16 steps of base-4 triangle subdivision driven by the bits of r0."""
     uf = (r0.astype(np.float64) * 4294967295.0).astype(np.uint64).astype(np.uint32)

@@ -15,6 +15,7 @@
 #include "../../rfw_rs_b200/csrc/bvh_build.h"
 #include "../../rfw_rs_b200/csrc/instance_build.h"
 #include "../../rfw_rs_b200/csrc/traverse.h"
+#include "../../rfw_rs_b200/csrc/tri_split.h"
 
 using namespace rfw;
 
@@ -283,4 +284,13 @@ int emu_validate(void* s, uint32_t mesh_id) {
     return errors;
 }
 float emu_sah(void* s, uint32_t mesh_id) { return ((EmuScene*)s)->meshes[mesh_id].bvh.sah; }
+// spatial splits (tri_split.h): priority of one triangle inside the mesh bounds, and its `count` reference boxes
+float emu_split_priority(const float* mesh_lo, const float* mesh_hi, const float* v) {
+    const SplitGrid g = make_split_grid(f3(mesh_lo[0], mesh_lo[1], mesh_lo[2]), f3(mesh_hi[0], mesh_hi[1], mesh_hi[2]));
+    return split_priority(g, f3(v[0], v[1], v[2]), f3(v[3], v[4], v[5]), f3(v[6], v[7], v[8]));
+}
+void emu_split_triangle(const float* mesh_lo, const float* mesh_hi, const float* v, int count, float pad, float* out_lo4, float* out_hi4) {
+    const SplitGrid g = make_split_grid(f3(mesh_lo[0], mesh_lo[1], mesh_lo[2]), f3(mesh_hi[0], mesh_hi[1], mesh_hi[2]));
+    split_triangle(g, f3(v[0], v[1], v[2]), f3(v[3], v[4], v[5]), f3(v[6], v[7], v[8]), count, pad, reinterpret_cast<float4*>(out_lo4), reinterpret_cast<float4*>(out_hi4));
+}
 }

@@ -769,3 +769,65 @@ def test_wavefront_kernels_on_the_cpu(emu, shade_emu, oracle_mod, which):
     o = oracle_mod.OracleBackend(det_eps=0.0); desc.apply(o)
     ref, _ = o.render(view, w, h, spp, depth, clamp=10.0, sky=sky)
     _check_image(acc / spp, ref / spp, which, diverged_fraction=4e-3)
+
+
+# ---- spatial splits: triangle pre-splitting (rfw_rs_b200/csrc/tri_split.h) on the CPU tier ------------------------------------
+def test_triangle_pre_splitting_covers_the_triangle(emu):
+    """split_triangle replaces a triangle by exactly `count` reference boxes (Karras & Aila 2013, section 4): every box lies inside the
+    triangle's own (padded) box, their union covers the triangle (2 000 random points of it each fall into a box — a ray that hits the
+    triangle therefore meets a reference), a long diagonal triangle's boxes are together much smaller than its one box, and triangles
+    inside one grid cell have priority 0.  Awkward inputs: axis-aligned flats, slivers, vertices exactly on cell boundaries, tiny and
+    mesh-sized triangles, scales 1e-3 ... 1e3."""
+    fp = C.POINTER(C.c_float)
+    emu.emu_split_triangle.argtypes = [fp, fp, fp, C.c_int, C.c_float, fp, fp]
+    emu.emu_split_priority.argtypes = [fp, fp, fp]; emu.emu_split_priority.restype = C.c_float
+    rng = np.random.default_rng(21)
+
+    def call(lo, hi, v, count, pad):
+        lo, hi, v = (np.ascontiguousarray(a, np.float32) for a in (lo, hi, v))
+        out_lo = np.full((count + 1, 4), np.nan, np.float32); out_hi = np.full((count + 1, 4), np.nan, np.float32)
+        emu.emu_split_triangle(lo.ctypes.data_as(fp), hi.ctypes.data_as(fp), v.ctypes.data_as(fp), count, pad, out_lo.ctypes.data_as(fp), out_hi.ctypes.data_as(fp))
+        assert np.isfinite(out_lo[:count, :3]).all() and np.isfinite(out_hi[:count, :3]).all()   # exactly `count` boxes written ...
+        assert np.isnan(out_lo[count]).all() and np.isnan(out_hi[count]).all()                     # ... and not one more
+        return out_lo[:count, :3], out_hi[:count, :3]
+
+    total_gain = []
+    for trial in range(400):
+        scale = 10.0 ** rng.integers(-3, 4)
+        off = rng.normal(size=3) * scale * rng.choice([0.0, 1.0, 30.0])
+        mesh_lo, mesh_hi = off, off + scale * np.array([1.0, rng.uniform(0.2, 1.0), rng.uniform(0.2, 1.0)])
+        kind = trial % 5
+        ext = mesh_hi - mesh_lo
+        a = mesh_lo + rng.uniform(0, 1, 3) * ext
+        if kind == 0:    # long diagonal
+            b = mesh_lo + rng.uniform(0, 1, 3) * ext; c = a + (b - a) * 0.5 + rng.normal(size=3) * 0.02 * ext
+        elif kind == 1:  # axis-aligned flat, large
+            b = mesh_lo + rng.uniform(0, 1, 3) * ext; c = mesh_lo + rng.uniform(0, 1, 3) * ext
+            ax = rng.integers(0, 3); b[ax] = a[ax]; c[ax] = a[ax]
+        elif kind == 2:  # tiny
+            b = a + rng.normal(size=3) * 1e-4 * ext; c = a + rng.normal(size=3) * 1e-4 * ext
+        elif kind == 3:  # vertices on cell boundaries
+            q = lambda: mesh_lo + rng.integers(0, 1025, 3) / 1024.0 * ext
+            a, b, c = q(), q(), q()
+        else:            # mesh-sized
+            b = mesh_lo + rng.uniform(0, 1, 3) * ext; c = mesh_lo + rng.uniform(0, 1, 3) * ext
+        v = np.stack([a, b, c]).astype(np.float32)
+        if np.linalg.norm(np.cross(v[1] - v[0], v[2] - v[0])) == 0:
+            continue
+        count = int(rng.choice([1, 2, 3, 7, 16, 32]))
+        pad = np.float32(2e-6 * np.abs(np.concatenate([mesh_lo, mesh_hi])).max())
+        blo, bhi = call(mesh_lo, mesh_hi, v, count, pad)
+        tlo, thi = v.min(axis=0) - 2 * pad, v.max(axis=0) + 2 * pad
+        assert (blo >= tlo - 1e-30).all() and (bhi <= thi + 1e-30).all() and (blo <= bhi).all()
+        w = rng.dirichlet((1, 1, 1), 2000).astype(np.float64)
+        pts = w @ v.astype(np.float64)
+        inside = ((pts[:, None, :] >= blo[None].astype(np.float64)) & (pts[:, None, :] <= bhi[None].astype(np.float64))).all(axis=2).any(axis=1)
+        assert inside.all(), (trial, kind, count, int((~inside).sum()))
+        if kind == 0 and count >= 16:
+            vol = lambda lo_, hi_: np.prod(np.maximum(hi_ - lo_, 1e-12 * scale), axis=-1)
+            total_gain.append(vol(blo.astype(np.float64), bhi.astype(np.float64)).sum() / vol(tlo.astype(np.float64), thi.astype(np.float64)))
+        pr = emu.emu_split_priority(np.ascontiguousarray(mesh_lo, np.float32).ctypes.data_as(fp), np.ascontiguousarray(mesh_hi, np.float32).ctypes.data_as(fp), v.ctypes.data_as(fp))
+        assert np.isfinite(pr) and pr >= 0.0
+        if kind == 2:
+            assert pr < 0.05
+    assert len(total_gain) > 5 and np.median(total_gain) < 0.35, total_gain
