@@ -93,6 +93,7 @@ struct EmuScene {
     std::vector<InstanceShading> shading;  // per GLOBAL instance id (what k_instance_prepare writes for k_wf_shade)
     EmuBvh tlas;
     SceneView sv{};
+    float split_budget = 0.0f;  // spatial splits (tri_split.h): extra references per triangle, as the product's option split_budget / 100
 };
 
 extern "C" {
@@ -119,11 +120,44 @@ void emu_build(void* s, float c_node, float c_prim, int pmax, uint64_t* stats) {
             m.lo = min3(m.lo, l); m.hi = max3(m.hi, h);
         }
         if (n == 0) continue;
+        // spatial splits, the way builder.cu::split_triangle_refs does them (same bodies, same fixed-point arithmetic): references replace triangles
+        std::vector<uint32_t> ref_prim;
+        if (sc.split_budget > 0.0f && n > RFW_DIRECT_TRIS) {
+            const SplitGrid g = make_split_grid(m.lo, m.hi);
+            std::vector<uint32_t> prio(n), counts(n);
+            unsigned long long sum = 0;
+            auto vtx = [&](int i, int k) { const float* p = k == 0 ? m.tris[i].vertex0 : (k == 1 ? m.tris[i].vertex1 : m.tris[i].vertex2); return f3(p[0], p[1], p[2]); };
+            for (int i = 0; i < n; i++) {
+                const float pr = split_priority(g, vtx(i, 0), vtx(i, 1), vtx(i, 2));
+                prio[i] = (uint32_t)fminf(fmaxf(pr, 0.0f) * 16777216.0f, 4.0e9f);
+                sum += prio[i];
+            }
+            const unsigned long long budget_refs = (unsigned long long)((double)sc.split_budget * (double)n);
+            size_t total = 0;
+            for (int i = 0; i < n; i++) {
+                unsigned long long extra = sum ? (unsigned long long)prio[i] * budget_refs / sum : 0ull;
+                if (extra > (unsigned long long)SPLIT_MAX_EXTRA) extra = SPLIT_MAX_EXTRA;
+                counts[i] = 1u + (uint32_t)extra;
+                total += counts[i];
+            }
+            const float big = fmaxf(fmaxf(fabsf(m.lo.x), fabsf(m.lo.y)), fmaxf(fmaxf(fabsf(m.lo.z), fabsf(m.hi.x)), fmaxf(fabsf(m.hi.y), fabsf(m.hi.z))));
+            std::vector<float4> rlo(total), rhi(total);
+            ref_prim.resize(total);
+            size_t off = 0;
+            for (int i = 0; i < n; i++) {
+                split_triangle(g, vtx(i, 0), vtx(i, 1), vtx(i, 2), (int)counts[i], counts[i] > 1u ? 2.0e-6f * big : 0.0f, rlo.data() + off, rhi.data() + off);
+                for (uint32_t k = 0; k < counts[i]; k++) ref_prim[off + k] = (uint32_t)i;
+                off += counts[i];
+            }
+            lo.swap(rlo); hi.swap(rhi);
+        }
+        const int n_refs = (int)lo.size();
         emu_build(lo, hi, P, m.bvh);
-        m.ttris.resize((size_t)n * 3);
-        for (int k = 0; k < n; k++) {
-            const RfwRTTriangle& t = m.tris[m.bvh.leaf_prims[k]];
-            m.ttris[(size_t)k * 3 + 0] = f4(t.vertex0[0], t.vertex0[1], t.vertex0[2], u2f(m.bvh.leaf_prims[k]));
+        m.ttris.resize((size_t)n_refs * 3);
+        for (int k = 0; k < n_refs; k++) {
+            const uint32_t prim = ref_prim.empty() ? m.bvh.leaf_prims[k] : ref_prim[m.bvh.leaf_prims[k]];
+            const RfwRTTriangle& t = m.tris[prim];
+            m.ttris[(size_t)k * 3 + 0] = f4(t.vertex0[0], t.vertex0[1], t.vertex0[2], u2f(prim));
             m.ttris[(size_t)k * 3 + 1] = f4(t.vertex1[0], t.vertex1[1], t.vertex1[2], 0);
             m.ttris[(size_t)k * 3 + 2] = f4(t.vertex2[0], t.vertex2[1], t.vertex2[2], 0);
         }
@@ -284,6 +318,7 @@ int emu_validate(void* s, uint32_t mesh_id) {
     return errors;
 }
 float emu_sah(void* s, uint32_t mesh_id) { return ((EmuScene*)s)->meshes[mesh_id].bvh.sah; }
+void emu_set_split_budget(void* s, float budget) { ((EmuScene*)s)->split_budget = budget; }
 // spatial splits (tri_split.h): priority of one triangle inside the mesh bounds, and its `count` reference boxes
 float emu_split_priority(const float* mesh_lo, const float* mesh_hi, const float* v) {
     const SplitGrid g = make_split_grid(f3(mesh_lo[0], mesh_lo[1], mesh_lo[2]), f3(mesh_hi[0], mesh_hi[1], mesh_hi[2]));

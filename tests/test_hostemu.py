@@ -36,9 +36,12 @@ def emu():
 
 
 class Emu:
-    def __init__(self, L, desc):
+    def __init__(self, L, desc, split_budget=0.0):
         self.L = L
         self.h = C.c_void_p(L.emu_create())
+        if split_budget > 0.0:
+            L.emu_set_split_budget.argtypes = [C.c_void_p, C.c_float]
+            L.emu_set_split_budget(self.h, split_budget)
         self.keep = []
         for mid, t in desc.meshes.items():
             t = np.ascontiguousarray(t); self.keep.append(t)
@@ -831,3 +834,25 @@ def test_triangle_pre_splitting_covers_the_triangle(emu):
         if kind == 2:
             assert pr < 0.05
     assert len(total_gain) > 5 and np.median(total_gain) < 0.35, total_gain
+
+
+def test_spatial_splits_on_the_cpu_tier_keep_the_hits(emu, oracle_mod):
+    """The product's pre-splitting bodies inside the CPU-tier builder harness (tests/hostemu/emu.cpp mirrors builder.cu::split_triangle_refs:
+    same bodies, same fixed-point budget arithmetic): a mesh mixing triangle scales traced with 0 %, 30 % and 100 % extra references — the
+    same closest hits and any-hit flags (bit for bit but for a handful of near-ties), agreement with the oracle, and far fewer node visits
+    and triangle tests per ray."""
+    desc = scenes.mixed_scale_scene(6000, 60, 8)
+    rays = scenes.random_rays(20000, seed=4)
+    o = oracle_mod.OracleBackend(det_eps=0.0); desc.apply(o)
+    ref = o.trace_closest(rays)
+    out = {}
+    for budget in (0.0, 0.3, 1.0):
+        e = Emu(emu, desc, split_budget=budget)
+        hits, occ, ctr = e.trace(rays)
+        same_id = (hits["inst"] == ref["inst"]) & (hits["prim"] == ref["prim"])
+        assert (~same_id).sum() <= 8, (budget, int((~same_id).sum()))
+        out[budget] = (hits, occ, ctr[0] / len(rays), ctr[1] / len(rays))
+    for budget in (0.3, 1.0):
+        same = (out[0.0][0]["prim"] == out[budget][0]["prim"]) & (out[0.0][0]["t"] == out[budget][0]["t"])
+        assert (~same).sum() <= 4 and (out[0.0][1] != out[budget][1]).sum() <= 2
+        assert out[budget][2] < 0.6 * out[0.0][2] and out[budget][3] < 0.4 * out[0.0][3], (out[0.0][2:], out[budget][2:])
