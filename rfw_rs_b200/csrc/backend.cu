@@ -754,6 +754,11 @@ void Backend::update_l2_policy() {
     auto consider = [&](const DeviceBvh& b) { if (b.nodes && (size_t)b.num_nodes * NODE_BYTES > best_bytes) { best = b.nodes; best_bytes = (size_t)b.num_nodes * NODE_BYTES; } };
     consider(tlas);
     for (const MeshRec& m : meshes) if (m.present) consider(m.bvh);
+    // l2_persist = 2: the window over the largest mesh's traversal triangles instead of its nodes (a stream has ONE window).  On C2 that is where the
+    // re-fetched HBM bytes come from: reads 1.75 -> 0.91 GB per launch (profiles/r2_trace_closest.md) at unchanged speed
+    if (l2_persist_mode == 2)
+        for (const MeshRec& m : meshes)
+            if (m.present && m.d_ttris && (size_t)(m.n_refs ? m.n_refs : m.n) * 48 > best_bytes) { best = m.d_ttris; best_bytes = (size_t)(m.n_refs ? m.n_refs : m.n) * 48; }
     cudaStreamAttrValue attr{};
     if (best && l2_persist_max > 0 && l2_window_max > 0) {
         attr.accessPolicyWindow.base_ptr = const_cast<void*>(best);
@@ -1612,7 +1617,7 @@ int Backend::set_option(const char* key, int64_t value) {
     else if (k == "wf_overlap") wf.overlap = value != 0;  // connect(b) beside extend(b + 1) on a second stream (1, default) or everything on one stream (0)
     else if (k == "inst_batch") tcfg.inst_batch = (int)std::max<int64_t>(1, value);
     else if (k == "min_blocks") tcfg.min_blocks = (int)value;
-    else if (k == "l2_persist") { l2_persist_enabled = value != 0; if (!l2_persist_enabled) { cudaStreamAttrValue a{}; cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &a); cudaCtxResetPersistingL2Cache(); } else { if (l2_persist_max && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, l2_persist_max) != cudaSuccess) { cudaGetLastError(); l2_persist_max = 0; } update_l2_policy(); } }
+    else if (k == "l2_persist") { l2_persist_enabled = value != 0; l2_persist_mode = (int)value; if (!l2_persist_enabled) { cudaStreamAttrValue a{}; cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &a); cudaCtxResetPersistingL2Cache(); } else { if (l2_persist_max && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, l2_persist_max) != cudaSuccess) { cudaGetLastError(); l2_persist_max = 0; } update_l2_policy(); } }
     else if (k == "streamed") streamed_enabled = value != 0;  // host-buffer entry points: single-launch streaming (1) or chunked pipeline (0)
     else if (k == "chunk_rays") chunk_rays = (uint64_t)std::max<int64_t>(1024, value);
     else if (k == "max_depth") cfg.max_depth = (uint32_t)value;

@@ -138,6 +138,7 @@ private:
     ShadeScene shade_scene() const;
     void update_l2_policy();
     size_t l2_persist_max = 0, l2_window_max = 0;
+    int l2_persist_mode = 0;          // 1: persisting window over the largest node array, 2: over the largest traversal-triangle array
     bool l2_persist_enabled = false;  // option "l2_persist": measured no effect on C2 (the 16 MB of nodes stay resident anyway), off by default
 
     RfwB200Config cfg;
