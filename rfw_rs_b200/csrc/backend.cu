@@ -764,6 +764,12 @@ void Backend::update_l2_policy() {
         attr.accessPolicyWindow.base_ptr = const_cast<void*>(best);
         attr.accessPolicyWindow.num_bytes = std::min(best_bytes, l2_window_max);
         attr.accessPolicyWindow.hitRatio = best_bytes <= l2_persist_max ? 1.0f : (float)((double)l2_persist_max / (double)best_bytes);
+        if (l2_persist_mode == 3 && best_bytes > l2_persist_max) {
+            // l2_persist = 3: node arrays are written level by level (k_collapse_all), so the FIRST bytes of a big one are the top of the tree:
+            // the window covers just those, fully persisting, instead of a random fraction of the whole array
+            attr.accessPolicyWindow.num_bytes = std::min(l2_persist_max, l2_window_max);
+            attr.accessPolicyWindow.hitRatio = 1.0f;
+        }
         attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
         attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     } else {
