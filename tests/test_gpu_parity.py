@@ -643,12 +643,15 @@ def rmse(a, b):
     return float(np.sqrt(np.mean((a[..., :3].astype(np.float64) - b[..., :3].astype(np.float64)) ** 2)))
 
 
-# Image tolerance (stated): with identical RNG streams the two path tracers take the same
-# discrete decisions except where a ray passes within float32 resolution of a triangle edge / silhouette or a hit
-# lies within rounding of tmin/tmax (the same near-tie classes as for IDs; measured rate ~1e-4 per sample).  Such a
-# path carries a different, up-to-clamp-sized contribution, so:
-#   * RMSE over the pixels left after dropping the DIVERGED_FRACTION (0.2 %) largest differences  <= 1e-3
-#   * RMSE over all pixels                                                                          <= ALL_PIXEL_RMSE
+# Image tolerance (stated; measured values of every comparison: profiles/r2_image_parity.md).  With identical RNG streams
+# the two path tracers take the same discrete decisions except where an ulp-sized difference — of a shaded ray (contracted FMAs, CUDA's vs
+# glibc's sinf / cosf: GLSL leaves both implementation-defined) or of a hit (watertight vs Moller-Trumbore at an edge) — decides an edge, a
+# silhouette or a tmin / tmax bound the other way.  Such a path carries a different, up-to-clamp-sized contribution, so:
+#   * RMSE over the pixels left after dropping the DIVERGED_FRACTION (0.2 %) largest differences  <= 1e-3   (measured 2e-7 ... 6e-4)
+#   * RMSE over all pixels                                                                          <= ALL_PIXEL_RMSE (measured 6e-6 ... 1e-2)
+# The literal all-pixel 1e-3 is asserted where it is reachable (test_literal_rmse_bar_with_the_reference_triangle_arithmetic,
+# test_all_pixel_rmse_at_converging_sample_count); option tri_test = 1 removes the hit differences entirely and the image differences
+# stay — they come from the shading arithmetic.
 RMSE_BAR = 1e-3
 ALL_PIXEL_RMSE = 1e-2
 DIVERGED_FRACTION = 2e-3
