@@ -477,47 +477,72 @@ int Backend::synchronize() {
             side_ctx.push_back(c);
         }
         if (n_side) BK_CUDA(cudaStreamSynchronize(stream), "sync");  // uploads and frees issued on the main stream precede the side streams' work
+        // one mesh's build, enqueued on `bc`'s stream (no host state beyond the mesh record and the context is touched: safe to run from a
+        // helper thread, one thread per context)
+        auto build_one = [&](MeshRec& m, BuilderContext& bc) -> cudaError_t {
+            cudaStream_t bs = bc.stream;
+            float4 *lo = nullptr, *hi = nullptr;
+            cudaError_t e = cudaMallocAsync(&lo, (size_t)m.n * sizeof(float4), bs);
+            if (e == cudaSuccess) e = cudaMallocAsync(&hi, (size_t)m.n * sizeof(float4), bs);
+            if (e == cudaSuccess) e = triangle_boxes(bc, m.d_tris, (int)m.n, lo, hi);
+            m.n_refs = m.n;
+            if (e == cudaSuccess && split_budget > 0 && m.n > (uint32_t)RFW_DIRECT_TRIS) {
+                // spatial splits (option "split_budget", percent of extra references): the BVH is built over clipped reference boxes,
+                // the leaf-ordered traversal triangles repeat a split triangle once per reference (tri_split.h)
+                SplitRefs refs;
+                e = split_triangle_refs(bc, m.d_tris, (int)m.n, lo, hi, (float)split_budget * 0.01f, refs);
+                if (e == cudaSuccess) e = build_wide_bvh(bc, refs.lo, refs.hi, refs.n_refs, blas_params, m.bvh, /*deferred=*/refs.n_refs <= BUILD_DEFER_MAX);
+                if (e == cudaSuccess) {
+                    m.n_refs = (uint32_t)refs.n_refs;
+                    e = cudaMallocAsync(&m.d_ttris, (size_t)m.n_refs * 3 * sizeof(float4), bs);
+                    if (e == cudaSuccess) e = gather_traversal_triangles_refs(bc, m.d_tris, m.bvh.leaf_prims, refs.prim, refs.n_refs, m.d_ttris);
+                }
+                if (refs.lo) cudaFreeAsync(refs.lo, bs);
+                if (refs.hi) cudaFreeAsync(refs.hi, bs);
+                if (refs.prim) cudaFreeAsync(refs.prim, bs);
+            } else {
+                if (e == cudaSuccess) e = build_wide_bvh(bc, lo, hi, (int)m.n, blas_params, m.bvh, /*deferred=*/true);  // small meshes: no host sync per mesh
+                if (e == cudaSuccess) e = cudaMallocAsync(&m.d_ttris, (size_t)m.n * 3 * sizeof(float4), bs);
+                if (e == cudaSuccess) e = gather_traversal_triangles(bc, m.d_tris, m.bvh.leaf_prims, (int)m.n, m.d_ttris);
+            }
+            if (lo) cudaFreeAsync(lo, bs);
+            if (hi) cudaFreeAsync(hi, bs);
+            return e;
+        };
+        // dirty meshes: old structures freed here, small ones dealt round-robin onto the side contexts, the rest stay on the main context
+        std::vector<std::vector<MeshRec*>> side_work((size_t)n_side);
+        std::vector<MeshRec*> main_work;
         int next_side = 0;
         for (MeshRec& m : meshes) {
             if (!m.present || !m.dirty) continue;
             rebuilt_meshes.insert((uint32_t)(&m - meshes.data()));
             if (m.d_ttris) { cudaFree(m.d_ttris); m.d_ttris = nullptr; }
             m.bvh.release();
-            if (m.n) {
-                BuilderContext& bc = (n_side && m.n <= (uint32_t)BUILD_DEFER_MAX) ? *side_ctx[(next_side++) % n_side] : bctx;
-                cudaStream_t bs = bc.stream;
-                float4 *lo = nullptr, *hi = nullptr;
-                BK_CUDA(cudaMallocAsync(&lo, (size_t)m.n * sizeof(float4), bs), "box alloc");
-                BK_CUDA(cudaMallocAsync(&hi, (size_t)m.n * sizeof(float4), bs), "box alloc");
-                cudaError_t e = triangle_boxes(bc, m.d_tris, (int)m.n, lo, hi);
-                m.n_refs = m.n;
-                if (e == cudaSuccess && split_budget > 0 && m.n > (uint32_t)RFW_DIRECT_TRIS) {
-                    // spatial splits (option "split_budget", percent of extra references): the BVH is built over clipped reference boxes,
-                    // the leaf-ordered traversal triangles repeat a split triangle once per reference (tri_split.h)
-                    SplitRefs refs;
-                    e = split_triangle_refs(bc, m.d_tris, (int)m.n, lo, hi, (float)split_budget * 0.01f, refs);
-                    if (e == cudaSuccess) e = build_wide_bvh(bc, refs.lo, refs.hi, refs.n_refs, blas_params, m.bvh, /*deferred=*/refs.n_refs <= BUILD_DEFER_MAX);
-                    cudaFreeAsync(lo, bs); cudaFreeAsync(hi, bs);
-                    if (e == cudaSuccess) {
-                        m.n_refs = (uint32_t)refs.n_refs;
-                        e = cudaMallocAsync(&m.d_ttris, (size_t)m.n_refs * 3 * sizeof(float4), bs);
-                        if (e == cudaSuccess) e = gather_traversal_triangles_refs(bc, m.d_tris, m.bvh.leaf_prims, refs.prim, refs.n_refs, m.d_ttris);
-                    }
-                    if (refs.lo) cudaFreeAsync(refs.lo, bs);
-                    if (refs.hi) cudaFreeAsync(refs.hi, bs);
-                    if (refs.prim) cudaFreeAsync(refs.prim, bs);
-                    if (e != cudaSuccess) return cuda_fail(e, "BLAS build (spatial splits)");
-                    m.dirty = false;
-                    continue;
-                }
-                if (e == cudaSuccess) e = build_wide_bvh(bc, lo, hi, (int)m.n, blas_params, m.bvh, /*deferred=*/true);  // small meshes: no host sync per mesh
-                cudaFreeAsync(lo, bs); cudaFreeAsync(hi, bs);
-                if (e != cudaSuccess) return cuda_fail(e, "BLAS build");
-                BK_CUDA(cudaMallocAsync(&m.d_ttris, (size_t)m.n * 3 * sizeof(float4), bs), "triangle alloc");
-                BK_CUDA(gather_traversal_triangles(bc, m.d_tris, m.bvh.leaf_prims, (int)m.n, m.d_ttris), "gather triangles");
-            }
             m.dirty = false;
+            if (!m.n) continue;
+            if (n_side && m.n <= (uint32_t)BUILD_DEFER_MAX) side_work[(size_t)((next_side++) % n_side)].push_back(&m);
+            else main_work.push_back(&m);
         }
+        // A small build is ~17 launches of tiny kernels: 170 meshes are ~3 000 launches, and ONE host thread enqueues them at ~4.7 us each
+        // (14 ms, whatever the number of streams).  With option build_threads (default on) every side context gets its own host thread.
+        std::vector<cudaError_t> side_err((size_t)n_side, cudaSuccess);
+        auto run_side = [&](int k) {
+            cudaSetDevice(cfg.device);
+            for (MeshRec* m : side_work[(size_t)k]) {
+                const cudaError_t e = build_one(*m, *side_ctx[(size_t)k]);
+                if (e != cudaSuccess) { side_err[(size_t)k] = e; break; }
+            }
+        };
+        if (n_side && build_threads) {
+            std::vector<std::thread> workers;
+            for (int k = 0; k < n_side; k++) workers.emplace_back(run_side, k);
+            for (MeshRec* m : main_work) { const cudaError_t e = build_one(*m, bctx); if (e != cudaSuccess) { for (auto& w : workers) w.join(); return cuda_fail(e, "BLAS build"); } }
+            for (auto& w : workers) w.join();
+        } else {
+            for (int k = 0; k < n_side; k++) run_side(k);
+            for (MeshRec* m : main_work) { const cudaError_t e = build_one(*m, bctx); if (e != cudaSuccess) return cuda_fail(e, "BLAS build"); }
+        }
+        for (int k = 0; k < n_side; k++) if (side_err[(size_t)k] != cudaSuccess) return cuda_fail(side_err[(size_t)k], "BLAS build");
         for (int k = 0; k < n_side; k++) {
             BK_CUDA(finish_pending_builds(*side_ctx[k]), "BLAS build");
             BK_CUDA(cudaStreamSynchronize(side_ctx[k]->stream), "BLAS build");
@@ -1627,6 +1652,7 @@ int Backend::set_option(const char* key, int64_t value) {
     else if (k == "streamed") streamed_enabled = value != 0;  // host-buffer entry points: single-launch streaming (1) or chunked pipeline (0)
     else if (k == "chunk_rays") chunk_rays = (uint64_t)std::max<int64_t>(1024, value);
     else if (k == "max_depth") cfg.max_depth = (uint32_t)value;
+    else if (k == "build_threads") build_threads = value != 0;  // one host thread per side builder context (1, default) or all launches from the calling thread (0)
     else if (k == "build_streams") build_streams = (int)std::min<int64_t>(64, std::max<int64_t>(1, value));
     else if (k == "sah_treelet_tlas") { sah_treelet_tlas = (int)value; scene_dirty = true; synchronized = false; }
     else if (k == "sah_treelet") { sah_treelet = (int)value; for (auto& m : meshes) if (m.present) m.dirty = true; scene_dirty = true; synchronized = false; }

@@ -8,6 +8,7 @@ be = backend.B200Backend(); desc.apply(be)
 print("cold", be.build_stats()["blas_build_ms"], "ms; meshes", be.build_stats()["num_meshes"], "launches", be.launch_count())
 for k in range(8):
     be.set_option("build_streams", 1 if k < 4 else int(os.environ.get("BUILD_STREAMS", 8)))  # first four: everything on the main stream
+    be.set_option("build_threads", int(os.environ.get("BUILD_THREADS", 1)))
     l0 = be.launch_count()
     be.set_option("sah_treelet", 8); t0 = time.perf_counter(); be.synchronize(); dt = (time.perf_counter() - t0) * 1e3
     print(f"warm rebuild {k}: blas_build_ms {be.build_stats()['blas_build_ms']:.2f} (device events), synchronize wall {dt:.2f} ms, kernel launches {be.launch_count() - l0}")
