@@ -468,7 +468,9 @@ int Backend::synchronize() {
         std::set<uint32_t> rebuilt_meshes;
         // many small dirty meshes: deal them onto the side contexts (see backend.h); big meshes fill the GPU on their own
         int n_small = 0;
-        for (const MeshRec& m : meshes) n_small += (m.present && m.dirty && m.n > 0 && m.n <= (uint32_t)BUILD_DEFER_MAX) ? 1 : 0;
+        // meshes of <= BUILD_FUSED_MAX triangles: all of them in ONE launch, one CTA per mesh (option "build_fused", default on)
+        auto fused_ok = [&](const MeshRec& m) { return build_fused && m.n > 0 && m.n <= (uint32_t)BUILD_FUSED_MAX && !(split_budget > 0 && m.n > (uint32_t)RFW_DIRECT_TRIS); };
+        for (const MeshRec& m : meshes) n_small += (m.present && m.dirty && m.n > 0 && m.n <= (uint32_t)BUILD_DEFER_MAX && !fused_ok(m)) ? 1 : 0;
         const int n_side = (n_small >= 4 && build_streams > 1) ? std::min(build_streams, n_small) : 0;
         while ((int)side_ctx.size() < n_side) {
             BuilderContext* c = new BuilderContext();
@@ -512,6 +514,7 @@ int Backend::synchronize() {
         // dirty meshes: old structures freed here, small ones dealt round-robin onto the side contexts, the rest stay on the main context
         std::vector<std::vector<MeshRec*>> side_work((size_t)n_side);
         std::vector<MeshRec*> main_work;
+        std::vector<SmallBuildItem> fused_work;
         int next_side = 0;
         for (MeshRec& m : meshes) {
             if (!m.present || !m.dirty) continue;
@@ -520,11 +523,13 @@ int Backend::synchronize() {
             m.bvh.release();
             m.dirty = false;
             if (!m.n) continue;
+            if (fused_ok(m)) { m.n_refs = m.n; fused_work.push_back(SmallBuildItem{m.d_tris, nullptr, nullptr, (int)m.n, &m.bvh, &m.d_ttris}); continue; }
             if (n_side && m.n <= (uint32_t)BUILD_DEFER_MAX) side_work[(size_t)((next_side++) % n_side)].push_back(&m);
             else main_work.push_back(&m);
         }
         // A small build is ~17 launches of tiny kernels: 170 meshes are ~3 000 launches, and ONE host thread enqueues them at ~4.7 us each
         // (14 ms, whatever the number of streams).  With option build_threads (default on) every side context gets its own host thread.
+        if (!fused_work.empty()) BK_CUDA(build_small_batch(bctx, fused_work.data(), (int)fused_work.size(), blas_params), "BLAS build (fused)");
         std::vector<cudaError_t> side_err((size_t)n_side, cudaSuccess);
         auto run_side = [&](int k) {
             cudaSetDevice(cfg.device);
@@ -680,7 +685,12 @@ int Backend::synchronize() {
             cudaError_t e = cudaSuccess;
             if (live > 1) {
                 const BuildParams tlas_params{1.0f, 4.0f, 1, sah_treelet_tlas};
-                e = build_wide_bvh(bctx, lo, hi, (int)live, tlas_params, tlas, /*deferred=*/true);
+                if (build_fused && live <= (uint32_t)BUILD_FUSED_MAX) {
+                    const SmallBuildItem item{nullptr, lo, hi, (int)live, &tlas, nullptr};
+                    e = build_small_batch(bctx, &item, 1, tlas_params);
+                } else {
+                    e = build_wide_bvh(bctx, lo, hi, (int)live, tlas_params, tlas, /*deferred=*/true);
+                }
                 if (e == cudaSuccess) e = d_leaf_instances.reserve(live);
                 if (e == cudaSuccess) {  // instance records in leaf-slot order (the leaf_prims pointer is valid stream-ordered)
                     k_gather_instances<<<(live + 127) / 128, 128, 0, stream>>>(d_instances.ptr, tlas.leaf_prims, live, d_leaf_instances.ptr);
@@ -1652,6 +1662,7 @@ int Backend::set_option(const char* key, int64_t value) {
     else if (k == "streamed") streamed_enabled = value != 0;  // host-buffer entry points: single-launch streaming (1) or chunked pipeline (0)
     else if (k == "chunk_rays") chunk_rays = (uint64_t)std::max<int64_t>(1024, value);
     else if (k == "max_depth") cfg.max_depth = (uint32_t)value;
+    else if (k == "build_fused") build_fused = value != 0;  // meshes / TLASes of <= 2 048 boxes built by one CTA each, all in one launch (1, default) or by the general builder (0)
     else if (k == "build_threads") build_threads = value != 0;  // one host thread per side builder context (1, default) or all launches from the calling thread (0)
     else if (k == "build_streams") build_streams = (int)std::min<int64_t>(64, std::max<int64_t>(1, value));
     else if (k == "sah_treelet_tlas") { sah_treelet_tlas = (int)value; scene_dirty = true; synchronized = false; }

@@ -152,6 +152,7 @@ private:
     // that several chains are in flight at once.  Option "build_streams" (default 8; 1 = everything on the main stream).
     std::vector<BuilderContext*> side_ctx;
     int build_streams = 8;
+    bool build_fused = true;    // option "build_fused": meshes (and a TLAS) of <= BUILD_FUSED_MAX boxes are built by ONE CTA each, all in one launch (builder.cu::k_build_small)
     bool build_threads = true;  // option "build_threads": the side contexts' launches are enqueued by one host thread each
     TraceConfig tcfg;
     RaySortScratch ray_sort;          // ray binning for scenes beyond the L2 (trace.h::trace_sorted)

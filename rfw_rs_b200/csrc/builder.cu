@@ -11,7 +11,10 @@
 #include <cooperative_groups.h>
 #include <stdio.h>
 
+#include <algorithm>
+
 #include "builder.h"
+#include "sort_small.cuh"
 #include "tri_split.h"
 
 namespace cg = cooperative_groups;
@@ -334,38 +337,57 @@ __device__ void sah_split_segment(int4 seg, int* __restrict__ items, int* __rest
     __syncwarp();
 }
 
-// cooperative: all levels of the top-down build in one launch, grid.sync between levels
-__global__ void __launch_bounds__(128) k_sah_top(BuildArrays A, int* __restrict__ items, int* __restrict__ items_tmp, int4* __restrict__ seg0, int4* __restrict__ seg1,
-                                                 uint32_t* __restrict__ counters) {
-    cg::grid_group grid = cg::this_grid();
-    __shared__ SahBins bins[4];
+// Who takes part in a level loop and how they wait for each other: the whole cooperative grid (one big build), or one CTA (the fused
+// build of many small meshes, k_build_small: one CTA per mesh).
+struct GridScope {
+    cg::grid_group g;
+    __device__ uint32_t tid() const { return blockIdx.x * blockDim.x + threadIdx.x; }
+    __device__ uint32_t n_threads() const { return gridDim.x * blockDim.x; }
+    __device__ bool leader() const { return blockIdx.x == 0 && threadIdx.x == 0; }
+    __device__ void sync() { __threadfence(); g.sync(); }
+};
+struct CtaScope {
+    __device__ uint32_t tid() const { return threadIdx.x; }
+    __device__ uint32_t n_threads() const { return blockDim.x; }
+    __device__ bool leader() const { return threadIdx.x == 0; }
+    __device__ void sync() { __threadfence(); __syncthreads(); }
+};
+
+// all levels of the top-down SAH build over the treelets; `bins`: one SahBins per warp of the CTA (shared memory)
+template <class Scope>
+__device__ void sah_top_loop(Scope sc, const BuildArrays& A, int* __restrict__ items, int* __restrict__ items_tmp, int4* __restrict__ seg0, int4* __restrict__ seg1,
+                             uint32_t* __restrict__ counters, SahBins* bins) {
     const int warp_in_block = threadIdx.x >> 5;
-    const uint32_t warp = blockIdx.x * 4 + warp_in_block, n_warps = gridDim.x * 4;
+    const uint32_t warp = sc.tid() >> 5, n_warps = sc.n_threads() >> 5;
     const uint32_t m = counters[4];
-    if (m < 2) return;  // uniform across the grid: nobody reaches a grid.sync
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (m < 2) return;  // uniform across the scope: nobody reaches a sync
+    if (sc.leader()) {
         seg0[0] = make_int4(0, (int)m, 2 * A.n - 1, 0);
         A.parent[2 * A.n - 1] = -1;
         counters[5] = 1;  // top nodes allocated (the root)
         counters[6] = 0; counters[7] = 0;
     }
-    __threadfence();
-    grid.sync();
+    sc.sync();
     uint32_t count = 1;
     int ping = 0;
     int4 *sin = seg0, *sout = seg1;
     while (count > 0) {
         uint32_t* next = counters + 6 + ping;
         for (uint32_t s = warp; s < count; s += n_warps) sah_split_segment(sin[s], items, items_tmp, A, bins[warp_in_block], sout, next, counters + 5);
-        __threadfence();
-        grid.sync();
+        sc.sync();
         count = *((volatile uint32_t*)next);
-        if (blockIdx.x == 0 && threadIdx.x == 0) counters[6 + (ping ^ 1)] = 0;
-        __threadfence();
-        grid.sync();
+        if (sc.leader()) counters[6 + (ping ^ 1)] = 0;
+        sc.sync();
         int4* t = sin; sin = sout; sout = t;
         ping ^= 1;
     }
+}
+
+// cooperative: all levels of the top-down build in one launch, grid.sync between levels
+__global__ void __launch_bounds__(128) k_sah_top(BuildArrays A, int* __restrict__ items, int* __restrict__ items_tmp, int4* __restrict__ seg0, int4* __restrict__ seg1,
+                                                 uint32_t* __restrict__ counters) {
+    __shared__ SahBins bins[4];
+    sah_top_loop(GridScope{cg::this_grid()}, A, items, items_tmp, seg0, seg1, counters, bins);
 }
 
 // re-cost the top tree bottom-up: one thread per treelet root climbs (second arrival computes the node)
@@ -387,18 +409,17 @@ __global__ void __launch_bounds__(TB) k_fit_top(BuildArrays A, BuildParams P, co
 // ------------------------------------------------------------------------------------------------
 // collapse: cooperative level loop
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_collapse_all(BuildArrays A, CollapseOut O, int2* __restrict__ q0, int2* __restrict__ q1, uint32_t* __restrict__ counters) {
-    cg::grid_group grid = cg::this_grid();
-    const uint32_t tid = blockIdx.x * 128 + threadIdx.x, n_threads = gridDim.x * 128;
-    if (tid == 0) {
+template <class Scope>
+__device__ void collapse_loop(Scope sc, const BuildArrays& A, const CollapseOut& O, int2* __restrict__ q0, int2* __restrict__ q1, uint32_t* __restrict__ counters) {
+    const uint32_t tid = sc.tid(), n_threads = sc.n_threads();
+    if (sc.leader()) {
         const bool refined = counters[4] >= 2;  // the SAH top tree exists: its root is node 2n-1
         q0[0] = make_int2(refined ? 2 * A.n - 1 : 0, 0);
         counters[0] = 1;  // wide nodes allocated (root)
         counters[1] = 0;  // leaf slots allocated
         counters[2] = 0; counters[3] = 0;
     }
-    __threadfence();
-    grid.sync();
+    sc.sync();
     uint32_t count = 1;
     int ping = 0;
     uint32_t levels = 0;
@@ -407,16 +428,17 @@ __global__ void __launch_bounds__(128) k_collapse_all(BuildArrays A, CollapseOut
         levels++;
         uint32_t* next = counters + 2 + ping;
         for (uint32_t t = tid; t < count; t += n_threads) collapse_body(qin[t], A, O, qout, next);
-        __threadfence();
-        grid.sync();
+        sc.sync();
         count = *((volatile uint32_t*)next);
-        if (tid == 0) counters[2 + (ping ^ 1)] = 0;
-        __threadfence();
-        grid.sync();
+        if (sc.leader()) counters[2 + (ping ^ 1)] = 0;
+        sc.sync();
         int2* t = qin; qin = qout; qout = t;
         ping ^= 1;
     }
-    if (tid == 0) counters[5] = levels;  // depth of the wide tree (counters[5] was the SAH top build's node counter, done by now)
+    if (sc.leader()) counters[5] = levels;  // depth of the wide tree (counters[5] was the SAH top build's node counter, done by now)
+}
+__global__ void __launch_bounds__(128) k_collapse_all(BuildArrays A, CollapseOut O, int2* __restrict__ q0, int2* __restrict__ q1, uint32_t* __restrict__ counters) {
+    collapse_loop(GridScope{cg::this_grid()}, A, O, q0, q1, counters);
 }
 
 __global__ void __launch_bounds__(TB) k_gather_tris(const RfwRTTriangle* __restrict__ tris, const uint32_t* __restrict__ leaf_prims, int n, float4* __restrict__ out) {
@@ -430,6 +452,228 @@ __global__ void __launch_bounds__(TB) k_gather_tris(const RfwRTTriangle* __restr
     out[(size_t)k * 3 + 0] = a;
     out[(size_t)k * 3 + 1] = b;
     out[(size_t)k * 3 + 2] = c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused build of small inputs: ONE CTA runs the whole pipeline of one mesh (n <= SORT_TILE boxes) — boxes, bounds, Morton, sort, Karras,
+// fit + cost DP, SAH refinement of the top tree, collapse, traversal triangles — with __syncthreads() where the big build has kernel
+// boundaries or grid syncs; one launch builds every small mesh of a scene (grid = number of meshes).  The bodies are the big build's own
+// (bvh_build.h, sort_small.cuh, sah_top_loop / collapse_loop above), so a mesh gets the same tree either way.
+// ------------------------------------------------------------------------------------------------
+struct SmallCarve {  // per-job scratch, carved the same way by the host (size) and the device (pointers)
+    uint64_t *keys, *keys_tmp;
+    uint32_t *vals, *vals_tmp, *decision, *counters, *tre_flag, *tre_rank;
+    int *parent, *flags, *tre_node, *items, *items_tmp;
+    int2 *children, *range, *q0, *q1;
+    int4 *seg0, *seg1;
+    float4 *node_lo, *node_hi, *prim_lo, *prim_hi;
+    float* cost;
+    template <typename T>
+    __host__ __device__ static T* take(char* base, size_t& off, size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        T* r = reinterpret_cast<T*>(base + off);
+        off += count * sizeof(T);
+        return r;
+    }
+    __host__ __device__ size_t carve(char* base, int n, bool refine, bool own_boxes) {
+        const size_t m_max = refine ? (size_t)n : 0, nn = 2 * (size_t)n - 1 + m_max, ni = (n > 1 ? (size_t)n - 1 : 1) + m_max;
+        size_t off = 0;
+        keys = take<uint64_t>(base, off, n); keys_tmp = take<uint64_t>(base, off, n);
+        vals = take<uint32_t>(base, off, n); vals_tmp = take<uint32_t>(base, off, n);
+        parent = take<int>(base, off, nn); flags = take<int>(base, off, ni);
+        children = take<int2>(base, off, ni); range = take<int2>(base, off, ni);
+        node_lo = take<float4>(base, off, nn); node_hi = take<float4>(base, off, nn);
+        cost = take<float>(base, off, nn * 8);
+        decision = take<uint32_t>(base, off, ni);
+        q0 = take<int2>(base, off, n); q1 = take<int2>(base, off, n);
+        counters = take<uint32_t>(base, off, 16);
+        prim_lo = prim_hi = nullptr;
+        if (own_boxes) { prim_lo = take<float4>(base, off, n); prim_hi = take<float4>(base, off, n); }
+        tre_flag = tre_rank = nullptr; tre_node = items = items_tmp = nullptr; seg0 = seg1 = nullptr;
+        if (refine) {
+            tre_flag = take<uint32_t>(base, off, n); tre_rank = take<uint32_t>(base, off, n); tre_node = take<int>(base, off, n);
+            items = take<int>(base, off, n); items_tmp = take<int>(base, off, n);
+            seg0 = take<int4>(base, off, n); seg1 = take<int4>(base, off, n);
+        }
+        return (off + 255) & ~(size_t)255;
+    }
+};
+
+struct SmallBuildJob {
+    const RfwRTTriangle* tris;  // BLAS: the mesh (boxes are computed here); null for a build over given boxes (TLAS)
+    const float4 *lo, *hi;      // given boxes (tris == null)
+    int n, refine;
+    char* scratch;
+    float4* nodes;              // [n] wide nodes (upper bound), zero-filled here
+    uint32_t* leaf_prims;       // [n]
+    float4* ttris;              // [3n] traversal triangles (BLAS) or null
+    BuildResultSlot* result;    // device
+};
+
+__global__ void __launch_bounds__(SORT_THREADS) k_build_small(const SmallBuildJob* __restrict__ jobs, BuildParams P) {
+    const SmallBuildJob job = jobs[blockIdx.x];
+    const int n = job.n, t = threadIdx.x;
+    const bool refine = job.refine != 0;
+    SmallCarve c;
+    c.carve(job.scratch, n, refine, job.tris != nullptr);
+    __shared__ SahBins bins[SORT_WARPS];
+    __shared__ float part[SORT_WARPS][12];
+    __shared__ uint32_t s_bounds[12];
+    __shared__ uint32_t s_scan[SORT_WARPS];
+    CtaScope sc;
+
+    // 0. clear; 1. boxes + bounds
+    const float4 *plo = job.lo, *phi = job.hi;
+    if (job.tris) {
+        for (int i = t; i < n; i += SORT_THREADS) {
+            const float4* p = reinterpret_cast<const float4*>(job.tris + i);
+            const float4 a = __ldg(p), b = __ldg(p + 1), cc = __ldg(p + 2);
+            c.prim_lo[i] = make_float4(fminf(a.x, fminf(b.x, cc.x)), fminf(a.y, fminf(b.y, cc.y)), fminf(a.z, fminf(b.z, cc.z)), 0.0f);
+            c.prim_hi[i] = make_float4(fmaxf(a.x, fmaxf(b.x, cc.x)), fmaxf(a.y, fmaxf(b.y, cc.y)), fmaxf(a.z, fmaxf(b.z, cc.z)), 0.0f);
+        }
+        plo = c.prim_lo; phi = c.prim_hi;
+    }
+    if (t < 16) c.counters[t] = 0;
+    {
+        const size_t ni = (n > 1 ? (size_t)n - 1 : 1) + (refine ? (size_t)n : 0);
+        for (size_t i = t; i < ni; i += SORT_THREADS) c.flags[i] = 0;
+        if (refine) for (int i = t; i < n; i += SORT_THREADS) c.tre_flag[i] = 0u;
+        for (size_t i = t; i < (size_t)n * NODE_F4; i += SORT_THREADS) job.nodes[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    sc.sync();
+    {
+        float v[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) v[k] = ((k % 6) < 3) ? 3.0e38f : -3.0e38f;
+        for (int i = t; i < n; i += SORT_THREADS) {
+            const float4 l = plo[i], h = phi[i];
+            const float cx = (l.x + h.x) * 0.5f, cy = (l.y + h.y) * 0.5f, cz = (l.z + h.z) * 0.5f;
+            v[0] = fminf(v[0], cx); v[1] = fminf(v[1], cy); v[2] = fminf(v[2], cz);
+            v[3] = fmaxf(v[3], cx); v[4] = fmaxf(v[4], cy); v[5] = fmaxf(v[5], cz);
+            v[6] = fminf(v[6], l.x); v[7] = fminf(v[7], l.y); v[8] = fminf(v[8], l.z);
+            v[9] = fmaxf(v[9], h.x); v[10] = fmaxf(v[10], h.y); v[11] = fmaxf(v[11], h.z);
+        }
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+            const bool is_min = (k % 6) < 3;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float y = __shfl_xor_sync(FULLMASK, v[k], o);
+                v[k] = is_min ? fminf(v[k], y) : fmaxf(v[k], y);
+            }
+        }
+        if ((t & 31) == 0) {
+#pragma unroll
+            for (int k = 0; k < 12; k++) part[t >> 5][k] = v[k];
+        }
+        __syncthreads();
+        if (t < 12) {
+            const bool is_min = (t % 6) < 3;
+            float r = part[0][t];
+            for (int w = 1; w < SORT_WARPS; w++) r = is_min ? fminf(r, part[w][t]) : fmaxf(r, part[w][t]);
+            s_bounds[t] = enc_f(r);
+        }
+        __syncthreads();
+    }
+    // 2. Morton keys
+    {
+        const float3 cmin = f3(dec_f(s_bounds[0]), dec_f(s_bounds[1]), dec_f(s_bounds[2]));
+        const float3 cmax = f3(dec_f(s_bounds[3]), dec_f(s_bounds[4]), dec_f(s_bounds[5]));
+        const float3 e = cmax - cmin;
+        const float3 cscale = f3(e.x > 0.0f ? 2097152.0f / e.x : 0.0f, e.y > 0.0f ? 2097152.0f / e.y : 0.0f, e.z > 0.0f ? 2097152.0f / e.z : 0.0f);
+        for (int i = t; i < n; i += SORT_THREADS) morton_body(i, plo, phi, cmin, cscale, c.keys, c.vals);
+    }
+    sc.sync();
+    // 3. sort (8 passes: the result is back in keys / vals)
+    if (n > 1) sort_small_body(c.keys, c.vals, c.keys_tmp, c.vals_tmp, n, 0, 64);
+    sc.sync();
+    BuildArrays A;
+    A.n = n; A.prim_lo = plo; A.prim_hi = phi; A.keys = c.keys; A.order = c.vals;
+    A.parent = c.parent; A.children = c.children; A.range = c.range; A.node_lo = c.node_lo; A.node_hi = c.node_hi;
+    A.cost = c.cost; A.decision = c.decision; A.flags = c.flags;
+    // 4. Karras tree, 5. fit + cost DP
+    for (int i = t; i < n - 1; i += SORT_THREADS) karras_body(i, n, c.keys, c.parent, c.children, c.range);
+    sc.sync();
+    for (int k = t; k < n; k += SORT_THREADS) fit_cost_body(k, A, P);
+    sc.sync();
+    // 6. binned-SAH refinement above the treelets
+    if (refine) {
+        for (int node = t; node < 2 * n - 1; node += SORT_THREADS) {
+            const int cnt = node_prim_count(node, A);
+            if (cnt > P.treelet) continue;
+            const int par = A.parent[node];
+            if (par >= 0 && node_prim_count(par, A) <= P.treelet) continue;
+            const int first = is_leaf_node(node, n) ? node - (n - 1) : A.range[node].x;
+            c.tre_flag[first] = 1u;
+            c.tre_node[first] = node;
+        }
+        sc.sync();
+        {   // exclusive scan of the flags: SORT_ITEMS consecutive positions per thread
+            uint32_t f[SORT_ITEMS], sum = 0;
+#pragma unroll
+            for (int k = 0; k < SORT_ITEMS; k++) { const int p = t * SORT_ITEMS + k; f[k] = p < n ? c.tre_flag[p] : 0u; sum += f[k]; }
+            uint32_t x = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULLMASK, x, o); if ((t & 31) >= o) x += y; }
+            if ((t & 31) == 31) s_scan[t >> 5] = x;
+            __syncthreads();
+            uint32_t run = x - sum;
+            for (int w = 0; w < (t >> 5); w++) run += s_scan[w];
+#pragma unroll
+            for (int k = 0; k < SORT_ITEMS; k++) {
+                const int p = t * SORT_ITEMS + k;
+                if (p < n) {
+                    if (f[k]) c.items[run] = c.tre_node[p];
+                    if (p == n - 1) c.counters[4] = run + f[k];  // number of treelets
+                }
+                run += f[k];
+            }
+        }
+        sc.sync();
+        sah_top_loop(sc, A, c.items, c.items_tmp, c.seg0, c.seg1, c.counters, bins);
+        sc.sync();
+        {
+            const uint32_t m = c.counters[4];
+            if (m >= 2) {
+                for (uint32_t k = t; k < m; k += SORT_THREADS) {
+                    int cur = A.parent[c.items[k]];
+                    while (cur >= 0) {
+                        __threadfence();
+                        const int old = atomicAdd(&A.flags[inner_index(cur, n)], 1);
+                        if (old == 0) break;
+                        __threadfence();
+                        fit_cost_node(cur, A, P);
+                        cur = A.parent[cur];
+                    }
+                }
+            }
+        }
+        sc.sync();
+    }
+    // 7. collapse
+    CollapseOut O;
+    O.nodes = job.nodes; O.leaf_prims = job.leaf_prims; O.node_counter = c.counters + 0; O.prim_counter = c.counters + 1;
+    collapse_loop(sc, A, O, c.q0, c.q1, c.counters);
+    sc.sync();
+    // 8. traversal triangles in leaf order, 9. what the host wants to know
+    if (job.ttris) {
+        for (int k = t; k < n; k += SORT_THREADS) {
+            const uint32_t prim = job.leaf_prims[k];
+            const float4* p = reinterpret_cast<const float4*>(job.tris + prim);
+            float4 a = __ldg(p), b = __ldg(p + 1), cc = __ldg(p + 2);
+            a.w = __uint_as_float(prim);
+            b.w = 0.0f; cc.w = 0.0f;
+            job.ttris[(size_t)k * 3 + 0] = a;
+            job.ttris[(size_t)k * 3 + 1] = b;
+            job.ttris[(size_t)k * 3 + 2] = cc;
+        }
+    }
+    if (t < 8) job.result->counters[t] = c.counters[t];
+    if (t < 12) job.result->bounds[t] = s_bounds[t];
+    if (t < 8) {
+        const size_t root = (refine && c.counters[4] >= 2u) ? 2 * (size_t)n - 1 : 0;
+        job.result->cost[t] = c.cost[root * 8 + t];
+    }
 }
 
 // layout-independent checksum: every record (node / triangle) is hashed on its own (words flagged in skip_mask —
@@ -662,6 +906,62 @@ cudaError_t finish_pending_builds(BuilderContext& ctx) {
     }
     ctx.pending.clear();
     return e;
+}
+
+static_assert(BUILD_FUSED_MAX == SORT_TILE, "the fused small build sorts inside one CTA");
+
+cudaError_t build_small_batch(BuilderContext& ctx, const SmallBuildItem* items, int count, const BuildParams& params) {
+    cudaStream_t s = ctx.stream;
+    if (!ctx.h_results && cudaHostAlloc(&ctx.h_results, sizeof(BuildResultSlot) * BUILD_DEFER_SLOTS, cudaHostAllocDefault) != cudaSuccess) {
+        ctx.h_results = nullptr;
+        return cudaGetLastError();
+    }
+    for (int first = 0; first < count;) {
+        if ((int)ctx.pending.size() >= BUILD_DEFER_SLOTS) RFW_CK(finish_pending_builds(ctx));
+        const int slot0 = (int)ctx.pending.size();
+        const int chunk = std::min(count - first, BUILD_DEFER_SLOTS - slot0);
+        std::vector<SmallBuildJob> jobs((size_t)chunk);
+        std::vector<size_t> offs((size_t)chunk);
+        size_t total = 0;
+        for (int k = 0; k < chunk; k++) {
+            const SmallBuildItem& it = items[first + k];
+            if (it.n <= 0 || it.n > BUILD_FUSED_MAX) return cudaErrorInvalidValue;
+            SmallBuildJob& j = jobs[(size_t)k];
+            j.tris = it.tris; j.lo = it.lo; j.hi = it.hi; j.n = it.n;
+            j.refine = (params.treelet > 0 && it.n > params.treelet) ? 1 : 0;
+            SmallCarve c;
+            offs[(size_t)k] = total;
+            total += c.carve(nullptr, it.n, j.refine != 0, it.tris != nullptr);
+        }
+        char* base = (char*)ctx.scratch.reserve(total + 512);
+        if (!base) return cudaErrorMemoryAllocation;
+        SmallBuildJob* d_jobs = nullptr;
+        BuildResultSlot* d_results = nullptr;
+        RFW_CK(cudaMallocAsync(&d_jobs, (size_t)chunk * sizeof(SmallBuildJob), s));
+        RFW_CK(cudaMallocAsync(&d_results, (size_t)chunk * sizeof(BuildResultSlot), s));
+        for (int k = 0; k < chunk; k++) {
+            const SmallBuildItem& it = items[first + k];
+            SmallBuildJob& j = jobs[(size_t)k];
+            it.out->release();
+            RFW_CK(cudaMallocAsync(&it.out->nodes, (size_t)it.n * NODE_BYTES, s));
+            RFW_CK(cudaMallocAsync(&it.out->leaf_prims, (size_t)it.n * sizeof(uint32_t), s));
+            j.ttris = nullptr;
+            if (it.ttris) { RFW_CK(cudaMallocAsync(it.ttris, (size_t)it.n * 3 * sizeof(float4), s)); j.ttris = *it.ttris; }
+            j.scratch = base + offs[(size_t)k];
+            j.nodes = it.out->nodes; j.leaf_prims = it.out->leaf_prims;
+            j.result = d_results + k;
+            ctx.pending.push_back(PendingBuild{it.out, slot0 + k, it.n, j.refine != 0});
+        }
+        RFW_CK(cudaMemcpyAsync(d_jobs, jobs.data(), (size_t)chunk * sizeof(SmallBuildJob), cudaMemcpyHostToDevice, s));  // pageable source: staged before the call returns
+        k_build_small<<<chunk, SORT_THREADS, 0, s>>>(d_jobs, params);
+        ctx.launches++;
+        RFW_CK(cudaGetLastError());
+        RFW_CK(cudaMemcpyAsync(ctx.h_results + slot0, d_results, (size_t)chunk * sizeof(BuildResultSlot), cudaMemcpyDeviceToHost, s));
+        cudaFreeAsync(d_jobs, s); cudaFreeAsync(d_results, s);
+        first += chunk;
+        if (first < count) RFW_CK(finish_pending_builds(ctx));  // the next chunk re-uses the scratch arena and the slots
+    }
+    return cudaSuccess;
 }
 
 cudaError_t build_wide_bvh(BuilderContext& ctx, const float4* prim_lo, const float4* prim_hi, int n, const BuildParams& params, DeviceBvh& out, bool deferred) {

@@ -71,6 +71,20 @@ static constexpr int BUILD_DEFER_SLOTS = 1024;
 cudaError_t build_wide_bvh(BuilderContext& ctx, const float4* prim_lo, const float4* prim_hi, int n, const BuildParams& params, DeviceBvh& out, bool deferred = false);
 cudaError_t finish_pending_builds(BuilderContext& ctx);
 
+// Fused build of many small inputs in ONE launch (one CTA per item, n <= BUILD_FUSED_MAX each): a BLAS item gives `tris` (boxes, tree and the
+// leaf-ordered traversal triangles *ttris — allocated here, stream-ordered — come out of the same kernel), a build over given boxes (TLAS)
+// gives lo / hi and ttris = null.  Always deferred: `out`'s host-side fields are filled by finish_pending_builds(), its device pointers are
+// valid stream-ordered at once.  Same tree as build_wide_bvh (same bodies).
+static constexpr int BUILD_FUSED_MAX = 2048;
+struct SmallBuildItem {
+    const RfwRTTriangle* tris;
+    const float4 *lo, *hi;
+    int n;
+    DeviceBvh* out;
+    float4** ttris;
+};
+cudaError_t build_small_batch(BuilderContext& ctx, const SmallBuildItem* items, int count, const BuildParams& params);
+
 // triangle boxes of a 176-byte RTTriangle array (device pointers)
 cudaError_t triangle_boxes(BuilderContext& ctx, const RfwRTTriangle* tris, int n, float4* prim_lo, float4* prim_hi);
 // traversal triangles: out[3k..3k+2] = vertices of tris[leaf_prims[k]], v0.w = prim index bits

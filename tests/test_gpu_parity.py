@@ -186,6 +186,38 @@ def test_spatial_splits_keep_the_hits_and_cut_the_traversal(B, oracle_mod, torch
     assert again.build_stats()["checksum"] == bs1["checksum"]
 
 
+def test_fused_small_builds_give_the_same_trees(B, oracle_mod):
+    """Meshes (and a TLAS) of <= 2 048 boxes are built by ONE CTA each, all in one launch (builder.cu::k_build_small, option build_fused,
+    default on).  Same bodies as the general builder, so: same BVH checksum, bit-identical hits, far fewer launches.  Sizes straddle every
+    special case of the pipeline: 1, 2 and 3 triangles (no Karras / no refinement), the treelet size, one warp, the sort tile and one past it."""
+    sizes = [1, 2, 3, 8, 9, 31, 33, 257, 1000, 2047, 2048, 2049]
+    desc = scenes.SceneDesc()
+    rng = np.random.default_rng(5)
+    for k, n in enumerate(sizes):
+        desc.meshes[k] = scenes.soup(n, 0.15, seed=scenes.SEED_SCENE + 17 * k)
+        desc.instances[k] = scenes.to_column_major([scenes.trs(tuple(rng.uniform(-1.5, 1.5, 3)), rot_angle=float(rng.uniform(0, 3)), scale=float(rng.uniform(0.5, 1.5))) for _ in range(2)])
+    fused, cpu = make_pair(B, oracle_mod, desc)
+    general = B.B200Backend(0, 0)
+    general.set_option("build_fused", 0)
+    l0 = general.launch_count(); desc.apply(general); l_general = general.launch_count() - l0
+    again = B.B200Backend(0, 0)
+    l0 = again.launch_count(); desc.apply(again); l_fused = again.launch_count() - l0
+    sf, sg = fused.build_stats(), general.build_stats()
+    assert sf["checksum"] == sg["checksum"] == again.build_stats()["checksum"]
+    for key in ("blas_nodes", "tlas_nodes", "num_triangles", "num_instances"):
+        assert sf[key] == sg[key], key
+    assert l_fused < l_general // 4, (l_fused, l_general)
+    rays = scenes.random_rays(200000, lo=-2.5, hi=2.5)
+    hf, hg = fused.trace_closest(rays), general.trace_closest(rays)
+    assert hf.tobytes() == hg.tobytes()
+    assert (hf["inst"] >= 0).mean() > 0.05
+    parity.compare_hits(rays, hf, cpu.trace_closest(rays), parity.lookup_from_desc(desc), "fused-build")
+    # a rebuild of only some meshes through the fused path leaves the others alone and reproduces the tree
+    fused.set_3d_mesh(3, desc.meshes[3]); fused.set_3d_mesh(9, desc.meshes[9]); fused.synchronize()
+    assert fused.build_stats()["checksum"] == sf["checksum"]
+    assert fused.trace_closest(rays).tobytes() == hf.tobytes()
+
+
 def test_randomised_stress_against_brute_force_on_the_gpu(B, oracle_mod):
     """The randomised stress of the CPU tier (tests/test_hostemu.py: scales 1e-3 ... 1e3, far from the origin, flat / duplicate / sliver
     triangles, non-uniformly scaled instances, axis-parallel and on-surface rays) with the GPU library in the harness's place, against the
