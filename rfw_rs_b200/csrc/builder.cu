@@ -203,7 +203,6 @@ __device__ void sah_split_segment(int4 seg, int* __restrict__ items, int* __rest
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
     const int begin = seg.x, end = seg.y, top = seg.z;
-    const int n = A.n;
     if (end - begin > SAH_BIG_SEGMENT) {
         // a big segment is still a contiguous run of the Morton order (all its ancestors were split this way too)
         if (lane == 0) {
@@ -670,6 +669,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_build_small(const SmallBuildJo
     }
     if (t < 8) job.result->counters[t] = c.counters[t];
     if (t < 12) job.result->bounds[t] = s_bounds[t];
+    if (t < 4) job.result->pad[t] = 0u;  // (the whole record is copied to the host)
     if (t < 8) {
         const size_t root = (refine && c.counters[4] >= 2u) ? 2 * (size_t)n - 1 : 0;
         job.result->cost[t] = c.cost[root * 8 + t];
