@@ -479,8 +479,9 @@ RFWB200_API int rfwb200_render_stats(void* handle, RfwRenderStats* out);
  *               largest node / traversal-triangle array: HBM reads of the C2 kernel 1.75 -> 0.91 GB with 2, no speed-up)
  *               tri_test (0 watertight; 1 = the reference's Moller-Trumbore arithmetic, operation for operation: parity runs)
  *   builder:    sah_treelet, sah_treelet_tlas, sah_c_prim_milli, sah_pmax, build_streams (8: small BLAS builds in flight at once),
- *               build_threads (1: one host thread per builder stream), build_fused (1: meshes and TLASes of <= 2 048 boxes are built by
- *               one CTA each, all of a scene in one launch; 0 = the general builder for everything: same trees),
+ *               build_threads (1: one host thread per builder stream), build_fused (1: meshes, skinned instances and TLASes of <= 2 048 boxes are
+ *               built by one CTA each, all of a scene in one launch; 0 = the general builder for everything: same trees), build_fused_medium_min
+ *               (2: builds of 2 049 .. 8 192 triangles join the fused launch when at least this many are dirty — a crowd of animated characters),
  *               split_budget (0 = off; percent of extra triangle references for SPATIAL SPLITS — triangle pre-splitting ahead of the
  *               Morton sort, the reference's "Spatial BVH" (backends/gpu-rt/README.md:10); 30 is a good value for authored assets)
  *   wavefront:  max_depth, wave_paths, sample_count, stage_timing (1: RfwRenderStats.stage_ms is filled), wf_overlap (1: connect stage on a

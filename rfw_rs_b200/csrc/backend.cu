@@ -462,109 +462,33 @@ int Backend::synchronize() {
     BK_CUDA(device_scope.status, "cudaSetDevice");
     float blas_ms = 0.0f, tlas_ms = 0.0f;
     if (scene_dirty) {
-        // ---- BLAS for dirty meshes ------------------------------------------------------------------
+        // ---- BLAS builds: dirty meshes + skinned instances (deformed copy + its own BLAS, rebuilt when its skin, its mesh or the skin id changed) ----
         BK_CUDA(cudaEventRecord(ev0, stream), "event");
         const BuildParams blas_params{1.0f, sah_c_prim, sah_pmax, sah_treelet};
-        std::set<uint32_t> rebuilt_meshes;
-        // many small dirty meshes: deal them onto the side contexts (see backend.h); big meshes fill the GPU on their own
-        int n_small = 0;
-        // meshes of <= BUILD_FUSED_MAX triangles: all of them in ONE launch, one CTA per mesh (option "build_fused", default on)
-        auto fused_ok = [&](const MeshRec& m) { return build_fused && m.n > 0 && m.n <= (uint32_t)BUILD_FUSED_MAX && !(split_budget > 0 && m.n > (uint32_t)RFW_DIRECT_TRIS); };
-        for (const MeshRec& m : meshes) n_small += (m.present && m.dirty && m.n > 0 && m.n <= (uint32_t)BUILD_DEFER_MAX && !fused_ok(m)) ? 1 : 0;
-        const int n_side = (n_small >= 4 && build_streams > 1) ? std::min(build_streams, n_small) : 0;
-        while ((int)side_ctx.size() < n_side) {
-            BuilderContext* c = new BuilderContext();
-            c->sm_count = sm_count;
-            if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return cuda_fail(cudaGetLastError(), "build stream"); }
-            side_ctx.push_back(c);
-        }
-        if (n_side) BK_CUDA(cudaStreamSynchronize(stream), "sync");  // uploads and frees issued on the main stream precede the side streams' work
-        // one mesh's build, enqueued on `bc`'s stream (no host state beyond the mesh record and the context is touched: safe to run from a
-        // helper thread, one thread per context)
-        auto build_one = [&](MeshRec& m, BuilderContext& bc) -> cudaError_t {
-            cudaStream_t bs = bc.stream;
-            float4 *lo = nullptr, *hi = nullptr;
-            cudaError_t e = cudaMallocAsync(&lo, (size_t)m.n * sizeof(float4), bs);
-            if (e == cudaSuccess) e = cudaMallocAsync(&hi, (size_t)m.n * sizeof(float4), bs);
-            if (e == cudaSuccess) e = triangle_boxes(bc, m.d_tris, (int)m.n, lo, hi);
-            m.n_refs = m.n;
-            if (e == cudaSuccess && split_budget > 0 && m.n > (uint32_t)RFW_DIRECT_TRIS) {
-                // spatial splits (option "split_budget", percent of extra references): the BVH is built over clipped reference boxes,
-                // the leaf-ordered traversal triangles repeat a split triangle once per reference (tri_split.h)
-                SplitRefs refs;
-                e = split_triangle_refs(bc, m.d_tris, (int)m.n, lo, hi, (float)split_budget * 0.01f, refs);
-                if (e == cudaSuccess) e = build_wide_bvh(bc, refs.lo, refs.hi, refs.n_refs, blas_params, m.bvh, /*deferred=*/refs.n_refs <= BUILD_DEFER_MAX);
-                if (e == cudaSuccess) {
-                    m.n_refs = (uint32_t)refs.n_refs;
-                    e = cudaMallocAsync(&m.d_ttris, (size_t)m.n_refs * 3 * sizeof(float4), bs);
-                    if (e == cudaSuccess) e = gather_traversal_triangles_refs(bc, m.d_tris, m.bvh.leaf_prims, refs.prim, refs.n_refs, m.d_ttris);
-                }
-                if (refs.lo) cudaFreeAsync(refs.lo, bs);
-                if (refs.hi) cudaFreeAsync(refs.hi, bs);
-                if (refs.prim) cudaFreeAsync(refs.prim, bs);
-            } else {
-                if (e == cudaSuccess) e = build_wide_bvh(bc, lo, hi, (int)m.n, blas_params, m.bvh, /*deferred=*/true);  // small meshes: no host sync per mesh
-                if (e == cudaSuccess) e = cudaMallocAsync(&m.d_ttris, (size_t)m.n * 3 * sizeof(float4), bs);
-                if (e == cudaSuccess) e = gather_traversal_triangles(bc, m.d_tris, m.bvh.leaf_prims, (int)m.n, m.d_ttris);
-            }
-            if (lo) cudaFreeAsync(lo, bs);
-            if (hi) cudaFreeAsync(hi, bs);
-            return e;
+        // One build job: a dirty mesh, or one skinned instance (then the job starts with the skinning kernel writing d_tris).  Jobs only touch their
+        // own record and the builder context they run on, so a helper thread per context can enqueue them.
+        struct BlasJob {
+            RfwRTTriangle* d_tris; uint32_t n; DeviceBvh* bvh; float4** d_ttris; uint32_t* n_refs;
+            const RfwRTTriangle* skin_src; const RfwJointData* skin_data; const float* joints; uint32_t num_joints;  // skinned instances only
+            bool may_split;
         };
-        // dirty meshes: old structures freed here, small ones dealt round-robin onto the side contexts, the rest stay on the main context
-        std::vector<std::vector<MeshRec*>> side_work((size_t)n_side);
-        std::vector<MeshRec*> main_work;
-        std::vector<SmallBuildItem> fused_work;
-        int next_side = 0;
-        for (MeshRec& m : meshes) {
+        std::vector<BlasJob> jobs;
+        std::vector<bool> mesh_was_dirty(meshes.size(), false);
+        for (MeshRec& m : meshes) {  // dirty meshes: old structures freed here
             if (!m.present || !m.dirty) continue;
-            rebuilt_meshes.insert((uint32_t)(&m - meshes.data()));
+            mesh_was_dirty[(size_t)(&m - meshes.data())] = true;
             if (m.d_ttris) { cudaFree(m.d_ttris); m.d_ttris = nullptr; }
             m.bvh.release();
             m.dirty = false;
-            if (!m.n) continue;
-            if (fused_ok(m)) { m.n_refs = m.n; fused_work.push_back(SmallBuildItem{m.d_tris, nullptr, nullptr, (int)m.n, &m.bvh, &m.d_ttris}); continue; }
-            if (n_side && m.n <= (uint32_t)BUILD_DEFER_MAX) side_work[(size_t)((next_side++) % n_side)].push_back(&m);
-            else main_work.push_back(&m);
+            m.n_refs = m.n;
+            if (m.n) jobs.push_back(BlasJob{m.d_tris, m.n, &m.bvh, &m.d_ttris, &m.n_refs, nullptr, nullptr, nullptr, 0, true});
         }
-        // A small build is ~17 launches of tiny kernels: 170 meshes are ~3 000 launches, and ONE host thread enqueues them at ~4.7 us each
-        // (14 ms, whatever the number of streams).  With option build_threads (default on) every side context gets its own host thread.
-        if (!fused_work.empty()) BK_CUDA(build_small_batch(bctx, fused_work.data(), (int)fused_work.size(), blas_params), "BLAS build (fused)");
-        std::vector<cudaError_t> side_err((size_t)n_side, cudaSuccess);
-        auto run_side = [&](int k) {
-            cudaSetDevice(cfg.device);
-            for (MeshRec* m : side_work[(size_t)k]) {
-                const cudaError_t e = build_one(*m, *side_ctx[(size_t)k]);
-                if (e != cudaSuccess) { side_err[(size_t)k] = e; break; }
-            }
-        };
-        if (n_side && build_threads) {
-            std::vector<std::thread> workers;
-            for (int k = 0; k < n_side; k++) workers.emplace_back(run_side, k);
-            for (MeshRec* m : main_work) { const cudaError_t e = build_one(*m, bctx); if (e != cudaSuccess) { for (auto& w : workers) w.join(); return cuda_fail(e, "BLAS build"); } }
-            for (auto& w : workers) w.join();
-        } else {
-            for (int k = 0; k < n_side; k++) run_side(k);
-            for (MeshRec* m : main_work) { const cudaError_t e = build_one(*m, bctx); if (e != cudaSuccess) return cuda_fail(e, "BLAS build"); }
-        }
-        for (int k = 0; k < n_side; k++) if (side_err[(size_t)k] != cudaSuccess) return cuda_fail(side_err[(size_t)k], "BLAS build");
-        for (int k = 0; k < n_side; k++) {
-            BK_CUDA(finish_pending_builds(*side_ctx[k]), "BLAS build");
-            BK_CUDA(cudaStreamSynchronize(side_ctx[k]->stream), "BLAS build");
-        }
-        BK_CUDA(finish_pending_builds(bctx), "BLAS build");  // ONE sync for all deferred builds: node counts, bounds, SAH costs
-        BK_CUDA(cudaEventRecord(ev1, stream), "event");
-        BK_CUDA(cudaEventSynchronize(ev1), "BLAS build");
-        cudaEventElapsedTime(&blas_ms, ev0, ev1);
-
-        // ---- skinned instances: deform + BLAS per instance (rebuilt when its skin, its mesh or the skin id changed) ----
-        for (SkinnedInstance& si : skinned) si.fresh = false;
-        std::vector<bool> mesh_was_dirty(meshes.size(), false);
-        for (size_t i = 0; i < meshes.size(); i++) mesh_was_dirty[i] = rebuilt_meshes.count((uint32_t)i) != 0;
+        // skinned instances, pass 1: find or create the records (the vector may grow: no pointers into it are kept across this loop)
+        for (SkinnedInstance& si : skinned) { si.fresh = false; si.rebuild = false; }
         for (size_t mesh_id = 0; mesh_id < inst_lists.size(); mesh_id++) {
             const InstanceList& l = inst_lists[mesh_id];
             if (!l.present || l.skin_ids.empty() || mesh_id >= meshes.size()) continue;
-            MeshRec& m = meshes[mesh_id];
+            const MeshRec& m = meshes[mesh_id];
             if (!m.present || !m.n || !m.d_skin) continue;
             for (size_t i = 0; i < l.skin_ids.size(); i++) {
                 const int32_t sid = l.skin_ids[i];
@@ -575,20 +499,7 @@ int Backend::synchronize() {
                 if (!si) { skinned.emplace_back(); si = &skinned.back(); si->mesh = (uint32_t)mesh_id; si->index = (uint32_t)i; rebuild = true; }
                 if (si->skin != sid) { si->skin = sid; rebuild = true; }
                 si->fresh = true;
-                if (!rebuild && si->d_tris) continue;
-                release_skinned(*si);
-                BK_CUDA(cudaMalloc(&si->d_tris, (size_t)m.n * sizeof(RfwRTTriangle)), "skinned triangles");
-                k_skin_triangles<<<(m.n + 127) / 128, 128, 0, stream>>>(m.d_tris, m.d_skin, skins[sid].joints.ptr, skins[sid].num_joints, m.n, si->d_tris);
-                launch_count++;
-                float4 *lo = nullptr, *hi = nullptr;
-                BK_CUDA(cudaMallocAsync(&lo, (size_t)m.n * sizeof(float4), stream), "box alloc");
-                BK_CUDA(cudaMallocAsync(&hi, (size_t)m.n * sizeof(float4), stream), "box alloc");
-                cudaError_t e = triangle_boxes(bctx, si->d_tris, (int)m.n, lo, hi);
-                if (e == cudaSuccess) e = build_wide_bvh(bctx, lo, hi, (int)m.n, blas_params, si->bvh);
-                cudaFreeAsync(lo, stream); cudaFreeAsync(hi, stream);
-                if (e != cudaSuccess) return cuda_fail(e, "skinned BLAS build");
-                BK_CUDA(cudaMallocAsync(&si->d_ttris, (size_t)m.n * 3 * sizeof(float4), stream), "triangle alloc");
-                BK_CUDA(gather_traversal_triangles(bctx, si->d_tris, si->bvh.leaf_prims, (int)m.n, si->d_ttris), "gather triangles");
+                si->rebuild = rebuild || !si->d_tris;
             }
         }
         for (size_t k = 0; k < skinned.size();) {  // instances that lost their skin (or their mesh)
@@ -597,7 +508,116 @@ int Backend::synchronize() {
             release_skinned(skinned[k]);
             skinned.erase(skinned.begin() + (long)k);
         }
+        // pass 2 (the vector is stable now): one job per instance to rebuild.  The deformed-triangle buffer is kept from frame to frame; the old
+        // BLAS and traversal triangles go back to the stream-ordered pool after ONE device-wide sync (an animated scene re-skins every character
+        // every frame: per-instance cudaFree / cudaMalloc pairs and two host syncs per build were 0.9 ms per character)
+        bool skin_synced = false;
+        for (SkinnedInstance& si : skinned) {
+            if (!si.rebuild) continue;
+            const MeshRec& m = meshes[si.mesh];
+            if (!skin_synced) { BK_CUDA(cudaDeviceSynchronize(), "sync"); skin_synced = true; }  // nothing in flight reads what is freed below
+            if (si.d_tris && si.n_alloc != m.n) { cudaFree(si.d_tris); si.d_tris = nullptr; }
+            if (!si.d_tris) { BK_CUDA(cudaMalloc(&si.d_tris, (size_t)m.n * sizeof(RfwRTTriangle)), "skinned triangles"); si.n_alloc = m.n; }
+            if (si.d_ttris) { cudaFreeAsync(si.d_ttris, stream); si.d_ttris = nullptr; }
+            si.bvh.release_async(stream);
+            jobs.push_back(BlasJob{si.d_tris, m.n, &si.bvh, &si.d_ttris, nullptr, m.d_tris, m.d_skin, skins[(size_t)si.skin].joints.ptr, skins[(size_t)si.skin].num_joints, false});
+        }
         skins_dirty = false;
+
+        // scheduling: jobs of <= BUILD_FUSED_MAX triangles all go into ONE launch, one CTA per job (option "build_fused", default on); four or more
+        // other small jobs are dealt round-robin onto the side contexts (see backend.h); big meshes fill the GPU on their own, on the main context
+        auto wants_split = [&](const BlasJob& j) { return j.may_split && split_budget > 0 && j.n > (uint32_t)RFW_DIRECT_TRIS; };
+        // One CTA (256 threads) builds a one-tile job (<= 2 048 triangles) about as fast as the general builder does (both are latency chains), so those
+        // are always fused.  A medium job (up to BUILD_FUSED_MAX) takes its CTA (512 threads) ~1.2 ms where the general builder takes ~1 ms — but the CTAs
+        // of many jobs run side by side, while general builds queue behind the host's launch rate (64 animated characters of 4 672 triangles: 17.5 ms
+        // general on 8 streams, 2.2 ms fused; one character: 1.1 vs 1.4 ms): medium jobs are fused when at least `build_fused_medium_min` are dirty.
+        int n_medium = 0;
+        for (const BlasJob& j : jobs) n_medium += (j.n > (uint32_t)BUILD_FUSED_ONE_TILE && j.n <= (uint32_t)BUILD_FUSED_MAX && !wants_split(j)) ? 1 : 0;
+        const uint32_t fused_limit = n_medium >= build_fused_medium_min ? (uint32_t)BUILD_FUSED_MAX : (uint32_t)BUILD_FUSED_ONE_TILE;
+        auto fused_ok = [&](const BlasJob& j) { return build_fused && j.n <= fused_limit && !wants_split(j); };
+        int n_small = 0;
+        for (const BlasJob& j : jobs) n_small += (j.n <= (uint32_t)BUILD_DEFER_MAX && !fused_ok(j)) ? 1 : 0;
+        const int n_side = (n_small >= 4 && build_streams > 1) ? std::min(build_streams, n_small) : 0;
+        while ((int)side_ctx.size() < n_side) {
+            BuilderContext* c = new BuilderContext();
+            c->sm_count = sm_count;
+            if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return cuda_fail(cudaGetLastError(), "build stream"); }
+            side_ctx.push_back(c);
+        }
+        if (n_side) BK_CUDA(cudaStreamSynchronize(stream), "sync");  // uploads and frees issued on the main stream precede the side streams' work
+        auto skin_stage = [&](const BlasJob& j, BuilderContext& bc) {
+            if (!j.skin_src) return;
+            k_skin_triangles<<<(j.n + 127) / 128, 128, 0, bc.stream>>>(j.skin_src, j.skin_data, j.joints, j.num_joints, j.n, j.d_tris);
+            bc.launches++;
+        };
+        auto build_one = [&](const BlasJob& j, BuilderContext& bc) -> cudaError_t {
+            cudaStream_t bs = bc.stream;
+            skin_stage(j, bc);
+            float4 *lo = nullptr, *hi = nullptr;
+            cudaError_t e = cudaMallocAsync(&lo, (size_t)j.n * sizeof(float4), bs);
+            if (e == cudaSuccess) e = cudaMallocAsync(&hi, (size_t)j.n * sizeof(float4), bs);
+            if (e == cudaSuccess) e = triangle_boxes(bc, j.d_tris, (int)j.n, lo, hi);
+            if (e == cudaSuccess && wants_split(j)) {
+                // spatial splits (option "split_budget", percent of extra references): the BVH is built over clipped reference boxes,
+                // the leaf-ordered traversal triangles repeat a split triangle once per reference (tri_split.h)
+                SplitRefs refs;
+                e = split_triangle_refs(bc, j.d_tris, (int)j.n, lo, hi, (float)split_budget * 0.01f, refs);
+                if (e == cudaSuccess) e = build_wide_bvh(bc, refs.lo, refs.hi, refs.n_refs, blas_params, *j.bvh, /*deferred=*/refs.n_refs <= BUILD_DEFER_MAX);
+                if (e == cudaSuccess) {
+                    if (j.n_refs) *j.n_refs = (uint32_t)refs.n_refs;
+                    e = cudaMallocAsync(j.d_ttris, (size_t)refs.n_refs * 3 * sizeof(float4), bs);
+                    if (e == cudaSuccess) e = gather_traversal_triangles_refs(bc, j.d_tris, j.bvh->leaf_prims, refs.prim, refs.n_refs, *j.d_ttris);
+                }
+                if (refs.lo) cudaFreeAsync(refs.lo, bs);
+                if (refs.hi) cudaFreeAsync(refs.hi, bs);
+                if (refs.prim) cudaFreeAsync(refs.prim, bs);
+            } else {
+                if (e == cudaSuccess) e = build_wide_bvh(bc, lo, hi, (int)j.n, blas_params, *j.bvh, /*deferred=*/true);  // small builds: no host sync per build
+                if (e == cudaSuccess) e = cudaMallocAsync(j.d_ttris, (size_t)j.n * 3 * sizeof(float4), bs);
+                if (e == cudaSuccess) e = gather_traversal_triangles(bc, j.d_tris, j.bvh->leaf_prims, (int)j.n, *j.d_ttris);
+            }
+            if (lo) cudaFreeAsync(lo, bs);
+            if (hi) cudaFreeAsync(hi, bs);
+            return e;
+        };
+        std::vector<std::vector<const BlasJob*>> side_work((size_t)n_side);
+        std::vector<const BlasJob*> main_work;
+        std::vector<SmallBuildItem> fused_work;
+        int next_side = 0;
+        for (const BlasJob& j : jobs) {
+            if (fused_ok(j)) { skin_stage(j, bctx); fused_work.push_back(SmallBuildItem{j.d_tris, nullptr, nullptr, (int)j.n, j.bvh, j.d_ttris}); }
+            else if (n_side && j.n <= (uint32_t)BUILD_DEFER_MAX) side_work[(size_t)((next_side++) % n_side)].push_back(&j);
+            else main_work.push_back(&j);
+        }
+        if (!fused_work.empty()) BK_CUDA(build_small_batch(bctx, fused_work.data(), (int)fused_work.size(), blas_params), "BLAS build (fused)");
+        // A small build is ~17 launches of tiny kernels: 170 meshes are ~3 000 launches, and ONE host thread enqueues them at ~4.7 us each
+        // (14 ms, whatever the number of streams).  With option build_threads (default on) every side context gets its own host thread.
+        std::vector<cudaError_t> side_err((size_t)n_side, cudaSuccess);
+        auto run_side = [&](int k) {
+            cudaSetDevice(cfg.device);
+            for (const BlasJob* j : side_work[(size_t)k]) {
+                const cudaError_t e = build_one(*j, *side_ctx[(size_t)k]);
+                if (e != cudaSuccess) { side_err[(size_t)k] = e; break; }
+            }
+        };
+        if (n_side && build_threads) {
+            std::vector<std::thread> workers;
+            for (int k = 0; k < n_side; k++) workers.emplace_back(run_side, k);
+            for (const BlasJob* j : main_work) { const cudaError_t e = build_one(*j, bctx); if (e != cudaSuccess) { for (auto& w : workers) w.join(); return cuda_fail(e, "BLAS build"); } }
+            for (auto& w : workers) w.join();
+        } else {
+            for (int k = 0; k < n_side; k++) run_side(k);
+            for (const BlasJob* j : main_work) { const cudaError_t e = build_one(*j, bctx); if (e != cudaSuccess) return cuda_fail(e, "BLAS build"); }
+        }
+        for (int k = 0; k < n_side; k++) if (side_err[(size_t)k] != cudaSuccess) return cuda_fail(side_err[(size_t)k], "BLAS build");
+        for (int k = 0; k < n_side; k++) {
+            BK_CUDA(finish_pending_builds(*side_ctx[k]), "BLAS build");
+            BK_CUDA(cudaStreamSynchronize(side_ctx[k]->stream), "BLAS build");
+        }
+        BK_CUDA(finish_pending_builds(bctx), "BLAS build");  // ONE sync for all deferred builds: node counts, bounds, SAH costs
+        BK_CUDA(cudaEventRecord(ev1, stream), "event");
+        BK_CUDA(cudaEventSynchronize(ev1), "BLAS build");
+        cudaEventElapsedTime(&blas_ms, ev0, ev1);
 
         // ---- instances + TLAS (rebuilt on every synchronize, as the reference does: lib.rs:1576-1581) ----
         BK_CUDA(cudaEventRecord(ev0, stream), "event");
@@ -1663,6 +1683,7 @@ int Backend::set_option(const char* key, int64_t value) {
     else if (k == "chunk_rays") chunk_rays = (uint64_t)std::max<int64_t>(1024, value);
     else if (k == "max_depth") cfg.max_depth = (uint32_t)value;
     else if (k == "build_fused") build_fused = value != 0;  // meshes / TLASes of <= 2 048 boxes built by one CTA each, all in one launch (1, default) or by the general builder (0)
+    else if (k == "build_fused_medium_min") build_fused_medium_min = (int)std::max<int64_t>(0, value);  // jobs of 2 049 .. 8 192 triangles are fused when at least this many are dirty
     else if (k == "build_threads") build_threads = value != 0;  // one host thread per side builder context (1, default) or all launches from the calling thread (0)
     else if (k == "build_streams") build_streams = (int)std::min<int64_t>(64, std::max<int64_t>(1, value));
     else if (k == "sah_treelet_tlas") { sah_treelet_tlas = (int)value; scene_dirty = true; synchronized = false; }

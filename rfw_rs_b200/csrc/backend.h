@@ -42,6 +42,8 @@ struct SkinnedInstance {
     uint32_t mesh = 0, index = 0;     // instance = (mesh id, index in the mesh's list)
     int32_t skin = -1;
     bool fresh = false;               // rebuilt (or confirmed) during the current synchronize()
+    bool rebuild = false;             // to be re-skinned and rebuilt by the current synchronize()
+    uint32_t n_alloc = 0;             // triangles d_tris was allocated for (kept from frame to frame)
     RfwRTTriangle* d_tris = nullptr;
     float4* d_ttris = nullptr;
     DeviceBvh bvh;
@@ -153,6 +155,7 @@ private:
     std::vector<BuilderContext*> side_ctx;
     int build_streams = 8;
     bool build_fused = true;    // option "build_fused": meshes (and a TLAS) of <= BUILD_FUSED_MAX boxes are built by ONE CTA each, all in one launch (builder.cu::k_build_small)
+    int build_fused_medium_min = 2;  // option: jobs of BUILD_FUSED_ONE_TILE < n <= BUILD_FUSED_MAX triangles join the fused launch when at least this many are dirty
     bool build_threads = true;  // option "build_threads": the side contexts' launches are enqueued by one host thread each
     TraceConfig tcfg;
     RaySortScratch ray_sort;          // ray binning for scenes beyond the L2 (trace.h::trace_sorted)

@@ -10,6 +10,7 @@
 //   -> top-down collapse into 80-byte 8-wide nodes -> leaf-ordered traversal triangles
 #include <cooperative_groups.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -349,7 +350,7 @@ struct CtaScope {
     __device__ uint32_t tid() const { return threadIdx.x; }
     __device__ uint32_t n_threads() const { return blockDim.x; }
     __device__ bool leader() const { return threadIdx.x == 0; }
-    __device__ void sync() { __threadfence(); __syncthreads(); }
+    __device__ void sync() { __syncthreads(); }  // (orders the CTA's global accesses too)
 };
 
 // all levels of the top-down SAH build over the treelets; `bins`: one SahBins per warp of the CTA (shared memory)
@@ -454,7 +455,7 @@ __global__ void __launch_bounds__(TB) k_gather_tris(const RfwRTTriangle* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// fused build of small inputs: ONE CTA runs the whole pipeline of one mesh (n <= SORT_TILE boxes) — boxes, bounds, Morton, sort, Karras,
+// fused build of small inputs: ONE CTA runs the whole pipeline of one mesh (n <= BUILD_FUSED_MAX boxes) — boxes, bounds, Morton, sort, Karras,
 // fit + cost DP, SAH refinement of the top tree, collapse, traversal triangles — with __syncthreads() where the big build has kernel
 // boundaries or grid syncs; one launch builds every small mesh of a scene (grid = number of meshes).  The bodies are the big build's own
 // (bvh_build.h, sort_small.cuh, sah_top_loop / collapse_loop above), so a mesh gets the same tree either way.
@@ -507,24 +508,36 @@ struct SmallBuildJob {
     uint32_t* leaf_prims;       // [n]
     float4* ttris;              // [3n] traversal triangles (BLAS) or null
     BuildResultSlot* result;    // device
+    unsigned long long* trace;  // debug (RFWB200_BUILD_TRACE=1): globaltimer at the phase boundaries of this job, else null
 };
+__device__ __forceinline__ void small_trace(const SmallBuildJob& job, int slot) {
+    if (job.trace && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        job.trace[slot] = t;
+    }
+}
 
-__global__ void __launch_bounds__(SORT_THREADS) k_build_small(const SmallBuildJob* __restrict__ jobs, BuildParams P) {
+// THREADS: 256 for one-tile jobs (n <= 2 048), 512 for the medium ones — every phase of a build inside ONE CTA is a latency chain (a 4 672-triangle
+// mesh: 2.0 ms with 256 threads), so the bigger jobs get the register file of a whole SM
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_build_small(const SmallBuildJob* __restrict__ jobs, BuildParams P) {
     const SmallBuildJob job = jobs[blockIdx.x];
     const int n = job.n, t = threadIdx.x;
     const bool refine = job.refine != 0;
     SmallCarve c;
     c.carve(job.scratch, n, refine, job.tris != nullptr);
-    __shared__ SahBins bins[SORT_WARPS];
-    __shared__ float part[SORT_WARPS][12];
+    __shared__ SahBins bins[(THREADS / 32)];
+    __shared__ float part[(THREADS / 32)][12];
     __shared__ uint32_t s_bounds[12];
-    __shared__ uint32_t s_scan[SORT_WARPS];
+    __shared__ uint32_t s_scan[(THREADS / 32)];
     CtaScope sc;
 
+    small_trace(job, 0);
     // 0. clear; 1. boxes + bounds
     const float4 *plo = job.lo, *phi = job.hi;
     if (job.tris) {
-        for (int i = t; i < n; i += SORT_THREADS) {
+        for (int i = t; i < n; i += THREADS) {
             const float4* p = reinterpret_cast<const float4*>(job.tris + i);
             const float4 a = __ldg(p), b = __ldg(p + 1), cc = __ldg(p + 2);
             c.prim_lo[i] = make_float4(fminf(a.x, fminf(b.x, cc.x)), fminf(a.y, fminf(b.y, cc.y)), fminf(a.z, fminf(b.z, cc.z)), 0.0f);
@@ -535,16 +548,16 @@ __global__ void __launch_bounds__(SORT_THREADS) k_build_small(const SmallBuildJo
     if (t < 16) c.counters[t] = 0;
     {
         const size_t ni = (n > 1 ? (size_t)n - 1 : 1) + (refine ? (size_t)n : 0);
-        for (size_t i = t; i < ni; i += SORT_THREADS) c.flags[i] = 0;
-        if (refine) for (int i = t; i < n; i += SORT_THREADS) c.tre_flag[i] = 0u;
-        for (size_t i = t; i < (size_t)n * NODE_F4; i += SORT_THREADS) job.nodes[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        for (size_t i = t; i < ni; i += THREADS) c.flags[i] = 0;
+        if (refine) for (int i = t; i < n; i += THREADS) c.tre_flag[i] = 0u;
+        for (size_t i = t; i < (size_t)n * NODE_F4; i += THREADS) job.nodes[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     sc.sync();
     {
         float v[12];
 #pragma unroll
         for (int k = 0; k < 12; k++) v[k] = ((k % 6) < 3) ? 3.0e38f : -3.0e38f;
-        for (int i = t; i < n; i += SORT_THREADS) {
+        for (int i = t; i < n; i += THREADS) {
             const float4 l = plo[i], h = phi[i];
             const float cx = (l.x + h.x) * 0.5f, cy = (l.y + h.y) * 0.5f, cz = (l.z + h.z) * 0.5f;
             v[0] = fminf(v[0], cx); v[1] = fminf(v[1], cy); v[2] = fminf(v[2], cz);
@@ -569,35 +582,40 @@ __global__ void __launch_bounds__(SORT_THREADS) k_build_small(const SmallBuildJo
         if (t < 12) {
             const bool is_min = (t % 6) < 3;
             float r = part[0][t];
-            for (int w = 1; w < SORT_WARPS; w++) r = is_min ? fminf(r, part[w][t]) : fmaxf(r, part[w][t]);
+            for (int w = 1; w < (THREADS / 32); w++) r = is_min ? fminf(r, part[w][t]) : fmaxf(r, part[w][t]);
             s_bounds[t] = enc_f(r);
         }
         __syncthreads();
     }
+    small_trace(job, 1);
     // 2. Morton keys
     {
         const float3 cmin = f3(dec_f(s_bounds[0]), dec_f(s_bounds[1]), dec_f(s_bounds[2]));
         const float3 cmax = f3(dec_f(s_bounds[3]), dec_f(s_bounds[4]), dec_f(s_bounds[5]));
         const float3 e = cmax - cmin;
         const float3 cscale = f3(e.x > 0.0f ? 2097152.0f / e.x : 0.0f, e.y > 0.0f ? 2097152.0f / e.y : 0.0f, e.z > 0.0f ? 2097152.0f / e.z : 0.0f);
-        for (int i = t; i < n; i += SORT_THREADS) morton_body(i, plo, phi, cmin, cscale, c.keys, c.vals);
+        for (int i = t; i < n; i += THREADS) morton_body(i, plo, phi, cmin, cscale, c.keys, c.vals);
     }
     sc.sync();
+    small_trace(job, 2);
     // 3. sort (8 passes: the result is back in keys / vals)
-    if (n > 1) sort_small_body(c.keys, c.vals, c.keys_tmp, c.vals_tmp, n, 0, 64);
+    if (n > 1) sort_tiles_body<THREADS / 32, (BUILD_FUSED_MAX + THREADS * SORT_ITEMS - 1) / (THREADS * SORT_ITEMS)>(c.keys, c.vals, c.keys_tmp, c.vals_tmp, n, 0, 64);
     sc.sync();
+    small_trace(job, 3);
     BuildArrays A;
     A.n = n; A.prim_lo = plo; A.prim_hi = phi; A.keys = c.keys; A.order = c.vals;
     A.parent = c.parent; A.children = c.children; A.range = c.range; A.node_lo = c.node_lo; A.node_hi = c.node_hi;
     A.cost = c.cost; A.decision = c.decision; A.flags = c.flags;
     // 4. Karras tree, 5. fit + cost DP
-    for (int i = t; i < n - 1; i += SORT_THREADS) karras_body(i, n, c.keys, c.parent, c.children, c.range);
+    for (int i = t; i < n - 1; i += THREADS) karras_body(i, n, c.keys, c.parent, c.children, c.range);
     sc.sync();
-    for (int k = t; k < n; k += SORT_THREADS) fit_cost_body(k, A, P);
+    small_trace(job, 4);
+    for (int k = t; k < n; k += THREADS) fit_cost_body<true>(k, A, P);
     sc.sync();
+    small_trace(job, 5);
     // 6. binned-SAH refinement above the treelets
     if (refine) {
-        for (int node = t; node < 2 * n - 1; node += SORT_THREADS) {
+        for (int node = t; node < 2 * n - 1; node += THREADS) {
             const int cnt = node_prim_count(node, A);
             if (cnt > P.treelet) continue;
             const int par = A.parent[node];
@@ -607,40 +625,48 @@ __global__ void __launch_bounds__(SORT_THREADS) k_build_small(const SmallBuildJo
             c.tre_node[first] = node;
         }
         sc.sync();
-        {   // exclusive scan of the flags: SORT_ITEMS consecutive positions per thread
-            uint32_t f[SORT_ITEMS], sum = 0;
+        {   // exclusive scan of the flags, SORT_TILE positions at a time (SORT_ITEMS consecutive ones per thread) with a running carry
+            uint32_t carry = 0;
+            for (int base = 0; base < n; base += THREADS * SORT_ITEMS) {
+                uint32_t f[SORT_ITEMS], sum = 0;
 #pragma unroll
-            for (int k = 0; k < SORT_ITEMS; k++) { const int p = t * SORT_ITEMS + k; f[k] = p < n ? c.tre_flag[p] : 0u; sum += f[k]; }
-            uint32_t x = sum;
+                for (int k = 0; k < SORT_ITEMS; k++) { const int p = base + t * SORT_ITEMS + k; f[k] = p < n ? c.tre_flag[p] : 0u; sum += f[k]; }
+                uint32_t x = sum;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULLMASK, x, o); if ((t & 31) >= o) x += y; }
-            if ((t & 31) == 31) s_scan[t >> 5] = x;
-            __syncthreads();
-            uint32_t run = x - sum;
-            for (int w = 0; w < (t >> 5); w++) run += s_scan[w];
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULLMASK, x, o); if ((t & 31) >= o) x += y; }
+                if ((t & 31) == 31) s_scan[t >> 5] = x;
+                __syncthreads();
+                uint32_t run = carry + x - sum, total = 0;
 #pragma unroll
-            for (int k = 0; k < SORT_ITEMS; k++) {
-                const int p = t * SORT_ITEMS + k;
-                if (p < n) {
-                    if (f[k]) c.items[run] = c.tre_node[p];
-                    if (p == n - 1) c.counters[4] = run + f[k];  // number of treelets
+                for (int w = 0; w < (THREADS / 32); w++) { if (w < (t >> 5)) run += s_scan[w]; total += s_scan[w]; }
+#pragma unroll
+                for (int k = 0; k < SORT_ITEMS; k++) {
+                    const int p = base + t * SORT_ITEMS + k;
+                    if (p < n) {
+                        if (f[k]) c.items[run] = c.tre_node[p];
+                        if (p == n - 1) c.counters[4] = run + f[k];  // number of treelets
+                    }
+                    run += f[k];
                 }
-                run += f[k];
+                carry += total;
+                __syncthreads();  // s_scan is re-used by the next chunk
             }
         }
         sc.sync();
+    small_trace(job, 6);
         sah_top_loop(sc, A, c.items, c.items_tmp, c.seg0, c.seg1, c.counters, bins);
         sc.sync();
+        small_trace(job, 7);
         {
             const uint32_t m = c.counters[4];
             if (m >= 2) {
-                for (uint32_t k = t; k < m; k += SORT_THREADS) {
+                for (uint32_t k = t; k < m; k += THREADS) {
                     int cur = A.parent[c.items[k]];
                     while (cur >= 0) {
-                        __threadfence();
+                        __threadfence_block();
                         const int old = atomicAdd(&A.flags[inner_index(cur, n)], 1);
                         if (old == 0) break;
-                        __threadfence();
+                        __threadfence_block();
                         fit_cost_node(cur, A, P);
                         cur = A.parent[cur];
                     }
@@ -649,14 +675,16 @@ __global__ void __launch_bounds__(SORT_THREADS) k_build_small(const SmallBuildJo
         }
         sc.sync();
     }
+    small_trace(job, 8);
     // 7. collapse
     CollapseOut O;
     O.nodes = job.nodes; O.leaf_prims = job.leaf_prims; O.node_counter = c.counters + 0; O.prim_counter = c.counters + 1;
     collapse_loop(sc, A, O, c.q0, c.q1, c.counters);
     sc.sync();
+    small_trace(job, 9);
     // 8. traversal triangles in leaf order, 9. what the host wants to know
     if (job.ttris) {
-        for (int k = t; k < n; k += SORT_THREADS) {
+        for (int k = t; k < n; k += THREADS) {
             const uint32_t prim = job.leaf_prims[k];
             const float4* p = reinterpret_cast<const float4*>(job.tris + prim);
             float4 a = __ldg(p), b = __ldg(p + 1), cc = __ldg(p + 2);
@@ -667,6 +695,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_build_small(const SmallBuildJo
             job.ttris[(size_t)k * 3 + 2] = cc;
         }
     }
+    small_trace(job, 10);
     if (t < 8) job.result->counters[t] = c.counters[t];
     if (t < 12) job.result->bounds[t] = s_bounds[t];
     if (t < 4) job.result->pad[t] = 0u;  // (the whole record is copied to the host)
@@ -700,6 +729,12 @@ __global__ void __launch_bounds__(TB) k_checksum(const uint32_t* __restrict__ wo
 void DeviceBvh::release() {
     if (nodes) cudaFree(nodes);
     if (leaf_prims) cudaFree(leaf_prims);
+    nodes = nullptr; leaf_prims = nullptr; num_nodes = 0; num_prims = 0;
+}
+
+void DeviceBvh::release_async(cudaStream_t s) {
+    if (nodes) cudaFreeAsync(nodes, s);
+    if (leaf_prims) cudaFreeAsync(leaf_prims, s);
     nodes = nullptr; leaf_prims = nullptr; num_nodes = 0; num_prims = 0;
 }
 
@@ -878,6 +913,7 @@ __global__ void k_pick_root_cost(const float* __restrict__ cost, const uint32_t*
 
 BuilderContext::~BuilderContext() {
     if (h_results) cudaFreeHost(h_results);
+    if (aux_stream) { cudaStreamDestroy(aux_stream); cudaEventDestroy(aux_fork); cudaEventDestroy(aux_join); }
 }
 
 
@@ -908,7 +944,7 @@ cudaError_t finish_pending_builds(BuilderContext& ctx) {
     return e;
 }
 
-static_assert(BUILD_FUSED_MAX == SORT_TILE, "the fused small build sorts inside one CTA");
+static_assert(BUILD_FUSED_MAX % SORT_TILE == 0, "the fused small build sorts whole tiles inside one CTA");
 
 cudaError_t build_small_batch(BuilderContext& ctx, const SmallBuildItem* items, int count, const BuildParams& params) {
     cudaStream_t s = ctx.stream;
@@ -922,9 +958,14 @@ cudaError_t build_small_batch(BuilderContext& ctx, const SmallBuildItem* items, 
         const int chunk = std::min(count - first, BUILD_DEFER_SLOTS - slot0);
         std::vector<SmallBuildJob> jobs((size_t)chunk);
         std::vector<size_t> offs((size_t)chunk);
+        std::vector<int> order;  // job k of the chunk = item order[k]: the one-tile items first, the medium ones behind them
+        order.reserve((size_t)chunk);
+        for (int k = 0; k < chunk; k++) if (items[first + k].n <= BUILD_FUSED_ONE_TILE) order.push_back(first + k);
+        const int n_one_tile = (int)order.size();
+        for (int k = 0; k < chunk; k++) if (items[first + k].n > BUILD_FUSED_ONE_TILE) order.push_back(first + k);
         size_t total = 0;
         for (int k = 0; k < chunk; k++) {
-            const SmallBuildItem& it = items[first + k];
+            const SmallBuildItem& it = items[order[(size_t)k]];
             if (it.n <= 0 || it.n > BUILD_FUSED_MAX) return cudaErrorInvalidValue;
             SmallBuildJob& j = jobs[(size_t)k];
             j.tris = it.tris; j.lo = it.lo; j.hi = it.hi; j.n = it.n;
@@ -937,10 +978,13 @@ cudaError_t build_small_batch(BuilderContext& ctx, const SmallBuildItem* items, 
         if (!base) return cudaErrorMemoryAllocation;
         SmallBuildJob* d_jobs = nullptr;
         BuildResultSlot* d_results = nullptr;
+        static const bool trace_on = getenv("RFWB200_BUILD_TRACE") != nullptr;
+        unsigned long long* d_trace = nullptr;
+        if (trace_on) { RFW_CK(cudaMallocAsync(&d_trace, (size_t)chunk * 16 * sizeof(unsigned long long), s)); RFW_CK(cudaMemsetAsync(d_trace, 0, (size_t)chunk * 16 * sizeof(unsigned long long), s)); }
         RFW_CK(cudaMallocAsync(&d_jobs, (size_t)chunk * sizeof(SmallBuildJob), s));
         RFW_CK(cudaMallocAsync(&d_results, (size_t)chunk * sizeof(BuildResultSlot), s));
         for (int k = 0; k < chunk; k++) {
-            const SmallBuildItem& it = items[first + k];
+            const SmallBuildItem& it = items[order[(size_t)k]];
             SmallBuildJob& j = jobs[(size_t)k];
             it.out->release();
             RFW_CK(cudaMallocAsync(&it.out->nodes, (size_t)it.n * NODE_BYTES, s));
@@ -950,13 +994,42 @@ cudaError_t build_small_batch(BuilderContext& ctx, const SmallBuildItem* items, 
             j.scratch = base + offs[(size_t)k];
             j.nodes = it.out->nodes; j.leaf_prims = it.out->leaf_prims;
             j.result = d_results + k;
+            j.trace = d_trace ? d_trace + (size_t)k * 16 : nullptr;
             ctx.pending.push_back(PendingBuild{it.out, slot0 + k, it.n, j.refine != 0});
         }
         RFW_CK(cudaMemcpyAsync(d_jobs, jobs.data(), (size_t)chunk * sizeof(SmallBuildJob), cudaMemcpyHostToDevice, s));  // pageable source: staged before the call returns
-        k_build_small<<<chunk, SORT_THREADS, 0, s>>>(d_jobs, params);
-        ctx.launches++;
+        // one-tile jobs first (sorted above), the medium ones behind them: two launches of the same kernel at 256 / 512 threads
+        // (side by side: the medium launch runs on the context's auxiliary stream, forked from and joined to the build stream by events)
+        const bool fork = n_one_tile > 0 && chunk > n_one_tile;
+        if (fork) {
+            if (!ctx.aux_stream) {
+                RFW_CK(cudaStreamCreateWithFlags(&ctx.aux_stream, cudaStreamNonBlocking));
+                RFW_CK(cudaEventCreateWithFlags(&ctx.aux_fork, cudaEventDisableTiming));
+                RFW_CK(cudaEventCreateWithFlags(&ctx.aux_join, cudaEventDisableTiming));
+            }
+            RFW_CK(cudaEventRecord(ctx.aux_fork, s));
+            RFW_CK(cudaStreamWaitEvent(ctx.aux_stream, ctx.aux_fork, 0));
+        }
+        if (chunk > n_one_tile) { k_build_small<512><<<chunk - n_one_tile, 512, 0, fork ? ctx.aux_stream : s>>>(d_jobs + n_one_tile, params); ctx.launches++; }
+        if (n_one_tile > 0) { k_build_small<256><<<n_one_tile, 256, 0, s>>>(d_jobs, params); ctx.launches++; }
+        if (fork) {
+            RFW_CK(cudaEventRecord(ctx.aux_join, ctx.aux_stream));
+            RFW_CK(cudaStreamWaitEvent(s, ctx.aux_join, 0));
+        }
         RFW_CK(cudaGetLastError());
         RFW_CK(cudaMemcpyAsync(ctx.h_results + slot0, d_results, (size_t)chunk * sizeof(BuildResultSlot), cudaMemcpyDeviceToHost, s));
+        if (d_trace) {  // debug: phase durations of the largest job of the chunk
+            std::vector<unsigned long long> tr((size_t)chunk * 16);
+            RFW_CK(cudaMemcpyAsync(tr.data(), d_trace, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+            RFW_CK(cudaStreamSynchronize(s));
+            int big = 0;
+            for (int k = 1; k < chunk; k++) if (jobs[(size_t)k].n > jobs[(size_t)big].n) big = k;
+            static const char* names[10] = {"boxes+bounds", "morton", "sort", "karras", "fit+cost", "treelets", "sah top", "fit top", "collapse", "tris"};
+            fprintf(stderr, "rfwb200 build trace: %d jobs, largest n = %d:", chunk, jobs[(size_t)big].n);
+            for (int p = 0; p < 10; p++) fprintf(stderr, " %s %.1f us;", names[p], (double)(tr[(size_t)big * 16 + p + 1] - tr[(size_t)big * 16 + p]) * 1e-3);
+            fprintf(stderr, " total %.1f us\n", (double)(tr[(size_t)big * 16 + 10] - tr[(size_t)big * 16]) * 1e-3);
+            cudaFreeAsync(d_trace, s);
+        }
         cudaFreeAsync(d_jobs, s); cudaFreeAsync(d_results, s);
         first += chunk;
         if (first < count) RFW_CK(finish_pending_builds(ctx));  // the next chunk re-uses the scratch arena and the slots

@@ -26,6 +26,7 @@ struct DeviceBvh {
     float sah = 0.0f;
     float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};  // bounds of all primitive boxes
     void release();
+    void release_async(cudaStream_t s);  // back to the stream-ordered pool, no device-wide sync (the buffers always come from cudaMallocAsync)
 };
 
 // Scratch arena reused across builds (grown on demand, never shrunk).
@@ -56,6 +57,8 @@ struct BuilderContext {
     int sm_count = 0;
     BuildResultSlot* h_results = nullptr;  // pinned, DEFER_SLOTS entries
     std::vector<PendingBuild> pending;
+    cudaStream_t aux_stream = nullptr;     // the medium launch of a fused batch runs here, beside the one-tile launch on `stream` (created on first use)
+    cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
     ~BuilderContext();
 };
 
@@ -71,11 +74,12 @@ static constexpr int BUILD_DEFER_SLOTS = 1024;
 cudaError_t build_wide_bvh(BuilderContext& ctx, const float4* prim_lo, const float4* prim_hi, int n, const BuildParams& params, DeviceBvh& out, bool deferred = false);
 cudaError_t finish_pending_builds(BuilderContext& ctx);
 
-// Fused build of many small inputs in ONE launch (one CTA per item, n <= BUILD_FUSED_MAX each): a BLAS item gives `tris` (boxes, tree and the
+// Fused build of many small inputs in ONE launch (one CTA per item, n <= BUILD_FUSED_MAX each; the caller decides which items are worth it): a BLAS item gives `tris` (boxes, tree and the
 // leaf-ordered traversal triangles *ttris — allocated here, stream-ordered — come out of the same kernel), a build over given boxes (TLAS)
 // gives lo / hi and ttris = null.  Always deferred: `out`'s host-side fields are filled by finish_pending_builds(), its device pointers are
 // valid stream-ordered at once.  Same tree as build_wide_bvh (same bodies).
-static constexpr int BUILD_FUSED_MAX = 2048;
+static constexpr int BUILD_FUSED_MAX = 8192;  // 4 tiles of the in-CTA radix sort (sort_small.cuh)
+static constexpr int BUILD_FUSED_ONE_TILE = 2048;
 struct SmallBuildItem {
     const RfwRTTriangle* tris;
     const float4 *lo, *hi;

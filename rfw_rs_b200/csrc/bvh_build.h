@@ -161,6 +161,7 @@ RFW_HD void fit_cost_node(int node, const BuildArrays& A, const BuildParams& P) 
 }
 
 // one thread per sorted leaf k: write the leaf, then climb; the second thread to arrive at a node computes it
+template <bool CTA_SCOPE = false>
 RFW_HD void fit_cost_body(int k, const BuildArrays& A, const BuildParams& P) {
     const int n = A.n;
     const int leaf = n - 1 + k;
@@ -174,10 +175,10 @@ RFW_HD void fit_cost_body(int k, const BuildArrays& A, const BuildParams& P) {
     if (n == 1) return;
     int cur = A.parent[leaf];
     while (cur >= 0) {
-        thread_fence();
+        thread_fence_scope<CTA_SCOPE>();
         const int old = atomic_add(&A.flags[inner_index(cur, n)], 1);
         if (old == 0) return;  // first arrival: the sibling subtree is not finished yet
-        thread_fence();
+        thread_fence_scope<CTA_SCOPE>();
         fit_cost_node(cur, A, P);
         cur = A.parent[cur];
     }

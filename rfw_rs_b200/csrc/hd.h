@@ -125,6 +125,14 @@ RFW_HD void thread_fence() {
     __threadfence();
 #endif
 }
+// (when every thread that takes part runs in ONE CTA — the fused small build — a block-scope fence orders the same accesses at a fraction of the cost)
+template <bool BLOCK_SCOPE>
+RFW_HD void thread_fence_scope() {
+#if defined(__CUDA_ARCH__)
+    if (BLOCK_SCOPE) __threadfence_block();
+    else __threadfence();
+#endif
+}
 template <typename T>
 RFW_HD T ldg(const T* p) {
 #if defined(__CUDA_ARCH__)

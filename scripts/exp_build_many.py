@@ -4,7 +4,10 @@ import numpy as np
 from rfw_rs_b200 import backend, gltf
 asset = gltf.load_npz(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "pica.npz"))
 desc = gltf.per_mesh(asset)
-be = backend.B200Backend(); be.set_option("build_fused", int(os.environ.get("BUILD_FUSED", 1))); desc.apply(be)
+be = backend.B200Backend(); be.set_option("build_fused", int(os.environ.get("BUILD_FUSED", 1)))
+for kv in os.environ.get("OPTS", "").split(","):
+    if "=" in kv: be.set_option(kv.split("=")[0], int(kv.split("=")[1]))
+desc.apply(be)
 print("cold", be.build_stats()["blas_build_ms"], "ms; meshes", be.build_stats()["num_meshes"], "launches", be.launch_count())
 for k in range(8):
     be.set_option("build_streams", 1 if k < 4 else int(os.environ.get("BUILD_STREAMS", 8)))  # first four: everything on the main stream

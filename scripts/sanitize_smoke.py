@@ -20,9 +20,9 @@ from rfw_rs_b200 import scenes as _sc
 many = _sc.SceneDesc(); many.materials = _sc.material()
 for m in range(12):
     many.meshes[m] = _sc.soup(40 + 7 * m, 0.2, seed=100 + m); many.instances[m] = _sc.to_column_major([_sc.trs((m % 4 - 1.5, 0, m // 4 - 1.0))])
-for m, n in enumerate((1, 2, 9, 2048)):  # the corner sizes of the fused small build (k_build_small: one CTA per mesh, one launch for all of them)
+for m, n in enumerate((1, 2, 9, 2048, 2049, 5000, 8192)):  # the corner sizes of the fused small build (k_build_small: one CTA per mesh, one launch for all of them)
     many.meshes[12 + m] = _sc.soup(n, 0.2, seed=300 + m); many.instances[12 + m] = _sc.to_column_major([_sc.trs((m - 1.5, 1.0, 0.0))])
-b4 = backend.B200Backend(); many.apply(b4); r4 = _sc.random_rays(2000, lo=-2.0, hi=2.0); r4["origin"][::7, 0] = np.nan; h4 = b4.trace_closest(r4); b4.trace_any(r4)
+b4 = backend.B200Backend(); b4.set_option("build_fused_medium_min", 1); many.apply(b4); r4 = _sc.random_rays(2000, lo=-2.0, hi=2.0); r4["origin"][::7, 0] = np.nan; h4 = b4.trace_closest(r4); b4.trace_any(r4)
 b4g = backend.B200Backend(); b4g.set_option("build_fused", 0); many.apply(b4g)  # the general builder on the side streams, same trees
 assert b4g.trace_closest(r4).tobytes() == h4.tobytes() and b4g.build_stats()["checksum"] == b4.build_stats()["checksum"]
 lob = _sc.lights_and_lobes_scene(grid=3, subdiv=1); b5 = backend.B200Backend(48, 32); lob.apply(b5)

@@ -187,20 +187,27 @@ def test_spatial_splits_keep_the_hits_and_cut_the_traversal(B, oracle_mod, torch
 
 
 def test_fused_small_builds_give_the_same_trees(B, oracle_mod):
-    """Meshes (and a TLAS) of <= 2 048 boxes are built by ONE CTA each, all in one launch (builder.cu::k_build_small, option build_fused,
+    """Meshes (and a TLAS) of <= 8 192 boxes are built by ONE CTA each, all in one launch (builder.cu::k_build_small, option build_fused,
     default on).  Same bodies as the general builder, so: same BVH checksum, bit-identical hits, far fewer launches.  Sizes straddle every
-    special case of the pipeline: 1, 2 and 3 triangles (no Karras / no refinement), the treelet size, one warp, the sort tile and one past it."""
-    sizes = [1, 2, 3, 8, 9, 31, 33, 257, 1000, 2047, 2048, 2049]
+    special case of the pipeline: 1, 2 and 3 triangles (no Karras / no refinement), the treelet size, one warp, one sort tile and one past it
+    (the in-CTA sort goes multi-tile), the fused limit and one past it (general builder)."""
+    sizes = [1, 2, 3, 8, 9, 31, 33, 257, 1000, 2047, 2048, 2049, 4097, 6000, 8191, 8192, 8193]
     desc = scenes.SceneDesc()
     rng = np.random.default_rng(5)
     for k, n in enumerate(sizes):
         desc.meshes[k] = scenes.soup(n, 0.15, seed=scenes.SEED_SCENE + 17 * k)
         desc.instances[k] = scenes.to_column_major([scenes.trs(tuple(rng.uniform(-1.5, 1.5, 3)), rot_angle=float(rng.uniform(0, 3)), scale=float(rng.uniform(0.5, 1.5))) for _ in range(2)])
-    fused, cpu = make_pair(B, oracle_mod, desc)
+    fused = B.B200Backend(0, 0)
+    fused.set_option("build_fused_medium_min", 1)   # (default 6: medium meshes join the fused launch only when there is a crowd of them)
+    desc.apply(fused)
+    cpu = oracle_mod.OracleBackend(det_eps=0.0); desc.apply(cpu)
     general = B.B200Backend(0, 0)
     general.set_option("build_fused", 0)
     l0 = general.launch_count(); desc.apply(general); l_general = general.launch_count() - l0
-    again = B.B200Backend(0, 0)
+    again = B.B200Backend(0, 0)   # default policy: the five medium meshes go through the general builder here
+    desc.apply(again)
+    assert again.build_stats()["checksum"] == general.build_stats()["checksum"]
+    again = B.B200Backend(0, 0); again.set_option("build_fused_medium_min", 1)
     l0 = again.launch_count(); desc.apply(again); l_fused = again.launch_count() - l0
     sf, sg = fused.build_stats(), general.build_stats()
     assert sf["checksum"] == sg["checksum"] == again.build_stats()["checksum"]
@@ -213,7 +220,7 @@ def test_fused_small_builds_give_the_same_trees(B, oracle_mod):
     assert (hf["inst"] >= 0).mean() > 0.05
     parity.compare_hits(rays, hf, cpu.trace_closest(rays), parity.lookup_from_desc(desc), "fused-build")
     # a rebuild of only some meshes through the fused path leaves the others alone and reproduces the tree
-    fused.set_3d_mesh(3, desc.meshes[3]); fused.set_3d_mesh(9, desc.meshes[9]); fused.synchronize()
+    fused.set_3d_mesh(3, desc.meshes[3]); fused.set_3d_mesh(9, desc.meshes[9]); fused.set_3d_mesh(13, desc.meshes[13]); fused.synchronize()
     assert fused.build_stats()["checksum"] == sf["checksum"]
     assert fused.trace_closest(rays).tobytes() == hf.tobytes()
 
