@@ -408,6 +408,37 @@ def _emit(line):
     out.flush()
 
 
+def dynamic_build_extra(backend):
+    """Per-frame build costs of dynamic scenes (the fused small / medium builds of builder.cu::k_build_small): warm rebuild of the 170 per-mesh
+    BLASes of the reference's pica asset, and N animated CesiumMan instances (4 672 triangles each) re-skinned and rebuilt with a new pose per frame
+    (set_skins + synchronize, wall clock).  Fixtures: tests/golden/{pica,cesium_man}.npz (made from /root/reference/assets, committed)."""
+    from rfw_rs_b200 import gltf
+    out = {}
+    gold = os.path.join(ROOT, "tests", "golden")
+    be = backend.B200Backend()
+    gltf.per_mesh(gltf.load_npz(os.path.join(gold, "pica.npz"))).apply(be)
+    wall = []
+    for _ in range(5):
+        l0 = be.launch_count()
+        be.set_option("sah_treelet", 8)   # marks every mesh dirty
+        t0 = time.perf_counter(); be.synchronize(); wall.append((time.perf_counter() - t0) * 1e3)
+        launches = be.launch_count() - l0
+    # (build_stats once, after the loop: it evaluates the lazy BVH checksum — two launches per mesh)
+    out["pica_170_blas_rebuild"] = {"blas_build_ms": be.build_stats()["blas_build_ms"], "synchronize_wall_ms": min(wall[1:]), "kernel_launches": int(launches), "meshes": 170, "triangles": 76274}
+    del be
+    man = gltf.load_npz(os.path.join(gold, "cesium_man.npz"))
+    for copies in (17, 65):
+        be = backend.B200Backend()
+        gltf.skinned(man, copies=copies).apply(be)
+        wall = []
+        for f in range(8):
+            pose = gltf.pose_joints(man.skins[0], angle=0.1 + 0.03 * f)
+            t0 = time.perf_counter(); be.set_skins([pose]); be.synchronize(); wall.append((time.perf_counter() - t0) * 1e3)
+        out[f"animated_characters_{copies - 1}"] = {"frame_ms_set_skins_plus_synchronize": min(wall[2:]), "triangles_each": 4672}
+        del be
+    return out
+
+
 def main():
     _quiet_stdout()
     ap = argparse.ArgumentParser()
@@ -416,6 +447,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-dynamic", action="store_true", help="skip extra.dynamic_scene_builds (pica rebuild, animated characters)")
     ap.add_argument("--pt-spp", type=int, default=16, help="C3 extra: samples per pixel")
     ap.add_argument("--no-path-tracing", action="store_true", help="skip the C5 path-tracing block")
     ap.add_argument("--c5-tris", type=int, default=10_000_000)
@@ -569,6 +601,11 @@ def main():
         extra["hit_rate"] = hit_rate
         extra["bvh_build"] = {"blas_build_ms": min(warm_build_ms), "blas_build_ms_first_in_process": bs["blas_build_ms"], "synchronize_wall_ms_incl_upload": sync_wall_ms, "wide_nodes": bs["blas_nodes"],
                               "bvh_bytes": bs["bvh_bytes"], "sah_cost": bs["sah_cost"]}
+    if not args.no_extras and not args.no_dynamic and rank == 0:
+        try:
+            extra["dynamic_scene_builds"] = dynamic_build_extra(backend)
+        except Exception as ex:
+            extra["dynamic_scene_builds"] = {"error": repr(ex)}
     if not args.no_extras:
         try:
             pt = path_tracing_extra(backend, scenes, sharding, torch, rank, world, args.pt_spp, dist)

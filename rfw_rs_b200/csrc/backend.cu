@@ -705,7 +705,9 @@ int Backend::synchronize() {
             cudaError_t e = cudaSuccess;
             if (live > 1) {
                 const BuildParams tlas_params{1.0f, 4.0f, 1, sah_treelet_tlas};
-                if (build_fused && live <= (uint32_t)BUILD_FUSED_MAX) {
+                // (one-tile TLASes only: alone, a medium job is quicker through the general builder — 4 917 instances 0.94 vs 1.08 ms per synchronize,
+                //  7 761: 0.86 vs 1.31; 213: 0.34 fused vs 0.41; scripts/exp_dynamic.py)
+                if (build_fused && live <= (uint32_t)BUILD_FUSED_ONE_TILE) {
                     const SmallBuildItem item{nullptr, lo, hi, (int)live, &tlas, nullptr};
                     e = build_small_batch(bctx, &item, 1, tlas_params);
                 } else {

@@ -6,9 +6,12 @@ from rfw_rs_b200 import backend, scenes
 grid = int(os.environ.get("GRID", 100))
 desc = scenes.instanced_scene(grid=grid, subdiv=3, n_lights=16)
 w, h = 1280, 720
-be = backend.B200Backend(w, h, sky=(0.3, 0.35, 0.5)); desc.apply(be)
+be = backend.B200Backend(w, h, sky=(0.3, 0.35, 0.5))
+for kv in os.environ.get("OPTS", "").split(","):
+    if "=" in kv: be.set_option(kv.split("=")[0], int(kv.split("=")[1]))
+desc.apply(be)
 view = scenes.camera_view((0.0, 14.0, -62.0), (0.0, -0.25, 1.0), w, h)
-print("initial build", be.build_stats())
+
 times, tl = [], []
 for frame in range(12):
     for m in range(8):
