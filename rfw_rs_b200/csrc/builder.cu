@@ -169,7 +169,10 @@ __device__ __forceinline__ float bins_area(const uint32_t lo[3], const uint32_t 
 
 // segments with more items than this are split like the radix tree does (highest differing Morton bit): the top few
 // levels of a big scene are spatial-median splits either way, and one warp per segment would serialise on them
-static constexpr int SAH_BIG_SEGMENT = 4096;
+#ifndef RFW_SAH_BIG_SEGMENT
+#define RFW_SAH_BIG_SEGMENT 4096
+#endif
+static constexpr int SAH_BIG_SEGMENT = RFW_SAH_BIG_SEGMENT;
 
 // lane 0: the top node of segment [begin, end) gets its two children (a treelet root when a side has one item, else a
 // new top node + a segment for the next level)

@@ -11,6 +11,9 @@ be = backend.B200Backend(); desc.apply(be)
 for kv in os.environ.get("AB_OPTS", "").split(","):
     if "=" in kv:
         k, v = kv.split("="); be.set_option(k, int(v))
+build_ms = []
+for _ in range(3):
+    be.set_option("sah_treelet", 8); be.synchronize(); build_ms.append(be.build_stats()["blas_build_ms"])
 rays = scenes.random_rays(n_rays)
 d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1).copy()).cuda()
 d_hits = torch.empty(n_rays * 20, dtype=torch.uint8, device="cuda")
@@ -26,7 +29,7 @@ run(False, 2)
 c, a = run(False), run(True)
 h = np.frombuffer(d_hits.cpu().numpy().tobytes(), dtype=wire.HIT)
 crc = zlib.crc32(h["prim"].tobytes()) ^ zlib.crc32(h["t"].tobytes()) ^ zlib.crc32(d_occ.cpu().numpy().tobytes())
-line = f"{name:24s} C2({n_tris}) closest {c:7.1f} any {a:7.1f} Mrays/s crc {crc:08x}"
+line = f"{name:24s} C2({n_tris}) build {min(build_ms):5.2f} ms closest {c:7.1f} any {a:7.1f} Mrays/s crc {crc:08x}"
 del be, d_rays, d_hits, d_occ
 if not os.environ.get("AB_SKIP_C3"):
     w, hh, spp, depth = 1920, 1080, 16, 5
