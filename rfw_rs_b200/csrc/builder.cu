@@ -340,6 +340,160 @@ __device__ void sah_split_segment(int4 seg, int* __restrict__ items, int* __rest
     __syncwarp();
 }
 
+// The same split by ALL warps of the CTA (segments of SAH_COOP_MIN < items <= SAH_BIG_SEGMENT: with one warp per segment the few big segments of the
+// upper levels were the serial part of the top build — a 4 096-item segment is 128 rounds of three passes for one warp).  Same bins (atomics are
+// order-independent), same candidate evaluation, same stable partition: the same tree as sah_split_segment.  Must be called by every thread of the CTA.
+#ifndef RFW_SAH_COOP_MIN
+#define RFW_SAH_COOP_MIN 256
+#endif
+static constexpr int SAH_COOP_MIN = RFW_SAH_COOP_MIN;
+static constexpr int SAH_MAX_WARPS = 16;
+struct SahCoop {
+    float red[SAH_MAX_WARPS][6];
+    int prims[SAH_MAX_WARPS];
+    int cnt[SAH_MAX_WARPS][2];
+    int best_cand, best_nl;
+};
+__device__ void sah_split_segment_cta(int4 seg, int* __restrict__ items, int* __restrict__ items_tmp, const BuildArrays& A, SahBins& bins, SahCoop& co, int4* __restrict__ next_segs,
+                                      uint32_t* __restrict__ next_count, uint32_t* __restrict__ top_counter) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, T = blockDim.x, W = T >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    const int begin = seg.x, end = seg.y, top = seg.z;
+    // a. centroid bounds, primitive count
+    float cmin[3] = {3e38f, 3e38f, 3e38f}, cmax[3] = {-3e38f, -3e38f, -3e38f};
+    int prims = 0;
+    for (int i = begin + (int)threadIdx.x; i < end; i += T) {
+        const int node = items[i];
+        const float4 l = A.node_lo[node], h = A.node_hi[node];
+        const float c[3] = {(l.x + h.x) * 0.5f, (l.y + h.y) * 0.5f, (l.z + h.z) * 0.5f};
+#pragma unroll
+        for (int a = 0; a < 3; a++) { cmin[a] = fminf(cmin[a], c[a]); cmax[a] = fmaxf(cmax[a], c[a]); }
+        prims += node_prim_count(node, A);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            cmin[a] = fminf(cmin[a], __shfl_xor_sync(FULLMASK, cmin[a], o));
+            cmax[a] = fmaxf(cmax[a], __shfl_xor_sync(FULLMASK, cmax[a], o));
+        }
+        prims += __shfl_xor_sync(FULLMASK, prims, o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) { co.red[warp][a] = cmin[a]; co.red[warp][3 + a] = cmax[a]; }
+        co.prims[warp] = prims;
+    }
+    for (int k = threadIdx.x; k < 48; k += T) {
+        const int a = k / 16, b = k % 16;
+        bins.cnt[a][b] = 0;
+#pragma unroll
+        for (int d = 0; d < 3; d++) { bins.lo[a][b][d] = 0xFFFFFFFFu; bins.hi[a][b][d] = 0u; }
+    }
+    __syncthreads();
+    prims = 0;
+    for (int w = 0; w < W; w++) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) { cmin[a] = fminf(cmin[a], co.red[w][a]); cmax[a] = fmaxf(cmax[a], co.red[w][3 + a]); }
+        prims += co.prims[w];
+    }
+    float scale[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) scale[a] = cmax[a] > cmin[a] ? 16.0f / (cmax[a] - cmin[a]) : 0.0f;
+    // b. bins
+    for (int i = begin + (int)threadIdx.x; i < end; i += T) {
+        const int node = items[i];
+        const float4 l = A.node_lo[node], h = A.node_hi[node];
+        const float c[3] = {(l.x + h.x) * 0.5f, (l.y + h.y) * 0.5f, (l.z + h.z) * 0.5f};
+        const uint32_t el[3] = {enc_f(l.x), enc_f(l.y), enc_f(l.z)}, eh[3] = {enc_f(h.x), enc_f(h.y), enc_f(h.z)};
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const int b = min(15, (int)((c[a] - cmin[a]) * scale[a]));
+            atomicAdd(&bins.cnt[a][b], 1);
+#pragma unroll
+            for (int d = 0; d < 3; d++) { atomicMin(&bins.lo[a][b][d], el[d]); atomicMax(&bins.hi[a][b][d], eh[d]); }
+        }
+    }
+    __syncthreads();
+    // c. 45 candidates, by warp 0
+    if (warp == 0) {
+        float best_cost = 3.0e38f;
+        int best_cand = -1, best_nl = 0;
+        for (int cand = lane; cand < 45; cand += 32) {
+            const int a = cand / 15, split = cand % 15;
+            if (scale[a] == 0.0f) continue;
+            uint32_t llo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, lhi[3] = {0, 0, 0}, rlo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, rhi[3] = {0, 0, 0};
+            int nl = 0, nr = 0;
+            for (int b = 0; b < 16; b++) {
+                const int c = bins.cnt[a][b];
+                if (c == 0) continue;
+                if (b <= split) {
+                    nl += c;
+#pragma unroll
+                    for (int d = 0; d < 3; d++) { llo[d] = min(llo[d], bins.lo[a][b][d]); lhi[d] = max(lhi[d], bins.hi[a][b][d]); }
+                } else {
+                    nr += c;
+#pragma unroll
+                    for (int d = 0; d < 3; d++) { rlo[d] = min(rlo[d], bins.lo[a][b][d]); rhi[d] = max(rhi[d], bins.hi[a][b][d]); }
+                }
+            }
+            if (nl == 0 || nr == 0) continue;
+            const float cost = bins_area(llo, lhi) * (float)nl + bins_area(rlo, rhi) * (float)nr;
+            if (cost < best_cost) { best_cost = cost; best_cand = cand; best_nl = nl; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float oc = __shfl_xor_sync(FULLMASK, best_cost, o);
+            const int ocand = __shfl_xor_sync(FULLMASK, best_cand, o);
+            const int onl = __shfl_xor_sync(FULLMASK, best_nl, o);
+            if (ocand >= 0 && (best_cand < 0 || oc < best_cost || (oc == best_cost && ocand < best_cand))) { best_cost = oc; best_cand = ocand; best_nl = onl; }
+        }
+        if (lane == 0) { co.best_cand = best_cand; co.best_nl = best_nl; }
+    }
+    __syncthreads();
+    const int best_cand = co.best_cand;
+    // d. partition (stable): T items per round, left / right counts of the warps through shared memory
+    int nl;
+    if (best_cand < 0) {
+        nl = (end - begin) / 2;  // all centroids coincide: median split in Morton order
+    } else {
+        nl = co.best_nl;
+        const int a = best_cand / 15, split = best_cand % 15;
+        const float cm = a == 0 ? cmin[0] : (a == 1 ? cmin[1] : cmin[2]);
+        const float sc = a == 0 ? scale[0] : (a == 1 ? scale[1] : scale[2]);
+        int loff = 0, roff = 0;
+        for (int base = begin; base < end; base += T) {
+            const int i = base + (int)threadIdx.x;
+            const bool valid = i < end;
+            int node = 0;
+            bool left = false;
+            if (valid) {
+                node = items[i];
+                const float4 l = A.node_lo[node], h = A.node_hi[node];
+                const float c = a == 0 ? (l.x + h.x) * 0.5f : (a == 1 ? (l.y + h.y) * 0.5f : (l.z + h.z) * 0.5f);
+                left = min(15, (int)((c - cm) * sc)) <= split;
+            }
+            const uint32_t ml = __ballot_sync(FULLMASK, valid && left), mr = __ballot_sync(FULLMASK, valid && !left);
+            if (lane == 0) { co.cnt[warp][0] = __popc(ml); co.cnt[warp][1] = __popc(mr); }
+            __syncthreads();
+            int lbefore = 0, rbefore = 0, ltot = 0, rtot = 0;
+            for (int w = 0; w < W; w++) {
+                const int cl = co.cnt[w][0], cr = co.cnt[w][1];
+                if (w < warp) { lbefore += cl; rbefore += cr; }
+                ltot += cl; rtot += cr;
+            }
+            if (valid) items_tmp[left ? begin + loff + lbefore + __popc(ml & lt) : begin + nl + roff + rbefore + __popc(mr & lt)] = node;
+            loff += ltot; roff += rtot;
+            __syncthreads();
+        }
+        for (int i = begin + (int)threadIdx.x; i < end; i += T) items[i] = items_tmp[i];
+    }
+    __syncthreads();
+    // e. children
+    if (threadIdx.x == 0) sah_emit_children(begin, end, nl, prims, top, items, A, next_segs, next_count, top_counter);
+    __syncthreads();
+}
+
 // Who takes part in a level loop and how they wait for each other: the whole cooperative grid (one big build), or one CTA (the fused
 // build of many small meshes, k_build_small: one CTA per mesh).
 struct GridScope {
@@ -347,19 +501,27 @@ struct GridScope {
     __device__ uint32_t tid() const { return blockIdx.x * blockDim.x + threadIdx.x; }
     __device__ uint32_t n_threads() const { return gridDim.x * blockDim.x; }
     __device__ bool leader() const { return blockIdx.x == 0 && threadIdx.x == 0; }
+    __device__ uint32_t cta() const { return blockIdx.x; }
+    __device__ uint32_t n_ctas() const { return gridDim.x; }
+    static constexpr int coop_min = SAH_COOP_MIN;
     __device__ void sync() { __threadfence(); g.sync(); }
 };
 struct CtaScope {
     __device__ uint32_t tid() const { return threadIdx.x; }
     __device__ uint32_t n_threads() const { return blockDim.x; }
     __device__ bool leader() const { return threadIdx.x == 0; }
+    __device__ uint32_t cta() const { return 0u; }
+    __device__ uint32_t n_ctas() const { return 1u; }
+    // (a fused job has at most 1 024 treelets: its two or three middle-sized segments cost more done one after the other by the whole CTA
+    //  than side by side by a warp each — 431 vs 367 us of SAH top build at 4 672 triangles)
+    static constexpr int coop_min = 1 << 30;
     __device__ void sync() { __syncthreads(); }  // (orders the CTA's global accesses too)
 };
 
 // all levels of the top-down SAH build over the treelets; `bins`: one SahBins per warp of the CTA (shared memory)
 template <class Scope>
 __device__ void sah_top_loop(Scope sc, const BuildArrays& A, int* __restrict__ items, int* __restrict__ items_tmp, int4* __restrict__ seg0, int4* __restrict__ seg1,
-                             uint32_t* __restrict__ counters, SahBins* bins) {
+                             uint32_t* __restrict__ counters, SahBins* bins, SahCoop* coop) {
     const int warp_in_block = threadIdx.x >> 5;
     const uint32_t warp = sc.tid() >> 5, n_warps = sc.n_threads() >> 5;
     const uint32_t m = counters[4];
@@ -376,7 +538,19 @@ __device__ void sah_top_loop(Scope sc, const BuildArrays& A, int* __restrict__ i
     int4 *sin = seg0, *sout = seg1;
     while (count > 0) {
         uint32_t* next = counters + 6 + ping;
-        for (uint32_t s = warp; s < count; s += n_warps) sah_split_segment(sin[s], items, items_tmp, A, bins[warp_in_block], sout, next, counters + 5);
+        // middle-sized segments: one CTA each, all its warps (uniform per CTA: every thread sees the same segment list)
+        for (uint32_t s = sc.cta(); s < count; s += sc.n_ctas()) {
+            const int4 sg = sin[s];
+            const int len = sg.y - sg.x;
+            if (len > Scope::coop_min && len <= SAH_BIG_SEGMENT) sah_split_segment_cta(sg, items, items_tmp, A, bins[0], *coop, sout, next, counters + 5);
+        }
+        // the rest: one warp each (small segments; segments above SAH_BIG_SEGMENT are split by their Morton keys, by one lane)
+        for (uint32_t s = warp; s < count; s += n_warps) {
+            const int4 sg = sin[s];
+            const int len = sg.y - sg.x;
+            if (len > Scope::coop_min && len <= SAH_BIG_SEGMENT) continue;
+            sah_split_segment(sg, items, items_tmp, A, bins[warp_in_block], sout, next, counters + 5);
+        }
         sc.sync();
         count = *((volatile uint32_t*)next);
         if (sc.leader()) counters[6 + (ping ^ 1)] = 0;
@@ -390,7 +564,8 @@ __device__ void sah_top_loop(Scope sc, const BuildArrays& A, int* __restrict__ i
 __global__ void __launch_bounds__(128) k_sah_top(BuildArrays A, int* __restrict__ items, int* __restrict__ items_tmp, int4* __restrict__ seg0, int4* __restrict__ seg1,
                                                  uint32_t* __restrict__ counters) {
     __shared__ SahBins bins[4];
-    sah_top_loop(GridScope{cg::this_grid()}, A, items, items_tmp, seg0, seg1, counters, bins);
+    __shared__ SahCoop coop;
+    sah_top_loop(GridScope{cg::this_grid()}, A, items, items_tmp, seg0, seg1, counters, bins, &coop);
 }
 
 // re-cost the top tree bottom-up: one thread per treelet root climbs (second arrival computes the node)
@@ -531,6 +706,7 @@ __global__ void __launch_bounds__(THREADS) k_build_small(const SmallBuildJob* __
     SmallCarve c;
     c.carve(job.scratch, n, refine, job.tris != nullptr);
     __shared__ SahBins bins[(THREADS / 32)];
+    __shared__ SahCoop coop;
     __shared__ float part[(THREADS / 32)][12];
     __shared__ uint32_t s_bounds[12];
     __shared__ uint32_t s_scan[(THREADS / 32)];
@@ -657,7 +833,7 @@ __global__ void __launch_bounds__(THREADS) k_build_small(const SmallBuildJob* __
         }
         sc.sync();
     small_trace(job, 6);
-        sah_top_loop(sc, A, c.items, c.items_tmp, c.seg0, c.seg1, c.counters, bins);
+        sah_top_loop(sc, A, c.items, c.items_tmp, c.seg0, c.seg1, c.counters, bins, &coop);
         sc.sync();
         small_trace(job, 7);
         {
