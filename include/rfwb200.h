@@ -475,7 +475,6 @@ RFWB200_API int rfwb200_render_stats(void* handle, RfwRenderStats* out);
  *   traversal:  trace_variant (0 persistent, 1 one thread per ray), min_blocks, blocks_per_sm, refill_below (28), tri_batch (4),
  *               tri_batch_two_level (4), inst_batch (6: two-level kernels enter instances when this many lanes wait at a TLAS leaf)
  *               sort_rays (0; 1 = device-pointer batches traced in Morton order of the ray origins), sort_min_bvh_mb
- *               instance_box_cull (1: an instance entry tests the object-space ray against the BLAS bounds before the root-node visit)
  *   host path:  streamed (1: single persistent launch overlapping upload and download), chunk_rays, l2_persist (0; 1 / 2 = persisting-L2 window over the
  *               largest node / traversal-triangle array: HBM reads of the C2 kernel 1.75 -> 0.91 GB with 2, no speed-up)
  *               tri_test (0 watertight; 1 = the reference's Moller-Trumbore arithmetic, operation for operation: parity runs)

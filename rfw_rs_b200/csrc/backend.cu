@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(128) k_instance_prepare(const MeshEntry* __res
     live_flag[gid] = live ? 1u : 0u;
 }
 
-// instance records gathered into TLAS leaf-slot order: one record = 7 x 16 B
+// instance records gathered into TLAS leaf-slot order: one record = 5 x 16 B
 __global__ void k_gather_instances(const InstanceRec* __restrict__ recs, const uint32_t* __restrict__ leaf_refs, uint32_t n, InstanceRec* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -430,7 +430,6 @@ __global__ void k_instance_override(const SkinOverride* __restrict__ ov, uint32_
     const SkinOverride o = ov[k];
     if (!live_flag[o.gid]) return;
     recs[o.gid].nodes = o.nodes; recs[o.gid].tris = o.ttris;
-    instance_box_pad(o.lo, o.hi, recs[o.gid].blo, recs[o.gid].bhi);
     shading[o.gid].tris = o.tris;
     const float* M = matrices + (size_t)o.gid * 16;
     float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
@@ -737,7 +736,6 @@ int Backend::synchronize() {
         sv.num_live = (int)live;
         sv.overflow = d_overflow;
         sv.tri_mt = tri_mt;
-        sv.box_cull = instance_box_cull ? 1 : 0;
         {   // the per-ray traversal stack bounds the depth of what can be traced (trace_kernel.cuh)
             uint32_t blas_depth = 0;
             for (const MeshRec& m : meshes) if (m.present && m.n) blas_depth = std::max(blas_depth, m.bvh.depth);
@@ -1686,7 +1684,6 @@ int Backend::set_option(const char* key, int64_t value) {
     else if (k == "streamed") streamed_enabled = value != 0;  // host-buffer entry points: single-launch streaming (1) or chunked pipeline (0)
     else if (k == "chunk_rays") chunk_rays = (uint64_t)std::max<int64_t>(1024, value);
     else if (k == "max_depth") cfg.max_depth = (uint32_t)value;
-    else if (k == "instance_box_cull") { instance_box_cull = value != 0; sv.box_cull = instance_box_cull ? 1 : 0; }  // instance entries test the object-space ray against the BLAS bounds before the root visit (1, default)
     else if (k == "build_fused") build_fused = value != 0;  // meshes / TLASes of <= 2 048 boxes built by one CTA each, all in one launch (1, default) or by the general builder (0)
     else if (k == "build_fused_medium_min") build_fused_medium_min = (int)std::max<int64_t>(0, value);  // jobs of 2 049 .. 8 192 triangles are fused when at least this many are dirty
     else if (k == "build_threads") build_threads = value != 0;  // one host thread per side builder context (1, default) or all launches from the calling thread (0)

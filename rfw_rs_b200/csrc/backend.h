@@ -154,7 +154,6 @@ private:
     // that several chains are in flight at once.  Option "build_streams" (default 8; 1 = everything on the main stream).
     std::vector<BuilderContext*> side_ctx;
     int build_streams = 8;
-    bool instance_box_cull = true;  // option "instance_box_cull"
     bool build_fused = true;    // option "build_fused": meshes (and a TLAS) of <= BUILD_FUSED_MAX boxes are built by ONE CTA each, all in one launch (builder.cu::k_build_small)
     int build_fused_medium_min = 2;  // option: jobs of BUILD_FUSED_ONE_TILE < n <= BUILD_FUSED_MAX triangles join the fused launch when at least this many are dirty
     bool build_threads = true;  // option "build_threads": the side contexts' launches are enqueued by one host thread each

@@ -61,7 +61,6 @@ RFW_HD bool instance_record(const MeshEntry& me, const float* M, bool zero, uint
     if (!live) return false;
     r.nodes = me.nodes; r.tris = me.ttris; r.inst_id = (int)gid; r.mesh_id = (int)mesh_index; r.pad1 = 0;
     r.direct_tris = (me.n_tris >= 1u && me.n_tris <= (uint32_t)RFW_DIRECT_TRIS) ? (int)me.n_tris : 0;
-    instance_box_pad(me.lo, me.hi, r.blo, r.bhi);
     sh.tris = me.tris; sh.mesh_id = (int)mesh_index; sh.pad = 0;
     lo[0] = lo[1] = lo[2] = 3e38f; hi[0] = hi[1] = hi[2] = -3e38f;
 #if defined(__CUDA_ARCH__)

@@ -363,10 +363,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_trace_persistent(SceneV
                         nodes = rec->nodes; tris = rec->tris;
                         // a BLAS of a handful of triangles (ground quad, light quads): straight to its triangles, no root-node visit
                         const int direct = rec->direct_tris;
-                        // the world box that led here is the box of the 8 transformed corners: far looser than the BLAS's own bounds for a rotated
-                        // instance.  A ray that misses those skips the root-node visit (a dependent 96-byte fetch + the 8-wide test) and leaves again.
-                        const bool skip = direct > 0 || (sv.box_cull && ray_misses_instance_box(*rec, rc, tmin, hit.t));
-                        ng = make_uint2(0u, skip ? 0u : 0x80000000u);
+                        ng = make_uint2(0u, direct > 0 ? 0u : 0x80000000u);
                         tg = make_uint2(0u, direct > 0 ? (1u << direct) - 1u : 0u);
                     }
                 }

@@ -46,11 +46,9 @@ struct Hit {
     float t, u, v;
 };
 
-// One live instance as the traversal sees it (112 B, 16-B aligned).
+// One live instance as the traversal sees it (80 B, 16-B aligned).
 struct InstanceRec {
     float4 inv0, inv1, inv2;   // rows of the 3x4 world->object matrix
-    float4 blo, bhi;           // object-space bounds of the BLAS, padded (instance_box_pad): the world box of a rotated instance is far looser than
-                               // this one (~2.25x the surface area for a random rotation), so the entry tests the transformed ray against it before the root visit
     const float4* nodes;       // BLAS wide nodes (5 float4 per node)
     const float4* tris;        // BLAS traversal triangles (3 float4 per triangle; v0.w = mesh-local prim id)
     int inst_id;               // global instance index reported in hits
@@ -68,7 +66,6 @@ struct SceneView {
     int two_level;                  // 0: exactly one live instance, traced directly
     int single_identity;            // single instance has an identity transform
     int num_live;
-    int box_cull;                   // 1: instance entries test the object-space ray against InstanceRec::blo/bhi first (option "instance_box_cull")
     int tri_mt;                     // triangle test: 0 = watertight (intersect_tri_wt, the product's), 1 = the reference's Moller-Trumbore
                                     // arithmetic operation for operation (intersect_tri_mt; option "tri_test"): parity runs
     uint32_t* overflow;             // one word the traversal kernels set when a push finds the per-ray stack full (the entry is
@@ -357,27 +354,6 @@ RFW_HD void xform_ray(const InstanceRec& rec, const float3 o, const float3 d, fl
             rec.inv2.x * d.x + rec.inv2.y * d.y + rec.inv2.z * d.z);
 }
 
-// Padded object-space bounds for InstanceRec: the box test at the instance entry must never reject a ray the triangle test would accept (the
-// object-space ray carries the rounding of the transform, the watertight test accepts hits an ulp outside an edge): 1e-5 of the box's size and
-// position per side costs no culling power.
-RFW_HD void instance_box_pad(const float lo[3], const float hi[3], float4& blo, float4& bhi) {
-    float l[3], h[3];
-    for (int a = 0; a < 3; a++) {
-        const float pad = 1.0e-5f * fmaxf(hi[a] - lo[a], fmaxf(fabsf(lo[a]), fabsf(hi[a]))) + 1.0e-30f;
-        l[a] = lo[a] - pad; h[a] = hi[a] + pad;
-    }
-    blo = f4(l[0], l[1], l[2], 0.0f); bhi = f4(h[0], h[1], h[2], 0.0f);
-}
-// slab test of the object-space ray (after ray_setup_box) against the instance's padded BLAS bounds; NaN slabs (0 * huge) do not constrain
-RFW_HD bool ray_misses_instance_box(const InstanceRec& rec, const RayCtx& r, float tmin, float tmax) {
-    const float x0 = (rec.blo.x - r.o.x) * r.idir.x, x1 = (rec.bhi.x - r.o.x) * r.idir.x;
-    const float y0 = (rec.blo.y - r.o.y) * r.idir.y, y1 = (rec.bhi.y - r.o.y) * r.idir.y;
-    const float z0 = (rec.blo.z - r.o.z) * r.idir.z, z1 = (rec.bhi.z - r.o.z) * r.idir.z;
-    const float cmin = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
-    const float cmax = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax)) * 1.0000006f;
-    return cmin > cmax;
-}
-
 // The same transform in the oracle's (= glm's mat4 * vec4) operation order, every operation rounded on its own: with option
 // "tri_test" = 1 the object-space ray — and with it t — is bit-identical to the oracle's in instanced scenes as well.
 RFW_HD void xform_ray_ref(const InstanceRec& rec, const float3 o, const float3 d, float3& oo, float3& od) {
@@ -493,7 +469,6 @@ RFW_HD bool trace_ray(const SceneView& sv, const float3 o, const float3 d, const
                 ng = make_uint2(0u, 0x80000000u);
                 tg = make_uint2(0u, 0u);
                 if (rec.direct_tris > 0) { ng = make_uint2(0u, 0u); tg = make_uint2(0u, (1u << rec.direct_tris) - 1u); continue; }
-                if (sv.box_cull && ray_misses_instance_box(rec, rc, tmin, hit.t)) ng = make_uint2(0u, 0u);  // nothing to visit: the BLAS exit below takes over
                 break;
             }
         }

@@ -199,7 +199,6 @@ void emu_build(void* s, float c_node, float c_prim, int pmax, uint64_t* stats) {
     }
     sc.sv.instances = sc.recs.data();
     sc.sv.num_live = (int)sc.recs.size();
-    sc.sv.box_cull = 1;  // the product's default (Backend::instance_box_cull)
     sc.sv.two_level = sc.recs.size() > 1;
     sc.sv.single_identity = (sc.recs.size() == 1) && identity_single;
     sc.sv.tlas_nodes = nullptr; sc.sv.tlas_refs = nullptr;
