@@ -707,6 +707,9 @@ __global__ void __launch_bounds__(THREADS) k_build_small(const SmallBuildJob* __
     c.carve(job.scratch, n, refine, job.tris != nullptr);
     __shared__ SahBins bins[(THREADS / 32)];
     __shared__ SahCoop coop;
+    // the level counters of the SAH top build / the collapse and the node / leaf allocators: in SHARED memory here (ncu: a quarter of the stall samples of
+    // the first version sat on the L2 round trip of `count = *next` after every level; three global atomics per wide node on top)
+    __shared__ uint32_t s_counters[16];
     __shared__ float part[(THREADS / 32)][12];
     __shared__ uint32_t s_bounds[12];
     __shared__ uint32_t s_scan[(THREADS / 32)];
@@ -724,7 +727,7 @@ __global__ void __launch_bounds__(THREADS) k_build_small(const SmallBuildJob* __
         }
         plo = c.prim_lo; phi = c.prim_hi;
     }
-    if (t < 16) c.counters[t] = 0;
+    if (t < 16) s_counters[t] = 0;
     {
         const size_t ni = (n > 1 ? (size_t)n - 1 : 1) + (refine ? (size_t)n : 0);
         for (size_t i = t; i < ni; i += THREADS) c.flags[i] = 0;
@@ -823,7 +826,7 @@ __global__ void __launch_bounds__(THREADS) k_build_small(const SmallBuildJob* __
                     const int p = base + t * SORT_ITEMS + k;
                     if (p < n) {
                         if (f[k]) c.items[run] = c.tre_node[p];
-                        if (p == n - 1) c.counters[4] = run + f[k];  // number of treelets
+                        if (p == n - 1) s_counters[4] = run + f[k];  // number of treelets
                     }
                     run += f[k];
                 }
@@ -833,11 +836,11 @@ __global__ void __launch_bounds__(THREADS) k_build_small(const SmallBuildJob* __
         }
         sc.sync();
     small_trace(job, 6);
-        sah_top_loop(sc, A, c.items, c.items_tmp, c.seg0, c.seg1, c.counters, bins, &coop);
+        sah_top_loop(sc, A, c.items, c.items_tmp, c.seg0, c.seg1, s_counters, bins, &coop);
         sc.sync();
         small_trace(job, 7);
         {
-            const uint32_t m = c.counters[4];
+            const uint32_t m = s_counters[4];
             if (m >= 2) {
                 for (uint32_t k = t; k < m; k += THREADS) {
                     int cur = A.parent[c.items[k]];
@@ -857,8 +860,8 @@ __global__ void __launch_bounds__(THREADS) k_build_small(const SmallBuildJob* __
     small_trace(job, 8);
     // 7. collapse
     CollapseOut O;
-    O.nodes = job.nodes; O.leaf_prims = job.leaf_prims; O.node_counter = c.counters + 0; O.prim_counter = c.counters + 1;
-    collapse_loop(sc, A, O, c.q0, c.q1, c.counters);
+    O.nodes = job.nodes; O.leaf_prims = job.leaf_prims; O.node_counter = s_counters + 0; O.prim_counter = s_counters + 1;
+    collapse_loop(sc, A, O, c.q0, c.q1, s_counters);
     sc.sync();
     small_trace(job, 9);
     // 8. traversal triangles in leaf order, 9. what the host wants to know
@@ -875,11 +878,11 @@ __global__ void __launch_bounds__(THREADS) k_build_small(const SmallBuildJob* __
         }
     }
     small_trace(job, 10);
-    if (t < 8) job.result->counters[t] = c.counters[t];
+    if (t < 8) job.result->counters[t] = s_counters[t];
     if (t < 12) job.result->bounds[t] = s_bounds[t];
     if (t < 4) job.result->pad[t] = 0u;  // (the whole record is copied to the host)
     if (t < 8) {
-        const size_t root = (refine && c.counters[4] >= 2u) ? 2 * (size_t)n - 1 : 0;
+        const size_t root = (refine && s_counters[4] >= 2u) ? 2 * (size_t)n - 1 : 0;
         job.result->cost[t] = c.cost[root * 8 + t];
     }
 }
