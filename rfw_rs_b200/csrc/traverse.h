@@ -232,6 +232,13 @@ RFW_HD uint32_t intersect_wide_node(const float4 n0, const float4 n1, const floa
     const float pax = aix * 32768.0f, pcx0 = aox - pax, pcxn = fmaf(-fabsf(pax), 2.3841858e-7f, pcx0), pcxf = fmaf(fabsf(pax), 2.3841858e-7f, pcx0);
     const float pay = aiy * 32768.0f, pcy0 = aoy - pay, pcyn = fmaf(-fabsf(pay), 2.3841858e-7f, pcy0), pcyf = fmaf(fabsf(pay), 2.3841858e-7f, pcy0);
     const float paz = aiz * 32768.0f, pcz0 = aoz - paz, pczn = fmaf(-fabsf(paz), 2.3841858e-7f, pcz0), pczf = fmaf(fabsf(paz), 2.3841858e-7f, pcz0);
+#if defined(RFW_FOLD_PAD)
+    // experiment: the 5-ulp pad of the far side folded into the far-plane constants and tmax (one FMUL per child less; min(a, b, c, d) * k == min(ak, bk, ck, dk), k > 0)
+    const float kpad = 1.0000006f;
+    const float aixf = aix * kpad, aoxf = aox * kpad, aiyf = aiy * kpad, aoyf = aoy * kpad, aizf = aiz * kpad, aozf = aoz * kpad;
+    const float paxf = pax * kpad, payf = pay * kpad, pazf = paz * kpad, pcxff = pcxf * kpad, pcyff = pcyf * kpad, pczff = pczf * kpad;
+    const float tmaxf = tmax * kpad;
+#endif
     uint32_t hitmask = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -254,14 +261,26 @@ RFW_HD uint32_t intersect_wide_node(const float4 n0, const float4 n1, const floa
             const int sh = 8 * j;
             // (RFW_B2F_PRMT_PLANES bit k set: the 8 conversions of plane set k = x near, x far, y near, y far, z near, z far go through PRMT)
             const float tlx = (RFW_B2F_PRMT_PLANES & 1) ? fmaf(byte_to_float_exp15(xmin, j), pax, pcxn) : fmaf(byte_to_float(xmin, j), aix, aox);
+#if defined(RFW_FOLD_PAD)
+            const float thx = (RFW_B2F_PRMT_PLANES & 2) ? fmaf(byte_to_float_exp15(xmax, j), paxf, pcxff) : fmaf(byte_to_float(xmax, j), aixf, aoxf);
+            const float thy = (RFW_B2F_PRMT_PLANES & 8) ? fmaf(byte_to_float_exp15(ymax, j), payf, pcyff) : fmaf(byte_to_float(ymax, j), aiyf, aoyf);
+            const float thz = (RFW_B2F_PRMT_PLANES & 32) ? fmaf(byte_to_float_exp15(zmax, j), pazf, pczff) : fmaf(byte_to_float(zmax, j), aizf, aozf);
+            const float tly = (RFW_B2F_PRMT_PLANES & 4) ? fmaf(byte_to_float_exp15(ymin, j), pay, pcyn) : fmaf(byte_to_float(ymin, j), aiy, aoy);
+            const float tlz = (RFW_B2F_PRMT_PLANES & 16) ? fmaf(byte_to_float_exp15(zmin, j), paz, pczn) : fmaf(byte_to_float(zmin, j), aiz, aoz);
+#else
             const float thx = (RFW_B2F_PRMT_PLANES & 2) ? fmaf(byte_to_float_exp15(xmax, j), pax, pcxf) : fmaf(byte_to_float(xmax, j), aix, aox);
             const float tly = (RFW_B2F_PRMT_PLANES & 4) ? fmaf(byte_to_float_exp15(ymin, j), pay, pcyn) : fmaf(byte_to_float(ymin, j), aiy, aoy);
             const float thy = (RFW_B2F_PRMT_PLANES & 8) ? fmaf(byte_to_float_exp15(ymax, j), pay, pcyf) : fmaf(byte_to_float(ymax, j), aiy, aoy);
             const float tlz = (RFW_B2F_PRMT_PLANES & 16) ? fmaf(byte_to_float_exp15(zmin, j), paz, pczn) : fmaf(byte_to_float(zmin, j), aiz, aoz);
             const float thz = (RFW_B2F_PRMT_PLANES & 32) ? fmaf(byte_to_float_exp15(zmax, j), paz, pczf) : fmaf(byte_to_float(zmax, j), aiz, aoz);
+#endif
             // fminf/fmaxf drop NaN operands (0 * inf): such a slab simply does not constrain
             const float cmin = fmaxf(fmaxf(tlx, tly), fmaxf(tlz, tmin));
+#if defined(RFW_FOLD_PAD)
+            const float cmax = fminf(fminf(thx, thy), fminf(thz, tmaxf));
+#else
             const float cmax = fminf(fminf(thx, thy), fminf(thz, tmax)) * 1.0000006f;  // 5-ulp pad: conservative slabs (FMA rounding + the <= 1 ulp of fast_rcp per axis)
+#endif
             if (cmin <= cmax) hitmask |= ((child_bits4 >> sh) & 0xFFu) << ((bit_index4 >> sh) & 0xFFu);
         }
     }
