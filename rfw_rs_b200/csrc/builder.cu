@@ -792,7 +792,41 @@ __global__ void __launch_bounds__(THREADS) k_build_small(const SmallBuildJob* __
     for (int i = t; i < n - 1; i += THREADS) karras_body(i, n, c.keys, c.parent, c.children, c.range);
     sc.sync();
     small_trace(job, 4);
-    for (int k = t; k < n; k += THREADS) fit_cost_body<true>(k, A, P);
+    // Bottom-up by ROUNDS instead of by climbing threads: a round computes every node whose two children are done — the nodes of a round are
+    // dealt to consecutive threads, so the cost DP runs at full lanes (climbing, a warp's 32 leaves merge pairwise and the DP of the upper nodes ran
+    // at ~1.3 active threads: ncu, profiles/r2_build_small_ncu.md).  Same per-node arithmetic, so the same costs and decisions.  The ready queues
+    // live in the collapse's task arrays (free until then); their counters in shared memory.
+    {
+        int* rq0 = reinterpret_cast<int*>(c.q0);
+        int* rq1 = reinterpret_cast<int*>(c.q1);
+        if (t == 0) { s_counters[8] = 0; s_counters[9] = 0; }
+        __syncthreads();
+        for (int k = t; k < n; k += THREADS) {
+            fit_cost_leaf(k, A, P);
+            if (n > 1) {
+                const int par = A.parent[n - 1 + k];
+                if (atomicAdd(&A.flags[inner_index(par, n)], 1) == 1) rq0[atomicAdd(&s_counters[8], 1u)] = par;  // second arrival: the parent is ready
+            }
+        }
+        __syncthreads();
+        int ping = 0;
+        for (;;) {
+            const uint32_t cnt = s_counters[8 + ping];
+            if (cnt == 0) break;  // (uniform: read after the barrier)
+            int* qin = ping ? rq1 : rq0;
+            int* qout = ping ? rq0 : rq1;
+            for (uint32_t i = t; i < cnt; i += THREADS) {
+                const int node = qin[i];
+                fit_cost_node(node, A, P);
+                const int par = A.parent[node];
+                if (par >= 0 && atomicAdd(&A.flags[inner_index(par, n)], 1) == 1) qout[atomicAdd(&s_counters[8 + (ping ^ 1)], 1u)] = par;
+            }
+            __syncthreads();
+            if (t == 0) s_counters[8 + ping] = 0;
+            ping ^= 1;
+            __syncthreads();
+        }
+    }
     sc.sync();
     small_trace(job, 5);
     // 6. binned-SAH refinement above the treelets

@@ -160,6 +160,18 @@ RFW_HD void fit_cost_node(int node, const BuildArrays& A, const BuildParams& P) 
     A.decision[inner_index(node, A.n)] = w;
 }
 
+// the leaf part of the bottom-up pass alone (box, costs); the climb is the caller's
+RFW_HD void fit_cost_leaf(int k, const BuildArrays& A, const BuildParams& P) {
+    const int leaf = A.n - 1 + k;
+    const uint32_t prim = A.order[k];
+    const float4 lo = A.prim_lo[prim], hi = A.prim_hi[prim];
+    A.node_lo[leaf] = lo;
+    A.node_hi[leaf] = hi;
+    const float area = box_area(xyz(lo), xyz(hi));
+    for (int i = 0; i < 7; i++) A.cost[(size_t)leaf * 8 + i] = area * P.c_prim;
+    A.cost[(size_t)leaf * 8 + 7] = area;
+}
+
 // one thread per sorted leaf k: write the leaf, then climb; the second thread to arrive at a node computes it
 template <bool CTA_SCOPE = false>
 RFW_HD void fit_cost_body(int k, const BuildArrays& A, const BuildParams& P) {
