@@ -519,9 +519,13 @@ struct SmallBuildJob {
 };
 __device__ __forceinline__ void small_trace(const SmallBuildJob& job, int slot) {
     if (job.trace && threadIdx.x == 0) {
+#if defined(RFW_HOST_SIMT)
+        job.trace[slot] = rfw_host_globaltimer();
+#else
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         job.trace[slot] = t;
+#endif
     }
 }
 

@@ -116,6 +116,8 @@ template <typename T>
 RFW_HD T atomic_add(T* p, T v) {
 #if defined(__CUDA_ARCH__)
     return atomicAdd(p, v);
+#elif defined(RFW_HOST_SIMT)
+    return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL);  // the CPU tier's SIMT machine runs the threads of a CTA concurrently (tests/hostemu/simt_machine.h)
 #else
     T o = *p; *p = o + v; return o;
 #endif
@@ -123,6 +125,8 @@ RFW_HD T atomic_add(T* p, T v) {
 RFW_HD void thread_fence() {
 #if defined(__CUDA_ARCH__)
     __threadfence();
+#elif defined(RFW_HOST_SIMT)
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
 #endif
 }
 // (when every thread that takes part runs in ONE CTA — the fused small build — a block-scope fence orders the same accesses at a fraction of the cost)
@@ -131,6 +135,8 @@ RFW_HD void thread_fence_scope() {
 #if defined(__CUDA_ARCH__)
     if (BLOCK_SCOPE) __threadfence_block();
     else __threadfence();
+#elif defined(RFW_HOST_SIMT)
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
 #endif
 }
 template <typename T>

@@ -594,6 +594,19 @@ def test_builder_structure_on_degenerate_distributions(emu, oracle_mod, dist, n)
     constant), exponentially spread sizes, a huge triangle among tiny ones (root box dominated by one primitive: the 8-bit
     quantisation grid is very coarse for the rest).  Structural validation (every primitive exactly once, every dequantised
     child box encloses its subtree) plus hit parity with the brute force."""
+    desc, tris, rng = degenerate_scene(dist, n)
+    e = Emu(emu, desc)
+    assert emu.emu_validate(e.h, 0) == 0
+    o = oracle_mod.OracleBackend(det_eps=0.0); desc.apply(o)
+    rays = aimed_rays(tris, rng, n)
+    hits, occ, _ = e.trace(rays)
+    ref = o.trace_closest(rays, mode=oracle_mod.MODE_BRUTE)
+    assert (ref["inst"] >= 0).mean() > 0.05
+    parity.compare_hits(rays, hits, ref, parity.lookup_from_desc(desc), f"{dist}/{n}", max_fraction=2e-2, oracle_artefacts=True)
+
+
+def degenerate_scene(dist, n):
+    """(scene, triangles, rng) of the degenerate centroid distributions (also used by tests/test_build_emu.py for the fused build kernel)"""
     rng = np.random.default_rng(n * 31 + len(dist))
     if dist == "identical":
         c = np.tile(rng.uniform(0, 1, (1, 3)), (n, 1))
@@ -615,10 +628,11 @@ def test_builder_structure_on_degenerate_distributions(emu, oracle_mod, dist, n)
     e1 /= np.linalg.norm(e1, axis=1, keepdims=True); e2 /= np.linalg.norm(e2, axis=1, keepdims=True)
     tris = scenes.make_triangles(c.astype(np.float32), (c + e1 * size[:, None]).astype(np.float32), (c + e2 * size[:, None]).astype(np.float32))
     desc = scenes.SceneDesc(); desc.meshes[0] = tris; desc.instances[0] = scenes.to_column_major([scenes.identity()]); desc.materials = scenes.material()
-    e = Emu(emu, desc)
-    assert emu.emu_validate(e.h, 0) == 0
-    o = oracle_mod.OracleBackend(det_eps=0.0); desc.apply(o)
-    rays = scenes.random_rays(1500, seed=n, lo=-0.2, hi=1.2)
+    return desc, tris, rng
+
+
+def aimed_rays(tris, rng, n, count=1500):
+    rays = scenes.random_rays(count, seed=n, lo=-0.2, hi=1.2)
     # aim half of the rays at primitives so the small ones are hit at all
     k = rng.integers(0, n, len(rays))
     aim = (np.arange(len(rays)) % 2 == 0)
@@ -626,10 +640,7 @@ def test_builder_structure_on_degenerate_distributions(emu, oracle_mod, dist, n)
     dirs = tgt - rays["origin"]
     dirs /= np.maximum(np.linalg.norm(dirs, axis=1, keepdims=True), 1e-20)
     rays["direction"][aim] = dirs[aim].astype(np.float32)
-    hits, occ, _ = e.trace(rays)
-    ref = o.trace_closest(rays, mode=oracle_mod.MODE_BRUTE)
-    assert (ref["inst"] >= 0).mean() > 0.05
-    parity.compare_hits(rays, hits, ref, parity.lookup_from_desc(desc), f"{dist}/{n}", max_fraction=2e-2, oracle_artefacts=True)
+    return rays
 
 
 # ---- the persistent kernel's warp-level schedule on the CPU (tests/hostemu/simt_emu.cpp) ----------------------------------------
