@@ -53,6 +53,16 @@ def mt_determinant(o, d, v0, v1, v2):
     return float(np.dot(v1 - v0, np.cross(d, v2 - v0)))
 
 
+def edge_on(o, d, v0, v1, v2, ulps=64.0):
+    """Is the triangle's projection along the ray thinner than `ulps` float32 ulps of its coordinates relative to the ray origin?"""
+    dn = d / max(np.linalg.norm(d), 1e-300)
+    P = [(v - o) - np.dot(v - o, dn) * dn for v in (v0, v1, v2)]   # the vertices projected onto the plane perpendicular to the ray
+    area2 = np.linalg.norm(np.cross(P[1] - P[0], P[2] - P[0]))
+    longest = max(np.linalg.norm(P[1] - P[0]), np.linalg.norm(P[2] - P[1]), np.linalg.norm(P[0] - P[2]), 1e-300)
+    scale = max(np.abs(v0 - o).max(), np.abs(v1 - o).max(), np.abs(v2 - o).max())
+    return area2 / longest <= ulps * 2.0 ** -24 * scale
+
+
 def compare_hits(rays, gpu, ref, scene_lookup, label="", max_fraction=MAX_MISMATCH_FRACTION, oracle_artefacts=False, reference_epsilon=0.0):
     """max_fraction bounds the number of CLASSIFIED near-ties (unclassified ones are never allowed).  Authored assets
     with coplanar duplicated faces (pica) need a looser count bound than the synthetic scenes: every pixel looking at
@@ -63,7 +73,7 @@ def compare_hits(rays, gpu, ref, scene_lookup, label="", max_fraction=MAX_MISMAT
     farther than the reference's, on a triangle whose float64 determinant is below that epsilon is explained by it.
     oracle_artefacts=True (stress tests on ill-conditioned inputs only): a hit the ORACLE reports whose float64-exact t lies outside
     the ray's (tmin, tmax) — its float32 Moller-Trumbore on a sliver triangle with the origin on the surface — explains a
-    mismatch as well; the product's answer is then checked to be exact-valid (or a miss)."""
+    mismatch as well; the product's answer is then checked to be exact-valid (or a miss); so does a triangle seen edge-on (edge_on())."""
     n = len(rays)
     assert len(gpu) == n and len(ref) == n
     same = (gpu["inst"] == ref["inst"]) & (gpu["prim"] == ref["prim"])
@@ -140,6 +150,15 @@ def compare_hits(rays, gpu, ref, scene_lookup, label="", max_fraction=MAX_MISMAT
         if not ok and oracle_artefacts and cand[1] is None and cand[0] is not None:
             # the oracle's float32 Moller-Trumbore missed a (sub-resolution) triangle that exact arithmetic says the ray hits
             ok = float(rays["tmin"][i]) < cand[0][0] < float(rays["tmax"][i]) and min(cand[0][1], cand[0][2], 1.0 - cand[0][1] - cand[0][2]) >= -EDGE_EPS
+        if not ok and oracle_artefacts:
+            # a triangle seen EDGE-ON: its projection along the ray is a sliver thinner than the float32 rounding of the vertex coordinates relative to the
+            # ray origin, so the sign of an edge function (watertight test) or of a barycentric (Moller-Trumbore) is decided by rounding, either way
+            for rec in (gpu[i], ref[i]):
+                if rec["inst"] < 0:
+                    continue
+                tris, inv = scene_lookup(int(rec["inst"]))
+                if edge_on(inv[:3, :3] @ o + inv[:3, 3], inv[:3, :3] @ d, *_tri_f64(tris, int(rec["prim"]))):
+                    ok = True
         if not ok and reference_epsilon > 0.0 and cand[0] is not None:
             tris, inv = scene_lookup(int(gpu[i]["inst"]))
             det = mt_determinant(inv[:3, :3] @ o + inv[:3, 3], inv[:3, :3] @ d, *_tri_f64(tris, int(gpu[i]["prim"])))
