@@ -531,7 +531,9 @@ __device__ __forceinline__ void small_trace(const SmallBuildJob& job, int slot) 
 
 // THREADS: 256 for one-tile jobs (n <= 2 048), 512 for the medium ones — every phase of a build inside ONE CTA is a latency chain (a 4 672-triangle
 // mesh: 2.0 ms with 256 threads), so the bigger jobs get the register file of a whole SM
-template <int THREADS>
+// Scope: CtaScope; the CPU test tier also instantiates a variant whose SAH top build sends middle-sized segments through sah_split_segment_cta (the path the
+// cooperative k_sah_top takes on the GPU) to hold that function against the per-warp split: same tree.
+template <int THREADS, class Scope = CtaScope>
 __global__ void __launch_bounds__(THREADS) k_build_small(const SmallBuildJob* __restrict__ jobs, BuildParams P) {
     const SmallBuildJob job = jobs[blockIdx.x];
     const int n = job.n, t = threadIdx.x;
@@ -546,7 +548,7 @@ __global__ void __launch_bounds__(THREADS) k_build_small(const SmallBuildJob* __
     __shared__ float part[(THREADS / 32)][12];
     __shared__ uint32_t s_bounds[12];
     __shared__ uint32_t s_scan[(THREADS / 32)];
-    CtaScope sc;
+    Scope sc;
 
     small_trace(job, 0);
     // 0. clear; 1. boxes + bounds

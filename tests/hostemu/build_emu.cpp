@@ -14,12 +14,31 @@
 
 using namespace rfw;
 
+// the fused kernel with the CTA-cooperative split switched on for segments of more than 32 treelets (on the GPU only the cooperative k_sah_top takes that path)
+struct CtaCoopScope : CtaScope {
+    static constexpr int coop_min = 32;
+};
+
 extern "C" {
+// the in-CTA radix sort alone (sort_small.cuh::sort_tiles_body on `threads` = 256 / 512 threads): sorts (keys, vals) in place
+int emu_sort_pairs(uint64_t* keys, uint32_t* vals, int n, int threads, int begin_bit, int end_bit) {
+    if (n < 0 || n > BUILD_FUSED_MAX || (threads != 256 && threads != 512)) return -2;
+    std::vector<uint64_t> kt((size_t)n + 1);
+    std::vector<uint32_t> vt((size_t)n + 1);
+    g_abort.store(false);
+    bool ok;
+    if (threads == 256) ok = simt_launch(1, 256, [&]() { sort_tiles_body<8, BUILD_FUSED_MAX / 2048>(keys, vals, kt.data(), vt.data(), n, begin_bit, end_bit); });
+    else ok = simt_launch(1, 512, [&]() { sort_tiles_body<16, BUILD_FUSED_MAX / 4096>(keys, vals, kt.data(), vt.data(), n, begin_bit, end_bit); });
+    if (!ok) return -1;
+    if ((((end_bit - begin_bit) + 7) / 8) & 1) { memcpy(keys, kt.data(), (size_t)n * 8); memcpy(vals, vt.data(), (size_t)n * 4); }  // odd number of passes: the result is in the tmp buffers
+    return 0;
+}
+
 // Builds the wide BVH of `n` triangles with k_build_small<THREADS> (threads = 256 or 512) on one emulated CTA.
 // nodes: n * NODE_F4 float4, leaf_prims: n, ttris: 3n float4, result: counters[8], bounds[12], cost[8].  Returns 0, -1 on a hang, -2 on bad arguments.
-int emu_build_small(const RfwRTTriangle* tris, int n, int treelet, float c_prim, int pmax, int threads, float4* nodes, uint32_t* leaf_prims, float4* ttris,
+int emu_build_small(const RfwRTTriangle* tris, int n, int treelet, float c_prim, int pmax, int threads /* 256, 512, or -256: 256 threads with CtaCoopScope */, float4* nodes, uint32_t* leaf_prims, float4* ttris,
                     uint32_t* out_counters, uint32_t* out_bounds, float* out_cost) {
-    if (n <= 0 || n > BUILD_FUSED_MAX || (threads != 256 && threads != 512)) return -2;
+    if (n <= 0 || n > BUILD_FUSED_MAX || (threads != 256 && threads != 512 && threads != -256)) return -2;
     const BuildParams P{1.0f, c_prim, pmax, treelet};
     SmallBuildJob job;
     memset(&job, 0, sizeof(job));
@@ -35,6 +54,7 @@ int emu_build_small(const RfwRTTriangle* tris, int n, int treelet, float c_prim,
     g_abort.store(false);
     bool ok;
     if (threads == 256) ok = simt_launch(1, 256, [&]() { k_build_small<256>(&job, P); });
+    else if (threads == -256) ok = simt_launch(1, 256, [&]() { k_build_small<256, CtaCoopScope>(&job, P); });
     else ok = simt_launch(1, 512, [&]() { k_build_small<512>(&job, P); });
     if (!ok) return -1;
     memcpy(out_counters, res.counters, sizeof(res.counters));

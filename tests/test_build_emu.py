@@ -118,3 +118,45 @@ def test_fused_build_kernel_on_degenerate_distributions(bemu, oracle_mod, dist, 
     rays = aimed_rays(tris, rng, len(tris), count=800)
     ref = o.trace_closest(rays, mode=oracle_mod.MODE_BRUTE)
     parity.compare_hits(rays, b.trace(rays), ref, parity.lookup_from_desc(desc), f"fused {dist}/{n}", max_fraction=2e-2, oracle_artefacts=True)
+
+
+@pytest.mark.parametrize("n,threads,bits", [(0, 256, (0, 64)), (1, 256, (0, 64)), (31, 256, (0, 64)), (2048, 256, (0, 64)), (2049, 256, (0, 64)), (5000, 256, (0, 64)),
+                                            (8192, 256, (0, 24)), (3000, 512, (0, 64)), (4097, 512, (0, 64)), (8192, 512, (8, 40)), (700, 256, (0, 8))])
+def test_in_cta_radix_sort_on_the_simt_machine(bemu, n, threads, bits):
+    """sort_small.cuh::sort_tiles_body alone: one tile (keys stay in registers) and several tiles (two sweeps per pass, a base per digit and tile), 8 and 16 warps,
+    full and partial bit ranges (odd pass counts end in the tmp buffers), many duplicate keys — against numpy's stable sort on the same bit range."""
+    bemu.emu_sort_pairs.restype = C.c_int
+    bemu.emu_sort_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    rng = np.random.default_rng(n + threads)
+    keys = rng.integers(0, 1 << 63, max(n, 1), dtype=np.uint64)[:n].copy()
+    if n > 10:
+        keys[rng.integers(0, n, n // 3)] = keys[0]                     # a third of the keys equal
+        keys[rng.integers(0, n, n // 5)] &= np.uint64(0xFFFF)          # and a cluster in the low digits
+    vals = np.arange(n, dtype=np.uint32)
+    k, v = keys.copy(), vals.copy()
+    assert bemu.emu_sort_pairs(k.ctypes.data, v.ctypes.data, n, threads, bits[0], bits[1]) == 0
+    mask = np.uint64(((1 << (bits[1] - bits[0])) - 1) << bits[0]) if bits[1] - bits[0] < 64 else np.uint64(0xFFFFFFFFFFFFFFFF)
+    order = np.argsort(keys & mask, kind="stable")
+    assert np.array_equal(v, vals[order]) and np.array_equal(k, keys[order])
+
+
+@pytest.mark.parametrize("n", [300, 1500, 2600])
+def test_cta_cooperative_sah_split_builds_the_same_tree(bemu, n):
+    """builder: middle-sized segments of the SAH top build are split by ALL warps of a CTA in the cooperative k_sah_top (sah_split_segment_cta) — claimed to give
+    the tree the one-warp split gives.  The fused kernel instantiated with a scope that sends every segment of more than 32 treelets through that function, against
+    the shipped instantiation (one warp per segment): same SAH cost to the bit, same multiset of node records."""
+    desc = scenes.soup_scene(n, 0.08, seed=scenes.SEED_SCENE + 7 * n)
+    a = Built(bemu, desc.meshes[0], treelet=4, threads=256)
+    b = Built(bemu, desc.meshes[0], treelet=4, threads=-256)
+    assert a.rc == 0 and b.rc == 0
+    assert int(a.counters[4]) > 64                      # enough treelets for several cooperative levels
+    assert a.counters.tolist()[:2] == b.counters.tolist()[:2] and int(a.counters[4]) == int(b.counters[4])
+    assert np.array_equal(a.cost.view(np.uint32), b.cost.view(np.uint32))
+    k = int(a.counters[0])
+
+    def records(x):
+        w = x.nodes.reshape(-1, 24)[:k].view(np.uint32).copy()
+        w[:, 4] = 0; w[:, 5] = 0
+        return sorted(bytes(r) for r in w)
+
+    assert records(a) == records(b)
