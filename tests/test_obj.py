@@ -66,6 +66,14 @@ def test_mtl_rules_follow_the_loader():
         names, mats, _ = obj.parse_mtl(open(ref).read())
         assert names[:4] == ["Light", "DarkGreen", "Khaki", "BloodyRed"]
         assert np.allclose(mats["color"][0, :3], 10.0) and np.allclose(mats["color"][1, :3], [0.0, 0.32, 0.0])
+        # the two big libraries of the snapshot: every material parses, the texture maps the loader reads are picked up by name
+        # (sponza: 24 diffuse + 22 normal maps through map_Ns — obj.rs:113 reads "map_ns" as the normal map; sibenik: 8 diffuse, 5 bump)
+        for rel, n_mats, n_kd, n_norm in (("sponza/sponza.mtl", 25, 24, 22), ("sibenik/sibenik.mtl", 15, 8, 5)):
+            names, mats, tex = obj.parse_mtl(open(os.path.join("/root/reference/assets/models", rel), errors="replace").read())
+            assert len(names) == n_mats == len(mats) and len(set(names)) == n_mats
+            assert sum(1 for t in tex.values() if "map_kd" in t) == n_kd
+            assert sum(1 for t in tex.values() if ("map_ns" in t or "map_bump" in t or "bump" in t or "norm" in t)) == n_norm
+            assert np.isfinite(mats["color"]).all() and not (mats["color"][:, :3].max(axis=1) > 1.0).any()   # no emissive material in either
 
 
 def test_obj_scene_casts_on_the_oracle(oracle_mod):
