@@ -459,9 +459,16 @@ cudaError_t build_small_batch(BuilderContext& ctx, const SmallBuildItem* items, 
         BuildResultSlot* d_results = nullptr;
         static const bool trace_on = getenv("RFWB200_BUILD_TRACE") != nullptr;
         unsigned long long* d_trace = nullptr;
-        if (trace_on) { RFW_CK(cudaMallocAsync(&d_trace, (size_t)chunk * 16 * sizeof(unsigned long long), s)); RFW_CK(cudaMemsetAsync(d_trace, 0, (size_t)chunk * 16 * sizeof(unsigned long long), s)); }
+        // the job table, the result records and the trace go back to the pool when the chunk is done — or abandoned: an error return frees them too
+        struct StreamFree { void* p; cudaStream_t s; ~StreamFree() { if (p) cudaFreeAsync(p, s); } };
+        StreamFree free_jobs{nullptr, s}, free_results{nullptr, s}, free_trace{nullptr, s};
+        // (a failed chunk must not leave its result slots queued: finish_pending_builds would read records no kernel wrote)
+        const cudaError_t chunk_status = [&]() -> cudaError_t {
+        if (trace_on) { RFW_CK(cudaMallocAsync(&d_trace, (size_t)chunk * 16 * sizeof(unsigned long long), s)); free_trace.p = d_trace; RFW_CK(cudaMemsetAsync(d_trace, 0, (size_t)chunk * 16 * sizeof(unsigned long long), s)); }
         RFW_CK(cudaMallocAsync(&d_jobs, (size_t)chunk * sizeof(SmallBuildJob), s));
+        free_jobs.p = d_jobs;
         RFW_CK(cudaMallocAsync(&d_results, (size_t)chunk * sizeof(BuildResultSlot), s));
+        free_results.p = d_results;
         for (int k = 0; k < chunk; k++) {
             const SmallBuildItem& it = items[order[(size_t)k]];
             SmallBuildJob& j = jobs[(size_t)k];
@@ -507,9 +514,10 @@ cudaError_t build_small_batch(BuilderContext& ctx, const SmallBuildItem* items, 
             fprintf(stderr, "rfwb200 build trace: %d jobs, largest n = %d:", chunk, jobs[(size_t)big].n);
             for (int p = 0; p < 10; p++) fprintf(stderr, " %s %.1f us;", names[p], (double)(tr[(size_t)big * 16 + p + 1] - tr[(size_t)big * 16 + p]) * 1e-3);
             fprintf(stderr, " total %.1f us\n", (double)(tr[(size_t)big * 16 + 10] - tr[(size_t)big * 16]) * 1e-3);
-            cudaFreeAsync(d_trace, s);
         }
-        cudaFreeAsync(d_jobs, s); cudaFreeAsync(d_results, s);
+        return cudaSuccess;
+        }();
+        if (chunk_status != cudaSuccess) { ctx.pending.resize((size_t)slot0); return chunk_status; }
         first += chunk;
         if (first < count) RFW_CK(finish_pending_builds(ctx));  // the next chunk re-uses the scratch arena and the slots
     }
